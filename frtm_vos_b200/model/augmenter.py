@@ -1,0 +1,253 @@
+"""First-frame augmentation (host logic).
+
+Produces the K=5 training images/masks the target model is initialised on: the original frame plus
+four synthetic views in which the object is cut out, the hole is Telea-inpainted, and background and
+object are warped independently (rotation / scale / skew / flip / directional blur) and re-composited.
+Behaviour follows the reference's ``ImageAugmenter`` (``model/augmenter.py:95-555``) including its
+draw order from ``numpy.random`` so that, with the same seed, the same views come out:
+
+* the spec generator always draws ``AugmentationParams2.num_aug - 1 = 19`` specs per round
+  (``augmenter.py:44,199``), renders all of them, keeps the valid ones and, if more than ``num_aug-1``
+  survive, shuffles and crops (``:516-545``);
+* parameter lists are tiled, shuffled in attribute order and sliced (``:204-211``);
+* transforms compose ``T(loc)·skew·rot·scale·T(-centre)`` (``:262-265``).
+
+Inpainting stays on the host with OpenCV, exactly like the reference (``:297-340``); warps run with
+OpenCV on host tensors (the reference's CPU path, ``lib/image.py:46-50``).  This is outside the §8
+kernel scope; a device-side warp/blur/paste is the "next" row f1.
+"""
+from __future__ import annotations
+
+import copy
+from typing import List, Optional, Sequence, Tuple
+
+import cv2
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+_SPEC_FIELDS = ("location", "rotation", "fliplr", "scale", "skew", "blur_size", "blur_angle")
+_SPEC_DEFAULT_POOL = dict(
+    num_aug=20,
+    location=[(0.5, 0.5)],
+    rotation=[5, -5, 10, -10, 20, -20, 30, -30, 45, -45, 60, -60],
+    fliplr=[False, False, True],
+    scale=[0.7, 1.0, 1.5, 2.0, "0.25", "0.5", "1.0"],
+    skew=[(0.0, 0.0), (0.0, 0.0), (0.1, 0.1)],
+    blur_size=[0.0, 0.0, 0.0, 2.0, 5.0],
+    blur_angle=[0, 45, 90, 135],
+)
+_SPEC_DEFAULT = dict(location=None, rotation=0.0, fliplr=False, scale=1.0, skew=(0, 0), blur_size=0, blur_angle=0,
+                     min_size=10)
+
+
+def _mat_translate(dx, dy):
+    return np.array([[1, 0, dx], [0, 1, dy], [0, 0, 1]])
+
+
+def _mat_scale(sx, sy):
+    return np.array([[sx, 0, 0], [0, sy, 0], [0, 0, 1]])
+
+
+def _mat_rotate(a):
+    c, s = np.cos(a), np.sin(a)
+    return np.array([[c, s, 0], [-s, c, 0], [0, 0, 1]])
+
+
+def _mat_skew(kx, ky):
+    return np.array([[1, kx, 0], [ky, 1, 0], [0, 0, 1]])
+
+
+def directional_blur_kernel(sx: float, sy: float, rot2: np.ndarray) -> np.ndarray:
+    """Rotated anisotropic Gaussian (augmenter.py:120-138)."""
+    cov = rot2 @ np.diag((sx, sy)) @ rot2.T
+    half = int(np.max((sx, sy)) / 2 + 0.5)
+    half = half + (half + 1) % 2
+    r = np.arange(-half, half + 1)
+    grid = np.stack(np.meshgrid(r, r))
+    quad = (grid * np.tensordot(np.linalg.inv(cov), grid, axes=[1, 0])).sum(0)
+    g = np.exp(-0.5 * quad)
+    return (g / g.sum() * 1.0).astype(np.float32)
+
+
+def draw_specs(pool: dict) -> List[dict]:
+    """Tile/shuffle/slice every parameter list, then zip into per-view specs (augmenter.py:194-222)."""
+    merged = dict(_SPEC_DEFAULT_POOL)
+    for k, v in pool.items():
+        merged[k] = v            # existing keys keep their position, new keys append (vars() order)
+    n = merged["num_aug"] - 1
+    cols = {}
+    for key, vals in merged.items():
+        if key == "num_aug":
+            continue
+        vals = list(vals) * ((n + len(vals) - 1) // len(vals))
+        np.random.shuffle(vals)
+        cols[key] = vals[:n]
+    specs = []
+    for i in range(n):
+        s = dict(_SPEC_DEFAULT)
+        s.update({k: cols[k][i] for k in cols})
+        assert s["location"] is not None
+        specs.append(s)
+    return specs
+
+
+def spec_transform(spec: dict, bbox, im_size, limit_scale: bool = True) -> Tuple[np.ndarray, np.ndarray]:
+    """Affine 3x3 + blur kernel of one spec (augmenter.py:224-276)."""
+    cx, cy, bw, bh = bbox
+    assert bw > 0 and bh > 0
+    ih, iw = im_size
+    s = spec["scale"]
+    if isinstance(s, str):
+        s = float(s) * ih / bh
+    if limit_scale:
+        if s * bw > iw or s * bh > ih:
+            s = min(iw / bw, ih / bh)
+        if s * bw < spec["min_size"] or s * bh < spec["min_size"]:
+            s = max(spec["min_size"] / bw, spec["min_size"] / bh)
+    mirror = -1 if spec["fliplr"] else 1
+    d2r = np.pi / 180
+    loc = spec["location"]
+    T = _mat_translate(loc[0] * iw, loc[1] * ih) @ _mat_skew(*spec["skew"]) @ _mat_rotate(spec["rotation"] * d2r) @ \
+        _mat_scale(mirror * s, s) @ _mat_translate(-cx, -cy)
+    if spec["blur_size"] > 0:
+        G = directional_blur_kernel(spec["blur_size"], 0.1, _mat_rotate(spec["blur_angle"] * d2r)[:2, :2])
+    else:
+        G = np.array([[1.0]], dtype=np.float32)
+    return T, G
+
+
+def warp_affine_host(src: torch.Tensor, H: np.ndarray, size, mode: str = "bicubic") -> torch.Tensor:
+    """Per-channel cv2.warpAffine (lib/image.py:38-59, CPU branch)."""
+    flat = src.reshape(-1, *src.shape[-2:])
+    dst = flat.new_zeros(flat.shape[0], *size)
+    H2 = H.astype(np.float32)[:2, :]
+    flag = dict(nearest=cv2.INTER_NEAREST, bilinear=cv2.INTER_LINEAR, bicubic=cv2.INTER_CUBIC)[mode]
+    for c in range(flat.shape[0]):
+        cv2.warpAffine(flat[c].numpy(), H2, (size[1], size[0]), dst[c].numpy(), flag)
+    return dst[0] if src.dim() == 2 else dst
+
+
+def _blur_channels(img: torch.Tensor, kernel: np.ndarray) -> torch.Tensor:
+    kernel = np.array(kernel, dtype=np.float32)
+    if kernel.shape == (1, 1):
+        return img
+    fh, fw = kernel.shape
+    k = torch.as_tensor(kernel).float().view(1, 1, fh, fw)
+    return F.conv2d(img.unsqueeze(1), k, padding=(fh // 2, fw // 2)).squeeze(1)
+
+
+def cut_and_inpaint(im: torch.Tensor, mask: torch.Tensor, d: int = 1, f: int = 1):
+    """Object cut-out (RGBA, feathered alpha) + Telea-inpainted background (augmenter.py:297-340)."""
+    image = im.detach().cpu().numpy().transpose((1, 2, 0))
+    m = (mask.squeeze() > 0).byte().detach().cpu().numpy()[..., None]
+    cut = m * image
+    se = cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (f, f))
+    alpha = cv2.blur(cv2.erode(m, se) * 255, (f, f))[..., None]
+    cut = np.concatenate((cut, alpha), axis=-1)
+    inner = cv2.erode(m, cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (d, d)))
+    outer = cv2.dilate(m, cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (d * 2, d * 2)))
+    image = cv2.inpaint(image, outer, inpaintRadius=d, flags=cv2.INPAINT_TELEA)
+    ring = cv2.blur((1 - inner) * outer * 255, ksize=(d, d))[..., None] / 255
+    soft = cv2.blur(image, ksize=(d, d))
+    image = (soft * ring + (1 - ring) * image).astype(np.uint8)
+    cut_t = torch.from_numpy(np.ascontiguousarray(cut.transpose((2, 0, 1))))
+    bg_t = torch.from_numpy(np.ascontiguousarray(image.transpose((2, 0, 1))))
+    return cut_t, bg_t
+
+
+def mask_center_bbox(mask: torch.Tensor):
+    """(cx, cy, w, h) of the nonzero region (augmenter.py:432-452)."""
+    m = mask.squeeze()
+    ys = m.sum(dim=-1).nonzero(as_tuple=False).view(-1).cpu().numpy()
+    xs = m.sum(dim=-2).nonzero(as_tuple=False).view(-1).cpu().numpy()
+    if len(ys) > 0 and len(xs) > 0:
+        x, y = xs[0], ys[0]
+        w, h = xs[-1] - xs[0] + 1, ys[-1] - ys[0] + 1
+    else:
+        x, y, w, h = 0, 0, 0, 0
+    return x + w / 2, y + h / 2, w, h
+
+
+def target_locations(n: int, im_size) -> List[Tuple[float, float]]:
+    """Jittered grid of new object centres, shuffled (augmenter.py:169-192)."""
+    h, w = im_size
+    aspect = w / h
+    nrows = int(np.ceil(np.sqrt(n / aspect)))
+    ncols = int(np.ceil(aspect * nrows))
+    pts = []
+    for r in range(nrows):
+        for c in range(ncols):
+            x = (c + 0.5) / ncols + np.random.normal(0, 0.5 / ncols / 4)
+            y = (r + 0.5) / nrows + np.random.normal(0, 0.5 / nrows / 4)
+            pts.append((np.round(x, 3), np.round(y, 3)))
+    np.random.shuffle(pts)
+    return pts[:n]
+
+
+class ImageAugmenter:
+    """Drop-in for the reference class of the same name: ``augment_first_frame(im, mask)``."""
+
+    def __init__(self, parameters: dict):
+        self.params = parameters
+        self.max_retries = 100
+
+    def _render(self, bg, cut, mask, fg_spec, bbox, bg_spec):
+        size = tuple(bg.shape[-2:])
+        if bg_spec is not None:
+            h, w = size
+            T, G = spec_transform(bg_spec, (w / 2, h / 2, w, h), size, limit_scale=False)
+            canvas = warp_affine_host(bg.float(), np.array(T, dtype=np.float32), size).clamp(0, 255)
+            canvas = _blur_channels(canvas, G)
+        else:
+            canvas = bg
+        T, G = spec_transform(fg_spec, bbox, size)
+        T = np.array(T, dtype=np.float32)
+        canvas = canvas.float()
+        obj = warp_affine_host(cut.float(), T, size).clamp(0, 255)
+        wmask = warp_affine_host(mask, T, size, "nearest")
+        obj = _blur_channels(obj, G)
+        a = obj[3].unsqueeze(0) / 255
+        out = (obj[:3] * a + canvas * (1 - a)).byte()
+        return out, wmask
+
+    def augment_first_frame(self, im: torch.Tensor, lb: torch.Tensor):
+        """(3,H,W) u8 + (1,H,W) u8 mask -> ((K,3,H,W) u8, (K,1,H,W) u8) on ``im.device`` (augmenter.py:473-555)."""
+        p = self.params
+        dev = im.device
+        im_h, lb_h = im.detach().cpu(), lb.detach().cpu()
+        size = tuple(im_h.shape[-2:])
+        count = int(lb_h.sum())
+        no_bg = count == lb_h.numel()
+        if count < p["min_px_count"]:
+            raise ValueError("Augmentation failed: Target object is too small.")
+        bbox = mask_center_bbox(lb_h)
+        if tuple(bbox[-2:]) == (0, 0):
+            raise ValueError("Augmentation failed: No object to augment.")
+        cut, bg = cut_and_inpaint(im_h, lb_h, d=1, f=1)
+
+        fg_pool = copy.deepcopy(dict(p["fg_aug_params"]))
+        fg_pool["location"] = target_locations(p["num_aug"], size)
+        bg_pool = copy.deepcopy(dict(p["bg_aug_params"])) if "bg_aug_params" in p else None
+        want = p["num_aug"] - 1
+        lo, hi = p["min_px_count"], lb_h.shape[-1] * lb_h.shape[-2] - p["min_px_count"]
+
+        views, masks = [], []
+        while len(views) < want:
+            fg_specs = draw_specs(fg_pool)
+            bg_specs = draw_specs(bg_pool) if bg_pool is not None else [None] * len(fg_specs)
+            for fs, bs in zip(fg_specs, bg_specs):
+                v, m = self._render(bg, cut, lb_h, fs, bbox, bs)
+                px = int((m == 1).sum())
+                if px >= lo and (px < hi or no_bg):
+                    views.append(v)
+                    masks.append(m)
+        if len(views) > want:
+            order = list(range(len(views)))
+            np.random.shuffle(order)
+            order = order[:want]
+            views = [views[i] for i in order]
+            masks = [masks[i] for i in order]
+        views.insert(0, im_h)
+        masks.insert(0, lb_h)
+        return torch.stack(views).to(dev), torch.stack(masks).to(dev)
