@@ -1,0 +1,443 @@
+// Bandwidth-bound glue kernels of the backbone / refinement network / mask merge (NHWC fp32).
+#include "common.cuh"
+
+namespace frtm {
+
+// ---------------------------------------------------------------- normalise ------------------------------------
+__global__ void normalize_kernel(const uint8_t *__restrict__ img, int64_t HW, int64_t total, float4 *__restrict__ out,
+                                 float s0, float s1, float s2, float b0, float b1, float b2) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int64_t b = i / HW, p = i - b * HW;
+  const uint8_t *src = img + b * 3 * HW + p;
+  float4 v;
+  // mul then add, separately rounded, exactly like  norm_weight * input.float() + norm_bias
+  v.x = __fadd_rn(__fmul_rn(s0, (float)src[0]), b0);
+  v.y = __fadd_rn(__fmul_rn(s1, (float)src[HW]), b1);
+  v.z = __fadd_rn(__fmul_rn(s2, (float)src[2 * HW]), b2);
+  v.w = 0.f;
+  out[i] = v;
+}
+
+// ---------------------------------------------------------------- max pool -------------------------------------
+__global__ void maxpool_kernel(const float *__restrict__ x, int B, int H, int W, int C, int Ho, int Wo,
+                               float *__restrict__ y, float *__restrict__ y_nchw) {
+  const int C4 = C / 4;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)B * Ho * Wo * C4;
+  if (i >= total) return;
+  const int c4 = (int)(i % C4);
+  int64_t r = i / C4;
+  const int ox = (int)(r % Wo);
+  r /= Wo;
+  const int oy = (int)(r % Ho);
+  const int b = (int)(r / Ho);
+  float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  for (int dy = 0; dy < 3; ++dy) {
+    const int iy = oy * 2 - 1 + dy;
+    if (iy < 0 || iy >= H) continue;
+    for (int dx = 0; dx < 3; ++dx) {
+      const int ix = ox * 2 - 1 + dx;
+      if (ix < 0 || ix >= W) continue;
+      const float4 v = *reinterpret_cast<const float4 *>(x + (((int64_t)b * H + iy) * W + ix) * C + c4 * 4);
+      m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+    }
+  }
+  *reinterpret_cast<float4 *>(y + (((int64_t)b * Ho + oy) * Wo + ox) * C + c4 * 4) = m;
+  if (y_nchw) {
+    const int64_t hw = (int64_t)Ho * Wo, pix = (int64_t)oy * Wo + ox;
+    float *d = y_nchw + ((int64_t)b * C + c4 * 4) * hw + pix;
+    d[0] = m.x; d[hw] = m.y; d[2 * hw] = m.z; d[3 * hw] = m.w;
+  }
+}
+
+// ---------------------------------------------------------------- bilinear -------------------------------------
+template <int VEC>
+__global__ void resize_bilinear_kernel(const float *__restrict__ x, int B, int H, int W, int C, int ldx,
+                                       float *__restrict__ y, int Ho, int Wo, int ldy, int coff, int accumulate,
+                                       float sh, float sw) {
+  const int CV = C / VEC;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)B * Ho * Wo * CV;
+  if (i >= total) return;
+  const int cv = (int)(i % CV);
+  int64_t r = i / CV;
+  const int ox = (int)(r % Wo);
+  r /= Wo;
+  const int oy = (int)(r % Ho);
+  const int b = (int)(r / Ho);
+  int y0, y1, x0, x1;
+  float ly, lx;
+  bilinear_src(oy, sh, H, y0, y1, ly);
+  bilinear_src(ox, sw, W, x0, x1, lx);
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  const float *p00 = x + (((int64_t)b * H + y0) * W + x0) * ldx + cv * VEC;
+  const float *p01 = x + (((int64_t)b * H + y0) * W + x1) * ldx + cv * VEC;
+  const float *p10 = x + (((int64_t)b * H + y1) * W + x0) * ldx + cv * VEC;
+  const float *p11 = x + (((int64_t)b * H + y1) * W + x1) * ldx + cv * VEC;
+  float *d = y + (((int64_t)b * Ho + oy) * Wo + ox) * ldy + coff + cv * VEC;
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    float v = hy * (hx * p00[k] + lx * p01[k]) + ly * (hx * p10[k] + lx * p11[k]);
+    d[k] = accumulate ? d[k] + v : v;
+  }
+}
+
+// ---------------------------------------------------------------- bicubic x2 -----------------------------------
+__constant__ float kCubicE[4] = {-0.10546875f, 0.87890625f, 0.26171875f, -0.03515625f};
+
+__global__ void pyrup_bicubic_kernel(const float *__restrict__ x, int B, int H, int W, int C, float *__restrict__ y) {
+  const int C4 = C / 4, Ho = 2 * H, Wo = 2 * W;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)B * Ho * Wo * C4;
+  if (i >= total) return;
+  const int c4 = (int)(i % C4);
+  int64_t r = i / C4;
+  const int ox = (int)(r % Wo);
+  r /= Wo;
+  const int oy = (int)(r % Ho);
+  const int b = (int)(r / Ho);
+  const int yf = oy + 1, xf = ox + 1;          // position before the 1-px crop
+  const int iy = yf >> 1, ix = xf >> 1;        // phase-image index
+  const bool oddy = yf & 1, oddx = xf & 1;     // odd phase uses the reversed taps
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int ky = 0; ky < 4; ++ky) {
+    const float wy = oddy ? kCubicE[3 - ky] : kCubicE[ky];
+    const int sy = min(max(iy + ky - 2, 0), H - 1);  // replicate pad 2
+    float4 row = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int kx = 0; kx < 4; ++kx) {
+      const float wx = oddx ? kCubicE[3 - kx] : kCubicE[kx];
+      const int sx = min(max(ix + kx - 2, 0), W - 1);
+      const float4 v = *reinterpret_cast<const float4 *>(x + (((int64_t)b * H + sy) * W + sx) * C + c4 * 4);
+      const float wt = wy * wx;  // the reference builds the non-separable 4x4 filter as an outer product
+      row.x = fmaf(wt, v.x, row.x); row.y = fmaf(wt, v.y, row.y); row.z = fmaf(wt, v.z, row.z); row.w = fmaf(wt, v.w, row.w);
+    }
+    acc.x += row.x; acc.y += row.y; acc.z += row.z; acc.w += row.w;
+  }
+  *reinterpret_cast<float4 *>(y + (((int64_t)b * Ho + oy) * Wo + ox) * C + c4 * 4) = acc;
+}
+
+// ---------------------------------------------------------------- global average pool ---------------------------
+constexpr int GAP_CHUNK = 256;  // pixels per stage-1 block
+
+__global__ void gap_stage1_kernel(const float *__restrict__ x, int HW, int C, int ldx, int nchunks, float *__restrict__ part) {
+  const int b = blockIdx.y, ch = blockIdx.x;
+  const int p0 = ch * GAP_CHUNK, p1 = min(p0 + GAP_CHUNK, HW);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int p = p0; p < p1; ++p) s += x[((int64_t)b * HW + p) * ldx + c];
+    part[((int64_t)b * nchunks + ch) * C + c] = s;
+  }
+}
+__global__ void gap_stage2_kernel(const float *__restrict__ part, int HW, int C, int nchunks, float *__restrict__ out) {
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < nchunks; ++k) s += part[((int64_t)b * nchunks + k) * C + c];
+    out[(int64_t)b * C + c] = s / (float)HW;
+  }
+}
+
+// ---------------------------------------------------------------- CAB -------------------------------------------
+__global__ void cab_gate_kernel(const float *__restrict__ sp, const float *__restrict__ dp, const float *__restrict__ w1,
+                                const float *__restrict__ b1, const float *__restrict__ w2, const float *__restrict__ b2,
+                                int C, float *__restrict__ gate) {
+  extern __shared__ float sm[];  // pooled[2C] + hidden[C]
+  float *pooled = sm, *hid = sm + 2 * C;
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    pooled[i] = sp[(int64_t)b * C + i];
+    pooled[C + i] = dp[(int64_t)b * C + i];
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < C; o += blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < 2 * C; ++k) s = fmaf(w1[(int64_t)o * 2 * C + k], pooled[k], s);
+    hid[o] = fmaxf(s + b1[o], 0.f);
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < C; o += blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < C; ++k) s = fmaf(w2[(int64_t)o * C + k], hid[k], s);
+    s += b2[o];
+    gate[(int64_t)b * C + o] = 1.f / (1.f + expf(-s));
+  }
+}
+
+__global__ void cab_apply_kernel(const float4 *__restrict__ sh, const float *__restrict__ gate,
+                                 const float *__restrict__ deeper, int vec, int HW, int C, int64_t total4,
+                                 float4 *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int C4 = C / 4;
+  const int c = (int)(i % C4) * 4;
+  const int64_t b = i / ((int64_t)HW * C4);
+  const float4 g = *reinterpret_cast<const float4 *>(gate + b * C + c);
+  const float4 d = vec ? *reinterpret_cast<const float4 *>(deeper + b * C + c)
+                       : reinterpret_cast<const float4 *>(deeper)[i];
+  const float4 s = sh[i];
+  // shallower * sigmoid(...) then + deeper: two roundings like the reference (seg_network.py:38-39)
+  float4 o;
+  o.x = __fadd_rn(__fmul_rn(s.x, g.x), d.x);
+  o.y = __fadd_rn(__fmul_rn(s.y, g.y), d.y);
+  o.z = __fadd_rn(__fmul_rn(s.z, g.z), d.z);
+  o.w = __fadd_rn(__fmul_rn(s.w, g.w), d.w);
+  out[i] = o;
+}
+
+// ---------------------------------------------------------------- layout helpers --------------------------------
+__global__ void scatter_channel_kernel(const float *__restrict__ src, int64_t total, float *__restrict__ dst, int ld,
+                                       int coff, int nzero) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  float *d = dst + i * ld + coff;
+  d[0] = src[i];
+  for (int k = 1; k <= nzero; ++k) d[k] = 0.f;
+}
+
+__global__ void broadcast_objects_kernel(const float *__restrict__ src, int N, int HW, int C, int lds,
+                                         float *__restrict__ dst, int ldd, int64_t total4) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int C4 = C / 4;
+  const int c = (int)(i % C4) * 4;
+  int64_t r = i / C4;
+  const int p = (int)(r % HW);
+  const int64_t bo = r / HW;     // f*N + n
+  const int64_t f = bo / N;
+  const float4 v = *reinterpret_cast<const float4 *>(src + (f * HW + p) * lds + c);
+  *reinterpret_cast<float4 *>(dst + (bo * HW + p) * ldd + c) = v;
+}
+
+// NHWC -> NCHW through a 32x32 shared tile (coalesced on both sides)
+__global__ void nhwc_to_nchw_kernel(const float *__restrict__ x, int HW, int C, int ldx, float *__restrict__ y) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int p = p0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (p < HW && c < C) ? x[((int64_t)b * HW + p) * ldx + c] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, p = p0 + threadIdx.x;
+    if (p < HW && c < C) y[((int64_t)b * C + c) * HW + p] = tile[threadIdx.x][j];
+  }
+}
+
+// ---------------------------------------------------------------- merge -----------------------------------------
+// One thread per pixel.  Mirrors model/tracker.py:203-221 (sigmoid of live objects, suppression under new objects'
+// start masks, clamp, background = min(1-p), softmax over p/(1-p), first-occurrence argmax gate) followed by the
+// label rule of :143-150 applied to the merged masks.  `src` holds logits for objects whose bit is set in
+// logit_mask and probabilities (start masks) for the others.  masks[] doubles as per-pixel scratch.
+__device__ __forceinline__ int softmax_argmax(const float *__restrict__ m, int N, int HW, int p, float z0, float &den_out,
+                                              float &mx_out) {
+  float mx = z0;
+  for (int n = 0; n < N; ++n) {
+    const float c = m[(int64_t)(n + 1) * HW + p];
+    mx = fmaxf(mx, c / (1.f - c));
+  }
+  float den = expf(z0 - mx);
+  for (int n = 0; n < N; ++n) {
+    const float c = m[(int64_t)(n + 1) * HW + p];
+    den += expf(c / (1.f - c) - mx);
+  }
+  float best = expf(z0 - mx) / den;
+  int arg = 0;
+  for (int n = 0; n < N; ++n) {
+    const float c = m[(int64_t)(n + 1) * HW + p];
+    const float s = expf(c / (1.f - c) - mx) / den;
+    if (s > best) { best = s; arg = n + 1; }
+  }
+  den_out = den;
+  mx_out = mx;
+  return arg;
+}
+
+__global__ void merge_masks_kernel(const float *__restrict__ src, unsigned long long logit_mask,
+                                   const uint8_t *__restrict__ suppress, int N, int HW, const uint8_t *__restrict__ lut,
+                                   int single, float *__restrict__ masks, uint8_t *__restrict__ labels,
+                                   int *__restrict__ counts) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const float lo = 1e-7f, hi = 1.f - 1e-7f;
+  if (p < HW) {
+    float bg = INFINITY;
+    const float keep = suppress ? (float)(1 - (int)suppress[p]) : 1.f;
+    for (int n = 0; n < N; ++n) {
+      float pr = src[(int64_t)n * HW + p];
+      if ((logit_mask >> n) & 1ull) pr = (1.f / (1.f + expf(-pr))) * keep;
+      pr = fminf(fmaxf(pr, lo), hi);
+      masks[(int64_t)(n + 1) * HW + p] = pr;
+      bg = fminf(bg, 1.f - pr);
+    }
+    float den, mx;
+    const float z0 = bg / (1.f - bg);
+    const int arg = softmax_argmax(masks, N, HW, p, z0, den, mx);
+    masks[p] = (arg == 0) ? expf(z0 - mx) / den : 0.f;
+    float bg2 = INFINITY;
+    for (int n = 0; n < N; ++n) {
+      const float c = masks[(int64_t)(n + 1) * HW + p];
+      const float s = (arg == n + 1) ? expf(c / (1.f - c) - mx) / den : 0.f;
+      masks[(int64_t)(n + 1) * HW + p] = s;
+      bg2 = fminf(bg2, 1.f - fminf(fmaxf(s, lo), hi));
+    }
+    int lab;
+    if (single) {
+      lab = masks[(int64_t)HW + p] > 0.5f ? 1 : 0;
+    } else {
+      // second clamp / softmax / argmax on the merged masks.  Only the winner is non-zero, so evaluate the rule
+      // on clamped values without disturbing the stored masks.
+      float mx2 = bg2 / (1.f - bg2);
+      for (int n = 0; n < N; ++n) {
+        const float c = fminf(fmaxf(masks[(int64_t)(n + 1) * HW + p], lo), hi);
+        mx2 = fmaxf(mx2, c / (1.f - c));
+      }
+      float den2 = expf(bg2 / (1.f - bg2) - mx2);
+      for (int n = 0; n < N; ++n) {
+        const float c = fminf(fmaxf(masks[(int64_t)(n + 1) * HW + p], lo), hi);
+        den2 += expf(c / (1.f - c) - mx2);
+      }
+      float best = expf(bg2 / (1.f - bg2) - mx2) / den2;
+      lab = 0;
+      for (int n = 0; n < N; ++n) {
+        const float c = fminf(fmaxf(masks[(int64_t)(n + 1) * HW + p], lo), hi);
+        const float s = expf(c / (1.f - c) - mx2) / den2;
+        if (s > best) { best = s; lab = n + 1; }
+      }
+    }
+    labels[p] = lut[lab];
+  }
+  // per-object count of pixels > 0.5 (update gate), one atomic per warp per object (integer -> deterministic)
+  for (int n = 0; n < N; ++n) {
+    const bool on = (p < HW) && masks[(int64_t)(n + 1) * HW + p] > 0.5f;
+    const unsigned b = __ballot_sync(0xffffffffu, on);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(&counts[n], __popc(b));
+  }
+}
+
+}  // namespace frtm
+
+using namespace frtm;
+
+extern "C" int frtm_normalize_u8(const uint8_t *img, int B, int H, int W, float *out, void *stream) {
+  FRTM_REQUIRE(img && out && B > 0 && H > 0 && W > 0, "normalize: bad arguments");
+  // constants rounded exactly like the reference: (1/255)/std and (-mean)/std in fp32
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+  float s[3], b[3];
+  for (int i = 0; i < 3; ++i) {
+    s[i] = (float)(1.0 / 255.0) / stdv[i];
+    b[i] = -mean[i] / stdv[i];
+  }
+  const int64_t HW = (int64_t)H * W, total = HW * B;
+  normalize_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(img, HW, total, reinterpret_cast<float4 *>(out),
+                                                                       s[0], s[1], s[2], b[0], b[1], b[2]);
+  FRTM_CHECK_LAUNCH("normalize_u8");
+  return FRTM_OK;
+}
+
+extern "C" int frtm_maxpool3x3s2_nhwc(const float *x, int B, int H, int W, int C, float *y, float *y_nchw, void *stream) {
+  FRTM_REQUIRE(x && y && C % 4 == 0, "maxpool: bad arguments");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const int64_t total = (int64_t)B * Ho * Wo * (C / 4);
+  maxpool_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, C, Ho, Wo, y, y_nchw);
+  FRTM_CHECK_LAUNCH("maxpool3x3s2");
+  return FRTM_OK;
+}
+
+extern "C" int frtm_resize_bilinear_nhwc(const float *x, int B, int H, int W, int C, int ldx, float *y, int Ho, int Wo,
+                                         int ldy, int y_coff, int accumulate, void *stream) {
+  FRTM_REQUIRE(x && y && B > 0 && C > 0, "resize_bilinear: bad arguments");
+  const float sh = (float)H / (float)Ho, sw = (float)W / (float)Wo;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C % 4 == 0) {
+    const int64_t total = (int64_t)B * Ho * Wo * (C / 4);
+    resize_bilinear_kernel<4><<<cdiv(total, 256), 256, 0, st>>>(x, B, H, W, C, ldx, y, Ho, Wo, ldy, y_coff, accumulate, sh, sw);
+  } else {
+    const int64_t total = (int64_t)B * Ho * Wo * C;
+    resize_bilinear_kernel<1><<<cdiv(total, 256), 256, 0, st>>>(x, B, H, W, C, ldx, y, Ho, Wo, ldy, y_coff, accumulate, sh, sw);
+  }
+  FRTM_CHECK_LAUNCH("resize_bilinear");
+  return FRTM_OK;
+}
+
+extern "C" int frtm_pyrup_bicubic_nhwc(const float *x, int B, int H, int W, int C, float *y, void *stream) {
+  FRTM_REQUIRE(x && y && C % 4 == 0, "pyrup_bicubic: bad arguments");
+  const int64_t total = (int64_t)B * 2 * H * 2 * W * (C / 4);
+  pyrup_bicubic_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, C, y);
+  FRTM_CHECK_LAUNCH("pyrup_bicubic");
+  return FRTM_OK;
+}
+
+extern "C" int64_t frtm_global_avgpool_workspace(int B, int HW, int C) {
+  return (int64_t)B * cdiv(HW, GAP_CHUNK) * C * sizeof(float);
+}
+
+extern "C" int frtm_global_avgpool_nhwc(const float *x, int B, int HW, int C, int ldx, float *out, float *workspace,
+                                        int64_t workspace_bytes, void *stream) {
+  FRTM_REQUIRE(x && out && workspace, "global_avgpool: null pointer");
+  FRTM_REQUIRE(workspace_bytes >= frtm_global_avgpool_workspace(B, HW, C), "global_avgpool: workspace too small");
+  const int nchunks = cdiv(HW, GAP_CHUNK);
+  cudaStream_t st = (cudaStream_t)stream;
+  gap_stage1_kernel<<<dim3(nchunks, B), 64, 0, st>>>(x, HW, C, ldx, nchunks, workspace);
+  FRTM_CHECK_LAUNCH("gap_stage1");
+  gap_stage2_kernel<<<B, 64, 0, st>>>(workspace, HW, C, nchunks, out);
+  FRTM_CHECK_LAUNCH("gap_stage2");
+  return FRTM_OK;
+}
+
+extern "C" int frtm_cab_gate(const float *sp, const float *dp, const float *w1, const float *b1, const float *w2,
+                             const float *b2, int B, int C, float *gate, void *stream) {
+  FRTM_REQUIRE(sp && dp && w1 && b1 && w2 && b2 && gate, "cab_gate: null pointer");
+  cab_gate_kernel<<<B, 64, 3 * C * sizeof(float), (cudaStream_t)stream>>>(sp, dp, w1, b1, w2, b2, C, gate);
+  FRTM_CHECK_LAUNCH("cab_gate");
+  return FRTM_OK;
+}
+
+extern "C" int frtm_cab_apply_nhwc(const float *shallow, const float *gate, const float *deeper, int deeper_is_vector,
+                                   int B, int HW, int C, float *out, void *stream) {
+  FRTM_REQUIRE(shallow && gate && deeper && out && C % 4 == 0, "cab_apply: bad arguments");
+  const int64_t total4 = (int64_t)B * HW * (C / 4);
+  cab_apply_kernel<<<cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4 *>(shallow), gate,
+                                                                        deeper, deeper_is_vector, HW, C, total4,
+                                                                        reinterpret_cast<float4 *>(out));
+  FRTM_CHECK_LAUNCH("cab_apply");
+  return FRTM_OK;
+}
+
+extern "C" int frtm_scatter_channel_nhwc(const float *src, int B, int HW, float *dst, int ld, int coff, int nzero,
+                                         void *stream) {
+  FRTM_REQUIRE(src && dst && coff + nzero < ld, "scatter_channel: bad arguments");
+  const int64_t total = (int64_t)B * HW;
+  scatter_channel_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(src, total, dst, ld, coff, nzero);
+  FRTM_CHECK_LAUNCH("scatter_channel");
+  return FRTM_OK;
+}
+
+extern "C" int frtm_broadcast_objects_nhwc(const float *src, int F, int N, int HW, int C, int lds, float *dst, int ldd,
+                                           void *stream) {
+  FRTM_REQUIRE(src && dst && C % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0, "broadcast_objects: bad arguments");
+  const int64_t total4 = (int64_t)F * N * HW * (C / 4);
+  broadcast_objects_kernel<<<cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(src, N, HW, C, lds, dst, ldd, total4);
+  FRTM_CHECK_LAUNCH("broadcast_objects");
+  return FRTM_OK;
+}
+
+extern "C" int frtm_nhwc_to_nchw(const float *x, int B, int HW, int C, int ldx, float *y, void *stream) {
+  FRTM_REQUIRE(x && y, "nhwc_to_nchw: null pointer");
+  dim3 grid(cdiv(HW, 32), cdiv(C, 32), B);
+  nhwc_to_nchw_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, HW, C, ldx, y);
+  FRTM_CHECK_LAUNCH("nhwc_to_nchw");
+  return FRTM_OK;
+}
+
+extern "C" int frtm_merge_masks(const float *src, uint64_t logit_mask, const uint8_t *suppress, int N, int HW,
+                                const uint8_t *lut, int single_object, float *masks, uint8_t *labels, int *counts,
+                                void *stream) {
+  FRTM_REQUIRE(src && lut && masks && labels && counts && N > 0 && N <= 64, "merge_masks: bad arguments");
+  merge_masks_kernel<<<cdiv(HW, 256), 256, 0, (cudaStream_t)stream>>>(src, (unsigned long long)logit_mask, suppress, N,
+                                                                      HW, lut, single_object, masks, labels, counts);
+  FRTM_CHECK_LAUNCH("merge_masks");
+  return FRTM_OK;
+}

@@ -1,0 +1,764 @@
+// Target-model kernels: 3x3 correlation and its adjoints, hinge pixel weights, the stencil form of
+// U^T diag(w^2) U, the frame memory, and the closed-form Gauss-Newton / Polak-Ribiere CG update.
+//
+// Math (model/discriminator.py:38-64, model/optimizer.py:77-157):
+//   residual  r0 = W (U s(theta) - y),  W_i = pw_i sqrt(sw_i),  U = bilinear (h,w)->(H,W), align_corners=False
+//   J^T J v   = Js^T [ sw_i * (U^T pw_i^2 U) ] Js v            -> 9-tap spatially varying stencil S_i on (h,w)
+//   J^T r0    = Js^T [ sw_i * (S_i s_i - U^T pw_i^2 y_i) ]
+// with Js the Jacobian of the low-resolution score map.  S_i and t_i = U^T pw_i^2 y_i are built once per memory
+// sample at insert time, so the full-resolution maps are never touched inside CG.
+#include "common.cuh"
+
+namespace frtm {
+
+// ---------------------------------------------------------------- 3x3 correlation --------------------------------
+// out[n][pix] = sum_c sum_tap x[n][c][pix+tap] f[fi(n)][c][tap]      (+= if accumulate)
+__global__ void __launch_bounds__(128) corr3x3_kernel(const float *__restrict__ x, const float *__restrict__ filt,
+                                                      const int *__restrict__ fidx, int c, int h, int w,
+                                                      float *__restrict__ out, int accumulate,
+                                                      const float *__restrict__ skip_if_zero) {
+  extern __shared__ float fs[];  // [c][9]
+  const int n = blockIdx.y;
+  if (skip_if_zero && skip_if_zero[n] == 0.f) return;
+  const float *f = filt + (int64_t)(fidx ? fidx[n] : 0) * c * 9;
+  for (int i = threadIdx.x; i < c * 9; i += blockDim.x) fs[i] = f[i];
+  __syncthreads();
+  const int hw = h * w;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= hw) return;
+  const int py = pix / w, px = pix - py * w;
+  bool ok[9];
+  int off[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int yy = py + t / 3 - 1, xx = px + t % 3 - 1;
+    ok[t] = yy >= 0 && yy < h && xx >= 0 && xx < w;
+    off[t] = yy * w + xx;
+  }
+  const float *xn = x + (int64_t)n * c * hw;
+  float acc = 0.f;
+  for (int ch = 0; ch < c; ++ch) {
+    const float *xc = xn + (int64_t)ch * hw;
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+      if (ok[t]) acc = fmaf(xc[off[t]], fs[ch * 9 + t], acc);
+  }
+  float *o = out + (int64_t)n * hw + pix;
+  *o = accumulate ? *o + acc : acc;
+}
+
+// v[n][pix] = sw[n] * ( sum_tap S[n][tap][pix] s[n][pix+tap] - use_y * t[n][pix] )
+__global__ void stencil_apply_kernel(const float *__restrict__ S, const float *__restrict__ s, const float *__restrict__ t,
+                                     const float *__restrict__ sw, int h, int w, int use_y, float *__restrict__ v) {
+  const int n = blockIdx.y, hw = h * w;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= hw) return;
+  const float wgt = sw[n];
+  if (wgt == 0.f) { v[(int64_t)n * hw + pix] = 0.f; return; }
+  const int py = pix / w, px = pix - py * w;
+  const float *Sn = S + (int64_t)n * 9 * hw, *sn = s + (int64_t)n * hw;
+  float acc = 0.f;
+#pragma unroll
+  for (int tp = 0; tp < 9; ++tp) {
+    const int yy = py + tp / 3 - 1, xx = px + tp % 3 - 1;
+    if (yy >= 0 && yy < h && xx >= 0 && xx < w) acc = fmaf(Sn[(int64_t)tp * hw + pix], sn[yy * w + xx], acc);
+  }
+  if (use_y) acc -= t[(int64_t)n * hw + pix];
+  v[(int64_t)n * hw + pix] = wgt * acc;
+}
+
+// partial[n][ch][tap] = sum_pix x[n][ch][pix+tap] v[n][pix]    one warp per channel, 8 channels per block
+__global__ void __launch_bounds__(256) corr3x3_grad_filter_kernel(const float *__restrict__ x, const float *__restrict__ v,
+                                                                  int c, int h, int w, float *__restrict__ partial,
+                                                                  const float *__restrict__ skip_if_zero) {
+  const int n = blockIdx.y;
+  const int ch = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (ch >= c) return;
+  float acc[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+  const int hw = h * w;
+  if (!(skip_if_zero && skip_if_zero[n] == 0.f)) {
+    const float *xc = x + ((int64_t)n * c + ch) * hw, *vn = v + (int64_t)n * hw;
+    for (int pix = lane; pix < hw; pix += 32) {
+      const float vv = vn[pix];
+      const int py = pix / w, px = pix - py * w;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int yy = py + t / 3 - 1, xx = px + t % 3 - 1;
+        if (yy >= 0 && yy < h && xx >= 0 && xx < w) acc[t] = fmaf(xc[yy * w + xx], vv, acc[t]);
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const float s = warp_sum(acc[t]);
+    if (lane == 0) partial[((int64_t)n * c + ch) * 9 + t] = s;
+  }
+}
+
+// out[i] = sum_n partial[n][i]   (fixed order)
+__global__ void reduce_rows_kernel(const float *__restrict__ partial, int rows, int64_t n, float *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int r = 0; r < rows; ++r) s += partial[(int64_t)r * n + i];
+  out[i] = s;
+}
+
+// gx[n][pix][ch] = sum_tap f[ch][tap] v[n][pix - tap]      (adjoint of the correlation w.r.t. its input), NHWC out
+__global__ void corr3x3_grad_input_kernel(const float *__restrict__ v, const float *__restrict__ filt, int c, int h, int w,
+                                          float *__restrict__ out) {
+  extern __shared__ float fs[];
+  for (int i = threadIdx.x; i < c * 9; i += blockDim.x) fs[i] = filt[i];
+  __syncthreads();
+  const int n = blockIdx.y, hw = h * w;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)hw * c) return;
+  const int ch = (int)(idx % c), pix = (int)(idx / c);
+  const int py = pix / w, px = pix - py * w;
+  const float *vn = v + (int64_t)n * hw;
+  float acc = 0.f;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int yy = py - (t / 3 - 1), xx = px - (t % 3 - 1);
+    if (yy >= 0 && yy < h && xx >= 0 && xx < w) acc = fmaf(fs[ch * 9 + t], vn[yy * w + xx], acc);
+  }
+  out[((int64_t)n * hw + pix) * c + ch] = acc;
+}
+
+// ---------------------------------------------------------------- pixel weights ----------------------------------
+__global__ void __launch_bounds__(1024) pixel_count_kernel(const float *__restrict__ y, int HW, int threshold,
+                                                           float *__restrict__ px) {
+  __shared__ float red[32];
+  const int k = blockIdx.x;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    const float v = y[(int64_t)k * HW + i];
+    s += threshold ? (v > 0.5f ? 1.f : 0.f) : v;
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) px[k] = s;
+}
+
+__global__ void pixel_weights_kernel(const float *__restrict__ y, const float *__restrict__ px, int HW, float tf,
+                                     int threshold, float *__restrict__ w) {
+  const int k = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= HW) return;
+  const float cnt = px[k];
+  float af = cnt / (float)HW;                       // discriminator.py:127
+  const float small = cnt < 10.f ? 1.f : 0.f;       // :131-132
+  af = small * tf + (1.f - small) * af;
+  const float big = af > tf ? 1.f : 0.f;            // :134-135
+  const float tfe = big * af + (1.f - big) * tf;
+  const float wf = tfe / af, wb = (1.f - tfe) / (1.f - af);
+  float v = y[(int64_t)k * HW + i];
+  if (threshold) v = v > 0.5f ? 1.f : 0.f;
+  w[(int64_t)k * HW + i] = sqrtf(wf * v + wb * (1.f - v));
+}
+
+// ---------------------------------------------------------------- stencil build ----------------------------------
+__device__ __forceinline__ float tent(int idx, int i0, int i1, float lam) {
+  return (idx == i0 ? 1.f - lam : 0.f) + (idx == i1 ? lam : 0.f);
+}
+
+// One warp per low-res pixel a=(i,j): gathers the ~ (2H/h)x(2W/w) high-res window that a contributes to.
+__global__ void __launch_bounds__(256) build_stencil_kernel(const float *__restrict__ pw, const float *__restrict__ y, int H,
+                                                            int W, int h, int w, float *__restrict__ stencil,
+                                                            float *__restrict__ uty) {
+  const int k = blockIdx.y, hw = h * w;
+  const int a = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (a >= hw) return;
+  const int i = a / w, j = a - i * w;
+  const float sh = (float)h / (float)H, sw = (float)w / (float)W;
+  // conservative window: all Y whose source row can be in (i-1, i+1)
+  int Y0 = (int)floorf(((float)i - 1.f + 0.5f) / sh - 0.5f) - 1, Y1 = (int)ceilf(((float)i + 1.f + 0.5f) / sh - 0.5f) + 1;
+  int X0 = (int)floorf(((float)j - 1.f + 0.5f) / sw - 0.5f) - 1, X1 = (int)ceilf(((float)j + 1.f + 0.5f) / sw - 0.5f) + 1;
+  Y0 = max(Y0, 0); X0 = max(X0, 0); Y1 = min(Y1, H - 1); X1 = min(X1, W - 1);
+  const int ny = Y1 - Y0 + 1, nx = X1 - X0 + 1;
+  float acc[9], accy = 0.f;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+  const float *pwk = pw + (int64_t)k * H * W, *yk = y + (int64_t)k * H * W;
+  for (int q = lane; q < ny * nx; q += 32) {
+    const int Y = Y0 + q / nx, X = X0 + q % nx;
+    int y0, y1, x0, x1;
+    float ly, lx;
+    bilinear_src(Y, sh, h, y0, y1, ly);
+    bilinear_src(X, sw, w, x0, x1, lx);
+    const float ua = tent(i, y0, y1, ly) * tent(j, x0, x1, lx);
+    if (ua == 0.f) continue;
+    const float p = pwk[(int64_t)Y * W + X];
+    const float w2 = p * p * ua;
+    accy = fmaf(w2, yk[(int64_t)Y * W + X], accy);
+    float ry[3], rx[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      ry[d] = tent(i + d - 1, y0, y1, ly);
+      rx[d] = tent(j + d - 1, x0, x1, lx);
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[t] = fmaf(w2, ry[t / 3] * rx[t % 3], acc[t]);
+  }
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const float s = warp_sum(acc[t]);
+    if (lane == 0) stencil[((int64_t)k * 9 + t) * hw + a] = s;
+  }
+  accy = warp_sum(accy);
+  if (lane == 0) uty[(int64_t)k * hw + a] = accy;
+}
+
+// ---------------------------------------------------------------- memory -----------------------------------------
+// state: {current_size, prev_replace_ind (-1 none), slot chosen now (-1 = skipped), inserts so far}
+__global__ void memory_next_slot_kernel(float *__restrict__ sw, int cap, float lr, int *__restrict__ state,
+                                        const int *__restrict__ gate_count, int min_px) {
+  if (threadIdx.x != 0) return;
+  if (gate_count && gate_count[0] < min_px) { state[2] = -1; return; }
+  int r = 0;
+  if (state[0] == 0 || lr == 1.f) {
+    for (int i = 0; i < cap; ++i) sw[i] = 0.f;
+    sw[0] = 1.f;
+  } else {
+    float best = sw[0];
+    for (int i = 1; i < cap; ++i)
+      if (sw[i] < best) { best = sw[i]; r = i; }   // first minimum, like torch.min(sw, 0)
+    if (state[1] < 0) {
+      for (int i = 0; i < cap; ++i) sw[i] = sw[i] / (1.f - lr);
+      sw[r] = lr;
+    } else {
+      sw[r] = sw[state[1]] / (1.f - lr);
+    }
+  }
+  double tot = 0.0;
+  for (int i = 0; i < cap; ++i) tot += (double)sw[i];
+  const float ft = (float)tot;
+  for (int i = 0; i < cap; ++i) sw[i] = sw[i] / ft;
+  state[1] = r;
+  state[2] = r;
+  state[0] = min(state[0] + 1, cap);
+  state[3] += 1;
+}
+
+__global__ void memory_insert_kernel(const float *__restrict__ src, int64_t n, float *__restrict__ dst_base,
+                                     const int *__restrict__ state) {
+  const int slot = state[2];
+  if (slot < 0) return;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst_base[(int64_t)slot * n + i] = src[i];
+}
+
+// ---------------------------------------------------------------- CG vector kernels (filter-only problem) --------
+// cg_state layout: p[n] | r_prev[n] | rho | has_p | pad | pad           (persists across updates)
+// work layout    : b/r[n] | x[n] | q[n] | scal[8]
+struct CgVec {
+  float *f, *p, *rprev, *rho, *hasp;  // persistent
+  float *r, *x, *q;                   // per-run scratch
+  const float *partial;               // [cap][n] per-sample gradient partials
+  int n, cap;
+  float reg2, minv, forget;
+};
+
+// mode 0: finish RHS ( r = b = -(sum partial + reg^2 f) ), x = 0, apply the forgetting factor, then first direction.
+// mode 1: finish A p ( q = sum partial + reg^2 p ), alpha step, optional residual update, next direction.
+// mode 2: like mode 1 but last CG iteration of the GN step: no residual update, no new direction, f += x.
+__global__ void __launch_bounds__(1024) cg_vector_kernel(CgVec s, int mode, const int *__restrict__ gate, int min_px) {
+  if (gate && gate[0] < min_px) return;
+  __shared__ float red[32];
+  const int t = threadIdx.x;
+  const bool act = t < s.n;
+  float g = 0.f;
+  if (act)
+    for (int k = 0; k < s.cap; ++k) g += s.partial[(int64_t)k * s.n + t];
+  float r = 0.f, p = 0.f, rp = 0.f;
+  float rho = *s.rho;
+  const bool hasp = *s.hasp != 0.f;
+  if (mode == 0) {
+    if (act) {
+      r = -(g + s.reg2 * s.f[t]);
+      s.x[t] = 0.f;
+      p = hasp ? s.p[t] : 0.f;
+      rp = hasp ? s.rprev[t] : 0.f;
+    }
+    if (hasp) rho = rho / s.forget;                    // optimizer.py:104-105
+  } else {
+    float q = 0.f;
+    if (act) {
+      p = s.p[t];
+      q = g + s.reg2 * p;
+      r = s.r[t];
+    }
+    const float pq = block_sum(act ? p * q : 0.f, red);
+    const float alpha = rho / pq;                      // standard_alpha, optimizer.py:134
+    if (act) {
+      rp = r;                                          // r_prev = r.clone()
+      s.rprev[t] = rp;
+      const float xn = s.x[t] + alpha * p;
+      s.x[t] = xn;
+      if (mode == 1) r = r - alpha * q;
+      else s.f[t] += xn;                               // theta += step_alpha * delta_x
+      s.r[t] = r;
+    }
+    if (mode == 2) return;
+  }
+  // next direction (optimizer.py:115-128): z = r / diag_M ; rho = <r,z> ; beta = max((rho - <r_prev,z>)/rho1, 0)
+  const float z = r * s.minv;
+  const float rho_new = block_sum(act ? r * z : 0.f, red);
+  float pn = z;
+  if (mode != 0 || hasp) {
+    const float rho2 = block_sum(act ? rp * z : 0.f, red);
+    const float beta = fmaxf((rho_new - rho2) / rho, 0.f);
+    pn = z + p * beta;
+  }
+  if (act) {
+    s.p[t] = pn;
+    if (mode == 0) s.r[t] = r;
+  }
+  __syncthreads();
+  if (t == 0) {
+    *s.rho = rho_new;
+    *s.hasp = 1.f;
+  }
+}
+
+// ---------------------------------------------------------------- small vector helpers (joint problem) -----------
+constexpr int VB = 64;  // blocks used by the multi-block vector kernels
+
+__device__ __forceinline__ float seg_sum(const float *__restrict__ part, int stride) {
+  float s = 0.f;
+  for (int i = 0; i < VB; ++i) s += part[i * stride];
+  return s;
+}
+
+// part[b][0] = sum_chunk (r0 r0 m0 + r1 r1 m1), part[b][1] = sum_chunk (rp0 r0 m0 + rp1 r1 m1)
+__global__ void __launch_bounds__(256) joint_dots_rz_kernel(const float *r0, const float *rp0, int64_t n0, float m0,
+                                                            const float *r1, const float *rp1, int64_t n1, float m1,
+                                                            float *part) {
+  __shared__ float red[32];
+  float a = 0.f, b = 0.f;
+  const int64_t tot = n0 + n1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) {
+    const bool first = i < n0;
+    const float r = first ? r0[i] : r1[i - n0];
+    const float rp = first ? rp0[i] : rp1[i - n0];
+    const float z = r * (first ? m0 : m1);
+    a = fmaf(r, z, a);
+    b = fmaf(rp, z, b);
+  }
+  a = block_sum(a, red);
+  b = block_sum(b, red);
+  if (threadIdx.x == 0) { part[blockIdx.x * 2] = a; part[blockIdx.x * 2 + 1] = b; }
+}
+
+// scal: [0]=rho [1]=has_p ; p = z + beta p
+__global__ void __launch_bounds__(256) joint_direction_kernel(float *p0, const float *r0, int64_t n0, float m0, float *p1,
+                                                              const float *r1, int64_t n1, float m1, const float *part,
+                                                              const float *scal_in, float *scal_out, float forget_div) {
+  const float rho_new = seg_sum(part, 2), rho2 = seg_sum(part + 1, 2);
+  const bool hasp = scal_in[1] != 0.f;
+  const float rho1 = scal_in[0] / forget_div;   // forget_div = forget on the first iteration of a run, else 1
+  const float beta = hasp ? fmaxf((rho_new - rho2) / rho1, 0.f) : 0.f;
+  const int64_t tot = n0 + n1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i < n0) p0[i] = r0[i] * m0 + (hasp ? p0[i] * beta : 0.f);
+    else { const int64_t k = i - n0; p1[k] = r1[k] * m1 + (hasp ? p1[k] * beta : 0.f); }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { scal_out[0] = rho_new; scal_out[1] = 1.f; }
+}
+
+__global__ void __launch_bounds__(256) joint_dot_pq_kernel(const float *p0, const float *q0, int64_t n0, const float *p1,
+                                                           const float *q1, int64_t n1, float *part) {
+  __shared__ float red[32];
+  float a = 0.f;
+  const int64_t tot = n0 + n1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x)
+    a = (i < n0) ? fmaf(p0[i], q0[i], a) : fmaf(p1[i - n0], q1[i - n0], a);
+  a = block_sum(a, red);
+  if (threadIdx.x == 0) part[blockIdx.x] = a;
+}
+
+__global__ void __launch_bounds__(256) joint_step_kernel(float *x0, float *r0, float *rp0, const float *p0, const float *q0,
+                                                         int64_t n0, float *x1, float *r1, float *rp1, const float *p1,
+                                                         const float *q1, int64_t n1, const float *part,
+                                                         const float *scal, int update_r) {
+  const float alpha = scal[0] / seg_sum(part, 1);
+  const int64_t tot = n0 + n1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) {
+    float *x = i < n0 ? x0 + i : x1 + (i - n0);
+    float *r = i < n0 ? r0 + i : r1 + (i - n0);
+    float *rp = i < n0 ? rp0 + i : rp1 + (i - n0);
+    const float p = i < n0 ? p0[i] : p1[i - n0];
+    const float q = i < n0 ? q0[i] : q1[i - n0];
+    *rp = *r;
+    *x = *x + alpha * p;
+    if (update_r) *r = *r - alpha * q;
+  }
+}
+
+// y = a*x + b*y ; used for q = g + reg^2 p, b = -(g + reg^2 theta), theta += x
+__global__ void axpby_kernel(float *y, const float *x, float a, float b, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = a * x[i] + b * y[i];
+}
+// out = a*x + b*y
+__global__ void axpby_out_kernel(float *out, const float *x, float a, const float *y, float b, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a * x[i] + b * y[i];
+}
+// (c, C) <-> (C, cpad) transposes of the projection matrix
+__global__ void transpose_pad_kernel(const float *src, int rows, int cols, float *dst, int ld) {  // dst[col][row]
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)rows * cols) return;
+  const int r = (int)(i / cols), c = (int)(i % cols);
+  dst[(int64_t)c * ld + r] = src[i];
+}
+__global__ void untranspose_kernel(const float *src, int rows, int cols, int ld, float *dst) {  // dst[r][c] = src[c][r]
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)rows * cols) return;
+  const int r = (int)(i / cols), c = (int)(i % cols);
+  dst[i] = src[(int64_t)c * ld + r];
+}
+
+// ---------------------------------------------------------------- TN GEMM (J^T over pixels) ----------------------
+// out[m][n] = sum_k A[k][m] B[k][n],  A: K x M (lda), B: K x N (ldb); split-K partials [split][M][N].
+constexpr int TM_ = 64, TN_ = 96, TK_ = 16, KSPLIT = 512;
+__global__ void __launch_bounds__(256) gemm_tn_kernel(const float *__restrict__ A, int lda, const float *__restrict__ Bm,
+                                                      int ldb, int K, int M, int N, float *__restrict__ part) {
+  __shared__ __align__(16) float As[TK_][TM_];
+  __shared__ __align__(16) float Bs[TK_][TN_];
+  const int t = threadIdx.x;
+  const int m0 = blockIdx.x * TM_, split = blockIdx.y;
+  const int k0 = split * KSPLIT, k1 = min(k0 + KSPLIT, K);
+  const int tx = t & 15, ty = t >> 4;  // thread tile: 4 (m) x 6 (n)
+  float acc[4][6];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) acc[i][j] = 0.f;
+  for (int kb = k0; kb < k1; kb += TK_) {
+    for (int i = t; i < TK_ * TM_; i += 256) {
+      const int kk = i / TM_, mm = i % TM_;
+      As[kk][mm] = (kb + kk < k1 && m0 + mm < M) ? A[(int64_t)(kb + kk) * lda + m0 + mm] : 0.f;
+    }
+    for (int i = t; i < TK_ * TN_; i += 256) {
+      const int kk = i / TN_, nn = i % TN_;
+      Bs[kk][nn] = (kb + kk < k1 && nn < N) ? Bm[(int64_t)(kb + kk) * ldb + nn] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < TK_; ++kk) {
+      float a[4], b[6];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) b[j] = Bs[kk][tx * 6 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const int n = tx * 6 + j;
+      if (n < N) part[((int64_t)split * M + m) * N + n] = acc[i][j];
+    }
+  }
+}
+
+}  // namespace frtm
+
+using namespace frtm;
+
+// =====================================================================================================================
+// C ABI
+// =====================================================================================================================
+extern "C" int frtm_corr3x3_nchw(const float *x, const float *filt, const int *filter_index, int NB, int c, int h, int w,
+                                 float *out, void *stream) {
+  FRTM_REQUIRE(x && filt && out && NB > 0 && c > 0, "corr3x3: bad arguments");
+  FRTM_REQUIRE(c * 9 * sizeof(float) <= 48 * 1024, "corr3x3: too many channels");
+  dim3 grid(cdiv(h * w, 128), NB);
+  corr3x3_kernel<<<grid, 128, c * 9 * sizeof(float), (cudaStream_t)stream>>>(x, filt, filter_index, c, h, w, out, 0, nullptr);
+  FRTM_CHECK_LAUNCH("corr3x3");
+  return FRTM_OK;
+}
+
+extern "C" int frtm_pixel_weights(const float *y, int K, int HW, float tf, int threshold, float *w, float *workspace,
+                                  void *stream) {
+  FRTM_REQUIRE(y && w && workspace && K > 0, "pixel_weights: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  pixel_count_kernel<<<K, 1024, 0, st>>>(y, HW, threshold, workspace);
+  FRTM_CHECK_LAUNCH("pixel_count");
+  pixel_weights_kernel<<<dim3(cdiv(HW, 256), K), 256, 0, st>>>(y, workspace, HW, tf, threshold, w);
+  FRTM_CHECK_LAUNCH("pixel_weights");
+  return FRTM_OK;
+}
+
+extern "C" int frtm_build_stencil(const float *pw, const float *y, int K, int H, int W, int h, int w, float *stencil,
+                                  float *uty, void *stream) {
+  FRTM_REQUIRE(pw && y && stencil && uty && K > 0, "build_stencil: bad arguments");
+  FRTM_REQUIRE(H >= h && W >= w, "build_stencil: expects an upsampling geometry (H>=h, W>=w)");
+  build_stencil_kernel<<<dim3(cdiv(h * w, 8), K), 256, 0, (cudaStream_t)stream>>>(pw, y, H, W, h, w, stencil, uty);
+  FRTM_CHECK_LAUNCH("build_stencil");
+  return FRTM_OK;
+}
+
+extern "C" int frtm_memory_next_slot(float *weights, int capacity, float lr, int *state, const int *gate_count, int min_px,
+                                     void *stream) {
+  FRTM_REQUIRE(weights && state && capacity > 0, "memory_next_slot: bad arguments");
+  memory_next_slot_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(weights, capacity, lr, state, gate_count, min_px);
+  FRTM_CHECK_LAUNCH("memory_next_slot");
+  return FRTM_OK;
+}
+
+extern "C" int frtm_memory_insert(const float *feat, int feat_elems, const float *label, const float *pw, int HW,
+                                  const float *stencil, const float *uty, int hw, float *mem_samples, float *mem_labels,
+                                  float *mem_pw, float *mem_stencil, float *mem_uty, const int *state, void *stream) {
+  FRTM_REQUIRE(feat && mem_samples && state, "memory_insert: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  memory_insert_kernel<<<cdiv(feat_elems, 256), 256, 0, st>>>(feat, feat_elems, mem_samples, state);
+  FRTM_CHECK_LAUNCH("memory_insert(samples)");
+  if (label && mem_labels) {
+    memory_insert_kernel<<<cdiv(HW, 256), 256, 0, st>>>(label, HW, mem_labels, state);
+    FRTM_CHECK_LAUNCH("memory_insert(labels)");
+  }
+  if (pw && mem_pw) {
+    memory_insert_kernel<<<cdiv(HW, 256), 256, 0, st>>>(pw, HW, mem_pw, state);
+    FRTM_CHECK_LAUNCH("memory_insert(pw)");
+  }
+  if (stencil && mem_stencil) {
+    memory_insert_kernel<<<cdiv(9 * hw, 256), 256, 0, st>>>(stencil, 9 * hw, mem_stencil, state);
+    FRTM_CHECK_LAUNCH("memory_insert(stencil)");
+  }
+  if (uty && mem_uty) {
+    memory_insert_kernel<<<cdiv(hw, 256), 256, 0, st>>>(uty, hw, mem_uty, state);
+    FRTM_CHECK_LAUNCH("memory_insert(uty)");
+  }
+  return FRTM_OK;
+}
+
+// ---- filter-only GN/CG ------------------------------------------------------------------------------------------
+extern "C" int64_t frtm_gn_update_workspace(int cap, int c, int h, int w) {
+  const int64_t n = (int64_t)c * 9, hw = (int64_t)h * w;
+  // s[cap][hw] | v[cap][hw] | partial[cap][n] | r[n] | x[n] | q[n]
+  return (2 * cap * hw + cap * n + 3 * n + 64) * (int64_t)sizeof(float);
+}
+
+extern "C" int frtm_gn_update(const float *samples, const float *stencil, const float *uty, const float *weights, int cap,
+                              int c, int h, int w, float *filt, float *cg_state, const int *cg_iters, int n_gn, float reg,
+                              float precond, float forget, const int *gate_count, int min_px, float *workspace,
+                              int64_t workspace_bytes, void *stream) {
+  FRTM_REQUIRE(samples && stencil && uty && weights && filt && cg_state && cg_iters && workspace, "gn_update: null pointer");
+  FRTM_REQUIRE(c * 9 <= 1024, "gn_update: filter too large for the single-block CG kernel (c*9 <= 1024)");
+  FRTM_REQUIRE(workspace_bytes >= frtm_gn_update_workspace(cap, c, h, w), "gn_update: workspace too small");
+  FRTM_REQUIRE(forget > 0.f, "gn_update: direction_forget_factor must be > 0 (0 = reset is not used on this path)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = c * 9, hw = h * w;
+  float *s = workspace, *v = s + (int64_t)cap * hw, *partial = v + (int64_t)cap * hw;
+  CgVec cg;
+  cg.f = filt; cg.p = cg_state; cg.rprev = cg_state + n; cg.rho = cg_state + 2 * n; cg.hasp = cg_state + 2 * n + 1;
+  cg.r = partial + (int64_t)cap * n; cg.x = cg.r + n; cg.q = cg.x + n;
+  cg.partial = partial; cg.n = n; cg.cap = cap; cg.reg2 = reg * reg; cg.minv = 1.f / precond; cg.forget = forget;
+  const size_t fsm = (size_t)n * sizeof(float);
+  dim3 gpix(cdiv(hw, 128), cap), gpix256(cdiv(hw, 256), cap), ggrad(cdiv(c, 8), cap);
+  // gating: the tiny vector kernel checks `gate` and skips all arithmetic; the streaming kernels are harmless
+  // (they only write workspace), so they are launched unconditionally to keep the stream free of host syncs.
+  for (int gi = 0; gi < n_gn; ++gi) {
+    const int iters = cg_iters[gi];
+    if (iters <= 0) continue;
+    // RHS: s = X * f ; v = sw (S s - t) ; partial = X^T v
+    corr3x3_kernel<<<gpix, 128, fsm, st>>>(samples, filt, nullptr, c, h, w, s, 0, weights);
+    FRTM_CHECK_LAUNCH("gn_update/score(f)");
+    stencil_apply_kernel<<<gpix256, 256, 0, st>>>(stencil, s, uty, weights, h, w, 1, v);
+    FRTM_CHECK_LAUNCH("gn_update/stencil(rhs)");
+    corr3x3_grad_filter_kernel<<<ggrad, 256, 0, st>>>(samples, v, c, h, w, partial, weights);
+    FRTM_CHECK_LAUNCH("gn_update/grad(rhs)");
+    cg_vector_kernel<<<1, 1024, 0, st>>>(cg, 0, gate_count, min_px);
+    FRTM_CHECK_LAUNCH("gn_update/cg(rhs)");
+    for (int it = 0; it < iters; ++it) {
+      corr3x3_kernel<<<gpix, 128, fsm, st>>>(samples, cg.p, nullptr, c, h, w, s, 0, weights);
+      FRTM_CHECK_LAUNCH("gn_update/score(p)");
+      stencil_apply_kernel<<<gpix256, 256, 0, st>>>(stencil, s, uty, weights, h, w, 0, v);
+      FRTM_CHECK_LAUNCH("gn_update/stencil");
+      corr3x3_grad_filter_kernel<<<ggrad, 256, 0, st>>>(samples, v, c, h, w, partial, weights);
+      FRTM_CHECK_LAUNCH("gn_update/grad");
+      cg_vector_kernel<<<1, 1024, 0, st>>>(cg, it == iters - 1 ? 2 : 1, gate_count, min_px);
+      FRTM_CHECK_LAUNCH("gn_update/cg");
+    }
+  }
+  return FRTM_OK;
+}
+
+// ---- joint (project, filter) GN/CG of Discriminator.init --------------------------------------------------------
+namespace {
+struct InitWs {
+  // sizes
+  int K, C, c, h, w, hw, nP, nF, splits;
+  // buffers (all float)
+  float *Pt, *cx, *a, *s, *v, *ga, *gpart, *fpart, *rP, *rF, *rpP, *rpF, *pP, *pF, *qP, *qF, *xP, *xF, *scal, *dpart;
+  int64_t total;
+  InitWs(int K_, int C_, int c_, int h_, int w_, float *base) : K(K_), C(C_), c(c_), h(h_), w(w_) {
+    hw = h * w; nP = C * c; nF = c * 9; splits = cdiv((int64_t)K * hw, KSPLIT);
+    int64_t o = 0;
+    auto take = [&](int64_t n) { float *p = base ? base + o : nullptr; o += (n + 3) / 4 * 4; return p; };
+    Pt = take(nP); cx = take((int64_t)K * c * hw); a = take((int64_t)K * c * hw); s = take((int64_t)K * hw);
+    v = take((int64_t)K * hw); ga = take((int64_t)K * hw * c); gpart = take((int64_t)splits * nP); fpart = take((int64_t)K * nF);
+    rP = take(nP); rF = take(nF); rpP = take(nP); rpF = take(nF); pP = take(nP); pF = take(nF); qP = take(nP); qF = take(nF);
+    xP = take(nP); xF = take(nF); scal = take(16); dpart = take(2 * VB);
+    total = o;
+  }
+};
+
+// g = J^T [ sw (S Js(d) - use_y t) ]  for the joint problem at the current (Pt, F); d = (dP, dF) or null for the RHS
+int joint_products(const InitWs &W, const float *x, const float *stencil, const float *uty, const float *sw, const float *F,
+                   const float *dP, const float *dF, float *gP, float *gF, cudaStream_t st) {
+  const size_t fsm = (size_t)W.nF * sizeof(float);
+  dim3 gpix(cdiv(W.hw, 128), W.K), gpix256(cdiv(W.hw, 256), W.K), ggrad(cdiv(W.c, 8), W.K);
+  int rc;
+  if (dP == nullptr) {  // RHS: s = F * (P x)
+    corr3x3_kernel<<<gpix, 128, fsm, st>>>(W.cx, F, nullptr, W.c, W.h, W.w, W.s, 0, nullptr);
+    FRTM_CHECK_LAUNCH("gn_init/score");
+  } else {              // J d: s = F * (dP x) + dF * (P x)
+    rc = frtm_conv2d_nhwc(x, W.K, W.h, W.w, W.C, W.C, dP, nullptr, nullptr, 0, nullptr, 0, 0, W.a, W.c, 1, 1, 1, 0, 0, st);
+    if (rc) return rc;
+    corr3x3_kernel<<<gpix, 128, fsm, st>>>(W.a, F, nullptr, W.c, W.h, W.w, W.s, 0, nullptr);
+    FRTM_CHECK_LAUNCH("gn_init/score(dP)");
+    corr3x3_kernel<<<gpix, 128, fsm, st>>>(W.cx, dF, nullptr, W.c, W.h, W.w, W.s, 1, nullptr);
+    FRTM_CHECK_LAUNCH("gn_init/score(dF)");
+  }
+  stencil_apply_kernel<<<gpix256, 256, 0, st>>>(stencil, W.s, uty, sw, W.h, W.w, dP == nullptr ? 1 : 0, W.v);
+  FRTM_CHECK_LAUNCH("gn_init/stencil");
+  corr3x3_grad_filter_kernel<<<ggrad, 256, 0, st>>>(W.cx, W.v, W.c, W.h, W.w, W.fpart, nullptr);
+  FRTM_CHECK_LAUNCH("gn_init/gradF");
+  reduce_rows_kernel<<<cdiv(W.nF, 256), 256, 0, st>>>(W.fpart, W.K, W.nF, gF);
+  FRTM_CHECK_LAUNCH("gn_init/gradF.reduce");
+  corr3x3_grad_input_kernel<<<dim3(cdiv((int64_t)W.hw * W.c, 256), W.K), 256, fsm, st>>>(W.v, F, W.c, W.h, W.w, W.ga);
+  FRTM_CHECK_LAUNCH("gn_init/gradIn");
+  gemm_tn_kernel<<<dim3(cdiv(W.C, TM_), W.splits), 256, 0, st>>>(x, W.C, W.ga, W.c, W.K * W.hw, W.C, W.c, W.gpart);
+  FRTM_CHECK_LAUNCH("gn_init/gemm_tn");
+  reduce_rows_kernel<<<cdiv(W.nP, 256), 256, 0, st>>>(W.gpart, W.splits, W.nP, gP);
+  FRTM_CHECK_LAUNCH("gn_init/gemm_tn.reduce");
+  return FRTM_OK;
+}
+}  // namespace
+
+extern "C" int64_t frtm_gn_init_workspace(int K, int C, int c, int h, int w) {
+  InitWs W(K, C, c, h, w, nullptr);
+  return W.total * (int64_t)sizeof(float);
+}
+
+// mode 0: full optimisation.  mode 1 (probe, for teacher-forced parity tests): out_b = RHS at (P,F), out_Ad = A (dP,dF).
+static int gn_init_impl(const float *x, const float *stencil, const float *uty, const float *sw, int K, int C, int c, int h,
+                        int w, float *P, float *F, const int *cg_iters, int n_gn, float regP, float regF, float mP, float mF,
+                        float forget, float *ws, int64_t ws_bytes, cudaStream_t st, const float *dP, const float *dF,
+                        float *out_bP, float *out_bF, float *out_AP, float *out_AF) {
+  FRTM_REQUIRE(x && stencil && uty && sw && P && F && ws, "gn_init: null pointer");
+  FRTM_REQUIRE(C % 4 == 0 && c % 4 == 0 && c <= TN_ && c * 9 <= 1024, "gn_init: unsupported channel counts C=%d c=%d", C, c);
+  FRTM_REQUIRE(ws_bytes >= frtm_gn_init_workspace(K, C, c, h, w), "gn_init: workspace too small");
+  FRTM_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "gn_init: workspace must be 16-byte aligned");
+  InitWs W(K, C, c, h, w, ws);
+  const int64_t nP = W.nP, nF = W.nF;
+  int rc;
+  auto blocks = [](int64_t n) { return cdiv(n, 256); };
+  transpose_pad_kernel<<<blocks(nP), 256, 0, st>>>(P, c, C, W.Pt, c);   // Pt[C][c]
+  FRTM_CHECK_LAUNCH("gn_init/transpose");
+  cudaMemsetAsync(W.scal, 0, 16 * sizeof(float), st);
+  const bool probe = dP != nullptr;
+  int scal_cur = 0;
+  for (int gi = 0; gi < (probe ? 1 : n_gn); ++gi) {
+    // cx = P x  (K,c,h,w)
+    rc = frtm_conv2d_nhwc(x, K, h, w, C, C, W.Pt, nullptr, nullptr, 0, nullptr, 0, 0, W.cx, c, 1, 1, 1, 0, 0, st);
+    if (rc) return rc;
+    rc = joint_products(W, x, stencil, uty, sw, F, nullptr, nullptr, W.qP, W.qF, st);
+    if (rc) return rc;
+    // r = b = -(g + reg^2 theta)
+    axpby_out_kernel<<<blocks(nP), 256, 0, st>>>(W.rP, W.qP, -1.f, W.Pt, -regP * regP, nP);
+    FRTM_CHECK_LAUNCH("gn_init/rhsP");
+    axpby_out_kernel<<<blocks(nF), 256, 0, st>>>(W.rF, W.qF, -1.f, F, -regF * regF, nF);
+    FRTM_CHECK_LAUNCH("gn_init/rhsF");
+    if (probe) {
+      untranspose_kernel<<<blocks(nP), 256, 0, st>>>(W.rP, c, C, c, out_bP);
+      FRTM_CHECK_LAUNCH("gn_init/probe.b");
+      cudaMemcpyAsync(out_bF, W.rF, nF * sizeof(float), cudaMemcpyDeviceToDevice, st);
+      transpose_pad_kernel<<<blocks(nP), 256, 0, st>>>(dP, c, C, W.pP, c);
+      FRTM_CHECK_LAUNCH("gn_init/probe.dP");
+      rc = joint_products(W, x, stencil, uty, sw, F, W.pP, dF, W.qP, W.qF, st);
+      if (rc) return rc;
+      axpby_kernel<<<blocks(nP), 256, 0, st>>>(W.qP, W.pP, regP * regP, 1.f, nP);
+      FRTM_CHECK_LAUNCH("gn_init/probe.qP");
+      axpby_kernel<<<blocks(nF), 256, 0, st>>>(W.qF, dF, regF * regF, 1.f, nF);
+      FRTM_CHECK_LAUNCH("gn_init/probe.qF");
+      untranspose_kernel<<<blocks(nP), 256, 0, st>>>(W.qP, c, C, c, out_AP);
+      FRTM_CHECK_LAUNCH("gn_init/probe.A");
+      cudaMemcpyAsync(out_AF, W.qF, nF * sizeof(float), cudaMemcpyDeviceToDevice, st);
+      return FRTM_OK;
+    }
+    cudaMemsetAsync(W.xP, 0, nP * sizeof(float), st);
+    cudaMemsetAsync(W.xF, 0, nF * sizeof(float), st);
+    const int iters = cg_iters[gi];
+    for (int it = 0; it < iters; ++it) {
+      float *sin = W.scal + 4 * scal_cur, *sout = W.scal + 4 * (scal_cur ^ 1);
+      joint_dots_rz_kernel<<<VB, 256, 0, st>>>(W.rP, W.rpP, nP, 1.f / mP, W.rF, W.rpF, nF, 1.f / mF, W.dpart);
+      FRTM_CHECK_LAUNCH("gn_init/dots_rz");
+      joint_direction_kernel<<<VB, 256, 0, st>>>(W.pP, W.rP, nP, 1.f / mP, W.pF, W.rF, nF, 1.f / mF, W.dpart, sin, sout,
+                                                 it == 0 ? forget : 1.f);
+      FRTM_CHECK_LAUNCH("gn_init/direction");
+      scal_cur ^= 1;
+      rc = joint_products(W, x, stencil, uty, sw, F, W.pP, W.pF, W.qP, W.qF, st);
+      if (rc) return rc;
+      axpby_kernel<<<blocks(nP), 256, 0, st>>>(W.qP, W.pP, regP * regP, 1.f, nP);
+      FRTM_CHECK_LAUNCH("gn_init/qP");
+      axpby_kernel<<<blocks(nF), 256, 0, st>>>(W.qF, W.pF, regF * regF, 1.f, nF);
+      FRTM_CHECK_LAUNCH("gn_init/qF");
+      joint_dot_pq_kernel<<<VB, 256, 0, st>>>(W.pP, W.qP, nP, W.pF, W.qF, nF, W.dpart);
+      FRTM_CHECK_LAUNCH("gn_init/dot_pq");
+      joint_step_kernel<<<VB, 256, 0, st>>>(W.xP, W.rP, W.rpP, W.pP, W.qP, nP, W.xF, W.rF, W.rpF, W.pF, W.qF, nF, W.dpart,
+                                            W.scal + 4 * scal_cur, it < iters - 1 ? 1 : 0);
+      FRTM_CHECK_LAUNCH("gn_init/step");
+    }
+    if (iters > 0) {
+      axpby_kernel<<<blocks(nP), 256, 0, st>>>(W.Pt, W.xP, 1.f, 1.f, nP);   // theta += delta
+      FRTM_CHECK_LAUNCH("gn_init/updP");
+      axpby_kernel<<<blocks(nF), 256, 0, st>>>(F, W.xF, 1.f, 1.f, nF);
+      FRTM_CHECK_LAUNCH("gn_init/updF");
+    }
+  }
+  untranspose_kernel<<<blocks(nP), 256, 0, st>>>(W.Pt, c, C, c, P);
+  FRTM_CHECK_LAUNCH("gn_init/untranspose");
+  return FRTM_OK;
+}
+
+extern "C" int frtm_gn_init(const float *x_nhwc, const float *stencil, const float *uty, const float *sw, int K, int C, int c,
+                            int h, int w, float *P, float *F, const int *cg_iters, int n_gn, float regP, float regF,
+                            float precondP, float precondF, float forget, float *workspace, int64_t workspace_bytes,
+                            void *stream) {
+  FRTM_REQUIRE(cg_iters && n_gn >= 0, "gn_init: bad schedule");
+  return gn_init_impl(x_nhwc, stencil, uty, sw, K, C, c, h, w, P, F, cg_iters, n_gn, regP, regF, precondP, precondF, forget,
+                      workspace, workspace_bytes, (cudaStream_t)stream, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+extern "C" int frtm_gn_init_probe(const float *x_nhwc, const float *stencil, const float *uty, const float *sw, int K, int C,
+                                  int c, int h, int w, float *P, float *F, const float *dP, const float *dF, float regP,
+                                  float regF, float *out_bP, float *out_bF, float *out_AP, float *out_AF, float *workspace,
+                                  int64_t workspace_bytes, void *stream) {
+  FRTM_REQUIRE(dP && dF && out_bP && out_bF && out_AP && out_AF, "gn_init_probe: null pointer");
+  return gn_init_impl(x_nhwc, stencil, uty, sw, K, C, c, h, w, P, F, nullptr, 1, regP, regF, 1.f, 1.f, 1.f, workspace,
+                      workspace_bytes, (cudaStream_t)stream, dP, dF, out_bP, out_bF, out_AP, out_AF);
+}
+
+// Stand-alone building blocks exported for the parity tests.
+extern "C" int frtm_stencil_apply(const float *stencil, const float *s, const float *uty, const float *sw, int NB, int h, int w,
+                                  int use_y, float *v, void *stream) {
+  FRTM_REQUIRE(stencil && s && uty && sw && v, "stencil_apply: null pointer");
+  stencil_apply_kernel<<<dim3(cdiv(h * w, 256), NB), 256, 0, (cudaStream_t)stream>>>(stencil, s, uty, sw, h, w, use_y, v);
+  FRTM_CHECK_LAUNCH("stencil_apply");
+  return FRTM_OK;
+}

@@ -1,0 +1,128 @@
+"""ResNet-18/101 backbone feature pass on libfrtm_b200 kernels.
+
+Drop-in for the reference's ``ResnetFeatureExtractor`` (``model/feature_extractor.py:7-87``): same constructor
+argument, ``.to(device)``, ``__call__(uint8 image, output_layers) -> {'layer1'..'layer5': (B,C,h,w) fp32}``,
+``.get_out_channels()`` (deep→shallow) and ``.no_grad_forward``.  The arithmetic the reference delegates to
+torchvision's ``ResNet`` modules (``resnet.py:92-105,146-163``: conv → BN → ReLU, residual add) runs here as NHWC
+implicit-GEMM convolutions with eval-mode BatchNorm folded into the weights and bias / residual / ReLU fused in the
+epilogue.  The returned dict additionally carries the NHWC working tensors in ``.nhwc`` so the refinement network
+consumes them without a layout change.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from .. import ops
+from .._lib import require_cuda
+
+_ARCH = {"resnet18": ("basic", (2, 2, 2, 2), (64, 64, 128, 256, 512)),
+         "resnet101": ("bottleneck", (3, 4, 23, 3), (64, 256, 512, 1024, 2048))}
+
+
+class FeatureMaps(dict):
+    """``dict`` of NCHW feature maps (reference contract) + ``.nhwc`` (B,h,w,C) working tensors."""
+
+    def __init__(self, nchw: Dict[str, torch.Tensor], nhwc: Dict[str, torch.Tensor]):
+        super().__init__(nchw)
+        self.nhwc = nhwc
+
+
+class ResnetFeatureExtractor:
+
+    def __init__(self, name: str = "resnet101", state_dict: Optional[Dict[str, torch.Tensor]] = None):
+        if name not in _ARCH:
+            raise ValueError("unsupported backbone '%s' (resnet18 | resnet101)" % name)
+        self.name = name
+        self.kind, self.depth, chans = _ARCH[name]
+        if state_dict is None:
+            # Same source of weights as the reference (feature_extractor.py:14): torchvision's ImageNet checkpoint.
+            import torchvision
+            state_dict = getattr(torchvision.models, name)(weights="IMAGENET1K_V1").state_dict()
+        self._sd = {k: v.detach().cpu() for k, v in state_dict.items() if not k.startswith("fc.")}
+        self._out_channels = OrderedDict(layer5=chans[4], layer4=chans[3], layer3=chans[2], layer2=chans[1], layer1=chans[0])
+        self.device = None
+        self._w: Dict[str, ops.PackedConv] = {}
+
+    # ------------------------------------------------------------------------------------------------------
+    def _bn(self, key):
+        return {k: self._sd[key + "." + k] for k in ("weight", "bias", "running_mean", "running_var")}
+
+    def to(self, device):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("frtm_vos_b200 runs on CUDA (sm_100a) only; got device '%s'" % device)
+        self.device = device
+        sd, w = self._sd, {}
+        w["stem"] = ops.pack_conv(sd["conv1.weight"], bn=self._bn("bn1"), stride=2, pad=3, device=device)
+        for si, nblk in enumerate(self.depth):
+            for bi in range(nblk):
+                key = "layer%d.%d" % (si + 1, bi)
+                stride = 2 if (bi == 0 and si > 0) else 1
+                if self.kind == "basic":
+                    w[key + ".c1"] = ops.pack_conv(sd[key + ".conv1.weight"], bn=self._bn(key + ".bn1"), stride=stride, device=device)
+                    w[key + ".c2"] = ops.pack_conv(sd[key + ".conv2.weight"], bn=self._bn(key + ".bn2"), device=device)
+                else:
+                    w[key + ".c1"] = ops.pack_conv(sd[key + ".conv1.weight"], bn=self._bn(key + ".bn1"), device=device)
+                    w[key + ".c2"] = ops.pack_conv(sd[key + ".conv2.weight"], bn=self._bn(key + ".bn2"), stride=stride, device=device)
+                    w[key + ".c3"] = ops.pack_conv(sd[key + ".conv3.weight"], bn=self._bn(key + ".bn3"), device=device)
+                if (key + ".downsample.0.weight") in sd:
+                    w[key + ".ds"] = ops.pack_conv(sd[key + ".downsample.0.weight"], bn=self._bn(key + ".downsample.1"),
+                                                   stride=stride, pad=0, device=device)
+        self._w = w
+        return self
+
+    def get_out_channels(self):
+        return self._out_channels
+
+    # ------------------------------------------------------------------------------------------------------
+    def forward_nhwc(self, images: torch.Tensor, nchw_layers: Sequence[str] = (), upto: str = "layer5"):
+        """uint8 (B,3,H,W) -> ({layer: NHWC}, {layer: NCHW for layers in nchw_layers}).  Stops after ``upto``."""
+        if self.device is None:
+            raise RuntimeError("call .to(device) first")
+        require_cuda(images, "image")
+        w = self._w
+        nhwc, nchw = {}, {}
+        x = ops.normalize_u8(images)
+        x = ops.conv2d(x, w["stem"], relu=True)
+        if "layer1" in nchw_layers:
+            x, nchw["layer1"] = ops.maxpool3x3s2(x, nchw=True)
+        else:
+            x = ops.maxpool3x3s2(x)
+        nhwc["layer1"] = x
+        last = int(upto[-1])
+        for si, nblk in enumerate(self.depth):
+            name = "layer%d" % (si + 2)
+            if si + 2 > last:
+                break
+            for bi in range(nblk):
+                key = "layer%d.%d" % (si + 1, bi)
+                want = (bi == nblk - 1) and (name in nchw_layers)
+                idt = ops.conv2d(x, w[key + ".ds"]) if (key + ".ds") in w else x
+                h = ops.conv2d(x, w[key + ".c1"], relu=True)
+                if self.kind == "basic":
+                    out = ops.conv2d(h, w[key + ".c2"], res=idt, relu=True, nchw=want)
+                else:
+                    h = ops.conv2d(h, w[key + ".c2"], relu=True)
+                    out = ops.conv2d(h, w[key + ".c3"], res=idt, relu=True, nchw=want)
+                if want:
+                    x, nchw[name] = out
+                else:
+                    x = out
+            nhwc[name] = x
+        return nhwc, nchw
+
+    def __call__(self, input: torch.Tensor, output_layers=None) -> FeatureMaps:
+        img = input if input.dim() == 4 else input.unsqueeze(0)
+        names = ["layer1", "layer2", "layer3", "layer4", "layer5"]
+        want = [n for n in names if output_layers is None or n in output_layers]
+        nhwc, nchw = self.forward_nhwc(img, want)   # like the reference, every stage runs regardless of the request
+        return FeatureMaps(OrderedDict((n, nchw[n]) for n in want), nhwc)
+
+    def no_grad_forward(self, input, output_layers=None, chunk_size=None):
+        if chunk_size is None:
+            return self(input, output_layers)
+        outs = [self(t, output_layers) for t in torch.split(input, chunk_size)]
+        return {L: torch.cat([o[L] for o in outs]) for L in outs[0]}

@@ -1,0 +1,114 @@
+"""Gauss-Newton + Polak-Ribiere conjugate gradient for the target model, in closed form on the device.
+
+The reference (``model/optimizer.py:18-160``) linearises the residual with autograd and evaluates ``J^T J p`` by a
+double backward pass — ~25 ATen launches per CG iteration, each a full pass over the (M,1,H,W) label-size tensors.
+For FRTM's two problems the operator has an exact closed form, so here ``run`` enqueues the
+library's streaming kernels instead (``frtm_gn_update`` for the filter-only problem, ``frtm_gn_init`` for the joint
+project+filter problem).  The CG recurrences are the reference's: ``z = r/diag_M``, Polak-Ribiere ``beta`` clamped at
+0, ``standard_alpha``, ``r`` not advanced on the last iteration, direction/``rho``/``r_prev`` persisting across
+``run`` calls with ``rho /= direction_forget_factor`` on entry (``:98-153``).
+
+Only ``DiscriminatorLoss`` problems are supported: a generic autograd ``MinimizationProblem`` would need a CPU /
+autograd fallback, which this package does not ship by design.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from ..lib.tensorlist import TensorList
+from .._lib import lib, ptr, stream
+
+
+class MinimizationProblem:
+    """Interface kept for API compatibility (``model/optimizer.py:5-15``)."""
+
+    def __call__(self, x: TensorList) -> TensorList:
+        raise NotImplementedError
+
+    def ip_input(self, a, b):
+        return sum(a.view(-1) @ b.view(-1))
+
+    def M1(self, x):
+        return x
+
+    def initialize(self):
+        pass
+
+
+class GaussNewtonCG:
+
+    def __init__(self, problem, variable: TensorList, cg_eps=0.0, fletcher_reeves=True, standard_alpha=True,
+                 direction_forget_factor=0, step_alpha=1.0):
+        from .discriminator import DiscriminatorLoss
+        if not isinstance(problem, DiscriminatorLoss):
+            raise NotImplementedError("GaussNewtonCG runs DiscriminatorLoss problems in closed form on the GPU; generic "
+                                      "autograd problems are not supported (no CPU/autograd fallback)")
+        if fletcher_reeves or not standard_alpha or step_alpha != 1.0 or cg_eps != 0.0:
+            raise NotImplementedError("only the configuration FRTM uses is implemented: Polak-Ribiere, standard_alpha, "
+                                      "step_alpha=1, cg_eps=0 (model/discriminator.py:172,192)")
+        if not direction_forget_factor > 0:
+            raise NotImplementedError("direction_forget_factor must be > 0")
+        self.problem = problem
+        self.x = variable
+        self.direction_forget_factor = float(direction_forget_factor)
+        self.joint = len(variable) == 2
+        n = variable[-1].numel()
+        dev = variable[-1].device
+        # p | r_prev | rho | has_p | pad | pad   (filter-only problem; persists across run() calls)
+        self.cg_state = torch.zeros(2 * n + 4, device=dev, dtype=torch.float32)
+        self._n = n
+        self._ws = None
+
+    # -- persistent CG state, exposed like the reference's attributes ---------------------------------------------
+    @property
+    def p(self):
+        return None if float(self.cg_state[2 * self._n + 1]) == 0.0 else TensorList([self.cg_state[:self._n].view_as(self.x[-1])])
+
+    @property
+    def r_prev(self):
+        return None if float(self.cg_state[2 * self._n + 1]) == 0.0 else TensorList([self.cg_state[self._n:2 * self._n].view_as(self.x[-1])])
+
+    @property
+    def rho(self):
+        return self.cg_state[2 * self._n]
+
+    def set_state(self, p, r_prev, rho):
+        """Inject (p, r_prev, rho) — used by the oracle-replay parity mode."""
+        n = self._n
+        self.cg_state[:n] = p.reshape(-1)
+        self.cg_state[n:2 * n] = r_prev.reshape(-1)
+        self.cg_state[2 * n] = float(rho)
+        self.cg_state[2 * n + 1] = 1.0
+
+    # -- run ----------------------------------------------------------------------------------------------------------
+    def run(self, num_cg_iter, num_gn_iter=None, gate_count=None, min_px=10):
+        if isinstance(num_cg_iter, int):
+            if num_gn_iter is None:
+                raise ValueError("Must specify number of GN iter if CG iter is constant")
+            num_cg_iter = [num_cg_iter] * num_gn_iter
+        num_cg_iter = [int(v) for v in num_cg_iter]
+        if len(num_cg_iter) == 0:
+            return
+        iters = (ctypes.c_int * len(num_cg_iter))(*num_cg_iter)
+        pr = self.problem
+        L = lib()
+        if self.joint:
+            K, h, w, C = pr.x_nhwc.shape
+            c = self.x[1].shape[1]
+            nbytes = L.gn_init_workspace(K, C, c, h, w)
+            ws = torch.empty(nbytes // 4, device=pr.x_nhwc.device, dtype=torch.float32)
+            L.gn_init(ptr(pr.x_nhwc), ptr(pr.stencil), ptr(pr.uty), ptr(pr.sample_weights), K, C, c, h, w, ptr(self.x[0]),
+                      ptr(self.x[1]), iters, len(num_cg_iter), pr.filter_regs[0], pr.filter_regs[1], pr.diag_M[0],
+                      pr.diag_M[1], self.direction_forget_factor, ptr(ws), nbytes, stream())
+        else:
+            mem = pr.memory
+            cap, c, h, w = mem.samples.shape
+            nbytes = L.gn_update_workspace(cap, c, h, w)
+            if self._ws is None or self._ws.numel() * 4 < nbytes:
+                self._ws = torch.empty(nbytes // 4, device=mem.samples.device, dtype=torch.float32)
+            L.gn_update(ptr(mem.samples), ptr(mem.stencil), ptr(mem.uty), ptr(mem.weights), cap, c, h, w, ptr(self.x[0]),
+                        ptr(self.cg_state), iters, len(num_cg_iter), pr.filter_regs[-1], pr.diag_M[-1],
+                        self.direction_forget_factor, ptr(gate_count), int(min_px), ptr(self._ws), nbytes, stream())
+        return [], [], None

@@ -1,0 +1,220 @@
+"""Refinement ("segmentation") network on libfrtm_b200 kernels.
+
+Drop-in for the reference's ``SegNetwork`` (``model/seg_network.py:149-189``): same constructor, same parameter
+names (so reference checkpoints load with ``load_state_dict``), ``forward(scores, features, image_size)`` ->
+``(B,1,H,W)`` logits.  Per pyramid level (deep -> shallow): TSE (``:7-21``) -> RRB (``:44-56``) -> CAB (``:24-41``)
+-> RRB, then the back-compat upsampler (``:129-146``) built on the fixed x2 bicubic pyramid filter (``:75-126``).
+
+What differs from the reference's execution (not from its results):
+  * activations are NHWC and the whole batch of objects (and frames) goes through every kernel at once, instead of
+    a Python loop with batch 1 per object (``model/tracker.py:199-204``);
+  * ``TSE.reduce(ft)`` depends only on the backbone features, so it is evaluated once per frame and broadcast to
+    the objects of that frame (SURVEY.md finding 5);
+  * eval-mode BatchNorm is folded into the preceding conv; bias / residual / ReLU are fused conv epilogues;
+  * ``cat(h, score)`` is never materialised by a copy: producers write into a 68-channel-stride buffer.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Dict
+
+import torch
+from torch import nn
+
+from .. import ops
+from .feature_extractor import FeatureMaps
+
+
+def _conv(ic, oc, k, bias=True):
+    return nn.Conv2d(ic, oc, k, padding=k // 2, bias=bias)
+
+
+def _relu():
+    return nn.LeakyReLU(0.0)
+
+
+class _Params(nn.Module):
+    """Parameter container; the arithmetic lives in SegNetwork.forward."""
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("parameter container only")
+
+
+class TSE(_Params):
+    def __init__(self, fc, ic, oc):
+        super().__init__()
+        nc = ic + oc
+        self.reduce = nn.Sequential(_conv(fc, oc, 1), _relu(), _conv(oc, oc, 1))
+        self.transform = nn.Sequential(_conv(nc, nc, 3), _relu(), _conv(nc, nc, 3), _relu(), _conv(nc, oc, 3), _relu())
+
+
+class CAB(_Params):
+    def __init__(self, oc, deepest):
+        super().__init__()
+        self.convreluconv = nn.Sequential(_conv(2 * oc, oc, 1), _relu(), _conv(oc, oc, 1))
+        self.deepest = deepest
+
+
+class RRB(_Params):
+    def __init__(self, oc, use_bn=False):
+        super().__init__()
+        self.conv1x1 = _conv(oc, oc, 1)
+        if use_bn:
+            self.bblock = nn.Sequential(_conv(oc, oc, 3), nn.BatchNorm2d(oc), _relu(), _conv(oc, oc, 3, bias=False))
+        else:
+            self.bblock = nn.Sequential(_conv(oc, oc, 3), _relu(), _conv(oc, oc, 3, bias=False))
+
+
+class BackwardCompatibleUpsampler(_Params):
+    def __init__(self, in_channels=64):
+        super().__init__()
+        self.conv1 = _conv(in_channels, in_channels // 2, 3)
+        self.conv2 = _conv(in_channels // 2, 1, 3)
+
+
+class SegNetwork(nn.Module):
+
+    def __init__(self, in_channels=1, out_channels=32, ft_channels=None, use_bn=False):
+        super().__init__()
+        assert ft_channels is not None
+        if in_channels != 1:
+            raise ValueError("the fused TSE kernels expect a single score channel (in_channels=1)")
+        self.ft_channels = ft_channels
+        self.use_bn = use_bn
+        self.oc = out_channels
+        self.TSE, self.RRB1, self.CAB, self.RRB2 = nn.ModuleDict(), nn.ModuleDict(), nn.ModuleDict(), nn.ModuleDict()
+        for i, (L, fc) in enumerate(self.ft_channels.items()):
+            self.TSE[L] = TSE(fc, in_channels, out_channels)
+            self.RRB1[L] = RRB(out_channels, use_bn=use_bn)
+            self.CAB[L] = CAB(out_channels, i == 0)   # reference: L == 'layer5', i.e. the first (deepest) level
+            self.RRB2[L] = RRB(out_channels, use_bn=use_bn)
+        self.project = BackwardCompatibleUpsampler(out_channels)
+        self._packed = None
+        self._bufs: Dict[tuple, torch.Tensor] = {}
+
+    # -- weight packing -----------------------------------------------------------------------------------------
+    def _apply(self, fn, *a, **k):
+        self._packed = None
+        self._bufs = {}
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._packed = None
+        return super().load_state_dict(*a, **k)
+
+    def _load_from_state_dict(self, *a, **k):
+        self._packed = None
+        return super()._load_from_state_dict(*a, **k)
+
+    def refresh(self):
+        """Re-pack weights after an in-place parameter edit."""
+        self._packed = None
+
+    def _pack(self):
+        dev = self.project.conv1.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("SegNetwork must live on a CUDA device (no CPU path)")
+        P = {}
+        oc, pad65 = self.oc, ops._rup(self.oc + 1, 4)
+
+        def pc(m, **kw):
+            return ops.pack_conv(m.weight, m.bias, device=dev, **kw)
+
+        for L in self.ft_channels:
+            t, r1, c, r2 = self.TSE[L], self.RRB1[L], self.CAB[L], self.RRB2[L]
+            P[L] = dict(
+                red0=pc(t.reduce[0]), red2=pc(t.reduce[2]),
+                tr0=pc(t.transform[0], cin_pad=pad65), tr2=pc(t.transform[2], cin_pad=pad65), tr4=pc(t.transform[4], cin_pad=pad65),
+                cab_w1=c.convreluconv[0].weight.detach().reshape(oc, 2 * oc).contiguous(), cab_b1=c.convreluconv[0].bias.detach(),
+                cab_w2=c.convreluconv[2].weight.detach().reshape(oc, oc).contiguous(), cab_b2=c.convreluconv[2].bias.detach(),
+            )
+            for tag, r in (("rrb1", r1), ("rrb2", r2)):
+                P[L][tag + "_1x1"] = pc(r.conv1x1)
+                if self.use_bn:
+                    bn = r.bblock[1]
+                    P[L][tag + "_a"] = ops.pack_conv(r.bblock[0].weight, r.bblock[0].bias, device=dev, eps=bn.eps, bn=dict(
+                        weight=bn.weight.detach(), bias=bn.bias.detach(), running_mean=bn.running_mean, running_var=bn.running_var))
+                    P[L][tag + "_b"] = pc(r.bblock[3])
+                else:
+                    P[L][tag + "_a"] = pc(r.bblock[0])
+                    P[L][tag + "_b"] = pc(r.bblock[2])
+        P["up1"] = pc(self.project.conv1)
+        w2 = self.project.conv2.weight.detach()
+        P["up2_w"] = w2.permute(2, 3, 1, 0).reshape(9, w2.shape[1]).contiguous()
+        P["up2_b"] = self.project.conv2.bias.detach().contiguous()
+        self._packed = P
+        self._pad65 = pad65
+
+    def _zbuf(self, tag, shape, dev):
+        key = (tag,) + tuple(shape)
+        b = self._bufs.get(key)
+        if b is None or b.device != dev:
+            b = torch.zeros(shape, device=dev, dtype=torch.float32)
+            self._bufs[key] = b
+        return b
+
+    # -- forward ------------------------------------------------------------------------------------------------
+    def forward_nhwc(self, scores: torch.Tensor, feats: Dict[str, torch.Tensor], image_size) -> torch.Tensor:
+        """scores (B,hs,ws) + NHWC feature maps (F,h,w,C) with B = F * objects  ->  logits (B,H,W)."""
+        if self._packed is None:
+            self._pack()
+        P = self._packed
+        B = scores.shape[0]
+        dev = scores.device
+        s_nhwc = scores.reshape(B, scores.shape[-2], scores.shape[-1], 1)
+        x = None
+        hpool = None
+        for li, L in enumerate(self.ft_channels):
+            ft = feats[L]
+            F, h, w, _ = ft.shape
+            n_obj = B // F
+            assert n_obj * F == B, "scores batch must be a multiple of the feature batch"
+            W = P[L]
+            cat_a = self._zbuf("cat_a", (B, h, w, self._pad65), dev)
+            cat_b = self._zbuf("cat_b", (B, h, w, self._pad65), dev)
+            r = ops.conv2d(ft, W["red0"], relu=True)
+            if n_obj == 1:
+                ops.conv2d(r, W["red2"], out=cat_a, coff=0)
+            else:
+                r = ops.conv2d(r, W["red2"])
+                ops.broadcast_objects(r, n_obj, cat_a, channels=self.oc)
+            if (h, w) == tuple(s_nhwc.shape[1:3]):
+                ops.scatter_channel(s_nhwc.reshape(B, h, w), cat_a, self.oc, 0)
+            else:
+                ops.resize_bilinear(s_nhwc, (h, w), channels=1, out=cat_a, coff=self.oc)
+            if li == 0:
+                hpool = ops.global_avgpool(cat_a, channels=self.oc)          # (B, oc) vector at the deepest level
+            ops.conv2d(cat_a, W["tr0"], relu=True, out=cat_b, coff=0)
+            ops.conv2d(cat_b, W["tr2"], relu=True, out=cat_a, coff=0)
+            t = ops.conv2d(cat_a, W["tr4"], relu=True)
+            # RRB1
+            hh = ops.conv2d(t, W["rrb1_1x1"])
+            b = ops.conv2d(hh, W["rrb1_a"], relu=True)
+            t = ops.conv2d(b, W["rrb1_b"], res=hh, relu=True)
+            # CAB
+            sp = ops.global_avgpool(t)
+            if li == 0:
+                t = ops.cab(t, sp, hpool, hpool, W["cab_w1"], W["cab_b1"], W["cab_w2"], W["cab_b2"])
+            else:
+                dp = ops.global_avgpool(x)
+                deeper = ops.resize_bilinear(x, (h, w))
+                t = ops.cab(t, sp, dp, deeper, W["cab_w1"], W["cab_b1"], W["cab_w2"], W["cab_b2"])
+            # RRB2
+            hh = ops.conv2d(t, W["rrb2_1x1"])
+            b = ops.conv2d(hh, W["rrb2_a"], relu=True)
+            x = ops.conv2d(b, W["rrb2_b"], res=hh, relu=True)
+        u = ops.pyrup_bicubic(x)
+        u = ops.conv2d(u, P["up1"], relu=True)
+        u = ops.pyrup_bicubic(u)
+        u = ops.resize_bilinear(u, image_size[-2:])
+        return ops.conv3x3_to1(u, P["up2_w"], P["up2_b"])
+
+    def forward(self, scores, features, image_size):
+        """Reference signature: scores (B,1,h,w), features dict (NCHW; ``FeatureMaps`` carries NHWC too)."""
+        if isinstance(features, FeatureMaps) and all(L in features.nhwc for L in self.ft_channels):
+            feats = features.nhwc
+        else:
+            feats = {L: ops.nchw_to_nhwc(features[L]) for L in self.ft_channels}
+        image_size = [int(v) for v in (image_size.tolist() if torch.is_tensor(image_size) else image_size)]
+        logits = self.forward_nhwc(scores.reshape(scores.shape[0], *scores.shape[-2:]).contiguous(), feats, image_size)
+        return logits.unsqueeze(1)

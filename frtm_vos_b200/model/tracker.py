@@ -1,0 +1,236 @@
+"""Sequence driver (drop-in for ``model/tracker.py:16-227``).
+
+``Tracker(augmenter, feature_extractor, disc_params, refiner, device)`` keeps the reference's public surface:
+``run_dataset``, ``run_sequence`` (same fps definition: frames / wall-clock of the frame loop including per-object
+initialisation, ``:130,159-161``), ``initialize``, ``track``, ``clear``, attributes ``targets``, ``current_masks``,
+``current_frame``.  What changes is how a frame executes:
+
+  * one batched pass per stage instead of a Python loop over objects: the 1x1 projections of all live objects are
+    stacked along Cout of a single conv, their 3x3 filters live in one contiguous buffer read by one correlation
+    launch, and the refinement network sees all objects as one batch;
+  * sigmoid + suppression + clamp + softmax-merge + argmax gating + label LUT + the per-object ``> 0.5`` pixel counts
+    are one fused kernel;
+  * the ``< 10 px`` update gate and the memory replace-index live on the device — no host sync inside the frame loop.
+"""
+from __future__ import annotations
+
+from time import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .discriminator import Discriminator
+from .seg_network import SegNetwork
+
+
+class TargetObject:
+
+    def __init__(self, obj_id, disc_params, **kwargs):
+        self.object_id = obj_id
+        self.discriminator = Discriminator(**disc_params)
+        self.disc_layer = disc_params["layer"]
+        self.start_frame = None
+        self.start_mask = None
+        self.index = -1
+        for key, val in kwargs.items():
+            setattr(self, key, val)
+
+    def initialize(self, ft, mask):
+        x_nhwc = ft.nhwc[self.disc_layer] if hasattr(ft, "nhwc") else None
+        self.discriminator.init(ft[self.disc_layer] if x_nhwc is None else None, mask, x_nhwc=x_nhwc)
+
+    def classify(self, ft):
+        return self.discriminator.apply(ft)
+
+
+class Tracker(nn.Module):
+
+    def __init__(self, augmenter, feature_extractor, disc_params, refiner: SegNetwork, device):
+        super().__init__()
+        self.augmenter = augmenter
+        self.augment = augmenter.augment_first_frame
+        self.disc_params = disc_params
+        self.feature_extractor = feature_extractor
+        self.refiner = refiner
+        for m in self.refiner.parameters():
+            m.requires_grad_(False)
+        self.refiner.eval()
+        self.device = device
+        self.first_frames = []
+        self.current_frame = 0
+        self.current_masks = None
+        self.num_objects = 0
+        self.targets = dict()
+        self.object_ids = []
+        self._stack = None          # cached stacked projection of the live objects
+        self._fbuf = None           # (maxN, c, 3, 3) contiguous filters (each Discriminator.filter.weight is a view)
+        self._last_labels = None
+
+    def clear(self):
+        self.first_frames = []
+        self.current_frame = 0
+        self.current_masks = None
+        self.num_objects = 0
+        self._stack = None
+        torch.cuda.empty_cache()
+
+    # ------------------------------------------------------------------------------------------------------------
+    def run_dataset(self, dataset, out_path, speedrun=False, restart=None):
+        """Runs every sequence of ``dataset`` and writes indexed PNG label maps under ``out_path`` (``:68-101``)."""
+        from ..lib.image import imwrite_indexed
+        out_path.mkdir(exist_ok=True, parents=True)
+        fps_sum, fps_n = 0.0, 0
+        print("Evaluating", dataset.name)
+        restarted = False
+        for sequence in dataset:
+            if restart is not None and not restarted:
+                if sequence.name != restart:
+                    continue
+                restarted = True
+            sequence.preload(self.device)
+            self.clear()
+            outputs, seq_fps = self.run_sequence(sequence, speedrun)
+            if not np.isnan(seq_fps):
+                fps_sum, fps_n = fps_sum + seq_fps, fps_n + 1
+            dst = out_path / sequence.name
+            dst.mkdir(exist_ok=True)
+            for lb, f in zip(outputs, sequence.frame_names):
+                imwrite_indexed(dst / (f + ".png"), lb)
+        print("Average frame rate: %.2f fps" % (fps_sum / max(fps_n, 1)))
+
+    def run_sequence(self, sequence, speedrun=False):
+        self.eval()
+        self.object_ids = sequence.obj_ids
+        self.current_frame = 0
+        self.targets = dict()
+        self._stack = None
+        self._fbuf = None
+        self._lut = torch.tensor([0] + list(sequence.obj_ids), dtype=torch.uint8, device=self.device)
+        N = 0
+        if speedrun:
+            image, labels, obj_ids = sequence[0]
+            image = image.to(self.device)
+            labels = labels.to(self.device)
+            self.initialize(image, labels, sequence.obj_ids)
+            self.track(image)
+            torch.cuda.synchronize()
+            self.targets = dict()
+            self._stack = None
+            self._fbuf = None
+
+        outputs = []
+        t0 = time()
+        for i in range(len(sequence)):
+            image, labels, new_objects = sequence[i]
+            had_targets = len(self.targets) > 0
+            image = image.to(self.device)
+            if len(new_objects) > 0:
+                labels = labels.to(self.device)
+                self.initialize(image, labels, new_objects)
+            if had_targets:
+                self.track(image)
+                labels = self._last_labels if len(sequence.obj_ids) > 1 else self._last_labels.unsqueeze(0)
+            if isinstance(labels, list) and len(labels) == 0:
+                labels = image.new_zeros(1, *image.shape[-2:])
+            outputs.append(labels)
+            self.current_frame += 1
+            N += 1
+        torch.cuda.synchronize()
+        T = time() - t0
+        return outputs, N / T
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _bind_filter(self, target):
+        """Move the object's 3x3 filter into the shared contiguous buffer (one correlation launch for all objects)."""
+        d = target.discriminator
+        c = d.filter.weight.shape[1]
+        need = target.index
+        if self._fbuf is None or self._fbuf.shape[0] < need:
+            cap = max(need, len(self.object_ids), 4)
+            new = torch.zeros(cap, c, 3, 3, device=d.filter.weight.device)
+            if self._fbuf is not None:
+                new[:self._fbuf.shape[0]] = self._fbuf
+                for t in self.targets.values():
+                    if t is not target:
+                        t.discriminator.filter.weight.data = new[t.index - 1:t.index]
+            self._fbuf = new
+        self._fbuf[need - 1:need] = d.filter.weight.data
+        d.filter.weight.data = self._fbuf[need - 1:need]
+        if d.update_optimizer is not None:
+            d.update_optimizer.x[0] = d.filter.weight
+
+    def initialize(self, image, labels, new_objects):
+        self.current_masks = torch.zeros((len(self.targets) + len(new_objects) + 1, *image.shape[-2:]), device=self.device)
+        for obj_id in new_objects:
+            mask = (labels == obj_id).byte()
+            target = TargetObject(obj_id=obj_id, index=len(self.targets) + 1, disc_params=self.disc_params,
+                                  start_frame=self.current_frame, start_mask=mask)
+            self.targets[obj_id] = target
+            # same (debug) reseeding as the reference so augmentation is deterministic per object (:178-180)
+            torch.random.manual_seed(0)
+            np.random.seed(0)
+            im, msk = self.augment(image, mask)
+            nhwc, _ = self.feature_extractor.forward_nhwc(im.to(self.device), (), upto=target.disc_layer)
+            target.discriminator.init(None, msk.to(self.device), x_nhwc=nhwc[target.disc_layer])
+            self._bind_filter(target)
+            self.current_masks[target.index] = mask
+        self._stack = None
+        return self.current_masks
+
+    def _live(self):
+        return [t for t in self.targets.values() if t.start_frame < self.current_frame]
+
+    def _stacked_projection(self, live):
+        key = tuple(t.object_id for t in live)
+        if self._stack is None or self._stack[0] != key:
+            W = torch.cat([t.discriminator.project.weight.detach() for t in live], dim=0)   # (N*c, C, 1, 1)
+            self._stack = (key, ops.pack_conv(W, device=W.device))
+        return self._stack[1]
+
+    def track(self, image):
+        im_size = image.shape[-2:]
+        feats, _ = self.feature_extractor.forward_nhwc(image if image.dim() == 4 else image.unsqueeze(0))
+        live = self._live()
+        n = len(live)
+        layer = live[0].disc_layer
+        c = live[0].discriminator.filter.weight.shape[1]
+        fmap = feats[layer]
+        h, w = fmap.shape[1:3]
+
+        # classify: one conv for all projections, one correlation for all filters
+        samples = ops.conv2d(fmap, self._stacked_projection(live), nchw=True, nhwc=False).view(n, c, h, w)
+        if not hasattr(self, "_arange") or self._arange.numel() < n:
+            self._arange = torch.arange(max(n, 16), dtype=torch.int32, device=fmap.device)
+        scores = ops.corr3x3(samples, self._fbuf, self._arange)
+        logits = self.refiner.forward_nhwc(scores, feats, im_size)
+        for k, t in enumerate(live):
+            t.discriminator.frame_num += 1
+            t.discriminator.current_sample = samples[k:k + 1]
+
+        # merge (new objects of this frame take part with their start masks and suppress the others under them)
+        fresh = [t for t in self.targets.values() if t.start_frame == self.current_frame]
+        if fresh:
+            src = torch.cat([logits] + [t.start_mask.reshape(1, *im_size).float() for t in fresh], dim=0)
+            suppress = torch.stack([t.start_mask.reshape(*im_size) for t in fresh]).amax(dim=0).contiguous()
+        else:
+            src, suppress = logits, None
+        total = n + len(fresh)
+        masks, labels, counts = ops.merge_masks(src, (1 << n) - 1, suppress, self._lut, len(self.object_ids) == 1)
+        self.current_masks = masks
+        self._last_labels = labels
+
+        # learn
+        if self.disc_params["update_filters"]:
+            d0 = live[0].discriminator
+            ys = masks[1:1 + n].reshape(n, 1, *im_size)
+            if d0.pw_params is not None and d0.pw_params["method"] == "hinge":
+                pw = ops.pixel_weights(ys, d0.pw_params["tf"], True)
+            else:
+                pw = torch.ones_like(ys)
+            stencil, uty = ops.build_stencil(pw, ys, (h, w))
+            for k, t in enumerate(live):
+                t.discriminator.update(ys[k:k + 1], gate_count=counts[k:k + 1], pw=pw[k:k + 1], stencil=stencil[k:k + 1],
+                                       uty=uty[k:k + 1])
+        return self.current_masks

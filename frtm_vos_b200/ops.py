@@ -1,0 +1,212 @@
+"""Thin tensor-level wrappers over the C ABI (``include/frtm_b200.h``).
+
+PyTorch is used for device memory and streams only; every function here enqueues hand-written kernels from
+``libfrtm_b200.so`` on the current CUDA stream and returns the output tensor(s).  Activations are NHWC fp32
+(``(B,H,W,ld)`` with the logical channel count carried separately when ``ld`` is padded).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from ._lib import lib, ptr, stream, require_cuda
+
+
+def _rup(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+@dataclass
+class PackedConv:
+    """Conv weights in the library layout ``[kh][kw*cin_pad][cout_pad]`` (+ optional bias with BN folded in)."""
+    w: torch.Tensor
+    bias: Optional[torch.Tensor]
+    cin: int
+    cin_pad: int
+    cout: int
+    kh: int
+    kw: int
+    stride: int
+    pad: int
+
+    @property
+    def flops(self) -> int:
+        return 2 * self.cin * self.cout * self.kh * self.kw
+
+
+def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, bn: Optional[dict] = None, stride: int = 1,
+              pad: Optional[int] = None, device=None, cin_pad: Optional[int] = None, eps: float = 1e-5) -> PackedConv:
+    """(Cout,Cin,kh,kw) [+ eval-mode BatchNorm folded] -> PackedConv on ``device``.  Host-side, done once per model."""
+    w = weight.detach().to("cpu", torch.float64)
+    cout, cin, kh, kw = w.shape
+    b = bias.detach().to("cpu", torch.float64) if bias is not None else None
+    if bn is not None:
+        scale = bn["weight"].double().cpu() / torch.sqrt(bn["running_var"].double().cpu() + eps)
+        w = w * scale.view(-1, 1, 1, 1)
+        shift = bn["bias"].double().cpu() - bn["running_mean"].double().cpu() * scale
+        b = shift if b is None else b * scale + shift
+    cin_pad = cin_pad or _rup(cin, 4)
+    cout_pad = _rup(cout, 4)
+    packed = torch.zeros(kh, kw, cin_pad, cout_pad, dtype=torch.float64)
+    packed[:, :, :cin, :cout] = w.permute(2, 3, 1, 0)
+    packed = packed.reshape(kh, kw * cin_pad, cout_pad).to(torch.float32).contiguous().to(device)
+    return PackedConv(packed, None if b is None else b.to(torch.float32).contiguous().to(device), cin, cin_pad, cout, kh,
+                      kw, stride, kh // 2 if pad is None else pad)
+
+
+def conv2d(x: torch.Tensor, pc: PackedConv, res: Optional[torch.Tensor] = None, relu: bool = False,
+           out: Optional[torch.Tensor] = None, coff: int = 0, nchw: bool = False, nhwc: bool = True):
+    """x (B,H,W,ldx) -> y (B,Ho,Wo,cout) [written into ``out`` at channel offset ``coff`` when given].
+
+    Returns ``y`` or ``(y, y_nchw)`` when ``nchw``; with ``nhwc=False`` only the NCHW tensor is produced."""
+    B, H, W, ldx = x.shape
+    Ho = (H + 2 * pc.pad - pc.kh) // pc.stride + 1
+    Wo = (W + 2 * pc.pad - pc.kw) // pc.stride + 1
+    y = None
+    if nhwc:
+        y = out if out is not None else torch.empty((B, Ho, Wo, pc.cout), device=x.device, dtype=torch.float32)
+        assert y.shape[:3] == (B, Ho, Wo) and y.is_contiguous()
+    y_nchw = torch.empty((B, pc.cout, Ho, Wo), device=x.device, dtype=torch.float32) if nchw else None
+    if res is not None:
+        assert res.shape[:3] == (B, Ho, Wo)
+    lib().conv2d_nhwc(ptr(x), B, H, W, pc.cin_pad, ldx, ptr(pc.w), ptr(pc.bias), ptr(res),
+                      0 if res is None else res.shape[3], ptr(y), 0 if y is None else y.shape[3], coff, ptr(y_nchw),
+                      pc.cout, pc.kh, pc.kw, pc.stride, pc.pad, 1 if relu else 0, stream())
+    if nchw and nhwc:
+        return y, y_nchw
+    return y_nchw if nchw else y
+
+
+def normalize_u8(img: torch.Tensor) -> torch.Tensor:
+    """uint8 (B,3,H,W) -> fp32 NHWC (B,H,W,4)."""
+    require_cuda(img, "image")
+    B, C, H, W = img.shape
+    assert C == 3 and img.dtype == torch.uint8
+    out = torch.empty((B, H, W, 4), device=img.device, dtype=torch.float32)
+    lib().normalize_u8(ptr(img.contiguous()), B, H, W, ptr(out), stream())
+    return out
+
+
+def maxpool3x3s2(x: torch.Tensor, nchw: bool = False):
+    B, H, W, C = x.shape
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    y = torch.empty((B, Ho, Wo, C), device=x.device, dtype=torch.float32)
+    y_nchw = torch.empty((B, C, Ho, Wo), device=x.device, dtype=torch.float32) if nchw else None
+    lib().maxpool3x3s2_nhwc(ptr(x), B, H, W, C, ptr(y), ptr(y_nchw), stream())
+    return (y, y_nchw) if nchw else y
+
+
+def resize_bilinear(x: torch.Tensor, size, channels: Optional[int] = None, out: Optional[torch.Tensor] = None,
+                    coff: int = 0, accumulate: bool = False) -> torch.Tensor:
+    B, H, W, ldx = x.shape
+    C = channels or ldx
+    Ho, Wo = int(size[0]), int(size[1])
+    y = out if out is not None else torch.empty((B, Ho, Wo, C), device=x.device, dtype=torch.float32)
+    lib().resize_bilinear_nhwc(ptr(x), B, H, W, C, ldx, ptr(y), Ho, Wo, y.shape[3], coff, 1 if accumulate else 0, stream())
+    return y
+
+
+def pyrup_bicubic(x: torch.Tensor) -> torch.Tensor:
+    B, H, W, C = x.shape
+    y = torch.empty((B, 2 * H, 2 * W, C), device=x.device, dtype=torch.float32)
+    lib().pyrup_bicubic_nhwc(ptr(x), B, H, W, C, ptr(y), stream())
+    return y
+
+
+def global_avgpool(x: torch.Tensor, channels: Optional[int] = None) -> torch.Tensor:
+    B, H, W, ldx = x.shape
+    C = channels or ldx
+    out = torch.empty((B, C), device=x.device, dtype=torch.float32)
+    nbytes = lib().global_avgpool_workspace(B, H * W, C)
+    ws = torch.empty(nbytes // 4, device=x.device, dtype=torch.float32)
+    lib().global_avgpool_nhwc(ptr(x), B, H * W, C, ldx, ptr(out), ptr(ws), nbytes, stream())
+    return out
+
+
+def cab(shallow: torch.Tensor, shallow_pool: torch.Tensor, deep_pool: torch.Tensor, deeper: torch.Tensor, w1, b1, w2, b2):
+    """gate from pooled vectors, then shallow*gate + deeper (map of the same shape, or a (B,C) vector)."""
+    B, H, W, C = shallow.shape
+    gate = torch.empty((B, C), device=shallow.device, dtype=torch.float32)
+    lib().cab_gate(ptr(shallow_pool), ptr(deep_pool), ptr(w1), ptr(b1), ptr(w2), ptr(b2), B, C, ptr(gate), stream())
+    out = torch.empty_like(shallow)
+    lib().cab_apply_nhwc(ptr(shallow), ptr(gate), ptr(deeper), 1 if deeper.dim() == 2 else 0, B, H * W, C, ptr(out), stream())
+    return out
+
+
+def scatter_channel(src: torch.Tensor, dst: torch.Tensor, coff: int, nzero: int):
+    """src (B,H,W) -> dst[..., coff], zeroing dst[..., coff+1 : coff+1+nzero]."""
+    B, H, W, ld = dst.shape
+    lib().scatter_channel_nhwc(ptr(src), B, H * W, ptr(dst), ld, coff, nzero, stream())
+
+
+def broadcast_objects(src: torch.Tensor, n_obj: int, out: torch.Tensor, channels: Optional[int] = None):
+    """src (F,H,W,lds) -> out (F*n_obj,H,W,ldd)[..., :C]."""
+    F, H, W, lds = src.shape
+    C = channels or lds
+    lib().broadcast_objects_nhwc(ptr(src), F, n_obj, H * W, C, lds, ptr(out), out.shape[3], stream())
+
+
+def nhwc_to_nchw(x: torch.Tensor, channels: Optional[int] = None) -> torch.Tensor:
+    B, H, W, ld = x.shape
+    C = channels or ld
+    y = torch.empty((B, C, H, W), device=x.device, dtype=torch.float32)
+    lib().nhwc_to_nchw(ptr(x), B, H * W, C, ld, ptr(y), stream())
+    return y
+
+
+def nchw_to_nhwc(x: torch.Tensor) -> torch.Tensor:
+    """Layout plumbing for foreign NCHW inputs (not on the fast path)."""
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def conv3x3_to1(x: torch.Tensor, w9c: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    B, H, W, C = x.shape
+    y = torch.empty((B, H, W), device=x.device, dtype=torch.float32)
+    lib().conv3x3_to1_nhwc(ptr(x), B, H, W, C, ptr(w9c), ptr(bias), ptr(y), stream())
+    return y
+
+
+def merge_masks(src: torch.Tensor, logit_mask: int, suppress: Optional[torch.Tensor], lut: torch.Tensor, single: bool,
+                masks: Optional[torch.Tensor] = None, counts: Optional[torch.Tensor] = None):
+    """src (N,H,W) -> masks (N+1,H,W), labels (H,W) uint8, counts (N) int32."""
+    N, H, W = src.shape
+    masks = masks if masks is not None else torch.empty((N + 1, H, W), device=src.device, dtype=torch.float32)
+    labels = torch.empty((H, W), device=src.device, dtype=torch.uint8)
+    if counts is None:
+        counts = torch.zeros(N, device=src.device, dtype=torch.int32)
+    else:
+        counts.zero_()
+    lib().merge_masks(ptr(src), logit_mask, ptr(suppress), N, H * W, ptr(lut), 1 if single else 0, ptr(masks), ptr(labels),
+                      ptr(counts), stream())
+    return masks, labels, counts
+
+
+def corr3x3(x: torch.Tensor, filt: torch.Tensor, index: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x (NB,c,h,w) NCHW, filt (NF,c,3,3) -> (NB,h,w); sample n uses filter index[n] (default 0)."""
+    NB, c, h, w = x.shape
+    out = torch.empty((NB, h, w), device=x.device, dtype=torch.float32)
+    lib().corr3x3_nchw(ptr(x), ptr(filt), ptr(index), NB, c, h, w, ptr(out), stream())
+    return out
+
+
+def pixel_weights(y: torch.Tensor, tf: float, threshold: bool, return_count: bool = False):
+    """y (K,1,H,W) or (K,H,W) float -> hinge pixel weights of the same shape (and the per-map pixel counts)."""
+    K = y.shape[0]
+    HW = y.shape[-1] * y.shape[-2]
+    w = torch.empty_like(y)
+    ws = torch.empty(K, device=y.device, dtype=torch.float32)
+    lib().pixel_weights(ptr(y), K, HW, float(tf), 1 if threshold else 0, ptr(w), ptr(ws), stream())
+    return (w, ws) if return_count else w
+
+
+def build_stencil(pw: torch.Tensor, y: torch.Tensor, fsize):
+    """pw, y (K,1,H,W) -> stencil (K,9,h,w), uty (K,h,w)."""
+    K = pw.shape[0]
+    H, W = pw.shape[-2:]
+    h, w = int(fsize[0]), int(fsize[1])
+    st = torch.empty((K, 9, h, w), device=pw.device, dtype=torch.float32)
+    uty = torch.empty((K, h, w), device=pw.device, dtype=torch.float32)
+    lib().build_stencil(ptr(pw), ptr(y), K, H, W, h, w, ptr(st), ptr(uty), stream())
+    return st, uty

@@ -204,6 +204,7 @@ def segnet_param_shapes(ft_channels: Dict[str, int], nch: int = 64, in_ch: int =
     def bnorm(key, c):
         for s in ("weight", "bias", "running_mean", "running_var"):
             shp[key + "." + s] = (c,)
+        shp[key + ".num_batches_tracked"] = ()
 
     for L, fc in ft_channels.items():
         conv("TSE.%s.reduce.0" % L, nch, fc, 1)
@@ -236,7 +237,9 @@ def segnet_state_dict(backbone: str = "resnet18", seed: int = 7, gain: float = 1
     g = torch.Generator().manual_seed(seed)
     sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
     for key, shape in segnet_param_shapes(ft_channels).items():
-        if key.endswith("running_var") or (".bblock.1.weight" in key):
+        if key.endswith("num_batches_tracked"):
+            t = torch.zeros((), dtype=torch.int64)
+        elif key.endswith("running_var") or (".bblock.1.weight" in key):
             t = torch.ones(shape)
         elif ".bblock.1." in key:
             t = torch.zeros(shape)

@@ -1,0 +1,178 @@
+/*
+ * frtm_b200.h — C ABI of libfrtm_b200.so: hand-written sm_100a kernels for the FRTM-VOS per-frame inference
+ * hot path (backbone feature pass, target-model correlation, refinement network, mask merge, frame memory and
+ * the online Gauss-Newton / conjugate-gradient filter update).
+ *
+ * The reference (andr345/frtm-vos) has no FFI for this path: every device kernel it runs is an ATen / cuDNN
+ * call made from Python.  Its only native component is lib/_npp/nppig.cpp, whose conventions
+ * this ABI follows (nppig.cpp:48-104): the caller owns and allocates every buffer, inputs are contiguous device
+ * tensors on the current device, work is enqueued on the caller's stream, nothing synchronises, nothing is
+ * retained.  Each entry point below cites the reference call site it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative FRTM_E* code otherwise; frtm_last_error() gives the text
+ *     (thread-local).  No host synchronisation, no allocation, no global state besides the error string and
+ *     one-time cudaFuncSetAttribute calls.
+ *   - all pointers are device pointers unless the name ends in _host; float = IEEE binary32.
+ *   - activations on the conv path are NHWC ("channels last"): element (b,y,x,c) at ((b*H+y)*W+x)*ld + c with a
+ *     channel stride ld >= C (lets a producer write straight into a wider concat buffer).
+ *   - target-model tensors keep the reference's NCHW layout because they are user-visible attributes
+ *     (Discriminator.memory.samples, .current_sample, project/filter weights).
+ *   - stream is a cudaStream_t passed as void*.
+ */
+#ifndef FRTM_B200_H
+#define FRTM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FRTM_OK 0
+#define FRTM_EINVAL (-1)  /* bad argument (shape / alignment / null) */
+#define FRTM_ELAUNCH (-2) /* CUDA launch or runtime failure           */
+#define FRTM_EARCH (-3)   /* device is not sm_100                     */
+
+const char *frtm_last_error(void);
+int frtm_version(void);
+/* Number of kernels this library has launched in this process (bench.py "gpu_launches"). */
+int64_t frtm_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Backbone + refinement-network building blocks  (model/feature_extractor.py:40-68 -> torchvision ResNet,
+ * model/seg_network.py:7-189, lib/utils.py:25-41)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* uint8 NCHW image(s) (B,3,H,W) -> normalised fp32 NHWC (B,H,W,4), 4th channel 0.
+ * Replaces  x = norm_weight * input.float() + norm_bias  (model/feature_extractor.py:27-32,42). */
+int frtm_normalize_u8(const uint8_t *img, int B, int H, int W, float *out_nhwc4, void *stream);
+
+/* Generic 2-D convolution, fp32 NHWC in / fp32 NHWC out, implicit GEMM.
+ *   x      (B,H,W,ldx) using channels [0,Cin), Cin % 4 == 0
+ *   w      packed by frtm_pack_conv_weight layout: [kh][kw*Cin][CoutPad], CoutPad = round_up(Cout,4)
+ *   bias   [Cout] or NULL;  res (B,Ho,Wo,ldr) residual added before the activation, or NULL
+ *   y      (B,Ho,Wo,ldy) written at channel offset y_coff (NULL to skip); y_nchw (B,Cout,Ho,Wo) optional copy
+ *   relu   1 -> max(.,0)
+ * Replaces every nn.Conv2d / folded BatchNorm / residual add / ReLU on the path: torchvision resnet.py:92-105,
+ * 146-163; model/seg_network.py:13-14,29,48-56,138-146; model/discriminator.py:81 (project, batched over
+ * objects by stacking the 1x1 kernels along Cout). */
+int frtm_conv2d_nhwc(const float *x, int B, int H, int W, int Cin, int ldx, const float *w, const float *bias,
+                     const float *res, int ldr, float *y, int ldy, int y_coff, float *y_nchw, int Cout, int kh,
+                     int kw, int stride, int pad, int relu, void *stream);
+
+/* 3x3 / stride 2 / pad 1 max pooling, NHWC (torchvision resnet.py maxpool; feature_extractor.py:53). */
+int frtm_maxpool3x3s2_nhwc(const float *x, int B, int H, int W, int C, float *y, float *y_nchw, void *stream);
+
+/* Bilinear resize (align_corners=False) of an NHWC tensor; writes C channels at offset y_coff of a tensor with
+ * channel stride ldy.  If accumulate != 0 the result is added to y.  (lib/utils.py:33-35, seg_network.py:39,144) */
+int frtm_resize_bilinear_nhwc(const float *x, int B, int H, int W, int C, int ldx, float *y, int Ho, int Wo, int ldy,
+                              int y_coff, int accumulate, void *stream);
+
+/* Fixed x2 bicubic pyramid upsample (replicate pad 2, 4 depthwise 4x4 phases, crop 1) NHWC (B,H,W,C)->(B,2H,2W,C)
+ * (model/seg_network.py:75-126). */
+int frtm_pyrup_bicubic_nhwc(const float *x, int B, int H, int W, int C, float *y, void *stream);
+
+/* Global average pool NHWC (B,H,W,ld)[0,C) -> (B,C)  (seg_network.py:18,34-35). Deterministic two-stage sum. */
+int frtm_global_avgpool_nhwc(const float *x, int B, int HW, int C, int ldx, float *out, float *workspace,
+                             int64_t workspace_bytes, void *stream);
+int64_t frtm_global_avgpool_workspace(int B, int HW, int C);
+
+/* Channel-attention block (seg_network.py:24-41):  gate = sigmoid(W2 relu(W1 [gap(shallow), deep_pool] + b1) + b2)
+ * then out = shallow * gate + deeper (deeper already resized to the shallow size, or a (B,C) vector when
+ * deeper_is_vector).  w1 (C,2C) row-major, w2 (C,C).  shallow_pool/deep_pool are (B,C). */
+int frtm_cab_gate(const float *shallow_pool, const float *deep_pool, const float *w1, const float *b1, const float *w2,
+                  const float *b2, int B, int C, float *gate, void *stream);
+int frtm_cab_apply_nhwc(const float *shallow, const float *gate, const float *deeper, int deeper_is_vector, int B,
+                        int HW, int C, float *out, void *stream);
+
+/* Copy a 1-channel map (B,H,W) into channel `coff` of an NHWC tensor with channel stride ld and zero channels
+ * (coff, coff+nzero] (builds cat(h, score), lib/utils.py:38-41 / seg_network.py:19). */
+int frtm_scatter_channel_nhwc(const float *src, int B, int HW, float *dst, int ld, int coff, int nzero, void *stream);
+/* Replicate an NHWC tensor (F,HW,C) along a new object axis into (F*N,HW,ld)[0,C): out[(f*N+n)] = in[f]. */
+int frtm_broadcast_objects_nhwc(const float *src, int F, int N, int HW, int C, int lds, float *dst, int ldd, void *stream);
+
+/* NHWC (B,HW,ld)[0,C) -> NCHW (B,C,HW). */
+int frtm_nhwc_to_nchw(const float *x, int B, int HW, int C, int ldx, float *y, void *stream);
+
+/* Final 3x3 conv to a single channel (project.conv2, seg_network.py:145): NHWC (B,H,W,C) -> (B,H,W). w [9][C]. */
+int frtm_conv3x3_to1_nhwc(const float *x, int B, int H, int W, int C, const float *w, const float *bias, float *y,
+                          void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Mask merge  (model/tracker.py:143-150, 203-221)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* One frame, N objects -> merged masks (N+1,H,W) [slot 0 = background] and uint8 labels (H,W).
+ *   src (N,H,W): logits for objects whose bit is set in logit_mask (p = sigmoid(logit) * (1 - suppress)), raw
+ *   probabilities (start masks of objects initialised on this frame) for the others;  suppress (H,W) uint8 or NULL;
+ *   clamp ; p_0 = min(1-p_i) ; softmax(p/(1-p)) ; first-occurrence argmax ; masks[i] = softmax_i * (argmax == i);
+ *   labels = lut[argmax of the same rule applied to the merged masks]  (or masks[1] > 0.5 when single_object).
+ * Also adds, per object, the number of pixels with merged mask > 0.5 to counts[N] (the `< 10 px` gate of
+ * model/discriminator.py:214) — counts must be zeroed by the caller.  N <= 64. */
+int frtm_merge_masks(const float *src, uint64_t logit_mask, const uint8_t *suppress, int N, int HW, const uint8_t *lut,
+                     int single_object, float *masks, uint8_t *labels, int *counts, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Target model: correlation, memory, GN/CG  (model/discriminator.py, model/memory.py, model/optimizer.py)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* scores[n] = filter[fidx(n)] (3x3, pad 1, no bias) applied to x[n] : x (NB,c,h,w) NCHW, filt (NF,c,3,3),
+ * filter_index[NB] (NULL -> n).  out (NB,h,w).  (discriminator.py:82,205; also J·p in optimizer.py:156) */
+int frtm_corr3x3_nchw(const float *x, const float *filt, const int *filter_index, int NB, int c, int h, int w,
+                      float *out, void *stream);
+
+/* Hinge pixel weights (discriminator.py:107-152): y (K,H*W) in [0,1] -> w (K,H*W).  If threshold != 0 the map is
+ * first binarised with y > 0.5 (discriminator.py:217).  workspace: K floats. */
+int frtm_pixel_weights(const float *y, int K, int HW, float tf, int threshold, float *w, float *workspace, void *stream);
+
+/* Stencil form of  U^T diag(pw^2) U  and  U^T (pw^2 * y)  for bilinear upsampling U : (h,w)->(H,W),
+ * align_corners=False (discriminator.py:48).  pw,y (K,H,W);  stencil (K,9,h,w) [tap = (dy+1)*3+(dx+1) couples
+ * pixel (i,j) with (i+dy,j+dx)],  uty (K,h,w).  Deterministic gather (no atomics). */
+int frtm_build_stencil(const float *pw, const float *y, int K, int H, int W, int h, int w, float *stencil, float *uty,
+                       void *stream);
+
+/* Device-side sample-weight update + slot choice (memory.py:65-92), predicated on gate_count[0] >= min_px.
+ * state = int[4]: {current_size, previous_replace_ind (-1 = none), last_slot (out, -1 if skipped), num_inserts}. */
+int frtm_memory_next_slot(float *weights, int capacity, float lr, int *state, const int *gate_count, int min_px,
+                          void *stream);
+/* Copy one sample into slot state[2] of the frame memory (skipped when state[2] < 0) (memory.py:48-57). */
+int frtm_memory_insert(const float *feat, int feat_elems, const float *label, const float *pw, int HW,
+                       const float *stencil, const float *uty, int hw, float *mem_samples, float *mem_labels,
+                       float *mem_pw, float *mem_stencil, float *mem_uty, const int *state, void *stream);
+
+/* Filter-only Gauss-Newton / Polak-Ribiere CG update in closed (stencil) form — replaces
+ * GaussNewtonCG.run on the update problem (optimizer.py:55-157, discriminator.py:38-64,221-227):
+ *   residual  r = W (U (X * f) - y),  A p = X^T (U^T W^2 U) X p + reg^2 p,  b = -(X^T U^T W^2 (U X f - y) + reg^2 f)
+ * samples (cap,c,h,w), stencil (cap,9,h,w), uty (cap,h,w), weights (cap) [inactive = 0];
+ * filt (c*9) updated in place;  cg_state = float[2*c*9 + 4]: p | r_prev | rho | has_p — persists across calls
+ * (zero-initialised by the caller);  cg_iters_host[n_gn] CG iterations per GN iteration (host array);
+ * the update is applied only if gate_count == NULL or gate_count[0] >= min_px (device-side predicate, replaces the
+ * host sync of discriminator.py:214).  workspace from frtm_gn_update_workspace.  No host synchronisation. */
+int frtm_gn_update(const float *samples, const float *stencil, const float *uty, const float *weights, int cap, int c,
+                   int h, int w, float *filt, float *cg_state, const int *cg_iters_host, int n_gn, float reg,
+                   float precond, float forget, const int *gate_count, int min_px, float *workspace,
+                   int64_t workspace_bytes, void *stream);
+int64_t frtm_gn_update_workspace(int cap, int c, int h, int w);
+
+/* Joint (project, filter) Gauss-Newton / CG of Discriminator.init (discriminator.py:154-175; optimizer.py:55-157):
+ *   s = F * (P x),  J[dP,dF] = F * (dP x) + dF * (P x)  on the low-resolution grid, normal equations through the
+ *   same stencil form.  x_nhwc (K,h,w,C) raw backbone features, stencil (K,9,h,w), uty (K,h,w), sw (K);
+ *   P (c,C) = project.weight, F (c*9) = filter.weight, both updated in place.  Fresh CG state per call. */
+int frtm_gn_init(const float *x_nhwc, const float *stencil, const float *uty, const float *sw, int K, int C, int c, int h,
+                 int w, float *P, float *F, const int *cg_iters_host, int n_gn, float regP, float regF, float precondP,
+                 float precondF, float forget, float *workspace, int64_t workspace_bytes, void *stream);
+int64_t frtm_gn_init_workspace(int K, int C, int c, int h, int w);
+/* Teacher-forced probe of the joint problem at (P,F): out_b = -(J^T r0 + reg^2 theta), out_A = J^T J d + reg^2 d. */
+int frtm_gn_init_probe(const float *x_nhwc, const float *stencil, const float *uty, const float *sw, int K, int C, int c,
+                       int h, int w, float *P, float *F, const float *dP, const float *dF, float regP, float regF,
+                       float *out_bP, float *out_bF, float *out_AP, float *out_AF, float *workspace,
+                       int64_t workspace_bytes, void *stream);
+/* v[n] = sw[n] * (S[n] s[n] - use_y * uty[n])   9-tap spatially varying stencil, all (NB,h,w). */
+int frtm_stencil_apply(const float *stencil, const float *s, const float *uty, const float *sw, int NB, int h, int w,
+                       int use_y, float *v, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRTM_B200_H */

@@ -1,0 +1,195 @@
+"""-m gpu: model-level parity (SURVEY.md §4 protocol).
+
+P1  feed-forward at fixed state: backbone maps, projected sample, scores, logits <= 1e-3, labels identical
+P4  end-to-end oracle-replay: post-init target-model state injected from the oracle, then the whole sequence
+P5  end-to-end free-running: functional agreement with the oracle (init is chaotic at ulp level, finding 8)
+The oracle (oracle/frtm_ref.py) runs live on the box's CPU on the same seeded inputs; the P1 case is also checked
+against the committed fixture produced by the executed reference."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import golden_inputs as GI
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _build(arch, bb, seg, dp):
+    from frtm_vos_b200.model.feature_extractor import ResnetFeatureExtractor
+    from frtm_vos_b200.model.seg_network import SegNetwork
+    from frtm_vos_b200.model.tracker import Tracker
+    from frtm_vos_b200.model.augmenter import ImageAugmenter
+    fe = ResnetFeatureExtractor(arch, state_dict=bb).to(DEV)
+    chans = fe.get_out_channels()
+    refiner = SegNetwork(1, 64, {L: c for L, c in chans.items() if L in ("layer5", "layer4", "layer3", "layer2")}, True)
+    trk = Tracker(ImageAugmenter(GI.AUG_PARAMS), fe, dict(dp, device=DEV), refiner, DEV)
+    missing = trk.load_state_dict(seg)
+    trk.to(DEV)
+    return trk, fe
+
+
+@pytest.mark.parametrize("arch", ["resnet18"])
+def test_P1_feedforward_fixed_state(arch, golden):
+    from oracle import frtm_ref as R
+    from frtm_vos_b200 import ops
+    case = GI.feedforward_case(arch)
+    C = case["PF"][0][0].shape[1]
+    trk, fe = _build(arch, case["bb"], case["seg"], GI.disc_params(C))
+    img = case["image"]
+    feats = fe(img.to(DEV))
+    ref = R.backbone_features(case["bb"], arch, img)
+    g = golden("feedforward_" + arch)
+    for L in ("layer1", "layer2", "layer3", "layer4", "layer5"):
+        d = (feats[L].cpu() - ref[L]).abs().max().item()
+        assert d < 2e-4 * max(1.0, ref[L].abs().max().item()), (L, d)
+        assert torch.equal(feats[L].cpu(), feats.nhwc[L].permute(0, 3, 1, 2).cpu())
+    assert np.abs(feats["layer4"].cpu().numpy() - g["ft_layer4"]).max() < 2e-4 * max(1.0, np.abs(g["ft_layer4"]).max())
+    seg = GI.strip_prefix(case["seg"])
+    logits_all = []
+    for i, (P, Fw) in enumerate(case["PF"]):
+        s_ref = F.conv2d(F.conv2d(ref["layer4"], P), Fw, None, 1, 1)
+        cft = ops.conv2d(feats.nhwc["layer4"], ops.pack_conv(P, device=DEV), nchw=True, nhwc=False)
+        s = ops.corr3x3(cft, Fw.to(DEV)).unsqueeze(1)
+        assert (s.cpu() - s_ref).abs().max() < 1e-4
+        lg = trk.refiner(s, feats, img.shape[-2:])
+        lg_ref = R.seg_forward(seg, s_ref, ref, img.shape[-2:])
+        err = (lg.cpu() - lg_ref).abs().max().item()
+        assert err < 1e-3, ("logits", i, err)                                   # north-star tolerance
+        assert np.abs(lg.cpu().numpy() - g["logits%d" % i]).max() < 1e-3        # vs the executed reference
+        logits_all.append((lg, lg_ref))
+    # merged labels identical
+    lut = torch.tensor([0, 1, 2], dtype=torch.uint8)
+    src = torch.cat([l[0][0] for l in logits_all], 0)
+    masks, labels, _ = ops.merge_masks(src.contiguous(), 0b11, None, lut.to(DEV), False)
+    cm = torch.zeros(3, *img.shape[-2:])
+    for i, l in enumerate(logits_all):
+        cm[i + 1] = torch.sigmoid(l[1][0, 0])
+    merged_ref = R.merge_masks(cm)
+    labels_ref = R.labels_from_masks(merged_ref.clone(), lut, False)
+    assert torch.equal(labels.cpu(), labels_ref)                                 # bit-exact argmax label map
+    assert (masks.cpu() - merged_ref).abs().max() < 1e-3
+
+
+def test_P1_batched_objects_and_frames_match_single():
+    """The batched path (objects x frames in one pass) must give bit-identical logits to batch 1."""
+    from frtm_vos_b200 import ops
+    case = GI.feedforward_case("resnet18")
+    trk, fe = _build("resnet18", case["bb"], case["seg"], GI.disc_params(256))
+    from frtm_vos_b200 import synth
+    seq = synth.SyntheticSequence(num_objects=2, num_frames=3, size=GI.MID, seq_id=9)
+    imgs = torch.stack([seq[t][0] for t in range(3)]).to(DEV)
+    nhwc, _ = fe.forward_nhwc(imgs)
+    g = torch.Generator().manual_seed(0)
+    scores = torch.randn(6, *nhwc["layer4"].shape[1:3], generator=g).to(DEV)       # 3 frames x 2 objects
+    lg = trk.refiner.forward_nhwc(scores, nhwc, GI.MID)
+    for f in range(3):
+        single, _ = fe.forward_nhwc(imgs[f:f + 1])
+        for n in range(2):
+            one = trk.refiner.forward_nhwc(scores[f * 2 + n:f * 2 + n + 1], single, GI.MID)
+            assert torch.equal(one[0], lg[f * 2 + n])
+
+
+def _oracle_tracker(bb, seg, dp, hooks=None):
+    from oracle import frtm_ref as R
+    from frtm_vos_b200.model.augmenter import ImageAugmenter
+    return R.TrackerRef(bb, "resnet18", seg, GI.oracle_disc_params(dp), ImageAugmenter(GI.AUG_PARAMS).augment_first_frame,
+                        "cpu", hooks=hooks)
+
+
+def _e2e_setup(n_frames=18):
+    from frtm_vos_b200 import synth
+    size = GI.MID
+    bb = synth.backbone_state_dict("resnet18", size=size)
+    seg = synth.segnet_state_dict("resnet18")
+    dp = GI.disc_params(256)
+    seq = synth.SyntheticSequence(num_objects=2, num_frames=n_frames, size=size, seq_id=3)
+    return bb, seg, dp, seq, size
+
+
+def test_P4_end_to_end_oracle_replay():
+    """Inject each object's post-init (P, F, memory, CG state) from the oracle, then run the sequence: logits within
+    1e-3 and identical label maps on every frame, through two GN updates per object."""
+    from frtm_vos_b200 import ops
+    bb, seg, dp, seq, size = _e2e_setup()
+    dump = {"state": {}, "logits": {}}
+
+    def after_init(oid, tm):
+        dump["state"][oid] = dict(P=tm.P.clone(), F=tm.F.clone(), samples=tm.memory.samples.clone(),
+                                  labels=tm.memory.labels.clone(), pw=tm.memory.pixel_weights.clone(),
+                                  weights=tm.memory.weights.clone(), p=tm.optimizer.p[0].clone(),
+                                  r_prev=tm.optimizer.r_prev[0].clone(), rho=tm.optimizer.rho.clone())
+
+    def on_logits(frame, oid, s, lg):
+        dump["logits"][(frame, oid)] = lg.clone()
+
+    orc = _oracle_tracker(bb, seg, dp, hooks=dict(after_init=after_init, logits=on_logits))
+    torch.manual_seed(11)
+    out_ref, _ = orc.run_sequence(seq)
+
+    trk, fe = _build("resnet18", bb, seg, dp)
+    got_logits = {}
+    orig_fwd = trk.refiner.forward_nhwc
+
+    def spy(scores, feats, im_size):
+        lg = orig_fwd(scores, feats, im_size)
+        got_logits[trk.current_frame] = lg.clone()
+        return lg
+
+    trk.refiner.forward_nhwc = spy
+    orig_init = trk.initialize
+
+    def init_and_inject(image, labels, new_objects):
+        r = orig_init(image, labels, new_objects)
+        for oid in new_objects:
+            st, d = dump["state"][oid], trk.targets[oid].discriminator
+            d.project.weight.data.copy_(st["P"]); d.filter.weight.data.copy_(st["F"])
+            m = d.memory
+            m.samples.copy_(st["samples"]); m.labels.copy_(st["labels"]); m.pixel_weights.copy_(st["pw"])
+            m.weights.copy_(st["weights"])
+            sten, uty = ops.build_stencil(m.pixel_weights[:5], m.labels[:5], m.samples.shape[-2:])
+            m.stencil[:5] = sten; m.uty[:5] = uty
+            d.update_optimizer.set_state(st["p"].to(DEV), st["r_prev"].to(DEV), float(st["rho"]))
+        trk._stack = None
+        return r
+
+    trk.initialize = init_and_inject
+    torch.manual_seed(11)
+    out, fps = trk.run_sequence(seq)
+    worst = 0.0
+    for (frame, oid), lg_ref in dump["logits"].items():
+        lg = got_logits[frame][seq.obj_ids.index(oid)].cpu()
+        worst = max(worst, (lg - lg_ref[0, 0]).abs().max().item())
+    assert worst < 1e-3, worst
+    for i, (a, b) in enumerate(zip(out, out_ref)):
+        assert torch.equal(a.reshape(size).cpu(), b.reshape(size)), "labels differ on frame %d" % i
+    for oid in seq.obj_ids:
+        d, m = trk.targets[oid].discriminator, orc.targets[oid]["model"]
+        assert (d.filter.weight.cpu() - m.F).abs().max() < 1e-4
+        assert torch.allclose(d.memory.weights.cpu(), m.memory.weights, atol=1e-6)
+        assert d.memory.previous_replace_ind == m.memory.prev_ind and d.memory.current_size == m.memory.size
+
+
+def test_P5_end_to_end_free_running():
+    bb, seg, dp, seq, size = _e2e_setup()
+    orc = _oracle_tracker(bb, seg, dp)
+    torch.manual_seed(11)
+    out_ref, _ = orc.run_sequence(seq)
+    trk, fe = _build("resnet18", bb, seg, dp)
+    torch.manual_seed(11)
+    out, fps = trk.run_sequence(seq)
+    a = torch.stack([o.reshape(size).cpu() for o in out])
+    b = torch.stack([o.reshape(size) for o in out_ref])
+    assert torch.equal(a[0], b[0])
+    agree = (a == b).float().mean().item()
+    assert agree > 0.97, agree
+    assert trk.targets[1].discriminator.memory.current_size == orc.targets[1]["model"].memory.size
+
+
+def test_no_cpu_fallback():
+    from frtm_vos_b200.model.feature_extractor import ResnetFeatureExtractor
+    from frtm_vos_b200 import synth
+    fe = ResnetFeatureExtractor("resnet18", state_dict=synth.backbone_state_dict("resnet18", size=GI.SMALL))
+    with pytest.raises(RuntimeError):
+        fe.to("cpu")

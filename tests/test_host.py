@@ -1,0 +1,115 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol the header declares, host-side containers and
+data generators behave, and (build container only) the host-side augmenter reproduces the reference's."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import golden_inputs as GI
+
+
+def test_library_exports_every_declared_symbol():
+    from frtm_vos_b200 import _lib
+    protos = _lib.parse_header()
+    assert len(protos) >= 25
+    cdll = ctypes.CDLL(_lib.LIB_PATH)
+    for name in protos:
+        assert hasattr(cdll, name), "libfrtm_b200.so does not export %s" % name
+    L = _lib.lib()
+    assert L.version() >= 100
+    assert L.launch_count() == 0            # nothing may have launched on a CPU-only host
+
+
+def test_header_cites_reference_and_is_plain_c():
+    src = open(os.path.join(os.path.dirname(__file__), "..", "include", "frtm_b200.h")).read()
+    assert 'extern "C"' in src and "torch" not in src.replace("pytorch", "").lower().replace("torchvision", "")
+    for cite in ("model/discriminator.py", "model/optimizer.py", "model/memory.py", "model/tracker.py",
+                 "model/seg_network.py", "model/feature_extractor.py", "nppig.cpp"):
+        assert cite in src, cite
+
+
+def test_product_fails_loudly_without_cuda():
+    from frtm_vos_b200 import ops
+    if torch.cuda.is_available():
+        pytest.skip("GPU host")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ops.normalize_u8(torch.zeros(1, 3, 8, 8, dtype=torch.uint8))
+    from frtm_vos_b200.model.feature_extractor import ResnetFeatureExtractor
+    from frtm_vos_b200 import synth
+    fe = ResnetFeatureExtractor("resnet18", state_dict=synth.backbone_state_dict("resnet18", size=GI.SMALL))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        fe.to("cpu")
+
+
+def test_product_does_not_import_oracle():
+    import subprocess, sys
+    code = ("import sys; import frtm_vos_b200.model.tracker, frtm_vos_b200.model.seg_network, frtm_vos_b200.ops; "
+            "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), 'oracle imported'")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run([sys.executable, "-c", code], check=True, cwd=root)
+
+
+def test_tensorlist_semantics():
+    from frtm_vos_b200.lib.tensorlist import TensorList
+    a = TensorList([torch.arange(3.0) + 1, torch.ones(2) * 2])
+    b = TensorList([torch.ones(3) * 3, torch.ones(2) * 5])
+    assert torch.equal((a * b)[0], torch.tensor([3.0, 6.0, 9.0]))
+    assert torch.equal((2.0 - a)[1], torch.zeros(2))
+    assert float(sum(a.view(-1) @ b.view(-1))) == 38.0
+    assert isinstance(a[0:1], TensorList) and torch.is_tensor(a[0])
+    c = a.clone()
+    c += b
+    c /= 2
+    assert torch.equal(c[1], torch.ones(2) * 3.5) and torch.equal(a[1], torch.ones(2) * 2)
+    assert not hasattr(a, "__torch_function__")
+    with pytest.raises(AttributeError):
+        a.not_a_tensor_method
+    assert torch.equal((-a)[0], -(torch.arange(3.0) + 1))
+    assert len(a.concat(b)) == 4 and len(TensorList([a, b]).unroll()) == 4
+
+
+def test_synthetic_sequence_protocol():
+    from frtm_vos_b200 import synth
+    seq = synth.SyntheticSequence(num_objects=3, num_frames=5, size=GI.SMALL, seq_id=2)
+    assert len(seq) == 5 and seq.obj_ids == [1, 2, 3] and len(seq.frame_names) == 5
+    im, lb, new = seq[0]
+    assert im.dtype == torch.uint8 and im.shape == (3, *GI.SMALL) and lb.shape == (1, *GI.SMALL) and new == [1, 2, 3]
+    assert set(lb.unique().tolist()) == {0, 1, 2, 3}
+    im1, lb1, new1 = seq[1]
+    assert lb1 == [] and new1 == []
+    again = synth.SyntheticSequence(num_objects=3, num_frames=5, size=GI.SMALL, seq_id=2)
+    assert torch.equal(again[3][0], seq[3][0])
+    late = synth.SyntheticSequence(num_objects=2, num_frames=5, size=GI.SMALL, seq_id=2, start_frames=[0, 2])
+    assert late[0][2] == [1] and late[2][2] == [2] and set(late[2][1].unique().tolist()) <= {0, 2}
+    sd = synth.segnet_state_dict("resnet18")
+    assert len(sd) == 140 and sd["refiner.TSE.layer4.reduce.0.weight"].shape[1] == 256
+
+
+def test_conv_weight_packing_layout():
+    from frtm_vos_b200 import ops
+    w = torch.arange(2 * 3 * 3 * 3, dtype=torch.float32).reshape(2, 3, 3, 3)
+    pc = ops.pack_conv(w, torch.tensor([1.0, 2.0]), device="cpu")
+    assert pc.w.shape == (3, 3 * 4, 4) and pc.cin_pad == 4
+    assert pc.w[1, 2 * 4 + 1, 1] == w[1, 1, 1, 2] and pc.w[0, 3, 0] == 0
+    bn = dict(weight=torch.tensor([2.0, 1.0]), bias=torch.tensor([0.5, 0.0]), running_mean=torch.tensor([1.0, 0.0]),
+              running_var=torch.tensor([4.0, 1.0]))
+    pc2 = ops.pack_conv(w, None, bn=bn, device="cpu", eps=0.0)
+    assert torch.allclose(pc2.w[0, 0, 0], w[0, 0, 0, 0] * 1.0) and torch.allclose(pc2.bias, torch.tensor([-0.5, 0.0]))
+
+
+@pytest.mark.needs_reference
+def test_augmenter_matches_reference():
+    from oracle import shims
+    from frtm_vos_b200 import synth
+    from frtm_vos_b200.model.augmenter import ImageAugmenter
+    ref = shims.load_reference()
+    seq = synth.SyntheticSequence(num_objects=2, num_frames=1, size=GI.MID, seq_id=5)
+    im, lb, _ = seq[0]
+    mask = (lb == 2).byte()
+    np.random.seed(0); torch.manual_seed(0)
+    a_im, a_lb = ref.augmenter.ImageAugmenter(ref.EasyDict(GI.AUG_PARAMS)).augment_first_frame(im, mask)
+    np.random.seed(0); torch.manual_seed(0)
+    b_im, b_lb = ImageAugmenter(GI.AUG_PARAMS).augment_first_frame(im, mask)
+    assert torch.equal(a_im, b_im) and torch.equal(a_lb, b_lb) and a_im.shape[0] == 5
