@@ -323,11 +323,13 @@ using namespace frtm;
 
 extern "C" int frtm_normalize_u8(const uint8_t *img, int B, int H, int W, float *out, void *stream) {
   FRTM_REQUIRE(img && out && B > 0 && H > 0 && W > 0, "normalize: bad arguments");
-  // constants rounded exactly like the reference: (1/255)/std and (-mean)/std in fp32
+  // constants rounded exactly like the reference: `1 / 255 / stds` is evaluated by torch as reciprocal(stds) * (1/255),
+  // `-means / stds` as a true division, both in fp32
   const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
   float s[3], b[3];
   for (int i = 0; i < 3; ++i) {
-    s[i] = (float)(1.0 / 255.0) / stdv[i];
+    volatile float rcp = 1.0f / stdv[i];
+    s[i] = rcp * (float)(1.0 / 255.0);
     b[i] = -mean[i] / stdv[i];
   }
   const int64_t HW = (int64_t)H * W, total = HW * B;

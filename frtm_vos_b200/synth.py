@@ -5,8 +5,8 @@ Nothing here is on the compute path: these are *data generators* used by
 the oracle and (in the build container) the real reference all read the same
 tensors.  Three generators:
 
-* :class:`SyntheticSequence` — textured moving objects over a rolling smooth
-  background, implementing the sequence protocol the reference driver consumes
+* :class:`SyntheticSequence` — smoothly textured, colour-tinted moving objects over a
+  rolling smooth background, implementing the sequence protocol the reference driver consumes
   (``lib/datasets.py:16-69``: ``name``, ``obj_ids``, ``frame_names``, ``len``,
   ``[i] -> (image u8 (3,H,W), labels u8 (1,H,W) | [], new_obj_ids)``,
   ``preload(device)``).
@@ -26,6 +26,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 import torch.nn.functional as F
 
+_PALETTE = torch.tensor([[0.9, 0.2, 0.2], [0.2, 0.8, 0.3], [0.2, 0.3, 0.9], [0.9, 0.8, 0.2], [0.8, 0.2, 0.8], [0.2, 0.8, 0.8]])
 BACKBONE_BLOCKS = {"resnet18": ("basic", (2, 2, 2, 2)), "resnet101": ("bottleneck", (3, 4, 23, 3))}
 
 
@@ -74,7 +75,12 @@ class SyntheticSequence:
             cy = (k // cols + 0.5) * ch
             vel = (torch.rand(2, generator=gk) * 6.0 - 3.0).tolist()
             ellipse = bool(k % 2)
-            tex = 0.5 * torch.rand(3, oh, ow, generator=gk) + 0.25
+            # smooth texture (noise on a 16-px grid) tinted with a per-object colour: a random-init backbone is not
+            # shift-invariant at stride 16, so per-pixel noise textures do not survive a 2-3 px motion (measured:
+            # score IoU 0.95 -> 0.30 one frame after init); this recipe keeps IoU 0.87-0.95 over 16 frames.
+            coarse_t = torch.rand(1, 3, max(oh // 16, 2), max(ow // 16, 2), generator=gk)
+            smooth = F.interpolate(coarse_t, (oh, ow), mode="bilinear", align_corners=False)[0]
+            tex = 0.7 * (0.5 * smooth + 0.25) + 0.3 * _PALETTE[k % len(_PALETTE)].view(3, 1, 1)
             yy = (torch.arange(oh).float() + 0.5) / oh * 2 - 1
             xx = (torch.arange(ow).float() + 0.5) / ow * 2 - 1
             shape = ((yy[:, None] ** 2 + xx[None, :] ** 2) <= 1.0) if ellipse else torch.ones(oh, ow, dtype=torch.bool)
