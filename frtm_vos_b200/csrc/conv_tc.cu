@@ -1,0 +1,399 @@
+// Tensor-core convolution for sm_100a: tcgen05.mma (kind::f16) with fp32 accumulation in TMEM, operands staged in
+// shared memory by TMA (activations: 4-D tiled tensor maps with zero OOB fill = the conv's zero padding; weights:
+// pre-swizzled tiles fetched with one bulk async copy), mbarrier producer/consumer pipeline, warp-specialised roles.
+//
+// Precision: the reference computes these convs in fp32 and the parity budget is 1e-3 on the logits, which no single
+// fp16/bf16/tf32 pass meets.  Operands are therefore split x = hi + lo (two fp16 planes, x pre-scaled
+// by 2^4, weights pre-scaled per output channel by a power of two so `lo` stays out of the fp16 subnormals) and each
+// k-step issues three MMAs into the same accumulator:  hi*hi + hi*lo + lo*hi  (the lo*lo term is < 2^-22 relative).
+// The epilogue undoes the power-of-two scales exactly, adds bias / residual, applies ReLU and writes fp32 NHWC and/or
+// the split planes for the next conv and/or an NCHW copy.
+//
+// GEMM view per CTA: D[128 pixels (8x16 spatial tile), BN couts] += A[128, 64] * B[64, BN] per (filter tap, 64-channel
+// chunk).  Stride-1 "same" convolutions only (1x1 and 3x3 here); everything else stays on conv_simt.cu.
+#include "common.cuh"
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+namespace frtm {
+
+constexpr int TC_TH = 8, TC_TW = 16;          // spatial tile -> 128 GEMM rows
+constexpr int TC_BK = 64;                     // fp16 elements per k-block = one 128-byte swizzle row
+constexpr int TC_A_BYTES = 128 * 128;         // one A plane tile (128 rows x 128 B)
+constexpr float TC_ACT_SCALE = 16.f;
+
+struct TcArgs {
+  const __half *wt;        // [ntile][tap][kchunk][hi|lo][BN rows x 128 B, SW128 image]
+  const float *oscale;     // [CoutPad] = 1 / (act_scale * weight_scale[n])   (exact powers of two)
+  const float *bias;       // [Cout] or null
+  const float *res;        // fp32 NHWC residual or null
+  const __half *res_hi, *res_lo;  // or split residual (scaled by TC_ACT_SCALE), channel stride ldrh
+  float *y;                // fp32 NHWC out (ldy, y_coff) or null
+  float *y_nchw;           // or null
+  __half *y_hi, *y_lo;     // split out planes (channel stride ldyh, offset yh_coff) or null
+  int ldr, ldrh, ldy, y_coff, ldyh, yh_coff;
+  int B, H, W, Cout, kh, kw, pad, relu, tiles_x, tiles_y, kchunks;
+};
+
+// ----------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ----------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug must surface as a trapped launch, not as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  printf("frtm conv_tc: mbarrier wait timed out (block %d,%d thread %d bar 0x%x parity %u)\n", blockIdx.x, blockIdx.y,
+         threadIdx.x, bar, parity);
+  __trap();
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 UMMA): start>>4 | SBO=1024B (8 rows x 128 B) |
+// version=1 | layout=SWIZZLE_128B(2).  LBO is unused for swizzled K-major operands.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__host__ __device__ constexpr int tmem_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
+
+// ----------------------------------------------------------------------------------------------------------------
+// kernel: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue (warp 2 owns the TMEM allocation)
+// ----------------------------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi,
+                                                      const __grid_constant__ CUtensorMap tm_lo, const TcArgs a) {
+  constexpr int B_BYTES = BN * 128;
+  constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
+  constexpr int COLS = tmem_cols(BN);
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar_full = base + STAGES * STAGE_BYTES;       // STAGES x 8 B
+  const uint32_t bar_empty = bar_full + 8 * STAGES;
+  const uint32_t bar_accum = bar_empty + 8 * STAGES;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gen + STAGES * STAGE_BYTES + 16 * STAGES + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_img = a.tiles_x * a.tiles_y;
+  const int b = blockIdx.x / tiles_per_img;
+  const int tr = blockIdx.x - b * tiles_per_img;
+  const int y0 = (tr / a.tiles_x) * TC_TH, x0 = (tr % a.tiles_x) * TC_TW;
+  const int ntile = blockIdx.y;
+  const int ntaps = a.kh * a.kw;
+  const int nkb = ntaps * a.kchunks;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_hi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_lo)) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_accum, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const __half *wbase = a.wt + (size_t)ntile * nkb * (2 * B_BYTES / 2);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
+        const int tap = kb / a.kchunks, kc = kb - tap * a.kchunks;
+        const int ky = tap / a.kw, kx = tap - ky * a.kw;
+        const uint32_t sa = base + s * STAGE_BYTES;
+        tma_load_4d(sa, &tm_hi, kc * TC_BK, x0 + kx - a.pad, y0 + ky - a.pad, b, bar_full + 8 * s);
+        tma_load_4d(sa + TC_A_BYTES, &tm_lo, kc * TC_BK, x0 + kx - a.pad, y0 + ky - a.pad, b, bar_full + 8 * s);
+        bulk_load(sa + 2 * TC_A_BYTES, wbase + (size_t)kb * (2 * B_BYTES / 2), 2 * B_BYTES, bar_full + 8 * s);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(128, BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(bar_full + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t sa = base + s * STAGE_BYTES;
+        const uint64_t a_hi = umma_desc(sa), a_lo = umma_desc(sa + TC_A_BYTES);
+        const uint64_t b_hi = umma_desc(sa + 2 * TC_A_BYTES), b_lo = umma_desc(sa + 2 * TC_A_BYTES + B_BYTES);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          const uint64_t adv = (uint64_t)(k * 32 >> 4);     // +32 bytes along K inside the swizzle atom
+          umma_f16(tmem_base, a_hi + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
+          umma_f16(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
+          umma_f16(tmem_base, a_lo + adv, b_hi + adv, idesc, 1u);
+        }
+        umma_commit(bar_empty + 8 * s);     // frees the stage once the MMAs above have consumed it
+      }
+      umma_commit(bar_accum);               // accumulator complete
+    }
+  } else {
+    // ---- epilogue: TMEM lane = tile row = pixel; a warp may only touch lanes 32*(warp%4) .. +31 ----
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int py = y0 + row / TC_TW, px = x0 + row % TC_TW;
+    const bool valid = py < a.H && px < a.W;
+    const int64_t pix = ((int64_t)b * a.H + py) * a.W + px;
+    mbar_wait(bar_accum, 0);
+    tc_fence_after();
+    const int n0 = ntile * BN;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      float v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      if (!valid) continue;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int n = n0 + c0 + j;
+        float o = v[j] * a.oscale[n];
+        if (n < a.Cout) {
+          if (a.bias) o += a.bias[n];
+          if (a.res) o += a.res[pix * a.ldr + n];
+          if (a.res_hi)
+            o += (__half2float(a.res_hi[pix * a.ldrh + n]) + __half2float(a.res_lo[pix * a.ldrh + n])) * (1.f / TC_ACT_SCALE);
+          if (a.relu) o = fmaxf(o, 0.f);
+        } else {
+          o = 0.f;
+        }
+        v[j] = o;
+      }
+      if (a.y) {
+        float *dst = a.y + pix * a.ldy + a.y_coff + n0 + c0;
+        if (n0 + c0 + 16 <= a.Cout && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4 *>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (n0 + c0 + j < a.Cout) dst[j] = v[j];
+        }
+      }
+      if (a.y_hi) {
+        __half *dh = a.y_hi + pix * a.ldyh + a.yh_coff + n0 + c0, *dl = a.y_lo + pix * a.ldyh + a.yh_coff + n0 + c0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (n0 + c0 + j < a.Cout) {
+            const float s = v[j] * TC_ACT_SCALE;
+            const __half h = __float2half_rn(s);
+            dh[j] = h;
+            dl[j] = __float2half_rn(s - __half2float(h));
+          }
+        }
+      }
+      if (a.y_nchw) {
+        const int64_t hw = (int64_t)a.H * a.W, p = (int64_t)py * a.W + px;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (n0 + c0 + j < a.Cout) a.y_nchw[((int64_t)b * a.Cout + n0 + c0 + j) * hw + p] = v[j];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(COLS) : "memory");
+  }
+}
+
+// fp32 NHWC (ldx) -> two fp16 planes hi/lo of x * 2^4 (channel stride ldh)
+__global__ void split_kernel(const float *__restrict__ x, int64_t npix, int C, int ldx, __half *__restrict__ hi,
+                             __half *__restrict__ lo, int ldh) {
+  const int C4 = C / 4;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix * C4) return;
+  const int64_t p = i / C4;
+  const int c = (int)(i - p * C4) * 4;
+  const float4 v = *reinterpret_cast<const float4 *>(x + p * ldx + c);
+  const float s[4] = {v.x * TC_ACT_SCALE, v.y * TC_ACT_SCALE, v.z * TC_ACT_SCALE, v.w * TC_ACT_SCALE};
+  __half h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    h[j] = __float2half_rn(s[j]);
+    l[j] = __float2half_rn(s[j] - __half2float(h[j]));
+  }
+  *reinterpret_cast<uint2 *>(hi + p * ldh + c) = *reinterpret_cast<uint2 *>(h);
+  *reinterpret_cast<uint2 *>(lo + p * ldh + c) = *reinterpret_cast<uint2 *>(l);
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int make_act_map(CUtensorMap *tm, const __half *ptr, int B, int H, int W, int C, int ld) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("conv_tc: cuTensorMapEncodeTiled entry point not available"); return FRTM_ELAUNCH; }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
+  cuuint32_t box[4] = {TC_BK, TC_TW, TC_TH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half *>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return FRTM_ELAUNCH; }
+  return FRTM_OK;
+}
+
+template <int BN, int STAGES>
+static int launch_tc(const CUtensorMap &mh, const CUtensorMap &ml, const TcArgs &a, dim3 grid, cudaStream_t st) {
+  constexpr int smem = STAGES * (2 * TC_A_BYTES + 2 * BN * 128) + 16 * STAGES + 16 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return FRTM_ELAUNCH; }
+    configured = true;
+  }
+  conv_tc_kernel<BN, STAGES><<<grid, 192, smem, st>>>(mh, ml, a);
+  FRTM_CHECK_LAUNCH("conv_tc");
+  return FRTM_OK;
+}
+
+}  // namespace frtm
+
+using namespace frtm;
+
+extern "C" int frtm_split_f16(const float *x, int64_t npix, int C, int ldx, void *hi, void *lo, int ldh, void *stream) {
+  FRTM_REQUIRE(x && hi && lo && C % 4 == 0 && ldx % 4 == 0 && ldh % 8 == 0, "split_f16: bad arguments");
+  const int64_t total = npix * (C / 4);
+  split_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, npix, C, ldx, (__half *)hi, (__half *)lo, ldh);
+  FRTM_CHECK_LAUNCH("split_f16");
+  return FRTM_OK;
+}
+
+extern "C" int frtm_conv2d_tc(const void *x_hi, const void *x_lo, int B, int H, int W, int Cin, int ldx, const void *wt,
+                              const float *oscale, int bn_tile, const float *bias, const float *res, int ldr,
+                              const void *res_hi, const void *res_lo, int ldrh, float *y, int ldy, int y_coff, float *y_nchw,
+                              void *y_hi, void *y_lo, int ldyh, int yh_coff, int Cout, int kh, int kw, int relu,
+                              void *stream) {
+  FRTM_REQUIRE(x_hi && x_lo && wt && oscale && (y || y_nchw || y_hi), "conv2d_tc: null pointer");
+  FRTM_REQUIRE(Cin % TC_BK == 0 && ldx % 8 == 0, "conv2d_tc: Cin must be a multiple of 64 and ldx of 8 (got %d, %d)", Cin, ldx);
+  FRTM_REQUIRE(kh == kw && (kh == 1 || kh == 3), "conv2d_tc: only 1x1 and 3x3 stride-1 'same' convolutions");
+  FRTM_REQUIRE((reinterpret_cast<uintptr_t>(x_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(x_lo) & 15) == 0 &&
+               (reinterpret_cast<uintptr_t>(wt) & 15) == 0, "conv2d_tc: operands must be 16-byte aligned");
+  FRTM_REQUIRE(!y_hi || (y_lo && ldyh % 2 == 0), "conv2d_tc: bad split output");
+  CUtensorMap mh, ml;
+  int rc = make_act_map(&mh, (const __half *)x_hi, B, H, W, Cin, ldx);
+  if (rc) return rc;
+  rc = make_act_map(&ml, (const __half *)x_lo, B, H, W, Cin, ldx);
+  if (rc) return rc;
+  TcArgs a;
+  a.wt = (const __half *)wt; a.oscale = oscale; a.bias = bias; a.res = res; a.res_hi = (const __half *)res_hi;
+  a.res_lo = (const __half *)res_lo; a.y = y; a.y_nchw = y_nchw; a.y_hi = (__half *)y_hi; a.y_lo = (__half *)y_lo;
+  a.ldr = ldr; a.ldrh = ldrh; a.ldy = ldy; a.y_coff = y_coff; a.ldyh = ldyh; a.yh_coff = yh_coff;
+  a.B = B; a.H = H; a.W = W; a.Cout = Cout; a.kh = kh; a.kw = kw; a.pad = kh / 2; a.relu = relu;
+  a.tiles_x = cdiv(W, TC_TW); a.tiles_y = cdiv(H, TC_TH); a.kchunks = Cin / TC_BK;
+  const int ntiles_n = cdiv(Cout, bn_tile);
+  dim3 grid((unsigned)(B * a.tiles_x * a.tiles_y), (unsigned)ntiles_n);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (bn_tile) {
+    case 32: return launch_tc<32, 2>(mh, ml, a, grid, st);
+    case 64: return launch_tc<64, 2>(mh, ml, a, grid, st);
+    case 80: return launch_tc<80, 2>(mh, ml, a, grid, st);
+    case 128: return launch_tc<128, 2>(mh, ml, a, grid, st);
+    default: set_error("conv2d_tc: unsupported N tile %d (32, 64, 80, 128)", bn_tile); return FRTM_EINVAL;
+  }
+}

@@ -210,3 +210,127 @@ def build_stencil(pw: torch.Tensor, y: torch.Tensor, fsize):
     uty = torch.empty((K, h, w), device=pw.device, dtype=torch.float32)
     lib().build_stencil(ptr(pw), ptr(y), K, H, W, h, w, ptr(st), ptr(uty), stream())
     return st, uty
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# tensor-core (tcgen05) convolution path: split-fp16 operands
+# ---------------------------------------------------------------------------------------------------------------------
+ACT_SCALE = 16.0
+
+
+@dataclass
+class Split:
+    """Activation as two fp16 NHWC planes with hi + lo = ACT_SCALE * x (channel stride = hi.shape[3])."""
+    hi: torch.Tensor
+    lo: torch.Tensor
+    channels: int
+
+    @property
+    def shape(self):
+        return self.hi.shape
+
+
+@dataclass
+class PackedConvTC:
+    wt: torch.Tensor          # fp16 [ntile][tap][cin/64][2][bn][64], 128-byte swizzled rows
+    oscale: torch.Tensor      # fp32 [cout_pad]
+    bias: Optional[torch.Tensor]
+    cin: int
+    cout: int
+    k: int
+    bn: int
+
+
+def _pick_bn(cout: int) -> int:
+    if cout <= 32:
+        return 32
+    if cout <= 64:
+        return 64
+    if cout <= 80:
+        return 80
+    return 128
+
+
+def pack_conv_tc(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, bn: Optional[dict] = None, device=None,
+                 eps: float = 1e-5, bn_tile: Optional[int] = None, cin_pad: Optional[int] = None) -> PackedConvTC:
+    """(Cout,Cin,k,k) [+ folded eval-mode BN] -> pre-split, pre-swizzled weight tiles for frtm_conv2d_tc (host, once)."""
+    w = weight.detach().to("cpu", torch.float64)
+    cout, cin, kh, kw = w.shape
+    assert kh == kw and kh in (1, 3)
+    b = bias.detach().to("cpu", torch.float64) if bias is not None else None
+    if bn is not None:
+        scale = bn["weight"].double().cpu() / torch.sqrt(bn["running_var"].double().cpu() + eps)
+        w = w * scale.view(-1, 1, 1, 1)
+        shift = bn["bias"].double().cpu() - bn["running_mean"].double().cpu() * scale
+        b = shift if b is None else b * scale + shift
+    cin_p = cin_pad or _rup(cin, 64)
+    assert cin_p % 64 == 0
+    tile = bn_tile or _pick_bn(cout)
+    ntile = (cout + tile - 1) // tile
+    cout_p = ntile * tile
+    # per-output-channel power-of-two scale: max |w| -> [2^9, 2^10)
+    amax = w.abs().amax(dim=(1, 2, 3))
+    expo = torch.where(amax > 0, 9 - torch.floor(torch.log2(amax.clamp_min(1e-300))), torch.zeros_like(amax))
+    wscale = torch.pow(torch.tensor(2.0, dtype=torch.float64), expo)
+    ws = torch.zeros(cout_p, cin_p, kh, kw, dtype=torch.float64)
+    ws[:cout, :cin] = w * wscale.view(-1, 1, 1, 1)
+    hi = ws.to(torch.float16)
+    lo = (ws - hi.double()).to(torch.float16)
+    oscale = torch.ones(cout_p, dtype=torch.float64)
+    oscale[:cout] = 1.0 / (ACT_SCALE * wscale)
+    # [2][cout_p][cin_p][kh][kw] -> [ntile][tap][kc][2][tile][64]
+    t = torch.stack((hi, lo))                                          # (2, cout_p, cin_p, kh, kw)
+    t = t.reshape(2, ntile, tile, cin_p // 64, 64, kh * kw)            # (2, nt, n, kc, k, tap)
+    t = t.permute(1, 5, 3, 0, 2, 4).contiguous()                       # (nt, tap, kc, 2, n, k)
+    # 128-byte swizzle: 16-byte chunk j of row r is stored at chunk position j ^ (r % 8)
+    t = t.reshape(ntile, kh * kw, cin_p // 64, 2, tile // 8, 8, 8, 8)   # (..., r8, r, chunk, elem)
+    sw = torch.empty_like(t)
+    for r in range(8):
+        perm = [j ^ r for j in range(8)]
+        sw[..., r, :, :] = t[..., r, perm, :]
+    wt = sw.reshape(-1).contiguous().to(device)
+    return PackedConvTC(wt, oscale.to(torch.float32).to(device), None if b is None else b.to(torch.float32).contiguous().to(device),
+                        cin_p, cout, kh, tile)
+
+
+def split_f16(x: torch.Tensor, channels: Optional[int] = None, ld: Optional[int] = None) -> Split:
+    """fp32 NHWC (B,H,W,ldx) -> Split planes (channel stride ld, default round_up(C, 8))."""
+    B, H, W, ldx = x.shape
+    C = channels or ldx
+    ld = ld or _rup(C, 8)
+    hi = torch.empty((B, H, W, ld), device=x.device, dtype=torch.float16)
+    lo = torch.empty((B, H, W, ld), device=x.device, dtype=torch.float16)
+    if ld != C:
+        hi.zero_(); lo.zero_()
+    lib().split_f16(ptr(x), B * H * W, C, ldx, ptr(hi), ptr(lo), ld, stream())
+    return Split(hi, lo, C)
+
+
+def conv2d_tc(x: Split, pc: PackedConvTC, res=None, relu: bool = False, out_f32: bool = True, out_split: bool = False,
+              nchw: bool = False, out: Optional[torch.Tensor] = None, coff: int = 0, split_ld: Optional[int] = None):
+    """Tensor-core conv.  Returns a dict with the requested outputs: 'y' (fp32 NHWC), 'split' (Split), 'nchw'."""
+    B, H, W, ldx = x.hi.shape
+    dev = x.hi.device
+    y = None
+    if out_f32:
+        y = out if out is not None else torch.empty((B, H, W, pc.cout), device=dev, dtype=torch.float32)
+    y_nchw = torch.empty((B, pc.cout, H, W), device=dev, dtype=torch.float32) if nchw else None
+    sp = None
+    if out_split:
+        ld = split_ld or _rup(pc.cout, 8)
+        if ld != pc.cout:
+            sp = Split(torch.zeros((B, H, W, ld), device=dev, dtype=torch.float16),
+                       torch.zeros((B, H, W, ld), device=dev, dtype=torch.float16), pc.cout)
+        else:
+            sp = Split(torch.empty((B, H, W, ld), device=dev, dtype=torch.float16),
+                       torch.empty((B, H, W, ld), device=dev, dtype=torch.float16), pc.cout)
+    res_f = res if torch.is_tensor(res) else None
+    res_s = res if isinstance(res, Split) else None
+    lib().conv2d_tc(ptr(x.hi), ptr(x.lo), B, H, W, pc.cin, ldx, ptr(pc.wt), ptr(pc.oscale), pc.bn, ptr(pc.bias),
+                    ptr(res_f), 0 if res_f is None else res_f.shape[3],
+                    None if res_s is None else ptr(res_s.hi), None if res_s is None else ptr(res_s.lo),
+                    0 if res_s is None else res_s.hi.shape[3],
+                    ptr(y), 0 if y is None else y.shape[3], coff, ptr(y_nchw),
+                    None if sp is None else ptr(sp.hi), None if sp is None else ptr(sp.lo), 0 if sp is None else sp.hi.shape[3], 0,
+                    pc.cout, pc.k, pc.k, 1 if relu else 0, stream())
+    return dict(y=y, split=sp, nchw=y_nchw)

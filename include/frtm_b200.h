@@ -61,6 +61,23 @@ int frtm_conv2d_nhwc(const float *x, int B, int H, int W, int Cin, int ldx, cons
                      const float *res, int ldr, float *y, int ldy, int y_coff, float *y_nchw, int Cout, int kh,
                      int kw, int stride, int pad, int relu, void *stream);
 
+/* Tensor-core (tcgen05) convolution: stride-1 "same" 1x1 / 3x3, split-fp16 operands, fp32 accumulation in TMEM.
+ *   x_hi/x_lo  fp16 NHWC planes (B,H,W,ldx) of 16*x = hi + lo (frtm_split_f16 or a previous conv's y_hi/y_lo),
+ *              Cin % 64 == 0, ldx % 8 == 0;  fetched by TMA, zero OOB fill supplies the padding
+ *   wt         weights pre-tiled by frtm_vos_b200.ops.pack_conv_tc: [ntile][tap][Cin/64][hi|lo][bn_tile x 64] fp16 in
+ *              the 128-byte-swizzled K-major shared-memory image, scaled per output channel by a power of two;
+ *              oscale[n] = 1 / (16 * that scale)
+ *   outputs    any of: y fp32 NHWC (ldy, y_coff), y_nchw fp32 (B,Cout,H,W), y_hi/y_lo split planes (ldyh, yh_coff)
+ *   res / res_hi,res_lo   optional residual (fp32 NHWC or split planes) added before the ReLU
+ * Same reference call sites as frtm_conv2d_nhwc; three MMAs per k-step (hi*hi + hi*lo + lo*hi) keep the result within
+ * ~1e-6 relative of an fp32 convolution. */
+int frtm_conv2d_tc(const void *x_hi, const void *x_lo, int B, int H, int W, int Cin, int ldx, const void *wt,
+                   const float *oscale, int bn_tile, const float *bias, const float *res, int ldr, const void *res_hi,
+                   const void *res_lo, int ldrh, float *y, int ldy, int y_coff, float *y_nchw, void *y_hi, void *y_lo,
+                   int ldyh, int yh_coff, int Cout, int kh, int kw, int relu, void *stream);
+/* fp32 NHWC (npix, ldx)[0,C) -> fp16 planes hi, lo with hi + lo = 16 * x  (channel stride ldh, ldh % 8 == 0). */
+int frtm_split_f16(const float *x, int64_t npix, int C, int ldx, void *hi, void *lo, int ldh, void *stream);
+
 /* 3x3 / stride 2 / pad 1 max pooling, NHWC (torchvision resnet.py maxpool; feature_extractor.py:53). */
 int frtm_maxpool3x3s2_nhwc(const float *x, int B, int H, int W, int C, float *y, float *y_nchw, void *stream);
 

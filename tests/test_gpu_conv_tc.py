@@ -1,0 +1,70 @@
+"""-m gpu: the tcgen05 tensor-core convolution (split-fp16, 3 MMAs per k-step) against torch fp32 on the CPU and
+against the library's own exact fp32 CUDA-core conv."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def _nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+@pytest.mark.parametrize("cin,cout,k,hw,B", [
+    (64, 64, 1, (8, 16), 1),        # exactly one tile, one k-block
+    (64, 64, 3, (8, 16), 1),        # 9 taps, halo entirely out of bounds
+    (64, 64, 3, (30, 54), 2),       # ragged tiles, batch
+    (128, 128, 3, (15, 27), 1),     # two k-chunks, BN=128
+    (256, 256, 3, (30, 54), 1),     # two N tiles
+    (64, 32, 3, (40, 44), 1),       # BN=32
+    (64, 65, 3, (15, 27), 3),       # BN=80, ragged Cout
+    (1024, 256, 1, (30, 54), 1),    # deep 1x1
+    (256, 1024, 1, (9, 5), 1),      # W < tile width
+])
+def test_conv2d_tc_matches_fp32(cin, cout, k, hw, B):
+    from frtm_vos_b200 import ops
+    g = torch.Generator().manual_seed(cin + 7 * cout + k)
+    x = torch.randn(B, cin, *hw, generator=g)
+    w = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    b = torch.randn(cout, generator=g)
+    ref = F.conv2d(x, w, b, 1, k // 2)
+    res = torch.randn(ref.shape, generator=g)
+    ref2 = F.relu(ref + res)
+    xs = ops.split_f16(_nhwc(x).to(DEV))
+    pc = ops.pack_conv_tc(w, b, device=DEV)
+    o = ops.conv2d_tc(xs, pc, nchw=True, out_split=True)
+    scale = max(1.0, ref.abs().max().item())
+    err = (_nchw(o["y"].cpu()) - ref).abs().max().item()
+    assert err < 1e-5 * scale, err
+    assert (o["nchw"].cpu() - ref).abs().max().item() < 1e-5 * scale
+    sp = o["split"]
+    back = (sp.hi.float() + sp.lo.float())[..., :cout].cpu() / ops.ACT_SCALE
+    assert (_nchw(back) - ref).abs().max().item() < 1e-5 * scale
+    o2 = ops.conv2d_tc(xs, pc, res=_nhwc(res).to(DEV), relu=True)
+    assert (_nchw(o2["y"].cpu()) - ref2).abs().max().item() < 1e-5 * scale
+    o3 = ops.conv2d_tc(xs, pc, res=ops.split_f16(_nhwc(res).to(DEV)), relu=True)
+    assert (_nchw(o3["y"].cpu()) - ref2).abs().max().item() < 2e-5 * scale
+    # and against the exact CUDA-core kernel of the same library
+    y_simt = ops.conv2d(_nhwc(x).to(DEV), ops.pack_conv(w, b, device=DEV))
+    assert (y_simt - o["y"]).abs().max().item() < 1e-5 * scale
+
+
+def test_conv2d_tc_small_magnitudes_and_wide_input():
+    """Weights of very different magnitude per output channel and tiny activations (subnormal-lo regime)."""
+    from frtm_vos_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 64, 16, 32, generator=g) * 1e-3
+    w = torch.randn(64, 64, 3, 3, generator=g) * torch.logspace(-6, 1, 64).view(-1, 1, 1, 1)
+    ref = F.conv2d(x.double(), w.double(), None, 1, 1)
+    wide = torch.zeros(1, 16, 32, 72)
+    wide[..., :64] = _nhwc(x)
+    xs = ops.split_f16(wide.to(DEV), channels=64, ld=72)
+    o = ops.conv2d_tc(xs, ops.pack_conv_tc(w, None, device=DEV))
+    rel = ((_nchw(o["y"].cpu()).double() - ref).abs().amax(dim=(0, 2, 3)) / ref.abs().amax(dim=(0, 2, 3))).max().item()
+    assert rel < 2e-5, rel
