@@ -32,7 +32,7 @@ struct TcArgs {
   float *y_nchw;           // or null
   __half *y_hi, *y_lo;     // split out planes (channel stride ldyh, offset yh_coff) or null
   int ldr, ldrh, ldy, y_coff, ldyh, yh_coff;
-  int B, H, W, Cout, kh, kw, pad, relu, tiles_x, tiles_y, kchunks;
+  int B, H, W, Ho, Wo, stride, Cout, kh, kw, pad, relu, tiles_x, tiles_y, kchunks;
 };
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -188,8 +188,8 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
         const int tap = kb / a.kchunks, kc = kb - tap * a.kchunks;
         const int ky = tap / a.kw, kx = tap - ky * a.kw;
         const uint32_t sa = base + s * STAGE_BYTES;
-        tma_load_4d(sa, &tm_hi, kc * TC_BK, x0 + kx - a.pad, y0 + ky - a.pad, b, bar_full + 8 * s);
-        tma_load_4d(sa + TC_A_BYTES, &tm_lo, kc * TC_BK, x0 + kx - a.pad, y0 + ky - a.pad, b, bar_full + 8 * s);
+        tma_load_4d(sa, &tm_hi, kc * TC_BK, x0 * a.stride + kx - a.pad, y0 * a.stride + ky - a.pad, b, bar_full + 8 * s);
+        tma_load_4d(sa + TC_A_BYTES, &tm_lo, kc * TC_BK, x0 * a.stride + kx - a.pad, y0 * a.stride + ky - a.pad, b, bar_full + 8 * s);
         bulk_load(sa + 2 * TC_A_BYTES, wbase + (size_t)kb * (2 * B_BYTES / 2), 2 * B_BYTES, bar_full + 8 * s);
       }
     }
@@ -220,8 +220,8 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int py = y0 + row / TC_TW, px = x0 + row % TC_TW;
-    const bool valid = py < a.H && px < a.W;
-    const int64_t pix = ((int64_t)b * a.H + py) * a.W + px;
+    const bool valid = py < a.Ho && px < a.Wo;
+    const int64_t pix = ((int64_t)b * a.Ho + py) * a.Wo + px;
     mbar_wait(bar_accum, 0);
     tc_fence_after();
     const int n0 = ntile * BN;
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
         }
       }
       if (a.y_nchw) {
-        const int64_t hw = (int64_t)a.H * a.W, p = (int64_t)py * a.W + px;
+        const int64_t hw = (int64_t)a.Ho * a.Wo, p = (int64_t)py * a.Wo + px;
 #pragma unroll
         for (int j = 0; j < 16; ++j)
           if (n0 + c0 + j < a.Cout) a.y_nchw[((int64_t)b * a.Cout + n0 + c0 + j) * hw + p] = v[j];
@@ -304,6 +304,46 @@ __global__ void split_kernel(const float *__restrict__ x, int64_t npix, int C, i
   *reinterpret_cast<uint2 *>(lo + p * ldh + c) = *reinterpret_cast<uint2 *>(l);
 }
 
+// Finishes a conv whose input is cat(64 channels, 1 score channel) (TSE.transform, model/seg_network.py:15,19-20): the
+// tensor-core kernel has produced the 64-channel part in y; this adds the score channel's 3x3 contribution, the bias and
+// the ReLU, and emits what the next layer needs: split planes for outputs [0,64) and/or fp32, and output channel 64 (when
+// Cout == 65) as a separate fp32 map — the next conv's score channel.
+__global__ void rank1_finish_kernel(const float *__restrict__ yin, int ldin, int n_obj, float *__restrict__ yout, int ldout,
+                                    const float *__restrict__ s, const float *__restrict__ wx, const float *__restrict__ bias,
+                                    int B, int H, int W, int Cout, int relu, __half *__restrict__ yh, __half *__restrict__ yl,
+                                    int ldh, float *__restrict__ extra) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)B * H * W * Cout;
+  if (idx >= total) return;
+  const int n = (int)(idx % Cout);
+  const int64_t pix = idx / Cout;
+  const int64_t hw = (int64_t)W * H;
+  const int px = (int)(pix % W);
+  const int py = (int)((pix / W) % H);
+  const int64_t img = pix / hw;
+  const float *sb = s + img * hw;
+  // the 64-channel part may be shared by the n_obj objects of a frame (it depends on backbone features only)
+  float acc = yin[((img / n_obj) * hw + (pix - img * hw)) * ldin + n];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int yy = py + t / 3 - 1, xx = px + t % 3 - 1;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) acc = fmaf(wx[t * Cout + n], sb[yy * W + xx], acc);
+  }
+  if (bias) acc += bias[n];
+  if (relu) acc = fmaxf(acc, 0.f);
+  if (yout) yout[pix * ldout + n] = acc;
+  if (n < 64) {
+    if (yh) {
+      const float sc = acc * TC_ACT_SCALE;
+      const __half h = __float2half_rn(sc);
+      yh[pix * ldh + n] = h;
+      yl[pix * ldh + n] = __float2half_rn(sc - __half2float(h));
+    }
+  } else if (extra) {
+    extra[pix] = acc;
+  }
+}
+
 // ----------------------------------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------------------------------
@@ -324,13 +364,14 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-static int make_act_map(CUtensorMap *tm, const __half *ptr, int B, int H, int W, int C, int ld) {
+static int make_act_map(CUtensorMap *tm, const __half *ptr, int B, int H, int W, int C, int ld, int stride) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("conv_tc: cuTensorMapEncodeTiled entry point not available"); return FRTM_ELAUNCH; }
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
-  cuuint32_t box[4] = {TC_BK, TC_TW, TC_TH, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  // with a traversal stride s the box spans TW*s x TH*s input pixels and TMA keeps every s-th one (ceil(box/s) elements)
+  cuuint32_t box[4] = {TC_BK, (cuuint32_t)(TC_TW * stride), (cuuint32_t)(TC_TH * stride), 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half *>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -367,25 +408,27 @@ extern "C" int frtm_split_f16(const float *x, int64_t npix, int C, int ldx, void
 extern "C" int frtm_conv2d_tc(const void *x_hi, const void *x_lo, int B, int H, int W, int Cin, int ldx, const void *wt,
                               const float *oscale, int bn_tile, const float *bias, const float *res, int ldr,
                               const void *res_hi, const void *res_lo, int ldrh, float *y, int ldy, int y_coff, float *y_nchw,
-                              void *y_hi, void *y_lo, int ldyh, int yh_coff, int Cout, int kh, int kw, int relu,
+                              void *y_hi, void *y_lo, int ldyh, int yh_coff, int Cout, int kh, int kw, int stride, int relu,
                               void *stream) {
   FRTM_REQUIRE(x_hi && x_lo && wt && oscale && (y || y_nchw || y_hi), "conv2d_tc: null pointer");
   FRTM_REQUIRE(Cin % TC_BK == 0 && ldx % 8 == 0, "conv2d_tc: Cin must be a multiple of 64 and ldx of 8 (got %d, %d)", Cin, ldx);
-  FRTM_REQUIRE(kh == kw && (kh == 1 || kh == 3), "conv2d_tc: only 1x1 and 3x3 stride-1 'same' convolutions");
+  FRTM_REQUIRE(kh == kw && (kh == 1 || kh == 3), "conv2d_tc: only 1x1 (pad 0) and 3x3 (pad 1) convolutions");
+  FRTM_REQUIRE(stride == 1 || stride == 2, "conv2d_tc: stride must be 1 or 2");
   FRTM_REQUIRE((reinterpret_cast<uintptr_t>(x_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(x_lo) & 15) == 0 &&
                (reinterpret_cast<uintptr_t>(wt) & 15) == 0, "conv2d_tc: operands must be 16-byte aligned");
   FRTM_REQUIRE(!y_hi || (y_lo && ldyh % 2 == 0), "conv2d_tc: bad split output");
   CUtensorMap mh, ml;
-  int rc = make_act_map(&mh, (const __half *)x_hi, B, H, W, Cin, ldx);
+  int rc = make_act_map(&mh, (const __half *)x_hi, B, H, W, Cin, ldx, stride);
   if (rc) return rc;
-  rc = make_act_map(&ml, (const __half *)x_lo, B, H, W, Cin, ldx);
+  rc = make_act_map(&ml, (const __half *)x_lo, B, H, W, Cin, ldx, stride);
   if (rc) return rc;
   TcArgs a;
   a.wt = (const __half *)wt; a.oscale = oscale; a.bias = bias; a.res = res; a.res_hi = (const __half *)res_hi;
   a.res_lo = (const __half *)res_lo; a.y = y; a.y_nchw = y_nchw; a.y_hi = (__half *)y_hi; a.y_lo = (__half *)y_lo;
   a.ldr = ldr; a.ldrh = ldrh; a.ldy = ldy; a.y_coff = y_coff; a.ldyh = ldyh; a.yh_coff = yh_coff;
-  a.B = B; a.H = H; a.W = W; a.Cout = Cout; a.kh = kh; a.kw = kw; a.pad = kh / 2; a.relu = relu;
-  a.tiles_x = cdiv(W, TC_TW); a.tiles_y = cdiv(H, TC_TH); a.kchunks = Cin / TC_BK;
+  a.B = B; a.H = H; a.W = W; a.Cout = Cout; a.kh = kh; a.kw = kw; a.pad = kh / 2; a.relu = relu; a.stride = stride;
+  a.Ho = (H + 2 * a.pad - kh) / stride + 1; a.Wo = (W + 2 * a.pad - kw) / stride + 1;
+  a.tiles_x = cdiv(a.Wo, TC_TW); a.tiles_y = cdiv(a.Ho, TC_TH); a.kchunks = Cin / TC_BK;
   const int ntiles_n = cdiv(Cout, bn_tile);
   dim3 grid((unsigned)(B * a.tiles_x * a.tiles_y), (unsigned)ntiles_n);
   cudaStream_t st = (cudaStream_t)stream;
@@ -396,4 +439,15 @@ extern "C" int frtm_conv2d_tc(const void *x_hi, const void *x_lo, int B, int H, 
     case 128: return launch_tc<128, 2>(mh, ml, a, grid, st);
     default: set_error("conv2d_tc: unsupported N tile %d (32, 64, 80, 128)", bn_tile); return FRTM_EINVAL;
   }
+}
+
+extern "C" int frtm_rank1_finish(const float *y_in, int ldin, int n_obj, float *y_out, int ldout, const float *score,
+                                 const float *wx, const float *bias, int B, int H, int W, int Cout, int relu, void *y_hi,
+                                 void *y_lo, int ldh, float *extra, void *stream) {
+  FRTM_REQUIRE(y_in && score && wx && Cout <= 65 && Cout >= 1 && n_obj >= 1, "rank1_finish: bad arguments");
+  const int64_t total = (int64_t)B * H * W * Cout;
+  rank1_finish_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(y_in, ldin, n_obj, y_out, ldout, score, wx, bias, B, H,
+                                                                          W, Cout, relu, (__half *)y_hi, (__half *)y_lo, ldh, extra);
+  FRTM_CHECK_LAUNCH("rank1_finish");
+  return FRTM_OK;
 }

@@ -23,11 +23,13 @@ _ARCH = {"resnet18": ("basic", (2, 2, 2, 2), (64, 64, 128, 256, 512)),
 
 
 class FeatureMaps(dict):
-    """``dict`` of NCHW feature maps (reference contract) + ``.nhwc`` (B,h,w,C) working tensors."""
+    """``dict`` of NCHW feature maps (reference contract) + the working tensors the other kernels consume directly:
+    ``.split`` — fp16 hi/lo NHWC planes (operands of the tensor-core convs), ``.nhwc`` — fp32 NHWC where produced."""
 
-    def __init__(self, nchw: Dict[str, torch.Tensor], nhwc: Dict[str, torch.Tensor]):
+    def __init__(self, nchw: Dict[str, torch.Tensor], nhwc: Dict[str, torch.Tensor], split=None):
         super().__init__(nchw)
         self.nhwc = nhwc
+        self.split = split or {}
 
 
 class ResnetFeatureExtractor:
@@ -57,20 +59,23 @@ class ResnetFeatureExtractor:
         self.device = device
         sd, w = self._sd, {}
         w["stem"] = ops.pack_conv(sd["conv1.weight"], bn=self._bn("bn1"), stride=2, pad=3, device=device)
+
+        def tc(conv_key, bn_key, stride=1):
+            return ops.pack_conv_tc(sd[conv_key + ".weight"], bn=self._bn(bn_key), device=device, stride=stride)
+
         for si, nblk in enumerate(self.depth):
             for bi in range(nblk):
                 key = "layer%d.%d" % (si + 1, bi)
                 stride = 2 if (bi == 0 and si > 0) else 1
                 if self.kind == "basic":
-                    w[key + ".c1"] = ops.pack_conv(sd[key + ".conv1.weight"], bn=self._bn(key + ".bn1"), stride=stride, device=device)
-                    w[key + ".c2"] = ops.pack_conv(sd[key + ".conv2.weight"], bn=self._bn(key + ".bn2"), device=device)
+                    w[key + ".c1"] = tc(key + ".conv1", key + ".bn1", stride)
+                    w[key + ".c2"] = tc(key + ".conv2", key + ".bn2")
                 else:
-                    w[key + ".c1"] = ops.pack_conv(sd[key + ".conv1.weight"], bn=self._bn(key + ".bn1"), device=device)
-                    w[key + ".c2"] = ops.pack_conv(sd[key + ".conv2.weight"], bn=self._bn(key + ".bn2"), stride=stride, device=device)
-                    w[key + ".c3"] = ops.pack_conv(sd[key + ".conv3.weight"], bn=self._bn(key + ".bn3"), device=device)
+                    w[key + ".c1"] = tc(key + ".conv1", key + ".bn1")
+                    w[key + ".c2"] = tc(key + ".conv2", key + ".bn2", stride)     # torchvision puts the stride on the 3x3
+                    w[key + ".c3"] = tc(key + ".conv3", key + ".bn3")
                 if (key + ".downsample.0.weight") in sd:
-                    w[key + ".ds"] = ops.pack_conv(sd[key + ".downsample.0.weight"], bn=self._bn(key + ".downsample.1"),
-                                                   stride=stride, pad=0, device=device)
+                    w[key + ".ds"] = tc(key + ".downsample.0", key + ".downsample.1", stride)
         self._w = w
         return self
 
@@ -78,20 +83,27 @@ class ResnetFeatureExtractor:
         return self._out_channels
 
     # ------------------------------------------------------------------------------------------------------
-    def forward_nhwc(self, images: torch.Tensor, nchw_layers: Sequence[str] = (), upto: str = "layer5"):
-        """uint8 (B,3,H,W) -> ({layer: NHWC}, {layer: NCHW for layers in nchw_layers}).  Stops after ``upto``."""
+    def forward_split(self, images: torch.Tensor, nchw_layers: Sequence[str] = (), f32_layers: Sequence[str] = (),
+                      upto: str = "layer5"):
+        """uint8 (B,3,H,W) -> ({layer: Split}, {layer: fp32 NHWC for f32_layers}, {layer: NCHW for nchw_layers}).
+
+        The 7x7/s2 stem (3 input channels) runs on the exact CUDA-core conv; every other conv — 1x1 and 3x3, stride 1
+        and 2 — is a tcgen05 tile with BatchNorm folded in, the residual read from the split planes and ReLU fused."""
         if self.device is None:
             raise RuntimeError("call .to(device) first")
         require_cuda(images, "image")
         w = self._w
-        nhwc, nchw = {}, {}
+        split, f32, nchw = {}, {}, {}
         x = ops.normalize_u8(images)
         x = ops.conv2d(x, w["stem"], relu=True)
         if "layer1" in nchw_layers:
             x, nchw["layer1"] = ops.maxpool3x3s2(x, nchw=True)
         else:
             x = ops.maxpool3x3s2(x)
-        nhwc["layer1"] = x
+        if "layer1" in f32_layers:
+            f32["layer1"] = x
+        xs = ops.split_f16(x)
+        split["layer1"] = xs
         last = int(upto[-1])
         for si, nblk in enumerate(self.depth):
             name = "layer%d" % (si + 2)
@@ -99,27 +111,35 @@ class ResnetFeatureExtractor:
                 break
             for bi in range(nblk):
                 key = "layer%d.%d" % (si + 1, bi)
-                want = (bi == nblk - 1) and (name in nchw_layers)
-                idt = ops.conv2d(x, w[key + ".ds"]) if (key + ".ds") in w else x
-                h = ops.conv2d(x, w[key + ".c1"], relu=True)
-                if self.kind == "basic":
-                    out = ops.conv2d(h, w[key + ".c2"], res=idt, relu=True, nchw=want)
-                else:
-                    h = ops.conv2d(h, w[key + ".c2"], relu=True)
-                    out = ops.conv2d(h, w[key + ".c3"], res=idt, relu=True, nchw=want)
-                if want:
-                    x, nchw[name] = out
-                else:
-                    x = out
-            nhwc[name] = x
-        return nhwc, nchw
+                final = bi == nblk - 1
+                idt = ops.conv2d_tc(xs, w[key + ".ds"], out_f32=False, out_split=True)["split"] if (key + ".ds") in w else xs
+                h = ops.conv2d_tc(xs, w[key + ".c1"], relu=True, out_f32=False, out_split=True)["split"]
+                if self.kind == "bottleneck":
+                    h = ops.conv2d_tc(h, w[key + ".c2"], relu=True, out_f32=False, out_split=True)["split"]
+                last_conv = w[key + (".c2" if self.kind == "basic" else ".c3")]
+                o = ops.conv2d_tc(h, last_conv, res=idt, relu=True, out_split=True, out_f32=final and name in f32_layers,
+                                  nchw=final and name in nchw_layers)
+                xs = o["split"]
+                if final:
+                    if o["y"] is not None:
+                        f32[name] = o["y"]
+                    if o["nchw"] is not None:
+                        nchw[name] = o["nchw"]
+            split[name] = xs
+        return split, f32, nchw
+
+    def forward_nhwc(self, images: torch.Tensor, nchw_layers: Sequence[str] = (), upto: str = "layer5"):
+        """Compatibility helper: ({layer: fp32 NHWC}, {layer: NCHW})."""
+        names = ["layer%d" % i for i in range(1, int(upto[-1]) + 1)]
+        split, f32, nchw = self.forward_split(images, nchw_layers, names, upto)
+        return f32, nchw
 
     def __call__(self, input: torch.Tensor, output_layers=None) -> FeatureMaps:
         img = input if input.dim() == 4 else input.unsqueeze(0)
         names = ["layer1", "layer2", "layer3", "layer4", "layer5"]
         want = [n for n in names if output_layers is None or n in output_layers]
-        nhwc, nchw = self.forward_nhwc(img, want)   # like the reference, every stage runs regardless of the request
-        return FeatureMaps(OrderedDict((n, nchw[n]) for n in want), nhwc)
+        split, f32, nchw = self.forward_split(img, want)   # like the reference, every stage runs regardless of the request
+        return FeatureMaps(OrderedDict((n, nchw[n]) for n in want), f32, split)
 
     def no_grad_forward(self, input, output_layers=None, chunk_size=None):
         if chunk_size is None:

@@ -11,7 +11,9 @@ What differs from the reference's execution (not from its results):
   * ``TSE.reduce(ft)`` depends only on the backbone features, so it is evaluated once per frame and broadcast to
     the objects of that frame (SURVEY.md finding 5);
   * eval-mode BatchNorm is folded into the preceding conv; bias / residual / ReLU are fused conv epilogues;
-  * ``cat(h, score)`` is never materialised by a copy: producers write into a 68-channel-stride buffer.
+  * every conv is a tcgen05 tensor-core tile on split-fp16 operands (see ``csrc/conv_tc.cu``); the 65-channel TSE
+    convs run as a 64-channel tensor-core conv plus an fp32 rank-1 term for the score channel, so ``cat(h, score)`` is
+    never materialised, and the 64-channel part of ``transform[0]`` is shared by all objects of a frame as well.
 """
 from __future__ import annotations
 
@@ -114,84 +116,78 @@ class SegNetwork(nn.Module):
         dev = self.project.conv1.weight.device
         if dev.type != "cuda":
             raise RuntimeError("SegNetwork must live on a CUDA device (no CPU path)")
+        if self.oc != 64:
+            raise ValueError("the tensor-core TSE path is specialised for 64 refinement channels")
         P = {}
-        oc, pad65 = self.oc, ops._rup(self.oc + 1, 4)
+        oc = self.oc
 
-        def pc(m, **kw):
-            return ops.pack_conv(m.weight, m.bias, device=dev, **kw)
+        def tc(m, **kw):
+            return ops.pack_conv_tc(m.weight, m.bias, device=dev, **kw)
 
         for L in self.ft_channels:
             t, r1, c, r2 = self.TSE[L], self.RRB1[L], self.CAB[L], self.RRB2[L]
             P[L] = dict(
-                red0=pc(t.reduce[0]), red2=pc(t.reduce[2]),
-                tr0=pc(t.transform[0], cin_pad=pad65), tr2=pc(t.transform[2], cin_pad=pad65), tr4=pc(t.transform[4], cin_pad=pad65),
+                red0=tc(t.reduce[0]), red2=tc(t.reduce[2]),
+                tr0=ops.pack_conv65(t.transform[0].weight, t.transform[0].bias, device=dev),
+                tr2=ops.pack_conv65(t.transform[2].weight, t.transform[2].bias, device=dev),
+                tr4=ops.pack_conv65(t.transform[4].weight, t.transform[4].bias, device=dev),
                 cab_w1=c.convreluconv[0].weight.detach().reshape(oc, 2 * oc).contiguous(), cab_b1=c.convreluconv[0].bias.detach(),
                 cab_w2=c.convreluconv[2].weight.detach().reshape(oc, oc).contiguous(), cab_b2=c.convreluconv[2].bias.detach(),
             )
             for tag, r in (("rrb1", r1), ("rrb2", r2)):
-                P[L][tag + "_1x1"] = pc(r.conv1x1)
+                P[L][tag + "_1x1"] = tc(r.conv1x1)
                 if self.use_bn:
                     bn = r.bblock[1]
-                    P[L][tag + "_a"] = ops.pack_conv(r.bblock[0].weight, r.bblock[0].bias, device=dev, eps=bn.eps, bn=dict(
+                    P[L][tag + "_a"] = ops.pack_conv_tc(r.bblock[0].weight, r.bblock[0].bias, device=dev, eps=bn.eps, bn=dict(
                         weight=bn.weight.detach(), bias=bn.bias.detach(), running_mean=bn.running_mean, running_var=bn.running_var))
-                    P[L][tag + "_b"] = pc(r.bblock[3])
+                    P[L][tag + "_b"] = tc(r.bblock[3])
                 else:
-                    P[L][tag + "_a"] = pc(r.bblock[0])
-                    P[L][tag + "_b"] = pc(r.bblock[2])
-        P["up1"] = pc(self.project.conv1)
+                    P[L][tag + "_a"] = tc(r.bblock[0])
+                    P[L][tag + "_b"] = tc(r.bblock[2])
+        P["up1"] = tc(self.project.conv1)
         w2 = self.project.conv2.weight.detach()
         P["up2_w"] = w2.permute(2, 3, 1, 0).reshape(9, w2.shape[1]).contiguous()
         P["up2_b"] = self.project.conv2.bias.detach().contiguous()
         self._packed = P
-        self._pad65 = pad65
-
-    def _zbuf(self, tag, shape, dev):
-        key = (tag,) + tuple(shape)
-        b = self._bufs.get(key)
-        if b is None or b.device != dev:
-            b = torch.zeros(shape, device=dev, dtype=torch.float32)
-            self._bufs[key] = b
-        return b
 
     # -- forward ------------------------------------------------------------------------------------------------
-    def forward_nhwc(self, scores: torch.Tensor, feats: Dict[str, torch.Tensor], image_size) -> torch.Tensor:
-        """scores (B,hs,ws) + NHWC feature maps (F,h,w,C) with B = F * objects  ->  logits (B,H,W)."""
+    def _rrb(self, x_split, W, tag):
+        """conv1x1 -> (3x3 + BN + ReLU -> 3x3) + skip -> ReLU, all tensor-core tiles; returns fp32 NHWC."""
+        hh = ops.conv2d_tc(x_split, W[tag + "_1x1"], out_f32=False, out_split=True)["split"]
+        b = ops.conv2d_tc(hh, W[tag + "_a"], relu=True, out_f32=False, out_split=True)["split"]
+        return ops.conv2d_tc(b, W[tag + "_b"], res=hh, relu=True)["y"]
+
+    def forward_nhwc(self, scores: torch.Tensor, feats, image_size) -> torch.Tensor:
+        """scores (B,hs,ws) + backbone features as ``ops.Split`` planes (F,h,w,C) with B = F * objects -> logits (B,H,W)."""
         if self._packed is None:
             self._pack()
         P = self._packed
         B = scores.shape[0]
-        dev = scores.device
         s_nhwc = scores.reshape(B, scores.shape[-2], scores.shape[-1], 1)
         x = None
         hpool = None
         for li, L in enumerate(self.ft_channels):
             ft = feats[L]
-            F, h, w, _ = ft.shape
+            if not isinstance(ft, ops.Split):
+                ft = ops.split_f16(ft)
+            F, h, w, _ = ft.hi.shape
             n_obj = B // F
             assert n_obj * F == B, "scores batch must be a multiple of the feature batch"
             W = P[L]
-            cat_a = self._zbuf("cat_a", (B, h, w, self._pad65), dev)
-            cat_b = self._zbuf("cat_b", (B, h, w, self._pad65), dev)
-            r = ops.conv2d(ft, W["red0"], relu=True)
-            if n_obj == 1:
-                ops.conv2d(r, W["red2"], out=cat_a, coff=0)
-            else:
-                r = ops.conv2d(r, W["red2"])
-                ops.broadcast_objects(r, n_obj, cat_a, channels=self.oc)
-            if (h, w) == tuple(s_nhwc.shape[1:3]):
-                ops.scatter_channel(s_nhwc.reshape(B, h, w), cat_a, self.oc, 0)
-            else:
-                ops.resize_bilinear(s_nhwc, (h, w), channels=1, out=cat_a, coff=self.oc)
+            # TSE.reduce depends on the backbone features only: once per frame, not per object (SURVEY finding 5)
+            r = ops.conv2d_tc(ft, W["red0"], relu=True, out_f32=False, out_split=True)["split"]
+            o = ops.conv2d_tc(r, W["red2"], out_f32=(li == 0), out_split=True)
+            hsp = o["split"]
             if li == 0:
-                hpool = ops.global_avgpool(cat_a, channels=self.oc)          # (B, oc) vector at the deepest level
-            ops.conv2d(cat_a, W["tr0"], relu=True, out=cat_b, coff=0)
-            ops.conv2d(cat_b, W["tr2"], relu=True, out=cat_a, coff=0)
-            t = ops.conv2d(cat_a, W["tr4"], relu=True)
-            # RRB1
-            hh = ops.conv2d(t, W["rrb1_1x1"])
-            b = ops.conv2d(hh, W["rrb1_a"], relu=True)
-            t = ops.conv2d(b, W["rrb1_b"], res=hh, relu=True)
-            # CAB
+                hpool = ops.global_avgpool(o["y"])                       # (F, oc)
+                if n_obj > 1:
+                    hpool = hpool.repeat_interleave(n_obj, dim=0)        # tiny (F,64) index plumbing
+            s = s_nhwc.reshape(B, h, w) if (h, w) == tuple(s_nhwc.shape[1:3]) else ops.resize_bilinear(s_nhwc, (h, w)).reshape(B, h, w)
+            # TSE.transform on cat(h, s): the 64-channel part of the first conv is also shared by the objects of a frame
+            _, t, e = ops.conv65(hsp, s, W["tr0"], n_obj=n_obj)
+            _, t, e = ops.conv65(t, e, W["tr2"])
+            _, t, _ = ops.conv65(t, e, W["tr4"])
+            t = self._rrb(t, W, "rrb1")
             sp = ops.global_avgpool(t)
             if li == 0:
                 t = ops.cab(t, sp, hpool, hpool, W["cab_w1"], W["cab_b1"], W["cab_w2"], W["cab_b2"])
@@ -199,20 +195,17 @@ class SegNetwork(nn.Module):
                 dp = ops.global_avgpool(x)
                 deeper = ops.resize_bilinear(x, (h, w))
                 t = ops.cab(t, sp, dp, deeper, W["cab_w1"], W["cab_b1"], W["cab_w2"], W["cab_b2"])
-            # RRB2
-            hh = ops.conv2d(t, W["rrb2_1x1"])
-            b = ops.conv2d(hh, W["rrb2_a"], relu=True)
-            x = ops.conv2d(b, W["rrb2_b"], res=hh, relu=True)
+            x = self._rrb(ops.split_f16(t), W, "rrb2")
         u = ops.pyrup_bicubic(x)
-        u = ops.conv2d(u, P["up1"], relu=True)
+        u = ops.conv2d_tc(ops.split_f16(u), P["up1"], relu=True)["y"]
         u = ops.pyrup_bicubic(u)
         u = ops.resize_bilinear(u, image_size[-2:])
         return ops.conv3x3_to1(u, P["up2_w"], P["up2_b"])
 
     def forward(self, scores, features, image_size):
         """Reference signature: scores (B,1,h,w), features dict (NCHW; ``FeatureMaps`` carries NHWC too)."""
-        if isinstance(features, FeatureMaps) and all(L in features.nhwc for L in self.ft_channels):
-            feats = features.nhwc
+        if isinstance(features, FeatureMaps) and all(L in features.split for L in self.ft_channels):
+            feats = features.split
         else:
             feats = {L: ops.nchw_to_nhwc(features[L]) for L in self.ft_channels}
         image_size = [int(v) for v in (image_size.tolist() if torch.is_tensor(image_size) else image_size)]

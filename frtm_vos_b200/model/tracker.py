@@ -172,8 +172,8 @@ class Tracker(nn.Module):
             torch.random.manual_seed(0)
             np.random.seed(0)
             im, msk = self.augment(image, mask)
-            nhwc, _ = self.feature_extractor.forward_nhwc(im.to(self.device), (), upto=target.disc_layer)
-            target.discriminator.init(None, msk.to(self.device), x_nhwc=nhwc[target.disc_layer])
+            _, f32, _ = self.feature_extractor.forward_split(im.to(self.device), (), (target.disc_layer,), upto=target.disc_layer)
+            target.discriminator.init(None, msk.to(self.device), x_nhwc=f32[target.disc_layer])
             self._bind_filter(target)
             self.current_masks[target.index] = mask
         self._stack = None
@@ -186,23 +186,23 @@ class Tracker(nn.Module):
         key = tuple(t.object_id for t in live)
         if self._stack is None or self._stack[0] != key:
             W = torch.cat([t.discriminator.project.weight.detach() for t in live], dim=0)   # (N*c, C, 1, 1)
-            self._stack = (key, ops.pack_conv(W, device=W.device))
+            self._stack = (key, ops.pack_conv_tc(W, device=W.device))
         return self._stack[1]
 
     def track(self, image):
         im_size = image.shape[-2:]
-        feats, _ = self.feature_extractor.forward_nhwc(image if image.dim() == 4 else image.unsqueeze(0))
+        feats, _, _ = self.feature_extractor.forward_split(image if image.dim() == 4 else image.unsqueeze(0))
         live = self._live()
         n = len(live)
         layer = live[0].disc_layer
         c = live[0].discriminator.filter.weight.shape[1]
         fmap = feats[layer]
-        h, w = fmap.shape[1:3]
+        h, w = fmap.hi.shape[1:3]
 
         # classify: one conv for all projections, one correlation for all filters
-        samples = ops.conv2d(fmap, self._stacked_projection(live), nchw=True, nhwc=False).view(n, c, h, w)
+        samples = ops.conv2d_tc(fmap, self._stacked_projection(live), out_f32=False, nchw=True)["nchw"].view(n, c, h, w)
         if not hasattr(self, "_arange") or self._arange.numel() < n:
-            self._arange = torch.arange(max(n, 16), dtype=torch.int32, device=fmap.device)
+            self._arange = torch.arange(max(n, 16), dtype=torch.int32, device=samples.device)
         scores = ops.corr3x3(samples, self._fbuf, self._arange)
         logits = self.refiner.forward_nhwc(scores, feats, im_size)
         for k, t in enumerate(live):

@@ -239,6 +239,7 @@ class PackedConvTC:
     cout: int
     k: int
     bn: int
+    stride: int = 1
 
 
 def _pick_bn(cout: int) -> int:
@@ -252,7 +253,7 @@ def _pick_bn(cout: int) -> int:
 
 
 def pack_conv_tc(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, bn: Optional[dict] = None, device=None,
-                 eps: float = 1e-5, bn_tile: Optional[int] = None, cin_pad: Optional[int] = None) -> PackedConvTC:
+                 eps: float = 1e-5, bn_tile: Optional[int] = None, cin_pad: Optional[int] = None, stride: int = 1) -> PackedConvTC:
     """(Cout,Cin,k,k) [+ folded eval-mode BN] -> pre-split, pre-swizzled weight tiles for frtm_conv2d_tc (host, once)."""
     w = weight.detach().to("cpu", torch.float64)
     cout, cin, kh, kw = w.shape
@@ -290,7 +291,7 @@ def pack_conv_tc(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, bn: 
         sw[..., r, :, :] = t[..., r, perm, :]
     wt = sw.reshape(-1).contiguous().to(device)
     return PackedConvTC(wt, oscale.to(torch.float32).to(device), None if b is None else b.to(torch.float32).contiguous().to(device),
-                        cin_p, cout, kh, tile)
+                        cin_p, cout, kh, tile, stride)
 
 
 def split_f16(x: torch.Tensor, channels: Optional[int] = None, ld: Optional[int] = None) -> Split:
@@ -309,7 +310,9 @@ def split_f16(x: torch.Tensor, channels: Optional[int] = None, ld: Optional[int]
 def conv2d_tc(x: Split, pc: PackedConvTC, res=None, relu: bool = False, out_f32: bool = True, out_split: bool = False,
               nchw: bool = False, out: Optional[torch.Tensor] = None, coff: int = 0, split_ld: Optional[int] = None):
     """Tensor-core conv.  Returns a dict with the requested outputs: 'y' (fp32 NHWC), 'split' (Split), 'nchw'."""
-    B, H, W, ldx = x.hi.shape
+    B, Hi, Wi, ldx = x.hi.shape
+    pad = pc.k // 2
+    H, W = (Hi + 2 * pad - pc.k) // pc.stride + 1, (Wi + 2 * pad - pc.k) // pc.stride + 1
     dev = x.hi.device
     y = None
     if out_f32:
@@ -326,11 +329,50 @@ def conv2d_tc(x: Split, pc: PackedConvTC, res=None, relu: bool = False, out_f32:
                        torch.empty((B, H, W, ld), device=dev, dtype=torch.float16), pc.cout)
     res_f = res if torch.is_tensor(res) else None
     res_s = res if isinstance(res, Split) else None
-    lib().conv2d_tc(ptr(x.hi), ptr(x.lo), B, H, W, pc.cin, ldx, ptr(pc.wt), ptr(pc.oscale), pc.bn, ptr(pc.bias),
+    lib().conv2d_tc(ptr(x.hi), ptr(x.lo), B, Hi, Wi, pc.cin, ldx, ptr(pc.wt), ptr(pc.oscale), pc.bn, ptr(pc.bias),
                     ptr(res_f), 0 if res_f is None else res_f.shape[3],
                     None if res_s is None else ptr(res_s.hi), None if res_s is None else ptr(res_s.lo),
                     0 if res_s is None else res_s.hi.shape[3],
                     ptr(y), 0 if y is None else y.shape[3], coff, ptr(y_nchw),
                     None if sp is None else ptr(sp.hi), None if sp is None else ptr(sp.lo), 0 if sp is None else sp.hi.shape[3], 0,
-                    pc.cout, pc.k, pc.k, 1 if relu else 0, stream())
+                    pc.cout, pc.k, pc.k, pc.stride, 1 if relu else 0, stream())
     return dict(y=y, split=sp, nchw=y_nchw)
+
+
+@dataclass
+class PackedConv65:
+    """3x3 conv whose input is cat(64 channels, score): tensor-core part + fp32 rank-1 part (see frtm_rank1_finish)."""
+    main: PackedConvTC
+    wx: torch.Tensor            # (9, cout) fp32
+    bias: Optional[torch.Tensor]
+    cout: int
+
+
+def pack_conv65(weight: torch.Tensor, bias: Optional[torch.Tensor], device=None) -> PackedConv65:
+    cout = weight.shape[0]
+    assert weight.shape[1] == 65 and weight.shape[2] == 3
+    main = pack_conv_tc(weight[:, :64], None, device=device)
+    wx = weight[:, 64].detach().float().permute(1, 2, 0).reshape(9, cout).contiguous().to(device)
+    return PackedConv65(main, wx, None if bias is None else bias.detach().float().contiguous().to(device), cout)
+
+
+def conv65(h: Split, score: torch.Tensor, pc: PackedConv65, n_obj: int = 1, relu: bool = True, want_f32: bool = False,
+           want_split: bool = True):
+    """h: Split with 64 channels for F = B/n_obj frames (n_obj > 1: shared by the objects of a frame); score (B,H,W) fp32.
+    Returns (y fp32 or None, Split(64) or None, extra (B,H,W) fp32 or None)."""
+    F, H, W, _ = h.hi.shape
+    B = score.shape[0]
+    assert B == F * n_obj
+    dev = score.device
+    ld = _rup(pc.cout, 4)
+    main = conv2d_tc(h, pc.main, out=torch.empty((F, H, W, ld), device=dev, dtype=torch.float32))["y"]
+    y = torch.empty((B, H, W, pc.cout), device=dev, dtype=torch.float32) if want_f32 else None
+    sp = None
+    if want_split:
+        sp = Split(torch.empty((B, H, W, 64), device=dev, dtype=torch.float16),
+                   torch.empty((B, H, W, 64), device=dev, dtype=torch.float16), 64)
+    extra = torch.empty((B, H, W), device=dev, dtype=torch.float32) if pc.cout == 65 else None
+    lib().rank1_finish(ptr(main), ld, n_obj, ptr(y), pc.cout, ptr(score), ptr(pc.wx), ptr(pc.bias), B, H, W, pc.cout,
+                       1 if relu else 0, None if sp is None else ptr(sp.hi), None if sp is None else ptr(sp.lo), 64, ptr(extra),
+                       stream())
+    return y, sp, extra

@@ -61,7 +61,7 @@ int frtm_conv2d_nhwc(const float *x, int B, int H, int W, int Cin, int ldx, cons
                      const float *res, int ldr, float *y, int ldy, int y_coff, float *y_nchw, int Cout, int kh,
                      int kw, int stride, int pad, int relu, void *stream);
 
-/* Tensor-core (tcgen05) convolution: stride-1 "same" 1x1 / 3x3, split-fp16 operands, fp32 accumulation in TMEM.
+/* Tensor-core (tcgen05) convolution: 1x1 (pad 0) / 3x3 (pad 1), stride 1 or 2, split-fp16 operands, fp32 accumulation in TMEM.
  *   x_hi/x_lo  fp16 NHWC planes (B,H,W,ldx) of 16*x = hi + lo (frtm_split_f16 or a previous conv's y_hi/y_lo),
  *              Cin % 64 == 0, ldx % 8 == 0;  fetched by TMA, zero OOB fill supplies the padding
  *   wt         weights pre-tiled by frtm_vos_b200.ops.pack_conv_tc: [ntile][tap][Cin/64][hi|lo][bn_tile x 64] fp16 in
@@ -74,9 +74,17 @@ int frtm_conv2d_nhwc(const float *x, int B, int H, int W, int Cin, int ldx, cons
 int frtm_conv2d_tc(const void *x_hi, const void *x_lo, int B, int H, int W, int Cin, int ldx, const void *wt,
                    const float *oscale, int bn_tile, const float *bias, const float *res, int ldr, const void *res_hi,
                    const void *res_lo, int ldrh, float *y, int ldy, int y_coff, float *y_nchw, void *y_hi, void *y_lo,
-                   int ldyh, int yh_coff, int Cout, int kh, int kw, int relu, void *stream);
+                   int ldyh, int yh_coff, int Cout, int kh, int kw, int stride, int relu, void *stream);
 /* fp32 NHWC (npix, ldx)[0,C) -> fp16 planes hi, lo with hi + lo = 16 * x  (channel stride ldh, ldh % 8 == 0). */
 int frtm_split_f16(const float *x, int64_t npix, int C, int ldx, void *hi, void *lo, int ldh, void *stream);
+
+/* Completes a 3x3 conv over cat(64 channels, score) (TSE.transform, seg_network.py:15,19-20) after frtm_conv2d_tc has
+ * produced the 64-channel part y_in (B/n_obj,H,W,ldin) — shared by the n_obj objects of a frame when it depends on the
+ * backbone features only: adds the score channel's contribution (wx [9][Cout], score (B,H,W)), bias and ReLU; writes
+ * fp32 y_out (B,H,W,ldout) and/or split planes for output channels [0,64), and output channel 64 (Cout == 65) to `extra`. */
+int frtm_rank1_finish(const float *y_in, int ldin, int n_obj, float *y_out, int ldout, const float *score, const float *wx,
+                      const float *bias, int B, int H, int W, int Cout, int relu, void *y_hi, void *y_lo, int ldh,
+                      float *extra, void *stream);
 
 /* 3x3 / stride 2 / pad 1 max pooling, NHWC (torchvision resnet.py maxpool; feature_extractor.py:53). */
 int frtm_maxpool3x3s2_nhwc(const float *x, int B, int H, int W, int C, float *y, float *y_nchw, void *stream);

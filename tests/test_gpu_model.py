@@ -44,13 +44,15 @@ def test_P1_feedforward_fixed_state(arch, golden):
     for L in ("layer1", "layer2", "layer3", "layer4", "layer5"):
         d = (feats[L].cpu() - ref[L]).abs().max().item()
         assert d < 2e-4 * max(1.0, ref[L].abs().max().item()), (L, d)
-        assert torch.equal(feats[L].cpu(), feats.nhwc[L].permute(0, 3, 1, 2).cpu())
+        sp = feats.split[L]
+        back = ((sp.hi.float() + sp.lo.float()) / ops.ACT_SCALE).permute(0, 3, 1, 2).cpu()
+        assert (back - feats[L].cpu()).abs().max().item() < 1e-6 * max(1.0, ref[L].abs().max().item())
     assert np.abs(feats["layer4"].cpu().numpy() - g["ft_layer4"]).max() < 2e-4 * max(1.0, np.abs(g["ft_layer4"]).max())
     seg = GI.strip_prefix(case["seg"])
     logits_all = []
     for i, (P, Fw) in enumerate(case["PF"]):
         s_ref = F.conv2d(F.conv2d(ref["layer4"], P), Fw, None, 1, 1)
-        cft = ops.conv2d(feats.nhwc["layer4"], ops.pack_conv(P, device=DEV), nchw=True, nhwc=False)
+        cft = ops.conv2d_tc(feats.split["layer4"], ops.pack_conv_tc(P, device=DEV), out_f32=False, nchw=True)["nchw"]
         s = ops.corr3x3(cft, Fw.to(DEV)).unsqueeze(1)
         assert (s.cpu() - s_ref).abs().max() < 1e-4
         lg = trk.refiner(s, feats, img.shape[-2:])
@@ -80,12 +82,12 @@ def test_P1_batched_objects_and_frames_match_single():
     from frtm_vos_b200 import synth
     seq = synth.SyntheticSequence(num_objects=2, num_frames=3, size=GI.MID, seq_id=9)
     imgs = torch.stack([seq[t][0] for t in range(3)]).to(DEV)
-    nhwc, _ = fe.forward_nhwc(imgs)
+    nhwc, _, _ = fe.forward_split(imgs)
     g = torch.Generator().manual_seed(0)
-    scores = torch.randn(6, *nhwc["layer4"].shape[1:3], generator=g).to(DEV)       # 3 frames x 2 objects
+    scores = torch.randn(6, *nhwc["layer4"].hi.shape[1:3], generator=g).to(DEV)       # 3 frames x 2 objects
     lg = trk.refiner.forward_nhwc(scores, nhwc, GI.MID)
     for f in range(3):
-        single, _ = fe.forward_nhwc(imgs[f:f + 1])
+        single, _, _ = fe.forward_split(imgs[f:f + 1])
         for n in range(2):
             one = trk.refiner.forward_nhwc(scores[f * 2 + n:f * 2 + n + 1], single, GI.MID)
             assert torch.equal(one[0], lg[f * 2 + n])

@@ -71,18 +71,18 @@ def main():
         for _ in range(n): fn()
         e.record(); torch.cuda.synchronize()
         return s.elapsed_time(e) / n
-    feats, _ = trk.feature_extractor.forward_nhwc(img[None])
-    print("backbone      %.3f ms" % timed(lambda: trk.feature_extractor.forward_nhwc(img[None])))
+    feats, _, _ = trk.feature_extractor.forward_split(img[None])
+    print("backbone      %.3f ms" % timed(lambda: trk.feature_extractor.forward_split(img[None])))
     n = a.objects
-    scores = torch.randn(n, *feats["layer4"].shape[1:3], device=dev)
+    scores = torch.randn(n, *feats["layer4"].hi.shape[1:3], device=dev)
     print("seg net (x%d)  %.3f ms" % (n, timed(lambda: trk.refiner.forward_nhwc(scores, feats, size))))
     print("track (all)   %.3f ms" % timed(lambda: trk.track(img)))
     d = trk.targets[1].discriminator
     print("gn update     %.3f ms" % timed(lambda: d.update_optimizer.run(d.update_iters)))
     t0 = time.time(); im5, m5 = trk.augment(img, (seq.ground_truth(a.frames - 1) == 1).byte().to(dev)); torch.cuda.synchronize()
     print("augment       %.1f ms (host)" % ((time.time() - t0) * 1e3))
-    nh, _ = trk.feature_extractor.forward_nhwc(im5, (), upto="layer4")
-    print("backbone x5   %.3f ms" % timed(lambda: trk.feature_extractor.forward_nhwc(im5, (), upto="layer4")))
+    _, nh, _ = trk.feature_extractor.forward_split(im5, (), ("layer4",), upto="layer4")
+    print("backbone x5   %.3f ms" % timed(lambda: trk.feature_extractor.forward_split(im5, (), ("layer4",), upto="layer4")))
     from frtm_vos_b200.model.discriminator import Discriminator
     import golden_inputs as GI
     def do_init():
