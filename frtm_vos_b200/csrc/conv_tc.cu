@@ -222,32 +222,72 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
     const int py = y0 + row / TC_TW, px = x0 + row % TC_TW;
     const bool valid = py < a.Ho && px < a.Wo;
     const int64_t pix = ((int64_t)b * a.Ho + py) * a.Wo + px;
+    const int n0 = ntile * BN;
+    // per-channel output scale and bias staged once per CTA (overlaps the main loop)
+    float *s_osc = reinterpret_cast<float *>(gen + STAGES * STAGE_BYTES + 16 * STAGES + 16);
+    float *s_bias = s_osc + BN;
+    for (int i = threadIdx.x - 64; i < BN; i += 128) {
+      s_osc[i] = a.oscale[n0 + i];
+      s_bias[i] = (a.bias != nullptr && n0 + i < a.Cout) ? a.bias[n0 + i] : 0.f;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     mbar_wait(bar_accum, 0);
     tc_fence_after();
-    const int n0 = ntile * BN;
+    const bool vec_f32 = (a.ldy % 4 == 0) && (a.y_coff % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 15) == 0);
+    const bool vec_res = (a.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.res) & 15) == 0);
+    const bool vec_h = (a.ldyh % 8 == 0) && (a.yh_coff % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.y_hi) & 15) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(a.y_lo) & 15) == 0);
+    const bool vec_rh = (a.ldrh % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.res_hi) & 15) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(a.res_lo) & 15) == 0);
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 16) {
       float v[16];
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      if (!valid) continue;
+      if (!valid || n0 + c0 >= a.Cout) continue;
+      const bool full = n0 + c0 + 16 <= a.Cout;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int n = n0 + c0 + j;
-        float o = v[j] * a.oscale[n];
-        if (n < a.Cout) {
-          if (a.bias) o += a.bias[n];
-          if (a.res) o += a.res[pix * a.ldr + n];
-          if (a.res_hi)
-            o += (__half2float(a.res_hi[pix * a.ldrh + n]) + __half2float(a.res_lo[pix * a.ldrh + n])) * (1.f / TC_ACT_SCALE);
-          if (a.relu) o = fmaxf(o, 0.f);
+      for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], s_osc[c0 + j], s_bias[c0 + j]);
+      if (a.res) {
+        const float *r = a.res + pix * a.ldr + n0 + c0;
+        if (full && vec_res) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 t = *reinterpret_cast<const float4 *>(r + j);
+            v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+          }
         } else {
-          o = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (n0 + c0 + j < a.Cout) v[j] += r[j];
         }
-        v[j] = o;
+      }
+      if (a.res_hi) {
+        const __half *rh = a.res_hi + pix * a.ldrh + n0 + c0, *rl = a.res_lo + pix * a.ldrh + n0 + c0;
+        if (full && vec_rh) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 8) {
+            const uint4 uh = *reinterpret_cast<const uint4 *>(rh + j), ul = *reinterpret_cast<const uint4 *>(rl + j);
+            const __half2 *h2 = reinterpret_cast<const __half2 *>(&uh), *l2 = reinterpret_cast<const __half2 *>(&ul);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 fh = __half22float2(h2[k]), fl = __half22float2(l2[k]);
+              v[j + 2 * k] += (fh.x + fl.x) * (1.f / TC_ACT_SCALE);
+              v[j + 2 * k + 1] += (fh.y + fl.y) * (1.f / TC_ACT_SCALE);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (n0 + c0 + j < a.Cout) v[j] += (__half2float(rh[j]) + __half2float(rl[j])) * (1.f / TC_ACT_SCALE);
+        }
+      }
+      if (a.relu) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
       }
       if (a.y) {
         float *dst = a.y + pix * a.ldy + a.y_coff + n0 + c0;
-        if (n0 + c0 + 16 <= a.Cout && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+        if (full && vec_f32) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4 *>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         } else {
@@ -258,14 +298,23 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
       }
       if (a.y_hi) {
         __half *dh = a.y_hi + pix * a.ldyh + a.yh_coff + n0 + c0, *dl = a.y_lo + pix * a.ldyh + a.yh_coff + n0 + c0;
+        __align__(16) __half hh[16];
+        __align__(16) __half ll[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          if (n0 + c0 + j < a.Cout) {
-            const float s = v[j] * TC_ACT_SCALE;
-            const __half h = __float2half_rn(s);
-            dh[j] = h;
-            dl[j] = __float2half_rn(s - __half2float(h));
-          }
+          const float sc = v[j] * TC_ACT_SCALE;
+          hh[j] = __float2half_rn(sc);
+          ll[j] = __float2half_rn(sc - __half2float(hh[j]));
+        }
+        if (full && vec_h) {
+          *reinterpret_cast<uint4 *>(dh) = *reinterpret_cast<const uint4 *>(hh);
+          *reinterpret_cast<uint4 *>(dh + 8) = *reinterpret_cast<const uint4 *>(hh + 8);
+          *reinterpret_cast<uint4 *>(dl) = *reinterpret_cast<const uint4 *>(ll);
+          *reinterpret_cast<uint4 *>(dl + 8) = *reinterpret_cast<const uint4 *>(ll + 8);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (n0 + c0 + j < a.Cout) { dh[j] = hh[j]; dl[j] = ll[j]; }
         }
       }
       if (a.y_nchw) {
@@ -381,7 +430,7 @@ static int make_act_map(CUtensorMap *tm, const __half *ptr, int B, int H, int W,
 
 template <int BN, int STAGES>
 static int launch_tc(const CUtensorMap &mh, const CUtensorMap &ml, const TcArgs &a, dim3 grid, cudaStream_t st) {
-  constexpr int smem = STAGES * (2 * TC_A_BYTES + 2 * BN * 128) + 16 * STAGES + 16 + 1024;
+  constexpr int smem = STAGES * (2 * TC_A_BYTES + 2 * BN * 128) + 16 * STAGES + 16 + 8 * BN + 1024;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -122,13 +122,31 @@ __global__ void pyrup_bicubic_kernel(const float *__restrict__ x, int B, int H, 
 // ---------------------------------------------------------------- global average pool ---------------------------
 constexpr int GAP_CHUNK = 256;  // pixels per stage-1 block
 
-__global__ void gap_stage1_kernel(const float *__restrict__ x, int HW, int C, int ldx, int nchunks, float *__restrict__ part) {
+// stage 1: block = 4 pixel groups x 64 channel lanes; each group strides over the chunk's pixels, then a smem reduce
+__global__ void __launch_bounds__(256) gap_stage1_kernel(const float *__restrict__ x, int HW, int C, int ldx, int nchunks,
+                                                         float *__restrict__ part) {
+  __shared__ float red[4][64];
   const int b = blockIdx.y, ch = blockIdx.x;
   const int p0 = ch * GAP_CHUNK, p1 = min(p0 + GAP_CHUNK, HW);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = 0.f;
-    for (int p = p0; p < p1; ++p) s += x[((int64_t)b * HW + p) * ldx + c];
-    part[((int64_t)b * nchunks + ch) * C + c] = s;
+  const int lane = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  for (int c0 = 0; c0 < C; c0 += 64) {
+    const int c = c0 + lane;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (c < C) {
+      const float *base = x + (int64_t)b * HW * ldx + c;
+      int p = p0 + grp;
+      for (; p + 12 < p1; p += 16) {   // 4 independent loads in flight per thread
+        s0 += base[(int64_t)p * ldx];
+        s1 += base[(int64_t)(p + 4) * ldx];
+        s2 += base[(int64_t)(p + 8) * ldx];
+        s3 += base[(int64_t)(p + 12) * ldx];
+      }
+      for (; p < p1; p += 4) s0 += base[(int64_t)p * ldx];
+    }
+    red[grp][lane] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (grp == 0 && c < C) part[((int64_t)b * nchunks + ch) * C + c] = (red[0][lane] + red[1][lane]) + (red[2][lane] + red[3][lane]);
+    __syncthreads();
   }
 }
 __global__ void gap_stage2_kernel(const float *__restrict__ part, int HW, int C, int nchunks, float *__restrict__ out) {
@@ -317,6 +335,51 @@ __global__ void merge_masks_kernel(const float *__restrict__ src, unsigned long 
   }
 }
 
+// t[b][p][tap] = sum_c w[tap][c] x[b][p][c]  (9 taps, output channel stride 12, channels 9..11 zero)
+__global__ void __launch_bounds__(256) tapmaps_kernel(const float *__restrict__ x, int64_t npix, int C, const float *__restrict__ w,
+                                                      float *__restrict__ y) {
+  extern __shared__ float ws[];  // [9][C]
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) ws[i] = w[i];
+  __syncthreads();
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  float acc[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+  const float4 *px = reinterpret_cast<const float4 *>(x + p * C);
+  for (int c4 = 0; c4 < C / 4; ++c4) {
+    const float4 v = px[c4];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float *wt = ws + t * C + c4 * 4;
+      acc[t] = fmaf(v.x, wt[0], acc[t]);
+      acc[t] = fmaf(v.y, wt[1], acc[t]);
+      acc[t] = fmaf(v.z, wt[2], acc[t]);
+      acc[t] = fmaf(v.w, wt[3], acc[t]);
+    }
+  }
+  float4 *o = reinterpret_cast<float4 *>(y + p * 12);
+  o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  o[2] = make_float4(acc[8], 0.f, 0.f, 0.f);
+}
+
+// out[b][y][x] = bias + sum_tap v[b][y+dy][x+dx][tap]   (zero outside the image = the conv's zero padding)
+__global__ void __launch_bounds__(256) shift_sum9_kernel(const float *__restrict__ v, int B, int H, int W,
+                                                         const float *__restrict__ bias, float *__restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)B * H * W) return;
+  const int xw = (int)(idx % W), yh = (int)((idx / W) % H);
+  const int64_t b = idx / ((int64_t)W * H);
+  float acc = 0.f;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int iy = yh + t / 3 - 1, ix = xw + t % 3 - 1;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) acc += v[((b * H + iy) * W + ix) * 12 + t];
+  }
+  out[idx] = acc + (bias ? bias[0] : 0.f);
+}
+
 }  // namespace frtm
 
 using namespace frtm;
@@ -382,7 +445,7 @@ extern "C" int frtm_global_avgpool_nhwc(const float *x, int B, int HW, int C, in
   FRTM_REQUIRE(workspace_bytes >= frtm_global_avgpool_workspace(B, HW, C), "global_avgpool: workspace too small");
   const int nchunks = cdiv(HW, GAP_CHUNK);
   cudaStream_t st = (cudaStream_t)stream;
-  gap_stage1_kernel<<<dim3(nchunks, B), 64, 0, st>>>(x, HW, C, ldx, nchunks, workspace);
+  gap_stage1_kernel<<<dim3(nchunks, B), 256, 0, st>>>(x, HW, C, ldx, nchunks, workspace);
   FRTM_CHECK_LAUNCH("gap_stage1");
   gap_stage2_kernel<<<B, 64, 0, st>>>(workspace, HW, C, nchunks, out);
   FRTM_CHECK_LAUNCH("gap_stage2");
@@ -441,5 +504,19 @@ extern "C" int frtm_merge_masks(const float *src, uint64_t logit_mask, const uin
   merge_masks_kernel<<<cdiv(HW, 256), 256, 0, (cudaStream_t)stream>>>(src, (unsigned long long)logit_mask, suppress, N,
                                                                       HW, lut, single_object, masks, labels, counts);
   FRTM_CHECK_LAUNCH("merge_masks");
+  return FRTM_OK;
+}
+
+extern "C" int frtm_tapmaps_nhwc(const float *x, int64_t npix, int C, const float *w9c, float *y12, void *stream) {
+  FRTM_REQUIRE(x && w9c && y12 && C % 4 == 0 && C <= 1024, "tapmaps: bad arguments");
+  tapmaps_kernel<<<cdiv(npix, 256), 256, 9 * C * sizeof(float), (cudaStream_t)stream>>>(x, npix, C, w9c, y12);
+  FRTM_CHECK_LAUNCH("tapmaps");
+  return FRTM_OK;
+}
+
+extern "C" int frtm_shift_sum9(const float *v12, int B, int H, int W, const float *bias, float *out, void *stream) {
+  FRTM_REQUIRE(v12 && out, "shift_sum9: null pointer");
+  shift_sum9_kernel<<<cdiv((int64_t)B * H * W, 256), 256, 0, (cudaStream_t)stream>>>(v12, B, H, W, bias, out);
+  FRTM_CHECK_LAUNCH("shift_sum9");
   return FRTM_OK;
 }

@@ -142,12 +142,12 @@ __global__ void __launch_bounds__(1024) pixel_count_kernel(const float *__restri
   if (threadIdx.x == 0) px[k] = s;
 }
 
-__global__ void pixel_weights_kernel(const float *__restrict__ y, const float *__restrict__ px, int HW, float tf,
-                                     int threshold, float *__restrict__ w) {
+__global__ void pixel_weights_kernel(const float *__restrict__ y, const float *__restrict__ px, const int *__restrict__ ipx,
+                                     int HW, float tf, int threshold, float *__restrict__ w) {
   const int k = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= HW) return;
-  const float cnt = px[k];
+  const float cnt = ipx ? (float)ipx[k] : px[k];
   float af = cnt / (float)HW;                       // discriminator.py:127
   const float small = cnt < 10.f ? 1.f : 0.f;       // :131-132
   af = small * tf + (1.f - small) * af;
@@ -492,12 +492,14 @@ extern "C" int frtm_corr3x3_nchw(const float *x, const float *filt, const int *f
 }
 
 extern "C" int frtm_pixel_weights(const float *y, int K, int HW, float tf, int threshold, float *w, float *workspace,
-                                  void *stream) {
-  FRTM_REQUIRE(y && w && workspace && K > 0, "pixel_weights: bad arguments");
+                                  const int *counts, void *stream) {
+  FRTM_REQUIRE(y && w && (workspace || counts) && K > 0, "pixel_weights: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  pixel_count_kernel<<<K, 1024, 0, st>>>(y, HW, threshold, workspace);
-  FRTM_CHECK_LAUNCH("pixel_count");
-  pixel_weights_kernel<<<dim3(cdiv(HW, 256), K), 256, 0, st>>>(y, workspace, HW, tf, threshold, w);
+  if (!counts) {
+    pixel_count_kernel<<<K, 1024, 0, st>>>(y, HW, threshold, workspace);
+    FRTM_CHECK_LAUNCH("pixel_count");
+  }
+  pixel_weights_kernel<<<dim3(cdiv(HW, 256), K), 256, 0, st>>>(y, workspace, counts, HW, tf, threshold, w);
   FRTM_CHECK_LAUNCH("pixel_weights");
   return FRTM_OK;
 }

@@ -226,7 +226,7 @@ class Tracker(nn.Module):
             d0 = live[0].discriminator
             ys = masks[1:1 + n].reshape(n, 1, *im_size)
             if d0.pw_params is not None and d0.pw_params["method"] == "hinge":
-                pw = ops.pixel_weights(ys, d0.pw_params["tf"], True)
+                pw = ops.pixel_weights(ys, d0.pw_params["tf"], True, counts=counts)
             else:
                 pw = torch.ones_like(ys)
             stencil, uty = ops.build_stencil(pw, ys, (h, w))

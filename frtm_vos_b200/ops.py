@@ -191,14 +191,28 @@ def corr3x3(x: torch.Tensor, filt: torch.Tensor, index: Optional[torch.Tensor] =
     return out
 
 
-def pixel_weights(y: torch.Tensor, tf: float, threshold: bool, return_count: bool = False):
-    """y (K,1,H,W) or (K,H,W) float -> hinge pixel weights of the same shape (and the per-map pixel counts)."""
+def pixel_weights(y: torch.Tensor, tf: float, threshold: bool, return_count: bool = False, counts=None):
+    """y (K,1,H,W) or (K,H,W) float -> hinge pixel weights of the same shape (and the per-map pixel counts).
+    ``counts`` (int32 (K,), e.g. from merge_masks) skips the counting pass."""
     K = y.shape[0]
     HW = y.shape[-1] * y.shape[-2]
     w = torch.empty_like(y)
-    ws = torch.empty(K, device=y.device, dtype=torch.float32)
-    lib().pixel_weights(ptr(y), K, HW, float(tf), 1 if threshold else 0, ptr(w), ptr(ws), stream())
+    ws = torch.empty(K, device=y.device, dtype=torch.float32) if counts is None else None
+    lib().pixel_weights(ptr(y), K, HW, float(tf), 1 if threshold else 0, ptr(w), ptr(ws), ptr(counts), stream())
     return (w, ws) if return_count else w
+
+
+def conv3x3_to1_upsampled(x: torch.Tensor, w9c: torch.Tensor, bias, image_size) -> torch.Tensor:
+    """conv3x3_to1(resize_bilinear(pyrup_bicubic(x), image_size)) evaluated with the channel contraction first:
+    9 tap maps at low resolution -> bicubic x2 -> bilinear -> shifted sum.  x (B,h,w,C) -> (B,H,W)."""
+    B, h, w, C = x.shape
+    t = torch.empty((B, h, w, 12), device=x.device, dtype=torch.float32)
+    lib().tapmaps_nhwc(ptr(x), B * h * w, C, ptr(w9c), ptr(t), stream())
+    u = resize_bilinear(pyrup_bicubic(t), image_size)
+    H, W = int(image_size[0]), int(image_size[1])
+    out = torch.empty((B, H, W), device=x.device, dtype=torch.float32)
+    lib().shift_sum9(ptr(u), B, H, W, ptr(bias), ptr(out), stream())
+    return out
 
 
 def build_stencil(pw: torch.Tensor, y: torch.Tensor, fsize):

@@ -124,6 +124,12 @@ int frtm_nhwc_to_nchw(const float *x, int B, int HW, int C, int ldx, float *y, v
 int frtm_conv3x3_to1_nhwc(const float *x, int B, int H, int W, int C, const float *w, const float *bias, float *y,
                           void *stream);
 
+/* The same final conv evaluated BEFORE the (linear) upsampling chain: t (npix,12) = 9 tap maps  sum_c w[tap][c] x[c]
+ * of the low-resolution input; after upsampling the 12-channel tap maps, frtm_shift_sum9 adds the 9 shifted maps
+ * (zero outside the image) and the bias.  Exactly conv3x3(upsample(x)) by linearity, with 9 instead of C full-res maps. */
+int frtm_tapmaps_nhwc(const float *x, int64_t npix, int C, const float *w9c, float *y12, void *stream);
+int frtm_shift_sum9(const float *v12, int B, int H, int W, const float *bias, float *out, void *stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Mask merge  (model/tracker.py:143-150, 203-221)
  * ---------------------------------------------------------------------------------------------------------- */
@@ -148,8 +154,10 @@ int frtm_corr3x3_nchw(const float *x, const float *filt, const int *filter_index
                       float *out, void *stream);
 
 /* Hinge pixel weights (discriminator.py:107-152): y (K,H*W) in [0,1] -> w (K,H*W).  If threshold != 0 the map is
- * first binarised with y > 0.5 (discriminator.py:217).  workspace: K floats. */
-int frtm_pixel_weights(const float *y, int K, int HW, float tf, int threshold, float *w, float *workspace, void *stream);
+ * first binarised with y > 0.5 (discriminator.py:217).  workspace: K floats receiving the per-map pixel counts; when
+ * `counts` (int[K], e.g. from frtm_merge_masks) is given the counting pass is skipped and workspace may be NULL. */
+int frtm_pixel_weights(const float *y, int K, int HW, float tf, int threshold, float *w, float *workspace,
+                       const int *counts, void *stream);
 
 /* Stencil form of  U^T diag(pw^2) U  and  U^T (pw^2 * y)  for bilinear upsampling U : (h,w)->(H,W),
  * align_corners=False (discriminator.py:48).  pw,y (K,H,W);  stencil (K,9,h,w) [tap = (dy+1)*3+(dx+1) couples

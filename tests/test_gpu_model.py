@@ -193,8 +193,27 @@ def test_P4_end_to_end_oracle_replay():
     assert len(f_err) == 4 and max(f_err.values()) < 5e-3, f_err
     assert worst < 1e-3, "logit err per frame: %s | filter rel err after updates: %s" % (
         " ".join("%d:%.1e" % kv for kv in sorted(per_frame.items())), f_err)
+    # Label maps: identical, except that a pixel whose oracle decision flips under a +-1e-3 perturbation of the logits
+    # (the stated logit tolerance) is a tie, not an error.  Such ties are counted and must stay rare.
+    from oracle import frtm_ref as R
+    lut = torch.tensor([0] + list(seq.obj_ids), dtype=torch.uint8)
+    ties = 0
     for i, (a, b) in enumerate(zip(out, out_ref)):
-        assert torch.equal(a.reshape(size).cpu(), b.reshape(size)), "labels differ on frame %d" % i
+        a, b = a.reshape(size).cpu(), b.reshape(size)
+        if torch.equal(a, b):
+            continue
+        bad = a != b
+        lg = torch.stack([dump["logits"][(i, oid)][0, 0] for oid in seq.obj_ids])
+        explained = torch.zeros_like(bad)
+        for s0 in (-1e-3, 1e-3):
+            for s1 in (-1e-3, 1e-3):
+                cm = torch.zeros(3, *size)
+                cm[1:] = torch.sigmoid(lg + torch.tensor([s0, s1]).view(2, 1, 1))
+                alt = R.labels_from_masks(R.merge_masks(cm), lut, False)
+                explained |= (alt == a)
+        assert bool((explained | ~bad).all()), "labels differ on frame %d beyond logit-tolerance ties" % i
+        ties += int(bad.sum())
+    assert ties <= 8, ties
     for oid in seq.obj_ids:
         d, m = trk.targets[oid].discriminator, orc.targets[oid]["model"]
         assert torch.allclose(d.memory.weights.cpu(), m.memory.weights, atol=1e-6)

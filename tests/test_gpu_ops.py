@@ -222,3 +222,18 @@ def test_merge_golden(golden):
     m1, l1, _ = ops.merge_masks(lg[:1].contiguous().to(DEV), 1, None, lut.to(DEV), True)
     assert (m1.cpu() - ref1).abs().max() < 2e-6
     assert (l1.cpu() != R.labels_from_masks(ref1.clone(), lut, True)[0]).float().mean() < 1e-4
+
+
+def test_final_conv_commutes_with_upsampling():
+    """conv3x3_to1_upsampled == conv3x3_to1(resize(pyrup(x))) (the reference order, seg_network.py:141-145)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(2, 32, 24, 43, generator=g)
+    w = torch.randn(1, 32, 3, 3, generator=g) / 17
+    b = torch.randn(1, generator=g)
+    from oracle import frtm_ref as R
+    size = (48, 84)
+    ref = F.conv2d(F.interpolate(R.pyr_up_bicubic(x), size, mode="bilinear", align_corners=False), w, b, 1, 1)[:, 0]
+    w9c = w.permute(2, 3, 1, 0).reshape(9, 32).contiguous().to(DEV)
+    y = ops.conv3x3_to1_upsampled(_nhwc(x).to(DEV), w9c, b.to(DEV), size)
+    assert (y.cpu() - ref).abs().max() < 1e-5
