@@ -195,16 +195,13 @@ def main():
 
     seq.preload(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    gather_buf = None
 
     def step(sequence, read_back=False):
         outs, _ = trk.run_sequence(sequence)
         labels = torch.stack([o.reshape(cfg["size"]) for o in outs])
         if world > 1:
-            nonlocal gather_buf
-            if gather_buf is None:
-                gather_buf = torch.empty((world,) + tuple(labels.shape), dtype=torch.uint8, device=dev)
-            dist.all_gather_into_tensor(gather_buf, labels)       # end-of-batch gather of the label maps (NCCL/NVLink)
+            from frtm_vos_b200.parallel import gather_label_maps
+            gather_label_maps(labels.unsqueeze(0), world)        # end-of-batch gather of the label maps (NCCL/NVLink)
         if read_back:
             return labels.cpu()
         return labels

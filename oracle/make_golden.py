@@ -250,6 +250,7 @@ def main():
     gen_update(ref)
     gen_init_step(ref)
     gen_feedforward(ref, "resnet18")
+    gen_feedforward(ref, "resnet101")
     gen_e2e(ref)
 
 

@@ -30,7 +30,7 @@ def _build(arch, bb, seg, dp):
     return trk, fe
 
 
-@pytest.mark.parametrize("arch", ["resnet18"])
+@pytest.mark.parametrize("arch", ["resnet18", "resnet101"])
 def test_P1_feedforward_fixed_state(arch, golden):
     from oracle import frtm_ref as R
     from frtm_vos_b200 import ops

@@ -72,10 +72,14 @@ def test_init_free_running(golden):
     assert np.allclose(tm.memory.weights.numpy(), g["w_fin"], atol=1e-7)
 
 
-def test_feedforward_fixed_state(golden):
-    g = golden("feedforward_resnet18")
-    case = GI.feedforward_case("resnet18")
-    feats = R.backbone_features(case["bb"], "resnet18", case["image"])
+import pytest
+
+
+@pytest.mark.parametrize("arch", ["resnet18", "resnet101"])
+def test_feedforward_fixed_state(golden, arch):
+    g = golden("feedforward_" + arch)
+    case = GI.feedforward_case(arch)
+    feats = R.backbone_features(case["bb"], arch, case["image"])
     for L in ("layer4", "layer5"):
         assert np.allclose(feats[L].numpy(), g["ft_" + L], atol=1e-4), L
     for L in ("layer1", "layer2", "layer3"):
