@@ -128,6 +128,142 @@ __global__ void corr3x3_grad_input_kernel(const float *__restrict__ v, const flo
   out[((int64_t)n * hw + pix) * c + ch] = acc;
 }
 
+// ---------------------------------------------------------------- fused J^T S J apply ----------------------------
+// One CTA per memory sample computes that sample's contribution to  g = X^T [ sw (S (X * p) - use_y t) ]  in a single
+// launch, streaming the sample (c x hw floats, NCHW) from HBM once and from L2 once:
+//   phase 1  tap maps   Y[tap][q] = sum_c X[c][q] p[c][tap]      (thread = 4 consecutive pixels, 36 FMAs per 16-byte load)
+//   phase 2  scores     s[q] = sum_tap Y[tap][q + tap];  v = sw (S s - use_y t)      (shared memory only)
+//   phase 3  gradient   g[c][tap] = sum_q X[c][q] v[q - tap]     (warp = 8 channels, lane = pixel group, 288 FMAs per
+//                                                                 36 shared loads; one shuffle reduction at the end)
+// Both passes are written around the SOURCE pixel q so every loaded element of X feeds 9 FMAs without touching its
+// neighbours; the spatial shifts are applied to the small maps (Y, v) held in shared memory instead.
+constexpr int GA_THREADS = 416;   // 13 warps: 405 pixel groups of a 30x54 map in one round; 12 channel octets in phase 3
+
+__global__ void __launch_bounds__(GA_THREADS, 1)
+gn_apply_kernel(const float *__restrict__ X, const float *__restrict__ S, const float *__restrict__ T,
+                const float *__restrict__ sw, const float *__restrict__ pvec, int c, int h, int w, int use_y,
+                float *__restrict__ partial) {
+  extern __shared__ __align__(16) float sm[];
+  const int hw = h * w, wp = w + 2, npad = (h + 2) * wp;
+  float *Y = sm;                       // [9][hw]
+  float *sp = Y + 9 * hw;              // padded scores
+  float *vp = sp + npad;               // padded v
+  float *ps = vp + npad;               // [c][12]
+  const int i = blockIdx.x;
+  const int n = c * 9;
+  const float wgt = sw[i];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (wgt == 0.f) {
+    for (int k = tid; k < n; k += GA_THREADS) partial[(int64_t)i * n + k] = 0.f;
+    return;
+  }
+  for (int k = tid; k < c * 12; k += GA_THREADS) {
+    const int ch = k / 12, t = k - ch * 12;
+    ps[k] = t < 9 ? pvec[ch * 9 + t] : 0.f;
+  }
+  for (int k = tid; k < 2 * npad; k += GA_THREADS) sp[k] = 0.f;   // sp and vp are contiguous
+  __syncthreads();
+  const float *Xi = X + (int64_t)i * c * hw;
+  const int ngroups = hw >> 2;       // hw % 4 == 0 is checked on the host
+
+  // ---- phase 1 ----
+  for (int g = tid; g < ngroups; g += GA_THREADS) {
+    float acc[4][9];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) acc[k][t] = 0.f;
+    const float4 *xp = reinterpret_cast<const float4 *>(Xi) + g;
+    const int stride4 = hw >> 2;
+#pragma unroll 1
+    for (int ch = 0; ch < c; ch += 4) {
+      float4 x4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) x4[u] = __ldg(xp + (int64_t)(ch + u) * stride4);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4 p0 = *reinterpret_cast<const float4 *>(ps + (ch + u) * 12);
+        const float4 p1 = *reinterpret_cast<const float4 *>(ps + (ch + u) * 12 + 4);
+        const float p8 = ps[(ch + u) * 12 + 8];
+        const float pv[9] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p8};
+        const float xv[4] = {x4[u].x, x4[u].y, x4[u].z, x4[u].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int t = 0; t < 9; ++t) acc[k][t] = fmaf(xv[k], pv[t], acc[k][t]);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+      *reinterpret_cast<float4 *>(Y + t * hw + 4 * g) = make_float4(acc[0][t], acc[1][t], acc[2][t], acc[3][t]);
+  }
+  __syncthreads();
+
+  // ---- phase 2: s[q] = sum_tap Y[tap][q + tap], then v = sw (S s - use_y t) ----
+  for (int q = tid; q < hw; q += GA_THREADS) {
+    const int py = q / w, px = q - py * w;
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int yy = py + t / 3 - 1, xx = px + t % 3 - 1;
+      if (yy >= 0 && yy < h && xx >= 0 && xx < w) s += Y[t * hw + yy * w + xx];
+    }
+    sp[(py + 1) * wp + px + 1] = s;
+  }
+  __syncthreads();
+  const float *Si = S + (int64_t)i * 9 * hw, *Ti = T + (int64_t)i * hw;
+  for (int q = tid; q < hw; q += GA_THREADS) {
+    const int py = q / w, px = q - py * w;
+    float a = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) a = fmaf(Si[t * hw + q], sp[(py + t / 3) * wp + px + t % 3], a);
+    if (use_y) a -= Ti[q];
+    vp[(py + 1) * wp + px + 1] = wgt * a;
+  }
+  __syncthreads();
+
+  // ---- phase 3: warp = channel octet, lane = pixel group ----
+  const int noct = c >> 3;
+  for (int oct = warp; oct < noct; oct += GA_THREADS / 32) {
+    float acc[8][9];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) acc[u][t] = 0.f;
+    const float4 *xo = reinterpret_cast<const float4 *>(Xi + (int64_t)oct * 8 * hw);
+    const int stride4 = hw >> 2;
+#pragma unroll 1
+    for (int g = lane; g < ngroups; g += 32) {
+      float4 x4[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) x4[u] = __ldg(xo + (int64_t)u * stride4 + g);
+      float V[4][9];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int q = 4 * g + k;
+        const int py = q / w, px = q - py * w;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) V[k][t] = vp[(py + 1 - (t / 3 - 1)) * wp + px + 1 - (t % 3 - 1)];
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float xv[4] = {x4[u].x, x4[u].y, x4[u].z, x4[u].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int t = 0; t < 9; ++t) acc[u][t] = fmaf(xv[k], V[k][t], acc[u][t]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const float r = warp_sum(acc[u][t]);
+        if (lane == 0) partial[(int64_t)i * n + (oct * 8 + u) * 9 + t] = r;
+      }
+  }
+}
+
 // ---------------------------------------------------------------- pixel weights ----------------------------------
 __global__ void __launch_bounds__(1024) pixel_count_kernel(const float *__restrict__ y, int HW, int threshold,
                                                            float *__restrict__ px) {
@@ -569,29 +705,29 @@ extern "C" int frtm_gn_update(const float *samples, const float *stencil, const 
   cg.f = filt; cg.p = cg_state; cg.rprev = cg_state + n; cg.rho = cg_state + 2 * n; cg.hasp = cg_state + 2 * n + 1;
   cg.r = partial + (int64_t)cap * n; cg.x = cg.r + n; cg.q = cg.x + n;
   cg.partial = partial; cg.n = n; cg.cap = cap; cg.reg2 = reg * reg; cg.minv = 1.f / precond; cg.forget = forget;
-  const size_t fsm = (size_t)n * sizeof(float);
-  dim3 gpix(cdiv(hw, 128), cap), gpix256(cdiv(hw, 256), cap), ggrad(cdiv(c, 8), cap);
-  // gating: the tiny vector kernel checks `gate` and skips all arithmetic; the streaming kernels are harmless
-  // (they only write workspace), so they are launched unconditionally to keep the stream free of host syncs.
+  (void)s; (void)v;
+  FRTM_REQUIRE(hw % 4 == 0 && c % 8 == 0, "gn_update: needs h*w %% 4 == 0 and c %% 8 == 0 (got %d, %d)", hw, c);
+  const size_t ga_smem = ((size_t)9 * hw + 2 * (size_t)(h + 2) * (w + 2) + (size_t)c * 12) * sizeof(float);
+  FRTM_REQUIRE(ga_smem <= 227 * 1024, "gn_update: feature map %dx%d too large for the shared-memory resident tap maps", h, w);
+  static size_t ga_configured = 0;
+  if (ga_smem > ga_configured) {
+    cudaError_t e = cudaFuncSetAttribute(gn_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ga_smem);
+    if (e != cudaSuccess) { set_error("gn_update: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return FRTM_ELAUNCH; }
+    ga_configured = ga_smem;
+  }
+  // gating: the tiny vector kernel checks `gate` and skips all arithmetic; the streaming kernel is harmless (it only
+  // writes workspace), so it is launched unconditionally to keep the stream free of host syncs.
   for (int gi = 0; gi < n_gn; ++gi) {
     const int iters = cg_iters[gi];
     if (iters <= 0) continue;
-    // RHS: s = X * f ; v = sw (S s - t) ; partial = X^T v
-    corr3x3_kernel<<<gpix, 128, fsm, st>>>(samples, filt, nullptr, c, h, w, s, 0, weights);
-    FRTM_CHECK_LAUNCH("gn_update/score(f)");
-    stencil_apply_kernel<<<gpix256, 256, 0, st>>>(stencil, s, uty, weights, h, w, 1, v);
-    FRTM_CHECK_LAUNCH("gn_update/stencil(rhs)");
-    corr3x3_grad_filter_kernel<<<ggrad, 256, 0, st>>>(samples, v, c, h, w, partial, weights);
-    FRTM_CHECK_LAUNCH("gn_update/grad(rhs)");
+    // RHS: partial_i = X_i^T sw_i (S_i (X_i * f) - t_i)
+    gn_apply_kernel<<<cap, GA_THREADS, ga_smem, st>>>(samples, stencil, uty, weights, filt, c, h, w, 1, partial);
+    FRTM_CHECK_LAUNCH("gn_update/apply(rhs)");
     cg_vector_kernel<<<1, 1024, 0, st>>>(cg, 0, gate_count, min_px);
     FRTM_CHECK_LAUNCH("gn_update/cg(rhs)");
     for (int it = 0; it < iters; ++it) {
-      corr3x3_kernel<<<gpix, 128, fsm, st>>>(samples, cg.p, nullptr, c, h, w, s, 0, weights);
-      FRTM_CHECK_LAUNCH("gn_update/score(p)");
-      stencil_apply_kernel<<<gpix256, 256, 0, st>>>(stencil, s, uty, weights, h, w, 0, v);
-      FRTM_CHECK_LAUNCH("gn_update/stencil");
-      corr3x3_grad_filter_kernel<<<ggrad, 256, 0, st>>>(samples, v, c, h, w, partial, weights);
-      FRTM_CHECK_LAUNCH("gn_update/grad");
+      gn_apply_kernel<<<cap, GA_THREADS, ga_smem, st>>>(samples, stencil, uty, weights, cg.p, c, h, w, 0, partial);
+      FRTM_CHECK_LAUNCH("gn_update/apply");
       cg_vector_kernel<<<1, 1024, 0, st>>>(cg, it == iters - 1 ? 2 : 1, gate_count, min_px);
       FRTM_CHECK_LAUNCH("gn_update/cg");
     }
