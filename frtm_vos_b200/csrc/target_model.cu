@@ -133,16 +133,35 @@ __global__ void corr3x3_grad_input_kernel(const float *__restrict__ v, const flo
 // launch, streaming the sample (c x hw floats, NCHW) from HBM once and from L2 once:
 //   phase 1  tap maps   Y[tap][q] = sum_c X[c][q] p[c][tap]      (thread = 4 consecutive pixels, 36 FMAs per 16-byte load)
 //   phase 2  scores     s[q] = sum_tap Y[tap][q + tap];  v = sw (S s - use_y t)      (shared memory only)
-//   phase 3  gradient   g[c][tap] = sum_q X[c][q] v[q - tap]     (warp = 8 channels, lane = pixel group, 288 FMAs per
+//   phase 3  gradient   g[c][tap] = sum_q X[c][q] v[q - tap]     (warp = 4 channels, lane = pixel group, 144 FMAs per
 //                                                                 36 shared loads; one shuffle reduction at the end)
 // Both passes are written around the SOURCE pixel q so every loaded element of X feeds 9 FMAs without touching its
 // neighbours; the spatial shifts are applied to the small maps (Y, v) held in shared memory instead.
-constexpr int GA_THREADS = 416;   // 13 warps: 405 pixel groups of a 30x54 map in one round; 12 channel octets in phase 3
+constexpr int GA_THREADS = 416;   // 13 warps: 405 pixel groups of a 30x54 map in one round; 24 channel quads in phase 3
 
-__global__ void __launch_bounds__(GA_THREADS, 1)
-gn_apply_kernel(const float *__restrict__ X, const float *__restrict__ S, const float *__restrict__ T,
-                const float *__restrict__ sw, const float *__restrict__ pvec, int c, int h, int w, int use_y,
-                float *__restrict__ partial) {
+// Pointer table for object-batched launches: rows {samples, stencil, uty, weights, filt, cg_state, gate_count} x n_obj.
+struct GaArgs {
+  const float *X, *S, *T, *sw, *pvec;   // single-object form (table == nullptr)
+  const long long *table;               // batched form: blockIdx.y = object
+  float *partial;                       // [n_obj][cap][c*9]
+  int n_obj, cap, c, h, w, use_y;
+};
+
+__global__ void __launch_bounds__(GA_THREADS, 1) gn_apply_kernel(const GaArgs a) {
+  const float *__restrict__ X = a.X, *__restrict__ S = a.S, *__restrict__ T = a.T, *__restrict__ sw = a.sw,
+                           *__restrict__ pvec = a.pvec;
+  float *__restrict__ partial = a.partial;
+  const int c = a.c, h = a.h, w = a.w, use_y = a.use_y;
+  if (a.table) {
+    const int o = blockIdx.y;
+    X = reinterpret_cast<const float *>(a.table[0 * a.n_obj + o]);
+    S = reinterpret_cast<const float *>(a.table[1 * a.n_obj + o]);
+    T = reinterpret_cast<const float *>(a.table[2 * a.n_obj + o]);
+    sw = reinterpret_cast<const float *>(a.table[3 * a.n_obj + o]);
+    // RHS pass linearises at the filter itself, CG passes apply the operator to the direction p (= cg_state[0:n])
+    pvec = reinterpret_cast<const float *>(a.table[(use_y ? 4 : 5) * a.n_obj + o]);
+    partial += (int64_t)o * a.cap * c * 9;
+  }
   extern __shared__ __align__(16) float sm[];
   const int hw = h * w, wp = w + 2, npad = (h + 2) * wp;
   float *Y = sm;                       // [9][hw]
@@ -166,7 +185,7 @@ gn_apply_kernel(const float *__restrict__ X, const float *__restrict__ S, const 
   const float *Xi = X + (int64_t)i * c * hw;
   const int ngroups = hw >> 2;       // hw % 4 == 0 is checked on the host
 
-  // ---- phase 1 ----
+  // ---- phase 1 ---- (register double buffering: the next 4 channels are in flight while the current 4 are consumed)
   for (int g = tid; g < ngroups; g += GA_THREADS) {
     float acc[4][9];
 #pragma unroll
@@ -175,11 +194,20 @@ gn_apply_kernel(const float *__restrict__ X, const float *__restrict__ S, const 
       for (int t = 0; t < 9; ++t) acc[k][t] = 0.f;
     const float4 *xp = reinterpret_cast<const float4 *>(Xi) + g;
     const int stride4 = hw >> 2;
+    float4 nx[4], nn[4];   // two groups of 4 channels in flight ahead of the one being consumed
+#pragma unroll
+    for (int u = 0; u < 4; ++u) nx[u] = __ldg(xp + (int64_t)u * stride4);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) nn[u] = (4 + u < c) ? __ldg(xp + (int64_t)(4 + u) * stride4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
     for (int ch = 0; ch < c; ch += 4) {
       float4 x4[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) x4[u] = __ldg(xp + (int64_t)(ch + u) * stride4);
+      for (int u = 0; u < 4; ++u) { x4[u] = nx[u]; nx[u] = nn[u]; }
+      if (ch + 8 < c) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) nn[u] = __ldg(xp + (int64_t)(ch + 8 + u) * stride4);
+      }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const float4 p0 = *reinterpret_cast<const float4 *>(ps + (ch + u) * 12);
@@ -222,21 +250,30 @@ gn_apply_kernel(const float *__restrict__ X, const float *__restrict__ S, const 
   }
   __syncthreads();
 
-  // ---- phase 3: warp = channel octet, lane = pixel group ----
-  const int noct = c >> 3;
-  for (int oct = warp; oct < noct; oct += GA_THREADS / 32) {
-    float acc[8][9];
+  // ---- phase 3: warp = channel quad, lane = pixel group; next group's loads in flight during the FMAs ----
+  const int nquad = c >> 2;
+  for (int quad = warp; quad < nquad; quad += GA_THREADS / 32) {
+    float acc[4][9];
 #pragma unroll
-    for (int u = 0; u < 8; ++u)
+    for (int u = 0; u < 4; ++u)
 #pragma unroll
       for (int t = 0; t < 9; ++t) acc[u][t] = 0.f;
-    const float4 *xo = reinterpret_cast<const float4 *>(Xi + (int64_t)oct * 8 * hw);
+    const float4 *xo = reinterpret_cast<const float4 *>(Xi + (int64_t)quad * 4 * hw);
     const int stride4 = hw >> 2;
+    float4 nx[4];
+    if (lane < ngroups) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) nx[u] = __ldg(xo + (int64_t)u * stride4 + lane);
+    }
 #pragma unroll 1
     for (int g = lane; g < ngroups; g += 32) {
-      float4 x4[8];
+      float4 x4[4];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) x4[u] = __ldg(xo + (int64_t)u * stride4 + g);
+      for (int u = 0; u < 4; ++u) x4[u] = nx[u];
+      if (g + 32 < ngroups) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) nx[u] = __ldg(xo + (int64_t)u * stride4 + g + 32);
+      }
       float V[4][9];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -246,7 +283,7 @@ gn_apply_kernel(const float *__restrict__ X, const float *__restrict__ S, const 
         for (int t = 0; t < 9; ++t) V[k][t] = vp[(py + 1 - (t / 3 - 1)) * wp + px + 1 - (t % 3 - 1)];
       }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < 4; ++u) {
         const float xv[4] = {x4[u].x, x4[u].y, x4[u].z, x4[u].w};
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -255,11 +292,11 @@ gn_apply_kernel(const float *__restrict__ X, const float *__restrict__ S, const 
       }
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u)
+    for (int u = 0; u < 4; ++u)
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         const float r = warp_sum(acc[u][t]);
-        if (lane == 0) partial[(int64_t)i * n + (oct * 8 + u) * 9 + t] = r;
+        if (lane == 0) partial[(int64_t)i * n + (quad * 4 + u) * 9 + t] = r;
       }
   }
 }
@@ -401,14 +438,32 @@ struct CgVec {
 // mode 0: finish RHS ( r = b = -(sum partial + reg^2 f) ), x = 0, apply the forgetting factor, then first direction.
 // mode 1: finish A p ( q = sum partial + reg^2 p ), alpha step, optional residual update, next direction.
 // mode 2: like mode 1 but last CG iteration of the GN step: no residual update, no new direction, f += x.
-__global__ void __launch_bounds__(1024) cg_vector_kernel(CgVec s, int mode, const int *__restrict__ gate, int min_px) {
+__global__ void __launch_bounds__(1024) cg_vector_kernel(CgVec s, int mode, const int *__restrict__ gate, int min_px,
+                                                         const long long *__restrict__ table, int n_obj) {
+  if (table) {   // object-batched: one CTA per object, pointers from the table
+    const int o = blockIdx.x;
+    float *cgst = reinterpret_cast<float *>(table[5 * n_obj + o]);
+    s.f = reinterpret_cast<float *>(table[4 * n_obj + o]);
+    s.p = cgst; s.rprev = cgst + s.n; s.rho = cgst + 2 * s.n; s.hasp = cgst + 2 * s.n + 1;
+    s.r += (int64_t)o * 3 * s.n; s.x += (int64_t)o * 3 * s.n; s.q += (int64_t)o * 3 * s.n;
+    s.partial += (int64_t)o * s.cap * s.n;
+    gate = reinterpret_cast<const int *>(table[6 * n_obj + o]);
+  }
   if (gate && gate[0] < min_px) return;
   __shared__ float red[32];
   const int t = threadIdx.x;
   const bool act = t < s.n;
   float g = 0.f;
-  if (act)
-    for (int k = 0; k < s.cap; ++k) g += s.partial[(int64_t)k * s.n + t];
+  if (act) {   // fixed summation order, 8 independent loads in flight
+    float g8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int k = 0;
+    for (; k + 8 <= s.cap; k += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) g8[u] += s.partial[(int64_t)(k + u) * s.n + t];
+    }
+    for (; k < s.cap; ++k) g8[0] += s.partial[(int64_t)k * s.n + t];
+    g = ((g8[0] + g8[1]) + (g8[2] + g8[3])) + ((g8[4] + g8[5]) + (g8[6] + g8[7]));
+  }
   float r = 0.f, p = 0.f, rp = 0.f;
   float rho = *s.rho;
   const bool hasp = *s.hasp != 0.f;
@@ -690,23 +745,16 @@ extern "C" int64_t frtm_gn_update_workspace(int cap, int c, int h, int w) {
   return (2 * cap * hw + cap * n + 3 * n + 64) * (int64_t)sizeof(float);
 }
 
-extern "C" int frtm_gn_update(const float *samples, const float *stencil, const float *uty, const float *weights, int cap,
-                              int c, int h, int w, float *filt, float *cg_state, const int *cg_iters, int n_gn, float reg,
-                              float precond, float forget, const int *gate_count, int min_px, float *workspace,
-                              int64_t workspace_bytes, void *stream) {
-  FRTM_REQUIRE(samples && stencil && uty && weights && filt && cg_state && cg_iters && workspace, "gn_update: null pointer");
+static int gn_update_impl(const float *samples, const float *stencil, const float *uty, const float *weights,
+                          const long long *table, int n_obj, int cap, int c, int h, int w, float *filt, float *cg_state,
+                          const int *cg_iters, int n_gn, float reg, float precond, float forget, const int *gate_count,
+                          int min_px, float *workspace, int64_t workspace_bytes, cudaStream_t st) {
+  FRTM_REQUIRE(cg_iters && workspace && n_obj >= 1, "gn_update: null pointer");
   FRTM_REQUIRE(c * 9 <= 1024, "gn_update: filter too large for the single-block CG kernel (c*9 <= 1024)");
-  FRTM_REQUIRE(workspace_bytes >= frtm_gn_update_workspace(cap, c, h, w), "gn_update: workspace too small");
+  FRTM_REQUIRE(workspace_bytes >= n_obj * frtm_gn_update_workspace(cap, c, h, w), "gn_update: workspace too small");
   FRTM_REQUIRE(forget > 0.f, "gn_update: direction_forget_factor must be > 0 (0 = reset is not used on this path)");
-  cudaStream_t st = (cudaStream_t)stream;
   const int n = c * 9, hw = h * w;
-  float *s = workspace, *v = s + (int64_t)cap * hw, *partial = v + (int64_t)cap * hw;
-  CgVec cg;
-  cg.f = filt; cg.p = cg_state; cg.rprev = cg_state + n; cg.rho = cg_state + 2 * n; cg.hasp = cg_state + 2 * n + 1;
-  cg.r = partial + (int64_t)cap * n; cg.x = cg.r + n; cg.q = cg.x + n;
-  cg.partial = partial; cg.n = n; cg.cap = cap; cg.reg2 = reg * reg; cg.minv = 1.f / precond; cg.forget = forget;
-  (void)s; (void)v;
-  FRTM_REQUIRE(hw % 4 == 0 && c % 8 == 0, "gn_update: needs h*w %% 4 == 0 and c %% 8 == 0 (got %d, %d)", hw, c);
+  FRTM_REQUIRE(hw % 4 == 0 && c % 4 == 0, "gn_update: needs h*w %% 4 == 0 and c %% 4 == 0 (got %d, %d)", hw, c);
   const size_t ga_smem = ((size_t)9 * hw + 2 * (size_t)(h + 2) * (w + 2) + (size_t)c * 12) * sizeof(float);
   FRTM_REQUIRE(ga_smem <= 227 * 1024, "gn_update: feature map %dx%d too large for the shared-memory resident tap maps", h, w);
   static size_t ga_configured = 0;
@@ -715,24 +763,55 @@ extern "C" int frtm_gn_update(const float *samples, const float *stencil, const 
     if (e != cudaSuccess) { set_error("gn_update: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return FRTM_ELAUNCH; }
     ga_configured = ga_smem;
   }
-  // gating: the tiny vector kernel checks `gate` and skips all arithmetic; the streaming kernel is harmless (it only
+  // workspace: partial[n_obj][cap][n] | per object r[n] x[n] q[n]
+  float *partial = workspace;
+  float *vecs = partial + (int64_t)n_obj * cap * n;
+  GaArgs ga;
+  ga.X = samples; ga.S = stencil; ga.T = uty; ga.sw = weights; ga.pvec = filt; ga.table = table; ga.partial = partial;
+  ga.n_obj = n_obj; ga.cap = cap; ga.c = c; ga.h = h; ga.w = w; ga.use_y = 1;
+  CgVec cg;
+  cg.f = filt; cg.p = cg_state; cg.rprev = cg_state ? cg_state + n : nullptr; cg.rho = cg_state ? cg_state + 2 * n : nullptr;
+  cg.hasp = cg_state ? cg_state + 2 * n + 1 : nullptr;
+  cg.r = vecs; cg.x = vecs + n; cg.q = vecs + 2 * n;
+  cg.partial = partial; cg.n = n; cg.cap = cap; cg.reg2 = reg * reg; cg.minv = 1.f / precond; cg.forget = forget;
+  const dim3 grid(cap, table ? n_obj : 1);
+  // gating: the tiny vector kernel checks the gate and skips all arithmetic; the streaming kernel is harmless (it only
   // writes workspace), so it is launched unconditionally to keep the stream free of host syncs.
   for (int gi = 0; gi < n_gn; ++gi) {
     const int iters = cg_iters[gi];
     if (iters <= 0) continue;
-    // RHS: partial_i = X_i^T sw_i (S_i (X_i * f) - t_i)
-    gn_apply_kernel<<<cap, GA_THREADS, ga_smem, st>>>(samples, stencil, uty, weights, filt, c, h, w, 1, partial);
+    ga.use_y = 1; ga.pvec = filt;        // RHS: partial_i = X_i^T sw_i (S_i (X_i * f) - t_i)
+    gn_apply_kernel<<<grid, GA_THREADS, ga_smem, st>>>(ga);
     FRTM_CHECK_LAUNCH("gn_update/apply(rhs)");
-    cg_vector_kernel<<<1, 1024, 0, st>>>(cg, 0, gate_count, min_px);
+    cg_vector_kernel<<<table ? n_obj : 1, 1024, 0, st>>>(cg, 0, gate_count, min_px, table, n_obj);
     FRTM_CHECK_LAUNCH("gn_update/cg(rhs)");
+    ga.use_y = 0; ga.pvec = cg.p;
     for (int it = 0; it < iters; ++it) {
-      gn_apply_kernel<<<cap, GA_THREADS, ga_smem, st>>>(samples, stencil, uty, weights, cg.p, c, h, w, 0, partial);
+      gn_apply_kernel<<<grid, GA_THREADS, ga_smem, st>>>(ga);
       FRTM_CHECK_LAUNCH("gn_update/apply");
-      cg_vector_kernel<<<1, 1024, 0, st>>>(cg, it == iters - 1 ? 2 : 1, gate_count, min_px);
+      cg_vector_kernel<<<table ? n_obj : 1, 1024, 0, st>>>(cg, it == iters - 1 ? 2 : 1, gate_count, min_px, table, n_obj);
       FRTM_CHECK_LAUNCH("gn_update/cg");
     }
   }
   return FRTM_OK;
+}
+
+extern "C" int frtm_gn_update(const float *samples, const float *stencil, const float *uty, const float *weights, int cap,
+                              int c, int h, int w, float *filt, float *cg_state, const int *cg_iters, int n_gn, float reg,
+                              float precond, float forget, const int *gate_count, int min_px, float *workspace,
+                              int64_t workspace_bytes, void *stream) {
+  FRTM_REQUIRE(samples && stencil && uty && weights && filt && cg_state, "gn_update: null pointer");
+  return gn_update_impl(samples, stencil, uty, weights, nullptr, 1, cap, c, h, w, filt, cg_state, cg_iters, n_gn, reg, precond,
+                        forget, gate_count, min_px, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int frtm_gn_update_batched(const void *table, int n_obj, int cap, int c, int h, int w, const int *cg_iters, int n_gn,
+                                      float reg, float precond, float forget, int min_px, float *workspace,
+                                      int64_t workspace_bytes, void *stream) {
+  FRTM_REQUIRE(table && n_obj >= 1, "gn_update_batched: null table");
+  return gn_update_impl(nullptr, nullptr, nullptr, nullptr, reinterpret_cast<const long long *>(table), n_obj, cap, c, h, w,
+                        nullptr, nullptr, cg_iters, n_gn, reg, precond, forget, nullptr, min_px, workspace, workspace_bytes,
+                        (cudaStream_t)stream);
 }
 
 // ---- joint (project, filter) GN/CG of Discriminator.init --------------------------------------------------------

@@ -137,7 +137,7 @@ class Discriminator(nn.Module):
         self.current_sample = cft
         return ops.corr3x3(cft, self.filter.weight).unsqueeze(1)
 
-    def update(self, train_y, gate_count=None, pw=None, stencil=None, uty=None):
+    def update(self, train_y, gate_count=None, pw=None, stencil=None, uty=None, run_optimizer=True):
         """train_y (1,1,H,W) merged soft mask (``:208-227``).  ``gate_count``: int32 device scalar with the number of
         pixels > 0.5 (computed here when not supplied by the tracker's merge kernel)."""
         if not self.update_filters or self.current_sample is None:
@@ -151,6 +151,6 @@ class Discriminator(nn.Module):
             if pw is None:
                 pw = pw_h if (self.pw_params and self.pw_params["method"] == "hinge") else torch.ones_like(train_y)
         self.memory.update(self.current_sample, train_y, pw, stencil, uty, gate_count=gate_count, min_px=self.min_px)
-        if self.frame_num % self.train_skipping != 0:
+        if self.frame_num % self.train_skipping != 0 or not run_optimizer:
             return
         self.update_optimizer.run(self.update_iters, gate_count=gate_count, min_px=self.min_px)

@@ -107,6 +107,7 @@ class Tracker(nn.Module):
         self.targets = dict()
         self._stack = None
         self._fbuf = None
+        self._gn_table = None
         self._lut = torch.tensor([0] + list(sequence.obj_ids), dtype=torch.uint8, device=self.device)
         N = 0
         if speedrun:
@@ -177,6 +178,7 @@ class Tracker(nn.Module):
             self._bind_filter(target)
             self.current_masks[target.index] = mask
         self._stack = None
+        self._gn_table = None
         return self.current_masks
 
     def _live(self):
@@ -217,7 +219,11 @@ class Tracker(nn.Module):
         else:
             src, suppress = logits, None
         total = n + len(fresh)
-        masks, labels, counts = ops.merge_masks(src, (1 << n) - 1, suppress, self._lut, len(self.object_ids) == 1)
+        if getattr(self, "_counts", None) is None or self._counts.numel() < total:
+            self._counts = torch.zeros(max(total, 8), dtype=torch.int32, device=src.device)   # stable address: it is
+            self._gn_table = None                                                             # referenced by the GN table
+        masks, labels, counts = ops.merge_masks(src, (1 << n) - 1, suppress, self._lut, len(self.object_ids) == 1,
+                                                counts=self._counts[:total])
         self.current_masks = masks
         self._last_labels = labels
 
@@ -232,5 +238,35 @@ class Tracker(nn.Module):
             stencil, uty = ops.build_stencil(pw, ys, (h, w))
             for k, t in enumerate(live):
                 t.discriminator.update(ys[k:k + 1], gate_count=counts[k:k + 1], pw=pw[k:k + 1], stencil=stencil[k:k + 1],
-                                       uty=uty[k:k + 1])
+                                       uty=uty[k:k + 1], run_optimizer=False)
+            due = [k for k, t in enumerate(live) if t.discriminator.frame_num % t.discriminator.train_skipping == 0]
+            if due:
+                self._batched_gn_update(live, due)
         return self.current_masks
+
+    def _batched_gn_update(self, live, due):
+        """One set of launches for the filter updates of all objects that are due on this frame (grid.y = object)."""
+        import ctypes
+        from .._lib import lib, ptr, stream
+        key = tuple((live[k].object_id, live[k].discriminator.filter.weight.data_ptr()) for k in due)
+        if getattr(self, "_gn_table", None) is None or self._gn_table[0] != key:
+            rows = [[], [], [], [], [], [], []]
+            for k in due:
+                d = live[k].discriminator
+                m = d.memory
+                for r, v in zip(rows, (m.samples, m.stencil, m.uty, m.weights, d.filter.weight, d.update_optimizer.cg_state)):
+                    r.append(v.data_ptr())
+                rows[6].append(self._counts.data_ptr() + 4 * k)
+            table = torch.tensor(rows, dtype=torch.int64).to(self._counts.device)
+            d0 = live[due[0]].discriminator
+            cap, c, h, w = d0.memory.samples.shape
+            nbytes = len(due) * lib().gn_update_workspace(cap, c, h, w)
+            ws = torch.empty(nbytes // 4, device=table.device, dtype=torch.float32)
+            self._gn_table = (key, table, ws, nbytes)
+        _, table, ws, nbytes = self._gn_table
+        d0 = live[due[0]].discriminator
+        cap, c, h, w = d0.memory.samples.shape
+        iters = [int(v) for v in d0.update_iters]
+        arr = (ctypes.c_int * len(iters))(*iters)
+        lib().gn_update_batched(ptr(table), len(due), cap, c, h, w, arr, len(iters), float(d0.filter_reg[-1]),
+                                float(d0.precond[-1]), float(d0.direction_forget_factor), int(d0.min_px), ptr(ws), nbytes, stream())

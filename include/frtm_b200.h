@@ -187,6 +187,13 @@ int frtm_gn_update(const float *samples, const float *stencil, const float *uty,
                    float precond, float forget, const int *gate_count, int min_px, float *workspace,
                    int64_t workspace_bytes, void *stream);
 int64_t frtm_gn_update_workspace(int cap, int c, int h, int w);
+/* The same update for n_obj objects in ONE set of launches (grid.y = object; the objects of a sequence update on the
+ * same frames).  table: device int64[7][n_obj] of device pointers, rows = {samples, stencil, uty, weights, filt,
+ * cg_state, gate_count (0 = ungated)}; all objects share cap, c, h, w and the schedule.  workspace >= n_obj times
+ * frtm_gn_update_workspace. */
+int frtm_gn_update_batched(const void *table, int n_obj, int cap, int c, int h, int w, const int *cg_iters_host, int n_gn,
+                           float reg, float precond, float forget, int min_px, float *workspace, int64_t workspace_bytes,
+                           void *stream);
 
 /* Joint (project, filter) Gauss-Newton / CG of Discriminator.init (discriminator.py:154-175; optimizer.py:55-157):
  *   s = F * (P x),  J[dP,dF] = F * (dP x) + dF * (P x)  on the low-resolution grid, normal equations through the
