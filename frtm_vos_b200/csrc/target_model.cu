@@ -131,13 +131,26 @@ __global__ void corr3x3_grad_input_kernel(const float *__restrict__ v, const flo
 // ---------------------------------------------------------------- fused J^T S J apply ----------------------------
 // One CTA per memory sample computes that sample's contribution to  g = X^T [ sw (S (X * p) - use_y t) ]  in a single
 // launch, streaming the sample (c x hw floats, NCHW) from HBM once and from L2 once:
-//   phase 1  tap maps   Y[tap][q] = sum_c X[c][q] p[c][tap]      (thread = 4 consecutive pixels, 36 FMAs per 16-byte load)
+//   phase 1  tap maps   Y[tap][q] = sum_c X[c][q] p[c][tap]      (thread = 2 consecutive pixels, 18 FMAs per 8-byte load)
 //   phase 2  scores     s[q] = sum_tap Y[tap][q + tap];  v = sw (S s - use_y t)      (shared memory only)
-//   phase 3  gradient   g[c][tap] = sum_q X[c][q] v[q - tap]     (warp = 4 channels, lane = pixel group, 144 FMAs per
-//                                                                 36 shared loads; one shuffle reduction at the end)
+//   phase 3  gradient   g[c][tap] = sum_q X[c][q] v[q - tap]     (warp = 4 channels, lane = pixel pair, 72 FMAs per
+//                                                                 12 shared loads; one shuffle reduction at the end)
 // Both passes are written around the SOURCE pixel q so every loaded element of X feeds 9 FMAs without touching its
 // neighbours; the spatial shifts are applied to the small maps (Y, v) held in shared memory instead.
-constexpr int GA_THREADS = 416;   // 13 warps: 405 pixel groups of a 30x54 map in one round; 24 channel quads in phase 3
+// Blackwell packed fp32 FMA (FFMA2): two independent IEEE fp32 FMAs per issue slot.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ void ffma2(unsigned long long &d, unsigned long long a, unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+
+constexpr int GA_THREADS = 832;   // 26 warps: 810 pixel pairs of a 30x54 map in one round; 24 channel quads in phase 3
 
 // Pointer table for object-batched launches: rows {samples, stencil, uty, weights, filt, cg_state, gate_count} x n_obj.
 struct GaArgs {
@@ -147,6 +160,7 @@ struct GaArgs {
   int n_obj, cap, c, h, w, use_y;
 };
 
+template <bool FAST>   // FAST: even width -> 8-byte loads and a shared 3x4 window per pixel pair
 __global__ void __launch_bounds__(GA_THREADS, 1) gn_apply_kernel(const GaArgs a) {
   const float *__restrict__ X = a.X, *__restrict__ S = a.S, *__restrict__ T = a.T, *__restrict__ sw = a.sw,
                            *__restrict__ pvec = a.pvec;
@@ -183,47 +197,58 @@ __global__ void __launch_bounds__(GA_THREADS, 1) gn_apply_kernel(const GaArgs a)
   for (int k = tid; k < 2 * npad; k += GA_THREADS) sp[k] = 0.f;   // sp and vp are contiguous
   __syncthreads();
   const float *Xi = X + (int64_t)i * c * hw;
-  const int ngroups = hw >> 2;       // hw % 4 == 0 is checked on the host
+  const int npairs = (hw + 1) >> 1;  // FAST: w even, so a pixel pair never straddles two rows and hw is even
+  const int stride2 = hw >> 1;
+  auto load2 = [&](const float *chan_base, int g) -> float2 {
+    if (FAST) return __ldg(reinterpret_cast<const float2 *>(chan_base) + g);
+    float2 r;
+    r.x = __ldg(chan_base + 2 * g);
+    r.y = (2 * g + 1 < hw) ? __ldg(chan_base + 2 * g + 1) : 0.f;
+    return r;
+  };
 
-  // ---- phase 1 ---- (register double buffering: the next 4 channels are in flight while the current 4 are consumed)
-  for (int g = tid; g < ngroups; g += GA_THREADS) {
-    float acc[4][9];
+  // ---- phase 1 ---- thread = pixel pair; taps are processed two at a time with packed FMAs (p pairs come straight out
+  // of the 16-byte shared loads, the pixel value is duplicated into both halves); the next 4 channels are in flight
+  for (int g = tid; g < npairs; g += GA_THREADS) {
+    unsigned long long acc[2][5];
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
+    for (int k = 0; k < 2; ++k)
 #pragma unroll
-      for (int t = 0; t < 9; ++t) acc[k][t] = 0.f;
-    const float4 *xp = reinterpret_cast<const float4 *>(Xi) + g;
-    const int stride4 = hw >> 2;
-    float4 nx[4], nn[4];   // two groups of 4 channels in flight ahead of the one being consumed
+      for (int t = 0; t < 5; ++t) acc[k][t] = 0ull;
+    float2 nx[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) nx[u] = __ldg(xp + (int64_t)u * stride4);
-#pragma unroll
-    for (int u = 0; u < 4; ++u) nn[u] = (4 + u < c) ? __ldg(xp + (int64_t)(4 + u) * stride4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int u = 0; u < 4; ++u) nx[u] = load2(Xi + (int64_t)u * hw, g);
 #pragma unroll 1
     for (int ch = 0; ch < c; ch += 4) {
-      float4 x4[4];
+      float2 x2[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { x4[u] = nx[u]; nx[u] = nn[u]; }
-      if (ch + 8 < c) {
+      for (int u = 0; u < 4; ++u) x2[u] = nx[u];
+      if (ch + 4 < c) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) nn[u] = __ldg(xp + (int64_t)(ch + 8 + u) * stride4);
+        for (int u = 0; u < 4; ++u) nx[u] = load2(Xi + (int64_t)(ch + 4 + u) * hw, g);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const float4 p0 = *reinterpret_cast<const float4 *>(ps + (ch + u) * 12);
-        const float4 p1 = *reinterpret_cast<const float4 *>(ps + (ch + u) * 12 + 4);
-        const float p8 = ps[(ch + u) * 12 + 8];
-        const float pv[9] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p8};
-        const float xv[4] = {x4[u].x, x4[u].y, x4[u].z, x4[u].w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-#pragma unroll
-          for (int t = 0; t < 9; ++t) acc[k][t] = fmaf(xv[k], pv[t], acc[k][t]);
+        const ulonglong2 pa = *reinterpret_cast<const ulonglong2 *>(ps + (ch + u) * 12);       // (p0,p1) (p2,p3)
+        const ulonglong2 pb = *reinterpret_cast<const ulonglong2 *>(ps + (ch + u) * 12 + 4);   // (p4,p5) (p6,p7)
+        const unsigned long long pc = *reinterpret_cast<const unsigned long long *>(ps + (ch + u) * 12 + 8);  // (p8,0)
+        const unsigned long long xa = pack2(x2[u].x, x2[u].x), xb = pack2(x2[u].y, x2[u].y);
+        ffma2(acc[0][0], xa, pa.x); ffma2(acc[0][1], xa, pa.y); ffma2(acc[0][2], xa, pb.x); ffma2(acc[0][3], xa, pb.y);
+        ffma2(acc[0][4], xa, pc);
+        ffma2(acc[1][0], xb, pa.x); ffma2(acc[1][1], xb, pa.y); ffma2(acc[1][2], xb, pb.x); ffma2(acc[1][3], xb, pb.y);
+        ffma2(acc[1][4], xb, pc);
       }
     }
+    float y[2][10];
 #pragma unroll
-    for (int t = 0; t < 9; ++t)
-      *reinterpret_cast<float4 *>(Y + t * hw + 4 * g) = make_float4(acc[0][t], acc[1][t], acc[2][t], acc[3][t]);
+    for (int k = 0; k < 2; ++k)
+#pragma unroll
+      for (int t = 0; t < 5; ++t) unpack2(acc[k][t], y[k][2 * t], y[k][2 * t + 1]);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      Y[t * hw + 2 * g] = y[0][t];
+      if (2 * g + 1 < hw) Y[t * hw + 2 * g + 1] = y[1][t];
+    }
   }
   __syncthreads();
 
@@ -250,7 +275,7 @@ __global__ void __launch_bounds__(GA_THREADS, 1) gn_apply_kernel(const GaArgs a)
   }
   __syncthreads();
 
-  // ---- phase 3: warp = channel quad, lane = pixel group; next group's loads in flight during the FMAs ----
+  // ---- phase 3: warp = channel quad, lane = pixel pair; the next pair's loads are in flight during the FMAs ----
   const int nquad = c >> 2;
   for (int quad = warp; quad < nquad; quad += GA_THREADS / 32) {
     float acc[4][9];
@@ -258,37 +283,54 @@ __global__ void __launch_bounds__(GA_THREADS, 1) gn_apply_kernel(const GaArgs a)
     for (int u = 0; u < 4; ++u)
 #pragma unroll
       for (int t = 0; t < 9; ++t) acc[u][t] = 0.f;
-    const float4 *xo = reinterpret_cast<const float4 *>(Xi + (int64_t)quad * 4 * hw);
-    const int stride4 = hw >> 2;
-    float4 nx[4];
-    if (lane < ngroups) {
+    const float *xo = Xi + (int64_t)quad * 4 * hw;
+    float2 nx[4];
+    if (lane < npairs) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) nx[u] = __ldg(xo + (int64_t)u * stride4 + lane);
+      for (int u = 0; u < 4; ++u) nx[u] = load2(xo + (int64_t)u * hw, lane);
     }
+    int py = (2 * lane) / w, px = 2 * lane - py * w;   // advanced incrementally: +64 pixels per iteration
 #pragma unroll 1
-    for (int g = lane; g < ngroups; g += 32) {
-      float4 x4[4];
+    for (int g = lane; g < npairs; g += 32) {
+      float2 x2[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) x4[u] = nx[u];
-      if (g + 32 < ngroups) {
+      for (int u = 0; u < 4; ++u) x2[u] = nx[u];
+      if (g + 32 < npairs) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) nx[u] = __ldg(xo + (int64_t)u * stride4 + g + 32);
+        for (int u = 0; u < 4; ++u) nx[u] = load2(xo + (int64_t)u * hw, g + 32);
       }
-      float V[4][9];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int q = 4 * g + k;
-        const int py = q / w, px = q - py * w;
-#pragma unroll
-        for (int t = 0; t < 9; ++t) V[k][t] = vp[(py + 1 - (t / 3 - 1)) * wp + px + 1 - (t % 3 - 1)];
+      const int q = 2 * g;
+      if (g != lane) {
+        px += 64;
+        while (px >= w) { px -= w; ++py; }
       }
+      if (FAST) {
+        // v window of the pair (same row): rows py-1..py+1 (padded +1), columns px-1..px+2 (padded +1) -> 12 loads
+        float vw[3][4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float xv[4] = {x4[u].x, x4[u].y, x4[u].z, x4[u].w};
+        for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+          for (int cc = 0; cc < 4; ++cc) vw[r][cc] = vp[(py + r) * wp + px + cc];
+        // tap t=(dy,dx): pixel k needs v[(py - dy, px + k - dx)] = vw[1 - dy][k + 1 - dx]
 #pragma unroll
-          for (int t = 0; t < 9; ++t) acc[u][t] = fmaf(xv[k], V[k][t], acc[u][t]);
+        for (int t = 0; t < 9; ++t) {
+          const int dy = t / 3 - 1, dx = t % 3 - 1;
+          const float v0 = vw[1 - dy][1 - dx], v1 = vw[1 - dy][2 - dx];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc[u][t] = fmaf(x2[u].x, v0, fmaf(x2[u].y, v1, acc[u][t]));
+        }
+      } else {
+        const int q1 = q + 1;
+        const int py1 = q1 / w, px1 = q1 - py1 * w;
+        const bool has1 = q1 < hw;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const int dy = t / 3 - 1, dx = t % 3 - 1;
+          const float v0 = vp[(py + 1 - dy) * wp + px + 1 - dx];
+          const float v1 = has1 ? vp[(py1 + 1 - dy) * wp + px1 + 1 - dx] : 0.f;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc[u][t] = fmaf(x2[u].x, v0, fmaf(x2[u].y, v1, acc[u][t]));
+        }
       }
     }
 #pragma unroll
@@ -754,12 +796,14 @@ static int gn_update_impl(const float *samples, const float *stencil, const floa
   FRTM_REQUIRE(workspace_bytes >= n_obj * frtm_gn_update_workspace(cap, c, h, w), "gn_update: workspace too small");
   FRTM_REQUIRE(forget > 0.f, "gn_update: direction_forget_factor must be > 0 (0 = reset is not used on this path)");
   const int n = c * 9, hw = h * w;
-  FRTM_REQUIRE(hw % 4 == 0 && c % 4 == 0, "gn_update: needs h*w %% 4 == 0 and c %% 4 == 0 (got %d, %d)", hw, c);
+  FRTM_REQUIRE(c % 4 == 0, "gn_update: needs c %% 4 == 0 (got %d)", c);
+  const bool fast = (w % 2 == 0);
   const size_t ga_smem = ((size_t)9 * hw + 2 * (size_t)(h + 2) * (w + 2) + (size_t)c * 12) * sizeof(float);
   FRTM_REQUIRE(ga_smem <= 227 * 1024, "gn_update: feature map %dx%d too large for the shared-memory resident tap maps", h, w);
   static size_t ga_configured = 0;
   if (ga_smem > ga_configured) {
-    cudaError_t e = cudaFuncSetAttribute(gn_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ga_smem);
+    cudaError_t e = cudaFuncSetAttribute(gn_apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ga_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gn_apply_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ga_smem);
     if (e != cudaSuccess) { set_error("gn_update: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return FRTM_ELAUNCH; }
     ga_configured = ga_smem;
   }
@@ -781,13 +825,15 @@ static int gn_update_impl(const float *samples, const float *stencil, const floa
     const int iters = cg_iters[gi];
     if (iters <= 0) continue;
     ga.use_y = 1; ga.pvec = filt;        // RHS: partial_i = X_i^T sw_i (S_i (X_i * f) - t_i)
-    gn_apply_kernel<<<grid, GA_THREADS, ga_smem, st>>>(ga);
+    if (fast) gn_apply_kernel<true><<<grid, GA_THREADS, ga_smem, st>>>(ga);
+    else gn_apply_kernel<false><<<grid, GA_THREADS, ga_smem, st>>>(ga);
     FRTM_CHECK_LAUNCH("gn_update/apply(rhs)");
     cg_vector_kernel<<<table ? n_obj : 1, 1024, 0, st>>>(cg, 0, gate_count, min_px, table, n_obj);
     FRTM_CHECK_LAUNCH("gn_update/cg(rhs)");
     ga.use_y = 0; ga.pvec = cg.p;
     for (int it = 0; it < iters; ++it) {
-      gn_apply_kernel<<<grid, GA_THREADS, ga_smem, st>>>(ga);
+      if (fast) gn_apply_kernel<true><<<grid, GA_THREADS, ga_smem, st>>>(ga);
+      else gn_apply_kernel<false><<<grid, GA_THREADS, ga_smem, st>>>(ga);
       FRTM_CHECK_LAUNCH("gn_update/apply");
       cg_vector_kernel<<<table ? n_obj : 1, 1024, 0, st>>>(cg, it == iters - 1 ? 2 : 1, gate_count, min_px, table, n_obj);
       FRTM_CHECK_LAUNCH("gn_update/cg");
