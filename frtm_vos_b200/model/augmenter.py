@@ -12,9 +12,12 @@ draw order from ``numpy.random`` so that, with the same seed, the same views com
 * parameter lists are tiled, shuffled in attribute order and sliced (``:204-211``);
 * transforms compose ``T(loc)·skew·rot·scale·T(-centre)`` (``:262-265``).
 
-Inpainting stays on the host with OpenCV, exactly like the reference (``:297-340``); warps run with
-OpenCV on host tensors (the reference's CPU path, ``lib/image.py:46-50``).  This is outside the §8
-kernel scope; a device-side warp/blur/paste is the "next" row f1.
+Inpainting stays on the host with OpenCV, exactly like the reference (``:297-340``).  For CPU inputs the
+warps run with OpenCV (the reference's CPU path, ``lib/image.py:46-50``) and reproduce the reference
+bit for bit; for CUDA inputs the selected views are rendered by libfrtm_b200 kernels (``csrc/augment.cu``:
+bicubic affine warp, directional blur, alpha paste) — the B200-native counterpart of the reference's NPP
+extension ``lib/_npp/nppig.cpp``.  Like NPP's, the device bicubic is not
+bit-identical to OpenCV's fixed-point one; masks (the training labels) always come from the host path.
 """
 from __future__ import annotations
 
@@ -188,9 +191,10 @@ def target_locations(n: int, im_size) -> List[Tuple[float, float]]:
 class ImageAugmenter:
     """Drop-in for the reference class of the same name: ``augment_first_frame(im, mask)``."""
 
-    def __init__(self, parameters: dict):
+    def __init__(self, parameters: dict, device_render: bool = True):
         self.params = parameters
         self.max_retries = 100
+        self.device_render = device_render     # CUDA inputs: render the selected views with libfrtm_b200 kernels
 
     def _warp_mask(self, mask, fg_spec, bbox, size):
         T, _ = spec_transform(fg_spec, bbox, size)
@@ -214,6 +218,41 @@ class ImageAugmenter:
         obj = _blur_channels(obj, G)
         a = obj[3].unsqueeze(0) / 255
         return (obj[:3] * a + canvas * (1 - a)).byte()
+
+    def _render_device(self, bg_d, cut_d, fg_spec, bbox, bg_spec):
+        """Same view as ``_render`` rendered by libfrtm_b200 kernels: bg_d (3,H,W) / cut_d (4,H,W) uint8 on the GPU."""
+        import ctypes
+        from .._lib import lib, ptr, stream
+        L = lib()
+        H, W = bg_d.shape[-2:]
+        dev = bg_d.device
+
+        def warp(src, T):
+            C = src.shape[0]
+            out = torch.empty((C, H, W), device=dev, dtype=torch.float32)
+            M = (ctypes.c_double * 6)(*np.asarray(T, dtype=np.float32)[:2, :].astype(np.float64).ravel())
+            L.warp_affine(ptr(src), 1, C, H, W, ptr(out), None, H, W, M, 0, 0.0, 255.0, stream())
+            return out
+
+        def blur(img, G):
+            G = np.asarray(G, dtype=np.float32)
+            if G.shape == (1, 1):
+                return img
+            k = torch.from_numpy(np.ascontiguousarray(G)).to(dev)
+            out = torch.empty_like(img)
+            L.filter2d(ptr(img), img.shape[0], H, W, ptr(k), G.shape[0], G.shape[1], ptr(out), stream())
+            return out
+
+        if bg_spec is not None:
+            T, G = spec_transform(bg_spec, (W / 2, H / 2, W, H), (H, W), limit_scale=False)
+            canvas = blur(warp(bg_d, T), G)
+        else:
+            canvas = bg_d.float()
+        T, G = spec_transform(fg_spec, bbox, (H, W))
+        obj = blur(warp(cut_d, T), G)
+        out = torch.empty((3, H, W), device=dev, dtype=torch.uint8)
+        L.alpha_paste(ptr(obj), ptr(canvas), H, W, ptr(out), stream())
+        return out
 
     def augment_first_frame(self, im: torch.Tensor, lb: torch.Tensor):
         """(3,H,W) u8 + (1,H,W) u8 mask -> ((K,3,H,W) u8, (K,1,H,W) u8) on ``im.device`` (augmenter.py:473-555)."""
@@ -255,6 +294,12 @@ class ImageAugmenter:
             order = order[:want]
             cand = [cand[i] for i in order]
             masks = [masks[i] for i in order]
+        if dev.type == "cuda" and self.device_render:
+            # rendering (bicubic warps, blur, alpha paste) on the GPU; inpainting, spec drawing and the nearest-neighbour
+            # mask warps above stay on the host like in the reference
+            bg_d, cut_d = bg.to(dev), cut.to(dev)
+            views = [self._render_device(bg_d, cut_d, fs, bbox, bs) for fs, bs in cand]
+            return torch.stack([im] + views), torch.stack([lb_h] + masks).to(dev)
         views = [self._render(bg, cut, fs, bbox, bs) for fs, bs in cand]
         views.insert(0, im_h)
         masks.insert(0, lb_h)

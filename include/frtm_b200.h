@@ -212,6 +212,21 @@ int frtm_gn_init_probe(const float *x_nhwc, const float *stencil, const float *u
 int frtm_stencil_apply(const float *stencil, const float *s, const float *uty, const float *sw, int NB, int h, int w,
                        int use_y, float *v, void *stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * First-frame augmentation rendering  (model/augmenter.py:342-396, lib/image.py:38-59, lib/_npp/nppig.cpp:48-104)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* Affine warp of a (C,H,W) uint8 or float image into (C,Ho,Wo).  M_host: 6 doubles (row-major 2x3) mapping source ->
+ * destination exactly as cv2.warpAffine / nppiWarpAffine take it (the kernel samples at the inverse).  Bicubic
+ * (a = -0.75) or nearest; samples outside the source read 0; the bicubic result is clamped to [clamp_lo, clamp_hi]
+ * (the reference clamps to [0,255] right after the warp, augmenter.py:357,384).  Replaces nppig.cpp warp_affine. */
+int frtm_warp_affine(const void *src, int src_is_u8, int C, int H, int W, float *dst_f32, uint8_t *dst_u8, int Ho, int Wo,
+                     const double *M_host, int nearest, float clamp_lo, float clamp_hi, void *stream);
+/* Per-channel 2-D cross-correlation with zero padding kh/2, kw/2 (the directional blur, augmenter.py:342-350). */
+int frtm_filter2d(const float *src, int C, int H, int W, const float *kernel, int kh, int kw, float *dst, void *stream);
+/* out (3,H,W) uint8 = rgba[:3] * a + canvas * (1 - a), a = rgba[3] / 255, truncated (augmenter.py:391-394). */
+int frtm_alpha_paste(const float *rgba, const float *canvas, int H, int W, uint8_t *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
