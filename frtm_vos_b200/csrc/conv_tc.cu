@@ -430,6 +430,43 @@ __global__ void rank1_finish_kernel(const float *__restrict__ yin, int ldin, int
   }
 }
 
+// Device-side packer for 1x1 weights that change at run time (the target models' projection matrices): W (Cout,Cin) fp32
+// -> the tile layout of TcArgs::wt with per-row power-of-two scaling, and oscale.  One block per output row.
+__global__ void __launch_bounds__(256) pack_tc_1x1_kernel(const float *__restrict__ W, int Cout, int Cin, int BN,
+                                                          __half *__restrict__ wt, float *__restrict__ oscale) {
+  __shared__ float red[32];
+  const int n = blockIdx.x;                       // 0 .. cout_pad-1
+  const int nkc = Cin / TC_BK;
+  const int ntile = n / BN, r = n - ntile * BN;
+  float amax = 0.f;
+  if (n < Cout)
+    for (int k = threadIdx.x; k < Cin; k += blockDim.x) amax = fmaxf(amax, fabsf(W[(int64_t)n * Cin + k]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = amax;
+  __syncthreads();
+  amax = 0.f;
+  for (int i = 0; i < (blockDim.x + 31) / 32; ++i) amax = fmaxf(amax, red[i]);
+  float scale = 1.f;
+  if (amax > 0.f) {
+    int e;
+    frexpf(amax, &e);                              // amax = m * 2^e, m in [0.5, 1)  ->  floor(log2(amax)) = e - 1
+    scale = ldexpf(1.f, 10 - e);                   // max |w| * scale in [2^9, 2^10)
+  }
+  if (threadIdx.x == 0) oscale[n] = (n < Cout) ? 1.f / (TC_ACT_SCALE * scale) : 1.f;
+  for (int k = threadIdx.x; k < Cin; k += blockDim.x) {
+    const float v = (n < Cout) ? W[(int64_t)n * Cin + k] * scale : 0.f;
+    const __half h = __float2half_rn(v);
+    const __half l = __float2half_rn(v - __half2float(h));
+    const int kc = k / TC_BK, kk = k - kc * TC_BK;
+    const int chunk = kk >> 3, e8 = kk & 7;
+    const int64_t tile = ((int64_t)ntile * nkc + kc) * 2;
+    const int64_t off = (int64_t)r * 64 + ((chunk ^ (r & 7)) << 3) + e8;
+    wt[(tile + 0) * BN * 64 + off] = h;
+    wt[(tile + 1) * BN * 64 + off] = l;
+  }
+}
+
 // ----------------------------------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------------------------------
@@ -535,5 +572,13 @@ extern "C" int frtm_rank1_finish(const float *y_in, int ldin, int n_obj, float *
   rank1_finish_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(y_in, ldin, n_obj, y_out, ldout, score, wx, bias, B, H,
                                                                           W, Cout, relu, (__half *)y_hi, (__half *)y_lo, ldh, extra);
   FRTM_CHECK_LAUNCH("rank1_finish");
+  return FRTM_OK;
+}
+
+extern "C" int frtm_pack_tc_1x1(const float *W, int Cout, int Cin, int bn_tile, void *wt, float *oscale, void *stream) {
+  FRTM_REQUIRE(W && wt && oscale && Cin % TC_BK == 0 && bn_tile % 8 == 0, "pack_tc_1x1: bad arguments");
+  const int cout_pad = cdiv(Cout, bn_tile) * bn_tile;
+  pack_tc_1x1_kernel<<<cout_pad, 256, 0, (cudaStream_t)stream>>>(W, Cout, Cin, bn_tile, (__half *)wt, oscale);
+  FRTM_CHECK_LAUNCH("pack_tc_1x1");
   return FRTM_OK;
 }

@@ -86,7 +86,7 @@ class Discriminator(nn.Module):
     # ---------------------------------------------------------------------------------------------------------
     def _project_nchw(self, x_nhwc):
         """(B,h,w,C) NHWC -> projected (B,c,h,w) NCHW (the layout memory samples are stored in)."""
-        pc = ops.pack_conv_tc(self.project.weight, device=self.project.weight.device)
+        pc = ops.pack_conv_tc_1x1_device(self.project.weight)
         return ops.conv2d_tc(ops.split_f16(x_nhwc), pc, out_f32=False, nchw=True)["nchw"]
 
     def compute_pixel_weights(self, y, threshold=False):

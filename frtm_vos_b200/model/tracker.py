@@ -10,7 +10,10 @@ initialisation, ``:130,159-161``), ``initialize``, ``track``, ``clear``, attribu
     launch, and the refinement network sees all objects as one batch;
   * sigmoid + suppression + clamp + softmax-merge + argmax gating + label LUT + the per-object ``> 0.5`` pixel counts
     are one fused kernel;
-  * the ``< 10 px`` update gate and the memory replace-index live on the device — no host sync inside the frame loop.
+  * the ``< 10 px`` update gate and the memory replace-index live on the device — no host sync inside the frame loop;
+  * ``run_sequence`` pushes up to 8 consecutive frames through backbone / projection / correlation / refinement as ONE
+    batch: masks never feed the next frame's forward pass and the filters only change every ``train_skipping`` frames
+    (``model/discriminator.py:221``), so the results are those of the frame-by-frame loop (SURVEY.md finding 4).
 """
 from __future__ import annotations
 
@@ -64,6 +67,8 @@ class Tracker(nn.Module):
         self.num_objects = 0
         self.targets = dict()
         self.object_ids = []
+        self.block_batching = True  # run_sequence batches up to max_block frames between two filter updates
+        self.max_block = 8
         self._stack = None          # cached stacked projection of the live objects
         self._fbuf = None           # (maxN, c, 3, 3) contiguous filters (each Discriminator.filter.weight is a view)
         self._last_labels = None
@@ -122,22 +127,45 @@ class Tracker(nn.Module):
             self._fbuf = None
 
         outputs = []
+        single = len(sequence.obj_ids) == 1
+        new_cache = {}
+
+        def item(i):
+            if i not in new_cache:
+                new_cache[i] = sequence[i]
+            return new_cache[i]
+
         t0 = time()
-        for i in range(len(sequence)):
-            image, labels, new_objects = sequence[i]
+        i = 0
+        n_frames = len(sequence)
+        while i < n_frames:
+            image, labels, new_objects = item(i)
             had_targets = len(self.targets) > 0
-            image = image.to(self.device)
-            if len(new_objects) > 0:
-                labels = labels.to(self.device)
-                self.initialize(image, labels, new_objects)
-            if had_targets:
-                self.track(image)
-                labels = self._last_labels if len(sequence.obj_ids) > 1 else self._last_labels.unsqueeze(0)
-            if isinstance(labels, list) and len(labels) == 0:
-                labels = image.new_zeros(1, *image.shape[-2:])
-            outputs.append(labels)
-            self.current_frame += 1
-            N += 1
+            if len(new_objects) > 0 or not had_targets:
+                image = image.to(self.device)
+                if len(new_objects) > 0:
+                    labels = labels.to(self.device)
+                    self.initialize(image, labels, new_objects)
+                if had_targets:
+                    self.track(image)
+                    labels = self._last_labels.unsqueeze(0) if single else self._last_labels
+                if isinstance(labels, list) and len(labels) == 0:
+                    labels = image.new_zeros(1, *image.shape[-2:])
+                outputs.append(labels)
+                self.current_frame += 1
+                new_cache.pop(i, None)
+                i += 1
+                N += 1
+                continue
+            nb = self._block_length(i, n_frames, lambda j: j < n_frames and len(item(j)[2]) > 0)
+            images = [item(j)[0].to(self.device, non_blocking=True) for j in range(i, i + nb)]
+            for lab in self._track_block(images):
+                outputs.append(lab.unsqueeze(0) if single else lab)
+            for j in range(i, i + nb):
+                new_cache.pop(j, None)
+            self.current_frame += nb
+            i += nb
+            N += nb
         torch.cuda.synchronize()
         T = time() - t0
         return outputs, N / T
@@ -188,61 +216,93 @@ class Tracker(nn.Module):
         key = tuple(t.object_id for t in live)
         if self._stack is None or self._stack[0] != key:
             W = torch.cat([t.discriminator.project.weight.detach() for t in live], dim=0)   # (N*c, C, 1, 1)
-            self._stack = (key, ops.pack_conv_tc(W, device=W.device))
+            self._stack = (key, ops.pack_conv_tc_1x1_device(W))
         return self._stack[1]
 
     def track(self, image):
-        im_size = image.shape[-2:]
-        feats, _, _ = self.feature_extractor.forward_split(image if image.dim() == 4 else image.unsqueeze(0))
+        """One frame (reference signature, ``:193-227``) = a block of one."""
+        self._track_block([image])
+        return self.current_masks
+
+    def _block_length(self, first, sequence_len, has_new):
+        """How many consecutive frames starting at ``first`` can go through the network as ONE batch with the
+        reference's semantics: masks never feed the next frame's forward pass, only the filters do, and those change
+        only when some live object reaches a multiple of ``train_skipping`` (SURVEY.md finding 4).  Frames on which
+        objects appear are processed alone."""
+        if has_new(first) or not self.block_batching:
+            return 1
+        live = self._live_at(first)
+        n = 0
+        while first + n < sequence_len and n < self.max_block:
+            if n > 0 and has_new(first + n):
+                break
+            n += 1
+            if any((t.discriminator.frame_num + n) % t.discriminator.train_skipping == 0 for t in live):
+                break
+        return max(n, 1)
+
+    def _live_at(self, frame):
+        return [t for t in self.targets.values() if t.start_frame < frame]
+
+    def _track_block(self, images):
+        """Tracks ``len(images)`` consecutive frames in one batched pass; returns the list of uint8 label maps."""
+        nF = len(images)
+        im_size = images[0].shape[-2:]
+        batch = torch.stack([im if im.dim() == 3 else im[0] for im in images]) if nF > 1 else \
+            (images[0] if images[0].dim() == 4 else images[0].unsqueeze(0))
+        feats, _, _ = self.feature_extractor.forward_split(batch)
         live = self._live()
         n = len(live)
         layer = live[0].disc_layer
         c = live[0].discriminator.filter.weight.shape[1]
         fmap = feats[layer]
         h, w = fmap.hi.shape[1:3]
+        dev = fmap.hi.device
 
-        # classify: one conv for all projections, one correlation for all filters
-        samples = ops.conv2d_tc(fmap, self._stacked_projection(live), out_f32=False, nchw=True)["nchw"].view(n, c, h, w)
-        if not hasattr(self, "_arange") or self._arange.numel() < n:
-            self._arange = torch.arange(max(n, 16), dtype=torch.int32, device=samples.device)
-        scores = ops.corr3x3(samples, self._fbuf, self._arange)
-        logits = self.refiner.forward_nhwc(scores, feats, im_size)
-        for k, t in enumerate(live):
-            t.discriminator.frame_num += 1
-            t.discriminator.current_sample = samples[k:k + 1]
+        # classify: one conv for all projections of all frames, one correlation for all filters
+        samples = ops.conv2d_tc(fmap, self._stacked_projection(live), out_f32=False, nchw=True)["nchw"].view(nF * n, c, h, w)
+        if getattr(self, "_fidx", None) is None or self._fidx[0] != (nF, n):
+            self._fidx = ((nF, n), torch.arange(n, dtype=torch.int32, device=dev).repeat(nF).contiguous())
+        scores = ops.corr3x3(samples, self._fbuf, self._fidx[1])
+        logits = self.refiner.forward_nhwc(scores, feats, im_size).view(nF, n, *im_size)
 
-        # merge (new objects of this frame take part with their start masks and suppress the others under them)
         fresh = [t for t in self.targets.values() if t.start_frame == self.current_frame]
-        if fresh:
-            src = torch.cat([logits] + [t.start_mask.reshape(1, *im_size).float() for t in fresh], dim=0)
-            suppress = torch.stack([t.start_mask.reshape(*im_size) for t in fresh]).amax(dim=0).contiguous()
-        else:
-            src, suppress = logits, None
+        assert not fresh or nF == 1
         total = n + len(fresh)
         if getattr(self, "_counts", None) is None or self._counts.numel() < total:
-            self._counts = torch.zeros(max(total, 8), dtype=torch.int32, device=src.device)   # stable address: it is
-            self._gn_table = None                                                             # referenced by the GN table
-        masks, labels, counts = ops.merge_masks(src, (1 << n) - 1, suppress, self._lut, len(self.object_ids) == 1,
-                                                counts=self._counts[:total])
-        self.current_masks = masks
-        self._last_labels = labels
-
-        # learn
-        if self.disc_params["update_filters"]:
-            d0 = live[0].discriminator
-            ys = masks[1:1 + n].reshape(n, 1, *im_size)
-            if d0.pw_params is not None and d0.pw_params["method"] == "hinge":
-                pw = ops.pixel_weights(ys, d0.pw_params["tf"], True, counts=counts)
+            self._counts = torch.zeros(max(total, 8), dtype=torch.int32, device=dev)   # stable address: it is
+            self._gn_table = None                                                      # referenced by the GN table
+        d0 = live[0].discriminator
+        hinge = d0.pw_params is not None and d0.pw_params["method"] == "hinge"
+        out_labels = []
+        for f in range(nF):
+            # merge (objects initialised on this frame take part with their start masks and suppress the others)
+            if fresh:
+                src = torch.cat([logits[f]] + [t.start_mask.reshape(1, *im_size).float() for t in fresh], dim=0)
+                suppress = torch.stack([t.start_mask.reshape(*im_size) for t in fresh]).amax(dim=0).contiguous()
             else:
-                pw = torch.ones_like(ys)
-            stencil, uty = ops.build_stencil(pw, ys, (h, w))
+                src, suppress = logits[f], None
+            masks, labels, counts = ops.merge_masks(src, (1 << n) - 1, suppress, self._lut, len(self.object_ids) == 1,
+                                                    counts=self._counts[:total])
+            out_labels.append(labels)
             for k, t in enumerate(live):
-                t.discriminator.update(ys[k:k + 1], gate_count=counts[k:k + 1], pw=pw[k:k + 1], stencil=stencil[k:k + 1],
-                                       uty=uty[k:k + 1], run_optimizer=False)
-            due = [k for k, t in enumerate(live) if t.discriminator.frame_num % t.discriminator.train_skipping == 0]
-            if due:
-                self._batched_gn_update(live, due)
-        return self.current_masks
+                t.discriminator.frame_num += 1
+                t.discriminator.current_sample = samples[f * n + k:f * n + k + 1]
+            # learn: memory insert every frame, filter update when due (always the last frame of a block)
+            if self.disc_params["update_filters"]:
+                ys = masks[1:1 + n].reshape(n, 1, *im_size)
+                pw = ops.pixel_weights(ys, d0.pw_params["tf"], True, counts=counts) if hinge else torch.ones_like(ys)
+                stencil, uty = ops.build_stencil(pw, ys, (h, w))
+                for k, t in enumerate(live):
+                    t.discriminator.update(ys[k:k + 1], gate_count=counts[k:k + 1], pw=pw[k:k + 1],
+                                           stencil=stencil[k:k + 1], uty=uty[k:k + 1], run_optimizer=False)
+                due = [k for k, t in enumerate(live) if t.discriminator.frame_num % t.discriminator.train_skipping == 0]
+                if due:
+                    assert f == nF - 1, "a filter update inside a block would change the following frames"
+                    self._batched_gn_update(live, due)
+            self.current_masks = masks
+            self._last_labels = labels
+        return out_labels
 
     def _batched_gn_update(self, live, due):
         """One set of launches for the filter updates of all objects that are due on this frame (grid.y = object)."""

@@ -390,3 +390,15 @@ def conv65(h: Split, score: torch.Tensor, pc: PackedConv65, n_obj: int = 1, relu
                        1 if relu else 0, None if sp is None else ptr(sp.hi), None if sp is None else ptr(sp.lo), 64, ptr(extra),
                        stream())
     return y, sp, extra
+
+
+def pack_conv_tc_1x1_device(weight: torch.Tensor, bn_tile: Optional[int] = None) -> PackedConvTC:
+    """(Cout,Cin[,1,1]) fp32 ON THE DEVICE -> PackedConvTC without a host round trip (no synchronisation)."""
+    w = weight.detach().reshape(weight.shape[0], -1).contiguous()
+    cout, cin = w.shape
+    tile = bn_tile or _pick_bn(cout)
+    cout_p = (cout + tile - 1) // tile * tile
+    wt = torch.empty(cout_p * cin * 2, device=w.device, dtype=torch.float16)
+    osc = torch.empty(cout_p, device=w.device, dtype=torch.float32)
+    lib().pack_tc_1x1(ptr(w), cout, cin, tile, ptr(wt), ptr(osc), stream())
+    return PackedConvTC(wt, osc, None, cin, cout, 1, tile, 1)

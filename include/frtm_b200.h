@@ -75,6 +75,9 @@ int frtm_conv2d_tc(const void *x_hi, const void *x_lo, int B, int H, int W, int 
                    const float *oscale, int bn_tile, const float *bias, const float *res, int ldr, const void *res_hi,
                    const void *res_lo, int ldrh, float *y, int ldy, int y_coff, float *y_nchw, void *y_hi, void *y_lo,
                    int ldyh, int yh_coff, int Cout, int kh, int kw, int stride, int relu, void *stream);
+/* Device-side weight packer for 1x1 convs whose weights change at run time (project.weight, model/discriminator.py:81):
+ * W (Cout,Cin) fp32 -> wt / oscale in the layout frtm_conv2d_tc expects (wt: cout_pad*Cin*2 halves, oscale: cout_pad). */
+int frtm_pack_tc_1x1(const float *W, int Cout, int Cin, int bn_tile, void *wt, float *oscale, void *stream);
 /* fp32 NHWC (npix, ldx)[0,C) -> fp16 planes hi, lo with hi + lo = 16 * x  (channel stride ldh, ldh % 8 == 0). */
 int frtm_split_f16(const float *x, int64_t npix, int C, int ldx, void *hi, void *lo, int ldh, void *stream);
 

@@ -103,3 +103,15 @@ def test_conv65(cout, n_obj):
     assert (_nchw(back) - ref[:, :64]).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item())
     if cout == 65:
         assert (extra.cpu() - ref[:, 64]).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item())
+
+
+def test_device_packer_matches_host_packer():
+    from frtm_vos_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    for cout, cin in [(96, 256), (288, 1024), (65, 64)]:
+        w = torch.randn(cout, cin, 1, 1, generator=g) * torch.logspace(-3, 1, cout).view(-1, 1, 1, 1)
+        w[3] = 0
+        a = ops.pack_conv_tc(w, None, device=DEV)
+        b = ops.pack_conv_tc_1x1_device(w.to(DEV))
+        assert a.bn == b.bn and torch.equal(a.oscale, b.oscale)
+        assert torch.equal(a.wt.view(torch.int16), b.wt.view(torch.int16))

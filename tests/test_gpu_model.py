@@ -150,7 +150,10 @@ def test_P4_end_to_end_oracle_replay():
 
     def spy(scores, feats, im_size):
         lg = orig_fwd(scores, feats, im_size)
-        got_logits[trk.current_frame] = lg.clone()
+        nF = feats["layer4"].hi.shape[0]                   # a block of frames goes through in one pass
+        per_frame_lg = lg.view(nF, -1, *lg.shape[-2:])
+        for f in range(nF):
+            got_logits[trk.current_frame + f] = per_frame_lg[f].clone()
         return lg
 
     trk.refiner.forward_nhwc = spy
@@ -172,18 +175,19 @@ def test_P4_end_to_end_oracle_replay():
 
     trk.initialize = init_and_inject
     got_F = {}
-    orig_track = trk.track
+    orig_block = trk._track_block
 
-    def track_and_record(image):
-        r = orig_track(image)
+    def block_and_record(images):
+        r = orig_block(images)
+        last = trk.current_frame + len(images) - 1          # filter updates happen on the last frame of a block
         for oid, t in trk.targets.items():
-            key = (trk.current_frame, oid)
+            key = (last, oid)
             if key in dump["F_upd"]:
                 got_F[key] = t.discriminator.filter.weight.detach().cpu().clone()
                 t.discriminator.filter.weight.data.copy_(dump["F_upd"][key])        # teacher-force the next frames
         return r
 
-    trk.track = track_and_record
+    trk._track_block = block_and_record
     torch.manual_seed(11)
     out, fps = trk.run_sequence(seq)
     f_err = {k: (got_F[k] - v).abs().max().item() / v.abs().max().item() for k, v in dump["F_upd"].items()}
@@ -237,6 +241,24 @@ def test_P5_end_to_end_free_running():
     agree = (a == b).float().mean().item()
     assert agree > 0.97, agree
     assert trk.targets[1].discriminator.memory.current_size == orc.targets[1]["model"].memory.size
+
+
+def test_block_batching_is_exact():
+    """Eight frames per pass must give exactly the frame-by-frame results (labels, filters, memory)."""
+    bb, seg, dp, seq, size = _e2e_setup()
+    res = []
+    for batching in (False, True):
+        trk, fe = _build("resnet18", bb, seg, dp)
+        trk.block_batching = batching
+        torch.manual_seed(11)
+        out, _ = trk.run_sequence(seq)
+        res.append((torch.stack([o.reshape(size).cpu() for o in out]),
+                    [trk.targets[o].discriminator.filter.weight.detach().cpu().clone() for o in seq.obj_ids],
+                    [trk.targets[o].discriminator.memory.weights.cpu().clone() for o in seq.obj_ids],
+                    [trk.targets[o].discriminator.memory.samples.cpu().clone() for o in seq.obj_ids]))
+    assert torch.equal(res[0][0], res[1][0])
+    for a, b in zip(res[0][1] + res[0][2] + res[0][3], res[1][1] + res[1][2] + res[1][3]):
+        assert torch.equal(a, b)
 
 
 def test_no_cpu_fallback():
