@@ -288,23 +288,25 @@ def main():
                     note="working set %.0f MB vs 126 MB L2: iterations after the first re-read it from L2" % (
                         M * 4 * (c + 10) * h * w / 1e6))
 
-    # ---- conv path: algorithmic FLOP/s of a tracked frame ---------------------------------------------------------
-    img = seq[len(seq) - 1][0]
+    # ---- conv path: algorithmic FLOP/s of one 8-frame block (the unit run_sequence executes) -------------------------
+    nblk = trk.max_block
+    imgs = [seq[len(seq) - 1 - j][0] for j in range(nblk)]
     for _ in range(2):
-        trk.track(img)
+        trk._track_block(imgs)           # frame_num stays aligned: every block ends on an update frame
     torch.cuda.synchronize()
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     c0.record()
-    for _ in range(8):
-        trk.track(img)
+    for _ in range(4):
+        trk._track_block(imgs)
     c1.record()
     torch.cuda.synchronize()
-    ms_track = c0.elapsed_time(c1) / 8
+    ms_track = c0.elapsed_time(c1) / (4 * nblk)
     gb, go = CONV_GFLOP[(cfg["arch"], cfg["size"][0])]
     conv_tflops = (gb + cfg["objects"] * go) / ms_track
     roofline_conv = dict(bound="tensor", achieved=conv_tflops, peak=pk["tensor"], unit="TFLOP/s", frac=conv_tflops / pk["tensor"],
-                         kernel="track(): backbone + %d x (project+filter+refinement); fp32 CUDA-core implicit GEMM" % cfg["objects"],
-                         ms_per_frame=ms_track, peak_source=pk["src"])
+                         kernel="8-frame track block: backbone + %d x (project+filter+refinement) + merge + memory insert + filter "
+                                "update; tcgen05 split-fp16 convs execute 3 MMAs per algorithmic MAC (executed tensor FLOPs = 3x)" % cfg["objects"],
+                         ms_per_frame=ms_track, algorithmic_gflop_per_frame=gb + cfg["objects"] * go, peak_source=pk["src"])
 
     if rank != 0:
         if world > 1:

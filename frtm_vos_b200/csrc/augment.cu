@@ -89,6 +89,27 @@ __global__ void alpha_paste_kernel(const float *__restrict__ rgba, const float *
   }
 }
 
+// Nearest-neighbour warp of a uint8 mask reproducing cv2.warpAffine(INTER_NEAREST) bit for bit: OpenCV inverts the
+// matrix in double precision, quantises the source coordinate to 1/1024 px per term (cvRound = round-half-even) and
+// rounds with +512 >> 10.  Also counts the pixels equal to `count_value` (the validity test of augmenter.py:453-471).
+__global__ void warp_mask_cv_kernel(const uint8_t *__restrict__ src, int H, int W, uint8_t *__restrict__ dst, int Ho, int Wo,
+                                    double i00, double i01, double i02, double i10, double i11, double i12, int count_value,
+                                    int *__restrict__ count) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  bool hit = false;
+  if (x < Wo) {
+    const int adx = __double2int_rn(i00 * x * 1024.0), ady = __double2int_rn(i10 * x * 1024.0);
+    const int X0 = __double2int_rn((i01 * y + i02) * 1024.0) + 512, Y0 = __double2int_rn((i11 * y + i12) * 1024.0) + 512;
+    const int sx = (X0 + adx) >> 10, sy = (Y0 + ady) >> 10;
+    uint8_t v = 0;
+    if (sx >= 0 && sx < W && sy >= 0 && sy < H) v = src[(int64_t)sy * W + sx];
+    dst[(int64_t)y * Wo + x] = v;
+    hit = v == count_value;
+  }
+  const unsigned b = __ballot_sync(0xffffffffu, hit);
+  if ((threadIdx.x & 31) == 0 && b) atomicAdd(count, __popc(b));
+}
+
 }  // namespace frtm
 
 using namespace frtm;
@@ -131,5 +152,23 @@ extern "C" int frtm_alpha_paste(const float *rgba, const float *canvas, int H, i
   const int64_t HW = (int64_t)H * W;
   alpha_paste_kernel<<<cdiv(HW, 256), 256, 0, (cudaStream_t)stream>>>(rgba, canvas, HW, out);
   FRTM_CHECK_LAUNCH("alpha_paste");
+  return FRTM_OK;
+}
+
+extern "C" int frtm_warp_mask_nearest(const uint8_t *src, int H, int W, uint8_t *dst, int Ho, int Wo, const double *M_host,
+                                      int count_value, int *count, void *stream) {
+  FRTM_REQUIRE(src && dst && M_host && count, "warp_mask_nearest: null pointer");
+  // cv::warpAffine's own inversion (imgwarp.cpp), in double
+  double M[6];
+  for (int i = 0; i < 6; ++i) M[i] = M_host[i];
+  double D = M[0] * M[4] - M[1] * M[3];
+  D = D != 0 ? 1. / D : 0;
+  const double A11 = M[4] * D, A22 = M[0] * D;
+  M[0] = A11; M[1] *= -D; M[3] *= -D; M[4] = A22;
+  const double b1 = -M[0] * M[2] - M[1] * M[5], b2 = -M[3] * M[2] - M[4] * M[5];
+  M[2] = b1; M[5] = b2;
+  warp_mask_cv_kernel<<<dim3(cdiv(Wo, 128), Ho), 128, 0, (cudaStream_t)stream>>>(src, H, W, dst, Ho, Wo, M[0], M[1], M[2], M[3],
+                                                                                 M[4], M[5], count_value, count);
+  FRTM_CHECK_LAUNCH("warp_mask_nearest");
   return FRTM_OK;
 }

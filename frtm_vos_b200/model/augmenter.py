@@ -144,6 +144,15 @@ def cut_and_inpaint(im: torch.Tensor, mask: torch.Tensor, d: int = 1, f: int = 1
     """Object cut-out (RGBA, feathered alpha) + Telea-inpainted background (augmenter.py:297-340)."""
     image = im.detach().cpu().numpy().transpose((1, 2, 0))
     m = (mask.squeeze() > 0).byte().detach().cpu().numpy()[..., None]
+    if d == 1 and f == 1:
+        # The configuration the tracker uses (augmenter.py:497).  With 1x1 structuring elements and 1x1 box blurs,
+        # erode/blur are identities: alpha = 255*m, and the "blur the inpainted border" blend x*r + (1-r)*x with
+        # r in {0,1} returns x exactly, so only the cut-out, the 2x2 dilation and the Telea inpaint remain.
+        cut = np.concatenate((m * image, m * 255), axis=-1)
+        outer = cv2.dilate(m, cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (2, 2)))
+        bg_np = cv2.inpaint(np.ascontiguousarray(image), outer, inpaintRadius=1, flags=cv2.INPAINT_TELEA)
+        return (torch.from_numpy(np.ascontiguousarray(cut.transpose((2, 0, 1)))),
+                torch.from_numpy(np.ascontiguousarray(bg_np.transpose((2, 0, 1)))))
     cut = m * image
     se = cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (f, f))
     alpha = cv2.blur(cv2.erode(m, se) * 255, (f, f))[..., None]
@@ -219,6 +228,23 @@ class ImageAugmenter:
         a = obj[3].unsqueeze(0) / 255
         return (obj[:3] * a + canvas * (1 - a)).byte()
 
+    def _warp_masks_device(self, mask_d, fg_specs, bbox, size):
+        """All candidate masks of a round warped on the GPU (bit-identical to cv2 INTER_NEAREST) + their pixel counts;
+        one device->host read of the counts for the whole round."""
+        import ctypes
+        from .._lib import lib, ptr, stream
+        L = lib()
+        H, W = size
+        n = len(fg_specs)
+        out = torch.empty((n, 1, H, W), device=mask_d.device, dtype=torch.uint8)
+        counts = torch.zeros(n, device=mask_d.device, dtype=torch.int32)
+        src = mask_d.reshape(H, W).contiguous()
+        for j, fs in enumerate(fg_specs):
+            T, _ = spec_transform(fs, bbox, size)
+            M = (ctypes.c_double * 6)(*np.asarray(T, dtype=np.float32)[:2, :].astype(np.float64).ravel())
+            L.warp_mask_nearest(ptr(src), H, W, ptr(out[j]), H, W, M, 1, counts[j:j + 1].data_ptr(), stream())
+        return out, counts.tolist()
+
     def _render_device(self, bg_d, cut_d, fg_spec, bbox, bg_spec):
         """Same view as ``_render`` rendered by libfrtm_b200 kernels: bg_d (3,H,W) / cut_d (4,H,W) uint8 on the GPU."""
         import ctypes
@@ -278,13 +304,19 @@ class ImageAugmenter:
         # The reference renders all 19 candidate views of a round and keeps 4 of the valid ones.  Validity depends
         # only on the (cheap, nearest-neighbour) warped mask, so decide first and render only the survivors: same
         # random draws, same selected views, ~5x less host work.
+        on_device = dev.type == "cuda" and self.device_render
         cand, masks = [], []
         while len(cand) < want:
             fg_specs = draw_specs(fg_pool)
             bg_specs = draw_specs(bg_pool) if bg_pool is not None else [None] * len(fg_specs)
-            for fs, bs in zip(fg_specs, bg_specs):
-                m = self._warp_mask(lb_h, fs, bbox, size)
-                px = int((m == 1).sum())
+            if on_device:
+                warped, counts = self._warp_masks_device(lb.to(dev), fg_specs, bbox, size)
+            for j, (fs, bs) in enumerate(zip(fg_specs, bg_specs)):
+                if on_device:
+                    m, px = warped[j], counts[j]
+                else:
+                    m = self._warp_mask(lb_h, fs, bbox, size)
+                    px = int((m == 1).sum())
                 if px >= lo and (px < hi or no_bg):
                     cand.append((fs, bs))
                     masks.append(m)
@@ -299,7 +331,7 @@ class ImageAugmenter:
             # mask warps above stay on the host like in the reference
             bg_d, cut_d = bg.to(dev), cut.to(dev)
             views = [self._render_device(bg_d, cut_d, fs, bbox, bs) for fs, bs in cand]
-            return torch.stack([im] + views), torch.stack([lb_h] + masks).to(dev)
+            return torch.stack([im] + views), torch.stack([lb.to(dev).reshape(1, *size)] + masks)
         views = [self._render(bg, cut, fs, bbox, bs) for fs, bs in cand]
         views.insert(0, im_h)
         masks.insert(0, lb_h)

@@ -225,6 +225,11 @@ int frtm_stencil_apply(const float *stencil, const float *s, const float *uty, c
  * (the reference clamps to [0,255] right after the warp, augmenter.py:357,384).  Replaces nppig.cpp warp_affine. */
 int frtm_warp_affine(const void *src, int src_is_u8, int C, int H, int W, float *dst_f32, uint8_t *dst_u8, int Ho, int Wo,
                      const double *M_host, int nearest, float clamp_lo, float clamp_hi, void *stream);
+/* Nearest-neighbour warp of a (H,W) uint8 mask, bit-identical to cv2.warpAffine(..., INTER_NEAREST) (OpenCV's 1/1024
+ * fixed-point coordinates), and the number of output pixels equal to count_value added to *count (device int, zeroed
+ * by the caller) — the visibility test of augmenter.py:453-471.  lib/image.py:53 with mode 'nearest'. */
+int frtm_warp_mask_nearest(const uint8_t *src, int H, int W, uint8_t *dst, int Ho, int Wo, const double *M_host,
+                           int count_value, int *count, void *stream);
 /* Per-channel 2-D cross-correlation with zero padding kh/2, kw/2 (the directional blur, augmenter.py:342-350). */
 int frtm_filter2d(const float *src, int C, int H, int W, const float *kernel, int kh, int kw, float *dst, void *stream);
 /* out (3,H,W) uint8 = rgba[:3] * a + canvas * (1 - a), a = rgba[3] / 255, truncated (augmenter.py:391-394). */

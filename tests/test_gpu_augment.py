@@ -44,3 +44,29 @@ def test_warp_affine_identity_and_shift():
     ref = torch.zeros(3, 40, 56)
     ref[:, :37, 5:] = src.cpu().float()[:, 3:, :51]
     assert torch.equal(out.cpu(), ref)
+
+
+def test_device_mask_warp_is_bit_identical_to_cv2():
+    import ctypes
+    import cv2
+    from frtm_vos_b200._lib import lib, ptr, stream
+    from frtm_vos_b200 import synth
+    from frtm_vos_b200.model import augmenter as A
+    seq = synth.SyntheticSequence(num_objects=3, num_frames=1, size=(480, 854), seq_id=2)
+    lb = seq[0][1]
+    np.random.seed(3)
+    for oid in (1, 2, 3):
+        mask = (lb == oid).byte()
+        bbox = A.mask_center_bbox(mask)
+        pool = dict(GI.AUG_PARAMS["fg_aug_params"])
+        pool["location"] = A.target_locations(5, (480, 854))
+        for spec in A.draw_specs(pool)[:8]:
+            T, _ = A.spec_transform(spec, bbox, (480, 854))
+            ref = A.warp_affine_host(mask, np.array(T, dtype=np.float32), (480, 854), "nearest")
+            M = (ctypes.c_double * 6)(*np.asarray(T, dtype=np.float32)[:2, :].astype(np.float64).ravel())
+            out = torch.empty((480, 854), device=DEV, dtype=torch.uint8)
+            cnt = torch.zeros(1, device=DEV, dtype=torch.int32)
+            lib().warp_mask_nearest(ptr(mask.to(DEV).reshape(480, 854).contiguous()), 480, 854, ptr(out), 480, 854, M, 1,
+                                    ptr(cnt), stream())
+            assert torch.equal(out.cpu(), ref.reshape(480, 854)), spec
+            assert int(cnt) == int((ref == 1).sum())
