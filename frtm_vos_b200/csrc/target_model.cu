@@ -13,38 +13,48 @@ namespace frtm {
 
 // ---------------------------------------------------------------- 3x3 correlation --------------------------------
 // out[n][pix] = sum_c sum_tap x[n][c][pix+tap] f[fi(n)][c][tap]      (+= if accumulate)
-__global__ void __launch_bounds__(128) corr3x3_kernel(const float *__restrict__ x, const float *__restrict__ filt,
+__global__ void __launch_bounds__(512) corr3x3_kernel(const float *__restrict__ x, const float *__restrict__ filt,
                                                       const int *__restrict__ fidx, int c, int h, int w,
                                                       float *__restrict__ out, int accumulate,
                                                       const float *__restrict__ skip_if_zero) {
-  extern __shared__ float fs[];  // [c][9]
+  // block = 128 pixels x 4 channel groups; partial sums are combined through shared memory in a fixed order
+  extern __shared__ float fs[];  // [c][9] then [4][128] partials
+  float *part = fs + c * 9;
   const int n = blockIdx.y;
   if (skip_if_zero && skip_if_zero[n] == 0.f) return;
   const float *f = filt + (int64_t)(fidx ? fidx[n] : 0) * c * 9;
   for (int i = threadIdx.x; i < c * 9; i += blockDim.x) fs[i] = f[i];
   __syncthreads();
   const int hw = h * w;
-  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= hw) return;
-  const int py = pix / w, px = pix - py * w;
-  bool ok[9];
-  int off[9];
-#pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    const int yy = py + t / 3 - 1, xx = px + t % 3 - 1;
-    ok[t] = yy >= 0 && yy < h && xx >= 0 && xx < w;
-    off[t] = yy * w + xx;
-  }
-  const float *xn = x + (int64_t)n * c * hw;
+  const int lp = threadIdx.x & 127, cg = threadIdx.x >> 7;
+  const int pix = blockIdx.x * 128 + lp;
   float acc = 0.f;
-  for (int ch = 0; ch < c; ++ch) {
-    const float *xc = xn + (int64_t)ch * hw;
+  if (pix < hw) {
+    const int py = pix / w, px = pix - py * w;
+    bool ok[9];
+    int off[9];
 #pragma unroll
-    for (int t = 0; t < 9; ++t)
-      if (ok[t]) acc = fmaf(xc[off[t]], fs[ch * 9 + t], acc);
+    for (int t = 0; t < 9; ++t) {
+      const int yy = py + t / 3 - 1, xx = px + t % 3 - 1;
+      ok[t] = yy >= 0 && yy < h && xx >= 0 && xx < w;
+      off[t] = yy * w + xx;
+    }
+    const float *xn = x + (int64_t)n * c * hw;
+    const int c0 = (c * cg) / 4, c1 = (c * (cg + 1)) / 4;
+    for (int ch = c0; ch < c1; ++ch) {
+      const float *xc = xn + (int64_t)ch * hw;
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+        if (ok[t]) acc = fmaf(xc[off[t]], fs[ch * 9 + t], acc);
+    }
   }
-  float *o = out + (int64_t)n * hw + pix;
-  *o = accumulate ? *o + acc : acc;
+  part[cg * 128 + lp] = acc;
+  __syncthreads();
+  if (cg == 0 && pix < hw) {
+    const float r = (part[lp] + part[128 + lp]) + (part[256 + lp] + part[384 + lp]);
+    float *o = out + (int64_t)n * hw + pix;
+    *o = accumulate ? *o + r : r;
+  }
 }
 
 // v[n][pix] = sw[n] * ( sum_tap S[n][tap][pix] s[n][pix+tap] - use_y * t[n][pix] )
@@ -657,7 +667,7 @@ __global__ void untranspose_kernel(const float *src, int rows, int cols, int ld,
 
 // ---------------------------------------------------------------- TN GEMM (J^T over pixels) ----------------------
 // out[m][n] = sum_k A[k][m] B[k][n],  A: K x M (lda), B: K x N (ldb); split-K partials [split][M][N].
-constexpr int TM_ = 64, TN_ = 96, TK_ = 16, KSPLIT = 512;
+constexpr int TM_ = 64, TN_ = 96, TK_ = 32, KSPLIT = 256;
 __global__ void __launch_bounds__(256) gemm_tn_kernel(const float *__restrict__ A, int lda, const float *__restrict__ Bm,
                                                       int ldb, int K, int M, int N, float *__restrict__ part) {
   __shared__ __align__(16) float As[TK_][TM_];
@@ -666,28 +676,54 @@ __global__ void __launch_bounds__(256) gemm_tn_kernel(const float *__restrict__ 
   const int m0 = blockIdx.x * TM_, split = blockIdx.y;
   const int k0 = split * KSPLIT, k1 = min(k0 + KSPLIT, K);
   const int tx = t & 15, ty = t >> 4;  // thread tile: 4 (m) x 6 (n)
+  const bool vecA = (lda % 4 == 0) && (m0 + TM_ <= M) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+  const bool vecB = (ldb % 4 == 0) && (N == TN_) && ((reinterpret_cast<uintptr_t>(Bm) & 15) == 0);
   float acc[4][6];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 6; ++j) acc[i][j] = 0.f;
   for (int kb = k0; kb < k1; kb += TK_) {
-    for (int i = t; i < TK_ * TM_; i += 256) {
-      const int kk = i / TM_, mm = i % TM_;
-      As[kk][mm] = (kb + kk < k1 && m0 + mm < M) ? A[(int64_t)(kb + kk) * lda + m0 + mm] : 0.f;
+    // A tile: 32 rows x 16 float4, B tile: 32 rows x 24 float4
+    for (int i = t; i < TK_ * (TM_ / 4); i += 256) {
+      const int kk = i / (TM_ / 4), m4 = (i % (TM_ / 4)) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kb + kk < k1) {
+        const float *src = A + (int64_t)(kb + kk) * lda + m0 + m4;
+        if (vecA) v = *reinterpret_cast<const float4 *>(src);
+        else {
+          if (m0 + m4 + 0 < M) v.x = src[0];
+          if (m0 + m4 + 1 < M) v.y = src[1];
+          if (m0 + m4 + 2 < M) v.z = src[2];
+          if (m0 + m4 + 3 < M) v.w = src[3];
+        }
+      }
+      *reinterpret_cast<float4 *>(&As[kk][m4]) = v;
     }
-    for (int i = t; i < TK_ * TN_; i += 256) {
-      const int kk = i / TN_, nn = i % TN_;
-      Bs[kk][nn] = (kb + kk < k1 && nn < N) ? Bm[(int64_t)(kb + kk) * ldb + nn] : 0.f;
+    for (int i = t; i < TK_ * (TN_ / 4); i += 256) {
+      const int kk = i / (TN_ / 4), n4 = (i % (TN_ / 4)) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kb + kk < k1) {
+        const float *src = Bm + (int64_t)(kb + kk) * ldb + n4;
+        if (vecB) v = *reinterpret_cast<const float4 *>(src);
+        else {
+          if (n4 + 0 < N) v.x = src[0];
+          if (n4 + 1 < N) v.y = src[1];
+          if (n4 + 2 < N) v.z = src[2];
+          if (n4 + 3 < N) v.w = src[3];
+        }
+      }
+      *reinterpret_cast<float4 *>(&Bs[kk][n4]) = v;
     }
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < TK_; ++kk) {
-      float a[4], b[6];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
-#pragma unroll
-      for (int j = 0; j < 6; ++j) b[j] = Bs[kk][tx * 6 + j];
+      const float4 a4 = *reinterpret_cast<const float4 *>(&As[kk][ty * 4]);
+      const float2 b0 = *reinterpret_cast<const float2 *>(&Bs[kk][tx * 6]);
+      const float2 b1 = *reinterpret_cast<const float2 *>(&Bs[kk][tx * 6 + 2]);
+      const float2 b2 = *reinterpret_cast<const float2 *>(&Bs[kk][tx * 6 + 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float b[6] = {b0.x, b0.y, b1.x, b1.y, b2.x, b2.y};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -719,7 +755,7 @@ extern "C" int frtm_corr3x3_nchw(const float *x, const float *filt, const int *f
   FRTM_REQUIRE(x && filt && out && NB > 0 && c > 0, "corr3x3: bad arguments");
   FRTM_REQUIRE(c * 9 * sizeof(float) <= 48 * 1024, "corr3x3: too many channels");
   dim3 grid(cdiv(h * w, 128), NB);
-  corr3x3_kernel<<<grid, 128, c * 9 * sizeof(float), (cudaStream_t)stream>>>(x, filt, filter_index, c, h, w, out, 0, nullptr);
+  corr3x3_kernel<<<grid, 512, (c * 9 + 512) * sizeof(float), (cudaStream_t)stream>>>(x, filt, filter_index, c, h, w, out, 0, nullptr);
   FRTM_CHECK_LAUNCH("corr3x3");
   return FRTM_OK;
 }
@@ -883,18 +919,18 @@ struct InitWs {
 // g = J^T [ sw (S Js(d) - use_y t) ]  for the joint problem at the current (Pt, F); d = (dP, dF) or null for the RHS
 int joint_products(const InitWs &W, const float *x, const float *stencil, const float *uty, const float *sw, const float *F,
                    const float *dP, const float *dF, float *gP, float *gF, cudaStream_t st) {
-  const size_t fsm = (size_t)W.nF * sizeof(float);
+  const size_t fsm = (size_t)W.nF * sizeof(float), csm = fsm + 512 * sizeof(float);
   dim3 gpix(cdiv(W.hw, 128), W.K), gpix256(cdiv(W.hw, 256), W.K), ggrad(cdiv(W.c, 8), W.K);
   int rc;
   if (dP == nullptr) {  // RHS: s = F * (P x)
-    corr3x3_kernel<<<gpix, 128, fsm, st>>>(W.cx, F, nullptr, W.c, W.h, W.w, W.s, 0, nullptr);
+    corr3x3_kernel<<<gpix, 512, csm, st>>>(W.cx, F, nullptr, W.c, W.h, W.w, W.s, 0, nullptr);
     FRTM_CHECK_LAUNCH("gn_init/score");
   } else {              // J d: s = F * (dP x) + dF * (P x)
     rc = frtm_conv2d_nhwc(x, W.K, W.h, W.w, W.C, W.C, dP, nullptr, nullptr, 0, nullptr, 0, 0, W.a, W.c, 1, 1, 1, 0, 0, st);
     if (rc) return rc;
-    corr3x3_kernel<<<gpix, 128, fsm, st>>>(W.a, F, nullptr, W.c, W.h, W.w, W.s, 0, nullptr);
+    corr3x3_kernel<<<gpix, 512, csm, st>>>(W.a, F, nullptr, W.c, W.h, W.w, W.s, 0, nullptr);
     FRTM_CHECK_LAUNCH("gn_init/score(dP)");
-    corr3x3_kernel<<<gpix, 128, fsm, st>>>(W.cx, dF, nullptr, W.c, W.h, W.w, W.s, 1, nullptr);
+    corr3x3_kernel<<<gpix, 512, csm, st>>>(W.cx, dF, nullptr, W.c, W.h, W.w, W.s, 1, nullptr);
     FRTM_CHECK_LAUNCH("gn_init/score(dF)");
   }
   stencil_apply_kernel<<<gpix256, 256, 0, st>>>(stencil, W.s, uty, sw, W.h, W.w, dP == nullptr ? 1 : 0, W.v);

@@ -191,18 +191,34 @@ class Tracker(nn.Module):
             d.update_optimizer.x[0] = d.filter.weight
 
     def initialize(self, image, labels, new_objects):
+        """Create and fit a target model per new object (``:165-191``).
+
+        Augmentation (host OpenCV inpaint + spec drawing, device rendering, one small device->host read) runs on a side
+        stream, so the host can prepare object k+1 while the GPU is still fitting object k on the main stream."""
         self.current_masks = torch.zeros((len(self.targets) + len(new_objects) + 1, *image.shape[-2:]), device=self.device)
+        main = torch.cuda.current_stream()
+        if getattr(self, "_aug_stream", None) is None:
+            self._aug_stream = torch.cuda.Stream(device=image.device)
+        side = self._aug_stream
+        side.wait_stream(main)                       # image / labels uploads are visible to the side stream
         for obj_id in new_objects:
-            mask = (labels == obj_id).byte()
+            with torch.cuda.stream(side):
+                mask = (labels == obj_id).byte()
             target = TargetObject(obj_id=obj_id, index=len(self.targets) + 1, disc_params=self.disc_params,
                                   start_frame=self.current_frame, start_mask=mask)
             self.targets[obj_id] = target
             # same (debug) reseeding as the reference so augmentation is deterministic per object (:178-180)
             torch.random.manual_seed(0)
             np.random.seed(0)
-            im, msk = self.augment(image, mask)
-            _, f32, _ = self.feature_extractor.forward_split(im.to(self.device), (), (target.disc_layer,), upto=target.disc_layer)
-            target.discriminator.init(None, msk.to(self.device), x_nhwc=f32[target.disc_layer])
+            with torch.cuda.stream(side):
+                im, msk = self.augment(image, mask)
+                im, msk = im.to(self.device), msk.to(self.device)
+                ready = side.record_event()
+            main.wait_event(ready)
+            for t in (im, msk, mask):
+                t.record_stream(main)
+            _, f32, _ = self.feature_extractor.forward_split(im, (), (target.disc_layer,), upto=target.disc_layer)
+            target.discriminator.init(None, msk, x_nhwc=f32[target.disc_layer])
             self._bind_filter(target)
             self.current_masks[target.index] = mask
         self._stack = None
