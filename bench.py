@@ -291,6 +291,9 @@ def main():
     # ---- conv path: algorithmic FLOP/s of one 8-frame block (the unit run_sequence executes) -------------------------
     nblk = trk.max_block
     imgs = [seq[len(seq) - 1 - j][0] for j in range(nblk)]
+    rem = (-trk.targets[seq.obj_ids[0]].discriminator.frame_num) % trk.targets[seq.obj_ids[0]].discriminator.train_skipping
+    if rem:
+        trk._track_block(imgs[:rem])     # align to the next filter-update frame
     for _ in range(2):
         trk._track_block(imgs)           # frame_num stays aligned: every block ends on an update frame
     torch.cuda.synchronize()
