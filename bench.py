@@ -280,7 +280,10 @@ def main():
     rhs_bytes = M * 4 * (c * h * w + 10 * h * w)
     launches_per_update = 2 * (n_cg + 1)
     achieved = (rhs_bytes + n_cg * ap_bytes) / (ms_update * 1e-3) / 1e9
-    roofline = dict(bound="hbm", achieved=achieved, peak=pk["hbm"], unit="GB/s", frac=achieved / pk["hbm"], traffic=None,
+    # DRAM traffic per launch from the committed `ncu --set full` capture (profiles/r01_ncu_full_summary.md): 47.0 MB read,
+    # 0 written for one object at M=69, i.e. 0.681 MB per active sample = the algorithmic bytes; scaled to this launch.
+    traffic = 47.0e6 / 69 * M if (c, h, w) == (96, 30, 54) else None
+    roofline = dict(bound="hbm", achieved=achieved, peak=pk["hbm"], unit="GB/s", frac=achieved / pk["hbm"], traffic=traffic,
                     kernel="gn_apply_kernel inside one batched filter update (RHS + %d x A.p, stencil form S; %d objects, "
                            "M=%s active samples of %d, sample = %dx%dx%d fp32); time includes the %d cg_vector launches" % (
                                n_cg, len(live), Ms, cap, c, h, w, n_cg + 1),
