@@ -153,6 +153,13 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    # host side per rank = OpenCV inpaint + kernel launches: do not oversubscribe the host cores with N ranks
+    torch.set_num_threads(max(1, (os.cpu_count() or 8) // max(world, 1)))
+    try:
+        import cv2
+        cv2.setNumThreads(max(1, (os.cpu_count() or 8) // max(world, 1)))
+    except Exception:
+        pass
     torch.cuda.set_device(local)
     dev = "cuda:%d" % local
     dist = None

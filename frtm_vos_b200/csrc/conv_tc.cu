@@ -394,39 +394,76 @@ __global__ void split_kernel(const float *__restrict__ x, int64_t npix, int C, i
 // tensor-core kernel has produced the 64-channel part in y; this adds the score channel's 3x3 contribution, the bias and
 // the ReLU, and emits what the next layer needs: split planes for outputs [0,64) and/or fp32, and output channel 64 (when
 // Cout == 65) as a separate fp32 map — the next conv's score channel.
-__global__ void rank1_finish_kernel(const float *__restrict__ yin, int ldin, int n_obj, float *__restrict__ yout, int ldout,
-                                    const float *__restrict__ s, const float *__restrict__ wx, const float *__restrict__ bias,
-                                    int B, int H, int W, int Cout, int relu, __half *__restrict__ yh, __half *__restrict__ yl,
-                                    int ldh, float *__restrict__ extra) {
+__global__ void __launch_bounds__(256)
+rank1_finish_kernel(const float *__restrict__ yin, int ldin, int n_obj, float *__restrict__ yout, int ldout,
+                    const float *__restrict__ s, const float *__restrict__ wx, const float *__restrict__ bias, int B, int H,
+                    int W, int Cout, int relu, __half *__restrict__ yh, __half *__restrict__ yl, int ldh,
+                    float *__restrict__ extra) {
+  // thread = (pixel, group of 4 output channels); the 65th output channel (if any) is a 17th, scalar group
+  extern __shared__ float wsm[];   // wx [9][Cout] then bias [Cout]
+  for (int i = threadIdx.x; i < 9 * Cout; i += blockDim.x) wsm[i] = wx[i];
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) wsm[9 * Cout + i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const int ngrp = (Cout + 3) >> 2;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = (int64_t)B * H * W * Cout;
+  const int64_t total = (int64_t)B * H * W * ngrp;
   if (idx >= total) return;
-  const int n = (int)(idx % Cout);
-  const int64_t pix = idx / Cout;
+  const int grp = (int)(idx % ngrp);
+  const int64_t pix = idx / ngrp;
   const int64_t hw = (int64_t)W * H;
   const int px = (int)(pix % W);
   const int py = (int)((pix / W) % H);
   const int64_t img = pix / hw;
   const float *sb = s + img * hw;
-  // the 64-channel part may be shared by the n_obj objects of a frame (it depends on backbone features only)
-  float acc = yin[((img / n_obj) * hw + (pix - img * hw)) * ldin + n];
+  float sv[9];
 #pragma unroll
   for (int t = 0; t < 9; ++t) {
     const int yy = py + t / 3 - 1, xx = px + t % 3 - 1;
-    if (yy >= 0 && yy < H && xx >= 0 && xx < W) acc = fmaf(wx[t * Cout + n], sb[yy * W + xx], acc);
+    sv[t] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? sb[yy * W + xx] : 0.f;
   }
-  if (bias) acc += bias[n];
-  if (relu) acc = fmaxf(acc, 0.f);
-  if (yout) yout[pix * ldout + n] = acc;
-  if (n < 64) {
+  // the 64-channel part may be shared by the n_obj objects of a frame (it depends on backbone features only)
+  const float *yi = yin + ((img / n_obj) * hw + (pix - img * hw)) * ldin;
+  const int n0 = grp * 4;
+  const int nv = min(4, Cout - n0);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (nv == 4 && (ldin & 3) == 0) {
+    const float4 v = *reinterpret_cast<const float4 *>(yi + n0);
+    acc[0] = v.x; acc[1] = v.y; acc[2] = v.z; acc[3] = v.w;
+  } else {
+    for (int j = 0; j < nv; ++j) acc[j] = yi[n0 + j];
+  }
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < nv) acc[j] = fmaf(wsm[t * Cout + n0 + j], sv[t], acc[j]);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (j < nv) {
+      acc[j] += wsm[9 * Cout + n0 + j];
+      if (relu) acc[j] = fmaxf(acc[j], 0.f);
+    }
+  }
+  if (yout) {
+    float *yo = yout + pix * ldout + n0;
+    if (nv == 4 && (ldout & 3) == 0) *reinterpret_cast<float4 *>(yo) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    else for (int j = 0; j < nv; ++j) yo[j] = acc[j];
+  }
+  if (n0 < 64) {
     if (yh) {
-      const float sc = acc * TC_ACT_SCALE;
-      const __half h = __float2half_rn(sc);
-      yh[pix * ldh + n] = h;
-      yl[pix * ldh + n] = __float2half_rn(sc - __half2float(h));
+      __align__(8) __half hh[4];
+      __align__(8) __half ll[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float sc = acc[j] * TC_ACT_SCALE;
+        hh[j] = __float2half_rn(sc);
+        ll[j] = __float2half_rn(sc - __half2float(hh[j]));
+      }
+      *reinterpret_cast<uint2 *>(yh + pix * ldh + n0) = *reinterpret_cast<const uint2 *>(hh);
+      *reinterpret_cast<uint2 *>(yl + pix * ldh + n0) = *reinterpret_cast<const uint2 *>(ll);
     }
   } else if (extra) {
-    extra[pix] = acc;
+    extra[pix] = acc[0];
   }
 }
 
@@ -568,9 +605,10 @@ extern "C" int frtm_rank1_finish(const float *y_in, int ldin, int n_obj, float *
                                  const float *wx, const float *bias, int B, int H, int W, int Cout, int relu, void *y_hi,
                                  void *y_lo, int ldh, float *extra, void *stream) {
   FRTM_REQUIRE(y_in && score && wx && Cout <= 65 && Cout >= 1 && n_obj >= 1, "rank1_finish: bad arguments");
-  const int64_t total = (int64_t)B * H * W * Cout;
-  rank1_finish_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(y_in, ldin, n_obj, y_out, ldout, score, wx, bias, B, H,
-                                                                          W, Cout, relu, (__half *)y_hi, (__half *)y_lo, ldh, extra);
+  FRTM_REQUIRE(!y_hi || (ldh % 4 == 0), "rank1_finish: split planes need a channel stride that is a multiple of 4");
+  const int64_t total = (int64_t)B * H * W * ((Cout + 3) / 4);
+  rank1_finish_kernel<<<cdiv(total, 256), 256, 10 * Cout * sizeof(float), (cudaStream_t)stream>>>(
+      y_in, ldin, n_obj, y_out, ldout, score, wx, bias, B, H, W, Cout, relu, (__half *)y_hi, (__half *)y_lo, ldh, extra);
   FRTM_CHECK_LAUNCH("rank1_finish");
   return FRTM_OK;
 }

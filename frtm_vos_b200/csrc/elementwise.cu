@@ -86,37 +86,54 @@ __global__ void resize_bilinear_kernel(const float *__restrict__ x, int B, int H
 // ---------------------------------------------------------------- bicubic x2 -----------------------------------
 __constant__ float kCubicE[4] = {-0.10546875f, 0.87890625f, 0.26171875f, -0.03515625f};
 
-__global__ void pyrup_bicubic_kernel(const float *__restrict__ x, int B, int H, int W, int C, float *__restrict__ y) {
+// One thread = one 4x4 input window = the 2x2 block of outputs (all four polyphase filters) that share it.
+__global__ void __launch_bounds__(256) pyrup_bicubic_kernel(const float *__restrict__ x, int B, int H, int W, int C,
+                                                            float *__restrict__ y) {
   const int C4 = C / 4, Ho = 2 * H, Wo = 2 * W;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = (int64_t)B * Ho * Wo * C4;
+  const int64_t total = (int64_t)B * (H + 1) * (W + 1) * C4;
   if (i >= total) return;
   const int c4 = (int)(i % C4);
   int64_t r = i / C4;
-  const int ox = (int)(r % Wo);
-  r /= Wo;
-  const int oy = (int)(r % Ho);
-  const int b = (int)(r / Ho);
-  const int yf = oy + 1, xf = ox + 1;          // position before the 1-px crop
-  const int iy = yf >> 1, ix = xf >> 1;        // phase-image index
-  const bool oddy = yf & 1, oddx = xf & 1;     // odd phase uses the reversed taps
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int n = (int)(r % (W + 1));
+  r /= (W + 1);
+  const int m = (int)(r % (H + 1));
+  const int b = (int)(r / (H + 1));
+  // window rows m-2..m+1, cols n-2..n+1 (replicate padding); outputs (pre-crop) rows 2m, 2m+1 -> cropped 2m-1, 2m
+  float4 win[4][4];
 #pragma unroll
   for (int ky = 0; ky < 4; ++ky) {
-    const float wy = oddy ? kCubicE[3 - ky] : kCubicE[ky];
-    const int sy = min(max(iy + ky - 2, 0), H - 1);  // replicate pad 2
-    float4 row = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int sy = min(max(m + ky - 2, 0), H - 1);
 #pragma unroll
     for (int kx = 0; kx < 4; ++kx) {
-      const float wx = oddx ? kCubicE[3 - kx] : kCubicE[kx];
-      const int sx = min(max(ix + kx - 2, 0), W - 1);
-      const float4 v = *reinterpret_cast<const float4 *>(x + (((int64_t)b * H + sy) * W + sx) * C + c4 * 4);
-      const float wt = wy * wx;  // the reference builds the non-separable 4x4 filter as an outer product
-      row.x = fmaf(wt, v.x, row.x); row.y = fmaf(wt, v.y, row.y); row.z = fmaf(wt, v.z, row.z); row.w = fmaf(wt, v.w, row.w);
+      const int sx = min(max(n + kx - 2, 0), W - 1);
+      win[ky][kx] = *reinterpret_cast<const float4 *>(x + (((int64_t)b * H + sy) * W + sx) * C + c4 * 4);
     }
-    acc.x += row.x; acc.y += row.y; acc.z += row.z; acc.w += row.w;
   }
-  *reinterpret_cast<float4 *>(y + (((int64_t)b * Ho + oy) * Wo + ox) * C + c4 * 4) = acc;
+#pragma unroll
+  for (int ry = 0; ry < 2; ++ry) {
+    const int oy = 2 * m + ry - 1;
+    if (oy < 0 || oy >= Ho) continue;
+#pragma unroll
+    for (int rx = 0; rx < 2; ++rx) {
+      const int ox = 2 * n + rx - 1;
+      if (ox < 0 || ox >= Wo) continue;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int ky = 0; ky < 4; ++ky) {
+        const float wy = ry ? kCubicE[3 - ky] : kCubicE[ky];
+        float4 row = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int kx = 0; kx < 4; ++kx) {
+          const float wt = wy * (rx ? kCubicE[3 - kx] : kCubicE[kx]);   // outer-product filter, like the reference
+          const float4 v = win[ky][kx];
+          row.x = fmaf(wt, v.x, row.x); row.y = fmaf(wt, v.y, row.y); row.z = fmaf(wt, v.z, row.z); row.w = fmaf(wt, v.w, row.w);
+        }
+        acc.x += row.x; acc.y += row.y; acc.z += row.z; acc.w += row.w;
+      }
+      *reinterpret_cast<float4 *>(y + (((int64_t)b * Ho + oy) * Wo + ox) * C + c4 * 4) = acc;
+    }
+  }
 }
 
 // ---------------------------------------------------------------- global average pool ---------------------------
@@ -429,7 +446,7 @@ extern "C" int frtm_resize_bilinear_nhwc(const float *x, int B, int H, int W, in
 
 extern "C" int frtm_pyrup_bicubic_nhwc(const float *x, int B, int H, int W, int C, float *y, void *stream) {
   FRTM_REQUIRE(x && y && C % 4 == 0, "pyrup_bicubic: bad arguments");
-  const int64_t total = (int64_t)B * 2 * H * 2 * W * (C / 4);
+  const int64_t total = (int64_t)B * (H + 1) * (W + 1) * (C / 4);
   pyrup_bicubic_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, C, y);
   FRTM_CHECK_LAUNCH("pyrup_bicubic");
   return FRTM_OK;

@@ -439,41 +439,73 @@ __global__ void __launch_bounds__(256) build_stencil_kernel(const float *__restr
 
 // ---------------------------------------------------------------- memory -----------------------------------------
 // state: {current_size, prev_replace_ind (-1 none), slot chosen now (-1 = skipped), inserts so far}
-__global__ void memory_next_slot_kernel(float *__restrict__ sw, int cap, float lr, int *__restrict__ state,
-                                        const int *__restrict__ gate_count, int min_px) {
-  if (threadIdx.x != 0) return;
-  if (gate_count && gate_count[0] < min_px) { state[2] = -1; return; }
+__global__ void __launch_bounds__(32) memory_next_slot_kernel(float *__restrict__ sw, int cap, float lr, int *__restrict__ state,
+                                                              const int *__restrict__ gate_count, int min_px) {
+  // one warp; lanes stride over the capacity, reductions by shuffle (first-minimum tie break = lowest index)
+  const int lane = threadIdx.x;
+  if (gate_count && gate_count[0] < min_px) { if (lane == 0) state[2] = -1; return; }
+  const int size = state[0], prev = state[1];
+  __syncwarp();
   int r = 0;
-  if (state[0] == 0 || lr == 1.f) {
-    for (int i = 0; i < cap; ++i) sw[i] = 0.f;
-    sw[0] = 1.f;
+  if (size == 0 || lr == 1.f) {
+    for (int i = lane; i < cap; i += 32) sw[i] = (i == 0) ? 1.f : 0.f;
   } else {
-    float best = sw[0];
-    for (int i = 1; i < cap; ++i)
-      if (sw[i] < best) { best = sw[i]; r = i; }   // first minimum, like torch.min(sw, 0)
-    if (state[1] < 0) {
-      for (int i = 0; i < cap; ++i) sw[i] = sw[i] / (1.f - lr);
-      sw[r] = lr;
+    float best = INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = lane; i < cap; i += 32) {
+      const float v = sw[i];
+      if (v < best) { best = v; bi = i; }          // ascending i within a lane keeps the first minimum
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    r = bi;                                        // like torch.min(sw, 0): first index of the minimum
+    if (prev < 0) {
+      for (int i = lane; i < cap; i += 32) sw[i] = (i == r) ? lr : sw[i] / (1.f - lr);
     } else {
-      sw[r] = sw[state[1]] / (1.f - lr);
+      const float pv = sw[prev];
+      __syncwarp();
+      if (lane == 0) sw[r] = pv / (1.f - lr);
     }
   }
+  __syncwarp();
   double tot = 0.0;
-  for (int i = 0; i < cap; ++i) tot += (double)sw[i];
+  for (int i = lane; i < cap; i += 32) tot += (double)sw[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
   const float ft = (float)tot;
-  for (int i = 0; i < cap; ++i) sw[i] = sw[i] / ft;
-  state[1] = r;
-  state[2] = r;
-  state[0] = min(state[0] + 1, cap);
-  state[3] += 1;
+  for (int i = lane; i < cap; i += 32) sw[i] = sw[i] / ft;
+  if (lane == 0) {
+    state[1] = r;
+    state[2] = r;
+    state[0] = min(size + 1, cap);
+    state[3] += 1;
+  }
 }
 
-__global__ void memory_insert_kernel(const float *__restrict__ src, int64_t n, float *__restrict__ dst_base,
-                                     const int *__restrict__ state) {
+// All five pieces of one sample (projected features, soft label, pixel weights, stencil, U^T w^2 y) in one launch.
+struct InsertArgs {
+  const float *src[5];
+  float *dst[5];
+  int64_t n[5];
+  int64_t total;
+};
+__global__ void memory_insert_kernel(const InsertArgs a, const int *__restrict__ state) {
   const int slot = state[2];
   if (slot < 0) return;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst_base[(int64_t)slot * n + i] = src[i];
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.total) return;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    if (i < a.n[k]) {
+      a.dst[k][(int64_t)slot * a.n[k] + i] = a.src[k][i];
+      return;
+    }
+    i -= a.n[k];
+  }
 }
 
 // ---------------------------------------------------------------- CG vector kernels (filter-only problem) --------
@@ -794,25 +826,18 @@ extern "C" int frtm_memory_insert(const float *feat, int feat_elems, const float
                                   const float *stencil, const float *uty, int hw, float *mem_samples, float *mem_labels,
                                   float *mem_pw, float *mem_stencil, float *mem_uty, const int *state, void *stream) {
   FRTM_REQUIRE(feat && mem_samples && state, "memory_insert: bad arguments");
-  cudaStream_t st = (cudaStream_t)stream;
-  memory_insert_kernel<<<cdiv(feat_elems, 256), 256, 0, st>>>(feat, feat_elems, mem_samples, state);
-  FRTM_CHECK_LAUNCH("memory_insert(samples)");
-  if (label && mem_labels) {
-    memory_insert_kernel<<<cdiv(HW, 256), 256, 0, st>>>(label, HW, mem_labels, state);
-    FRTM_CHECK_LAUNCH("memory_insert(labels)");
+  InsertArgs a;
+  const float *src[5] = {feat, label, pw, stencil, uty};
+  float *dst[5] = {mem_samples, mem_labels, mem_pw, mem_stencil, mem_uty};
+  const int64_t n[5] = {feat_elems, HW, HW, 9 * (int64_t)hw, hw};
+  a.total = 0;
+  for (int k = 0; k < 5; ++k) {
+    const bool on = src[k] != nullptr && dst[k] != nullptr;
+    a.src[k] = src[k]; a.dst[k] = dst[k]; a.n[k] = on ? n[k] : 0;
+    a.total += a.n[k];
   }
-  if (pw && mem_pw) {
-    memory_insert_kernel<<<cdiv(HW, 256), 256, 0, st>>>(pw, HW, mem_pw, state);
-    FRTM_CHECK_LAUNCH("memory_insert(pw)");
-  }
-  if (stencil && mem_stencil) {
-    memory_insert_kernel<<<cdiv(9 * hw, 256), 256, 0, st>>>(stencil, 9 * hw, mem_stencil, state);
-    FRTM_CHECK_LAUNCH("memory_insert(stencil)");
-  }
-  if (uty && mem_uty) {
-    memory_insert_kernel<<<cdiv(hw, 256), 256, 0, st>>>(uty, hw, mem_uty, state);
-    FRTM_CHECK_LAUNCH("memory_insert(uty)");
-  }
+  memory_insert_kernel<<<cdiv(a.total, 256), 256, 0, (cudaStream_t)stream>>>(a, state);
+  FRTM_CHECK_LAUNCH("memory_insert");
   return FRTM_OK;
 }
 

@@ -19,7 +19,7 @@ def main():
     ap.add_argument("--frames", type=int, default=17)
     ap.add_argument("--size", default="480x854")
     ap.add_argument("--full", action="store_true")
-    ap.add_argument("--what", default="sequence", choices=["sequence", "track", "update"])
+    ap.add_argument("--what", default="sequence", choices=["sequence", "track", "update", "block", "init"])
     a = ap.parse_args()
     from quick_run import build_tracker
     from frtm_vos_b200 import synth
@@ -37,6 +37,24 @@ def main():
         trk.run_sequence(seq)
     elif a.what == "track":
         trk.track(img)
+    elif a.what == "block":
+        imgs = [seq[a.frames - 1 - j][0] for j in range(8)]
+        rem = (-d.frame_num) % d.train_skipping
+        torch.cuda.profiler.stop()
+        if rem:
+            trk._track_block(imgs[:rem])
+        trk._track_block(imgs)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        trk._track_block(imgs)
+    elif a.what == "init":
+        from frtm_vos_b200.model.discriminator import Discriminator
+        m5 = None
+        im5, m5 = trk.augment(img, (seq.ground_truth(a.frames - 1) == 1).byte().to(dev))
+        _, nh, _ = trk.feature_extractor.forward_split(im5, (), ("layer4",), upto="layer4")
+        dd = Discriminator(**trk.disc_params)
+        torch.cuda.synchronize()
+        dd.init(None, m5, x_nhwc=nh["layer4"])
     else:
         d.update_optimizer.run(d.update_iters)
     torch.cuda.synchronize()
