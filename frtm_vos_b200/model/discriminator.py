@@ -105,9 +105,11 @@ class Discriminator(nn.Module):
         yf = y.float().contiguous()
         pw = self.compute_pixel_weights(yf)
         stencil, uty = ops.build_stencil(pw, yf, (h, w))
-        sw = torch.full((K,), 1.0 / K)
-        sw[0] = 2.0 / K
-        sw = (sw / sw.sum()).to(x_nhwc.device)
+        sw_h = torch.full((K,), 1.0 / K)
+        sw_h[0] = 2.0 / K
+        sw_h = sw_h / sw_h.sum()
+        sw = torch.empty(K, device=x_nhwc.device, dtype=torch.float32)
+        ops.fill_small(fdst=sw, fvals=sw_h.tolist())                     # no synchronising H2D copy
 
         # joint optimisation of projection and filter on the raw features
         problem = DiscriminatorLoss(x=x_nhwc, y=yf, filter_regs=self.filter_reg, precond=self.precond, sample_weights=sw,

@@ -26,7 +26,8 @@ class Memory:
         self.stencil = torch.zeros(capacity, 9, h, w, device=device)
         self.uty = torch.zeros(capacity, h, w, device=device)
         # {current_size, previous_replace_ind (-1 = None), slot of the last insert (-1 = skipped), inserts}
-        self.state = torch.tensor([0, -1, -1, 0], dtype=torch.int32, device=device)
+        self.state = torch.empty(4, dtype=torch.int32, device=device)
+        ops.fill_small(idst=self.state, ivals=(0, -1, -1, 0))          # asynchronous: no pageable H2D copy
         self._capacity = capacity
         self.device = device
         self.learning_rates = learning_rates
@@ -52,15 +53,15 @@ class Memory:
         if stencil is None:
             stencil, uty = ops.build_stencil(pixel_weights, labels, self.samples.shape[-2:])
         self.samples[:K] = init_features.detach()
-        w = torch.full((K,), 1.0 / K)
+        w = torch.full((K,), 1.0 / K)            # host arithmetic identical to the reference's, uploaded without a sync
         w[0] = 2.0 / K
         w = w / w.sum()
-        self.weights[:K] = w.to(self.device)
+        assert K <= 16
+        ops.fill_small(fdst=self.weights, fvals=w.tolist(), idst=self.state, ivals=(K, -1, -1, 0))
         self.labels[:K] = labels
         self.pixel_weights[:K] = pixel_weights
         self.stencil[:K] = stencil
         self.uty[:K] = uty
-        self.state.copy_(torch.tensor([K, -1, -1, 0], dtype=torch.int32))
 
     def update(self, features, labels, pixel_weights, stencil=None, uty=None, gate_count=None, min_px=10):
         """Insert one sample (``:59-92``).  With ``gate_count`` (int32 device scalar) the insert — including the

@@ -204,8 +204,10 @@ class Tracker(nn.Module):
         for obj_id in new_objects:
             with torch.cuda.stream(side):
                 mask = (labels == obj_id).byte()
-            target = TargetObject(obj_id=obj_id, index=len(self.targets) + 1, disc_params=self.disc_params,
-                                  start_frame=self.current_frame, start_mask=mask)
+                # constructed under the side stream: the (pageable, hence synchronous) upload of the freshly drawn
+                # project/filter weights then waits for the side stream only, not for the previous object's fit
+                target = TargetObject(obj_id=obj_id, index=len(self.targets) + 1, disc_params=self.disc_params,
+                                      start_frame=self.current_frame, start_mask=mask)
             self.targets[obj_id] = target
             # same (debug) reseeding as the reference so augmentation is deterministic per object (:178-180)
             torch.random.manual_seed(0)
@@ -215,7 +217,7 @@ class Tracker(nn.Module):
                 im, msk = im.to(self.device), msk.to(self.device)
                 ready = side.record_event()
             main.wait_event(ready)
-            for t in (im, msk, mask):
+            for t in (im, msk, mask, target.discriminator.project.weight.data, target.discriminator.filter.weight.data):
                 t.record_stream(main)
             _, f32, _ = self.feature_extractor.forward_split(im, (), (target.disc_layer,), upto=target.disc_layer)
             target.discriminator.init(None, msk, x_nhwc=f32[target.disc_layer])
@@ -333,7 +335,9 @@ class Tracker(nn.Module):
                 for r, v in zip(rows, (m.samples, m.stencil, m.uty, m.weights, d.filter.weight, d.update_optimizer.cg_state)):
                     r.append(v.data_ptr())
                 rows[6].append(self._counts.data_ptr() + 4 * k)
-            table = torch.tensor(rows, dtype=torch.int64).to(self._counts.device)
+            flat = [v for r in rows for v in r]
+            table = torch.empty((7, len(due)), dtype=torch.int64, device=self._counts.device)
+            lib().fill_i64(ptr(table), (ctypes.c_int64 * len(flat))(*flat), len(flat), stream())   # no synchronising H2D
             d0 = live[due[0]].discriminator
             cap, c, h, w = d0.memory.samples.shape
             nbytes = len(due) * lib().gn_update_workspace(cap, c, h, w)

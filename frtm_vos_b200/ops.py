@@ -402,3 +402,11 @@ def pack_conv_tc_1x1_device(weight: torch.Tensor, bn_tile: Optional[int] = None)
     osc = torch.empty(cout_p, device=w.device, dtype=torch.float32)
     lib().pack_tc_1x1(ptr(w), cout, cin, tile, ptr(wt), ptr(osc), stream())
     return PackedConvTC(wt, osc, None, cin, cout, 1, tile, 1)
+
+
+def fill_small(fdst: Optional[torch.Tensor] = None, fvals=(), idst: Optional[torch.Tensor] = None, ivals=()):
+    """Write a few host scalars into device tensors asynchronously (values travel as kernel arguments)."""
+    import ctypes
+    fa = (ctypes.c_float * max(len(fvals), 1))(*[float(v) for v in fvals])
+    ia = (ctypes.c_int * max(len(ivals), 1))(*[int(v) for v in ivals])
+    lib().fill_small(ptr(fdst), fa, len(fvals), ptr(idst), ia, len(ivals), stream())

@@ -39,6 +39,13 @@ int frtm_version(void);
 /* Number of kernels this library has launched in this process (bench.py "gpu_launches"). */
 int64_t frtm_launch_count(void);
 
+/* Upload up to 16 floats and 16 ints from HOST arrays to device memory as kernel arguments (no memcpy, hence no
+ * synchronisation with work already queued on the stream).  Used for memory.weights / memory state initialisation
+ * (model/memory.py:38-46). */
+int frtm_fill_small(float *fdst, const float *fvals_host, int nf, int *idst, const int *ivals_host, int ni, void *stream);
+/* Same for n 64-bit integers (device pointer tables of the batched GN update). */
+int frtm_fill_i64(void *dst, const int64_t *vals_host, int n, void *stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Backbone + refinement-network building blocks  (model/feature_extractor.py:40-68 -> torchvision ResNet,
  * model/seg_network.py:7-189, lib/utils.py:25-41)
