@@ -21,6 +21,22 @@ from ..lib.tensorlist import TensorList
 from .._lib import lib, ptr, stream
 
 
+_INIT_STAGE = {}
+
+
+def _init_stage(K, C, c, h, w, device):
+    key = (K, C, c, h, w, str(device), torch.cuda.current_stream().cuda_stream)
+    st = _INIT_STAGE.get(key)
+    if st is None:
+        nbytes = lib().gn_init_workspace(K, C, c, h, w)
+        f = dict(device=device, dtype=torch.float32)
+        st = dict(x=torch.empty((K, h, w, C), **f), stencil=torch.empty((K, 9, h, w), **f), uty=torch.empty((K, h, w), **f),
+                  sw=torch.empty(K, **f), P=torch.empty((c, C), **f), F=torch.empty(c * 9, **f),
+                  ws=torch.empty(nbytes // 4, **f), nbytes=nbytes)
+        _INIT_STAGE[key] = st
+    return st
+
+
 class MinimizationProblem:
     """Interface kept for API compatibility (``model/optimizer.py:5-15``)."""
 
@@ -97,11 +113,17 @@ class GaussNewtonCG:
         if self.joint:
             K, h, w, C = pr.x_nhwc.shape
             c = self.x[1].shape[1]
-            nbytes = L.gn_init_workspace(K, C, c, h, w)
-            ws = torch.empty(nbytes // 4, device=pr.x_nhwc.device, dtype=torch.float32)
-            L.gn_init(ptr(pr.x_nhwc), ptr(pr.stencil), ptr(pr.uty), ptr(pr.sample_weights), K, C, c, h, w, ptr(self.x[0]),
-                      ptr(self.x[1]), iters, len(num_cg_iter), pr.filter_regs[0], pr.filter_regs[1], pr.diag_M[0],
-                      pr.diag_M[1], self.direction_forget_factor, ptr(ws), nbytes, stream())
+            # Stage through persistent buffers: the library recognises the repeated signature and replays the whole
+            # ~650-launch optimisation as one CUDA graph from the second object on.
+            st = _init_stage(K, C, c, h, w, pr.x_nhwc.device)
+            st["x"].copy_(pr.x_nhwc); st["stencil"].copy_(pr.stencil); st["uty"].copy_(pr.uty)
+            st["sw"].copy_(pr.sample_weights); st["P"].copy_(self.x[0].detach().reshape(c, C))
+            st["F"].copy_(self.x[1].detach().reshape(-1))
+            L.gn_init(ptr(st["x"]), ptr(st["stencil"]), ptr(st["uty"]), ptr(st["sw"]), K, C, c, h, w, ptr(st["P"]),
+                      ptr(st["F"]), iters, len(num_cg_iter), pr.filter_regs[0], pr.filter_regs[1], pr.diag_M[0],
+                      pr.diag_M[1], self.direction_forget_factor, ptr(st["ws"]), st["nbytes"], stream())
+            self.x[0].data.copy_(st["P"].view_as(self.x[0]))
+            self.x[1].data.copy_(st["F"].view_as(self.x[1]))
         else:
             mem = pr.memory
             cap, c, h, w = mem.samples.shape
