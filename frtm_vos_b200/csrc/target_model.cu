@@ -1098,30 +1098,49 @@ extern "C" int frtm_gn_init(const float *x_nhwc, const float *stencil, const flo
   std::lock_guard<std::mutex> lock(g_init_mutex);
   InitGraph &g = g_init_graphs[key];
   g.calls += 1;
-  if (g.exec != nullptr) {
-    cudaError_t e = cudaGraphLaunch(g.exec, st);
-    if (e != cudaSuccess) { set_error("gn_init: cudaGraphLaunch: %s", cudaGetErrorString(e)); return FRTM_ELAUNCH; }
-    count_launch(1);
-    return FRTM_OK;
+  if (g.calls < 2 || g.calls < 0) return eager();
+  // The legacy default stream cannot be captured: fork to an internal stream (event in / event out) for graph work.
+  static cudaStream_t side = nullptr;
+  static cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  cudaStream_t gs = st;
+  const bool fork = (st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread);
+  if (fork) {
+    if (!side) {
+      if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&ev_out, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError(); side = nullptr; g.calls = -1000000; return eager();
+      }
+    }
+    gs = side;
+    cudaEventRecord(ev_in, st);
+    cudaStreamWaitEvent(gs, ev_in, 0);
   }
-  if (g.calls < 2) return eager();
-  // second call with this signature: capture
-  cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed);
-  if (e != cudaSuccess) { cudaGetLastError(); return eager(); }
-  const int rc = eager();
-  cudaGraph_t graph = nullptr;
-  e = cudaStreamEndCapture(st, &graph);
-  if (rc != FRTM_OK || e != cudaSuccess || graph == nullptr) {
-    cudaGetLastError();
-    if (graph) cudaGraphDestroy(graph);
-    g.calls = -1000000;                       // never try again for this signature
-    return rc != FRTM_OK ? rc : eager();
+  auto join = [&]() {
+    if (fork) { cudaEventRecord(ev_out, gs); cudaStreamWaitEvent(st, ev_out, 0); }
+  };
+  if (g.exec == nullptr) {
+    // second call with this signature: capture on gs
+    cudaError_t e = cudaStreamBeginCapture(gs, cudaStreamCaptureModeRelaxed);
+    if (e != cudaSuccess) { cudaGetLastError(); g.calls = -1000000; join(); return eager(); }
+    const int rc = gn_init_impl(x_nhwc, stencil, uty, sw, K, C, c, h, w, P, F, cg_iters, n_gn, regP, regF, precondP, precondF,
+                                forget, workspace, workspace_bytes, gs, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    cudaGraph_t graph = nullptr;
+    e = cudaStreamEndCapture(gs, &graph);
+    if (rc != FRTM_OK || e != cudaSuccess || graph == nullptr) {
+      cudaGetLastError();
+      if (graph) cudaGraphDestroy(graph);
+      g.calls = -1000000;                     // never try again for this signature
+      join();
+      return rc != FRTM_OK ? rc : eager();
+    }
+    e = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { cudaGetLastError(); g.exec = nullptr; g.calls = -1000000; join(); return eager(); }
   }
-  e = cudaGraphInstantiate(&g.exec, graph, 0);
-  cudaGraphDestroy(graph);
-  if (e != cudaSuccess) { cudaGetLastError(); g.exec = nullptr; g.calls = -1000000; return eager(); }
-  e = cudaGraphLaunch(g.exec, st);
-  if (e != cudaSuccess) { set_error("gn_init: cudaGraphLaunch: %s", cudaGetErrorString(e)); return FRTM_ELAUNCH; }
+  cudaError_t e = cudaGraphLaunch(g.exec, gs);
+  join();
+  if (e != cudaSuccess) { set_error("gn_init: cudaGraphLaunch: %s", cudaGetLastError() == cudaSuccess ? cudaGetErrorString(e) : "launch failed"); return FRTM_ELAUNCH; }
   count_launch(1);
   return FRTM_OK;
 }
