@@ -9,6 +9,7 @@
 // sample at insert time, so the full-resolution maps are never touched inside CG.
 #include "common.cuh"
 #include <cstring>
+#include <algorithm>
 
 namespace frtm {
 
@@ -351,6 +352,218 @@ __global__ void __launch_bounds__(GA_THREADS, 1) gn_apply_kernel(const GaArgs a)
         const float r = warp_sum(acc[u][t]);
         if (lane == 0) partial[(int64_t)i * n + (quad * 4 + u) * 9 + t] = r;
       }
+  }
+}
+
+// ---------------------------------------------------------------- fused J^T S J apply, bulk-copy staged ----------
+// Same three phases as gn_apply_kernel, but the sample is streamed into shared memory by a producer warp with
+// cp.async.bulk (TMA 1-D bulk copies) through an mbarrier full/empty ring, so no load latency is ever exposed to the
+// 26 compute warps and no registers are tied up by loads in flight:
+//   phase 1 stages = CQ whole channels (contiguous CQ*hw floats, one bulk copy),  consumer thread = pixel pair
+//   phase 3 stages = all c channels x 64 pixels (c row segments of 256 B),         consumer warp = channel quad
+constexpr int GT_CONSUMER_WARPS = 26;
+constexpr int GT_THREADS = (GT_CONSUMER_WARPS + 1) * 32;
+constexpr int GT_SLAB = 64;           // pixels per phase-3 stage (one pixel pair per lane)
+
+__device__ __forceinline__ uint32_t gt_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void gt_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return;
+  }
+  printf("frtm gn_apply_tma: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+  __trap();
+}
+
+__global__ void __launch_bounds__(GT_THREADS, 1) gn_apply_tma_kernel(const GaArgs a, int CQ, int NST, int stage_floats) {
+  const float *__restrict__ X = a.X, *__restrict__ S = a.S, *__restrict__ T = a.T, *__restrict__ sw = a.sw,
+                           *__restrict__ pvec = a.pvec;
+  float *__restrict__ partial = a.partial;
+  const int c = a.c, h = a.h, w = a.w, use_y = a.use_y;
+  if (a.table) {
+    const int o = blockIdx.y;
+    X = reinterpret_cast<const float *>(a.table[0 * a.n_obj + o]);
+    S = reinterpret_cast<const float *>(a.table[1 * a.n_obj + o]);
+    T = reinterpret_cast<const float *>(a.table[2 * a.n_obj + o]);
+    sw = reinterpret_cast<const float *>(a.table[3 * a.n_obj + o]);
+    pvec = reinterpret_cast<const float *>(a.table[(use_y ? 4 : 5) * a.n_obj + o]);
+    partial += (int64_t)o * a.cap * c * 9;
+  }
+  extern __shared__ __align__(128) float sm[];
+  const int hw = h * w, wp = w + 2, npad = (h + 2) * wp;
+  float *Y = sm;                                   // [9][hw]
+  float *sp = Y + 9 * hw;                          // padded scores
+  float *vp = sp + npad;                           // padded v
+  float *ps = vp + npad;                           // [c][12]
+  float *ring = ps + c * 12;
+  ring = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(ring) + 127) & ~(uintptr_t)127);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(ring + (size_t)NST * stage_floats);   // full[NST] | empty[NST]
+  const uint32_t bar_full = gt_smem_u32(bars), bar_empty = bar_full + 8 * NST;
+
+  const int i = blockIdx.x;
+  const int n = c * 9;
+  const float wgt = sw[i];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (wgt == 0.f) {
+    for (int k = tid; k < n; k += GT_THREADS) partial[(int64_t)i * n + k] = 0.f;
+    return;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < NST; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_full + 8 * s), "r"(1));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_empty + 8 * s), "r"(GT_CONSUMER_WARPS));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int k = tid; k < c * 12; k += GT_THREADS) {
+    const int ch = k / 12, t = k - ch * 12;
+    ps[k] = t < 9 ? pvec[ch * 9 + t] : 0.f;
+  }
+  for (int k = tid; k < 2 * npad; k += GT_THREADS) sp[k] = 0.f;
+  __syncthreads();
+
+  const float *Xi = X + (int64_t)i * c * hw;
+  const int npairs = hw >> 1;
+  const int nst1 = c / CQ;                              // phase-1 stages
+  const int nst3 = (hw + GT_SLAB - 1) / GT_SLAB;        // phase-3 stages
+
+  if (warp == GT_CONSUMER_WARPS) {
+    // ===== producer warp =====
+    for (int it = 0; it < nst1 + nst3; ++it) {
+      const int s = it % NST;
+      const uint32_t ph = (it / NST) & 1;
+      if (lane == 0) gt_mbar_wait(bar_empty + 8 * s, ph ^ 1);
+      __syncwarp();
+      const uint32_t dst = gt_smem_u32(ring + (size_t)s * stage_floats);
+      if (it < nst1) {
+        if (lane == 0) {
+          const uint32_t bytes = (uint32_t)CQ * hw * 4;
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_full + 8 * s), "r"(bytes) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                       "l"(reinterpret_cast<uint64_t>(Xi + (int64_t)it * CQ * hw)), "r"(bytes), "r"(bar_full + 8 * s) : "memory");
+        }
+      } else {
+        const int q0 = (it - nst1) * GT_SLAB;
+        const uint32_t rowbytes = (uint32_t)min(GT_SLAB, hw - q0) * 4;
+        if (lane == 0)
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_full + 8 * s), "r"(rowbytes * c) : "memory");
+        __syncwarp();
+        for (int ch = lane; ch < c; ch += 32)
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + ch * GT_SLAB * 4),
+                       "l"(reinterpret_cast<uint64_t>(Xi + (int64_t)ch * hw + q0)), "r"(rowbytes), "r"(bar_full + 8 * s) : "memory");
+      }
+    }
+  } else {
+    // ===== compute warps =====
+    // ---- phase 1: thread = pixel pair, stage = CQ channels ----
+    const bool own = tid < npairs;                 // host guarantees npairs <= 832
+    unsigned long long acc[2][5];
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+#pragma unroll
+      for (int t = 0; t < 5; ++t) acc[k][t] = 0ull;
+    for (int it = 0; it < nst1; ++it) {
+      const int s = it % NST;
+      gt_mbar_wait(bar_full + 8 * s, (it / NST) & 1);
+      const float *st = ring + (size_t)s * stage_floats;
+      if (own) {
+        for (int u = 0; u < CQ; ++u) {
+          const float2 x2 = *reinterpret_cast<const float2 *>(st + (size_t)u * hw + 2 * tid);
+          const float *pp = ps + (it * CQ + u) * 12;
+          const ulonglong2 pa = *reinterpret_cast<const ulonglong2 *>(pp);
+          const ulonglong2 pb = *reinterpret_cast<const ulonglong2 *>(pp + 4);
+          const unsigned long long pc = *reinterpret_cast<const unsigned long long *>(pp + 8);
+          const unsigned long long xa = pack2(x2.x, x2.x), xb = pack2(x2.y, x2.y);
+          ffma2(acc[0][0], xa, pa.x); ffma2(acc[0][1], xa, pa.y); ffma2(acc[0][2], xa, pb.x); ffma2(acc[0][3], xa, pb.y);
+          ffma2(acc[0][4], xa, pc);
+          ffma2(acc[1][0], xb, pa.x); ffma2(acc[1][1], xb, pa.y); ffma2(acc[1][2], xb, pb.x); ffma2(acc[1][3], xb, pb.y);
+          ffma2(acc[1][4], xb, pc);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_empty + 8 * s) : "memory");
+    }
+    if (own) {
+      float y[2][10];
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int t = 0; t < 5; ++t) unpack2(acc[k][t], y[k][2 * t], y[k][2 * t + 1]);
+#pragma unroll
+      for (int t = 0; t < 9; ++t) *reinterpret_cast<float2 *>(Y + t * hw + 2 * tid) = make_float2(y[0][t], y[1][t]);
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(GT_CONSUMER_WARPS * 32) : "memory");
+
+    // ---- phase 2 ----
+    for (int q = tid; q < hw; q += GT_CONSUMER_WARPS * 32) {
+      const int py = q / w, px = q - py * w;
+      float sv = 0.f;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int yy = py + t / 3 - 1, xx = px + t % 3 - 1;
+        if (yy >= 0 && yy < h && xx >= 0 && xx < w) sv += Y[t * hw + yy * w + xx];
+      }
+      sp[(py + 1) * wp + px + 1] = sv;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(GT_CONSUMER_WARPS * 32) : "memory");
+    const float *Si = S + (int64_t)i * 9 * hw, *Ti = T + (int64_t)i * hw;
+    for (int q = tid; q < hw; q += GT_CONSUMER_WARPS * 32) {
+      const int py = q / w, px = q - py * w;
+      float av = 0.f;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) av = fmaf(Si[t * hw + q], sp[(py + t / 3) * wp + px + t % 3], av);
+      if (use_y) av -= Ti[q];
+      vp[(py + 1) * wp + px + 1] = wgt * av;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(GT_CONSUMER_WARPS * 32) : "memory");
+
+    // ---- phase 3: warp = channel quad (warps beyond c/4 only keep the ring's arrival count), stage = 64 pixels ----
+    const int nquad = c >> 2;
+    float g[4][9];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) g[u][t] = 0.f;
+    for (int k3 = 0; k3 < nst3; ++k3) {
+      const int it = nst1 + k3;
+      const int s = it % NST;
+      gt_mbar_wait(bar_full + 8 * s, (it / NST) & 1);
+      const float *st = ring + (size_t)s * stage_floats;
+      const int q = k3 * GT_SLAB + 2 * lane;
+      if (warp < nquad && q < hw) {
+        const int py = q / w, px = q - py * w;
+        float vw[3][4];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const float2 v01 = *reinterpret_cast<const float2 *>(vp + (py + r) * wp + px);
+          const float2 v23 = *reinterpret_cast<const float2 *>(vp + (py + r) * wp + px + 2);
+          vw[r][0] = v01.x; vw[r][1] = v01.y; vw[r][2] = v23.x; vw[r][3] = v23.y;
+        }
+        float2 x2[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x2[u] = *reinterpret_cast<const float2 *>(st + (size_t)(warp * 4 + u) * GT_SLAB + 2 * lane);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const int dy = t / 3 - 1, dx = t % 3 - 1;
+          const float v0 = vw[1 - dy][1 - dx], v1 = vw[1 - dy][2 - dx];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) g[u][t] = fmaf(x2[u].x, v0, fmaf(x2[u].y, v1, g[u][t]));
+        }
+      }
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_empty + 8 * s) : "memory");
+    }
+    if (warp < nquad) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const float r = warp_sum(g[u][t]);
+          if (lane == 0) partial[(int64_t)i * n + (warp * 4 + u) * 9 + t] = r;
+        }
+    }
   }
 }
 
@@ -881,20 +1094,42 @@ static int gn_update_impl(const float *samples, const float *stencil, const floa
   cg.r = vecs; cg.x = vecs + n; cg.q = vecs + 2 * n;
   cg.partial = partial; cg.n = n; cg.cap = cap; cg.reg2 = reg * reg; cg.minv = 1.f / precond; cg.forget = forget;
   const dim3 grid(cap, table ? n_obj : 1);
+  // bulk-copy staged kernel: needs an even width (pixel pairs stay inside a row), hw % 4 == 0 (16-byte bulk copies),
+  // one pixel pair per compute thread, one channel quad per compute warp, and the ring must fit in shared memory
+  int CQ = 0, NST = 0, stage_floats = 0;
+  size_t gt_smem = 0;
+  if (fast && hw % 4 == 0 && hw / 2 <= GT_CONSUMER_WARPS * 32 && c / 4 <= GT_CONSUMER_WARPS && c % 4 == 0) {
+    const size_t fixed = ((size_t)9 * hw + 2 * (size_t)(h + 2) * (w + 2) + (size_t)c * 12) * sizeof(float) + 256;
+    for (int cq = 4; cq >= 1 && CQ == 0; cq >>= 1) {
+      if (c % cq) continue;
+      const int sf = (std::max(cq * hw, c * GT_SLAB) + 31) / 32 * 32;
+      for (int nst = 4; nst >= 2; --nst) {
+        const size_t total = fixed + (size_t)nst * sf * sizeof(float) + 16 * nst;
+        if (total <= 227 * 1024) { CQ = cq; NST = nst; stage_floats = sf; gt_smem = total; break; }
+      }
+    }
+  }
+  static size_t gt_configured = 0;
+  if (CQ && gt_smem > gt_configured) {
+    cudaError_t e = cudaFuncSetAttribute(gn_apply_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gt_smem);
+    if (e != cudaSuccess) { cudaGetLastError(); CQ = 0; } else gt_configured = gt_smem;
+  }
   // gating: the tiny vector kernel checks the gate and skips all arithmetic; the streaming kernel is harmless (it only
   // writes workspace), so it is launched unconditionally to keep the stream free of host syncs.
   for (int gi = 0; gi < n_gn; ++gi) {
     const int iters = cg_iters[gi];
     if (iters <= 0) continue;
     ga.use_y = 1; ga.pvec = filt;        // RHS: partial_i = X_i^T sw_i (S_i (X_i * f) - t_i)
-    if (fast) gn_apply_kernel<true><<<grid, GA_THREADS, ga_smem, st>>>(ga);
+    if (CQ) gn_apply_tma_kernel<<<grid, GT_THREADS, gt_smem, st>>>(ga, CQ, NST, stage_floats);
+    else if (fast) gn_apply_kernel<true><<<grid, GA_THREADS, ga_smem, st>>>(ga);
     else gn_apply_kernel<false><<<grid, GA_THREADS, ga_smem, st>>>(ga);
     FRTM_CHECK_LAUNCH("gn_update/apply(rhs)");
     cg_vector_kernel<<<table ? n_obj : 1, 1024, 0, st>>>(cg, 0, gate_count, min_px, table, n_obj);
     FRTM_CHECK_LAUNCH("gn_update/cg(rhs)");
     ga.use_y = 0; ga.pvec = cg.p;
     for (int it = 0; it < iters; ++it) {
-      if (fast) gn_apply_kernel<true><<<grid, GA_THREADS, ga_smem, st>>>(ga);
+      if (CQ) gn_apply_tma_kernel<<<grid, GT_THREADS, gt_smem, st>>>(ga, CQ, NST, stage_floats);
+      else if (fast) gn_apply_kernel<true><<<grid, GA_THREADS, ga_smem, st>>>(ga);
       else gn_apply_kernel<false><<<grid, GA_THREADS, ga_smem, st>>>(ga);
       FRTM_CHECK_LAUNCH("gn_update/apply");
       cg_vector_kernel<<<table ? n_obj : 1, 1024, 0, st>>>(cg, it == iters - 1 ? 2 : 1, gate_count, min_px, table, n_obj);
@@ -1073,7 +1308,7 @@ struct InitKey {
   std::vector<long long> v;
   bool operator<(const InitKey &o) const { return v < o.v; }
 };
-struct InitGraph { int calls = 0; cudaGraphExec_t exec = nullptr; };
+struct InitGraph { int calls = 0; int kernels = 1; cudaGraphExec_t exec = nullptr; };
 std::map<InitKey, InitGraph> g_init_graphs;
 std::mutex g_init_mutex;
 }  // namespace
@@ -1123,8 +1358,11 @@ extern "C" int frtm_gn_init(const float *x_nhwc, const float *stencil, const flo
     // second call with this signature: capture on gs
     cudaError_t e = cudaStreamBeginCapture(gs, cudaStreamCaptureModeRelaxed);
     if (e != cudaSuccess) { cudaGetLastError(); g.calls = -1000000; join(); return eager(); }
+    const int64_t before = frtm_launch_count();
     const int rc = gn_init_impl(x_nhwc, stencil, uty, sw, K, C, c, h, w, P, F, cg_iters, n_gn, regP, regF, precondP, precondF,
                                 forget, workspace, workspace_bytes, gs, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    g.kernels = (int)(frtm_launch_count() - before);     // kernel nodes in the graph (counted once here, per replay below)
+    count_launch(-g.kernels);
     cudaGraph_t graph = nullptr;
     e = cudaStreamEndCapture(gs, &graph);
     if (rc != FRTM_OK || e != cudaSuccess || graph == nullptr) {
@@ -1141,7 +1379,7 @@ extern "C" int frtm_gn_init(const float *x_nhwc, const float *stencil, const flo
   cudaError_t e = cudaGraphLaunch(g.exec, gs);
   join();
   if (e != cudaSuccess) { set_error("gn_init: cudaGraphLaunch: %s", cudaGetLastError() == cudaSuccess ? cudaGetErrorString(e) : "launch failed"); return FRTM_ELAUNCH; }
-  count_launch(1);
+  count_launch(g.kernels);                               // kernels executed by the replayed graph
   return FRTM_OK;
 }
 
