@@ -377,7 +377,8 @@ __device__ __forceinline__ void gt_mbar_wait(uint32_t bar, uint32_t parity) {
   __trap();
 }
 
-__global__ void __launch_bounds__(GT_THREADS, 1) gn_apply_tma_kernel(const GaArgs a, int CQ, int NST, int stage_floats) {
+template <int CQ>
+__global__ void __launch_bounds__(GT_THREADS, 1) gn_apply_tma_kernel(const GaArgs a, int NST, int stage_floats) {
   const float *__restrict__ X = a.X, *__restrict__ S = a.S, *__restrict__ T = a.T, *__restrict__ sw = a.sw,
                            *__restrict__ pvec = a.pvec;
   float *__restrict__ partial = a.partial;
@@ -427,32 +428,22 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gn_apply_tma_kernel(const GaArg
   const float *Xi = X + (int64_t)i * c * hw;
   const int npairs = hw >> 1;
   const int nst1 = c / CQ;                              // phase-1 stages
-  const int nst3 = (hw + GT_SLAB - 1) / GT_SLAB;        // phase-3 stages
 
   if (warp == GT_CONSUMER_WARPS) {
     // ===== producer warp =====
-    for (int it = 0; it < nst1 + nst3; ++it) {
-      const int s = it % NST;
-      const uint32_t ph = (it / NST) & 1;
-      if (lane == 0) gt_mbar_wait(bar_empty + 8 * s, ph ^ 1);
-      __syncwarp();
-      const uint32_t dst = gt_smem_u32(ring + (size_t)s * stage_floats);
-      if (it < nst1) {
-        if (lane == 0) {
-          const uint32_t bytes = (uint32_t)CQ * hw * 4;
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_full + 8 * s), "r"(bytes) : "memory");
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                       "l"(reinterpret_cast<uint64_t>(Xi + (int64_t)it * CQ * hw)), "r"(bytes), "r"(bar_full + 8 * s) : "memory");
-        }
-      } else {
-        const int q0 = (it - nst1) * GT_SLAB;
-        const uint32_t rowbytes = (uint32_t)min(GT_SLAB, hw - q0) * 4;
-        if (lane == 0)
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_full + 8 * s), "r"(rowbytes * c) : "memory");
-        __syncwarp();
-        for (int ch = lane; ch < c; ch += 32)
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + ch * GT_SLAB * 4),
-                       "l"(reinterpret_cast<uint64_t>(Xi + (int64_t)ch * hw + q0)), "r"(rowbytes), "r"(bar_full + 8 * s) : "memory");
+    // phase 1 only: large contiguous copies (CQ whole channels each).  Phase 3 wants all channels x few pixels, i.e.
+    // c small row segments per stage; issued as separate bulk copies those are request-rate bound (measured 2.4x slower
+    // than direct loads), so phase 3 reads its second pass straight from L2 with register prefetch instead.
+    if (lane == 0) {
+      for (int it = 0; it < nst1; ++it) {
+        const int s = it % NST;
+        const uint32_t ph = (it / NST) & 1;
+        gt_mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        const uint32_t dst = gt_smem_u32(ring + (size_t)s * stage_floats);
+        const uint32_t bytes = (uint32_t)CQ * hw * 4;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_full + 8 * s), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                     "l"(reinterpret_cast<uint64_t>(Xi + (int64_t)it * CQ * hw)), "r"(bytes), "r"(bar_full + 8 * s) : "memory");
       }
     }
   } else {
@@ -466,12 +457,16 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gn_apply_tma_kernel(const GaArg
       for (int t = 0; t < 5; ++t) acc[k][t] = 0ull;
     for (int it = 0; it < nst1; ++it) {
       const int s = it % NST;
-      gt_mbar_wait(bar_full + 8 * s, (it / NST) & 1);
+      if (lane == 0) gt_mbar_wait(bar_full + 8 * s, (it / NST) & 1);   // one poller per warp
+      __syncwarp();
       const float *st = ring + (size_t)s * stage_floats;
       if (own) {
+        const float *xs = st + 2 * tid;
+        const float *pq = ps + it * CQ * 12;
+#pragma unroll
         for (int u = 0; u < CQ; ++u) {
-          const float2 x2 = *reinterpret_cast<const float2 *>(st + (size_t)u * hw + 2 * tid);
-          const float *pp = ps + (it * CQ + u) * 12;
+          const float2 x2 = *reinterpret_cast<const float2 *>(xs + (size_t)u * hw);
+          const float *pp = pq + u * 12;
           const ulonglong2 pa = *reinterpret_cast<const ulonglong2 *>(pp);
           const ulonglong2 pb = *reinterpret_cast<const ulonglong2 *>(pp + 4);
           const unsigned long long pc = *reinterpret_cast<const unsigned long long *>(pp + 8);
@@ -519,21 +514,32 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gn_apply_tma_kernel(const GaArg
     }
     asm volatile("bar.sync 1, %0;" ::"n"(GT_CONSUMER_WARPS * 32) : "memory");
 
-    // ---- phase 3: warp = channel quad (warps beyond c/4 only keep the ring's arrival count), stage = 64 pixels ----
+    // ---- phase 3: warp = channel quad, lane = pixel pair, second pass over the sample straight from L2 ----
     const int nquad = c >> 2;
-    float g[4][9];
+    for (int quad = warp; quad < nquad; quad += GT_CONSUMER_WARPS) {
+      float g[4][9];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < 4; ++u)
 #pragma unroll
-      for (int t = 0; t < 9; ++t) g[u][t] = 0.f;
-    for (int k3 = 0; k3 < nst3; ++k3) {
-      const int it = nst1 + k3;
-      const int s = it % NST;
-      gt_mbar_wait(bar_full + 8 * s, (it / NST) & 1);
-      const float *st = ring + (size_t)s * stage_floats;
-      const int q = k3 * GT_SLAB + 2 * lane;
-      if (warp < nquad && q < hw) {
-        const int py = q / w, px = q - py * w;
+        for (int t = 0; t < 9; ++t) g[u][t] = 0.f;
+      const float2 *xo = reinterpret_cast<const float2 *>(Xi + (int64_t)quad * 4 * hw) + lane;
+      const int stride2 = hw >> 1;
+      float2 nx[4];
+      if (lane < npairs) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) nx[u] = __ldg(xo + (int64_t)u * stride2);
+      }
+      int py = (2 * lane) / w, px = 2 * lane - py * w;
+#pragma unroll 1
+      for (int gp = lane; gp < npairs; gp += 32) {
+        float2 x2[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x2[u] = nx[u];
+        xo += 32;
+        if (gp + 32 < npairs) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) nx[u] = __ldg(xo + (int64_t)u * stride2);
+        }
         float vw[3][4];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
@@ -541,9 +547,6 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gn_apply_tma_kernel(const GaArg
           const float2 v23 = *reinterpret_cast<const float2 *>(vp + (py + r) * wp + px + 2);
           vw[r][0] = v01.x; vw[r][1] = v01.y; vw[r][2] = v23.x; vw[r][3] = v23.y;
         }
-        float2 x2[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) x2[u] = *reinterpret_cast<const float2 *>(st + (size_t)(warp * 4 + u) * GT_SLAB + 2 * lane);
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
           const int dy = t / 3 - 1, dx = t % 3 - 1;
@@ -551,17 +554,15 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gn_apply_tma_kernel(const GaArg
 #pragma unroll
           for (int u = 0; u < 4; ++u) g[u][t] = fmaf(x2[u].x, v0, fmaf(x2[u].y, v1, g[u][t]));
         }
+        px += 64;
+        while (px >= w) { px -= w; ++py; }
       }
-      __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_empty + 8 * s) : "memory");
-    }
-    if (warp < nquad) {
 #pragma unroll
       for (int u = 0; u < 4; ++u)
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
           const float r = warp_sum(g[u][t]);
-          if (lane == 0) partial[(int64_t)i * n + (warp * 4 + u) * 9 + t] = r;
+          if (lane == 0) partial[(int64_t)i * n + (quad * 4 + u) * 9 + t] = r;
         }
     }
   }
@@ -1098,11 +1099,11 @@ static int gn_update_impl(const float *samples, const float *stencil, const floa
   // one pixel pair per compute thread, one channel quad per compute warp, and the ring must fit in shared memory
   int CQ = 0, NST = 0, stage_floats = 0;
   size_t gt_smem = 0;
-  if (fast && hw % 4 == 0 && hw / 2 <= GT_CONSUMER_WARPS * 32 && c / 4 <= GT_CONSUMER_WARPS && c % 4 == 0) {
+  if (fast && hw % 4 == 0 && hw / 2 <= GT_CONSUMER_WARPS * 32 && c % 4 == 0) {
     const size_t fixed = ((size_t)9 * hw + 2 * (size_t)(h + 2) * (w + 2) + (size_t)c * 12) * sizeof(float) + 256;
     for (int cq = 4; cq >= 1 && CQ == 0; cq >>= 1) {
       if (c % cq) continue;
-      const int sf = (std::max(cq * hw, c * GT_SLAB) + 31) / 32 * 32;
+      const int sf = (cq * hw + 31) / 32 * 32;
       for (int nst = 4; nst >= 2; --nst) {
         const size_t total = fixed + (size_t)nst * sf * sizeof(float) + 16 * nst;
         if (total <= 227 * 1024) { CQ = cq; NST = nst; stage_floats = sf; gt_smem = total; break; }
@@ -1111,26 +1112,31 @@ static int gn_update_impl(const float *samples, const float *stencil, const floa
   }
   static size_t gt_configured = 0;
   if (CQ && gt_smem > gt_configured) {
-    cudaError_t e = cudaFuncSetAttribute(gn_apply_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gt_smem);
+    cudaError_t e = cudaFuncSetAttribute(gn_apply_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gt_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gn_apply_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gt_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gn_apply_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gt_smem);
     if (e != cudaSuccess) { cudaGetLastError(); CQ = 0; } else gt_configured = gt_smem;
   }
+  auto launch_apply = [&]() {
+    if (CQ == 4) gn_apply_tma_kernel<4><<<grid, GT_THREADS, gt_smem, st>>>(ga, NST, stage_floats);
+    else if (CQ == 2) gn_apply_tma_kernel<2><<<grid, GT_THREADS, gt_smem, st>>>(ga, NST, stage_floats);
+    else if (CQ == 1) gn_apply_tma_kernel<1><<<grid, GT_THREADS, gt_smem, st>>>(ga, NST, stage_floats);
+    else if (fast) gn_apply_kernel<true><<<grid, GA_THREADS, ga_smem, st>>>(ga);
+    else gn_apply_kernel<false><<<grid, GA_THREADS, ga_smem, st>>>(ga);
+  };
   // gating: the tiny vector kernel checks the gate and skips all arithmetic; the streaming kernel is harmless (it only
   // writes workspace), so it is launched unconditionally to keep the stream free of host syncs.
   for (int gi = 0; gi < n_gn; ++gi) {
     const int iters = cg_iters[gi];
     if (iters <= 0) continue;
     ga.use_y = 1; ga.pvec = filt;        // RHS: partial_i = X_i^T sw_i (S_i (X_i * f) - t_i)
-    if (CQ) gn_apply_tma_kernel<<<grid, GT_THREADS, gt_smem, st>>>(ga, CQ, NST, stage_floats);
-    else if (fast) gn_apply_kernel<true><<<grid, GA_THREADS, ga_smem, st>>>(ga);
-    else gn_apply_kernel<false><<<grid, GA_THREADS, ga_smem, st>>>(ga);
+    launch_apply();
     FRTM_CHECK_LAUNCH("gn_update/apply(rhs)");
     cg_vector_kernel<<<table ? n_obj : 1, 1024, 0, st>>>(cg, 0, gate_count, min_px, table, n_obj);
     FRTM_CHECK_LAUNCH("gn_update/cg(rhs)");
     ga.use_y = 0; ga.pvec = cg.p;
     for (int it = 0; it < iters; ++it) {
-      if (CQ) gn_apply_tma_kernel<<<grid, GT_THREADS, gt_smem, st>>>(ga, CQ, NST, stage_floats);
-      else if (fast) gn_apply_kernel<true><<<grid, GA_THREADS, ga_smem, st>>>(ga);
-      else gn_apply_kernel<false><<<grid, GA_THREADS, ga_smem, st>>>(ga);
+      launch_apply();
       FRTM_CHECK_LAUNCH("gn_update/apply");
       cg_vector_kernel<<<table ? n_obj : 1, 1024, 0, st>>>(cg, it == iters - 1 ? 2 : 1, gate_count, min_px, table, n_obj);
       FRTM_CHECK_LAUNCH("gn_update/cg");
