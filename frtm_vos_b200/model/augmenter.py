@@ -73,7 +73,7 @@ def directional_blur_kernel(sx: float, sy: float, rot2: np.ndarray) -> np.ndarra
     return (g / g.sum() * 1.0).astype(np.float32)
 
 
-def draw_specs(pool: dict) -> List[dict]:
+def draw_specs(pool: dict, rng=np.random) -> List[dict]:
     """Tile/shuffle/slice every parameter list, then zip into per-view specs (augmenter.py:194-222)."""
     merged = dict(_SPEC_DEFAULT_POOL)
     for k, v in pool.items():
@@ -84,7 +84,7 @@ def draw_specs(pool: dict) -> List[dict]:
         if key == "num_aug":
             continue
         vals = list(vals) * ((n + len(vals) - 1) // len(vals))
-        np.random.shuffle(vals)
+        rng.shuffle(vals)
         cols[key] = vals[:n]
     specs = []
     for i in range(n):
@@ -181,7 +181,7 @@ def mask_center_bbox(mask: torch.Tensor):
     return x + w / 2, y + h / 2, w, h
 
 
-def target_locations(n: int, im_size) -> List[Tuple[float, float]]:
+def target_locations(n: int, im_size, rng=np.random) -> List[Tuple[float, float]]:
     """Jittered grid of new object centres, shuffled (augmenter.py:169-192)."""
     h, w = im_size
     aspect = w / h
@@ -190,10 +190,10 @@ def target_locations(n: int, im_size) -> List[Tuple[float, float]]:
     pts = []
     for r in range(nrows):
         for c in range(ncols):
-            x = (c + 0.5) / ncols + np.random.normal(0, 0.5 / ncols / 4)
-            y = (r + 0.5) / nrows + np.random.normal(0, 0.5 / nrows / 4)
+            x = (c + 0.5) / ncols + rng.normal(0, 0.5 / ncols / 4)
+            y = (r + 0.5) / nrows + rng.normal(0, 0.5 / nrows / 4)
             pts.append((np.round(x, 3), np.round(y, 3)))
-    np.random.shuffle(pts)
+    rng.shuffle(pts)
     return pts[:n]
 
 
@@ -280,8 +280,9 @@ class ImageAugmenter:
         L.alpha_paste(ptr(obj), ptr(canvas), H, W, ptr(out), stream())
         return out
 
-    def augment_first_frame(self, im: torch.Tensor, lb: torch.Tensor):
+    def augment_first_frame(self, im: torch.Tensor, lb: torch.Tensor, rng=None):
         """(3,H,W) u8 + (1,H,W) u8 mask -> ((K,3,H,W) u8, (K,1,H,W) u8) on ``im.device`` (augmenter.py:473-555)."""
+        rng = np.random if rng is None else rng     # np.random.RandomState(seed) draws the same stream as seed(seed)
         p = self.params
         dev = im.device
         im_h, lb_h = im.detach().cpu(), lb.detach().cpu()
@@ -296,7 +297,7 @@ class ImageAugmenter:
         cut, bg = cut_and_inpaint(im_h, lb_h, d=1, f=1)
 
         fg_pool = copy.deepcopy(dict(p["fg_aug_params"]))
-        fg_pool["location"] = target_locations(p["num_aug"], size)
+        fg_pool["location"] = target_locations(p["num_aug"], size, rng)
         bg_pool = copy.deepcopy(dict(p["bg_aug_params"])) if "bg_aug_params" in p else None
         want = p["num_aug"] - 1
         lo, hi = p["min_px_count"], lb_h.shape[-1] * lb_h.shape[-2] - p["min_px_count"]
@@ -307,8 +308,8 @@ class ImageAugmenter:
         on_device = dev.type == "cuda" and self.device_render
         cand, masks = [], []
         while len(cand) < want:
-            fg_specs = draw_specs(fg_pool)
-            bg_specs = draw_specs(bg_pool) if bg_pool is not None else [None] * len(fg_specs)
+            fg_specs = draw_specs(fg_pool, rng)
+            bg_specs = draw_specs(bg_pool, rng) if bg_pool is not None else [None] * len(fg_specs)
             if on_device:
                 warped, counts = self._warp_masks_device(lb.to(dev), fg_specs, bbox, size)
             for j, (fs, bs) in enumerate(zip(fg_specs, bg_specs)):
@@ -322,7 +323,7 @@ class ImageAugmenter:
                     masks.append(m)
         if len(cand) > want:
             order = list(range(len(cand)))
-            np.random.shuffle(order)
+            rng.shuffle(order)
             order = order[:want]
             cand = [cand[i] for i in order]
             masks = [masks[i] for i in order]

@@ -67,6 +67,7 @@ class Tracker(nn.Module):
         self.num_objects = 0
         self.targets = dict()
         self.object_ids = []
+        self.augment_workers = 4    # host threads preparing first-frame augmentations of several new objects at once
         self.block_batching = True  # run_sequence batches up to max_block frames between two filter updates
         self.max_block = 8
         self._stack = None          # cached stacked projection of the live objects
@@ -193,36 +194,69 @@ class Tracker(nn.Module):
     def initialize(self, image, labels, new_objects):
         """Create and fit a target model per new object (``:165-191``).
 
-        Augmentation (host OpenCV inpaint + spec drawing, device rendering, one small device->host read) runs on a side
-        stream, so the host can prepare object k+1 while the GPU is still fitting object k on the main stream."""
+        Augmentation is host work (OpenCV inpaint, spec drawing) plus a few device kernels and one small device->host read
+        per object.  It runs in worker threads, each on its own CUDA side stream and with its own
+        ``numpy.random.RandomState(0)`` (the reference reseeds the global generators to 0 before every object,
+        ``:178-180``, so the draws are identical), while the main thread fits the objects on the main stream in order."""
         self.current_masks = torch.zeros((len(self.targets) + len(new_objects) + 1, *image.shape[-2:]), device=self.device)
         main = torch.cuda.current_stream()
-        if getattr(self, "_aug_stream", None) is None:
-            self._aug_stream = torch.cuda.Stream(device=image.device)
-        side = self._aug_stream
-        side.wait_stream(main)                       # image / labels uploads are visible to the side stream
-        for obj_id in new_objects:
-            with torch.cuda.stream(side):
+        n_new = len(new_objects)
+        if getattr(self, "_aug_streams", None) is None or len(self._aug_streams) < n_new:
+            self._aug_streams = [torch.cuda.Stream(device=image.device) for _ in range(max(n_new, 1))]
+        for st in self._aug_streams[:n_new]:
+            st.wait_stream(main)                     # image / labels uploads are visible to the side streams
+        # targets are constructed in order on the main thread: each constructor draws its initial weights from the global
+        # torch generator exactly where the reference does (before the reseed of that object)
+        targets = []
+        for k, obj_id in enumerate(new_objects):
+            with torch.cuda.stream(self._aug_streams[k]):
                 mask = (labels == obj_id).byte()
-                # constructed under the side stream: the (pageable, hence synchronous) upload of the freshly drawn
-                # project/filter weights then waits for the side stream only, not for the previous object's fit
+                # built under a side stream: the (pageable, hence synchronous) upload of the freshly drawn project/filter
+                # weights then waits for that stream only
                 target = TargetObject(obj_id=obj_id, index=len(self.targets) + 1, disc_params=self.disc_params,
                                       start_frame=self.current_frame, start_mask=mask)
             self.targets[obj_id] = target
-            # same (debug) reseeding as the reference so augmentation is deterministic per object (:178-180)
+            targets.append(target)
             torch.random.manual_seed(0)
             np.random.seed(0)
+
+        def augment_job(k):
+            side = self._aug_streams[k]
             with torch.cuda.stream(side):
-                im, msk = self.augment(image, mask)
+                if self._augment_takes_rng:
+                    im, msk = self.augment(image, targets[k].start_mask, rng=np.random.RandomState(0))
+                else:
+                    im, msk = self.augment(image, targets[k].start_mask)
                 im, msk = im.to(self.device), msk.to(self.device)
-                ready = side.record_event()
+                return im, msk, side.record_event()
+
+        if getattr(self, "_augment_takes_rng", None) is None:
+            import inspect
+            try:
+                self._augment_takes_rng = "rng" in inspect.signature(self.augment).parameters
+            except (TypeError, ValueError):
+                self._augment_takes_rng = False
+        workers = min(n_new, self.augment_workers) if self._augment_takes_rng else 1
+        if workers > 1:
+            if getattr(self, "_pool", None) is None:
+                from concurrent.futures import ThreadPoolExecutor
+                self._pool = ThreadPoolExecutor(max_workers=self.augment_workers, thread_name_prefix="frtm-aug")
+            futures = [self._pool.submit(augment_job, k) for k in range(n_new)]
+            results = (f.result() for f in futures)
+        else:
+            def sequential():
+                for k in range(n_new):
+                    np.random.seed(0)                # foreign augmenters use the global generator, like the reference
+                    yield augment_job(k)
+            results = sequential()
+        for target, (im, msk, ready) in zip(targets, results):
             main.wait_event(ready)
-            for t in (im, msk, mask, target.discriminator.project.weight.data, target.discriminator.filter.weight.data):
+            for t in (im, msk, target.start_mask, target.discriminator.project.weight.data, target.discriminator.filter.weight.data):
                 t.record_stream(main)
             _, f32, _ = self.feature_extractor.forward_split(im, (), (target.disc_layer,), upto=target.disc_layer)
             target.discriminator.init(None, msk, x_nhwc=f32[target.disc_layer])
             self._bind_filter(target)
-            self.current_masks[target.index] = mask
+            self.current_masks[target.index] = target.start_mask
         self._stack = None
         self._gn_table = None
         return self.current_masks
