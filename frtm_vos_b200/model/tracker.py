@@ -249,12 +249,21 @@ class Tracker(nn.Module):
                     np.random.seed(0)                # foreign augmenters use the global generator, like the reference
                     yield augment_job(k)
             results = sequential()
-        for target, (im, msk, ready) in zip(targets, results):
-            main.wait_event(ready)
-            for t in (im, msk, target.start_mask, target.discriminator.project.weight.data, target.discriminator.filter.weight.data):
+        # Object k is fitted on its own stream k (the one its augmentation ran on): the fits are chains of small kernels
+        # (~650 per object, replayed as one CUDA graph each) that leave most of the GPU idle, so the objects of a frame
+        # overlap on the device instead of queueing behind each other.
+        for k, (target, (im, msk, ready)) in enumerate(zip(targets, results)):
+            side = self._aug_streams[k]
+            with torch.cuda.stream(side):
+                _, f32, _ = self.feature_extractor.forward_split(im, (), (target.disc_layer,), upto=target.disc_layer)
+                target.discriminator.init(None, msk, x_nhwc=f32[target.disc_layer])
+        for k, target in enumerate(targets):
+            main.wait_stream(self._aug_streams[k])
+            d = target.discriminator
+            for t in (target.start_mask, d.project.weight.data, d.filter.weight.data, d.memory.samples, d.memory.labels,
+                      d.memory.pixel_weights, d.memory.weights, d.memory.stencil, d.memory.uty, d.memory.state,
+                      d.update_optimizer.cg_state):
                 t.record_stream(main)
-            _, f32, _ = self.feature_extractor.forward_split(im, (), (target.disc_layer,), upto=target.disc_layer)
-            target.discriminator.init(None, msk, x_nhwc=f32[target.disc_layer])
             self._bind_filter(target)
             self.current_masks[target.index] = target.start_mask
         self._stack = None
