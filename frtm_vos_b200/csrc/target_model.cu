@@ -8,6 +8,7 @@
 // with Js the Jacobian of the low-resolution score map.  S_i and t_i = U^T pw_i^2 y_i are built once per memory
 // sample at insert time, so the full-resolution maps are never touched inside CG.
 #include "common.cuh"
+#include "target_model.cuh"
 #include <cstring>
 #include <algorithm>
 
@@ -164,14 +165,6 @@ __device__ __forceinline__ void ffma2(unsigned long long &d, unsigned long long 
 
 constexpr int GA_THREADS = 832;   // 26 warps: 810 pixel pairs of a 30x54 map in one round; 24 channel quads in phase 3
 
-// Pointer table for object-batched launches: rows {samples, stencil, uty, weights, filt, cg_state, gate_count} x n_obj.
-struct GaArgs {
-  const float *X, *S, *T, *sw, *pvec;   // single-object form (table == nullptr)
-  const long long *table;               // batched form: blockIdx.y = object
-  float *partial;                       // [n_obj][cap][c*9]
-  int n_obj, cap, c, h, w, use_y;
-};
-
 template <bool FAST>   // FAST: even width -> 8-byte loads and a shared 3x4 window per pixel pair
 __global__ void __launch_bounds__(GA_THREADS, 1) gn_apply_kernel(const GaArgs a) {
   const float *__restrict__ X = a.X, *__restrict__ S = a.S, *__restrict__ T = a.T, *__restrict__ sw = a.sw,
@@ -193,7 +186,8 @@ __global__ void __launch_bounds__(GA_THREADS, 1) gn_apply_kernel(const GaArgs a)
   float *Y = sm;                       // [9][hw]
   float *sp = Y + 9 * hw;              // padded scores
   float *vp = sp + npad;               // padded v
-  float *ps = vp + npad;               // [c][12]
+  float *ps = vp + npad;               // [c][12], read with 16-byte loads
+  ps = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(ps) + 15) & ~(uintptr_t)15);
   const int i = blockIdx.x;
   const int n = c * 9;
   const float wgt = sw[i];
@@ -397,7 +391,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gn_apply_tma_kernel(const GaArg
   float *Y = sm;                                   // [9][hw]
   float *sp = Y + 9 * hw;                          // padded scores
   float *vp = sp + npad;                           // padded v
-  float *ps = vp + npad;                           // [c][12]
+  float *ps = vp + npad;                           // [c][12], read with 16-byte loads
+  ps = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(ps) + 15) & ~(uintptr_t)15);
   float *ring = ps + c * 12;
   ring = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(ring) + 127) & ~(uintptr_t)127);
   uint64_t *bars = reinterpret_cast<uint64_t *>(ring + (size_t)NST * stage_floats);   // full[NST] | empty[NST]
@@ -701,18 +696,26 @@ __global__ void __launch_bounds__(32) memory_next_slot_kernel(float *__restrict_
   }
 }
 
-// All five pieces of one sample (projected features, soft label, pixel weights, stencil, U^T w^2 y) in one launch.
+// All five pieces of one sample (projected features, soft label, pixel weights, stencil, U^T w^2 y) in one launch, plus
+// the split tile image of the features that the tensor-core operator kernel streams (gn_apply_tc.cu).
 struct InsertArgs {
   const float *src[5];
   float *dst[5];
   int64_t n[5];
   int64_t total;
+  __half *split;          // [cap][gc_sample_halves] or null
+  int c, hw;
+  int64_t split_items;
 };
 __global__ void memory_insert_kernel(const InsertArgs a, const int *__restrict__ state) {
   const int slot = state[2];
   if (slot < 0) return;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.total) return;
+  if (i >= a.total) {
+    i -= a.total;
+    if (i < a.split_items) gc_split_item(a.src[0], a.split + (int64_t)slot * gc_sample_halves(a.c, a.hw), a.c, a.hw, i);
+    return;
+  }
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
     if (i < a.n[k]) {
@@ -1039,7 +1042,8 @@ extern "C" int frtm_memory_next_slot(float *weights, int capacity, float lr, int
 
 extern "C" int frtm_memory_insert(const float *feat, int feat_elems, const float *label, const float *pw, int HW,
                                   const float *stencil, const float *uty, int hw, float *mem_samples, float *mem_labels,
-                                  float *mem_pw, float *mem_stencil, float *mem_uty, const int *state, void *stream) {
+                                  float *mem_pw, float *mem_stencil, float *mem_uty, void *mem_split, const int *state,
+                                  void *stream) {
   FRTM_REQUIRE(feat && mem_samples && state, "memory_insert: bad arguments");
   InsertArgs a;
   const float *src[5] = {feat, label, pw, stencil, uty};
@@ -1051,20 +1055,29 @@ extern "C" int frtm_memory_insert(const float *feat, int feat_elems, const float
     a.src[k] = src[k]; a.dst[k] = dst[k]; a.n[k] = on ? n[k] : 0;
     a.total += a.n[k];
   }
-  memory_insert_kernel<<<cdiv(a.total, 256), 256, 0, (cudaStream_t)stream>>>(a, state);
+  a.split = (__half *)mem_split; a.c = 0; a.hw = hw; a.split_items = 0;
+  if (mem_split) {
+    FRTM_REQUIRE(hw > 0 && feat_elems % hw == 0 && (feat_elems / hw) % 8 == 0, "memory_insert: split image needs c %% 8 == 0");
+    a.c = feat_elems / hw;
+    a.split_items = (int64_t)gc_ntiles(hw) * a.c * 8;
+  }
+  memory_insert_kernel<<<cdiv(a.total + a.split_items, 256), 256, 0, (cudaStream_t)stream>>>(a, state);
   FRTM_CHECK_LAUNCH("memory_insert");
   return FRTM_OK;
 }
 
 // ---- filter-only GN/CG ------------------------------------------------------------------------------------------
+static float *g_gn_debug_dump = nullptr;   // tests only: device buffer receiving the score / v maps of CTA (0,0)
+extern "C" int frtm_gn_debug_dump(float *buf) { g_gn_debug_dump = buf; return FRTM_OK; }
+
 extern "C" int64_t frtm_gn_update_workspace(int cap, int c, int h, int w) {
   const int64_t n = (int64_t)c * 9, hw = (int64_t)h * w;
   // s[cap][hw] | v[cap][hw] | partial[cap][n] | r[n] | x[n] | q[n]
   return (2 * cap * hw + cap * n + 3 * n + 64) * (int64_t)sizeof(float);
 }
 
-static int gn_update_impl(const float *samples, const float *stencil, const float *uty, const float *weights,
-                          const long long *table, int n_obj, int cap, int c, int h, int w, float *filt, float *cg_state,
+static int gn_update_impl(const float *samples, const __half *samples_split, const float *stencil, const float *uty,
+                          const float *weights, const long long *table, bool table_has_split, int n_obj, int cap, int c, int h, int w, float *filt, float *cg_state,
                           const int *cg_iters, int n_gn, float reg, float precond, float forget, const int *gate_count,
                           int min_px, float *workspace, int64_t workspace_bytes, cudaStream_t st) {
   FRTM_REQUIRE(cg_iters && workspace && n_obj >= 1, "gn_update: null pointer");
@@ -1074,7 +1087,7 @@ static int gn_update_impl(const float *samples, const float *stencil, const floa
   const int n = c * 9, hw = h * w;
   FRTM_REQUIRE(c % 4 == 0, "gn_update: needs c %% 4 == 0 (got %d)", c);
   const bool fast = (w % 2 == 0);
-  const size_t ga_smem = ((size_t)9 * hw + 2 * (size_t)(h + 2) * (w + 2) + (size_t)c * 12) * sizeof(float);
+  const size_t ga_smem = ((size_t)9 * hw + 2 * (size_t)(h + 2) * (w + 2) + (size_t)c * 12) * sizeof(float) + 16;
   FRTM_REQUIRE(ga_smem <= 227 * 1024, "gn_update: feature map %dx%d too large for the shared-memory resident tap maps", h, w);
   static size_t ga_configured = 0;
   if (ga_smem > ga_configured) {
@@ -1088,6 +1101,9 @@ static int gn_update_impl(const float *samples, const float *stencil, const floa
   float *vecs = partial + (int64_t)n_obj * cap * n;
   GaArgs ga;
   ga.X = samples; ga.S = stencil; ga.T = uty; ga.sw = weights; ga.pvec = filt; ga.table = table; ga.partial = partial;
+  ga.XS = samples_split; ga.dbg = g_gn_debug_dump;
+  // tensor-core operator kernel: needs the split tile image of the samples (written at insert time)
+  const bool use_tc = (table ? table_has_split : samples_split != nullptr) && gn_apply_tc_supported(c, h, w);
   ga.n_obj = n_obj; ga.cap = cap; ga.c = c; ga.h = h; ga.w = w; ga.use_y = 1;
   CgVec cg;
   cg.f = filt; cg.p = cg_state; cg.rprev = cg_state ? cg_state + n : nullptr; cg.rho = cg_state ? cg_state + 2 * n : nullptr;
@@ -1117,12 +1133,18 @@ static int gn_update_impl(const float *samples, const float *stencil, const floa
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gn_apply_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gt_smem);
     if (e != cudaSuccess) { cudaGetLastError(); CQ = 0; } else gt_configured = gt_smem;
   }
-  auto launch_apply = [&]() {
+  auto launch_apply = [&]() -> int {
+    if (use_tc) {
+      const int rc = gn_apply_tc_launch(ga, st);
+      if (rc == FRTM_OK) count_launch(-1);                  // counted again by FRTM_CHECK_LAUNCH at the call site
+      return rc;
+    }
     if (CQ == 4) gn_apply_tma_kernel<4><<<grid, GT_THREADS, gt_smem, st>>>(ga, NST, stage_floats);
     else if (CQ == 2) gn_apply_tma_kernel<2><<<grid, GT_THREADS, gt_smem, st>>>(ga, NST, stage_floats);
     else if (CQ == 1) gn_apply_tma_kernel<1><<<grid, GT_THREADS, gt_smem, st>>>(ga, NST, stage_floats);
     else if (fast) gn_apply_kernel<true><<<grid, GA_THREADS, ga_smem, st>>>(ga);
     else gn_apply_kernel<false><<<grid, GA_THREADS, ga_smem, st>>>(ga);
+    return FRTM_OK;
   };
   // gating: the tiny vector kernel checks the gate and skips all arithmetic; the streaming kernel is harmless (it only
   // writes workspace), so it is launched unconditionally to keep the stream free of host syncs.
@@ -1130,13 +1152,13 @@ static int gn_update_impl(const float *samples, const float *stencil, const floa
     const int iters = cg_iters[gi];
     if (iters <= 0) continue;
     ga.use_y = 1; ga.pvec = filt;        // RHS: partial_i = X_i^T sw_i (S_i (X_i * f) - t_i)
-    launch_apply();
+    if (int rc = launch_apply()) return rc;
     FRTM_CHECK_LAUNCH("gn_update/apply(rhs)");
     cg_vector_kernel<<<table ? n_obj : 1, 1024, 0, st>>>(cg, 0, gate_count, min_px, table, n_obj);
     FRTM_CHECK_LAUNCH("gn_update/cg(rhs)");
     ga.use_y = 0; ga.pvec = cg.p;
     for (int it = 0; it < iters; ++it) {
-      launch_apply();
+      if (int rc = launch_apply()) return rc;
       FRTM_CHECK_LAUNCH("gn_update/apply");
       cg_vector_kernel<<<table ? n_obj : 1, 1024, 0, st>>>(cg, it == iters - 1 ? 2 : 1, gate_count, min_px, table, n_obj);
       FRTM_CHECK_LAUNCH("gn_update/cg");
@@ -1145,20 +1167,20 @@ static int gn_update_impl(const float *samples, const float *stencil, const floa
   return FRTM_OK;
 }
 
-extern "C" int frtm_gn_update(const float *samples, const float *stencil, const float *uty, const float *weights, int cap,
-                              int c, int h, int w, float *filt, float *cg_state, const int *cg_iters, int n_gn, float reg,
-                              float precond, float forget, const int *gate_count, int min_px, float *workspace,
-                              int64_t workspace_bytes, void *stream) {
+extern "C" int frtm_gn_update(const float *samples, const void *samples_split, const float *stencil, const float *uty,
+                              const float *weights, int cap, int c, int h, int w, float *filt, float *cg_state,
+                              const int *cg_iters, int n_gn, float reg, float precond, float forget, const int *gate_count,
+                              int min_px, float *workspace, int64_t workspace_bytes, void *stream) {
   FRTM_REQUIRE(samples && stencil && uty && weights && filt && cg_state, "gn_update: null pointer");
-  return gn_update_impl(samples, stencil, uty, weights, nullptr, 1, cap, c, h, w, filt, cg_state, cg_iters, n_gn, reg, precond,
+  return gn_update_impl(samples, (const __half *)samples_split, stencil, uty, weights, nullptr, false, 1, cap, c, h, w, filt, cg_state, cg_iters, n_gn, reg, precond,
                         forget, gate_count, min_px, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
-extern "C" int frtm_gn_update_batched(const void *table, int n_obj, int cap, int c, int h, int w, const int *cg_iters, int n_gn,
-                                      float reg, float precond, float forget, int min_px, float *workspace,
-                                      int64_t workspace_bytes, void *stream) {
+extern "C" int frtm_gn_update_batched(const void *table, int n_obj, int has_split, int cap, int c, int h, int w,
+                                      const int *cg_iters, int n_gn, float reg, float precond, float forget, int min_px,
+                                      float *workspace, int64_t workspace_bytes, void *stream) {
   FRTM_REQUIRE(table && n_obj >= 1, "gn_update_batched: null table");
-  return gn_update_impl(nullptr, nullptr, nullptr, nullptr, reinterpret_cast<const long long *>(table), n_obj, cap, c, h, w,
+  return gn_update_impl(nullptr, nullptr, nullptr, nullptr, nullptr, reinterpret_cast<const long long *>(table), has_split != 0, n_obj, cap, c, h, w,
                         nullptr, nullptr, cg_iters, n_gn, reg, precond, forget, nullptr, min_px, workspace, workspace_bytes,
                         (cudaStream_t)stream);
 }

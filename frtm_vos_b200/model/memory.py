@@ -25,6 +25,11 @@ class Memory:
         h, w = feature_size[-2:]
         self.stencil = torch.zeros(capacity, 9, h, w, device=device)
         self.uty = torch.zeros(capacity, h, w, device=device)
+        # split tile images of ``samples`` for the tensor-core operator kernel (include/frtm_b200.h: frtm_split_samples)
+        c = feature_size[0]
+        self._split_ok = c % 8 == 0
+        nb = lib().split_sample_bytes(c, h * w) if self._split_ok else 16
+        self.split = torch.zeros(capacity, nb // 2, dtype=torch.float16, device=device)
         # {current_size, previous_replace_ind (-1 = None), slot of the last insert (-1 = skipped), inserts}
         self.state = torch.empty(4, dtype=torch.int32, device=device)
         ops.fill_small(idst=self.state, ivals=(0, -1, -1, 0))          # asynchronous: no pageable H2D copy
@@ -45,6 +50,14 @@ class Memory:
         v = int(self.state[1].item())
         return None if v < 0 else v
 
+    def refresh_split(self, first=0, count=None):
+        """Rebuild the split tile images of slots [first, first+count) from ``samples`` (after a direct write)."""
+        if not self._split_ok:
+            return
+        count = self._capacity - first if count is None else count
+        c, h, w = self.samples.shape[1:]
+        lib().split_samples(ptr(self.samples[first:]), int(count), c, h * w, ptr(self.split[first:]), stream())
+
     def initialize(self, init_features, init_labels, pixel_weights, stencil=None, uty=None):
         """First K slots <- the augmented first-frame samples; weights 2/K, 1/K, ... normalised (``:33-46``)."""
         K = init_features.shape[0]
@@ -62,6 +75,7 @@ class Memory:
         self.pixel_weights[:K] = pixel_weights
         self.stencil[:K] = stencil
         self.uty[:K] = uty
+        self.refresh_split(0, K)
 
     def update(self, features, labels, pixel_weights, stencil=None, uty=None, gate_count=None, min_px=10):
         """Insert one sample (``:59-92``).  With ``gate_count`` (int32 device scalar) the insert — including the
@@ -76,4 +90,4 @@ class Memory:
         HW = self.labels.shape[-1] * self.labels.shape[-2]
         L.memory_insert(ptr(features), features.numel(), ptr(labels), ptr(pixel_weights), HW, ptr(stencil), ptr(uty), hw,
                         ptr(self.samples), ptr(self.labels), ptr(self.pixel_weights), ptr(self.stencil), ptr(self.uty),
-                        ptr(self.state), stream())
+                        ptr(self.split) if self._split_ok else None, ptr(self.state), stream())

@@ -130,7 +130,11 @@ class GaussNewtonCG:
             nbytes = L.gn_update_workspace(cap, c, h, w)
             if self._ws is None or self._ws.numel() * 4 < nbytes:
                 self._ws = torch.empty(nbytes // 4, device=mem.samples.device, dtype=torch.float32)
-            L.gn_update(ptr(mem.samples), ptr(mem.stencil), ptr(mem.uty), ptr(mem.weights), cap, c, h, w, ptr(self.x[0]),
+            # The single-object entry point is the API-fidelity path (tests, smoke): callers may have written
+            # ``memory.samples`` directly, so the split tile image is rebuilt here; the tracker's batched path relies on
+            # the image maintained by ``Memory.update`` / ``Memory.initialize``.
+            mem.refresh_split()
+            L.gn_update(ptr(mem.samples), ptr(mem.split), ptr(mem.stencil), ptr(mem.uty), ptr(mem.weights), cap, c, h, w, ptr(self.x[0]),
                         ptr(self.cg_state), iters, len(num_cg_iter), pr.filter_regs[-1], pr.diag_M[-1],
                         self.direction_forget_factor, ptr(gate_count), int(min_px), ptr(self._ws), nbytes, stream())
         return [], [], None

@@ -371,15 +371,16 @@ class Tracker(nn.Module):
         from .._lib import lib, ptr, stream
         key = tuple((live[k].object_id, live[k].discriminator.filter.weight.data_ptr()) for k in due)
         if getattr(self, "_gn_table", None) is None or self._gn_table[0] != key:
-            rows = [[], [], [], [], [], [], []]
+            rows = [[], [], [], [], [], [], [], []]
             for k in due:
                 d = live[k].discriminator
                 m = d.memory
                 for r, v in zip(rows, (m.samples, m.stencil, m.uty, m.weights, d.filter.weight, d.update_optimizer.cg_state)):
                     r.append(v.data_ptr())
                 rows[6].append(self._counts.data_ptr() + 4 * k)
+                rows[7].append(m.split.data_ptr())
             flat = [v for r in rows for v in r]
-            table = torch.empty((7, len(due)), dtype=torch.int64, device=self._counts.device)
+            table = torch.empty((8, len(due)), dtype=torch.int64, device=self._counts.device)
             lib().fill_i64(ptr(table), (ctypes.c_int64 * len(flat))(*flat), len(flat), stream())   # no synchronising H2D
             d0 = live[due[0]].discriminator
             cap, c, h, w = d0.memory.samples.shape
@@ -391,5 +392,5 @@ class Tracker(nn.Module):
         cap, c, h, w = d0.memory.samples.shape
         iters = [int(v) for v in d0.update_iters]
         arr = (ctypes.c_int * len(iters))(*iters)
-        lib().gn_update_batched(ptr(table), len(due), cap, c, h, w, arr, len(iters), float(d0.filter_reg[-1]),
+        lib().gn_update_batched(ptr(table), len(due), 1, cap, c, h, w, arr, len(iters), float(d0.filter_reg[-1]),
                                 float(d0.precond[-1]), float(d0.direction_forget_factor), int(d0.min_px), ptr(ws), nbytes, stream())

@@ -179,31 +179,45 @@ int frtm_build_stencil(const float *pw, const float *y, int K, int H, int W, int
  * state = int[4]: {current_size, previous_replace_ind (-1 = none), last_slot (out, -1 if skipped), num_inserts}. */
 int frtm_memory_next_slot(float *weights, int capacity, float lr, int *state, const int *gate_count, int min_px,
                           void *stream);
-/* Copy one sample into slot state[2] of the frame memory (skipped when state[2] < 0) (memory.py:48-57). */
+/* Copy one sample into slot state[2] of the frame memory (skipped when state[2] < 0) (memory.py:48-57).
+ * mem_split (optional): the memory's split tile images (frtm_split_samples layout), kept in step with mem_samples. */
 int frtm_memory_insert(const float *feat, int feat_elems, const float *label, const float *pw, int HW,
                        const float *stencil, const float *uty, int hw, float *mem_samples, float *mem_labels,
-                       float *mem_pw, float *mem_stencil, float *mem_uty, const int *state, void *stream);
+                       float *mem_pw, float *mem_stencil, float *mem_uty, void *mem_split, const int *state,
+                       void *stream);
+
+/* Split tile image of n memory samples (n,c,hw) fp32 for the tensor-core GN/CG operator kernel: per sample
+ * [ntiles][hi|lo][c][64 pixels] fp16 with 16*x = hi + lo, rows in the 128-byte swizzled shared-memory layout, pixels
+ * beyond hw zero; ntiles = hw/64 rounded up to an even count.  Same bytes per element as the fp32 sample.
+ * frtm_split_sample_bytes = bytes of one sample's image.  c % 8 == 0. */
+int frtm_split_samples(const float *samples, int n, int c, int hw, void *split, void *stream);
+int64_t frtm_split_sample_bytes(int c, int hw);
 
 /* Filter-only Gauss-Newton / Polak-Ribiere CG update in closed (stencil) form — replaces
  * GaussNewtonCG.run on the update problem (optimizer.py:55-157, discriminator.py:38-64,221-227):
  *   residual  r = W (U (X * f) - y),  A p = X^T (U^T W^2 U) X p + reg^2 p,  b = -(X^T U^T W^2 (U X f - y) + reg^2 f)
  * samples (cap,c,h,w), stencil (cap,9,h,w), uty (cap,h,w), weights (cap) [inactive = 0];
+ * samples_split (optional, NULL = absent): the split tile images of `samples` (frtm_split_samples); when given (and
+ * c % 16 == 0, c <= 128) both contractions of the operator run on the tensor cores, otherwise on CUDA cores;
  * filt (c*9) updated in place;  cg_state = float[2*c*9 + 4]: p | r_prev | rho | has_p — persists across calls
  * (zero-initialised by the caller);  cg_iters_host[n_gn] CG iterations per GN iteration (host array);
  * the update is applied only if gate_count == NULL or gate_count[0] >= min_px (device-side predicate, replaces the
  * host sync of discriminator.py:214).  workspace from frtm_gn_update_workspace.  No host synchronisation. */
-int frtm_gn_update(const float *samples, const float *stencil, const float *uty, const float *weights, int cap, int c,
-                   int h, int w, float *filt, float *cg_state, const int *cg_iters_host, int n_gn, float reg,
-                   float precond, float forget, const int *gate_count, int min_px, float *workspace,
-                   int64_t workspace_bytes, void *stream);
+int frtm_gn_update(const float *samples, const void *samples_split, const float *stencil, const float *uty,
+                   const float *weights, int cap, int c, int h, int w, float *filt, float *cg_state,
+                   const int *cg_iters_host, int n_gn, float reg, float precond, float forget, const int *gate_count,
+                   int min_px, float *workspace, int64_t workspace_bytes, void *stream);
 int64_t frtm_gn_update_workspace(int cap, int c, int h, int w);
 /* The same update for n_obj objects in ONE set of launches (grid.y = object; the objects of a sequence update on the
- * same frames).  table: device int64[7][n_obj] of device pointers, rows = {samples, stencil, uty, weights, filt,
- * cg_state, gate_count (0 = ungated)}; all objects share cap, c, h, w and the schedule.  workspace >= n_obj times
- * frtm_gn_update_workspace. */
-int frtm_gn_update_batched(const void *table, int n_obj, int cap, int c, int h, int w, const int *cg_iters_host, int n_gn,
-                           float reg, float precond, float forget, int min_px, float *workspace, int64_t workspace_bytes,
-                           void *stream);
+ * same frames).  table: device int64[8][n_obj] of device pointers, rows = {samples, stencil, uty, weights, filt,
+ * cg_state, gate_count (0 = ungated), samples_split (read only if has_split != 0)}; all objects share cap, c, h, w and
+ * the schedule.  workspace >= n_obj times frtm_gn_update_workspace. */
+int frtm_gn_update_batched(const void *table, int n_obj, int has_split, int cap, int c, int h, int w,
+                           const int *cg_iters_host, int n_gn, float reg, float precond, float forget, int min_px,
+                           float *workspace, int64_t workspace_bytes, void *stream);
+/* Tests only: when buf != NULL the right-hand-side launches of the tensor-core operator dump the padded score and v
+ * maps of the first sample of the first object, 2*(h+2)*(w+2) floats, into buf. */
+int frtm_gn_debug_dump(float *buf);
 
 /* Joint (project, filter) Gauss-Newton / CG of Discriminator.init (discriminator.py:154-175; optimizer.py:55-157):
  *   s = F * (P x),  J[dP,dF] = F * (dP x) + dF * (P x)  on the low-resolution grid, normal equations through the

@@ -169,6 +169,7 @@ def test_P4_end_to_end_oracle_replay():
             m.weights.copy_(st["weights"])
             sten, uty = ops.build_stencil(m.pixel_weights[:5], m.labels[:5], m.samples.shape[-2:])
             m.stencil[:5] = sten; m.uty[:5] = uty
+            m.refresh_split()
             d.update_optimizer.set_state(st["p"].to(DEV), st["r_prev"].to(DEV), float(st["rho"]))
         trk._stack = None
         return r

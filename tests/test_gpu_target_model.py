@@ -79,6 +79,71 @@ def test_update_phase_matches_reference_golden(golden):
     assert np.abs(filt.cpu().numpy() - g["F2"]).max() < 1e-5 * max(np.abs(g["F2"]).max(), 1.0)
 
 
+@pytest.mark.parametrize("cap,M,c,h,w", [(16, 12, 96, 4, 7), (6, 5, 96, 30, 54), (4, 4, 64, 9, 13), (3, 3, 112, 17, 8)])
+def test_tensor_core_operator_matches_cuda_core_operator(cap, M, c, h, w):
+    """The tcgen05 operator kernel (split tile images) against the CUDA-core kernel (fp32 samples) through the C ABI:
+    same filter after RHS + 5 CG iterations, and the phase-1 score map against a float64 conv2d."""
+    from frtm_vos_b200._lib import lib, ptr, stream
+    g = torch.Generator().manual_seed(c + h)
+    X = torch.zeros(cap, c, h, w)
+    X[:M] = torch.randn(M, c, h, w, generator=g) * 0.5
+    S = (torch.rand(cap, 9, h, w, generator=g) * 4.0).to(DEV)
+    T = torch.randn(cap, h, w, generator=g).to(DEV)
+    sw = torch.zeros(cap)
+    sw[:M] = torch.rand(M, generator=g) + 0.1
+    sw = (sw / sw.sum()).to(DEV)
+    f0 = torch.randn(c * 9, generator=g) * 0.05
+    Xd = X.to(DEV)
+    L = lib()
+    nb = L.split_sample_bytes(c, h * w)
+    assert nb == -(-h * w // 128) * 2 * 2 * c * 64 * 2
+    XS = torch.zeros(cap, nb // 2, dtype=torch.float16, device=DEV)
+    L.split_samples(ptr(Xd), cap, c, h * w, ptr(XS), stream())
+    nbytes = L.gn_update_workspace(cap, c, h, w)
+    ws = torch.empty(nbytes // 4, device=DEV)
+    arr = (ctypes.c_int * 1)(5)
+    npad = (h + 2) * (w + 2)
+    dbg = torch.zeros(2 * npad, device=DEV)
+    res = {}
+    for name, split in (("cuda_core", None), ("tensor_core", XS)):
+        filt = f0.clone().to(DEV)
+        st = torch.zeros(2 * c * 9 + 4, device=DEV)
+        L.gn_debug_dump(ptr(dbg) if split is not None else None)
+        try:
+            L.gn_update(ptr(Xd), ptr(split), ptr(S), ptr(T), ptr(sw), cap, c, h, w, ptr(filt), ptr(st), arr, 1, 1e-2, 1e-2,
+                        0.9 ** 750, None, 10, ptr(ws), nbytes, stream())
+            torch.cuda.synchronize()
+        finally:
+            L.gn_debug_dump(None)
+        res[name] = filt.cpu()
+    ref = F.conv2d(X[0:1].double(), f0.double().view(1, c, 3, 3), padding=1)[0, 0].float()
+    sp = dbg[:npad].view(h + 2, w + 2)[1:-1, 1:-1].cpu()
+    assert (sp - ref).abs().max() < 4e-6 * max(ref.abs().max().item(), 1.0)
+    step = (res["cuda_core"] - f0).abs().max().item()
+    assert step > 1e-3                                         # the update did something
+    assert (res["tensor_core"] - res["cuda_core"]).abs().max() < 2e-6 * max(res["cuda_core"].abs().max().item(), 1.0)
+
+
+def test_memory_keeps_split_image_in_step():
+    """Memory.update (device-side slot choice) writes the split tile image of the inserted sample."""
+    from frtm_vos_b200.model.memory import Memory
+    from frtm_vos_b200._lib import lib, ptr, stream
+    g = torch.Generator().manual_seed(11)
+    c, h, w, H, W = 96, 4, 7, 64, 112
+    mem = Memory(6, (c, h, w), (1, H, W), DEV, 0.1)
+    feats = torch.randn(5, c, h, w, generator=g).to(DEV)
+    labels = (torch.rand(5, 1, H, W, generator=g) > 0.5).to(DEV)
+    pw = (0.5 + torch.rand(5, 1, H, W, generator=g)).to(DEV)
+    mem.initialize(feats, labels, pw)
+    for k in range(3):
+        f = torch.randn(1, c, h, w, generator=g).to(DEV)
+        mem.update(f, torch.rand(1, 1, H, W, generator=g).to(DEV), (0.5 + torch.rand(1, 1, H, W, generator=g)).to(DEV))
+    want = torch.zeros_like(mem.split)
+    lib().split_samples(ptr(mem.samples), 6, c, h * w, ptr(want), stream())
+    assert torch.equal(want, mem.split)
+    assert mem.split.abs().sum() > 0
+
+
 def test_update_gate_skips_on_device():
     from frtm_vos_b200.model.discriminator import DiscriminatorLoss
     from frtm_vos_b200.model.optimizer import GaussNewtonCG
