@@ -703,7 +703,7 @@ struct InsertArgs {
   float *dst[5];
   int64_t n[5];
   int64_t total;
-  __half *split;          // [cap][gc_sample_halves] or null
+  uint8_t *split;         // [cap][gc_sample_bytes] operator images or null
   int c, hw;
   int64_t split_items;
 };
@@ -713,7 +713,8 @@ __global__ void memory_insert_kernel(const InsertArgs a, const int *__restrict__
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.total) {
     i -= a.total;
-    if (i < a.split_items) gc_split_item(a.src[0], a.split + (int64_t)slot * gc_sample_halves(a.c, a.hw), a.c, a.hw, i);
+    if (i < a.split_items)
+      gc_image_item(a.src[0], a.src[3], a.src[4], a.split + (int64_t)slot * gc_sample_bytes(a.c, a.hw), a.c, a.hw, i);
     return;
   }
 #pragma unroll
@@ -1055,11 +1056,12 @@ extern "C" int frtm_memory_insert(const float *feat, int feat_elems, const float
     a.src[k] = src[k]; a.dst[k] = dst[k]; a.n[k] = on ? n[k] : 0;
     a.total += a.n[k];
   }
-  a.split = (__half *)mem_split; a.c = 0; a.hw = hw; a.split_items = 0;
+  a.split = (uint8_t *)mem_split; a.c = 0; a.hw = hw; a.split_items = 0;
   if (mem_split) {
-    FRTM_REQUIRE(hw > 0 && feat_elems % hw == 0 && (feat_elems / hw) % 8 == 0, "memory_insert: split image needs c %% 8 == 0");
+    FRTM_REQUIRE(hw > 0 && feat_elems % hw == 0 && (feat_elems / hw) % 8 == 0, "memory_insert: operator image needs c %% 8 == 0");
+    FRTM_REQUIRE(stencil && uty, "memory_insert: operator image needs the sample's stencil and uty");
     a.c = feat_elems / hw;
-    a.split_items = (int64_t)gc_ntiles(hw) * a.c * 8;
+    a.split_items = gc_sample_items(a.c, hw);
   }
   memory_insert_kernel<<<cdiv(a.total + a.split_items, 256), 256, 0, (cudaStream_t)stream>>>(a, state);
   FRTM_CHECK_LAUNCH("memory_insert");

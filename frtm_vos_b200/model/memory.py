@@ -25,7 +25,7 @@ class Memory:
         h, w = feature_size[-2:]
         self.stencil = torch.zeros(capacity, 9, h, w, device=device)
         self.uty = torch.zeros(capacity, h, w, device=device)
-        # split tile images of ``samples`` for the tensor-core operator kernel (include/frtm_b200.h: frtm_split_samples)
+        # operator images (split tile image of the sample + its stencil rows) for the tensor-core operator kernel (include/frtm_b200.h: frtm_split_samples)
         c = feature_size[0]
         self._split_ok = c % 8 == 0
         nb = lib().split_sample_bytes(c, h * w) if self._split_ok else 16
@@ -51,12 +51,14 @@ class Memory:
         return None if v < 0 else v
 
     def refresh_split(self, first=0, count=None):
-        """Rebuild the split tile images of slots [first, first+count) from ``samples`` (after a direct write)."""
+        """Rebuild the operator images of slots [first, first+count) from ``samples`` / ``stencil`` / ``uty`` (after a
+        direct write to any of them)."""
         if not self._split_ok:
             return
         count = self._capacity - first if count is None else count
         c, h, w = self.samples.shape[1:]
-        lib().split_samples(ptr(self.samples[first:]), int(count), c, h * w, ptr(self.split[first:]), stream())
+        lib().split_samples(ptr(self.samples[first:]), ptr(self.stencil[first:]), ptr(self.uty[first:]), int(count), c, h * w,
+                            ptr(self.split[first:]), stream())
 
     def initialize(self, init_features, init_labels, pixel_weights, stencil=None, uty=None):
         """First K slots <- the augmented first-frame samples; weights 2/K, 1/K, ... normalised (``:33-46``)."""

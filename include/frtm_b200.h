@@ -180,25 +180,28 @@ int frtm_build_stencil(const float *pw, const float *y, int K, int H, int W, int
 int frtm_memory_next_slot(float *weights, int capacity, float lr, int *state, const int *gate_count, int min_px,
                           void *stream);
 /* Copy one sample into slot state[2] of the frame memory (skipped when state[2] < 0) (memory.py:48-57).
- * mem_split (optional): the memory's split tile images (frtm_split_samples layout), kept in step with mem_samples. */
+ * mem_split (optional): the memory's operator images (frtm_split_samples layout), kept in step with the sample. */
 int frtm_memory_insert(const float *feat, int feat_elems, const float *label, const float *pw, int HW,
                        const float *stencil, const float *uty, int hw, float *mem_samples, float *mem_labels,
                        float *mem_pw, float *mem_stencil, float *mem_uty, void *mem_split, const int *state,
                        void *stream);
 
-/* Split tile image of n memory samples (n,c,hw) fp32 for the tensor-core GN/CG operator kernel: per sample
- * [ntiles][hi|lo][c][64 pixels] fp16 with 16*x = hi + lo, rows in the 128-byte swizzled shared-memory layout, pixels
- * beyond hw zero; ntiles = hw/64 rounded up to an even count.  Same bytes per element as the fp32 sample.
- * frtm_split_sample_bytes = bytes of one sample's image.  c % 8 == 0. */
-int frtm_split_samples(const float *samples, int n, int c, int hw, void *split, void *stream);
+/* Operator images of n memory samples for the tensor-core GN/CG operator kernel.  Per sample:
+ *   [ntiles][hi|lo][c][64 pixels] fp16 with 16*x = hi + lo, rows in the 128-byte swizzled shared-memory layout, pixels
+ *   beyond hw zero, ntiles = hw/64 rounded up to an even count;  then  [ceil(hw/256)][10][256] fp32: the 9 stencil taps
+ *   and U^T w^2 y of 256 consecutive pixels.  Same bytes per element as the fp32 arrays it mirrors.
+ * samples (n,c,hw), stencil (n,9,hw), uty (n,hw);  frtm_split_sample_bytes = bytes of one image.  c % 8 == 0. */
+int frtm_split_samples(const float *samples, const float *stencil, const float *uty, int n, int c, int hw, void *split,
+                       void *stream);
 int64_t frtm_split_sample_bytes(int c, int hw);
 
 /* Filter-only Gauss-Newton / Polak-Ribiere CG update in closed (stencil) form — replaces
  * GaussNewtonCG.run on the update problem (optimizer.py:55-157, discriminator.py:38-64,221-227):
  *   residual  r = W (U (X * f) - y),  A p = X^T (U^T W^2 U) X p + reg^2 p,  b = -(X^T U^T W^2 (U X f - y) + reg^2 f)
  * samples (cap,c,h,w), stencil (cap,9,h,w), uty (cap,h,w), weights (cap) [inactive = 0];
- * samples_split (optional, NULL = absent): the split tile images of `samples` (frtm_split_samples); when given (and
- * c % 16 == 0, c <= 128) both contractions of the operator run on the tensor cores, otherwise on CUDA cores;
+ * samples_split (optional, NULL = absent): the operator images of the samples (frtm_split_samples); when given (and
+ * c % 16 == 0, 48 <= c <= 128) the operator streams only the images and both contractions run on the tensor cores,
+ * otherwise on CUDA cores;
  * filt (c*9) updated in place;  cg_state = float[2*c*9 + 4]: p | r_prev | rho | has_p — persists across calls
  * (zero-initialised by the caller);  cg_iters_host[n_gn] CG iterations per GN iteration (host array);
  * the update is applied only if gate_count == NULL or gate_count[0] >= min_px (device-side predicate, replaces the

@@ -28,7 +28,7 @@ def run(cap, M, c, h, w, iters, seed=0, time_it=False):
     L = lib()
     nb = L.split_sample_bytes(c, h * w)
     XS = torch.zeros(cap, nb // 2, dtype=torch.float16, device=DEV)
-    L.split_samples(ptr(X), cap, c, h * w, ptr(XS), stream())
+    L.split_samples(ptr(X), ptr(S), ptr(T), cap, c, h * w, ptr(XS), stream())
     nbytes = L.gn_update_workspace(cap, c, h, w)
     ws = torch.empty(nbytes // 4, device=DEV)
     arr = (ctypes.c_int * 1)(iters)
