@@ -32,12 +32,14 @@ namespace frtm {
 constexpr int GC_SLOTS = 3;                // ring slots (one tile each)
 constexpr int GC_FOLD = 4;                 // tiles accumulated inside the tensor core between fp32 register folds
 constexpr int GC_VSTEP = 2;                // tiles per v-operand slot
-constexpr int GC_PGROUP = 4;               // tile pairs per phase-1 accumulator slot
+constexpr int GC_PGROUP = 2;               // tile pairs per phase-1 accumulator slot
 constexpr int GC_THREADS = 192;
 constexpr int GC_VTILE_BYTES = 4096;       // [hi|lo][16 rows][64] fp16
 constexpr int GC_VSLOT_BYTES = GC_VSTEP * GC_VTILE_BYTES;
 constexpr int GC_NBARS = 2 * GC_SLOTS + 12;
-constexpr int GC_TMEM_COLS = 128;
+constexpr int GC_P1_COLS = 48;             // phase 1: one 16-column accumulator per pass (hi*hi, hi*lo, lo*hi) of a pair
+constexpr int GC_P3_COLS = 48;             // phase 3: A_hi x [B_hi|B_lo] (32 columns) and A_lo x B_hi (16) of one tile parity
+constexpr int GC_TMEM_COLS = 256;          // 2 slots x max(GC_PGROUP * GC_P1_COLS, GC_VSTEP * GC_P3_COLS) = 192
 
 // SW128 shared-memory matrix descriptor with explicit leading/stride byte offsets (MN-major operands use both)
 __device__ __forceinline__ uint64_t umma_desc_ls(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -65,6 +67,21 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void drain_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
+// Timeline tracing (debug builds only, -DGC_TRACE): CTA (0,0) of an RHS launch stamps globaltimer values into a.dbg
+// (as 64-bit words after the 2*npad floats of the map dump): slot k of role r at dbg64[r * 64 + k].
+#ifdef GC_TRACE
+#define GC_STAMP(role, k)                                                                                        \
+  do {                                                                                                           \
+    if (a.dbg != nullptr && use_y && blockIdx.x == 0 && blockIdx.y == 0 && (k) < 64) {                           \
+      unsigned long long t__;                                                                                    \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                                                    \
+      reinterpret_cast<unsigned long long *>(a.dbg + 2 * npad + 2)[(role) * 64 + (k)] = t__;                     \
+    }                                                                                                            \
+  } while (0)
+#else
+#define GC_STAMP(role, k) do { } while (0)
+#endif
+
 struct GcParams {
   int ntiles, nchunks, tile_bytes;
   int64_t image_bytes;
@@ -74,8 +91,10 @@ __global__ void __launch_bounds__(GC_THREADS, 2) gn_apply_tc_kernel(const GaArgs
   const int c = a.c, h = a.h, w = a.w, use_y = a.use_y;
   const int n = c * 9;
   const int hw = h * w, wp = w + 2, npad = (h + 2) * wp;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = uniform_warp_idx();
   const int ntiles = P.ntiles, nchunks = P.nchunks, tile_bytes = P.tile_bytes;
+  const int cps = tile_bytes >= 2 * GC_CHUNK_BYTES ? 2 : 1;      // stencil chunks per ring slot
+  const int ncl = (nchunks + cps - 1) / cps;                      // stencil loads
   const int plane_bytes = tile_bytes >> 1;
   const int npairs = ntiles >> 1;
   const int i = blockIdx.x;
@@ -90,6 +109,7 @@ __global__ void __launch_bounds__(GC_THREADS, 2) gn_apply_tc_kernel(const GaArgs
     xs = reinterpret_cast<const __half *>(a.table[7 * a.n_obj + o]);
     part += (int64_t)o * a.cap * n;
   }
+  GC_STAMP(0, 0);
   const float wgt = sw[i];
   if (wgt == 0.f) {
     for (int k = tid; k < n; k += GC_THREADS) part[k] = 0.f;
@@ -165,31 +185,43 @@ __global__ void __launch_bounds__(GC_THREADS, 2) gn_apply_tc_kernel(const GaArgs
   }
   fence_async_smem();
   tc_fence_before();
-  __syncthreads();
+  // the producer only needs the barriers (first __syncthreads above): it signals its share of the setup and starts
+  // streaming while the other warps finish the p operand
+  if (warp == 0) asm volatile("bar.arrive 2, %0;" ::"n"(GC_THREADS) : "memory");
+  else asm volatile("bar.sync 2, %0;" ::"n"(GC_THREADS) : "memory");
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) GC_STAMP(0, 1);
 
   if (warp == 0) {
     // ===== producer: ntiles tiles, nchunks stencil chunks, ntiles tiles again =====
-    if (lane == 0) {
+    {
       const uint8_t *st = img + (int64_t)ntiles * tile_bytes;
-      for (int it = 0; it < 2 * ntiles + nchunks; ++it) {
+      for (int it = 0; it < 2 * ntiles + ncl; ++it) {
         const int s = it % GC_SLOTS;
         mbar_wait(bar_empty + 8 * s, ((it / GC_SLOTS) & 1) ^ 1);
         const uint8_t *src;
         uint32_t bytes = tile_bytes;
         if (it < ntiles) src = img + (int64_t)it * tile_bytes;
-        else if (it < ntiles + nchunks) { src = st + (int64_t)(it - ntiles) * GC_CHUNK_BYTES; bytes = GC_CHUNK_BYTES; }
-        else src = img + (int64_t)(ntiles - 1 - (it - ntiles - nchunks)) * tile_bytes;   // second pass: last tile first
-        mbar_expect_tx(bar_full + 8 * s, bytes);
-        bulk_load(ring + s * tile_bytes, src, bytes, bar_full + 8 * s);
+        else if (it < ntiles + ncl) {
+          const int m0 = (it - ntiles) * cps;
+          src = st + (int64_t)m0 * GC_CHUNK_BYTES;
+          bytes = (uint32_t)min(cps, nchunks - m0) * GC_CHUNK_BYTES;
+        } else src = img + (int64_t)(ntiles - 1 - (it - ntiles - ncl)) * tile_bytes;     // second pass: last tile first
+        if (elect_one()) {
+          mbar_expect_tx(bar_full + 8 * s, bytes);
+          bulk_load(ring + s * tile_bytes, src, bytes, bar_full + 8 * s);
+          GC_STAMP(1, it);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp walks the schedule, one elected lane issues =====
+    {
       constexpr uint32_t idesc16 = umma_idesc(128, 16), idesc32 = umma_idesc(128, 32);
       constexpr uint32_t idesc1 = idesc16 | (1u << 15);        // A is MN-major (pixels contiguous, K = channel rows)
+      constexpr uint32_t idesc1_32 = idesc32 | (1u << 15);
       // phase 1: one M = 128 (two tiles) x N = 16 x K = c product per tile pair, GC_PGROUP pairs per accumulator slot
       for (int tp = 0; tp < npairs; ++tp) {
         const int it0 = 2 * tp, it1 = it0 + 1;
@@ -199,46 +231,79 @@ __global__ void __launch_bounds__(GC_THREADS, 2) gn_apply_tc_kernel(const GaArgs
         mbar_wait(bar_full + 8 * s0, (it0 / GC_SLOTS) & 1);
         mbar_wait(bar_full + 8 * s1, (it1 / GC_SLOTS) & 1);
         tc_fence_after();
+        if (lane == 0) GC_STAMP(2, tp);
         const int slo = min(s0, s1), shi = max(s0, s1);       // TMEM lanes 0-63 <- the tile in the lower slot
         const uint32_t lbo = (uint32_t)(shi - slo) * tile_bytes;
         const uint32_t a0 = ring + slo * tile_bytes;
-        const uint32_t tacc = tmem_base + as * (16 * GC_PGROUP) + sub * 16;
+        // An MMA of this shape costs ~90 cycles whatever N is (measured), so the passes are packed: A_hi x [p_hi | p_lo] as
+        // one N = 32 product, A_lo x p_hi as a second one, into separate accumulator columns.
+        const uint32_t tacc = tmem_base + as * (GC_P1_COLS * GC_PGROUP) + sub * GC_P1_COLS;
         for (int ks = 0; ks < c / 16; ++ks) {
           const uint64_t a_hi = umma_desc_ls(a0 + ks * 2048, lbo, 1024);
           const uint64_t a_lo = umma_desc_ls(a0 + plane_bytes + ks * 2048, lbo, 1024);
           const uint32_t bb = obuf + (ks >> 2) * GC_VTILE_BYTES + (ks & 3) * 32;
-          const uint64_t b_hi = umma_desc_ls(bb, 0, 1024), b_lo = umma_desc_ls(bb + 2048, 0, 1024);
-          umma_f16(tacc, a_hi, b_hi, idesc1, ks > 0 ? 1u : 0u);
-          umma_f16(tacc, a_hi, b_lo, idesc1, 1u);
-          umma_f16(tacc, a_lo, b_hi, idesc1, 1u);
+          const uint64_t b_hl = umma_desc_ls(bb, 0, 1024);                   // rows 0-15 p_hi taps, rows 16-31 p_lo taps
+          if (elect_one()) {
+            umma_f16(tacc, a_hi, b_hl, idesc1_32, ks > 0 ? 1u : 0u);      // N = 32: hi*hi | hi*lo
+            umma_f16(tacc + 32, a_lo, b_hl, idesc1, ks > 0 ? 1u : 0u);           // N = 16: lo*hi
+          }
         }
-        umma_commit(bar_empty + 8 * s0);
-        umma_commit(bar_empty + 8 * s1);
-        if (sub == GC_PGROUP - 1 || tp == npairs - 1) umma_commit(bar_accfull + 8 * as);
+        if (elect_one()) {
+          umma_commit(bar_empty + 8 * s0);
+          umma_commit(bar_empty + 8 * s1);
+          if (sub == GC_PGROUP - 1 || tp == npairs - 1) umma_commit(bar_accfull + 8 * as);
+        }
+        __syncwarp();
       }
       // phase 3: per tile  D[0:32) (+)= A_hi x [B_hi | B_lo],  D[0:16) += A_lo x B_hi ;  M = 128 (c channel rows valid),
       // K = 64 pixels per tile, GC_FOLD tiles per accumulator slot, GC_VSTEP tiles per v-operand slot
-      for (int j = 0; j < ntiles; ++j) {
-        const int it = ntiles + nchunks + j, s = it % GC_SLOTS;
-        const int vstep = j / GC_VSTEP, vs = vstep & 1, vsub = j - vstep * GC_VSTEP;
-        const int grp = j / GC_FOLD, fs = grp & 1;
-        const bool first = (j % GC_FOLD) == 0;
+      // The two tiles of a v-operand slot and the two products of a tile go to four independent accumulators and are
+      // issued interleaved, for the same reason as above.
+      const int nvs = (ntiles + GC_VSTEP - 1) / GC_VSTEP;
+      for (int vstep = 0; vstep < nvs; ++vstep) {
+        const int vs = vstep & 1;
+        const int j0 = vstep * GC_VSTEP;
+        const int nt = min(GC_VSTEP, ntiles - j0);
+        const int grp = j0 / GC_FOLD, fs = grp & 1;
+        const bool first = (j0 % GC_FOLD) == 0;
         if (first) mbar_wait(bar_foldfree + 8 * fs, ((grp >> 1) & 1) ^ 1);
-        if (vsub == 0) mbar_wait(bar_vready + 8 * vs, (vstep >> 1) & 1);
-        mbar_wait(bar_full + 8 * s, (it / GC_SLOTS) & 1);
+        mbar_wait(bar_vready + 8 * vs, (vstep >> 1) & 1);
+        uint32_t a0[GC_VSTEP];
+#pragma unroll
+        for (int u = 0; u < GC_VSTEP; ++u) {
+          const int it = ntiles + ncl + j0 + u, s = it % GC_SLOTS;
+          if (u < nt) mbar_wait(bar_full + 8 * s, (it / GC_SLOTS) & 1);
+          a0[u] = ring + s * tile_bytes;
+        }
         tc_fence_after();
-        const uint32_t a0 = ring + s * tile_bytes, b0 = obuf + vs * GC_VSLOT_BYTES + vsub * GC_VTILE_BYTES;
-        const uint32_t tacc = tmem_base + fs * 32;
+        if (lane == 0) GC_STAMP(2, 16 + vstep);
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4) {
-          const uint64_t a_hi = umma_desc_ls(a0 + k4 * 32, 0, 1024), a_lo = umma_desc_ls(a0 + plane_bytes + k4 * 32, 0, 1024);
-          const uint64_t b_hl = umma_desc_ls(b0 + k4 * 32, 0, 1024);          // rows 0-15 hi taps, rows 16-31 lo taps
-          umma_f16(tacc, a_hi, b_hl, idesc32, (first && k4 == 0) ? 0u : 1u);
-          umma_f16(tacc, a_lo, b_hl, idesc16, 1u);
+#pragma unroll
+          for (int u = 0; u < GC_VSTEP; ++u) {
+            if (u < nt) {
+              const uint32_t b0 = obuf + vs * GC_VSLOT_BYTES + u * GC_VTILE_BYTES;
+              const uint32_t tacc = tmem_base + fs * (GC_P3_COLS * GC_VSTEP) + u * GC_P3_COLS;
+              const uint64_t a_hi = umma_desc_ls(a0[u] + k4 * 32, 0, 1024), a_lo = umma_desc_ls(a0[u] + plane_bytes + k4 * 32, 0, 1024);
+              const uint64_t b_hl = umma_desc_ls(b0 + k4 * 32, 0, 1024);        // rows 0-15 hi taps, rows 16-31 lo taps
+              if (elect_one()) {
+                umma_f16(tacc, a_hi, b_hl, idesc32, (first && k4 == 0) ? 0u : 1u);
+                umma_f16(tacc + 32, a_lo, b_hl, idesc16, (first && k4 == 0) ? 0u : 1u);
+              }
+            }
+          }
         }
-        umma_commit(bar_empty + 8 * s);
-        if (vsub == GC_VSTEP - 1 || j == ntiles - 1) umma_commit(bar_vfree + 8 * vs);
-        if ((j % GC_FOLD) == GC_FOLD - 1 || j == ntiles - 1) umma_commit(bar_foldfull + 8 * fs);
+        if (elect_one()) {
+#pragma unroll
+          for (int u = 0; u < GC_VSTEP; ++u) {
+            const int it = ntiles + ncl + j0 + u;
+            if (u < nt) umma_commit(bar_empty + 8 * (it % GC_SLOTS));
+          }
+          umma_commit(bar_vfree + 8 * vs);
+          const int jl = j0 + nt - 1;
+          if ((jl % GC_FOLD) == GC_FOLD - 1 || jl == ntiles - 1) umma_commit(bar_foldfull + 8 * fs);
+        }
+        __syncwarp();
       }
     }
   } else {
@@ -255,10 +320,20 @@ __global__ void __launch_bounds__(GC_THREADS, 2) gn_apply_tc_kernel(const GaArgs
       const int np = min(GC_PGROUP, npairs - grp * GC_PGROUP);
       mbar_wait(bar_accfull + 8 * as, (grp >> 1) & 1);
       tc_fence_after();
+      if (dt == 0) GC_STAMP(3, grp);
       float y[GC_PGROUP][16];
 #pragma unroll
-      for (int u = 0; u < GC_PGROUP; ++u)
-        if (u < np) tmem_ld16(tlane + as * (16 * GC_PGROUP) + u * 16, y[u]);
+      for (int u = 0; u < GC_PGROUP; ++u) {
+        if (u < np) {
+          float y1[16], y2[16];
+          const uint32_t col = tlane + as * (GC_P1_COLS * GC_PGROUP) + u * GC_P1_COLS;
+          tmem_ld16(col, y[u]);
+          tmem_ld16(col + 16, y1);
+          tmem_ld16(col + 32, y2);
+#pragma unroll
+          for (int t = 0; t < 9; ++t) y[u][t] += y1[t] + y2[t];
+        }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_accfree + 8 * as);
@@ -287,11 +362,12 @@ __global__ void __launch_bounds__(GC_THREADS, 2) gn_apply_tc_kernel(const GaArgs
       }
     }
     // ---- phase 2: v = sw (S s - use_y t) from the stencil chunks in the ring, and its maximum ----
+    if (dt == 0) GC_STAMP(3, 15);
     float vmax = 0.f;
     for (int m = 0; m < nchunks; ++m) {
-      const int it = ntiles + m, s = it % GC_SLOTS;
-      mbar_wait(bar_full + 8 * s, (it / GC_SLOTS) & 1);
-      const float *ck = reinterpret_cast<const float *>(gen + (size_t)s * tile_bytes);
+      const int it = ntiles + m / cps, s = it % GC_SLOTS;
+      if (m % cps == 0) mbar_wait(bar_full + 8 * s, (it / GC_SLOTS) & 1);
+      const float *ck = reinterpret_cast<const float *>(gen + (size_t)s * tile_bytes + (size_t)(m % cps) * GC_CHUNK_BYTES);
 #pragma unroll
       for (int u = 0; u < GC_CHUNK_PX / 128; ++u) {
         const int pxl = dt + u * 128;
@@ -307,8 +383,10 @@ __global__ void __launch_bounds__(GC_THREADS, 2) gn_apply_tc_kernel(const GaArgs
           vmax = fmaxf(vmax, fabsf(av));
         }
       }
-      drain_sync();
-      if (dt == 0) mbar_arrive(bar_empty + 8 * s);
+      if (m % cps == cps - 1 || m == nchunks - 1) {
+        drain_sync();
+        if (dt == 0) mbar_arrive(bar_empty + 8 * s);
+      }
     }
     // the operand buffer held p until now (every phase-1 product has completed): clear it for the v operand
     {
@@ -334,19 +412,28 @@ __global__ void __launch_bounds__(GC_THREADS, 2) gn_apply_tc_kernel(const GaArgs
       const int fs = grp & 1;
       mbar_wait(bar_foldfull + 8 * fs, (grp >> 1) & 1);
       tc_fence_after();
-      float f[32];
-      tmem_ld32(tlane + fs * 32, f);
+      float f[GC_VSTEP][32], f2[GC_VSTEP][16];
+#pragma unroll
+      for (int u = 0; u < GC_VSTEP; ++u) {
+        const uint32_t col = tlane + fs * (GC_P3_COLS * GC_VSTEP) + u * GC_P3_COLS;
+        tmem_ld32(col, f[u]);
+        tmem_ld16(col + 32, f2[u]);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_foldfree + 8 * fs);
 #pragma unroll
-      for (int u = 0; u < 16; ++u) gacc[u] += f[u] + f[16 + u];
+      for (int u = 0; u < GC_VSTEP; ++u)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) gacc[t] += f[u][t] + f[u][16 + t] + f2[u][t];
     };
     const int nvsteps = (ntiles + GC_VSTEP - 1) / GC_VSTEP;
     constexpr int STEPS_PER_FOLD = GC_FOLD / GC_VSTEP;
+    if (dt == 0) GC_STAMP(3, 16);
     for (int vstep = 0; vstep < nvsteps; ++vstep) {
       const int vs = vstep & 1;
       mbar_wait(bar_vfree + 8 * vs, ((vstep >> 1) & 1) ^ 1);
+      if (dt == 0) GC_STAMP(3, 17 + vstep);
       if (t16 < 9) {
 #pragma unroll
         for (int u = 0; u < GC_VSTEP; ++u) {
@@ -372,6 +459,7 @@ __global__ void __launch_bounds__(GC_THREADS, 2) gn_apply_tc_kernel(const GaArgs
       if (vstep > 0 && (vstep % STEPS_PER_FOLD) == 0) fold(vstep / STEPS_PER_FOLD - 1);
     }
     fold((ntiles - 1) / GC_FOLD);
+    if (dt == 0) GC_STAMP(3, 40);
     if (dt < c) {
       const float gscale = 1.f / (GC_ACT_SCALE * vscale);
 #pragma unroll

@@ -29,7 +29,7 @@ class Memory:
         c = feature_size[0]
         self._split_ok = c % 8 == 0
         nb = lib().split_sample_bytes(c, h * w) if self._split_ok else 16
-        self.split = torch.zeros(capacity, nb // 2, dtype=torch.float16, device=device)
+        self.split = torch.zeros(capacity, nb, dtype=torch.uint8, device=device)
         # {current_size, previous_replace_ind (-1 = None), slot of the last insert (-1 = skipped), inserts}
         self.state = torch.empty(4, dtype=torch.int32, device=device)
         ops.fill_small(idst=self.state, ivals=(0, -1, -1, 0))          # asynchronous: no pageable H2D copy

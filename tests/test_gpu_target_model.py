@@ -97,7 +97,7 @@ def test_tensor_core_operator_matches_cuda_core_operator(cap, M, c, h, w):
     L = lib()
     nb = L.split_sample_bytes(c, h * w)
     assert nb == -(-h * w // 128) * 2 * 2 * c * 64 * 2 + -(-h * w // 256) * 10 * 256 * 4
-    XS = torch.zeros(cap, nb // 2, dtype=torch.float16, device=DEV)
+    XS = torch.zeros(cap, nb, dtype=torch.uint8, device=DEV)
     L.split_samples(ptr(Xd), ptr(S), ptr(T), cap, c, h * w, ptr(XS), stream())
     nbytes = L.gn_update_workspace(cap, c, h, w)
     ws = torch.empty(nbytes // 4, device=DEV)
@@ -126,7 +126,7 @@ def test_tensor_core_operator_matches_cuda_core_operator(cap, M, c, h, w):
 
 
 def test_memory_keeps_split_image_in_step():
-    """Memory.update (device-side slot choice) writes the split tile image of the inserted sample."""
+    """Memory.update (device-side slot choice) writes the operator image of the inserted sample."""
     from frtm_vos_b200.model.memory import Memory
     from frtm_vos_b200._lib import lib, ptr, stream
     g = torch.Generator().manual_seed(11)
@@ -142,7 +142,7 @@ def test_memory_keeps_split_image_in_step():
     want = torch.zeros_like(mem.split)
     lib().split_samples(ptr(mem.samples), ptr(mem.stencil), ptr(mem.uty), 6, c, h * w, ptr(want), stream())
     assert torch.equal(want, mem.split)
-    assert mem.split.abs().sum() > 0
+    assert int((mem.split != 0).sum()) > 0
 
 
 def test_update_gate_skips_on_device():
