@@ -38,6 +38,8 @@ struct TcArgs {
   float *y;                // fp32 NHWC out (ldy, y_coff) or null
   float *y_nchw;           // or null
   __half *y_hi, *y_lo;     // split out planes (channel stride ldyh, offset yh_coff) or null
+  const float *tapw;       // [9][Cout] weights of a following 3x3 -> 1 conv, contracted per pixel in the epilogue, or null
+  float *y_tap;            // (B,Ho,Wo,12): the 9 tap maps  sum_c tapw[tap][c] * out[c]  (needs Cout <= BN), or null
   int ldr, ldrh, ldy, y_coff, ldyh, yh_coff;
   int B, H, W, Ho, Wo, stride, Cout, kh, kw, pad, relu, tiles_x, tiles_y, kchunks;
 };
@@ -51,7 +53,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
                                                       const __grid_constant__ CUtensorMap tm_lo, const TcArgs a) {
   constexpr int B_BYTES = BN * 128;
   constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
-  constexpr int COLS = tmem_cols(2 * BN);      // two accumulator slots
+  constexpr int COLS = tmem_cols(4 * BN);      // two accumulator slots of 2*BN columns: [hi*hi + lo*hi | hi*lo]
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
@@ -61,7 +63,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
   const uint32_t bar_acce = bar_accf + 16;                     // 2 x 8 B: accumulator slot drained
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gen + STAGES * STAGE_BYTES + 16 * STAGES + 32);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int tiles_per_img = a.tiles_x * a.tiles_y;
   const int b = blockIdx.x / tiles_per_img;
   const int tr = blockIdx.x - b * tiles_per_img;
@@ -93,25 +95,33 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Producer and MMA warps walk their loops converged and issue through one elected lane (elect.sync): control flow and
+  // descriptor arithmetic stay warp-uniform, so the TMA / tcgen05 instructions are issued back to back from uniform
+  // registers instead of through the per-lane serialisation loops an `if (lane == 0)` region compiles to.
   if (warp == 0) {
-    if (lane == 0) {
+    {
       const __half *wbase = a.wt + (size_t)ntile * nkb * (2 * B_BYTES / 2);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(bar_empty + 8 * s, ph ^ 1);
-        mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
         const int tap = kb / a.kchunks, kc = kb - tap * a.kchunks;
         const int ky = tap / a.kw, kx = tap - ky * a.kw;
         const uint32_t sa = base + s * STAGE_BYTES;
-        tma_load_4d(sa, &tm_hi, kc * TC_BK, x0 * a.stride + kx - a.pad, y0 * a.stride + ky - a.pad, b, bar_full + 8 * s);
-        tma_load_4d(sa + TC_A_BYTES, &tm_lo, kc * TC_BK, x0 * a.stride + kx - a.pad, y0 * a.stride + ky - a.pad, b, bar_full + 8 * s);
-        bulk_load(sa + 2 * TC_A_BYTES, wbase + (size_t)kb * (2 * B_BYTES / 2), 2 * B_BYTES, bar_full + 8 * s);
+        if (elect_one()) {
+          mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
+          tma_load_4d(sa, &tm_hi, kc * TC_BK, x0 * a.stride + kx - a.pad, y0 * a.stride + ky - a.pad, b, bar_full + 8 * s);
+          tma_load_4d(sa + TC_A_BYTES, &tm_lo, kc * TC_BK, x0 * a.stride + kx - a.pad, y0 * a.stride + ky - a.pad, b, bar_full + 8 * s);
+          bulk_load(sa + 2 * TC_A_BYTES, wbase + (size_t)kb * (2 * B_BYTES / 2), 2 * B_BYTES, bar_full + 8 * s);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(128, BN);
+    {
+      // per k-step:  D[0:2BN) (+)= A_hi x [B_hi | B_lo]  (one N = 2*BN product: the hi and lo weight rows are contiguous in
+      // the stage) and  D[0:BN) += A_lo x B_hi  — two reads of the A tile per k-step instead of three
+      constexpr uint32_t idesc = umma_idesc(128, BN), idesc2 = umma_idesc(128, 2 * BN);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -123,19 +133,21 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
           mbar_wait(bar_acce + 8 * slot, ((grp >> 1) & 1) ^ 1);
           tc_fence_after();
         }
-        const uint32_t tacc = tmem_base + slot * BN;
+        const uint32_t tacc = tmem_base + slot * (2 * BN);
         const uint32_t sa = base + s * STAGE_BYTES;
         const uint64_t a_hi = umma_desc(sa), a_lo = umma_desc(sa + TC_A_BYTES);
-        const uint64_t b_hi = umma_desc(sa + 2 * TC_A_BYTES), b_lo = umma_desc(sa + 2 * TC_A_BYTES + B_BYTES);
+        const uint64_t b_hl = umma_desc(sa + 2 * TC_A_BYTES);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
-          const uint64_t adv = (uint64_t)(k * 32 >> 4);     // +32 bytes along K inside the swizzle atom
-          umma_f16(tacc, a_hi + adv, b_hi + adv, idesc, (first && k == 0) ? 0u : 1u);
-          umma_f16(tacc, a_hi + adv, b_lo + adv, idesc, 1u);
-          umma_f16(tacc, a_lo + adv, b_hi + adv, idesc, 1u);
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);     // +32 bytes along K inside the swizzle atom
+            umma_f16(tacc, a_hi + adv, b_hl + adv, idesc2, (first && k == 0) ? 0u : 1u);
+            umma_f16(tacc, a_lo + adv, b_hl + adv, idesc, 1u);
+          }
+          umma_commit(bar_empty + 8 * s);     // frees the stage once the MMAs above have consumed it
+          if ((kb % TC_FOLD) == TC_FOLD - 1 || kb == nkb - 1) umma_commit(bar_accf + 8 * slot);   // slot ready to fold
         }
-        umma_commit(bar_empty + 8 * s);     // frees the stage once the MMAs above have consumed it
-        if ((kb % TC_FOLD) == TC_FOLD - 1 || kb == nkb - 1) umma_commit(bar_accf + 8 * slot);   // slot ready to fold
+        __syncwarp();
       }
     }
   } else {
@@ -149,9 +161,16 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
     // per-channel output scale and bias staged once per CTA (overlaps the main loop)
     float *s_osc = reinterpret_cast<float *>(gen + STAGES * STAGE_BYTES + 16 * STAGES + 48);
     float *s_bias = s_osc + BN;
+    float *s_tap = s_bias + BN;             // [9][BN]
     for (int i = threadIdx.x - 64; i < BN; i += 128) {
       s_osc[i] = a.oscale[n0 + i];
       s_bias[i] = (a.bias != nullptr && n0 + i < a.Cout) ? a.bias[n0 + i] : 0.f;
+    }
+    if (a.y_tap != nullptr) {
+      for (int i = threadIdx.x - 64; i < 9 * BN; i += 128) {
+        const int t = i / BN, ch = i - t * BN;
+        s_tap[i] = (n0 + ch < a.Cout) ? a.tapw[t * a.Cout + n0 + ch] : 0.f;
+      }
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
     // fold every finished accumulator slot into fp32 registers (round-to-nearest adds)
@@ -166,10 +185,12 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
       tc_fence_after();
 #pragma unroll
       for (int c0 = 0; c0 < BN; c0 += 16) {
-        float t[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + slot * BN + (uint32_t)c0, t);
+        float t[16], t2[16];
+        const uint32_t col = tmem_base + ((uint32_t)(q * 32) << 16) + slot * (2 * BN) + (uint32_t)c0;
+        tmem_ld16(col, t);
+        tmem_ld16(col + BN, t2);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[c0 + j] += t[j];
+        for (int j = 0; j < 16; ++j) acc[c0 + j] += t[j] + t2[j];
       }
       tc_fence_before();
       __syncwarp();
@@ -181,6 +202,9 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
                        ((reinterpret_cast<uintptr_t>(a.y_lo) & 15) == 0);
     const bool vec_rh = (a.ldrh % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.res_hi) & 15) == 0) &&
                         ((reinterpret_cast<uintptr_t>(a.res_lo) & 15) == 0);
+    float tp[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) tp[t] = 0.f;
 #pragma unroll
     for (int c0 = 0; c0 < BN; c0 += 16) {
       float v[16];
@@ -228,6 +252,12 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
       }
+      if (a.y_tap) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) tp[t] = fmaf(v[j], s_tap[t * BN + c0 + j], tp[t]);
+      }
       if (a.y) {
         float *dst = a.y + pix * a.ldy + a.y_coff + n0 + c0;
         if (full && vec_f32) {
@@ -266,6 +296,12 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
         for (int j = 0; j < 16; ++j)
           if (n0 + c0 + j < a.Cout) a.y_nchw[((int64_t)b * a.Cout + n0 + c0 + j) * hw + p] = v[j];
       }
+    }
+    if (a.y_tap && valid) {
+      float4 *o = reinterpret_cast<float4 *>(a.y_tap + pix * 12);
+      o[0] = make_float4(tp[0], tp[1], tp[2], tp[3]);
+      o[1] = make_float4(tp[4], tp[5], tp[6], tp[7]);
+      o[2] = make_float4(tp[8], 0.f, 0.f, 0.f);
     }
   }
   tc_fence_before();
@@ -447,7 +483,7 @@ static int make_act_map(CUtensorMap *tm, const __half *ptr, int B, int H, int W,
 
 template <int BN, int STAGES>
 static int launch_tc(const CUtensorMap &mh, const CUtensorMap &ml, const TcArgs &a, dim3 grid, cudaStream_t st) {
-  constexpr int smem = STAGES * (2 * TC_A_BYTES + 2 * BN * 128) + 16 * STAGES + 48 + 8 * BN + 1024;
+  constexpr int smem = STAGES * (2 * TC_A_BYTES + 2 * BN * 128) + 16 * STAGES + 48 + 44 * BN + 1024;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -474,9 +510,11 @@ extern "C" int frtm_split_f16(const float *x, int64_t npix, int C, int ldx, void
 extern "C" int frtm_conv2d_tc(const void *x_hi, const void *x_lo, int B, int H, int W, int Cin, int ldx, const void *wt,
                               const float *oscale, int bn_tile, const float *bias, const float *res, int ldr,
                               const void *res_hi, const void *res_lo, int ldrh, float *y, int ldy, int y_coff, float *y_nchw,
-                              void *y_hi, void *y_lo, int ldyh, int yh_coff, int Cout, int kh, int kw, int stride, int relu,
-                              void *stream) {
-  FRTM_REQUIRE(x_hi && x_lo && wt && oscale && (y || y_nchw || y_hi), "conv2d_tc: null pointer");
+                              void *y_hi, void *y_lo, int ldyh, int yh_coff, const float *tapw, float *y_tap, int Cout, int kh,
+                              int kw, int stride, int relu, void *stream) {
+  FRTM_REQUIRE(x_hi && x_lo && wt && oscale && (y || y_nchw || y_hi || y_tap), "conv2d_tc: null pointer");
+  FRTM_REQUIRE(!y_tap || (tapw && Cout <= bn_tile && (reinterpret_cast<uintptr_t>(y_tap) & 15) == 0),
+               "conv2d_tc: the tap-map output needs tapw, a single N tile (Cout <= bn_tile) and a 16-byte aligned buffer");
   FRTM_REQUIRE(Cin % TC_BK == 0 && ldx % 8 == 0, "conv2d_tc: Cin must be a multiple of 64 and ldx of 8 (got %d, %d)", Cin, ldx);
   FRTM_REQUIRE(kh == kw && (kh == 1 || kh == 3), "conv2d_tc: only 1x1 (pad 0) and 3x3 (pad 1) convolutions");
   FRTM_REQUIRE(stride == 1 || stride == 2, "conv2d_tc: stride must be 1 or 2");
@@ -491,6 +529,7 @@ extern "C" int frtm_conv2d_tc(const void *x_hi, const void *x_lo, int B, int H, 
   TcArgs a;
   a.wt = (const __half *)wt; a.oscale = oscale; a.bias = bias; a.res = res; a.res_hi = (const __half *)res_hi;
   a.res_lo = (const __half *)res_lo; a.y = y; a.y_nchw = y_nchw; a.y_hi = (__half *)y_hi; a.y_lo = (__half *)y_lo;
+  a.tapw = tapw; a.y_tap = y_tap;
   a.ldr = ldr; a.ldrh = ldrh; a.ldy = ldy; a.y_coff = y_coff; a.ldyh = ldyh; a.yh_coff = yh_coff;
   a.B = B; a.H = H; a.W = W; a.Cout = Cout; a.kh = kh; a.kw = kw; a.pad = kh / 2; a.relu = relu; a.stride = stride;
   a.Ho = (H + 2 * a.pad - kh) / stride + 1; a.Wo = (W + 2 * a.pad - kw) / stride + 1;

@@ -1,5 +1,6 @@
 // Bandwidth-bound glue kernels of the backbone / refinement network / mask merge (NHWC fp32).
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace frtm {
 
@@ -88,7 +89,8 @@ __constant__ float kCubicE[4] = {-0.10546875f, 0.87890625f, 0.26171875f, -0.0351
 
 // One thread = one 4x4 input window = the 2x2 block of outputs (all four polyphase filters) that share it.
 __global__ void __launch_bounds__(256) pyrup_bicubic_kernel(const float *__restrict__ x, int B, int H, int W, int C,
-                                                            float *__restrict__ y) {
+                                                            float *__restrict__ y, __half *__restrict__ y_hi,
+                                                            __half *__restrict__ y_lo) {
   const int C4 = C / 4, Ho = 2 * H, Wo = 2 * W;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t total = (int64_t)B * (H + 1) * (W + 1) * C4;
@@ -131,7 +133,20 @@ __global__ void __launch_bounds__(256) pyrup_bicubic_kernel(const float *__restr
         }
         acc.x += row.x; acc.y += row.y; acc.z += row.z; acc.w += row.w;
       }
-      *reinterpret_cast<float4 *>(y + (((int64_t)b * Ho + oy) * Wo + ox) * C + c4 * 4) = acc;
+      const int64_t o = (((int64_t)b * Ho + oy) * Wo + ox) * C + c4 * 4;
+      if (y) *reinterpret_cast<float4 *>(y + o) = acc;
+      if (y_hi) {   // split planes of 16*x for the tensor-core conv that follows (conv_tc.cu)
+        const float sc[4] = {acc.x * 16.f, acc.y * 16.f, acc.z * 16.f, acc.w * 16.f};
+        __align__(8) __half hh[4];
+        __align__(8) __half ll[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          hh[j] = __float2half_rn(sc[j]);
+          ll[j] = __float2half_rn(sc[j] - __half2float(hh[j]));
+        }
+        *reinterpret_cast<uint2 *>(y_hi + o) = *reinterpret_cast<const uint2 *>(hh);
+        *reinterpret_cast<uint2 *>(y_lo + o) = *reinterpret_cast<const uint2 *>(ll);
+      }
     }
   }
 }
@@ -397,6 +412,117 @@ __global__ void __launch_bounds__(256) shift_sum9_kernel(const float *__restrict
   out[idx] = acc + (bias ? bias[0] : 0.f);
 }
 
+
+// ---------------------------------------------------------------- fused tail of the upsampler --------------------
+// out[b][Y][X] = bias + sum_tap R_tap[Y+dy][X+dx]  (zero outside the image = the final conv's zero padding), where
+// R_tap = bilinear_(H,W)( pyrup_bicubic( t_tap ) ) and t (B,h,w,12) are the 9 tap maps of the final 3x3 conv contracted at
+// low resolution (seg_network.py:139-145 by linearity).  One block = a 16x64 output tile: the tap maps of the tile
+// (with halo) are staged once, then per tap the bicubic x2 runs separably in shared memory (rows, then columns) and the
+// bilinear + shifted sum accumulate in registers — nothing but t is read and nothing but the logits are written.
+constexpr int FT_TY = 16, FT_TX = 64, FT_UY = 24, FT_UX = 76, FT_NTY = 16, FT_NTX = 42;
+
+__global__ void __launch_bounds__(256) upsample_tapsum_kernel(const float *__restrict__ t12, int B, int h, int w, int H,
+                                                              int W, const float *__restrict__ bias,
+                                                              float *__restrict__ out) {
+  __shared__ float T[9][FT_NTY][FT_NTX + 1];
+  __shared__ float H1[FT_NTY][FT_UX + 1];
+  __shared__ float U[FT_UY][FT_UX + 1];
+  const int Hu = 2 * h, Wu = 2 * w;
+  const float sy = (float)Hu / (float)H, sx = (float)Wu / (float)W;
+  const int b = blockIdx.z, Y0 = blockIdx.y * FT_TY, X0 = blockIdx.x * FT_TX;
+  const int tid = threadIdx.x;
+  // upsampled (pre-resize) rows / columns the tile touches, and the low-resolution window behind them
+  int i0, i1;
+  float lam;
+  bilinear_src(max(Y0 - 1, 0), sy, Hu, i0, i1, lam);
+  const int uy_lo = i0;
+  bilinear_src(min(Y0 + FT_TY, H - 1), sy, Hu, i0, i1, lam);
+  const int nuy = i1 - uy_lo + 1;
+  bilinear_src(max(X0 - 1, 0), sx, Wu, i0, i1, lam);
+  const int ux_lo = i0;
+  bilinear_src(min(X0 + FT_TX, W - 1), sx, Wu, i0, i1, lam);
+  const int nux = i1 - ux_lo + 1;
+  const int ty_lo = ((uy_lo + 1) >> 1) - 2, nty = ((uy_lo + nuy) >> 1) + 1 - ty_lo + 1;
+  const int tx_lo = ((ux_lo + 1) >> 1) - 2, ntx = ((ux_lo + nux) >> 1) + 1 - tx_lo + 1;
+  // (the host checks nuy <= FT_UY, nux <= FT_UX, nty <= FT_NTY, ntx <= FT_NTX for the given sizes)
+  for (int i = tid; i < nty * ntx; i += 256) {
+    const int ry = i / ntx, rx = i - ry * ntx;
+    const int sy_ = min(max(ty_lo + ry, 0), h - 1), sx_ = min(max(tx_lo + rx, 0), w - 1);   // replicate padding
+    const float4 *src = reinterpret_cast<const float4 *>(t12 + (((int64_t)b * h + sy_) * w + sx_) * 12);
+    const float4 a0 = src[0], a1 = src[1], a2 = src[2];
+    T[0][ry][rx] = a0.x; T[1][ry][rx] = a0.y; T[2][ry][rx] = a0.z; T[3][ry][rx] = a0.w;
+    T[4][ry][rx] = a1.x; T[5][ry][rx] = a1.y; T[6][ry][rx] = a1.z; T[7][ry][rx] = a1.w;
+    T[8][ry][rx] = a2.x;
+  }
+  // own output pixels: rows tid/64 + 4k, column tid%64
+  const int lx = tid & 63, ly = tid >> 6;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  __syncthreads();
+  for (int tap = 0; tap < 9; ++tap) {
+    // bicubic x2 along x: H1[ry][ux] = sum_kx wx[kx] T[ry][n - 2 + kx],  upsampled column uxg (cropped index) = 2n + rx - 1
+    for (int i = tid; i < nty * nux; i += 256) {
+      const int ry = i / nux, ux = i - ry * nux;
+      const int uxg = ux_lo + ux + 1;
+      const int n = uxg >> 1, odd = uxg & 1;
+      const float *row = &T[tap][ry][n - 2 - tx_lo];
+      H1[ry][ux] = odd ? (kCubicE[3] * row[0] + kCubicE[2] * row[1]) + (kCubicE[1] * row[2] + kCubicE[0] * row[3])
+                       : (kCubicE[0] * row[0] + kCubicE[1] * row[1]) + (kCubicE[2] * row[2] + kCubicE[3] * row[3]);
+    }
+    __syncthreads();
+    // ... and along y
+    for (int i = tid; i < nuy * nux; i += 256) {
+      const int uy = i / nux, ux = i - uy * nux;
+      const int uyg = uy_lo + uy + 1;
+      const int m = uyg >> 1, odd = uyg & 1;
+      const int r0 = m - 2 - ty_lo;
+      const float v0 = H1[r0][ux], v1 = H1[r0 + 1][ux], v2 = H1[r0 + 2][ux], v3 = H1[r0 + 3][ux];
+      U[uy][ux] = odd ? (kCubicE[3] * v0 + kCubicE[2] * v1) + (kCubicE[1] * v2 + kCubicE[0] * v3)
+                      : (kCubicE[0] * v0 + kCubicE[1] * v1) + (kCubicE[2] * v2 + kCubicE[3] * v3);
+    }
+    __syncthreads();
+    // bilinear to (H, W) at the tap-shifted position, accumulated per output pixel
+    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+    const int Xs = X0 + lx + dx;
+    if (Xs >= 0 && Xs < W && X0 + lx < W) {
+      int x0, x1;
+      float lx_;
+      bilinear_src(Xs, sx, Wu, x0, x1, lx_);
+      x0 -= ux_lo; x1 -= ux_lo;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int Ys = Y0 + ly + 4 * k + dy;
+        if (Ys >= 0 && Ys < H) {
+          int y0, y1;
+          float ly_;
+          bilinear_src(Ys, sy, Hu, y0, y1, ly_);
+          y0 -= uy_lo; y1 -= uy_lo;
+          // ATen's order: (1-ly) * ((1-lx) a + lx b) + ly * ((1-lx) c + lx d)
+          const float top = (1.f - lx_) * U[y0][x0] + lx_ * U[y0][x1];
+          const float bot = (1.f - lx_) * U[y1][x0] + lx_ * U[y1][x1];
+          acc[k] += (1.f - ly_) * top + ly_ * bot;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  const float bv = bias ? bias[0] : 0.f;
+  if (X0 + lx < W) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int Y = Y0 + ly + 4 * k;
+      if (Y < H) out[((int64_t)b * H + Y) * W + X0 + lx] = acc[k] + bv;
+    }
+  }
+}
+
+// host-side check that every tile of the given problem fits the shared-memory windows of upsample_tapsum_kernel
+static bool upsample_tapsum_fits(int h, int w, int H, int W) {
+  const int Hu = 2 * h, Wu = 2 * w;
+  if (Hu < H || Wu < W) return false;
+  const double sy = (double)Hu / H, sx = (double)Wu / W;
+  const int nuy = (int)((FT_TY + 2) * sy) + 3, nux = (int)((FT_TX + 2) * sx) + 3;
+  return nuy <= FT_UY && nux <= FT_UX && nuy / 2 + 5 <= FT_NTY && nux / 2 + 5 <= FT_NTX;
+}
 }  // namespace frtm
 
 using namespace frtm;
@@ -444,10 +570,11 @@ extern "C" int frtm_resize_bilinear_nhwc(const float *x, int B, int H, int W, in
   return FRTM_OK;
 }
 
-extern "C" int frtm_pyrup_bicubic_nhwc(const float *x, int B, int H, int W, int C, float *y, void *stream) {
-  FRTM_REQUIRE(x && y && C % 4 == 0, "pyrup_bicubic: bad arguments");
+extern "C" int frtm_pyrup_bicubic_nhwc(const float *x, int B, int H, int W, int C, float *y, void *y_hi, void *y_lo,
+                                       void *stream) {
+  FRTM_REQUIRE(x && (y || y_hi) && C % 4 == 0 && (!y_hi || y_lo), "pyrup_bicubic: bad arguments");
   const int64_t total = (int64_t)B * (H + 1) * (W + 1) * (C / 4);
-  pyrup_bicubic_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, C, y);
+  pyrup_bicubic_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, C, y, (__half *)y_hi, (__half *)y_lo);
   FRTM_CHECK_LAUNCH("pyrup_bicubic");
   return FRTM_OK;
 }
@@ -537,3 +664,16 @@ extern "C" int frtm_shift_sum9(const float *v12, int B, int H, int W, const floa
   FRTM_CHECK_LAUNCH("shift_sum9");
   return FRTM_OK;
 }
+
+extern "C" int frtm_upsample_tapsum(const float *t12, int B, int h, int w, int H, int W, const float *bias, float *out,
+                                    void *stream) {
+  FRTM_REQUIRE(t12 && out && B > 0, "upsample_tapsum: bad arguments");
+  FRTM_REQUIRE(upsample_tapsum_fits(h, w, H, W), "upsample_tapsum: (%d,%d) -> x2 -> (%d,%d) does not fit the fused tile windows", h,
+               w, H, W);
+  FRTM_REQUIRE(B <= 65535, "upsample_tapsum: batch too large");
+  const dim3 grid(cdiv(W, FT_TX), cdiv(H, FT_TY), B);
+  upsample_tapsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(t12, B, h, w, H, W, bias, out);
+  FRTM_CHECK_LAUNCH("upsample_tapsum");
+  return FRTM_OK;
+}
+extern "C" int64_t frtm_upsample_tapsum_supported(int h, int w, int H, int W) { return upsample_tapsum_fits(h, w, H, W) ? 1 : 0; }

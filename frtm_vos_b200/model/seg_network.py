@@ -196,11 +196,12 @@ class SegNetwork(nn.Module):
                 deeper = ops.resize_bilinear(x, (h, w))
                 t = ops.cab(t, sp, dp, deeper, W["cab_w1"], W["cab_b1"], W["cab_w2"], W["cab_b2"])
             x = self._rrb(ops.split_f16(t), W, "rrb2")
-        u = ops.pyrup_bicubic(x)
-        u = ops.conv2d_tc(ops.split_f16(u), P["up1"], relu=True)["y"]
-        # conv2 is linear and so is the bicubic/bilinear chain in front of it: contract the 32 channels to the 9 tap maps
-        # at 240x428 first, upsample those, then add the 9 shifted maps (identical result, 3.5x fewer full-res bytes)
-        return ops.conv3x3_to1_upsampled(u, P["up2_w"], P["up2_b"], image_size[-2:])
+        # conv2 is linear and so is the bicubic/bilinear chain in front of it: the 32 channels are contracted to the 9 tap
+        # maps of conv2 at 240x428 in conv1's epilogue (the 32-channel tensor is never written); one kernel then does
+        # bicubic x2 -> bilinear -> sum of the 9 shifted maps.  The x2 in front of conv1 writes conv1's input planes directly.
+        u = ops.pyrup_bicubic(x, split=True)
+        t12 = ops.conv2d_tc(u, P["up1"], relu=True, out_f32=False, tapw=P["up2_w"])["tap"]
+        return ops.upsample_tapsum(t12, P["up2_b"], image_size[-2:])
 
     def forward(self, scores, features, image_size):
         """Reference signature: scores (B,1,h,w), features dict (NCHW; ``FeatureMaps`` carries NHWC too)."""

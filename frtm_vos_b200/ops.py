@@ -108,10 +108,18 @@ def resize_bilinear(x: torch.Tensor, size, channels: Optional[int] = None, out: 
     return y
 
 
-def pyrup_bicubic(x: torch.Tensor) -> torch.Tensor:
+def pyrup_bicubic(x: torch.Tensor, split: bool = False):
+    """x2 bicubic pyramid upsample; ``split=True`` returns the result as ``Split`` planes (the next conv's input format)
+    without ever writing the fp32 tensor."""
     B, H, W, C = x.shape
+    if split:
+        assert C % 8 == 0
+        sp = Split(torch.empty((B, 2 * H, 2 * W, C), device=x.device, dtype=torch.float16),
+                   torch.empty((B, 2 * H, 2 * W, C), device=x.device, dtype=torch.float16), C)
+        lib().pyrup_bicubic_nhwc(ptr(x), B, H, W, C, None, ptr(sp.hi), ptr(sp.lo), stream())
+        return sp
     y = torch.empty((B, 2 * H, 2 * W, C), device=x.device, dtype=torch.float32)
-    lib().pyrup_bicubic_nhwc(ptr(x), B, H, W, C, ptr(y), stream())
+    lib().pyrup_bicubic_nhwc(ptr(x), B, H, W, C, ptr(y), None, None, stream())
     return y
 
 
@@ -200,6 +208,20 @@ def pixel_weights(y: torch.Tensor, tf: float, threshold: bool, return_count: boo
     ws = torch.empty(K, device=y.device, dtype=torch.float32) if counts is None else None
     lib().pixel_weights(ptr(y), K, HW, float(tf), 1 if threshold else 0, ptr(w), ptr(ws), ptr(counts), stream())
     return (w, ws) if return_count else w
+
+
+def upsample_tapsum(t12: torch.Tensor, bias, image_size) -> torch.Tensor:
+    """Tap maps (B,h,w,12) of the final 3x3 conv -> bicubic x2 -> bilinear to image_size -> shifted sum + bias -> (B,H,W),
+    in one kernel when the sizes fit its shared-memory windows, else through the separate kernels."""
+    B, h, w, _ = t12.shape
+    H, W = int(image_size[0]), int(image_size[1])
+    out = torch.empty((B, H, W), device=t12.device, dtype=torch.float32)
+    if lib().upsample_tapsum_supported(h, w, H, W):
+        lib().upsample_tapsum(ptr(t12), B, h, w, H, W, ptr(bias), ptr(out), stream())
+    else:
+        u = resize_bilinear(pyrup_bicubic(t12), (H, W))
+        lib().shift_sum9(ptr(u), B, H, W, ptr(bias), ptr(out), stream())
+    return out
 
 
 def conv3x3_to1_upsampled(x: torch.Tensor, w9c: torch.Tensor, bias, image_size) -> torch.Tensor:
@@ -322,8 +344,10 @@ def split_f16(x: torch.Tensor, channels: Optional[int] = None, ld: Optional[int]
 
 
 def conv2d_tc(x: Split, pc: PackedConvTC, res=None, relu: bool = False, out_f32: bool = True, out_split: bool = False,
-              nchw: bool = False, out: Optional[torch.Tensor] = None, coff: int = 0, split_ld: Optional[int] = None):
-    """Tensor-core conv.  Returns a dict with the requested outputs: 'y' (fp32 NHWC), 'split' (Split), 'nchw'."""
+              nchw: bool = False, out: Optional[torch.Tensor] = None, coff: int = 0, split_ld: Optional[int] = None,
+              tapw: Optional[torch.Tensor] = None):
+    """Tensor-core conv.  Returns a dict with the requested outputs: 'y' (fp32 NHWC), 'split' (Split), 'nchw', and with
+    ``tapw`` ((9, cout) weights of a following 3x3 -> 1 conv) 'tap': the (B,H,W,12) tap maps contracted in the epilogue."""
     B, Hi, Wi, ldx = x.hi.shape
     pad = pc.k // 2
     H, W = (Hi + 2 * pad - pc.k) // pc.stride + 1, (Wi + 2 * pad - pc.k) // pc.stride + 1
@@ -343,14 +367,15 @@ def conv2d_tc(x: Split, pc: PackedConvTC, res=None, relu: bool = False, out_f32:
                        torch.empty((B, H, W, ld), device=dev, dtype=torch.float16), pc.cout)
     res_f = res if torch.is_tensor(res) else None
     res_s = res if isinstance(res, Split) else None
+    tap = torch.empty((B, H, W, 12), device=dev, dtype=torch.float32) if tapw is not None else None
     lib().conv2d_tc(ptr(x.hi), ptr(x.lo), B, Hi, Wi, pc.cin, ldx, ptr(pc.wt), ptr(pc.oscale), pc.bn, ptr(pc.bias),
                     ptr(res_f), 0 if res_f is None else res_f.shape[3],
                     None if res_s is None else ptr(res_s.hi), None if res_s is None else ptr(res_s.lo),
                     0 if res_s is None else res_s.hi.shape[3],
                     ptr(y), 0 if y is None else y.shape[3], coff, ptr(y_nchw),
                     None if sp is None else ptr(sp.hi), None if sp is None else ptr(sp.lo), 0 if sp is None else sp.hi.shape[3], 0,
-                    pc.cout, pc.k, pc.k, pc.stride, 1 if relu else 0, stream())
-    return dict(y=y, split=sp, nchw=y_nchw)
+                    ptr(tapw), ptr(tap), pc.cout, pc.k, pc.k, pc.stride, 1 if relu else 0, stream())
+    return dict(y=y, split=sp, nchw=y_nchw, tap=tap)
 
 
 @dataclass

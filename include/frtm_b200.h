@@ -74,14 +74,17 @@ int frtm_conv2d_nhwc(const float *x, int B, int H, int W, int Cin, int ldx, cons
  *   wt         weights pre-tiled by frtm_vos_b200.ops.pack_conv_tc: [ntile][tap][Cin/64][hi|lo][bn_tile x 64] fp16 in
  *              the 128-byte-swizzled K-major shared-memory image, scaled per output channel by a power of two;
  *              oscale[n] = 1 / (16 * that scale)
- *   outputs    any of: y fp32 NHWC (ldy, y_coff), y_nchw fp32 (B,Cout,H,W), y_hi/y_lo split planes (ldyh, yh_coff)
+ *   outputs    any of: y fp32 NHWC (ldy, y_coff), y_nchw fp32 (B,Cout,H,W), y_hi/y_lo split planes (ldyh, yh_coff),
+ *              y_tap (B,Ho,Wo,12) = the 9 tap maps  sum_c tapw[tap][c] * out[c]  of a following 3x3 -> 1 conv contracted
+ *              per pixel in the epilogue (tapw [9][Cout]; needs Cout <= bn_tile; see frtm_upsample_tapsum)
  *   res / res_hi,res_lo   optional residual (fp32 NHWC or split planes) added before the ReLU
- * Same reference call sites as frtm_conv2d_nhwc; three MMAs per k-step (hi*hi + hi*lo + lo*hi) keep the result within
- * ~1e-6 relative of an fp32 convolution. */
+ * Same reference call sites as frtm_conv2d_nhwc; the products hi*hi + hi*lo + lo*hi (issued as A_hi x [B_hi | B_lo] and
+ * A_lo x B_hi) keep the result within ~1e-6 relative of an fp32 convolution. */
 int frtm_conv2d_tc(const void *x_hi, const void *x_lo, int B, int H, int W, int Cin, int ldx, const void *wt,
                    const float *oscale, int bn_tile, const float *bias, const float *res, int ldr, const void *res_hi,
                    const void *res_lo, int ldrh, float *y, int ldy, int y_coff, float *y_nchw, void *y_hi, void *y_lo,
-                   int ldyh, int yh_coff, int Cout, int kh, int kw, int stride, int relu, void *stream);
+                   int ldyh, int yh_coff, const float *tapw, float *y_tap, int Cout, int kh, int kw, int stride, int relu,
+                   void *stream);
 /* Device-side weight packer for 1x1 convs whose weights change at run time (project.weight, model/discriminator.py:81):
  * W (Cout,Cin) fp32 -> wt / oscale in the layout frtm_conv2d_tc expects (wt: cout_pad*Cin*2 halves, oscale: cout_pad). */
 int frtm_pack_tc_1x1(const float *W, int Cout, int Cin, int bn_tile, void *wt, float *oscale, void *stream);
@@ -106,7 +109,8 @@ int frtm_resize_bilinear_nhwc(const float *x, int B, int H, int W, int C, int ld
 
 /* Fixed x2 bicubic pyramid upsample (replicate pad 2, 4 depthwise 4x4 phases, crop 1) NHWC (B,H,W,C)->(B,2H,2W,C)
  * (model/seg_network.py:75-126). */
-int frtm_pyrup_bicubic_nhwc(const float *x, int B, int H, int W, int C, float *y, void *stream);
+int frtm_pyrup_bicubic_nhwc(const float *x, int B, int H, int W, int C, float *y, void *y_hi, void *y_lo, void *stream);
+/* (y may be NULL when only the split fp16 planes y_hi / y_lo of 16*result are wanted — the input format of frtm_conv2d_tc.) */
 
 /* Global average pool NHWC (B,H,W,ld)[0,C) -> (B,C)  (seg_network.py:18,34-35). Deterministic two-stage sum. */
 int frtm_global_avgpool_nhwc(const float *x, int B, int HW, int C, int ldx, float *out, float *workspace,
@@ -139,6 +143,11 @@ int frtm_conv3x3_to1_nhwc(const float *x, int B, int H, int W, int C, const floa
  * (zero outside the image) and the bias.  Exactly conv3x3(upsample(x)) by linearity, with 9 instead of C full-res maps. */
 int frtm_tapmaps_nhwc(const float *x, int64_t npix, int C, const float *w9c, float *y12, void *stream);
 int frtm_shift_sum9(const float *v12, int B, int H, int W, const float *bias, float *out, void *stream);
+/* The whole tail in one kernel: t12 (B,h,w,12) tap maps -> bicubic x2 (PyrUpBicubic2d) -> bilinear to (H,W) -> sum of the 9
+ * tap-shifted maps + bias -> logits (B,H,W).  Reads only t12, writes only the logits.  frtm_upsample_tapsum_supported
+ * returns 1 if the sizes fit the kernel's shared-memory windows (2h >= H, 2w >= W, scale close to 1). */
+int frtm_upsample_tapsum(const float *t12, int B, int h, int w, int H, int W, const float *bias, float *out, void *stream);
+int64_t frtm_upsample_tapsum_supported(int h, int w, int H, int W);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Mask merge  (model/tracker.py:143-150, 203-221)

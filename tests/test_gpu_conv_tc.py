@@ -115,3 +115,25 @@ def test_device_packer_matches_host_packer():
         b = ops.pack_conv_tc_1x1_device(w.to(DEV))
         assert a.bn == b.bn and torch.equal(a.oscale, b.oscale)
         assert torch.equal(a.wt.view(torch.int16), b.wt.view(torch.int16))
+
+
+def test_conv2d_tc_tap_contraction_in_epilogue():
+    """'tap' output: the 9 tap maps of a following 3x3 -> 1 conv, contracted per pixel from the ReLU'd conv output."""
+    from frtm_vos_b200 import ops
+    from frtm_vos_b200._lib import lib
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(2, 64, 20, 37, generator=g)
+    w = torch.randn(32, 64, 3, 3, generator=g) / 24
+    b = torch.randn(32, generator=g) * 0.1
+    w2 = torch.randn(1, 32, 3, 3, generator=g) / 17
+    pc = ops.pack_conv_tc(w, b, device=DEV)
+    xs = ops.split_f16(x.permute(0, 2, 3, 1).contiguous().to(DEV))
+    w9c = w2.permute(2, 3, 1, 0).reshape(9, 32).contiguous().to(DEV)
+    o = ops.conv2d_tc(xs, pc, relu=True, tapw=w9c)
+    y = torch.relu(F.conv2d(x.double(), w.double(), b.double(), 1, 1)).float()
+    assert (o["y"].cpu().permute(0, 3, 1, 2) - y).abs().max() < 1e-5
+    ref = torch.einsum("bchw,tc->bhwt", y.double(), w9c.cpu().double()).float()
+    assert (o["tap"][..., :9].cpu() - ref).abs().max() < 1e-5
+    assert float(o["tap"][..., 9:].abs().max()) == 0.0
+    only = ops.conv2d_tc(xs, pc, relu=True, out_f32=False, tapw=w9c)
+    assert only["y"] is None and torch.equal(only["tap"], o["tap"])

@@ -237,3 +237,37 @@ def test_final_conv_commutes_with_upsampling():
     w9c = w.permute(2, 3, 1, 0).reshape(9, 32).contiguous().to(DEV)
     y = ops.conv3x3_to1_upsampled(_nhwc(x).to(DEV), w9c, b.to(DEV), size)
     assert (y.cpu() - ref).abs().max() < 1e-5
+
+
+@pytest.mark.parametrize("hw,size", [((24, 43), (48, 84)), ((24, 43), (48, 86)), ((37, 50), (73, 99)), ((120, 214), (240, 427))])
+def test_fused_upsampler_tail(hw, size):
+    """frtm_upsample_tapsum (bicubic x2 -> bilinear -> 9 shifted taps in one kernel) == conv3x3_to1(resize(pyrup(x)))."""
+    ops = _ops()
+    from frtm_vos_b200._lib import lib
+    g = torch.Generator().manual_seed(21)
+    h, w = hw
+    x = torch.randn(2, 32, h, w, generator=g)
+    wt = torch.randn(1, 32, 3, 3, generator=g) / 17
+    b = torch.randn(1, generator=g)
+    from oracle import frtm_ref as R
+    ref = F.conv2d(F.interpolate(R.pyr_up_bicubic(x), size, mode="bilinear", align_corners=False), wt, b, 1, 1)[:, 0]
+    w9c = wt.permute(2, 3, 1, 0).reshape(9, 32).contiguous().to(DEV)
+    xd = _nhwc(x).to(DEV)
+    t12 = torch.empty((2, h, w, 12), device=DEV)
+    lib().tapmaps_nhwc(xd.data_ptr(), 2 * h * w, 32, w9c.data_ptr(), t12.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert lib().upsample_tapsum_supported(h, w, size[0], size[1]) == 1
+    y = ops.upsample_tapsum(t12, b.to(DEV), size)
+    assert (y.cpu() - ref).abs().max() < 2e-5
+    # and the unfused chain agrees too
+    y2 = ops.conv3x3_to1_upsampled(xd, w9c, b.to(DEV), size)
+    assert (y.cpu() - y2.cpu()).abs().max() < 2e-5
+
+
+def test_pyrup_bicubic_split_planes():
+    ops = _ops()
+    g = torch.Generator().manual_seed(22)
+    x = torch.randn(2, 9, 11, 64, generator=g).to(DEV)
+    y = ops.pyrup_bicubic(x)
+    sp = ops.pyrup_bicubic(x, split=True)
+    rec = (sp.hi.float() + sp.lo.float()) / 16.0
+    assert (rec - y).abs().max() < 2e-6 * max(y.abs().max().item(), 1.0)
