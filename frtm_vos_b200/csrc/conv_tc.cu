@@ -38,6 +38,11 @@ struct TcArgs {
   float *y;                // fp32 NHWC out (ldy, y_coff) or null
   float *y_nchw;           // or null
   __half *y_hi, *y_lo;     // split out planes (channel stride ldyh, offset yh_coff) or null
+  const float *r1_score;   // (B,Ho,Wo) fp32: a 65th input channel handled as an fp32 rank-1 term (TSE.transform), or null
+  const float *r1_w;       // [9][Cout] its 3x3 weights
+  const float *r1_bias;    // [Cout] bias added after the rank-1 term, or null
+  float *y_extra;          // (B,Ho,Wo): receives output channel `extra_ch` (the next conv's score channel), or null
+  int extra_ch, yh_cout;   // yh_cout: number of leading output channels written to the split planes
   const float *tapw;       // [9][Cout] weights of a following 3x3 -> 1 conv, contracted per pixel in the epilogue, or null
   float *y_tap;            // (B,Ho,Wo,12): the 9 tap maps  sum_c tapw[tap][c] * out[c]  (needs Cout <= BN), or null
   int ldr, ldrh, ldy, y_coff, ldyh, yh_coff;
@@ -48,12 +53,16 @@ struct TcArgs {
 // ----------------------------------------------------------------------------------------------------------------
 // kernel: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue (warp 2 owns the TMEM allocation)
 // ----------------------------------------------------------------------------------------------------------------
+// PACK: issue the passes as A_hi x [B_hi | B_lo] (N = 2*BN) + A_lo x B_hi — needs 4*BN TMEM columns; tiles whose
+// 4*BN would push the allocation to all 512 columns (one CTA per SM) keep the three separate N = BN products.
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi,
                                                       const __grid_constant__ CUtensorMap tm_lo, const TcArgs a) {
   constexpr int B_BYTES = BN * 128;
   constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
-  constexpr int COLS = tmem_cols(4 * BN);      // two accumulator slots of 2*BN columns: [hi*hi + lo*hi | hi*lo]
+  constexpr bool PACK = (4 * BN <= 256) || BN == 128;
+  constexpr int SLOT = PACK ? 2 * BN : BN;     // accumulator slot: [hi*hi + lo*hi | hi*lo] or one sum
+  constexpr int COLS = tmem_cols(2 * SLOT);    // two accumulator slots
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
@@ -133,16 +142,22 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
           mbar_wait(bar_acce + 8 * slot, ((grp >> 1) & 1) ^ 1);
           tc_fence_after();
         }
-        const uint32_t tacc = tmem_base + slot * (2 * BN);
+        const uint32_t tacc = tmem_base + slot * SLOT;
         const uint32_t sa = base + s * STAGE_BYTES;
         const uint64_t a_hi = umma_desc(sa), a_lo = umma_desc(sa + TC_A_BYTES);
-        const uint64_t b_hl = umma_desc(sa + 2 * TC_A_BYTES);
+        const uint64_t b_hl = umma_desc(sa + 2 * TC_A_BYTES), b_lo = umma_desc(sa + 2 * TC_A_BYTES + B_BYTES);
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
             const uint64_t adv = (uint64_t)(k * 32 >> 4);     // +32 bytes along K inside the swizzle atom
-            umma_f16(tacc, a_hi + adv, b_hl + adv, idesc2, (first && k == 0) ? 0u : 1u);
-            umma_f16(tacc, a_lo + adv, b_hl + adv, idesc, 1u);
+            if (PACK) {
+              umma_f16(tacc, a_hi + adv, b_hl + adv, idesc2, (first && k == 0) ? 0u : 1u);
+              umma_f16(tacc, a_lo + adv, b_hl + adv, idesc, 1u);
+            } else {
+              umma_f16(tacc, a_hi + adv, b_hl + adv, idesc, (first && k == 0) ? 0u : 1u);
+              umma_f16(tacc, a_hi + adv, b_lo + adv, idesc, 1u);
+              umma_f16(tacc, a_lo + adv, b_hl + adv, idesc, 1u);
+            }
           }
           umma_commit(bar_empty + 8 * s);     // frees the stage once the MMAs above have consumed it
           if ((kb % TC_FOLD) == TC_FOLD - 1 || kb == nkb - 1) umma_commit(bar_accf + 8 * slot);   // slot ready to fold
@@ -172,6 +187,22 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
         s_tap[i] = (n0 + ch < a.Cout) ? a.tapw[t * a.Cout + n0 + ch] : 0.f;
       }
     }
+    float *s_r1 = s_tap + 9 * BN;           // [10][BN]: rank-1 weights of the 9 taps, then the bias that follows them
+    float sv[9];
+    if (a.r1_score != nullptr) {
+      for (int i = threadIdx.x - 64; i < 10 * BN; i += 128) {
+        const int t = i / BN, ch = i - t * BN;
+        float v = 0.f;
+        if (n0 + ch < a.Cout) v = t < 9 ? a.r1_w[t * a.Cout + n0 + ch] : (a.r1_bias ? a.r1_bias[n0 + ch] : 0.f);
+        s_r1[i] = v;
+      }
+      const float *sb = a.r1_score + (int64_t)b * a.Ho * a.Wo;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int yy = py + t / 3 - 1, xx = px + t % 3 - 1;
+        sv[t] = (valid && yy >= 0 && yy < a.Ho && xx >= 0 && xx < a.Wo) ? sb[yy * a.Wo + xx] : 0.f;
+      }
+    }
     asm volatile("bar.sync 1, 128;" ::: "memory");
     // fold every finished accumulator slot into fp32 registers (round-to-nearest adds)
     float acc[BN];
@@ -185,12 +216,18 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
       tc_fence_after();
 #pragma unroll
       for (int c0 = 0; c0 < BN; c0 += 16) {
-        float t[16], t2[16];
-        const uint32_t col = tmem_base + ((uint32_t)(q * 32) << 16) + slot * (2 * BN) + (uint32_t)c0;
+        float t[16];
+        const uint32_t col = tmem_base + ((uint32_t)(q * 32) << 16) + slot * SLOT + (uint32_t)c0;
         tmem_ld16(col, t);
-        tmem_ld16(col + BN, t2);
+        if (PACK) {
+          float t2[16];
+          tmem_ld16(col + BN, t2);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[c0 + j] += t[j] + t2[j];
+          for (int j = 0; j < 16; ++j) acc[c0 + j] += t[j] + t2[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[c0 + j] += t[j];
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -214,6 +251,14 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
       const bool full = n0 + c0 + 16 <= a.Cout;
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], s_osc[c0 + j], s_bias[c0 + j]);
+      if (a.r1_score) {       // same order as frtm_rank1_finish: taps 0..8, then the bias
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaf(s_r1[t * BN + c0 + j], sv[t], v[j]);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] += s_r1[9 * BN + c0 + j];
+      }
       if (a.res) {
         const float *r = a.res + pix * a.ldr + n0 + c0;
         if (full && vec_res) {
@@ -279,7 +324,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
           hh[j] = __float2half_rn(sc);
           ll[j] = __float2half_rn(sc - __half2float(hh[j]));
         }
-        if (full && vec_h) {
+        if (n0 + c0 + 16 <= a.yh_cout && vec_h) {
           *reinterpret_cast<uint4 *>(dh) = *reinterpret_cast<const uint4 *>(hh);
           *reinterpret_cast<uint4 *>(dh + 8) = *reinterpret_cast<const uint4 *>(hh + 8);
           *reinterpret_cast<uint4 *>(dl) = *reinterpret_cast<const uint4 *>(ll);
@@ -287,8 +332,13 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            if (n0 + c0 + j < a.Cout) { dh[j] = hh[j]; dl[j] = ll[j]; }
+            if (n0 + c0 + j < a.yh_cout) { dh[j] = hh[j]; dl[j] = ll[j]; }
         }
+      }
+      if (a.y_extra && a.extra_ch >= n0 + c0 && a.extra_ch < n0 + c0 + 16) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (n0 + c0 + j == a.extra_ch) a.y_extra[pix] = v[j];
       }
       if (a.y_nchw) {
         const int64_t hw = (int64_t)a.Ho * a.Wo, p = (int64_t)py * a.Wo + px;
@@ -483,7 +533,7 @@ static int make_act_map(CUtensorMap *tm, const __half *ptr, int B, int H, int W,
 
 template <int BN, int STAGES>
 static int launch_tc(const CUtensorMap &mh, const CUtensorMap &ml, const TcArgs &a, dim3 grid, cudaStream_t st) {
-  constexpr int smem = STAGES * (2 * TC_A_BYTES + 2 * BN * 128) + 16 * STAGES + 48 + 44 * BN + 1024;
+  constexpr int smem = STAGES * (2 * TC_A_BYTES + 2 * BN * 128) + 16 * STAGES + 48 + 84 * BN + 1024;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -510,9 +560,12 @@ extern "C" int frtm_split_f16(const float *x, int64_t npix, int C, int ldx, void
 extern "C" int frtm_conv2d_tc(const void *x_hi, const void *x_lo, int B, int H, int W, int Cin, int ldx, const void *wt,
                               const float *oscale, int bn_tile, const float *bias, const float *res, int ldr,
                               const void *res_hi, const void *res_lo, int ldrh, float *y, int ldy, int y_coff, float *y_nchw,
-                              void *y_hi, void *y_lo, int ldyh, int yh_coff, const float *tapw, float *y_tap, int Cout, int kh,
-                              int kw, int stride, int relu, void *stream) {
+                              void *y_hi, void *y_lo, int ldyh, int yh_coff, int yh_cout, const float *tapw, float *y_tap,
+                              const float *r1_score, const float *r1_w, const float *r1_bias, float *y_extra, int extra_ch,
+                              int Cout, int kh, int kw, int stride, int relu, void *stream) {
   FRTM_REQUIRE(x_hi && x_lo && wt && oscale && (y || y_nchw || y_hi || y_tap), "conv2d_tc: null pointer");
+  FRTM_REQUIRE(!r1_score || r1_w, "conv2d_tc: the rank-1 score channel needs its weights");
+  FRTM_REQUIRE(!y_extra || (extra_ch >= 0 && extra_ch < Cout), "conv2d_tc: extra_ch out of range");
   FRTM_REQUIRE(!y_tap || (tapw && Cout <= bn_tile && (reinterpret_cast<uintptr_t>(y_tap) & 15) == 0),
                "conv2d_tc: the tap-map output needs tapw, a single N tile (Cout <= bn_tile) and a 16-byte aligned buffer");
   FRTM_REQUIRE(Cin % TC_BK == 0 && ldx % 8 == 0, "conv2d_tc: Cin must be a multiple of 64 and ldx of 8 (got %d, %d)", Cin, ldx);
@@ -530,6 +583,8 @@ extern "C" int frtm_conv2d_tc(const void *x_hi, const void *x_lo, int B, int H, 
   a.wt = (const __half *)wt; a.oscale = oscale; a.bias = bias; a.res = res; a.res_hi = (const __half *)res_hi;
   a.res_lo = (const __half *)res_lo; a.y = y; a.y_nchw = y_nchw; a.y_hi = (__half *)y_hi; a.y_lo = (__half *)y_lo;
   a.tapw = tapw; a.y_tap = y_tap;
+  a.r1_score = r1_score; a.r1_w = r1_w; a.r1_bias = r1_bias; a.y_extra = y_extra; a.extra_ch = extra_ch;
+  a.yh_cout = (yh_cout > 0 && yh_cout < Cout) ? yh_cout : Cout;
   a.ldr = ldr; a.ldrh = ldrh; a.ldy = ldy; a.y_coff = y_coff; a.ldyh = ldyh; a.yh_coff = yh_coff;
   a.B = B; a.H = H; a.W = W; a.Cout = Cout; a.kh = kh; a.kw = kw; a.pad = kh / 2; a.relu = relu; a.stride = stride;
   a.Ho = (H + 2 * a.pad - kh) / stride + 1; a.Wo = (W + 2 * a.pad - kw) / stride + 1;

@@ -345,7 +345,7 @@ def split_f16(x: torch.Tensor, channels: Optional[int] = None, ld: Optional[int]
 
 def conv2d_tc(x: Split, pc: PackedConvTC, res=None, relu: bool = False, out_f32: bool = True, out_split: bool = False,
               nchw: bool = False, out: Optional[torch.Tensor] = None, coff: int = 0, split_ld: Optional[int] = None,
-              tapw: Optional[torch.Tensor] = None):
+              tapw: Optional[torch.Tensor] = None, r1=None, split_cout: int = 0, extra_ch: int = -1):
     """Tensor-core conv.  Returns a dict with the requested outputs: 'y' (fp32 NHWC), 'split' (Split), 'nchw', and with
     ``tapw`` ((9, cout) weights of a following 3x3 -> 1 conv) 'tap': the (B,H,W,12) tap maps contracted in the epilogue."""
     B, Hi, Wi, ldx = x.hi.shape
@@ -358,24 +358,28 @@ def conv2d_tc(x: Split, pc: PackedConvTC, res=None, relu: bool = False, out_f32:
     y_nchw = torch.empty((B, pc.cout, H, W), device=dev, dtype=torch.float32) if nchw else None
     sp = None
     if out_split:
-        ld = split_ld or _rup(pc.cout, 8)
-        if ld != pc.cout:
+        nch = split_cout or pc.cout                      # channels that go to the split planes
+        ld = split_ld or _rup(nch, 8)
+        if ld != nch:
             sp = Split(torch.zeros((B, H, W, ld), device=dev, dtype=torch.float16),
-                       torch.zeros((B, H, W, ld), device=dev, dtype=torch.float16), pc.cout)
+                       torch.zeros((B, H, W, ld), device=dev, dtype=torch.float16), nch)
         else:
             sp = Split(torch.empty((B, H, W, ld), device=dev, dtype=torch.float16),
-                       torch.empty((B, H, W, ld), device=dev, dtype=torch.float16), pc.cout)
+                       torch.empty((B, H, W, ld), device=dev, dtype=torch.float16), nch)
     res_f = res if torch.is_tensor(res) else None
     res_s = res if isinstance(res, Split) else None
     tap = torch.empty((B, H, W, 12), device=dev, dtype=torch.float32) if tapw is not None else None
+    extra = torch.empty((B, H, W), device=dev, dtype=torch.float32) if extra_ch >= 0 else None
+    r1_score, r1_w, r1_bias = r1 if r1 is not None else (None, None, None)      # 65th input channel as a rank-1 term
     lib().conv2d_tc(ptr(x.hi), ptr(x.lo), B, Hi, Wi, pc.cin, ldx, ptr(pc.wt), ptr(pc.oscale), pc.bn, ptr(pc.bias),
                     ptr(res_f), 0 if res_f is None else res_f.shape[3],
                     None if res_s is None else ptr(res_s.hi), None if res_s is None else ptr(res_s.lo),
                     0 if res_s is None else res_s.hi.shape[3],
                     ptr(y), 0 if y is None else y.shape[3], coff, ptr(y_nchw),
                     None if sp is None else ptr(sp.hi), None if sp is None else ptr(sp.lo), 0 if sp is None else sp.hi.shape[3], 0,
-                    ptr(tapw), ptr(tap), pc.cout, pc.k, pc.k, pc.stride, 1 if relu else 0, stream())
-    return dict(y=y, split=sp, nchw=y_nchw, tap=tap)
+                    int(split_cout), ptr(tapw), ptr(tap), ptr(r1_score), ptr(r1_w), ptr(r1_bias), ptr(extra), int(extra_ch),
+                    pc.cout, pc.k, pc.k, pc.stride, 1 if relu else 0, stream())
+    return dict(y=y, split=sp, nchw=y_nchw, tap=tap, extra=extra)
 
 
 @dataclass
@@ -403,6 +407,12 @@ def conv65(h: Split, score: torch.Tensor, pc: PackedConv65, n_obj: int = 1, relu
     B = score.shape[0]
     assert B == F * n_obj
     dev = score.device
+    if n_obj == 1 and want_split and not want_f32:
+        # per-object input: the score channel's rank-1 term, bias and ReLU run in the tensor-core conv's epilogue, which
+        # writes the 64-channel split planes and (Cout == 65) the next conv's score channel directly
+        o = conv2d_tc(h, pc.main, relu=relu, out_f32=False, out_split=True, split_ld=64, split_cout=64,
+                      r1=(score, pc.wx, pc.bias), extra_ch=64 if pc.cout == 65 else -1)
+        return None, o["split"], o["extra"]
     ld = _rup(pc.cout, 4)
     main = conv2d_tc(h, pc.main, out=torch.empty((F, H, W, ld), device=dev, dtype=torch.float32))["y"]
     y = torch.empty((B, H, W, pc.cout), device=dev, dtype=torch.float32) if want_f32 else None

@@ -77,14 +77,18 @@ int frtm_conv2d_nhwc(const float *x, int B, int H, int W, int Cin, int ldx, cons
  *   outputs    any of: y fp32 NHWC (ldy, y_coff), y_nchw fp32 (B,Cout,H,W), y_hi/y_lo split planes (ldyh, yh_coff),
  *              y_tap (B,Ho,Wo,12) = the 9 tap maps  sum_c tapw[tap][c] * out[c]  of a following 3x3 -> 1 conv contracted
  *              per pixel in the epilogue (tapw [9][Cout]; needs Cout <= bn_tile; see frtm_upsample_tapsum)
+ *              (only the first yh_cout channels go to the split planes; 0 = all), y_extra (B,Ho,Wo) = output channel extra_ch
+ *   r1_score   optional 65th input channel (B,Ho,Wo) fp32 handled in the epilogue as an exact fp32 rank-1 term with weights
+ *              r1_w [9][Cout] and bias r1_bias (TSE.transform on cat(h, score), seg_network.py:15,19-20; see frtm_rank1_finish)
  *   res / res_hi,res_lo   optional residual (fp32 NHWC or split planes) added before the ReLU
  * Same reference call sites as frtm_conv2d_nhwc; the products hi*hi + hi*lo + lo*hi (issued as A_hi x [B_hi | B_lo] and
  * A_lo x B_hi) keep the result within ~1e-6 relative of an fp32 convolution. */
 int frtm_conv2d_tc(const void *x_hi, const void *x_lo, int B, int H, int W, int Cin, int ldx, const void *wt,
                    const float *oscale, int bn_tile, const float *bias, const float *res, int ldr, const void *res_hi,
                    const void *res_lo, int ldrh, float *y, int ldy, int y_coff, float *y_nchw, void *y_hi, void *y_lo,
-                   int ldyh, int yh_coff, const float *tapw, float *y_tap, int Cout, int kh, int kw, int stride, int relu,
-                   void *stream);
+                   int ldyh, int yh_coff, int yh_cout, const float *tapw, float *y_tap, const float *r1_score,
+                   const float *r1_w, const float *r1_bias, float *y_extra, int extra_ch, int Cout, int kh, int kw,
+                   int stride, int relu, void *stream);
 /* Device-side weight packer for 1x1 convs whose weights change at run time (project.weight, model/discriminator.py:81):
  * W (Cout,Cin) fp32 -> wt / oscale in the layout frtm_conv2d_tc expects (wt: cout_pad*Cin*2 halves, oscale: cout_pad). */
 int frtm_pack_tc_1x1(const float *W, int Cout, int Cin, int bn_tile, void *wt, float *oscale, void *stream);

@@ -105,6 +105,27 @@ def test_conv65(cout, n_obj):
         assert (extra.cpu() - ref[:, 64]).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("cout,hw", [(65, (15, 27)), (64, (15, 27)), (65, (21, 40))])
+def test_conv65_fused_epilogue(cout, hw):
+    """n_obj == 1: the score channel's rank-1 term, bias and ReLU run inside the tensor-core conv's epilogue."""
+    from frtm_vos_b200 import ops
+    g = torch.Generator().manual_seed(7 * cout + hw[0])
+    B = 3
+    h = torch.randn(B, 64, *hw, generator=g)
+    s = torch.randn(B, 1, *hw, generator=g)
+    w = torch.randn(cout, 65, 3, 3, generator=g) / 24
+    b = torch.randn(cout, generator=g)
+    ref = F.relu(F.conv2d(torch.cat((h, s), 1), w, b, 1, 1))
+    y, sp, extra = ops.conv65(ops.split_f16(_nhwc(h).to(DEV)), s[:, 0].contiguous().to(DEV), ops.pack_conv65(w, b, device=DEV))
+    assert y is None and sp.hi.shape[-1] == 64
+    back = (sp.hi.float() + sp.lo.float()).cpu() / ops.ACT_SCALE
+    assert (_nchw(back) - ref[:, :64]).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item())
+    if cout == 65:
+        assert (extra.cpu() - ref[:, 64]).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item())
+    else:
+        assert extra is None
+
+
 def test_device_packer_matches_host_packer():
     from frtm_vos_b200 import ops
     g = torch.Generator().manual_seed(4)
