@@ -55,7 +55,9 @@ struct TcArgs {
 // ----------------------------------------------------------------------------------------------------------------
 // PACK: issue the passes as A_hi x [B_hi | B_lo] (N = 2*BN) + A_lo x B_hi — needs 4*BN TMEM columns; tiles whose
 // 4*BN would push the allocation to all 512 columns (one CTA per SM) keep the three separate N = BN products.
-template <int BN, int STAGES>
+// R1 / TAP: epilogue features compiled in only where used (rank-1 score channel; tap-map contraction) — the unrolled
+// epilogue is most of the kernel's code, and the plain instances must not pay for them in instruction-cache misses.
+template <int BN, int STAGES, bool R1, bool TAP>
 __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi,
                                                       const __grid_constant__ CUtensorMap tm_lo, const TcArgs a) {
   constexpr int B_BYTES = BN * 128;
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
       s_osc[i] = a.oscale[n0 + i];
       s_bias[i] = (a.bias != nullptr && n0 + i < a.Cout) ? a.bias[n0 + i] : 0.f;
     }
-    if (a.y_tap != nullptr) {
+    if constexpr (TAP) {
       for (int i = threadIdx.x - 64; i < 9 * BN; i += 128) {
         const int t = i / BN, ch = i - t * BN;
         s_tap[i] = (n0 + ch < a.Cout) ? a.tapw[t * a.Cout + n0 + ch] : 0.f;
@@ -189,7 +191,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
     }
     float *s_r1 = s_tap + 9 * BN;           // [10][BN]: rank-1 weights of the 9 taps, then the bias that follows them
     float sv[9];
-    if (a.r1_score != nullptr) {
+    if constexpr (R1) {
       for (int i = threadIdx.x - 64; i < 10 * BN; i += 128) {
         const int t = i / BN, ch = i - t * BN;
         float v = 0.f;
@@ -251,7 +253,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
       const bool full = n0 + c0 + 16 <= a.Cout;
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], s_osc[c0 + j], s_bias[c0 + j]);
-      if (a.r1_score) {       // same order as frtm_rank1_finish: taps 0..8, then the bias
+      if constexpr (R1) {     // same order as frtm_rank1_finish: taps 0..8, then the bias
 #pragma unroll
         for (int t = 0; t < 9; ++t)
 #pragma unroll
@@ -297,7 +299,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
       }
-      if (a.y_tap) {
+      if constexpr (TAP) {
 #pragma unroll
         for (int t = 0; t < 9; ++t)
 #pragma unroll
@@ -335,7 +337,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
             if (n0 + c0 + j < a.yh_cout) { dh[j] = hh[j]; dl[j] = ll[j]; }
         }
       }
-      if (a.y_extra && a.extra_ch >= n0 + c0 && a.extra_ch < n0 + c0 + 16) {
+      if (R1 && a.y_extra && a.extra_ch >= n0 + c0 && a.extra_ch < n0 + c0 + 16) {
 #pragma unroll
         for (int j = 0; j < 16; ++j)
           if (n0 + c0 + j == a.extra_ch) a.y_extra[pix] = v[j];
@@ -347,7 +349,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
           if (n0 + c0 + j < a.Cout) a.y_nchw[((int64_t)b * a.Cout + n0 + c0 + j) * hw + p] = v[j];
       }
     }
-    if (a.y_tap && valid) {
+    if (TAP && valid) {
       float4 *o = reinterpret_cast<float4 *>(a.y_tap + pix * 12);
       o[0] = make_float4(tp[0], tp[1], tp[2], tp[3]);
       o[1] = make_float4(tp[4], tp[5], tp[6], tp[7]);
@@ -531,16 +533,16 @@ static int make_act_map(CUtensorMap *tm, const __half *ptr, int B, int H, int W,
   return FRTM_OK;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool R1, bool TAP>
 static int launch_tc(const CUtensorMap &mh, const CUtensorMap &ml, const TcArgs &a, dim3 grid, cudaStream_t st) {
   constexpr int smem = STAGES * (2 * TC_A_BYTES + 2 * BN * 128) + 16 * STAGES + 48 + 84 * BN + 1024;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, R1, TAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return FRTM_ELAUNCH; }
     configured = true;
   }
-  conv_tc_kernel<BN, STAGES><<<grid, 192, smem, st>>>(mh, ml, a);
+  conv_tc_kernel<BN, STAGES, R1, TAP><<<grid, 192, smem, st>>>(mh, ml, a);
   FRTM_CHECK_LAUNCH("conv_tc");
   return FRTM_OK;
 }
@@ -592,11 +594,16 @@ extern "C" int frtm_conv2d_tc(const void *x_hi, const void *x_lo, int B, int H, 
   const int ntiles_n = cdiv(Cout, bn_tile);
   dim3 grid((unsigned)(B * a.tiles_x * a.tiles_y), (unsigned)ntiles_n);
   cudaStream_t st = (cudaStream_t)stream;
+  const bool r1 = r1_score != nullptr, tap = y_tap != nullptr;
+  FRTM_REQUIRE(!(r1 && tap), "conv2d_tc: rank-1 input and tap-map output cannot be combined");
+  FRTM_REQUIRE(!r1 || bn_tile == 64 || bn_tile == 80, "conv2d_tc: the rank-1 score channel is built for N tiles 64 and 80");
+  FRTM_REQUIRE(!tap || bn_tile == 32, "conv2d_tc: the tap-map output is built for the N tile 32");
+  FRTM_REQUIRE(r1 || !y_extra, "conv2d_tc: y_extra needs the rank-1 epilogue");
   switch (bn_tile) {
-    case 32: return launch_tc<32, 2>(mh, ml, a, grid, st);
-    case 64: return launch_tc<64, 2>(mh, ml, a, grid, st);
-    case 80: return launch_tc<80, 2>(mh, ml, a, grid, st);
-    case 128: return launch_tc<128, 2>(mh, ml, a, grid, st);
+    case 32: return tap ? launch_tc<32, 2, false, true>(mh, ml, a, grid, st) : launch_tc<32, 2, false, false>(mh, ml, a, grid, st);
+    case 64: return r1 ? launch_tc<64, 2, true, false>(mh, ml, a, grid, st) : launch_tc<64, 2, false, false>(mh, ml, a, grid, st);
+    case 80: return r1 ? launch_tc<80, 2, true, false>(mh, ml, a, grid, st) : launch_tc<80, 2, false, false>(mh, ml, a, grid, st);
+    case 128: return launch_tc<128, 2, false, false>(mh, ml, a, grid, st);
     default: set_error("conv2d_tc: unsupported N tile %d (32, 64, 80, 128)", bn_tile); return FRTM_EINVAL;
   }
 }
