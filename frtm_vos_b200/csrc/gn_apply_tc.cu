@@ -87,7 +87,8 @@ struct GcParams {
   int64_t image_bytes;
 };
 
-__global__ void __launch_bounds__(GC_THREADS, 2) gn_apply_tc_kernel(const GaArgs a, const GcParams P) {
+// the operator for the sample of this CTA (returns early, after zeroing its partial row, for inactive memory slots)
+__device__ __forceinline__ void gc_sample(const GaArgs &a, const GcParams &P) {
   const int c = a.c, h = a.h, w = a.w, use_y = a.use_y;
   const int n = c * 9;
   const int hw = h * w, wp = w + 2, npad = (h + 2) * wp;
@@ -474,6 +475,66 @@ __global__ void __launch_bounds__(GC_THREADS, 2) gn_apply_tc_kernel(const GaArgs
   }
 }
 
+// The per-sample partials are reduced and the CG vector step is run by the operator kernel itself, so an operator
+// application is ONE launch instead of two: the CTA that retires last within a group of GC_RGROUP samples sums the
+// group's rows (fixed order), the one that completes the last group of an object sums the group rows (fixed order) and
+// advances the Polak-Ribiere recurrences.  Tickets are global atomics; every sum has a fixed order -> deterministic.
+__global__ void __launch_bounds__(GC_THREADS, 2) gn_apply_tc_kernel(const GaArgs a, const GcParams P, const GcFuse F) {
+  gc_sample(a, P);
+  if (!F.enabled) return;
+  __shared__ float red[32];
+  __shared__ int s_last;
+  const int o = a.table ? blockIdx.y : 0;
+  const int n = a.c * 9;
+  const int ngrp = (a.cap + GC_RGROUP - 1) / GC_RGROUP;
+  const int grp = blockIdx.x / GC_RGROUP;
+  const int gsize = min(GC_RGROUP, a.cap - grp * GC_RGROUP);
+  int *cnt = F.counters + (int64_t)o * (1 + ngrp);
+  __threadfence();                                   // this CTA's partial row is visible before its ticket
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int ticket = atomicAdd(cnt + 1 + grp, 1);
+    s_last = (ticket == gsize - 1) ? 1 : 0;
+    if (s_last) cnt[1 + grp] = 0;                    // every ticket of this group has been drawn: reset for the next launch
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  {   // group sum: rows grp*8 .. +gsize of this object's partials
+    const float *part = a.partial + ((int64_t)o * a.cap + (int64_t)grp * GC_RGROUP) * n;
+    float *dst = F.gsum + ((int64_t)o * ngrp + grp) * n;
+    for (int t = threadIdx.x; t < n; t += GC_THREADS) {
+      float v[GC_RGROUP];
+#pragma unroll
+      for (int u = 0; u < GC_RGROUP; ++u) v[u] = u < gsize ? __ldcg(part + (int64_t)u * n + t) : 0.f;
+      dst[t] = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int ticket = atomicAdd(cnt, 1);
+    s_last = (ticket == ngrp - 1) ? 1 : 0;
+    if (s_last) cnt[0] = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  CgVec cg = F.cg;
+  const int *gate = F.gate;
+  if (a.table) {
+    float *cgst = reinterpret_cast<float *>(a.table[5 * a.n_obj + o]);
+    cg.f = reinterpret_cast<float *>(a.table[4 * a.n_obj + o]);
+    cg.p = cgst; cg.rprev = cgst + cg.n; cg.rho = cgst + 2 * cg.n; cg.hasp = cgst + 2 * cg.n + 1;
+    cg.r += (int64_t)o * 3 * cg.n; cg.x += (int64_t)o * 3 * cg.n; cg.q += (int64_t)o * 3 * cg.n;
+    gate = reinterpret_cast<const int *>(a.table[6 * a.n_obj + o]);
+  }
+  cg.partial = F.gsum + (int64_t)o * ngrp * n;       // the vector step sums the group rows
+  cg.cap = ngrp;
+  if (gate && gate[0] < F.min_px) return;
+  cg_vector_step_cta<GC_THREADS, 6>(cg, F.mode, red);
+}
+
 // n samples (c, hw) fp32 + their stencils -> operator images
 __global__ void __launch_bounds__(256) build_images_kernel(const float *__restrict__ x, const float *__restrict__ stencil,
                                                            const float *__restrict__ uty, uint8_t *__restrict__ img, int c,
@@ -492,10 +553,10 @@ static size_t gc_smem_bytes(int c, int h, int w) {
 
 bool gn_apply_tc_supported(int c, int h, int w) {
   // the stencil chunks travel through the tile ring, so a tile slot must hold one (c >= 40); p is staged in registers
-  return c % 16 == 0 && c >= 48 && c * 9 <= 6 * GC_THREADS && c <= 128 && w < 65536 && gc_smem_bytes(c, h, w) <= 227 * 1024;
+  return c % 16 == 0 && c >= 48 && c * 9 <= 6 * GC_THREADS && c * 9 <= 1024 && c <= 128 && w < 65536 && gc_smem_bytes(c, h, w) <= 227 * 1024;
 }
 
-int gn_apply_tc_launch(const GaArgs &a, cudaStream_t st) {
+int gn_apply_tc_launch(const GaArgs &a, const GcFuse &fuse, cudaStream_t st) {
   GcParams P;
   const int hw = a.h * a.w;
   P.ntiles = gc_ntiles(hw); P.nchunks = gc_nchunks(hw); P.tile_bytes = 2 * a.c * 128;
@@ -509,7 +570,7 @@ int gn_apply_tc_launch(const GaArgs &a, cudaStream_t st) {
     configured = smem;
   }
   const dim3 grid(a.cap, a.table ? a.n_obj : 1);
-  gn_apply_tc_kernel<<<grid, GC_THREADS, smem, st>>>(a, P);
+  gn_apply_tc_kernel<<<grid, GC_THREADS, smem, st>>>(a, P, fuse);
   FRTM_CHECK_LAUNCH("gn_apply_tc");
   return FRTM_OK;
 }

@@ -730,13 +730,6 @@ __global__ void memory_insert_kernel(const InsertArgs a, const int *__restrict__
 // ---------------------------------------------------------------- CG vector kernels (filter-only problem) --------
 // cg_state layout: p[n] | r_prev[n] | rho | has_p | pad | pad           (persists across updates)
 // work layout    : b/r[n] | x[n] | q[n] | scal[8]
-struct CgVec {
-  float *f, *p, *rprev, *rho, *hasp;  // persistent
-  float *r, *x, *q;                   // per-run scratch
-  const float *partial;               // [cap][n] per-sample gradient partials
-  int n, cap;
-  float reg2, minv, forget;
-};
 
 // mode 0: finish RHS ( r = b = -(sum partial + reg^2 f) ), x = 0, apply the forgetting factor, then first direction.
 // mode 1: finish A p ( q = sum partial + reg^2 p ), alpha step, optional residual update, next direction.
@@ -1074,8 +1067,9 @@ extern "C" int frtm_gn_debug_dump(float *buf) { g_gn_debug_dump = buf; return FR
 
 extern "C" int64_t frtm_gn_update_workspace(int cap, int c, int h, int w) {
   const int64_t n = (int64_t)c * 9, hw = (int64_t)h * w;
-  // s[cap][hw] | v[cap][hw] | partial[cap][n] | r[n] | x[n] | q[n]
-  return (2 * cap * hw + cap * n + 3 * n + 64) * (int64_t)sizeof(float);
+  // s[cap][hw] | v[cap][hw] | partial[cap][n] | r[n] | x[n] | q[n] | tickets[1 + ngroups] | group sums[ngroups][n]
+  const int64_t ngrp = (cap + GC_RGROUP - 1) / GC_RGROUP;
+  return (2 * cap * hw + cap * n + 3 * n + 64 + (1 + ngrp) + 8 + ngrp * n) * (int64_t)sizeof(float);
 }
 
 static int gn_update_impl(const float *samples, const __half *samples_split, const float *stencil, const float *uty,
@@ -1135,9 +1129,21 @@ static int gn_update_impl(const float *samples, const __half *samples_split, con
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gn_apply_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gt_smem);
     if (e != cudaSuccess) { cudaGetLastError(); CQ = 0; } else gt_configured = gt_smem;
   }
+  // tensor-core path: the operator kernel's last CTA per object runs the CG vector step itself (tickets in the workspace)
+  GcFuse fuse;
+  fuse.cg = cg; fuse.gate = gate_count; fuse.mode = 0; fuse.min_px = min_px; fuse.enabled = use_tc ? 1 : 0;
+  const int ngrp = (cap + GC_RGROUP - 1) / GC_RGROUP;
+  fuse.counters = reinterpret_cast<int *>(vecs + (int64_t)n_obj * 3 * n);
+  fuse.gsum = vecs + (int64_t)n_obj * 3 * n + (((int64_t)n_obj * (1 + ngrp) + 3) & ~(int64_t)3);
+  if (use_tc) {
+    if (cudaMemsetAsync(fuse.counters, 0, sizeof(int) * n_obj * (1 + ngrp), st) != cudaSuccess) {
+      set_error("gn_update: cudaMemsetAsync failed");
+      return FRTM_ELAUNCH;
+    }
+  }
   auto launch_apply = [&]() -> int {
     if (use_tc) {
-      const int rc = gn_apply_tc_launch(ga, st);
+      const int rc = gn_apply_tc_launch(ga, fuse, st);
       if (rc == FRTM_OK) count_launch(-1);                  // counted again by FRTM_CHECK_LAUNCH at the call site
       return rc;
     }
@@ -1154,16 +1160,22 @@ static int gn_update_impl(const float *samples, const __half *samples_split, con
     const int iters = cg_iters[gi];
     if (iters <= 0) continue;
     ga.use_y = 1; ga.pvec = filt;        // RHS: partial_i = X_i^T sw_i (S_i (X_i * f) - t_i)
+    fuse.mode = 0;
     if (int rc = launch_apply()) return rc;
     FRTM_CHECK_LAUNCH("gn_update/apply(rhs)");
-    cg_vector_kernel<<<table ? n_obj : 1, 1024, 0, st>>>(cg, 0, gate_count, min_px, table, n_obj);
-    FRTM_CHECK_LAUNCH("gn_update/cg(rhs)");
+    if (!use_tc) {
+      cg_vector_kernel<<<table ? n_obj : 1, 1024, 0, st>>>(cg, 0, gate_count, min_px, table, n_obj);
+      FRTM_CHECK_LAUNCH("gn_update/cg(rhs)");
+    }
     ga.use_y = 0; ga.pvec = cg.p;
     for (int it = 0; it < iters; ++it) {
+      fuse.mode = it == iters - 1 ? 2 : 1;
       if (int rc = launch_apply()) return rc;
       FRTM_CHECK_LAUNCH("gn_update/apply");
-      cg_vector_kernel<<<table ? n_obj : 1, 1024, 0, st>>>(cg, it == iters - 1 ? 2 : 1, gate_count, min_px, table, n_obj);
-      FRTM_CHECK_LAUNCH("gn_update/cg");
+      if (!use_tc) {
+        cg_vector_kernel<<<table ? n_obj : 1, 1024, 0, st>>>(cg, fuse.mode, gate_count, min_px, table, n_obj);
+        FRTM_CHECK_LAUNCH("gn_update/cg");
+      }
     }
   }
   return FRTM_OK;

@@ -38,7 +38,8 @@ __host__ __device__ inline int64_t gc_sample_items(int c, int hw) {
 // true if the tensor-core operator kernel supports this problem shape
 bool gn_apply_tc_supported(int c, int h, int w);
 // launches the tensor-core operator kernel over all (object, sample) pairs
-int gn_apply_tc_launch(const GaArgs &a, cudaStream_t st);
+struct GcFuse;
+int gn_apply_tc_launch(const GaArgs &a, const GcFuse &fuse, cudaStream_t st);
 
 // One work item of the image build.  Items [0, ntiles*c*8): 8 consecutive pixels of channel row r in tile j -> one
 // 16-byte chunk in each plane.  Remaining items: 4 consecutive pixels of one stencil / uty row of one chunk.
@@ -77,6 +78,142 @@ __device__ __forceinline__ void gc_image_item(const float *__restrict__ x, const
     for (int u = 0; u < 4; ++u) v[u] = (q0 + u < hw) ? src[q0 + u] : 0.f;
     float *dst = reinterpret_cast<float *>(img + (int64_t)ntiles * 2 * c * GC_TILE * 2) + ((int64_t)m * 10 + t) * GC_CHUNK_PX + g4 * 4;
     *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+
+// ---------------------------------------------------------------- CG vector step (filter-only problem) -------------
+// cg_state layout: p[n] | r_prev[n] | rho | has_p | pad | pad           (persists across updates)
+// work layout    : b/r[n] | x[n] | q[n]
+struct CgVec {
+  float *f, *p, *rprev, *rho, *hasp;  // persistent
+  float *r, *x, *q;                   // per-run scratch
+  const float *partial;               // [cap][n] per-sample gradient partials
+  int n, cap;
+  float reg2, minv, forget;
+};
+
+// What the operator kernel needs to run the CG vector step itself when its last CTA of an object retires.
+constexpr int GC_RGROUP = 8;      // samples per first-level reduction group
+struct GcFuse {
+  CgVec cg;            // template: pointers of the single-object form, or per-object offsets applied from the table
+  const int *gate;     // single-object gate (table form: row 6)
+  int *counters;       // [n_obj][1 + ngroups] zero-initialised tickets (object, then its groups of GC_RGROUP samples);
+                       // whoever draws the last ticket resets the counter
+  float *gsum;         // [n_obj][ngroups][n] group sums of the per-sample partials
+  int mode, min_px, enabled;
+};
+
+// One CG vector step by the whole CTA (NT threads, EPT = ceil(n / NT) elements per thread):
+// mode 0: finish RHS ( r = b = -(sum partial + reg^2 f) ), x = 0, apply the forgetting factor, then first direction.
+// mode 1: finish A p ( q = sum partial + reg^2 p ), alpha step, residual update, next direction.
+// mode 2: like mode 1 but last CG iteration of the GN step: no residual update, no new direction, f += x.
+// Same recurrences as cg_vector_kernel (optimizer.py:98-153); partials are read with ld.global.cg (written by other SMs).
+template <int NT, int EPT>
+__device__ __forceinline__ void cg_vector_step_cta(const CgVec &s, int mode, float *red) {
+  const int tid = threadIdx.x;
+  float g[EPT], r[EPT], p[EPT], rp[EPT], q[EPT];
+  {   // fixed summation order; all EPT x 8 loads of a round are independent and in flight together
+    float g8[EPT][8];
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+      r[e] = 0.f; p[e] = 0.f; rp[e] = 0.f; q[e] = 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) g8[e][u] = 0.f;
+    }
+    int k = 0;
+    for (; k + 8 <= s.cap; k += 8) {
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        const int t = tid + e * NT;
+        if (t < s.n) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) g8[e][u] += __ldcg(s.partial + (int64_t)(k + u) * s.n + t);
+        }
+      }
+    }
+    for (; k < s.cap; ++k) {
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        const int t = tid + e * NT;
+        if (t < s.n) g8[e][0] += __ldcg(s.partial + (int64_t)k * s.n + t);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < EPT; ++e)
+      g[e] = ((g8[e][0] + g8[e][1]) + (g8[e][2] + g8[e][3])) + ((g8[e][4] + g8[e][5]) + (g8[e][6] + g8[e][7]));
+  }
+  float rho = *s.rho;
+  const bool hasp = *s.hasp != 0.f;
+  if (mode == 0) {
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+      const int t = tid + e * NT;
+      if (t < s.n) {
+        r[e] = -(g[e] + s.reg2 * s.f[t]);
+        s.x[t] = 0.f;
+        p[e] = hasp ? s.p[t] : 0.f;
+        rp[e] = hasp ? s.rprev[t] : 0.f;
+      }
+    }
+    if (hasp) rho = rho / s.forget;                    // optimizer.py:104-105
+  } else {
+    float pq_l = 0.f;
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+      const int t = tid + e * NT;
+      if (t < s.n) {
+        p[e] = s.p[t];
+        q[e] = g[e] + s.reg2 * p[e];
+        r[e] = s.r[t];
+        pq_l += p[e] * q[e];
+      }
+    }
+    const float pq = block_sum(pq_l, red);
+    const float alpha = rho / pq;                      // standard_alpha, optimizer.py:134
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+      const int t = tid + e * NT;
+      if (t < s.n) {
+        rp[e] = r[e];                                  // r_prev = r.clone()
+        s.rprev[t] = rp[e];
+        const float xn = s.x[t] + alpha * p[e];
+        s.x[t] = xn;
+        if (mode == 1) r[e] = r[e] - alpha * q[e];
+        else s.f[t] += xn;                             // theta += step_alpha * delta_x
+        s.r[t] = r[e];
+      }
+    }
+    if (mode == 2) return;
+  }
+  // next direction (optimizer.py:115-128): z = r / diag_M ; rho = <r,z> ; beta = max((rho - <r_prev,z>)/rho1, 0)
+  float rz = 0.f, rpz = 0.f;
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) {
+    const float z = r[e] * s.minv;
+    rz += r[e] * z;
+    rpz += rp[e] * z;
+  }
+  const float rho_new = block_sum(rz, red);
+  float beta = 0.f;
+  const bool use_beta = (mode != 0 || hasp);
+  if (use_beta) {
+    const float rho2 = block_sum(rpz, red);
+    beta = fmaxf((rho_new - rho2) / rho, 0.f);
+  }
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) {
+    const int t = tid + e * NT;
+    if (t < s.n) {
+      const float z = r[e] * s.minv;
+      s.p[t] = use_beta ? z + p[e] * beta : z;
+      if (mode == 0) s.r[t] = r[e];
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    *s.rho = rho_new;
+    *s.hasp = 1.f;
   }
 }
 
