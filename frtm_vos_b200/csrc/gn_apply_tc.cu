@@ -29,14 +29,14 @@
 
 namespace frtm {
 
-constexpr int GC_SLOTS = 3;                // ring slots (one tile each)
+constexpr int GC_MAX_SLOTS = 8;            // ring slots (one tile each): as many as fit, see gc_slots()
 constexpr int GC_FOLD = 4;                 // tiles accumulated inside the tensor core between fp32 register folds
 constexpr int GC_VSTEP = 2;                // tiles per v-operand slot
 constexpr int GC_PGROUP = 2;               // tile pairs per phase-1 accumulator slot
 constexpr int GC_THREADS = 192;
 constexpr int GC_VTILE_BYTES = 4096;       // [hi|lo][16 rows][64] fp16
 constexpr int GC_VSLOT_BYTES = GC_VSTEP * GC_VTILE_BYTES;
-constexpr int GC_NBARS = 2 * GC_SLOTS + 12;
+constexpr int GC_NBARS = 2 * GC_MAX_SLOTS + 12;
 constexpr int GC_P1_COLS = 48;             // phase 1: one 16-column accumulator per pass (hi*hi, hi*lo, lo*hi) of a pair
 constexpr int GC_P3_COLS = 48;             // phase 3: A_hi x [B_hi|B_lo] (32 columns) and A_lo x B_hi (16) of one tile parity
 constexpr int GC_TMEM_COLS = 256;          // 2 slots x max(GC_PGROUP * GC_P1_COLS, GC_VSTEP * GC_P3_COLS) = 192
@@ -83,7 +83,7 @@ __device__ __forceinline__ void drain_sync() { asm volatile("bar.sync 1, 128;" :
 #endif
 
 struct GcParams {
-  int ntiles, nchunks, tile_bytes;
+  int ntiles, nchunks, tile_bytes, slots;
   int64_t image_bytes;
 };
 
@@ -93,7 +93,7 @@ __device__ __forceinline__ void gc_sample(const GaArgs &a, const GcParams &P) {
   const int n = c * 9;
   const int hw = h * w, wp = w + 2, npad = (h + 2) * wp;
   const int tid = threadIdx.x, lane = tid & 31, warp = uniform_warp_idx();
-  const int ntiles = P.ntiles, nchunks = P.nchunks, tile_bytes = P.tile_bytes;
+  const int ntiles = P.ntiles, nchunks = P.nchunks, tile_bytes = P.tile_bytes, NS = P.slots;
   const int cps = tile_bytes >= 2 * GC_CHUNK_BYTES ? 2 : 1;      // stencil chunks per ring slot
   const int ncl = (nchunks + cps - 1) / cps;                      // stencil loads
   const int plane_bytes = tile_bytes >> 1;
@@ -123,8 +123,8 @@ __device__ __forceinline__ void gc_sample(const GaArgs &a, const GcParams &P) {
   uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t ring = base;
   // operand buffer: phase 1 keeps p here (2 chunks x [hi|lo][16][64]), phase 3 the two v-operand slots
-  const uint32_t obuf = ring + GC_SLOTS * tile_bytes;
-  uint8_t *obuf_g = gen + GC_SLOTS * tile_bytes;
+  const uint32_t obuf = ring + NS * tile_bytes;
+  uint8_t *obuf_g = gen + NS * tile_bytes;
   float *sp = reinterpret_cast<float *>(obuf_g + 2 * GC_VSLOT_BYTES);
   float *vp = sp + npad;
   uint8_t *tail = reinterpret_cast<uint8_t *>(vp + npad);
@@ -132,12 +132,12 @@ __device__ __forceinline__ void gc_sample(const GaArgs &a, const GcParams &P) {
   const uint32_t bars = base + (uint32_t)(tail - gen);
   float *red = reinterpret_cast<float *>(tail + 8 * GC_NBARS);            // 8 floats
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(red + 8);
-  const uint32_t bar_full = bars, bar_empty = bars + 8 * GC_SLOTS;
-  const uint32_t bar_accfull = bars + 8 * (2 * GC_SLOTS), bar_accfree = bar_accfull + 16, bar_vready = bar_accfull + 32,
+  const uint32_t bar_full = bars, bar_empty = bars + 8 * GC_MAX_SLOTS;
+  const uint32_t bar_accfull = bars + 8 * (2 * GC_MAX_SLOTS), bar_accfree = bar_accfull + 16, bar_vready = bar_accfull + 32,
                  bar_vfree = bar_accfull + 48, bar_foldfull = bar_accfull + 64, bar_foldfree = bar_accfull + 80;
 
   if (tid == 0) {
-    for (int s = 0; s < GC_SLOTS; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < GC_MAX_SLOTS; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_accfull + 8 * s, 1); mbar_init(bar_accfree + 8 * s, 4);
       mbar_init(bar_vready + 8 * s, 4); mbar_init(bar_vfree + 8 * s, 1);
@@ -199,8 +199,8 @@ __device__ __forceinline__ void gc_sample(const GaArgs &a, const GcParams &P) {
     {
       const uint8_t *st = img + (int64_t)ntiles * tile_bytes;
       for (int it = 0; it < 2 * ntiles + ncl; ++it) {
-        const int s = it % GC_SLOTS;
-        mbar_wait(bar_empty + 8 * s, ((it / GC_SLOTS) & 1) ^ 1);
+        const int s = it % NS;
+        mbar_wait(bar_empty + 8 * s, ((it / NS) & 1) ^ 1);
         const uint8_t *src;
         uint32_t bytes = tile_bytes;
         if (it < ntiles) src = img + (int64_t)it * tile_bytes;
@@ -223,43 +223,54 @@ __device__ __forceinline__ void gc_sample(const GaArgs &a, const GcParams &P) {
       constexpr uint32_t idesc16 = umma_idesc(128, 16), idesc32 = umma_idesc(128, 32);
       constexpr uint32_t idesc1 = idesc16 | (1u << 15);        // A is MN-major (pixels contiguous, K = channel rows)
       constexpr uint32_t idesc1_32 = idesc32 | (1u << 15);
-      // phase 1: one M = 128 (two tiles) x N = 16 x K = c product per tile pair, GC_PGROUP pairs per accumulator slot
+      // This warp is a single serial instruction stream, so its instruction count per product IS the kernel's critical
+      // path (measured: ~150 instructions per MMA pair cost more than the MMAs).  Descriptors are therefore built once
+      // per operand and advanced by adding constants, the k loops are unrolled with compile-time offsets, and one elected
+      // region issues all the products of a hand-off.
+      const uint64_t dP = umma_desc_ls(obuf, 0, 1024);           // p operand, k-step ks at + (ks>>2)*4 KB + (ks&3)*32 B
+      const int nks = c / 16;
+      // phase 1: per tile pair (M = 128 pixels), per k-step (16 channels):  D[0:32) (+)= A_hi x [p_hi | p_lo]  as one
+      // N = 32 product and  D[32:48) (+)= A_lo x p_hi  (N = 16); GC_PGROUP pairs per accumulator slot
       for (int tp = 0; tp < npairs; ++tp) {
         const int it0 = 2 * tp, it1 = it0 + 1;
-        const int s0 = it0 % GC_SLOTS, s1 = it1 % GC_SLOTS;
+        const int s0 = it0 % NS, s1 = it1 % NS;
         const int grp = tp / GC_PGROUP, as = grp & 1, sub = tp - grp * GC_PGROUP;
-        if (sub == 0) mbar_wait(bar_accfree + 8 * as, ((grp >> 1) & 1) ^ 1);
-        mbar_wait(bar_full + 8 * s0, (it0 / GC_SLOTS) & 1);
-        mbar_wait(bar_full + 8 * s1, (it1 / GC_SLOTS) & 1);
-        tc_fence_after();
+        if (sub == 0) {     // the drain warps have read this accumulator slot out of TMEM (tcgen05.ld) before arriving
+          mbar_wait(bar_accfree + 8 * as, ((grp >> 1) & 1) ^ 1);
+          tc_fence_after();
+        }
+        mbar_wait(bar_full + 8 * s0, (it0 / NS) & 1);
+        mbar_wait(bar_full + 8 * s1, (it1 / NS) & 1);
         if (lane == 0) GC_STAMP(2, tp);
         const int slo = min(s0, s1), shi = max(s0, s1);       // TMEM lanes 0-63 <- the tile in the lower slot
-        const uint32_t lbo = (uint32_t)(shi - slo) * tile_bytes;
-        const uint32_t a0 = ring + slo * tile_bytes;
-        // An MMA of this shape costs ~90 cycles whatever N is (measured), so the passes are packed: A_hi x [p_hi | p_lo] as
-        // one N = 32 product, A_lo x p_hi as a second one, into separate accumulator columns.
+        const uint64_t dA = umma_desc_ls(ring + slo * tile_bytes, (uint32_t)(shi - slo) * tile_bytes, 1024);
+        const uint64_t dAlo = dA + (uint64_t)(plane_bytes >> 4);
         const uint32_t tacc = tmem_base + as * (GC_P1_COLS * GC_PGROUP) + sub * GC_P1_COLS;
-        for (int ks = 0; ks < c / 16; ++ks) {
-          const uint64_t a_hi = umma_desc_ls(a0 + ks * 2048, lbo, 1024);
-          const uint64_t a_lo = umma_desc_ls(a0 + plane_bytes + ks * 2048, lbo, 1024);
-          const uint32_t bb = obuf + (ks >> 2) * GC_VTILE_BYTES + (ks & 3) * 32;
-          const uint64_t b_hl = umma_desc_ls(bb, 0, 1024);                   // rows 0-15 p_hi taps, rows 16-31 p_lo taps
-          if (elect_one()) {
-            umma_f16(tacc, a_hi, b_hl, idesc1_32, ks > 0 ? 1u : 0u);      // N = 32: hi*hi | hi*lo
-            umma_f16(tacc + 32, a_lo, b_hl, idesc1, ks > 0 ? 1u : 0u);           // N = 16: lo*hi
-          }
-        }
         if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            if (ks < nks) {
+              const uint64_t ka = (uint64_t)(ks * 2048 >> 4);                              // 16 channel rows = 2 KB
+              const uint64_t kb = (uint64_t)(((ks >> 2) * GC_VTILE_BYTES + (ks & 3) * 32) >> 4);
+              if (ks == 0) {
+                umma_f16(tacc, dA, dP, idesc1_32, 0u);
+                umma_f16(tacc + 32, dAlo, dP, idesc1, 0u);
+              } else {
+                umma_f16(tacc, dA + ka, dP + kb, idesc1_32, 1u);
+                umma_f16(tacc + 32, dAlo + ka, dP + kb, idesc1, 1u);
+              }
+            }
+          }
           umma_commit(bar_empty + 8 * s0);
           umma_commit(bar_empty + 8 * s1);
           if (sub == GC_PGROUP - 1 || tp == npairs - 1) umma_commit(bar_accfull + 8 * as);
         }
         __syncwarp();
+        if (lane == 0) GC_STAMP(0, 2 + tp);
       }
-      // phase 3: per tile  D[0:32) (+)= A_hi x [B_hi | B_lo],  D[0:16) += A_lo x B_hi ;  M = 128 (c channel rows valid),
-      // K = 64 pixels per tile, GC_FOLD tiles per accumulator slot, GC_VSTEP tiles per v-operand slot
-      // The two tiles of a v-operand slot and the two products of a tile go to four independent accumulators and are
-      // issued interleaved, for the same reason as above.
+      // phase 3: per tile  D[0:32) (+)= A_hi x [v_hi | v_lo],  D[32:48) (+)= A_lo x v_hi ;  M = 128 (c channel rows valid),
+      // K = 64 pixels per tile, GC_FOLD tiles per accumulator slot, GC_VSTEP tiles per v-operand slot, each tile of a
+      // slot with its own accumulator columns
       const int nvs = (ntiles + GC_VSTEP - 1) / GC_VSTEP;
       for (int vstep = 0; vstep < nvs; ++vstep) {
         const int vs = vstep & 1;
@@ -267,39 +278,41 @@ __device__ __forceinline__ void gc_sample(const GaArgs &a, const GcParams &P) {
         const int nt = min(GC_VSTEP, ntiles - j0);
         const int grp = j0 / GC_FOLD, fs = grp & 1;
         const bool first = (j0 % GC_FOLD) == 0;
-        if (first) mbar_wait(bar_foldfree + 8 * fs, ((grp >> 1) & 1) ^ 1);
+        if (first) {
+          mbar_wait(bar_foldfree + 8 * fs, ((grp >> 1) & 1) ^ 1);
+          tc_fence_after();
+        }
         mbar_wait(bar_vready + 8 * vs, (vstep >> 1) & 1);
-        uint32_t a0[GC_VSTEP];
+        uint64_t dX[GC_VSTEP];
+        int sl[GC_VSTEP];
 #pragma unroll
         for (int u = 0; u < GC_VSTEP; ++u) {
-          const int it = ntiles + ncl + j0 + u, s = it % GC_SLOTS;
-          if (u < nt) mbar_wait(bar_full + 8 * s, (it / GC_SLOTS) & 1);
-          a0[u] = ring + s * tile_bytes;
+          const int it = ntiles + ncl + j0 + u;
+          sl[u] = it % NS;
+          if (u < nt) mbar_wait(bar_full + 8 * sl[u], (it / NS) & 1);
+          dX[u] = umma_desc_ls(ring + sl[u] * tile_bytes, 0, 1024);
         }
-        tc_fence_after();
         if (lane == 0) GC_STAMP(2, 16 + vstep);
+        const uint64_t dV = umma_desc_ls(obuf + vs * GC_VSLOT_BYTES, 0, 1024);
+        const uint64_t pl = (uint64_t)(plane_bytes >> 4);
+        const uint32_t tacc = tmem_base + fs * (GC_P3_COLS * GC_VSTEP);
+        const uint32_t acc0 = first ? 0u : 1u;
+        if (elect_one()) {
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {
+          for (int k4 = 0; k4 < 4; ++k4) {
 #pragma unroll
-          for (int u = 0; u < GC_VSTEP; ++u) {
-            if (u < nt) {
-              const uint32_t b0 = obuf + vs * GC_VSLOT_BYTES + u * GC_VTILE_BYTES;
-              const uint32_t tacc = tmem_base + fs * (GC_P3_COLS * GC_VSTEP) + u * GC_P3_COLS;
-              const uint64_t a_hi = umma_desc_ls(a0[u] + k4 * 32, 0, 1024), a_lo = umma_desc_ls(a0[u] + plane_bytes + k4 * 32, 0, 1024);
-              const uint64_t b_hl = umma_desc_ls(b0 + k4 * 32, 0, 1024);        // rows 0-15 hi taps, rows 16-31 lo taps
-              if (elect_one()) {
-                umma_f16(tacc, a_hi, b_hl, idesc32, (first && k4 == 0) ? 0u : 1u);
-                umma_f16(tacc + 32, a_lo, b_hl, idesc16, (first && k4 == 0) ? 0u : 1u);
+            for (int u = 0; u < GC_VSTEP; ++u) {
+              if (u < nt) {
+                const uint64_t kk = (uint64_t)(k4 * 32 >> 4);
+                const uint64_t dB = dV + (uint64_t)(u * GC_VTILE_BYTES >> 4) + kk;      // rows 0-15 hi taps, rows 16-31 lo taps
+                umma_f16(tacc + u * GC_P3_COLS, dX[u] + kk, dB, idesc32, k4 == 0 ? acc0 : 1u);
+                umma_f16(tacc + u * GC_P3_COLS + 32, dX[u] + pl + kk, dB, idesc16, k4 == 0 ? acc0 : 1u);
               }
             }
           }
-        }
-        if (elect_one()) {
 #pragma unroll
-          for (int u = 0; u < GC_VSTEP; ++u) {
-            const int it = ntiles + ncl + j0 + u;
-            if (u < nt) umma_commit(bar_empty + 8 * (it % GC_SLOTS));
-          }
+          for (int u = 0; u < GC_VSTEP; ++u)
+            if (u < nt) umma_commit(bar_empty + 8 * sl[u]);
           umma_commit(bar_vfree + 8 * vs);
           const int jl = j0 + nt - 1;
           if ((jl % GC_FOLD) == GC_FOLD - 1 || jl == ntiles - 1) umma_commit(bar_foldfull + 8 * fs);
@@ -343,7 +356,7 @@ __device__ __forceinline__ void gc_sample(const GaArgs &a, const GcParams &P) {
 #pragma unroll
       for (int u = 0; u < GC_PGROUP; ++u) {
         const int tp = grp * GC_PGROUP + u;
-        const bool swapped = ((2 * tp) % GC_SLOTS) > ((2 * tp + 1) % GC_SLOTS);
+        const bool swapped = ((2 * tp) % NS) > ((2 * tp + 1) % NS);
         const int tile = 2 * tp + (((dt >> 6) & 1) ^ (swapped ? 1 : 0));
         const int q = tile * GC_TILE + (dt & 63);
         const int py = q / w, px = q - py * w;
@@ -366,8 +379,8 @@ __device__ __forceinline__ void gc_sample(const GaArgs &a, const GcParams &P) {
     if (dt == 0) GC_STAMP(3, 15);
     float vmax = 0.f;
     for (int m = 0; m < nchunks; ++m) {
-      const int it = ntiles + m / cps, s = it % GC_SLOTS;
-      if (m % cps == 0) mbar_wait(bar_full + 8 * s, (it / GC_SLOTS) & 1);
+      const int it = ntiles + m / cps, s = it % NS;
+      if (m % cps == 0) mbar_wait(bar_full + 8 * s, (it / NS) & 1);
       const float *ck = reinterpret_cast<const float *>(gen + (size_t)s * tile_bytes + (size_t)(m % cps) * GC_CHUNK_BYTES);
 #pragma unroll
       for (int u = 0; u < GC_CHUNK_PX / 128; ++u) {
@@ -546,22 +559,33 @@ __global__ void __launch_bounds__(256) build_images_kernel(const float *__restri
                 hw, item);
 }
 
-static size_t gc_smem_bytes(int c, int h, int w) {
+static size_t gc_fixed_smem(int h, int w) {
   const size_t npad = (size_t)(h + 2) * (w + 2);
-  return 1024 + (size_t)GC_SLOTS * 2 * c * 128 + 2 * GC_VSLOT_BYTES + 2 * npad * 4 + 16 + 8 * GC_NBARS + 32 + 16;
+  return 1024 + 2 * GC_VSLOT_BYTES + 2 * npad * 4 + 16 + 8 * GC_NBARS + 32 + 16;
+}
+// Ring depth: measured on B200 (3 objects x 69 samples at 30x54) two CTAs per SM with 3 slots each (0.37 ms per update)
+// beat one CTA per SM with 8 slots (0.48 ms): a sample's phases are serialised by the role hand-offs, not by load
+// latency, so a second resident sample hides more than a deeper ring does.
+constexpr int GC_RING_SLOTS = 3;
+static int gc_slots(int c, int h, int w) {
+  const size_t tile = (size_t)2 * c * 128;
+  const size_t fixed = gc_fixed_smem(h, w);
+  if (fixed + 3 * tile > 227 * 1024) return 0;
+  const int s = (int)((227 * 1024 - fixed) / tile);
+  return s > GC_RING_SLOTS ? GC_RING_SLOTS : s;
 }
 
 bool gn_apply_tc_supported(int c, int h, int w) {
   // the stencil chunks travel through the tile ring, so a tile slot must hold one (c >= 40); p is staged in registers
-  return c % 16 == 0 && c >= 48 && c * 9 <= 6 * GC_THREADS && c * 9 <= 1024 && c <= 128 && w < 65536 && gc_smem_bytes(c, h, w) <= 227 * 1024;
+  return c % 16 == 0 && c >= 48 && c * 9 <= 6 * GC_THREADS && c * 9 <= 1024 && c <= 128 && w < 65536 && gc_slots(c, h, w) >= 3;
 }
 
 int gn_apply_tc_launch(const GaArgs &a, const GcFuse &fuse, cudaStream_t st) {
   GcParams P;
   const int hw = a.h * a.w;
-  P.ntiles = gc_ntiles(hw); P.nchunks = gc_nchunks(hw); P.tile_bytes = 2 * a.c * 128;
+  P.ntiles = gc_ntiles(hw); P.nchunks = gc_nchunks(hw); P.tile_bytes = 2 * a.c * 128; P.slots = gc_slots(a.c, a.h, a.w);
   P.image_bytes = gc_sample_bytes(a.c, hw);
-  const size_t smem = gc_smem_bytes(a.c, a.h, a.w);
+  const size_t smem = gc_fixed_smem(a.h, a.w) + (size_t)P.slots * P.tile_bytes;
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(gn_apply_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -30,12 +30,14 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 // Bounded wait: a protocol bug must surface as a trapped launch, not as a hung GPU.
+// Pure polling with test_wait: try_wait may suspend the thread for an implementation-defined time slice, which adds
+// a fraction of a microsecond to every producer/consumer hand-off — and the hand-off chains are what bound these kernels.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
-  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+  for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
     asm volatile(
         "{\n.reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
         "selp.u32 %0, 1, 0, p;\n}"
         : "=r"(done)
         : "r"(bar), "r"(parity)
