@@ -53,188 +53,53 @@ struct TcArgs {
 // ----------------------------------------------------------------------------------------------------------------
 // kernel: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue (warp 2 owns the TMEM allocation)
 // ----------------------------------------------------------------------------------------------------------------
-// PACK: issue the passes as A_hi x [B_hi | B_lo] (N = 2*BN) + A_lo x B_hi — needs 4*BN TMEM columns; tiles whose
-// 4*BN would push the allocation to all 512 columns (one CTA per SM) keep the three separate N = BN products.
-// R1 / TAP: epilogue features compiled in only where used (rank-1 score channel; tap-map contraction) — the unrolled
-// epilogue is most of the kernel's code, and the plain instances must not pay for them in instruction-cache misses.
-template <int BN, int STAGES, bool R1, bool TAP>
-__global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi,
-                                                      const __grid_constant__ CUtensorMap tm_lo, const TcArgs a) {
-  constexpr int B_BYTES = BN * 128;
-  constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
-  constexpr bool PACK = (4 * BN <= 256) || BN == 128;
-  constexpr int SLOT = PACK ? 2 * BN : BN;     // accumulator slot: [hi*hi + lo*hi | hi*lo] or one sum
-  constexpr int COLS = tmem_cols(2 * SLOT);    // two accumulator slots
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t bar_full = base + STAGES * STAGE_BYTES;       // STAGES x 8 B
-  const uint32_t bar_empty = bar_full + 8 * STAGES;
-  const uint32_t bar_accf = bar_empty + 8 * STAGES;            // 2 x 8 B: accumulator slot full
-  const uint32_t bar_acce = bar_accf + 16;                     // 2 x 8 B: accumulator slot drained
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gen + STAGES * STAGE_BYTES + 16 * STAGES + 32);
-
-  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
-  const int tiles_per_img = a.tiles_x * a.tiles_y;
-  const int b = blockIdx.x / tiles_per_img;
-  const int tr = blockIdx.x - b * tiles_per_img;
-  const int y0 = (tr / a.tiles_x) * TC_TH, x0 = (tr % a.tiles_x) * TC_TW;
-  const int ntile = blockIdx.y;
-  const int ntaps = a.kh * a.kw;
-  const int nkb = ntaps * a.kchunks;
-
-  if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_hi)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_lo)) : "memory");
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
-    }
-    for (int j = 0; j < 2; ++j) {
-      mbar_init(bar_accf + 8 * j, 1);
-      mbar_init(bar_acce + 8 * j, 4);      // one arrive per epilogue warp
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+// ----------------------------------------------------------------------------------------------------------------
+// epilogue pieces shared by the tensor-core conv kernels (threads 64..191 = the four epilogue warps)
+// ----------------------------------------------------------------------------------------------------------------
+// shared-memory staging of the per-channel scale / bias (and the optional rank-1 / tap weights) of N tile n0
+template <int BN, bool R1, bool TAP>
+__device__ __forceinline__ void tc_epilogue_stage(const TcArgs &a, int n0, float *s_osc) {
+  float *s_bias = s_osc + BN;
+  float *s_tap = s_bias + BN;             // [9][BN]
+  float *s_r1 = s_tap + 9 * BN;           // [10][BN]: rank-1 weights of the 9 taps, then the bias that follows them
+  for (int i = threadIdx.x - 64; i < BN; i += 128) {
+    s_osc[i] = a.oscale[n0 + i];
+    s_bias[i] = (a.bias != nullptr && n0 + i < a.Cout) ? a.bias[n0 + i] : 0.f;
   }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if constexpr (TAP) {
+    for (int i = threadIdx.x - 64; i < 9 * BN; i += 128) {
+      const int t = i / BN, ch = i - t * BN;
+      s_tap[i] = (n0 + ch < a.Cout) ? a.tapw[t * a.Cout + n0 + ch] : 0.f;
+    }
   }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  if constexpr (R1) {
+    for (int i = threadIdx.x - 64; i < 10 * BN; i += 128) {
+      const int t = i / BN, ch = i - t * BN;
+      float v = 0.f;
+      if (n0 + ch < a.Cout) v = t < 9 ? a.r1_w[t * a.Cout + n0 + ch] : (a.r1_bias ? a.r1_bias[n0 + ch] : 0.f);
+      s_r1[i] = v;
+    }
+  }
+}
 
-  // Producer and MMA warps walk their loops converged and issue through one elected lane (elect.sync): control flow and
-  // descriptor arithmetic stay warp-uniform, so the TMA / tcgen05 instructions are issued back to back from uniform
-  // registers instead of through the per-lane serialisation loops an `if (lane == 0)` region compiles to.
-  if (warp == 0) {
-    {
-      const __half *wbase = a.wt + (size_t)ntile * nkb * (2 * B_BYTES / 2);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(bar_empty + 8 * s, ph ^ 1);
-        const int tap = kb / a.kchunks, kc = kb - tap * a.kchunks;
-        const int ky = tap / a.kw, kx = tap - ky * a.kw;
-        const uint32_t sa = base + s * STAGE_BYTES;
-        if (elect_one()) {
-          mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
-          tma_load_4d(sa, &tm_hi, kc * TC_BK, x0 * a.stride + kx - a.pad, y0 * a.stride + ky - a.pad, b, bar_full + 8 * s);
-          tma_load_4d(sa + TC_A_BYTES, &tm_lo, kc * TC_BK, x0 * a.stride + kx - a.pad, y0 * a.stride + ky - a.pad, b, bar_full + 8 * s);
-          bulk_load(sa + 2 * TC_A_BYTES, wbase + (size_t)kb * (2 * B_BYTES / 2), 2 * B_BYTES, bar_full + 8 * s);
-        }
-        __syncwarp();
-      }
-    }
-  } else if (warp == 1) {
-    {
-      // per k-step:  D[0:2BN) (+)= A_hi x [B_hi | B_lo]  (one N = 2*BN product: the hi and lo weight rows are contiguous in
-      // the stage) and  D[0:BN) += A_lo x B_hi  — two reads of the A tile per k-step instead of three
-      constexpr uint32_t idesc = umma_idesc(128, BN), idesc2 = umma_idesc(128, 2 * BN);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(bar_full + 8 * s, ph);
-        tc_fence_after();
-        const int grp = kb / TC_FOLD, first = (kb % TC_FOLD) == 0;
-        const uint32_t slot = grp & 1;
-        if (first) {                        // the epilogue must have drained this slot (two groups ago)
-          mbar_wait(bar_acce + 8 * slot, ((grp >> 1) & 1) ^ 1);
-          tc_fence_after();
-        }
-        const uint32_t tacc = tmem_base + slot * SLOT;
-        const uint32_t sa = base + s * STAGE_BYTES;
-        const uint64_t a_hi = umma_desc(sa), a_lo = umma_desc(sa + TC_A_BYTES);
-        const uint64_t b_hl = umma_desc(sa + 2 * TC_A_BYTES), b_lo = umma_desc(sa + 2 * TC_A_BYTES + B_BYTES);
-        if (elect_one()) {
+// output pixel (b, py, px) with its BN accumulated channels: unscale, bias, rank-1 term, residual, ReLU, all outputs
+template <int BN, bool R1, bool TAP>
+__device__ __forceinline__ void tc_epilogue_store(const TcArgs &a, const float (&acc)[BN], int b, int py, int px, int n0,
+                                                  const float *s_osc) {
+  const float *s_bias = s_osc + BN;
+  const float *s_tap = s_bias + BN;
+  const float *s_r1 = s_tap + 9 * BN;
+  const bool valid = py < a.Ho && px < a.Wo;
+  const int64_t pix = ((int64_t)b * a.Ho + py) * a.Wo + px;
+  float sv[9];
+  if constexpr (R1) {
+    const float *sb = a.r1_score + (int64_t)b * a.Ho * a.Wo;
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {
-            const uint64_t adv = (uint64_t)(k * 32 >> 4);     // +32 bytes along K inside the swizzle atom
-            if (PACK) {
-              umma_f16(tacc, a_hi + adv, b_hl + adv, idesc2, (first && k == 0) ? 0u : 1u);
-              umma_f16(tacc, a_lo + adv, b_hl + adv, idesc, 1u);
-            } else {
-              umma_f16(tacc, a_hi + adv, b_hl + adv, idesc, (first && k == 0) ? 0u : 1u);
-              umma_f16(tacc, a_hi + adv, b_lo + adv, idesc, 1u);
-              umma_f16(tacc, a_lo + adv, b_hl + adv, idesc, 1u);
-            }
-          }
-          umma_commit(bar_empty + 8 * s);     // frees the stage once the MMAs above have consumed it
-          if ((kb % TC_FOLD) == TC_FOLD - 1 || kb == nkb - 1) umma_commit(bar_accf + 8 * slot);   // slot ready to fold
-        }
-        __syncwarp();
-      }
+    for (int t = 0; t < 9; ++t) {
+      const int yy = py + t / 3 - 1, xx = px + t % 3 - 1;
+      sv[t] = (valid && yy >= 0 && yy < a.Ho && xx >= 0 && xx < a.Wo) ? sb[yy * a.Wo + xx] : 0.f;
     }
-  } else {
-    // ---- epilogue: TMEM lane = tile row = pixel; a warp may only touch lanes 32*(warp%4) .. +31 ----
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int py = y0 + row / TC_TW, px = x0 + row % TC_TW;
-    const bool valid = py < a.Ho && px < a.Wo;
-    const int64_t pix = ((int64_t)b * a.Ho + py) * a.Wo + px;
-    const int n0 = ntile * BN;
-    // per-channel output scale and bias staged once per CTA (overlaps the main loop)
-    float *s_osc = reinterpret_cast<float *>(gen + STAGES * STAGE_BYTES + 16 * STAGES + 48);
-    float *s_bias = s_osc + BN;
-    float *s_tap = s_bias + BN;             // [9][BN]
-    for (int i = threadIdx.x - 64; i < BN; i += 128) {
-      s_osc[i] = a.oscale[n0 + i];
-      s_bias[i] = (a.bias != nullptr && n0 + i < a.Cout) ? a.bias[n0 + i] : 0.f;
-    }
-    if constexpr (TAP) {
-      for (int i = threadIdx.x - 64; i < 9 * BN; i += 128) {
-        const int t = i / BN, ch = i - t * BN;
-        s_tap[i] = (n0 + ch < a.Cout) ? a.tapw[t * a.Cout + n0 + ch] : 0.f;
-      }
-    }
-    float *s_r1 = s_tap + 9 * BN;           // [10][BN]: rank-1 weights of the 9 taps, then the bias that follows them
-    float sv[9];
-    if constexpr (R1) {
-      for (int i = threadIdx.x - 64; i < 10 * BN; i += 128) {
-        const int t = i / BN, ch = i - t * BN;
-        float v = 0.f;
-        if (n0 + ch < a.Cout) v = t < 9 ? a.r1_w[t * a.Cout + n0 + ch] : (a.r1_bias ? a.r1_bias[n0 + ch] : 0.f);
-        s_r1[i] = v;
-      }
-      const float *sb = a.r1_score + (int64_t)b * a.Ho * a.Wo;
-#pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const int yy = py + t / 3 - 1, xx = px + t % 3 - 1;
-        sv[t] = (valid && yy >= 0 && yy < a.Ho && xx >= 0 && xx < a.Wo) ? sb[yy * a.Wo + xx] : 0.f;
-      }
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    // fold every finished accumulator slot into fp32 registers (round-to-nearest adds)
-    float acc[BN];
-#pragma unroll
-    for (int j = 0; j < BN; ++j) acc[j] = 0.f;
-    const int ngrp = (nkb + TC_FOLD - 1) / TC_FOLD;
-#pragma unroll 1
-    for (int grp = 0; grp < ngrp; ++grp) {
-      const uint32_t slot = grp & 1;
-      mbar_wait(bar_accf + 8 * slot, (grp >> 1) & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        float t[16];
-        const uint32_t col = tmem_base + ((uint32_t)(q * 32) << 16) + slot * SLOT + (uint32_t)c0;
-        tmem_ld16(col, t);
-        if (PACK) {
-          float t2[16];
-          tmem_ld16(col + BN, t2);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) acc[c0 + j] += t[j] + t2[j];
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) acc[c0 + j] += t[j];
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_acce + 8 * slot) : "memory");
-    }
+  }
     const bool vec_f32 = (a.ldy % 4 == 0) && (a.y_coff % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 15) == 0);
     const bool vec_res = (a.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.res) & 15) == 0);
     const bool vec_h = (a.ldyh % 8 == 0) && (a.yh_coff % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.y_hi) & 15) == 0) &&
@@ -354,6 +219,348 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
       o[0] = make_float4(tp[0], tp[1], tp[2], tp[3]);
       o[1] = make_float4(tp[4], tp[5], tp[6], tp[7]);
       o[2] = make_float4(tp[8], 0.f, 0.f, 0.f);
+    }
+}
+
+// PACK: issue the passes as A_hi x [B_hi | B_lo] (N = 2*BN) + A_lo x B_hi — needs 4*BN TMEM columns; tiles whose
+// 4*BN would push the allocation to all 512 columns (one CTA per SM) keep the three separate N = BN products.
+// R1 / TAP: epilogue features compiled in only where used (rank-1 score channel; tap-map contraction) — the unrolled
+// epilogue is most of the kernel's code, and the plain instances must not pay for them in instruction-cache misses.
+template <int BN, int STAGES, bool R1, bool TAP>
+__global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi,
+                                                      const __grid_constant__ CUtensorMap tm_lo, const TcArgs a) {
+  constexpr int B_BYTES = BN * 128;
+  constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
+  constexpr bool PACK = (4 * BN <= 256) || BN == 128;
+  constexpr int SLOT = PACK ? 2 * BN : BN;     // accumulator slot: [hi*hi + lo*hi | hi*lo] or one sum
+  constexpr int COLS = tmem_cols(2 * SLOT);    // two accumulator slots
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar_full = base + STAGES * STAGE_BYTES;       // STAGES x 8 B
+  const uint32_t bar_empty = bar_full + 8 * STAGES;
+  const uint32_t bar_accf = bar_empty + 8 * STAGES;            // 2 x 8 B: accumulator slot full
+  const uint32_t bar_acce = bar_accf + 16;                     // 2 x 8 B: accumulator slot drained
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gen + STAGES * STAGE_BYTES + 16 * STAGES + 32);
+
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  const int tiles_per_img = a.tiles_x * a.tiles_y;
+  const int b = blockIdx.x / tiles_per_img;
+  const int tr = blockIdx.x - b * tiles_per_img;
+  const int y0 = (tr / a.tiles_x) * TC_TH, x0 = (tr % a.tiles_x) * TC_TW;
+  const int ntile = blockIdx.y;
+  const int ntaps = a.kh * a.kw;
+  const int nkb = ntaps * a.kchunks;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_hi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_lo)) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int j = 0; j < 2; ++j) {
+      mbar_init(bar_accf + 8 * j, 1);
+      mbar_init(bar_acce + 8 * j, 4);      // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // Producer and MMA warps walk their loops converged and issue through one elected lane (elect.sync): control flow and
+  // descriptor arithmetic stay warp-uniform, so the TMA / tcgen05 instructions are issued back to back from uniform
+  // registers instead of through the per-lane serialisation loops an `if (lane == 0)` region compiles to.
+  if (warp == 0) {
+    {
+      const __half *wbase = a.wt + (size_t)ntile * nkb * (2 * B_BYTES / 2);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        const int tap = kb / a.kchunks, kc = kb - tap * a.kchunks;
+        const int ky = tap / a.kw, kx = tap - ky * a.kw;
+        const uint32_t sa = base + s * STAGE_BYTES;
+        if (elect_one()) {
+          mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
+          tma_load_4d(sa, &tm_hi, kc * TC_BK, x0 * a.stride + kx - a.pad, y0 * a.stride + ky - a.pad, b, bar_full + 8 * s);
+          tma_load_4d(sa + TC_A_BYTES, &tm_lo, kc * TC_BK, x0 * a.stride + kx - a.pad, y0 * a.stride + ky - a.pad, b, bar_full + 8 * s);
+          bulk_load(sa + 2 * TC_A_BYTES, wbase + (size_t)kb * (2 * B_BYTES / 2), 2 * B_BYTES, bar_full + 8 * s);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    {
+      // per k-step:  D[0:2BN) (+)= A_hi x [B_hi | B_lo]  (one N = 2*BN product: the hi and lo weight rows are contiguous in
+      // the stage) and  D[0:BN) += A_lo x B_hi  — two reads of the A tile per k-step instead of three
+      constexpr uint32_t idesc = umma_idesc(128, BN), idesc2 = umma_idesc(128, 2 * BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(bar_full + 8 * s, ph);
+        tc_fence_after();
+        const int grp = kb / TC_FOLD, first = (kb % TC_FOLD) == 0;
+        const uint32_t slot = grp & 1;
+        if (first) {                        // the epilogue must have drained this slot (two groups ago)
+          mbar_wait(bar_acce + 8 * slot, ((grp >> 1) & 1) ^ 1);
+          tc_fence_after();
+        }
+        const uint32_t tacc = tmem_base + slot * SLOT;
+        const uint32_t sa = base + s * STAGE_BYTES;
+        const uint64_t a_hi = umma_desc(sa), a_lo = umma_desc(sa + TC_A_BYTES);
+        const uint64_t b_hl = umma_desc(sa + 2 * TC_A_BYTES), b_lo = umma_desc(sa + 2 * TC_A_BYTES + B_BYTES);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);     // +32 bytes along K inside the swizzle atom
+            if (PACK) {
+              umma_f16(tacc, a_hi + adv, b_hl + adv, idesc2, (first && k == 0) ? 0u : 1u);
+              umma_f16(tacc, a_lo + adv, b_hl + adv, idesc, 1u);
+            } else {
+              umma_f16(tacc, a_hi + adv, b_hl + adv, idesc, (first && k == 0) ? 0u : 1u);
+              umma_f16(tacc, a_hi + adv, b_lo + adv, idesc, 1u);
+              umma_f16(tacc, a_lo + adv, b_hl + adv, idesc, 1u);
+            }
+          }
+          umma_commit(bar_empty + 8 * s);     // frees the stage once the MMAs above have consumed it
+          if ((kb % TC_FOLD) == TC_FOLD - 1 || kb == nkb - 1) umma_commit(bar_accf + 8 * slot);   // slot ready to fold
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ---- epilogue: TMEM lane = tile row = pixel; a warp may only touch lanes 32*(warp%4) .. +31 ----
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int py = y0 + row / TC_TW, px = x0 + row % TC_TW;
+    const int n0 = ntile * BN;
+    // per-channel output scale and bias (and the optional rank-1 / tap weights) staged once per CTA (overlaps the main loop)
+    float *s_osc = reinterpret_cast<float *>(gen + STAGES * STAGE_BYTES + 16 * STAGES + 48);
+    tc_epilogue_stage<BN, R1, TAP>(a, n0, s_osc);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    // fold every finished accumulator slot into fp32 registers (round-to-nearest adds)
+    float acc[BN];
+#pragma unroll
+    for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+    const int ngrp = (nkb + TC_FOLD - 1) / TC_FOLD;
+#pragma unroll 1
+    for (int grp = 0; grp < ngrp; ++grp) {
+      const uint32_t slot = grp & 1;
+      mbar_wait(bar_accf + 8 * slot, (grp >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        float t[16];
+        const uint32_t col = tmem_base + ((uint32_t)(q * 32) << 16) + slot * SLOT + (uint32_t)c0;
+        tmem_ld16(col, t);
+        if (PACK) {
+          float t2[16];
+          tmem_ld16(col + BN, t2);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[c0 + j] += t[j] + t2[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[c0 + j] += t[j];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_acce + 8 * slot) : "memory");
+    }
+    tc_epilogue_store<BN, R1, TAP>(a, acc, b, py, px, n0, s_osc);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(COLS) : "memory");
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// 3x3 stride-1 convolution with 64 input channels — the shape of every 3x3 conv of the refinement network and of the
+// first backbone stage, i.e. most of the conv time at 480p.  The general kernel above is bound by L2 -> shared-memory
+// operand traffic (every CTA re-fetches each tap's shifted A tile and all the weights: 48 KB per 128x64x64 product,
+// 10.5 TB/s measured).  Here
+//   * the weights of all 9 taps (hi + lo planes, 9 x 2 x BN x 128 B) are fetched ONCE per CTA and stay in shared memory;
+//     the CTA is persistent and walks output tiles with stride gridDim.x;
+//   * an output tile is 16 rows x 8 pixels, and its input arrives as three column-shifted SLABS (dx = 0,1,2) of
+//     18 rows x 8 pixels x 64 channels: with 8-pixel rows a vertical shift dy is a shift by exactly one 1024-byte
+//     swizzle atom, so the three vertical taps of a slab are three UMMA descriptors into the same bytes.
+// 110 KB of A per tile instead of 295 KB, no weight traffic in the steady state.  Accumulation, fold and epilogue are
+// those of the general kernel (packed hi|lo products, TC_FOLD taps per TMEM slot, fp32 register fold).
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int S3_TH = 16, S3_TW = 8;
+constexpr int S3_SLAB_BYTES = (S3_TH + 2) * S3_TW * 128;      // one plane of one slab: 18 rows x 8 px x 64 ch fp16
+constexpr int S3_STAGES = 2;
+constexpr int S3_FOLD = 3;                                     // taps per TMEM slot = one slab (K = 192 per product)
+constexpr int S3_THREADS = 64 + 2 * 128;                       // producer warp, MMA warp, two epilogue groups of 4 warps
+constexpr int S3_NBAR = 2 * S3_STAGES + 8 + 1;
+
+// The epilogue of a tile (three TMEM folds + scale / bias / residual / ReLU + the stores) takes longer than its MMAs, and
+// a persistent CTA has no second resident CTA to hide it behind: two epilogue groups take alternate tiles, each with
+// its own pair of accumulator slots, so the tensor core runs one tile ahead of the stores.
+template <int BN, bool R1, bool TAP>
+__global__ void __launch_bounds__(S3_THREADS, 1) conv_tc3_kernel(const __grid_constant__ CUtensorMap tm_hi,
+                                                                 const __grid_constant__ CUtensorMap tm_lo, const TcArgs a) {
+  constexpr int B_BYTES = BN * 128;
+  constexpr int W_BYTES = 9 * 2 * B_BYTES;
+  constexpr int STAGE_BYTES = 2 * S3_SLAB_BYTES;
+  constexpr int SLOT = 2 * BN;
+  constexpr int COLS = tmem_cols(4 * SLOT);                      // 2 groups x 2 slots
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t wsm = base;                                     // weights [tap][hi|lo][BN x 128 B]
+  const uint32_t slabs = base + W_BYTES;                         // S3_STAGES x [hi|lo] slab
+  constexpr int TAIL = W_BYTES + S3_STAGES * STAGE_BYTES;
+  const uint32_t bar_full = base + TAIL;                         // S3_STAGES x 8 B
+  const uint32_t bar_empty = bar_full + 8 * S3_STAGES;
+  const uint32_t bar_accf = bar_empty + 8 * S3_STAGES;           // [group][slot]: accumulator slot full
+  const uint32_t bar_acce = bar_accf + 32;                       // [group][slot]: accumulator slot drained
+  const uint32_t bar_w = bar_acce + 32;                          // weights landed
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gen + TAIL + 8 * S3_NBAR);
+  float *s_osc = reinterpret_cast<float *>(gen + TAIL + 8 * S3_NBAR + 16);
+
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  const int tiles_per_img = a.tiles_x * a.tiles_y;
+  const int ntiles = a.B * tiles_per_img;
+  constexpr int NGRP = 9 / S3_FOLD;                              // folds per tile
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_hi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_lo)) : "memory");
+    for (int s = 0; s < S3_STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int j = 0; j < 4; ++j) {
+      mbar_init(bar_accf + 8 * j, 1);
+      mbar_init(bar_acce + 8 * j, 4);      // one arrive per epilogue warp of the group
+    }
+    mbar_init(bar_w, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---- producer: the weights once, then three slabs per tile ----
+    if (elect_one()) {
+      mbar_expect_tx(bar_w, W_BYTES);
+#pragma unroll 1
+      for (int t = 0; t < 9; ++t)
+        bulk_load(wsm + t * 2 * B_BYTES, reinterpret_cast<const uint8_t *>(a.wt) + (size_t)t * 2 * B_BYTES, 2 * B_BYTES, bar_w);
+    }
+    __syncwarp();
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int b = tile / tiles_per_img, tr = tile - b * tiles_per_img;
+      const int y0 = (tr / a.tiles_x) * S3_TH, x0 = (tr % a.tiles_x) * S3_TW;
+      for (int dx = 0; dx < 3; ++dx, ++it) {
+        const int s = it % S3_STAGES;
+        mbar_wait(bar_empty + 8 * s, ((it / S3_STAGES) & 1) ^ 1);
+        const uint32_t sa = slabs + s * STAGE_BYTES;
+        if (elect_one()) {
+          mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
+          tma_load_4d(sa, &tm_hi, 0, x0 + dx - 1, y0 - 1, b, bar_full + 8 * s);
+          tma_load_4d(sa + S3_SLAB_BYTES, &tm_lo, 0, x0 + dx - 1, y0 - 1, b, bar_full + 8 * s);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer: per slab (dx) the three vertical taps, each 4 k-steps of the packed products, one TMEM slot ----
+    constexpr uint32_t idesc = umma_idesc(128, BN), idesc2 = umma_idesc(128, 2 * BN);
+    mbar_wait(bar_w, 0);
+    uint32_t it = 0, nt = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++nt) {
+      const uint32_t eg = nt & 1;                                // epilogue group of this tile
+      const uint32_t gc = (nt >> 1) * NGRP;                      // folds this group has seen before this tile
+      for (int dx = 0; dx < 3; ++dx, ++it) {
+        const int s = it % S3_STAGES;
+        const uint32_t grp = gc + dx, slot = grp & 1;
+        mbar_wait(bar_acce + 8 * (2 * eg + slot), ((grp >> 1) & 1) ^ 1);   // the group has drained this slot
+        tc_fence_after();
+        mbar_wait(bar_full + 8 * s, (it / S3_STAGES) & 1);
+        const uint64_t dA = umma_desc(slabs + s * STAGE_BYTES);
+        const uint32_t tacc = tmem_base + (2 * eg + slot) * SLOT;
+        if (elect_one()) {
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+            const uint64_t a_hi = dA + (uint64_t)(dy * 1024 >> 4), a_lo = a_hi + (uint64_t)(S3_SLAB_BYTES >> 4);
+            const uint64_t b_hl = umma_desc(wsm + (dy * 3 + dx) * 2 * B_BYTES);
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k) {
+              const uint64_t adv = (uint64_t)(k * 32 >> 4);
+              umma_f16(tacc, a_hi + adv, b_hl + adv, idesc2, (dy == 0 && k == 0) ? 0u : 1u);
+              umma_f16(tacc, a_lo + adv, b_hl + adv, idesc, 1u);
+            }
+          }
+          umma_commit(bar_empty + 8 * s);
+          umma_commit(bar_accf + 8 * (2 * eg + slot));
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ---- epilogue groups: warps 2-5 take the even tiles of this CTA, warps 6-9 the odd ones ----
+    const int eg = (warp - 2) >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    tc_epilogue_stage<BN, R1, TAP>(a, 0, s_osc);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    uint32_t nt = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++nt) {
+      if ((int)(nt & 1) != eg) continue;
+      const uint32_t gc = (nt >> 1) * NGRP;
+      const int b = tile / tiles_per_img, tr = tile - b * tiles_per_img;
+      const int y0 = (tr / a.tiles_x) * S3_TH, x0 = (tr % a.tiles_x) * S3_TW;
+      float acc[BN];
+#pragma unroll
+      for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+#pragma unroll 1
+      for (int g = 0; g < NGRP; ++g) {
+        const uint32_t grp = gc + g, slot = grp & 1;
+        mbar_wait(bar_accf + 8 * (2 * eg + slot), (grp >> 1) & 1);
+        tc_fence_after();
+        const uint32_t col0 = tmem_base + ((uint32_t)(q * 32) << 16) + (2 * eg + slot) * SLOT;
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          if (c0 + 32 <= BN) {
+            float t[32], t2[32];
+            tmem_ld32(col0 + c0, t);
+            tmem_ld32(col0 + BN + c0, t2);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[c0 + j] += t[j] + t2[j];
+          } else {
+            float t[16], t2[16];
+            tmem_ld16(col0 + c0, t);
+            tmem_ld16(col0 + BN + c0, t2);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[c0 + j] += t[j] + t2[j];
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_acce + 8 * (2 * eg + slot)) : "memory");
+      }
+      tc_epilogue_store<BN, R1, TAP>(a, acc, b, y0 + row / S3_TW, x0 + row % S3_TW, 0, s_osc);
     }
   }
   tc_fence_before();
@@ -518,13 +725,14 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-static int make_act_map(CUtensorMap *tm, const __half *ptr, int B, int H, int W, int C, int ld, int stride) {
+static int make_act_map(CUtensorMap *tm, const __half *ptr, int B, int H, int W, int C, int ld, int stride, int box_w = 0,
+                        int box_h = 0) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("conv_tc: cuTensorMapEncodeTiled entry point not available"); return FRTM_ELAUNCH; }
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
   // with a traversal stride s the box spans TW*s x TH*s input pixels and TMA keeps every s-th one (ceil(box/s) elements)
-  cuuint32_t box[4] = {TC_BK, (cuuint32_t)(TC_TW * stride), (cuuint32_t)(TC_TH * stride), 1};
+  cuuint32_t box[4] = {TC_BK, (cuuint32_t)(box_w ? box_w : TC_TW * stride), (cuuint32_t)(box_h ? box_h : TC_TH * stride), 1};
   cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half *>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -547,9 +755,33 @@ static int launch_tc(const CUtensorMap &mh, const CUtensorMap &ml, const TcArgs 
   return FRTM_OK;
 }
 
+template <int BN, bool R1, bool TAP>
+static int launch_tc3(const CUtensorMap &mh, const CUtensorMap &ml, const TcArgs &a, cudaStream_t st) {
+  constexpr int smem = 9 * 2 * BN * 128 + S3_STAGES * 2 * S3_SLAB_BYTES + 8 * S3_NBAR + 16 + 84 * BN + 1024;
+  static_assert(smem <= 227 * 1024, "conv_tc3: shared memory budget");
+  static bool configured = false;
+  static int num_sms = 0;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc3_kernel<BN, R1, TAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { set_error("conv_tc3: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return FRTM_ELAUNCH; }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+    configured = true;
+  }
+  const int ntiles = a.B * a.tiles_x * a.tiles_y;
+  conv_tc3_kernel<BN, R1, TAP><<<ntiles < num_sms ? ntiles : num_sms, S3_THREADS, smem, st>>>(mh, ml, a);
+  FRTM_CHECK_LAUNCH("conv_tc3");
+  return FRTM_OK;
+}
+
 }  // namespace frtm
 
 using namespace frtm;
+
+static bool g_conv_slab_enabled = true;
+/* Tests / A-B measurements: route the 3x3, 64-input-channel convs through the general kernel (0) or the slab kernel (1). */
+extern "C" int frtm_conv_tc_slab_enable(int on) { g_conv_slab_enabled = on != 0; return FRTM_OK; }
 
 extern "C" int frtm_split_f16(const float *x, int64_t npix, int C, int ldx, void *hi, void *lo, int ldh, void *stream) {
   FRTM_REQUIRE(x && hi && lo && C % 4 == 0 && ldx % 4 == 0 && ldh % 8 == 0, "split_f16: bad arguments");
@@ -576,10 +808,13 @@ extern "C" int frtm_conv2d_tc(const void *x_hi, const void *x_lo, int B, int H, 
   FRTM_REQUIRE((reinterpret_cast<uintptr_t>(x_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(x_lo) & 15) == 0 &&
                (reinterpret_cast<uintptr_t>(wt) & 15) == 0, "conv2d_tc: operands must be 16-byte aligned");
   FRTM_REQUIRE(!y_hi || (y_lo && ldyh % 2 == 0), "conv2d_tc: bad split output");
+  // 3x3 / stride 1 / 64 input channels / one N tile of 32 or 64: the slab kernel with resident weights
+  const bool slab3 = kh == 3 && stride == 1 && Cin == TC_BK && Cout <= bn_tile && (bn_tile == 64 || bn_tile == 32) &&
+                     !(y_tap && bn_tile != 32) && !(r1_score && bn_tile != 64) && g_conv_slab_enabled;
   CUtensorMap mh, ml;
-  int rc = make_act_map(&mh, (const __half *)x_hi, B, H, W, Cin, ldx, stride);
+  int rc = make_act_map(&mh, (const __half *)x_hi, B, H, W, Cin, ldx, stride, slab3 ? S3_TW : 0, slab3 ? S3_TH + 2 : 0);
   if (rc) return rc;
-  rc = make_act_map(&ml, (const __half *)x_lo, B, H, W, Cin, ldx, stride);
+  rc = make_act_map(&ml, (const __half *)x_lo, B, H, W, Cin, ldx, stride, slab3 ? S3_TW : 0, slab3 ? S3_TH + 2 : 0);
   if (rc) return rc;
   TcArgs a;
   a.wt = (const __half *)wt; a.oscale = oscale; a.bias = bias; a.res = res; a.res_hi = (const __half *)res_hi;
@@ -596,6 +831,11 @@ extern "C" int frtm_conv2d_tc(const void *x_hi, const void *x_lo, int B, int H, 
   cudaStream_t st = (cudaStream_t)stream;
   const bool r1 = r1_score != nullptr, tap = y_tap != nullptr;
   FRTM_REQUIRE(!(r1 && tap), "conv2d_tc: rank-1 input and tap-map output cannot be combined");
+  if (slab3) {
+    a.tiles_x = cdiv(a.Wo, S3_TW); a.tiles_y = cdiv(a.Ho, S3_TH);
+    if (bn_tile == 64) return r1 ? launch_tc3<64, true, false>(mh, ml, a, st) : launch_tc3<64, false, false>(mh, ml, a, st);
+    return tap ? launch_tc3<32, false, true>(mh, ml, a, st) : launch_tc3<32, false, false>(mh, ml, a, st);
+  }
   FRTM_REQUIRE(!r1 || bn_tile == 64 || bn_tile == 80, "conv2d_tc: the rank-1 score channel is built for N tiles 64 and 80");
   FRTM_REQUIRE(!tap || bn_tile == 32, "conv2d_tc: the tap-map output is built for the N tile 32");
   FRTM_REQUIRE(r1 || !y_extra, "conv2d_tc: y_extra needs the rank-1 epilogue");

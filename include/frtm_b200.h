@@ -93,6 +93,9 @@ int frtm_conv2d_tc(const void *x_hi, const void *x_lo, int B, int H, int W, int 
  * W (Cout,Cin) fp32 -> wt / oscale in the layout frtm_conv2d_tc expects (wt: cout_pad*Cin*2 halves, oscale: cout_pad). */
 int frtm_pack_tc_1x1(const float *W, int Cout, int Cin, int bn_tile, void *wt, float *oscale, void *stream);
 /* fp32 NHWC (npix, ldx)[0,C) -> fp16 planes hi, lo with hi + lo = 16 * x  (channel stride ldh, ldh % 8 == 0). */
+/* Tests / A-B measurements: route 3x3, stride-1, 64-input-channel convs through the slab kernel with resident weights
+ * (1, default) or through the general kernel (0). */
+int frtm_conv_tc_slab_enable(int on);
 int frtm_split_f16(const float *x, int64_t npix, int C, int ldx, void *hi, void *lo, int ldh, void *stream);
 
 /* Completes a 3x3 conv over cat(64 channels, score) (TSE.transform, seg_network.py:15,19-20) after frtm_conv2d_tc has

@@ -158,3 +158,37 @@ def test_conv2d_tc_tap_contraction_in_epilogue():
     assert float(o["tap"][..., 9:].abs().max()) == 0.0
     only = ops.conv2d_tc(xs, pc, relu=True, out_f32=False, tapw=w9c)
     assert only["y"] is None and torch.equal(only["tap"], o["tap"])
+
+
+@pytest.mark.parametrize("cout,hw,B", [(64, (8, 16), 1), (64, (30, 54), 2), (64, (37, 29), 3), (32, (40, 44), 1), (64, (120, 214), 24)])
+def test_slab_kernel_matches_general_kernel(cout, hw, B):
+    """3x3 / stride 1 / 64 input channels: the persistent slab kernel (resident weights, column-shifted slabs) against
+    the general tensor-core kernel and against fp32 conv2d; more tiles than SMs in the last case."""
+    from frtm_vos_b200 import ops
+    from frtm_vos_b200._lib import lib
+    g = torch.Generator().manual_seed(cout + hw[0])
+    x = torch.randn(B, 64, *hw, generator=g)
+    w = torch.randn(cout, 64, 3, 3, generator=g) / 24
+    b = torch.randn(cout, generator=g)
+    res = torch.randn(B, cout, *hw, generator=g)
+    xs = ops.split_f16(_nhwc(x).to(DEV))
+    pc = ops.pack_conv_tc(w, b, device=DEV)
+    rs = _nhwc(res).to(DEV)
+    out = {}
+    for on in (1, 0):
+        lib().conv_tc_slab_enable(on)
+        try:
+            o = ops.conv2d_tc(xs, pc, res=rs, relu=True, out_split=True, nchw=(B <= 3))
+            torch.cuda.synchronize()
+        finally:
+            lib().conv_tc_slab_enable(1)
+        out[on] = o
+    if B <= 3:
+        ref = F.relu(F.conv2d(x, w, b, 1, 1) + res)
+        scale = max(1.0, ref.abs().max().item())
+        assert (_nchw(out[1]["y"].cpu()) - ref).abs().max().item() < 1e-5 * scale
+        assert (out[1]["nchw"].cpu() - ref).abs().max().item() < 1e-5 * scale
+    scale = max(1.0, out[0]["y"].abs().max().item())
+    assert (out[1]["y"] - out[0]["y"]).abs().max().item() < 4e-6 * scale
+    d = (out[1]["split"].hi.float() + out[1]["split"].lo.float()) - (out[0]["split"].hi.float() + out[0]["split"].lo.float())
+    assert d.abs().max().item() / 16.0 < 4e-6 * scale
