@@ -20,6 +20,47 @@ __global__ void normalize_kernel(const uint8_t *__restrict__ img, int64_t HW, in
   out[i] = v;
 }
 
+// ---------------------------------------------------------------- stem patches --------------------------------
+// im2col of the 7x7 / stride-2 / pad-3 stem on the normalised image, written directly as the split fp16 planes of a
+// (B,Ho,Wo,192) tensor with k = ky*24 + c*8 + kx (kx = 7 and k >= 168 are zero): every (ky, c) row of a patch is one
+// aligned 16-byte chunk of 7 consecutive input bytes.  The stem then runs as a 1x1 tensor-core conv with K = 192
+// (weights permuted the same way) instead of 7.7 GMAC of fp32 CUDA-core FMAs per 8 frames.
+// One thread = one chunk (one 16-byte store per plane).
+__global__ void __launch_bounds__(256) stem_patches_kernel(const uint8_t *__restrict__ img, int B, int H, int W, int Ho, int Wo,
+                                                           __half *__restrict__ hi, __half *__restrict__ lo, float s0, float s1,
+                                                           float s2, float b0, float b1, float b2) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)B * Ho * Wo * 24;
+  if (i >= total) return;
+  const int j = (int)(i % 24);
+  const int64_t pix = i / 24;
+  const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho);
+  const int b = (int)(pix / ((int64_t)Wo * Ho));
+  __align__(16) __half hh[8];
+  __align__(16) __half ll[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { hh[e] = __float2half_rn(0.f); ll[e] = hh[e]; }
+  const int ky = j / 3, c = j - ky * 3;
+  const int iy = 2 * oy + ky - 3;
+  if (j < 21 && iy >= 0 && iy < H) {
+    const float sc = c == 0 ? s0 : (c == 1 ? s1 : s2), bc = c == 0 ? b0 : (c == 1 ? b1 : b2);
+    const uint8_t *row = img + (((int64_t)b * 3 + c) * H + iy) * (int64_t)W;
+    const int ix0 = 2 * ox - 3;
+#pragma unroll
+    for (int kx = 0; kx < 7; ++kx) {
+      const int ix = ix0 + kx;
+      if (ix >= 0 && ix < W) {
+        // mul then add, separately rounded, exactly like  norm_weight * input.float() + norm_bias
+        const float v = __fadd_rn(__fmul_rn(sc, (float)row[ix]), bc) * 16.f;
+        hh[kx] = __float2half_rn(v);
+        ll[kx] = __float2half_rn(v - __half2float(hh[kx]));
+      }
+    }
+  }
+  *reinterpret_cast<uint4 *>(hi + pix * 192 + j * 8) = *reinterpret_cast<const uint4 *>(hh);
+  *reinterpret_cast<uint4 *>(lo + pix * 192 + j * 8) = *reinterpret_cast<const uint4 *>(ll);
+}
+
 // ---------------------------------------------------------------- max pool -------------------------------------
 __global__ void maxpool_kernel(const float *__restrict__ x, int B, int H, int W, int C, int Ho, int Wo,
                                float *__restrict__ y, float *__restrict__ y_nchw) {
@@ -454,48 +495,75 @@ __global__ void __launch_bounds__(256) upsample_tapsum_kernel(const float *__res
     T[4][ry][rx] = a1.x; T[5][ry][rx] = a1.y; T[6][ry][rx] = a1.z; T[7][ry][rx] = a1.w;
     T[8][ry][rx] = a2.x;
   }
-  // own output pixels: rows tid/64 + 4k, column tid%64
+  // own output pixels: rows tid/64 + 4k, column tid%64.  The bilinear source indices / weights of the three horizontal
+  // and twelve vertical tap-shifted positions do not depend on the tap map: computed once, relative to the U window.
   const int lx = tid & 63, ly = tid >> 6;
+  int bx0[3], bx1[3];
+  float blx[3];
+  bool okx[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const int Xs = X0 + lx + d - 1;
+    okx[d] = Xs >= 0 && Xs < W && X0 + lx < W;
+    bilinear_src(min(max(Xs, 0), W - 1), sx, Wu, bx0[d], bx1[d], blx[d]);
+    bx0[d] -= ux_lo; bx1[d] -= ux_lo;
+  }
+  int by0[3][4], by1[3][4];
+  float bly[3][4];
+  bool oky[3][4];
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int Ys = Y0 + ly + 4 * k + d - 1;
+      oky[d][k] = Ys >= 0 && Ys < H;
+      bilinear_src(min(max(Ys, 0), H - 1), sy, Hu, by0[d][k], by1[d][k], bly[d][k]);
+      by0[d][k] -= uy_lo; by1[d][k] -= uy_lo;
+    }
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  // window geometry of the two bicubic passes: one item = one low-resolution sample position and the even / odd pair of
+  // upsampled positions (pre-crop indices 2n, 2n+1) that share its 4-tap window
+  const int n_lo = (ux_lo + 1) >> 1, n_cnt = ((ux_lo + nux) >> 1) - n_lo + 1;
+  const int m_lo = (uy_lo + 1) >> 1, m_cnt = ((uy_lo + nuy) >> 1) - m_lo + 1;
   __syncthreads();
+#pragma unroll
   for (int tap = 0; tap < 9; ++tap) {
-    // bicubic x2 along x: H1[ry][ux] = sum_kx wx[kx] T[ry][n - 2 + kx],  upsampled column uxg (cropped index) = 2n + rx - 1
-    for (int i = tid; i < nty * nux; i += 256) {
-      const int ry = i / nux, ux = i - ry * nux;
-      const int uxg = ux_lo + ux + 1;
-      const int n = uxg >> 1, odd = uxg & 1;
-      const float *row = &T[tap][ry][n - 2 - tx_lo];
-      H1[ry][ux] = odd ? (kCubicE[3] * row[0] + kCubicE[2] * row[1]) + (kCubicE[1] * row[2] + kCubicE[0] * row[3])
-                       : (kCubicE[0] * row[0] + kCubicE[1] * row[1]) + (kCubicE[2] * row[2] + kCubicE[3] * row[3]);
+    // bicubic x2 along x: H1[ry][ux] = sum_kx wx[kx] T[ry][n - 2 + kx],  upsampled column (cropped index) = 2n + rx - 1
+    for (int i = tid; i < nty * FT_NTX; i += 256) {
+      const int ry = i / FT_NTX, nn = i - ry * FT_NTX;
+      if (nn < n_cnt) {
+        const int n = n_lo + nn;
+        const float *row = &T[tap][ry][n - 2 - tx_lo];
+        const float r0 = row[0], r1 = row[1], r2 = row[2], r3 = row[3];
+        const int ue = 2 * n - 1 - ux_lo;                    // even pre-crop index 2n -> cropped 2n - 1
+        if (ue >= 0 && ue < nux) H1[ry][ue] = (kCubicE[0] * r0 + kCubicE[1] * r1) + (kCubicE[2] * r2 + kCubicE[3] * r3);
+        if (ue + 1 >= 0 && ue + 1 < nux) H1[ry][ue + 1] = (kCubicE[3] * r0 + kCubicE[2] * r1) + (kCubicE[1] * r2 + kCubicE[0] * r3);
+      }
     }
     __syncthreads();
     // ... and along y
-    for (int i = tid; i < nuy * nux; i += 256) {
-      const int uy = i / nux, ux = i - uy * nux;
-      const int uyg = uy_lo + uy + 1;
-      const int m = uyg >> 1, odd = uyg & 1;
-      const int r0 = m - 2 - ty_lo;
-      const float v0 = H1[r0][ux], v1 = H1[r0 + 1][ux], v2 = H1[r0 + 2][ux], v3 = H1[r0 + 3][ux];
-      U[uy][ux] = odd ? (kCubicE[3] * v0 + kCubicE[2] * v1) + (kCubicE[1] * v2 + kCubicE[0] * v3)
-                      : (kCubicE[0] * v0 + kCubicE[1] * v1) + (kCubicE[2] * v2 + kCubicE[3] * v3);
+    for (int i = tid; i < m_cnt * FT_UX; i += 256) {
+      const int mm = i / FT_UX, ux = i - mm * FT_UX;
+      if (ux < nux) {
+        const int m = m_lo + mm;
+        const int r0 = m - 2 - ty_lo;
+        const float v0 = H1[r0][ux], v1 = H1[r0 + 1][ux], v2 = H1[r0 + 2][ux], v3 = H1[r0 + 3][ux];
+        const int ue = 2 * m - 1 - uy_lo;
+        if (ue >= 0 && ue < nuy) U[ue][ux] = (kCubicE[0] * v0 + kCubicE[1] * v1) + (kCubicE[2] * v2 + kCubicE[3] * v3);
+        if (ue + 1 >= 0 && ue + 1 < nuy) U[ue + 1][ux] = (kCubicE[3] * v0 + kCubicE[2] * v1) + (kCubicE[1] * v2 + kCubicE[0] * v3);
+      }
     }
     __syncthreads();
     // bilinear to (H, W) at the tap-shifted position, accumulated per output pixel
-    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-    const int Xs = X0 + lx + dx;
-    if (Xs >= 0 && Xs < W && X0 + lx < W) {
-      int x0, x1;
-      float lx_;
-      bilinear_src(Xs, sx, Wu, x0, x1, lx_);
-      x0 -= ux_lo; x1 -= ux_lo;
+    const int dy = tap / 3, dx = tap - dy * 3;
+    if (okx[dx]) {
+      const int x0 = bx0[dx], x1 = bx1[dx];
+      const float lx_ = blx[dx];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int Ys = Y0 + ly + 4 * k + dy;
-        if (Ys >= 0 && Ys < H) {
-          int y0, y1;
-          float ly_;
-          bilinear_src(Ys, sy, Hu, y0, y1, ly_);
-          y0 -= uy_lo; y1 -= uy_lo;
+        if (oky[dy][k]) {
+          const int y0 = by0[dy][k], y1 = by1[dy][k];
+          const float ly_ = bly[dy][k];
           // ATen's order: (1-ly) * ((1-lx) a + lx b) + ly * ((1-lx) c + lx d)
           const float top = (1.f - lx_) * U[y0][x0] + lx_ * U[y0][x1];
           const float bot = (1.f - lx_) * U[y1][x0] + lx_ * U[y1][x1];
@@ -542,6 +610,23 @@ extern "C" int frtm_normalize_u8(const uint8_t *img, int B, int H, int W, float 
   normalize_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(img, HW, total, reinterpret_cast<float4 *>(out),
                                                                        s[0], s[1], s[2], b[0], b[1], b[2]);
   FRTM_CHECK_LAUNCH("normalize_u8");
+  return FRTM_OK;
+}
+
+extern "C" int frtm_stem_patches_u8(const uint8_t *img, int B, int H, int W, void *hi, void *lo, void *stream) {
+  FRTM_REQUIRE(img && hi && lo && B > 0 && H > 0 && W > 0, "stem_patches: bad arguments");
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+  float s[3], b[3];
+  for (int i = 0; i < 3; ++i) {        // same constants, rounded the same way, as frtm_normalize_u8
+    volatile float rcp = 1.0f / stdv[i];
+    s[i] = rcp * (float)(1.0 / 255.0);
+    b[i] = -mean[i] / stdv[i];
+  }
+  const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
+  const int64_t total = (int64_t)B * Ho * Wo * 24;
+  stem_patches_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(img, B, H, W, Ho, Wo, (__half *)hi, (__half *)lo, s[0], s[1],
+                                                                          s[2], b[0], b[1], b[2]);
+  FRTM_CHECK_LAUNCH("stem_patches");
   return FRTM_OK;
 }
 

@@ -58,7 +58,8 @@ class ResnetFeatureExtractor:
             raise RuntimeError("frtm_vos_b200 runs on CUDA (sm_100a) only; got device '%s'" % device)
         self.device = device
         sd, w = self._sd, {}
-        w["stem"] = ops.pack_conv(sd["conv1.weight"], bn=self._bn("bn1"), stride=2, pad=3, device=device)
+        # the 7x7/s2 stem as a 1x1 tensor-core conv over the im2col patches (K = 7 x 3 x 8 = 168 -> 192)
+        w["stem"] = ops.pack_conv_tc(ops.stem_weight_as_1x1(sd["conv1.weight"]), bn=self._bn("bn1"), device=device)
 
         def tc(conv_key, bn_key, stride=1):
             return ops.pack_conv_tc(sd[conv_key + ".weight"], bn=self._bn(bn_key), device=device, stride=stride)
@@ -87,15 +88,14 @@ class ResnetFeatureExtractor:
                       upto: str = "layer5"):
         """uint8 (B,3,H,W) -> ({layer: Split}, {layer: fp32 NHWC for f32_layers}, {layer: NCHW for nchw_layers}).
 
-        The 7x7/s2 stem (3 input channels) runs on the exact CUDA-core conv; every other conv — 1x1 and 3x3, stride 1
-        and 2 — is a tcgen05 tile with BatchNorm folded in, the residual read from the split planes and ReLU fused."""
+        Every conv is a tcgen05 tile with BatchNorm folded in, the residual read from the split planes and ReLU fused:
+        1x1 and 3x3, stride 1 and 2, directly; the 7x7/s2 stem as a 1x1 conv over its im2col patches (ops.stem_patches)."""
         if self.device is None:
             raise RuntimeError("call .to(device) first")
         require_cuda(images, "image")
         w = self._w
         split, f32, nchw = {}, {}, {}
-        x = ops.normalize_u8(images)
-        x = ops.conv2d(x, w["stem"], relu=True)
+        x = ops.conv2d_tc(ops.stem_patches(images), w["stem"], relu=True)["y"]
         if "layer1" in nchw_layers:
             x, nchw["layer1"] = ops.maxpool3x3s2(x, nchw=True)
         else:

@@ -108,6 +108,27 @@ def resize_bilinear(x: torch.Tensor, size, channels: Optional[int] = None, out: 
     return y
 
 
+def stem_weight_as_1x1(weight: torch.Tensor) -> torch.Tensor:
+    """conv1.weight (64,3,7,7) -> (64,192,1,1) in the k order of ``stem_patches``: k = ky*24 + c*8 + kx."""
+    cout = weight.shape[0]
+    w = torch.zeros(cout, 7, 3, 8, dtype=weight.dtype)
+    w[..., :7] = weight.detach().cpu().permute(0, 2, 1, 3)
+    out = torch.zeros(cout, 192, dtype=weight.dtype)
+    out[:, :168] = w.reshape(cout, 168)
+    return out.reshape(cout, 192, 1, 1)
+
+
+def stem_patches(images: torch.Tensor) -> "Split":
+    """uint8 (B,3,H,W) -> Split planes (B,Ho,Wo,192): the 7x7/s2/p3 patches of the normalised image (k = ky*24+c*8+kx)."""
+    B, C, H, W = images.shape
+    assert C == 3 and images.dtype == torch.uint8
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    sp = Split(torch.empty((B, Ho, Wo, 192), device=images.device, dtype=torch.float16),
+               torch.empty((B, Ho, Wo, 192), device=images.device, dtype=torch.float16), 192)
+    lib().stem_patches_u8(ptr(images.contiguous()), B, H, W, ptr(sp.hi), ptr(sp.lo), stream())
+    return sp
+
+
 def pyrup_bicubic(x: torch.Tensor, split: bool = False):
     """x2 bicubic pyramid upsample; ``split=True`` returns the result as ``Split`` planes (the next conv's input format)
     without ever writing the fp32 tensor."""

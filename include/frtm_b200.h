@@ -107,6 +107,10 @@ int frtm_rank1_finish(const float *y_in, int ldin, int n_obj, float *y_out, int 
                       float *extra, void *stream);
 
 /* 3x3 / stride 2 / pad 1 max pooling, NHWC (torchvision resnet.py maxpool; feature_extractor.py:53). */
+/* im2col of the 7x7 / stride-2 / pad-3 stem (torchvision resnet.py conv1) on the normalised image, as split fp16 planes
+ * (B,Ho,Wo,192) of 16*x: k = ky*24 + c*8 + kx (kx = 7 and k >= 168 are zero); Ho = (H-1)/2+1.  The stem is then a 1x1
+ * frtm_conv2d_tc with Cin = 192 and conv1.weight permuted the same way (frtm_vos_b200.ops.stem_weight_as_1x1). */
+int frtm_stem_patches_u8(const uint8_t *img, int B, int H, int W, void *hi, void *lo, void *stream);
 int frtm_maxpool3x3s2_nhwc(const float *x, int B, int H, int W, int C, float *y, float *y_nchw, void *stream);
 
 /* Bilinear resize (align_corners=False) of an NHWC tensor; writes C channels at offset y_coff of a tensor with

@@ -271,3 +271,26 @@ def test_pyrup_bicubic_split_planes():
     sp = ops.pyrup_bicubic(x, split=True)
     rec = (sp.hi.float() + sp.lo.float()) / 16.0
     assert (rec - y).abs().max() < 2e-6 * max(y.abs().max().item(), 1.0)
+
+
+@pytest.mark.parametrize("hw", [(64, 112), (33, 47), (480, 854)])
+def test_stem_as_tensor_core_conv_over_patches(hw):
+    """7x7/s2/p3 stem + folded BN + ReLU: im2col patches (frtm_stem_patches_u8) + 1x1 tcgen05 conv vs torch on the
+    normalised image (feature_extractor.py:27-32,42; torchvision resnet.py conv1/bn1/relu)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(hw[0])
+    B = 2
+    img = torch.randint(0, 256, (B, 3, *hw), generator=g, dtype=torch.uint8)
+    w = torch.randn(64, 3, 7, 7, generator=g) / 12
+    bn = dict(weight=torch.rand(64, generator=g) + 0.5, bias=torch.randn(64, generator=g) * 0.1,
+              running_mean=torch.randn(64, generator=g) * 0.1, running_var=torch.rand(64, generator=g) + 0.5)
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    x = img.float() * (1 / 255 / std) + (-mean / std)
+    y = F.conv2d(x.double(), w.double(), None, 2, 3)
+    sc = bn["weight"].double() / torch.sqrt(bn["running_var"].double() + 1e-5)
+    ref = torch.relu(y * sc.view(1, -1, 1, 1) + (bn["bias"].double() - bn["running_mean"].double() * sc).view(1, -1, 1, 1)).float()
+    pc = ops.pack_conv_tc(ops.stem_weight_as_1x1(w), bn=bn, device=DEV)
+    out = ops.conv2d_tc(ops.stem_patches(img.to(DEV)), pc, relu=True)["y"]
+    assert out.shape == (B, (hw[0] - 1) // 2 + 1, (hw[1] - 1) // 2 + 1, 64)
+    assert (out.cpu().permute(0, 3, 1, 2) - ref).abs().max() < 1e-5 * max(1.0, ref.abs().max().item())
