@@ -285,18 +285,18 @@ def main():
     M = sum(Ms)
     ap_bytes = M * 4 * (c * h * w + 9 * h * w)                  # form S, one A.p over all objects
     rhs_bytes = M * 4 * (c * h * w + 10 * h * w)
-    launches_per_update = 2 * (n_cg + 1)
+    launches_per_update = n_cg + 1          # the operator kernel's last CTA per object runs the CG vector step itself
     achieved = (rhs_bytes + n_cg * ap_bytes) / (ms_update * 1e-3) / 1e9
-    # DRAM traffic per launch from the committed `ncu --set full` capture (profiles/r01_ncu_full_summary.md): 47.0 MB read,
-    # 0 written for one object at M=69, i.e. 0.681 MB per active sample = the algorithmic bytes; scaled to this launch.
-    traffic = 47.0e6 / 69 * M if (c, h, w) == (96, 30, 54) else None
+    # DRAM traffic per launch from the committed `ncu --set full` capture (profiles/r01_ncu_full_summary.md): 211 MB read for
+    # 3 objects x 69 samples = 1.02 MB per active sample — 1.5x the algorithmic bytes: the second (reversed) pass over a
+    # sample finds about half of it still in L2 when 207 samples stream at once; scaled to this launch.
+    traffic = 211.0e6 / 207 * M if (c, h, w) == (96, 30, 54) else None
     roofline = dict(bound="hbm", achieved=achieved, peak=pk["hbm"], unit="GB/s", frac=achieved / pk["hbm"], traffic=traffic,
-                    kernel="gn_apply_kernel inside one batched filter update (RHS + %d x A.p, stencil form S; %d objects, "
-                           "M=%s active samples of %d, sample = %dx%dx%d fp32); time includes the %d cg_vector launches" % (
-                               n_cg, len(live), Ms, cap, c, h, w, n_cg + 1),
+                    kernel="gn_apply_tc_kernel (tcgen05 operator over the operator images, CG vector step fused into its tail) "
+                           "inside one batched filter update (RHS + %d x A.p, stencil form S; %d objects, M=%s active samples "
+                           "of %d, sample = %dx%dx%d as split fp16 planes = fp32 bytes)" % (n_cg, len(live), Ms, cap, c, h, w),
                     ms=ms_update, launches=launches_per_update, algorithmic_bytes_per_launch=ap_bytes, peak_source=pk["src"],
-                    note="working set %.0f MB vs 126 MB L2: iterations after the first re-read it from L2" % (
-                        M * 4 * (c + 10) * h * w / 1e6))
+                    note="working set %.0f MB vs 126 MB L2" % (M * 4 * (c + 10) * h * w / 1e6))
 
     # ---- conv path: algorithmic FLOP/s of one 8-frame block (the unit run_sequence executes) -------------------------
     nblk = trk.max_block
@@ -318,7 +318,7 @@ def main():
     conv_tflops = (gb + cfg["objects"] * go) / ms_track
     roofline_conv = dict(bound="tensor", achieved=conv_tflops, peak=pk["tensor"], unit="TFLOP/s", frac=conv_tflops / pk["tensor"],
                          kernel="8-frame track block: backbone + %d x (project+filter+refinement) + merge + memory insert + filter "
-                                "update; tcgen05 split-fp16 convs execute 3 MMAs per algorithmic MAC (executed tensor FLOPs = 3x)" % cfg["objects"],
+                                "update; tcgen05 split-fp16 convs execute hi*hi + hi*lo + lo*hi per algorithmic MAC (executed tensor FLOPs = 3x)" % cfg["objects"],
                          ms_per_frame=ms_track, algorithmic_gflop_per_frame=gb + cfg["objects"] * go, peak_source=pk["src"])
 
     if rank != 0:
