@@ -571,6 +571,156 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_tc3_kernel(const __grid_co
   }
 }
 
+// ----------------------------------------------------------------------------------------------------------------
+// 1x1 stride-1 convolution with up to 256 input channels and one N tile (the RRB / TSE 1x1 convs of the refinement
+// network, the stem over its patches).  These are pure streaming kernels — 64 MACs per loaded element — and the
+// general kernel spends them one CTA per 128 pixels, each paying barrier / TMEM / tensor-map setup, one exposed load and
+// an unoverlapped epilogue (2.4 TB/s measured).  Same remedy as the slab kernel: persistent CTAs, weights resident,
+// a 4-stage ring of 16x8-pixel tiles x 64 channels, one TMEM slot per tile (K <= 256), two epilogue groups.
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int S1_STAGES = 4;
+constexpr int S1_TILE_BYTES = 128 * 128;                       // one plane of one k-chunk of a tile
+constexpr int S1_NBAR = 2 * S1_STAGES + 8 + 1;
+
+template <int BN, bool R1, bool TAP>
+__global__ void __launch_bounds__(S3_THREADS, 1) conv_tc1_kernel(const __grid_constant__ CUtensorMap tm_hi,
+                                                                 const __grid_constant__ CUtensorMap tm_lo, const TcArgs a) {
+  constexpr int B_BYTES = BN * 128;
+  constexpr int STAGE_BYTES = 2 * S1_TILE_BYTES;
+  constexpr int SLOT = 2 * BN;
+  constexpr int COLS = tmem_cols(4 * SLOT);                      // 2 groups x 2 slots
+  const int KC = a.kchunks;
+  const int W_BYTES = KC * 2 * B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t ring = base;                                    // S1_STAGES x [hi|lo] tile chunk
+  const uint32_t wsm = base + S1_STAGES * STAGE_BYTES;           // weights [kc][hi|lo][BN x 128 B] (up to 4 chunks)
+  constexpr int TAIL = S1_STAGES * STAGE_BYTES + 4 * 2 * B_BYTES;
+  const uint32_t bar_full = base + TAIL;
+  const uint32_t bar_empty = bar_full + 8 * S1_STAGES;
+  const uint32_t bar_accf = bar_empty + 8 * S1_STAGES;           // [group][slot]
+  const uint32_t bar_acce = bar_accf + 32;
+  const uint32_t bar_w = bar_acce + 32;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gen + TAIL + 8 * S1_NBAR);
+  float *s_osc = reinterpret_cast<float *>(gen + TAIL + 8 * S1_NBAR + 16);
+
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  const int tiles_per_img = a.tiles_x * a.tiles_y;
+  const int ntiles = a.B * tiles_per_img;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_hi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_lo)) : "memory");
+    for (int s = 0; s < S1_STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int j = 0; j < 4; ++j) {
+      mbar_init(bar_accf + 8 * j, 1);
+      mbar_init(bar_acce + 8 * j, 4);
+    }
+    mbar_init(bar_w, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(bar_w, W_BYTES);
+      for (int kc = 0; kc < KC; ++kc)
+        bulk_load(wsm + kc * 2 * B_BYTES, reinterpret_cast<const uint8_t *>(a.wt) + (size_t)kc * 2 * B_BYTES, 2 * B_BYTES, bar_w);
+    }
+    __syncwarp();
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int b = tile / tiles_per_img, tr = tile - b * tiles_per_img;
+      const int y0 = (tr / a.tiles_x) * S3_TH, x0 = (tr % a.tiles_x) * S3_TW;
+      for (int kc = 0; kc < KC; ++kc, ++it) {
+        const int s = it % S1_STAGES;
+        mbar_wait(bar_empty + 8 * s, ((it / S1_STAGES) & 1) ^ 1);
+        const uint32_t sa = ring + s * STAGE_BYTES;
+        if (elect_one()) {
+          mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
+          tma_load_4d(sa, &tm_hi, kc * TC_BK, x0, y0, b, bar_full + 8 * s);
+          tma_load_4d(sa + S1_TILE_BYTES, &tm_lo, kc * TC_BK, x0, y0, b, bar_full + 8 * s);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = umma_idesc(128, BN), idesc2 = umma_idesc(128, 2 * BN);
+    mbar_wait(bar_w, 0);
+    uint32_t it = 0, nt = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++nt) {
+      const uint32_t eg = nt & 1, grp = nt >> 1, slot = grp & 1;
+      mbar_wait(bar_acce + 8 * (2 * eg + slot), ((grp >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (2 * eg + slot) * SLOT;
+      for (int kc = 0; kc < KC; ++kc, ++it) {
+        const int s = it % S1_STAGES;
+        mbar_wait(bar_full + 8 * s, (it / S1_STAGES) & 1);
+        const uint64_t a_hi = umma_desc(ring + s * STAGE_BYTES), a_lo = a_hi + (uint64_t)(S1_TILE_BYTES >> 4);
+        const uint64_t b_hl = umma_desc(wsm + kc * 2 * B_BYTES);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+            umma_f16(tacc, a_hi + adv, b_hl + adv, idesc2, (kc == 0 && k == 0) ? 0u : 1u);
+            umma_f16(tacc, a_lo + adv, b_hl + adv, idesc, 1u);
+          }
+          umma_commit(bar_empty + 8 * s);
+          if (kc == KC - 1) umma_commit(bar_accf + 8 * (2 * eg + slot));
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    const int eg = (warp - 2) >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    tc_epilogue_stage<BN, R1, TAP>(a, 0, s_osc);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    uint32_t nt = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++nt) {
+      if ((int)(nt & 1) != eg) continue;
+      const uint32_t grp = nt >> 1, slot = grp & 1;
+      const int b = tile / tiles_per_img, tr = tile - b * tiles_per_img;
+      const int y0 = (tr / a.tiles_x) * S3_TH, x0 = (tr % a.tiles_x) * S3_TW;
+      float acc[BN];
+      mbar_wait(bar_accf + 8 * (2 * eg + slot), (grp >> 1) & 1);
+      tc_fence_after();
+      const uint32_t col0 = tmem_base + ((uint32_t)(q * 32) << 16) + (2 * eg + slot) * SLOT;
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float t[32], t2[32];
+        tmem_ld32(col0 + c0, t);
+        tmem_ld32(col0 + BN + c0, t2);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[c0 + j] = t[j] + t2[j];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_acce + 8 * (2 * eg + slot)) : "memory");
+      tc_epilogue_store<BN, R1, TAP>(a, acc, b, y0 + row / S3_TW, x0 + row % S3_TW, 0, s_osc);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(COLS) : "memory");
+  }
+}
+
 // fp32 NHWC (ldx) -> two fp16 planes hi/lo of x * 2^4 (channel stride ldh)
 __global__ void split_kernel(const float *__restrict__ x, int64_t npix, int C, int ldx, __half *__restrict__ hi,
                              __half *__restrict__ lo, int ldh) {
@@ -775,6 +925,26 @@ static int launch_tc3(const CUtensorMap &mh, const CUtensorMap &ml, const TcArgs
   return FRTM_OK;
 }
 
+template <int BN>
+static int launch_tc1(const CUtensorMap &mh, const CUtensorMap &ml, const TcArgs &a, cudaStream_t st) {
+  constexpr int smem = S1_STAGES * 2 * S1_TILE_BYTES + 4 * 2 * BN * 128 + 8 * S1_NBAR + 16 + 84 * BN + 1024;
+  static_assert(smem <= 227 * 1024, "conv_tc1: shared memory budget");
+  static bool configured = false;
+  static int num_sms = 0;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc1_kernel<BN, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { set_error("conv_tc1: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return FRTM_ELAUNCH; }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+    configured = true;
+  }
+  const int ntiles = a.B * a.tiles_x * a.tiles_y;
+  conv_tc1_kernel<BN, false, false><<<ntiles < num_sms ? ntiles : num_sms, S3_THREADS, smem, st>>>(mh, ml, a);
+  FRTM_CHECK_LAUNCH("conv_tc1");
+  return FRTM_OK;
+}
+
 }  // namespace frtm
 
 using namespace frtm;
@@ -811,10 +981,14 @@ extern "C" int frtm_conv2d_tc(const void *x_hi, const void *x_lo, int B, int H, 
   // 3x3 / stride 1 / 64 input channels / one N tile of 32 or 64: the slab kernel with resident weights
   const bool slab3 = kh == 3 && stride == 1 && Cin == TC_BK && Cout <= bn_tile && (bn_tile == 64 || bn_tile == 32) &&
                      !(y_tap && bn_tile != 32) && !(r1_score && bn_tile != 64) && g_conv_slab_enabled;
+  // 1x1 / stride 1 / up to 256 input channels / one N tile of 32 or 64, plain epilogue: the persistent streaming kernel
+  const bool stream1 = kh == 1 && stride == 1 && Cin <= 4 * TC_BK && Cout <= bn_tile && (bn_tile == 64 || bn_tile == 32) &&
+                       !y_tap && !r1_score && g_conv_slab_enabled;
+  const int box_w = (slab3 || stream1) ? S3_TW : 0, box_h = slab3 ? S3_TH + 2 : (stream1 ? S3_TH : 0);
   CUtensorMap mh, ml;
-  int rc = make_act_map(&mh, (const __half *)x_hi, B, H, W, Cin, ldx, stride, slab3 ? S3_TW : 0, slab3 ? S3_TH + 2 : 0);
+  int rc = make_act_map(&mh, (const __half *)x_hi, B, H, W, Cin, ldx, stride, box_w, box_h);
   if (rc) return rc;
-  rc = make_act_map(&ml, (const __half *)x_lo, B, H, W, Cin, ldx, stride, slab3 ? S3_TW : 0, slab3 ? S3_TH + 2 : 0);
+  rc = make_act_map(&ml, (const __half *)x_lo, B, H, W, Cin, ldx, stride, box_w, box_h);
   if (rc) return rc;
   TcArgs a;
   a.wt = (const __half *)wt; a.oscale = oscale; a.bias = bias; a.res = res; a.res_hi = (const __half *)res_hi;
@@ -831,6 +1005,10 @@ extern "C" int frtm_conv2d_tc(const void *x_hi, const void *x_lo, int B, int H, 
   cudaStream_t st = (cudaStream_t)stream;
   const bool r1 = r1_score != nullptr, tap = y_tap != nullptr;
   FRTM_REQUIRE(!(r1 && tap), "conv2d_tc: rank-1 input and tap-map output cannot be combined");
+  if (stream1) {
+    a.tiles_x = cdiv(a.Wo, S3_TW); a.tiles_y = cdiv(a.Ho, S3_TH);
+    return bn_tile == 64 ? launch_tc1<64>(mh, ml, a, st) : launch_tc1<32>(mh, ml, a, st);
+  }
   if (slab3) {
     a.tiles_x = cdiv(a.Wo, S3_TW); a.tiles_y = cdiv(a.Ho, S3_TH);
     if (bn_tile == 64) return r1 ? launch_tc3<64, true, false>(mh, ml, a, st) : launch_tc3<64, false, false>(mh, ml, a, st);

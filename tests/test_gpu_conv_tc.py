@@ -192,3 +192,37 @@ def test_slab_kernel_matches_general_kernel(cout, hw, B):
     assert (out[1]["y"] - out[0]["y"]).abs().max().item() < 4e-6 * scale
     d = (out[1]["split"].hi.float() + out[1]["split"].lo.float()) - (out[0]["split"].hi.float() + out[0]["split"].lo.float())
     assert d.abs().max().item() / 16.0 < 4e-6 * scale
+
+
+@pytest.mark.parametrize("cin,cout,hw,B", [(64, 64, (8, 16), 1), (64, 64, (37, 29), 3), (128, 64, (30, 54), 2), (192, 64, (33, 47), 2),
+                                           (256, 32, (15, 27), 2), (64, 64, (120, 214), 24)])
+def test_streaming_1x1_kernel_matches_general_kernel(cin, cout, hw, B):
+    """1x1 / stride 1 / Cin <= 256 / one N tile: the persistent streaming kernel against the general kernel and fp32."""
+    from frtm_vos_b200 import ops
+    from frtm_vos_b200._lib import lib
+    g = torch.Generator().manual_seed(cin + cout + hw[0])
+    x = torch.randn(B, cin, *hw, generator=g)
+    w = torch.randn(cout, cin, 1, 1, generator=g) / cin ** 0.5
+    b = torch.randn(cout, generator=g)
+    res = torch.randn(B, cout, *hw, generator=g)
+    xs = ops.split_f16(_nhwc(x).to(DEV))
+    pc = ops.pack_conv_tc(w, b, device=DEV)
+    rs = _nhwc(res).to(DEV)
+    out = {}
+    for on in (1, 0):
+        lib().conv_tc_slab_enable(on)
+        try:
+            o = ops.conv2d_tc(xs, pc, res=rs, relu=True, out_split=True, nchw=(B <= 3))
+            torch.cuda.synchronize()
+        finally:
+            lib().conv_tc_slab_enable(1)
+        out[on] = o
+    if B <= 3:
+        ref = F.relu(F.conv2d(x, w, b) + res)
+        scale = max(1.0, ref.abs().max().item())
+        assert (_nchw(out[1]["y"].cpu()) - ref).abs().max().item() < 1e-5 * scale
+        assert (out[1]["nchw"].cpu() - ref).abs().max().item() < 1e-5 * scale
+    scale = max(1.0, out[0]["y"].abs().max().item())
+    assert (out[1]["y"] - out[0]["y"]).abs().max().item() < 4e-6 * scale
+    d = (out[1]["split"].hi.float() + out[1]["split"].lo.float()) - (out[0]["split"].hi.float() + out[0]["split"].lo.float())
+    assert d.abs().max().item() / 16.0 < 4e-6 * scale
