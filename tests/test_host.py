@@ -113,3 +113,24 @@ def test_augmenter_matches_reference():
     np.random.seed(0); torch.manual_seed(0)
     b_im, b_lb = ImageAugmenter(GI.AUG_PARAMS).augment_first_frame(im, mask)
     assert torch.equal(a_im, b_im) and torch.equal(a_lb, b_lb) and a_im.shape[0] == 5
+
+
+def test_cropped_telea_inpaint_is_identical_to_full_frame():
+    """The augmenter inpaints only the hole's bounding box (+ margin); the result must equal cv2.inpaint on the full frame."""
+    import cv2
+    import numpy as np
+    from frtm_vos_b200 import synth
+    from frtm_vos_b200.model.augmenter import telea_inpaint_cropped
+    seq = synth.SyntheticSequence(num_objects=3, num_frames=1, size=(240, 427), seq_id=3)
+    im, lb, ids = seq[0]
+    image = np.ascontiguousarray(im.numpy().transpose(1, 2, 0))
+    for oid in ids:
+        m = (lb[0].numpy() == oid).astype(np.uint8)[..., None]
+        outer = cv2.dilate(m, cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (2, 2)))
+        for radius in (1, 3):
+            full = cv2.inpaint(image, outer, inpaintRadius=radius, flags=cv2.INPAINT_TELEA)
+            assert np.array_equal(telea_inpaint_cropped(image, outer, radius), full)
+    # hole touching the frame border, and an empty hole
+    edge = np.zeros(image.shape[:2], np.uint8); edge[:20, :30] = 1; edge[-5:, -40:] = 1
+    assert np.array_equal(telea_inpaint_cropped(image, edge, 1), cv2.inpaint(image, edge, inpaintRadius=1, flags=cv2.INPAINT_TELEA))
+    assert np.array_equal(telea_inpaint_cropped(image, np.zeros_like(edge), 1), image)
