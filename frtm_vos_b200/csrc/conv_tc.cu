@@ -1021,7 +1021,7 @@ extern "C" int frtm_conv2d_tc(const void *x_hi, const void *x_lo, int B, int H, 
     case 32: return tap ? launch_tc<32, 2, false, true>(mh, ml, a, grid, st) : launch_tc<32, 2, false, false>(mh, ml, a, grid, st);
     case 64: return r1 ? launch_tc<64, 2, true, false>(mh, ml, a, grid, st) : launch_tc<64, 2, false, false>(mh, ml, a, grid, st);
     case 80: return r1 ? launch_tc<80, 2, true, false>(mh, ml, a, grid, st) : launch_tc<80, 2, false, false>(mh, ml, a, grid, st);
-    case 128: return launch_tc<128, 2, false, false>(mh, ml, a, grid, st);
+    case 128: return launch_tc<128, 3, false, false>(mh, ml, a, grid, st);   // one CTA per SM anyway (TMEM): a third stage hides the L2 latency
     default: set_error("conv2d_tc: unsupported N tile %d (32, 64, 80, 128)", bn_tile); return FRTM_EINVAL;
   }
 }
