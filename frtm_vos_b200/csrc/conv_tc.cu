@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
 // ----------------------------------------------------------------------------------------------------------------
 constexpr int S3_TH = 16, S3_TW = 8;
 constexpr int S3_SLAB_BYTES = (S3_TH + 2) * S3_TW * 128;      // one plane of one slab: 18 rows x 8 px x 64 ch fp16
-constexpr int S3_STAGES = 2;
+constexpr int S3_STAGES = 4;                                   // ring of slab PLANES (hi and lo are separate stages)
 constexpr int S3_FOLD = 3;                                     // taps per TMEM slot = one slab (K = 192 per product)
 constexpr int S3_THREADS = 64 + 2 * 128;                       // producer warp, MMA warp, two epilogue groups of 4 warps
 constexpr int S3_NBAR = 2 * S3_STAGES + 8 + 1;
@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_tc3_kernel(const __grid_co
                                                                  const __grid_constant__ CUtensorMap tm_lo, const TcArgs a) {
   constexpr int B_BYTES = BN * 128;
   constexpr int W_BYTES = 9 * 2 * B_BYTES;
-  constexpr int STAGE_BYTES = 2 * S3_SLAB_BYTES;
+  constexpr int STAGE_BYTES = S3_SLAB_BYTES;                    // one plane of one slab
   constexpr int SLOT = 2 * BN;
   constexpr int COLS = tmem_cols(4 * SLOT);                      // 2 groups x 2 slots
   extern __shared__ uint8_t smem_raw[];
@@ -472,14 +472,16 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_tc3_kernel(const __grid_co
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int b = tile / tiles_per_img, tr = tile - b * tiles_per_img;
       const int y0 = (tr / a.tiles_x) * S3_TH, x0 = (tr % a.tiles_x) * S3_TW;
-      for (int dx = 0; dx < 3; ++dx, ++it) {
+      // the hi and the lo plane of a slab are separate ring stages: a stage is refilled as soon as the products that
+      // read ITS plane have completed, which keeps twice as many refills in flight for the same shared memory
+      for (int st = 0; st < 6; ++st, ++it) {
+        const int dx = st >> 1;
         const int s = it % S3_STAGES;
         mbar_wait(bar_empty + 8 * s, ((it / S3_STAGES) & 1) ^ 1);
         const uint32_t sa = slabs + s * STAGE_BYTES;
         if (elect_one()) {
           mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
-          tma_load_4d(sa, &tm_hi, 0, x0 + dx - 1, y0 - 1, b, bar_full + 8 * s);
-          tma_load_4d(sa + S3_SLAB_BYTES, &tm_lo, 0, x0 + dx - 1, y0 - 1, b, bar_full + 8 * s);
+          tma_load_4d(sa, (st & 1) ? &tm_lo : &tm_hi, 0, x0 + dx - 1, y0 - 1, b, bar_full + 8 * s);
         }
         __syncwarp();
       }
@@ -492,30 +494,34 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_tc3_kernel(const __grid_co
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++nt) {
       const uint32_t eg = nt & 1;                                // epilogue group of this tile
       const uint32_t gc = (nt >> 1) * NGRP;                      // folds this group has seen before this tile
-      for (int dx = 0; dx < 3; ++dx, ++it) {
-        const int s = it % S3_STAGES;
+      for (int dx = 0; dx < 3; ++dx) {
         const uint32_t grp = gc + dx, slot = grp & 1;
         mbar_wait(bar_acce + 8 * (2 * eg + slot), ((grp >> 1) & 1) ^ 1);   // the group has drained this slot
         tc_fence_after();
-        mbar_wait(bar_full + 8 * s, (it / S3_STAGES) & 1);
-        const uint64_t dA = umma_desc(slabs + s * STAGE_BYTES);
         const uint32_t tacc = tmem_base + (2 * eg + slot) * SLOT;
-        if (elect_one()) {
+        // hi plane: A_hi x [B_hi | B_lo] (N = 2*BN) for the three vertical taps; then lo plane: A_lo x B_hi (N = BN)
 #pragma unroll
-          for (int dy = 0; dy < 3; ++dy) {
-            const uint64_t a_hi = dA + (uint64_t)(dy * 1024 >> 4), a_lo = a_hi + (uint64_t)(S3_SLAB_BYTES >> 4);
-            const uint64_t b_hl = umma_desc(wsm + (dy * 3 + dx) * 2 * B_BYTES);
+        for (int pl = 0; pl < 2; ++pl, ++it) {
+          const int s = it % S3_STAGES;
+          mbar_wait(bar_full + 8 * s, (it / S3_STAGES) & 1);
+          const uint64_t dA = umma_desc(slabs + s * STAGE_BYTES);
+          if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < TC_BK / 16; ++k) {
-              const uint64_t adv = (uint64_t)(k * 32 >> 4);
-              umma_f16(tacc, a_hi + adv, b_hl + adv, idesc2, (dy == 0 && k == 0) ? 0u : 1u);
-              umma_f16(tacc, a_lo + adv, b_hl + adv, idesc, 1u);
+            for (int dy = 0; dy < 3; ++dy) {
+              const uint64_t a_p = dA + (uint64_t)(dy * 1024 >> 4);
+              const uint64_t b_hl = umma_desc(wsm + (dy * 3 + dx) * 2 * B_BYTES);
+#pragma unroll
+              for (int k = 0; k < TC_BK / 16; ++k) {
+                const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                if (pl == 0) umma_f16(tacc, a_p + adv, b_hl + adv, idesc2, (dy == 0 && k == 0) ? 0u : 1u);
+                else umma_f16(tacc, a_p + adv, b_hl + adv, idesc, 1u);
+              }
             }
+            umma_commit(bar_empty + 8 * s);
+            if (pl == 1) umma_commit(bar_accf + 8 * (2 * eg + slot));
           }
-          umma_commit(bar_empty + 8 * s);
-          umma_commit(bar_accf + 8 * (2 * eg + slot));
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
   } else {
@@ -907,7 +913,7 @@ static int launch_tc(const CUtensorMap &mh, const CUtensorMap &ml, const TcArgs 
 
 template <int BN, bool R1, bool TAP>
 static int launch_tc3(const CUtensorMap &mh, const CUtensorMap &ml, const TcArgs &a, cudaStream_t st) {
-  constexpr int smem = 9 * 2 * BN * 128 + S3_STAGES * 2 * S3_SLAB_BYTES + 8 * S3_NBAR + 16 + 84 * BN + 1024;
+  constexpr int smem = 9 * 2 * BN * 128 + S3_STAGES * S3_SLAB_BYTES + 8 * S3_NBAR + 16 + 84 * BN + 1024;
   static_assert(smem <= 227 * 1024, "conv_tc3: shared memory budget");
   static bool configured = false;
   static int num_sms = 0;

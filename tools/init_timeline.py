@@ -26,6 +26,12 @@ orig_init = D.Discriminator.init
 def dinit(self, *a, **k):
     t0 = time.perf_counter(); r = orig_init(self, *a, **k); marks.append(("disc.init", (time.perf_counter() - t0) * 1e3)); return r
 D.Discriminator.init = dinit
+from frtm_vos_b200.model import augmenter as A
+for nm in ("cut_and_inpaint", "mask_center_bbox", "draw_specs", "target_locations"):
+    wrap(A, nm, "  aug." + nm)
+wrap(trk.augment.__self__ if hasattr(trk.augment, "__self__") else trk, "_warp_masks_device", "  aug._warp_masks_device") if hasattr(getattr(trk.augment, "__self__", None), "_warp_masks_device") else None
+if hasattr(getattr(trk.augment, "__self__", None), "_render_device"):
+    wrap(trk.augment.__self__, "_render_device", "  aug._render_device")
 orig_aug = trk.augment
 def aug(*a, **k):
     t0 = time.perf_counter(); r = orig_aug(*a, **k); marks.append(("augment(thread)", (time.perf_counter() - t0) * 1e3)); return r
