@@ -350,7 +350,12 @@ __device__ __forceinline__ int softmax_argmax(const float *__restrict__ m, int N
 __global__ void merge_masks_kernel(const float *__restrict__ src, unsigned long long logit_mask,
                                    const uint8_t *__restrict__ suppress, int N, int HW, const uint8_t *__restrict__ lut,
                                    int single, float *__restrict__ masks, uint8_t *__restrict__ labels,
-                                   int *__restrict__ counts) {
+                                   int *__restrict__ counts, int counts_stride) {
+  // blockIdx.y = frame of a block of consecutive frames (independent merges, one launch)
+  src += (int64_t)blockIdx.y * N * HW;
+  masks += (int64_t)blockIdx.y * (N + 1) * HW;
+  labels += (int64_t)blockIdx.y * HW;
+  counts += (int64_t)blockIdx.y * counts_stride;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   const float lo = 1e-7f, hi = 1.f - 1e-7f;
   if (p < HW) {
@@ -731,8 +736,20 @@ extern "C" int frtm_merge_masks(const float *src, uint64_t logit_mask, const uin
                                 void *stream) {
   FRTM_REQUIRE(src && lut && masks && labels && counts && N > 0 && N <= 64, "merge_masks: bad arguments");
   merge_masks_kernel<<<cdiv(HW, 256), 256, 0, (cudaStream_t)stream>>>(src, (unsigned long long)logit_mask, suppress, N,
-                                                                      HW, lut, single_object, masks, labels, counts);
+                                                                      HW, lut, single_object, masks, labels, counts, 0);
   FRTM_CHECK_LAUNCH("merge_masks");
+  return FRTM_OK;
+}
+
+extern "C" int frtm_merge_masks_frames(const float *src, int F, uint64_t logit_mask, int N, int HW, const uint8_t *lut,
+                                       int single_object, float *masks, uint8_t *labels, int *counts, int counts_stride,
+                                       void *stream) {
+  FRTM_REQUIRE(src && lut && masks && labels && counts && N > 0 && N <= 64 && F > 0 && F <= 65535 && counts_stride >= N,
+               "merge_masks_frames: bad arguments");
+  merge_masks_kernel<<<dim3(cdiv(HW, 256), F), 256, 0, (cudaStream_t)stream>>>(src, (unsigned long long)logit_mask, nullptr, N, HW,
+                                                                               lut, single_object, masks, labels, counts,
+                                                                               counts_stride);
+  FRTM_CHECK_LAUNCH("merge_masks_frames");
   return FRTM_OK;
 }
 

@@ -336,6 +336,32 @@ class Tracker(nn.Module):
         d0 = live[0].discriminator
         hinge = d0.pw_params is not None and d0.pw_params["method"] == "hinge"
         out_labels = []
+        if nF > 1 and not fresh and self.disc_params["update_filters"] and hinge:
+            # A block of frames without new objects: the merges, pixel weights and stencils of all its frames are
+            # independent (masks never feed the next frame's forward pass) -> one launch each for the whole block.  Only the
+            # memory inserts stay per frame (the slot policy is sequential per object).
+            if getattr(self, "_counts_blk", None) is None or self._counts_blk.shape[0] < nF or self._counts_blk.shape[1] != n:
+                self._counts_blk = torch.zeros((self.max_block, n), dtype=torch.int32, device=dev)
+            cblk = self._counts_blk[:nF]
+            masks_all, labels_all = ops.merge_masks_frames(logits.contiguous(), (1 << n) - 1, self._lut, len(self.object_ids) == 1, cblk)
+            ys_all = masks_all[:, 1:1 + n].reshape(nF * n, 1, *im_size)
+            pw_all = ops.pixel_weights(ys_all, d0.pw_params["tf"], True, counts=cblk.reshape(-1))
+            st_all, uty_all = ops.build_stencil(pw_all, ys_all, (h, w))
+            for f in range(nF):
+                out_labels.append(labels_all[f])
+                for k, t in enumerate(live):
+                    t.discriminator.frame_num += 1
+                    t.discriminator.current_sample = samples[f * n + k:f * n + k + 1]
+                    j = f * n + k
+                    t.discriminator.update(ys_all[j:j + 1], gate_count=cblk[f, k:k + 1], pw=pw_all[j:j + 1],
+                                           stencil=st_all[j:j + 1], uty=uty_all[j:j + 1], run_optimizer=False)
+            self._counts[:n].copy_(cblk[nF - 1])          # the GN table gates on this (stable) buffer
+            due = [k for k, t in enumerate(live) if t.discriminator.frame_num % t.discriminator.train_skipping == 0]
+            if due:
+                self._batched_gn_update(live, due)
+            self.current_masks = masks_all[nF - 1]
+            self._last_labels = labels_all[nF - 1]
+            return out_labels
         for f in range(nF):
             # merge (objects initialised on this frame take part with their start masks and suppress the others)
             if fresh:

@@ -212,6 +212,17 @@ def merge_masks(src: torch.Tensor, logit_mask: int, suppress: Optional[torch.Ten
     return masks, labels, counts
 
 
+def merge_masks_frames(src: torch.Tensor, logit_mask: int, lut: torch.Tensor, single: bool, counts: torch.Tensor):
+    """src (F,N,H,W) -> masks (F,N+1,H,W), labels (F,H,W) uint8; counts (F,>=N) int32 is zeroed and filled."""
+    F, N, H, W = src.shape
+    masks = torch.empty((F, N + 1, H, W), device=src.device, dtype=torch.float32)
+    labels = torch.empty((F, H, W), device=src.device, dtype=torch.uint8)
+    counts.zero_()
+    lib().merge_masks_frames(ptr(src), F, logit_mask, N, H * W, ptr(lut), 1 if single else 0, ptr(masks), ptr(labels),
+                             ptr(counts), counts.shape[1], stream())
+    return masks, labels
+
+
 def corr3x3(x: torch.Tensor, filt: torch.Tensor, index: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x (NB,c,h,w) NCHW, filt (NF,c,3,3) -> (NB,h,w); sample n uses filter index[n] (default 0)."""
     NB, c, h, w = x.shape

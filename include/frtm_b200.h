@@ -173,6 +173,11 @@ int64_t frtm_upsample_tapsum_supported(int h, int w, int H, int W);
  * model/discriminator.py:214) — counts must be zeroed by the caller.  N <= 64. */
 int frtm_merge_masks(const float *src, uint64_t logit_mask, const uint8_t *suppress, int N, int HW, const uint8_t *lut,
                      int single_object, float *masks, uint8_t *labels, int *counts, void *stream);
+/* The same merge for F consecutive frames in one launch (masks never feed the next frame's forward pass): src (F,N,HW),
+ * masks (F,N+1,HW), labels (F,HW), counts (F,counts_stride) zeroed by the caller.  No `suppress` (no object starts inside
+ * a block). */
+int frtm_merge_masks_frames(const float *src, int F, uint64_t logit_mask, int N, int HW, const uint8_t *lut, int single_object,
+                            float *masks, uint8_t *labels, int *counts, int counts_stride, void *stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Target model: correlation, memory, GN/CG  (model/discriminator.py, model/memory.py, model/optimizer.py)
