@@ -599,7 +599,9 @@ __device__ __forceinline__ float tent(int idx, int i0, int i1, float lam) {
   return (idx == i0 ? 1.f - lam : 0.f) + (idx == i1 ? lam : 0.f);
 }
 
-// One warp per low-res pixel a=(i,j): gathers the ~ (2H/h)x(2W/w) high-res window that a contributes to.
+// One warp per low-res pixel a=(i,j): gathers the ~ (2H/h)x(2W/w) high-res window that a contributes to.  The bilinear
+// weights are separable, so each lane keeps the column factors of its (at most two) window columns in registers and
+// the row factors are computed once per window row: 12 FMAs and two loads per high-res pixel, no index arithmetic.
 __global__ void __launch_bounds__(256) build_stencil_kernel(const float *__restrict__ pw, const float *__restrict__ y, int H,
                                                             int W, int h, int w, float *__restrict__ stencil,
                                                             float *__restrict__ uty) {
@@ -613,30 +615,44 @@ __global__ void __launch_bounds__(256) build_stencil_kernel(const float *__restr
   int Y0 = (int)floorf(((float)i - 1.f + 0.5f) / sh - 0.5f) - 1, Y1 = (int)ceilf(((float)i + 1.f + 0.5f) / sh - 0.5f) + 1;
   int X0 = (int)floorf(((float)j - 1.f + 0.5f) / sw - 0.5f) - 1, X1 = (int)ceilf(((float)j + 1.f + 0.5f) / sw - 0.5f) + 1;
   Y0 = max(Y0, 0); X0 = max(X0, 0); Y1 = min(Y1, H - 1); X1 = min(X1, W - 1);
-  const int ny = Y1 - Y0 + 1, nx = X1 - X0 + 1;
+  const int nx = X1 - X0 + 1;
   float acc[9], accy = 0.f;
 #pragma unroll
   for (int t = 0; t < 9; ++t) acc[t] = 0.f;
   const float *pwk = pw + (int64_t)k * H * W, *yk = y + (int64_t)k * H * W;
-  for (int q = lane; q < ny * nx; q += 32) {
-    const int Y = Y0 + q / nx, X = X0 + q % nx;
-    int y0, y1, x0, x1;
-    float ly, lx;
-    bilinear_src(Y, sh, h, y0, y1, ly);
-    bilinear_src(X, sw, w, x0, x1, lx);
-    const float ua = tent(i, y0, y1, ly) * tent(j, x0, x1, lx);
-    if (ua == 0.f) continue;
-    const float p = pwk[(int64_t)Y * W + X];
-    const float w2 = p * p * ua;
-    accy = fmaf(w2, yk[(int64_t)Y * W + X], accy);
-    float ry[3], rx[3];
+  for (int xb = 0; xb < nx; xb += 32) {                    // (one or two passes: the window is ~2W/w + 4 columns wide)
+    const int X = X0 + xb + lane;
+    float cx[3] = {0.f, 0.f, 0.f}, cxc = 0.f;
+    if (X <= X1) {
+      int x0, x1;
+      float lx;
+      bilinear_src(X, sw, w, x0, x1, lx);
+      cxc = tent(j, x0, x1, lx);                           // U[(Y,X), (.,j)] column factor
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      ry[d] = tent(i + d - 1, y0, y1, ly);
-      rx[d] = tent(j + d - 1, x0, x1, lx);
+      for (int d = 0; d < 3; ++d) cx[d] = cxc * tent(j + d - 1, x0, x1, lx);
     }
+    if (__ballot_sync(0xffffffffu, cxc != 0.f) == 0u) continue;
+    for (int Y = Y0; Y <= Y1; ++Y) {
+      int y0, y1;
+      float ly;
+      bilinear_src(Y, sh, h, y0, y1, ly);
+      const float cyc = tent(i, y0, y1, ly);
+      if (cyc == 0.f) continue;                            // warp-uniform
+      float cy[3];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) acc[t] = fmaf(w2, ry[t / 3] * rx[t % 3], acc[t]);
+      for (int d = 0; d < 3; ++d) cy[d] = cyc * tent(i + d - 1, y0, y1, ly);
+      if (cxc != 0.f) {
+        const float p = pwk[(int64_t)Y * W + X];
+        const float p2 = p * p;
+        accy = fmaf(p2 * (cyc * cxc), yk[(int64_t)Y * W + X], accy);
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+          const float r = p2 * cy[dy];
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) acc[dy * 3 + dx] = fmaf(r, cx[dx], acc[dy * 3 + dx]);
+        }
+      }
+    }
   }
 #pragma unroll
   for (int t = 0; t < 9; ++t) {
