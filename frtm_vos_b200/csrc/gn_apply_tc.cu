@@ -16,13 +16,15 @@
 // as hi*hi + hi*lo + lo*hi.  Phase 3 accumulates GC_FOLD tiles (K = 256) inside the tensor core and folds the slot into
 // fp32 registers with round-to-nearest adds (the tensor-core accumulator truncates, see conv_tc.cu).
 //
-// One CTA per sample, two CTAs per SM (106 KB of shared memory, 128 TMEM columns each), so every active sample of a
-// 3-object update is in flight at once and one sample's phase 3 (second pass, from L2) overlaps another's phase 1.
-// Warp 0 streams the image through a 3-slot mbarrier ring (ntiles tiles from HBM, the stencil chunks, the ntiles tiles
-// again in REVERSE order, so the most recently streamed tiles — the ones still in L2 — are re-read first); warp 1 issues the MMAs; warps 2-5 drain TMEM, run phase 2 and build the v operand.  The kernel is
-// bound by the producer/consumer hand-offs, so work per hand-off is batched: phase 1 drains four tile pairs (512
-// pixels) per accumulator slot, phase 3 consumes two tiles per v-operand slot and issues  A_hi x [B_hi | B_lo]  as one
-// N = 32 product plus  A_lo x B_hi  (two reads of the A tile instead of three).
+// One CTA per sample, two CTAs per SM (115 KB of shared memory, 256 TMEM columns each), so every active sample of a
+// 3-object update is in flight at once and one sample's phase 3 overlaps another's phase 1.  Warp 0 streams the image
+// through a 3-slot mbarrier ring (ntiles tiles from HBM, the stencil chunks, the ntiles tiles again in REVERSE order, so
+// the most recently streamed tiles — the ones still in L2 — are re-read first); warp 1 issues the MMAs; warps 2-5 drain
+// TMEM, run phase 2 and build the v operand.  Measured (profiles/r01_gn_tc_timeline.md; -DFRTM_DEBUG_NO_MMA removes only
+// 14 % of the time): the kernel is bound by the serial hand-offs between the roles, not by the tensor pipe or by
+// bandwidth, so work per hand-off is batched — two tile pairs (256 pixels) per phase-1 accumulator slot, drained with
+// one gather pass per group; two tiles per v-operand slot; A_hi x [B_hi | B_lo] as one N = 32 product plus A_lo x B_hi —
+// and the per-sample partial reduction and the CG vector step run in the kernel's tail (last CTA per object).
 #include "common.cuh"
 #include "target_model.cuh"
 #include "tc_ptx.cuh"
@@ -127,7 +129,8 @@ __device__ __forceinline__ void gc_sample(const GaArgs &a, const GcParams &P) {
   uint8_t *obuf_g = gen + NS * tile_bytes;
   float *sp = reinterpret_cast<float *>(obuf_g + 2 * GC_VSLOT_BYTES);
   float *vp = sp + npad;
-  uint8_t *tail = reinterpret_cast<uint8_t *>(vp + npad);
+  float *ybuf = vp + npad;                       // [9][GC_PGROUP * 128] tap values of one phase-1 drain group
+  uint8_t *tail = reinterpret_cast<uint8_t *>(ybuf + 9 * GC_PGROUP * 128);
   tail = gen + (((tail - gen) + 15) & ~(size_t)15);
   const uint32_t bars = base + (uint32_t)(tail - gen);
   float *red = reinterpret_cast<float *>(tail + 8 * GC_NBARS);            // 8 floats
@@ -351,29 +354,36 @@ __device__ __forceinline__ void gc_sample(const GaArgs &a, const GcParams &P) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_accfree + 8 * as);
-      int sidx[GC_PGROUP];                                   // padded index of the own pixel of each pair, -1 = none
-      int pyx[GC_PGROUP];
+      // The group's tap values go to shared memory as plain stores; then every score-map entry the group can reach
+      // (its pixels +- one row and one column) is owned by exactly one thread, which gathers the up to nine contributions
+      // and does ONE read-modify-write: two barriers per group instead of nine conflict-free scatter rounds.
+      constexpr int GPX = GC_PGROUP * 128;
+      const int g0 = grp * GPX;
 #pragma unroll
       for (int u = 0; u < GC_PGROUP; ++u) {
         const int tp = grp * GC_PGROUP + u;
         const bool swapped = ((2 * tp) % NS) > ((2 * tp + 1) % NS);
         const int tile = 2 * tp + (((dt >> 6) & 1) ^ (swapped ? 1 : 0));
-        const int q = tile * GC_TILE + (dt & 63);
-        const int py = q / w, px = q - py * w;
-        sidx[u] = (u < np && q < hw) ? (py + 1) * wp + px + 1 : -1;
-        pyx[u] = (py << 16) | px;
+        const int li = (tile - 2 * grp * GC_PGROUP) * GC_TILE + (dt & 63);
+        const bool on = u < np && g0 + li < hw;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) ybuf[t * GPX + li] = on ? y[u][t] * yscale : 0.f;
       }
+      drain_sync();
+      const int tlo = max(g0 - (w + 1), 0), thi = min(g0 + GPX + w + 1, hw);      // targets [tlo, thi)
+      for (int qt = tlo + dt; qt < thi; qt += 128) {
+        const int ty = qt / w, tx = qt - ty * w;
+        float sum = 0.f;
 #pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const int ddy = t / 3 - 1, ddx = t % 3 - 1;
-#pragma unroll
-        for (int u = 0; u < GC_PGROUP; ++u) {
-          const int py = pyx[u] >> 16, px = pyx[u] & 0xffff;
-          const int yy = py - ddy, xx = px - ddx;
-          if (sidx[u] >= 0 && yy >= 0 && yy < h && xx >= 0 && xx < w) sp[sidx[u] - ddy * wp - ddx] += y[u][t] * yscale;
+        for (int t = 0; t < 9; ++t) {
+          const int ddy = t / 3 - 1, ddx = t % 3 - 1;
+          const int sy = ty + ddy, sx = tx + ddx;
+          const int li = qt + ddy * w + ddx - g0;                   // source pixel, local to the group
+          if (sy >= 0 && sy < h && sx >= 0 && sx < w && li >= 0 && li < GPX) sum += ybuf[t * GPX + li];
         }
-        drain_sync();
+        sp[(ty + 1) * wp + tx + 1] += sum;
       }
+      drain_sync();
     }
     // ---- phase 2: v = sw (S s - use_y t) from the stencil chunks in the ring, and its maximum ----
     if (dt == 0) GC_STAMP(3, 15);
@@ -420,8 +430,6 @@ __device__ __forceinline__ void gc_sample(const GaArgs &a, const GcParams &P) {
     float gacc[16];
 #pragma unroll
     for (int u = 0; u < 16; ++u) gacc[u] = 0.f;
-    const int t16 = dt >> 3, ch8 = dt & 7;
-    const int dy = t16 / 3 - 1, dx = t16 % 3 - 1;
     auto fold = [&](int grp) {
       const int fs = grp & 1;
       mbar_wait(bar_foldfull + 8 * fs, (grp >> 1) & 1);
@@ -448,24 +456,28 @@ __device__ __forceinline__ void gc_sample(const GaArgs &a, const GcParams &P) {
       const int vs = vstep & 1;
       mbar_wait(bar_vfree + 8 * vs, ((vstep >> 1) & 1) ^ 1);
       if (dt == 0) GC_STAMP(3, 17 + vstep);
-      if (t16 < 9) {
+      // 9 tap rows x GC_VSTEP tiles x 16 half-chunks of 4 pixels, spread over all 128 threads
+      for (int item = dt; item < 9 * GC_VSTEP * 16; item += 128) {
+        const int t = item / (GC_VSTEP * 16), rem = item - t * (GC_VSTEP * 16);
+        const int u = rem >> 4, c8 = (rem >> 1) & 7, half = rem & 1;
+        const int ddy = t / 3 - 1, ddx = t % 3 - 1;
+        const int q0 = (ntiles - 1 - (vstep * GC_VSTEP + u)) * GC_TILE + c8 * 8 + half * 4;   // second pass runs backwards
+        int py = q0 / w, px = q0 - py * w;
+        float v[4];
 #pragma unroll
-        for (int u = 0; u < GC_VSTEP; ++u) {
-          const int q0 = (ntiles - 1 - (vstep * GC_VSTEP + u)) * GC_TILE + ch8 * 8;   // second pass runs backwards
-          int py = q0 / w, px = q0 - py * w;
-          __align__(16) __half hh[8];
-          __align__(16) __half ll[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float v = (q0 + e < hw) ? vp[(py + 1 - dy) * wp + px + 1 - dx] * vscale : 0.f;
-            hh[e] = __float2half_rn(v);
-            ll[e] = __float2half_rn(v - __half2float(hh[e]));
-            if (++px == w) { px = 0; ++py; }
-          }
-          uint8_t *row = obuf_g + vs * GC_VSLOT_BYTES + u * GC_VTILE_BYTES + t16 * 128 + ((ch8 ^ (t16 & 7)) << 4);
-          *reinterpret_cast<uint4 *>(row) = *reinterpret_cast<const uint4 *>(hh);
-          *reinterpret_cast<uint4 *>(row + 2048) = *reinterpret_cast<const uint4 *>(ll);
+        for (int e = 0; e < 4; ++e) {
+          v[e] = (q0 + e < hw) ? vp[(py + 1 - ddy) * wp + px + 1 - ddx] * vscale : 0.f;
+          if (++px == w) { px = 0; ++py; }
         }
+        const __half2 h01 = __floats2half2_rn(v[0], v[1]), h23 = __floats2half2_rn(v[2], v[3]);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(v[0] - f01.x, v[1] - f01.y), l23 = __floats2half2_rn(v[2] - f23.x, v[3] - f23.y);
+        uint8_t *row = obuf_g + vs * GC_VSLOT_BYTES + u * GC_VTILE_BYTES + t * 128 + ((c8 ^ (t & 7)) << 4) + half * 8;
+        uint2 ph, pl;
+        ph.x = *reinterpret_cast<const uint32_t *>(&h01); ph.y = *reinterpret_cast<const uint32_t *>(&h23);
+        pl.x = *reinterpret_cast<const uint32_t *>(&l01); pl.y = *reinterpret_cast<const uint32_t *>(&l23);
+        *reinterpret_cast<uint2 *>(row) = ph;
+        *reinterpret_cast<uint2 *>(row + 2048) = pl;
       }
       fence_async_smem();
       __syncwarp();
@@ -561,7 +573,7 @@ __global__ void __launch_bounds__(256) build_images_kernel(const float *__restri
 
 static size_t gc_fixed_smem(int h, int w) {
   const size_t npad = (size_t)(h + 2) * (w + 2);
-  return 1024 + 2 * GC_VSLOT_BYTES + 2 * npad * 4 + 16 + 8 * GC_NBARS + 32 + 16;
+  return 1024 + 2 * GC_VSLOT_BYTES + 2 * npad * 4 + 9 * GC_PGROUP * 128 * 4 + 16 + 8 * GC_NBARS + 32 + 16;
 }
 // Ring depth: measured on B200 (3 objects x 69 samples at 30x54) two CTAs per SM with 3 slots each (0.37 ms per update)
 // beat one CTA per SM with 8 slots (0.48 ms): a sample's phases are serialised by the role hand-offs, not by load
