@@ -311,13 +311,17 @@ class PackedConvTC:
 
 
 def _pick_bn(cout: int) -> int:
+    """N tile of the tensor-core conv.  Wide convs use 64 too: measured on B200 (rn18 and rn101 at 480p) two resident CTAs
+    per SM with N = 64 tiles beat one CTA per SM with N = 128 tiles (wave quantisation of the 56-tile stages, and the
+    128-wide tile needs all 512 TMEM columns); FRTM_BN_MAX=128 restores the wide tile for experiments."""
+    import os
     if cout <= 32:
         return 32
     if cout <= 64:
         return 64
     if cout <= 80:
         return 80
-    return 128
+    return 128 if int(os.environ.get("FRTM_BN_MAX", "64")) >= 128 else 64
 
 
 def pack_conv_tc(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, bn: Optional[dict] = None, device=None,

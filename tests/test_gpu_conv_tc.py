@@ -226,3 +226,19 @@ def test_streaming_1x1_kernel_matches_general_kernel(cin, cout, hw, B):
     assert (out[1]["y"] - out[0]["y"]).abs().max().item() < 4e-6 * scale
     d = (out[1]["split"].hi.float() + out[1]["split"].lo.float()) - (out[0]["split"].hi.float() + out[0]["split"].lo.float())
     assert d.abs().max().item() / 16.0 < 4e-6 * scale
+
+
+def test_conv2d_tc_wide_tile_128():
+    """The N = 128 tile (three stages, all 512 TMEM columns) is no longer the default for wide convs; keep it covered."""
+    from frtm_vos_b200 import ops
+    g = torch.Generator().manual_seed(128)
+    x = torch.randn(2, 128, 15, 27, generator=g)
+    w = torch.randn(256, 128, 3, 3, generator=g) / (128 * 9) ** 0.5
+    b = torch.randn(256, generator=g)
+    ref = F.relu(F.conv2d(x, w, b, 1, 1))
+    xs = ops.split_f16(_nhwc(x).to(DEV))
+    for tile in (128, 64):
+        pc = ops.pack_conv_tc(w, b, device=DEV, bn_tile=tile)
+        assert pc.bn == tile
+        o = ops.conv2d_tc(xs, pc, relu=True)
+        assert (_nchw(o["y"].cpu()) - ref).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item())
