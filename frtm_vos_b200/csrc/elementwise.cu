@@ -128,68 +128,70 @@ __global__ void resize_bilinear_kernel(const float *__restrict__ x, int B, int H
 // ---------------------------------------------------------------- bicubic x2 -----------------------------------
 __constant__ float kCubicE[4] = {-0.10546875f, 0.87890625f, 0.26171875f, -0.03515625f};
 
-// One thread = one 4x4 input window = the 2x2 block of outputs (all four polyphase filters) that share it.
+// One thread = two horizontally adjacent 4x4 input windows (a 4x5 patch, 4 channels) = a 2x4 block of outputs.  The
+// polyphase filters are outer products of the same two 4-tap rows, so the patch is filtered along x once (four phase
+// values per input row) and then along y: 20 loads and 384 FMAs per 8 outputs instead of 32 loads and 640 — the kernel
+// is instruction-bound, not bandwidth-bound.
 __global__ void __launch_bounds__(256) pyrup_bicubic_kernel(const float *__restrict__ x, int B, int H, int W, int C,
                                                             float *__restrict__ y, __half *__restrict__ y_hi,
                                                             __half *__restrict__ y_lo) {
   const int C4 = C / 4, Ho = 2 * H, Wo = 2 * W;
+  const int NP = (W + 2) / 2;                                   // window pairs per row (windows n = 0..W)
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = (int64_t)B * (H + 1) * (W + 1) * C4;
+  const int64_t total = (int64_t)B * (H + 1) * NP * C4;
   if (i >= total) return;
   const int c4 = (int)(i % C4);
   int64_t r = i / C4;
-  const int n = (int)(r % (W + 1));
-  r /= (W + 1);
+  const int n = 2 * (int)(r % NP);
+  r /= NP;
   const int m = (int)(r % (H + 1));
   const int b = (int)(r / (H + 1));
-  // window rows m-2..m+1, cols n-2..n+1 (replicate padding); outputs (pre-crop) rows 2m, 2m+1 -> cropped 2m-1, 2m
-  float4 win[4][4];
+  const float E0 = kCubicE[0], E1 = kCubicE[1], E2 = kCubicE[2], E3 = kCubicE[3];
+  // window rows m-2..m+1, cols n-2..n+2 (replicate padding); x pass -> phases: window n even/odd, window n+1 even/odd
+  float4 hx[4][4];
 #pragma unroll
   for (int ky = 0; ky < 4; ++ky) {
     const int sy = min(max(m + ky - 2, 0), H - 1);
+    float4 v[5];
 #pragma unroll
-    for (int kx = 0; kx < 4; ++kx) {
+    for (int kx = 0; kx < 5; ++kx) {
       const int sx = min(max(n + kx - 2, 0), W - 1);
-      win[ky][kx] = *reinterpret_cast<const float4 *>(x + (((int64_t)b * H + sy) * W + sx) * C + c4 * 4);
+      v[kx] = *reinterpret_cast<const float4 *>(x + (((int64_t)b * H + sy) * W + sx) * C + c4 * 4);
     }
+#define FRTM_DOT4(a0, a1, a2, a3, w0, w1, w2, w3)                                                         \
+  make_float4((w0 * a0.x + w1 * a1.x) + (w2 * a2.x + w3 * a3.x), (w0 * a0.y + w1 * a1.y) + (w2 * a2.y + w3 * a3.y), \
+              (w0 * a0.z + w1 * a1.z) + (w2 * a2.z + w3 * a3.z), (w0 * a0.w + w1 * a1.w) + (w2 * a2.w + w3 * a3.w))
+    hx[ky][0] = FRTM_DOT4(v[0], v[1], v[2], v[3], E0, E1, E2, E3);
+    hx[ky][1] = FRTM_DOT4(v[0], v[1], v[2], v[3], E3, E2, E1, E0);
+    hx[ky][2] = FRTM_DOT4(v[1], v[2], v[3], v[4], E0, E1, E2, E3);
+    hx[ky][3] = FRTM_DOT4(v[1], v[2], v[3], v[4], E3, E2, E1, E0);
   }
 #pragma unroll
   for (int ry = 0; ry < 2; ++ry) {
-    const int oy = 2 * m + ry - 1;
+    const int oy = 2 * m + ry - 1;                              // pre-crop row 2m + ry -> cropped 2m + ry - 1
     if (oy < 0 || oy >= Ho) continue;
 #pragma unroll
-    for (int rx = 0; rx < 2; ++rx) {
-      const int ox = 2 * n + rx - 1;
+    for (int ph = 0; ph < 4; ++ph) {
+      const int ox = 2 * n + ph - 1;
       if (ox < 0 || ox >= Wo) continue;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int ky = 0; ky < 4; ++ky) {
-        const float wy = ry ? kCubicE[3 - ky] : kCubicE[ky];
-        float4 row = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int kx = 0; kx < 4; ++kx) {
-          const float wt = wy * (rx ? kCubicE[3 - kx] : kCubicE[kx]);   // outer-product filter, like the reference
-          const float4 v = win[ky][kx];
-          row.x = fmaf(wt, v.x, row.x); row.y = fmaf(wt, v.y, row.y); row.z = fmaf(wt, v.z, row.z); row.w = fmaf(wt, v.w, row.w);
-        }
-        acc.x += row.x; acc.y += row.y; acc.z += row.z; acc.w += row.w;
-      }
+      const float4 acc = ry ? FRTM_DOT4(hx[0][ph], hx[1][ph], hx[2][ph], hx[3][ph], E3, E2, E1, E0)
+                            : FRTM_DOT4(hx[0][ph], hx[1][ph], hx[2][ph], hx[3][ph], E0, E1, E2, E3);
       const int64_t o = (((int64_t)b * Ho + oy) * Wo + ox) * C + c4 * 4;
       if (y) *reinterpret_cast<float4 *>(y + o) = acc;
       if (y_hi) {   // split planes of 16*x for the tensor-core conv that follows (conv_tc.cu)
-        const float sc[4] = {acc.x * 16.f, acc.y * 16.f, acc.z * 16.f, acc.w * 16.f};
-        __align__(8) __half hh[4];
-        __align__(8) __half ll[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          hh[j] = __float2half_rn(sc[j]);
-          ll[j] = __float2half_rn(sc[j] - __half2float(hh[j]));
-        }
-        *reinterpret_cast<uint2 *>(y_hi + o) = *reinterpret_cast<const uint2 *>(hh);
-        *reinterpret_cast<uint2 *>(y_lo + o) = *reinterpret_cast<const uint2 *>(ll);
+        const __half2 h01 = __floats2half2_rn(acc.x * 16.f, acc.y * 16.f), h23 = __floats2half2_rn(acc.z * 16.f, acc.w * 16.f);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(acc.x * 16.f - f01.x, acc.y * 16.f - f01.y);
+        const __half2 l23 = __floats2half2_rn(acc.z * 16.f - f23.x, acc.w * 16.f - f23.y);
+        uint2 ph_, pl_;
+        ph_.x = *reinterpret_cast<const uint32_t *>(&h01); ph_.y = *reinterpret_cast<const uint32_t *>(&h23);
+        pl_.x = *reinterpret_cast<const uint32_t *>(&l01); pl_.y = *reinterpret_cast<const uint32_t *>(&l23);
+        *reinterpret_cast<uint2 *>(y_hi + o) = ph_;
+        *reinterpret_cast<uint2 *>(y_lo + o) = pl_;
       }
     }
   }
+#undef FRTM_DOT4
 }
 
 // ---------------------------------------------------------------- global average pool ---------------------------
@@ -663,7 +665,7 @@ extern "C" int frtm_resize_bilinear_nhwc(const float *x, int B, int H, int W, in
 extern "C" int frtm_pyrup_bicubic_nhwc(const float *x, int B, int H, int W, int C, float *y, void *y_hi, void *y_lo,
                                        void *stream) {
   FRTM_REQUIRE(x && (y || y_hi) && C % 4 == 0 && (!y_hi || y_lo), "pyrup_bicubic: bad arguments");
-  const int64_t total = (int64_t)B * (H + 1) * (W + 1) * (C / 4);
+  const int64_t total = (int64_t)B * (H + 1) * ((W + 2) / 2) * (C / 4);
   pyrup_bicubic_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, C, y, (__half *)y_hi, (__half *)y_lo);
   FRTM_CHECK_LAUNCH("pyrup_bicubic");
   return FRTM_OK;
