@@ -70,6 +70,11 @@ class Tracker(nn.Module):
         self.augment_workers = 4    # host threads preparing first-frame augmentations of several new objects at once
         self.block_batching = True  # run_sequence batches up to max_block frames between two filter updates
         self.max_block = 8
+        # Experimental, off by default: full blocks (max_block frames, no object starting inside) captured once per sequence
+        # as a CUDA graph and replayed (~170 launches and their Python cost per block -> one graph launch).  The capture
+        # still trips over a pageable host->device copy somewhere on the block path; falls back to eager on any error.
+        self.graph_blocks = False
+        self._blk_graph = None
         self._stack = None          # cached stacked projection of the live objects
         self._fbuf = None           # (maxN, c, 3, 3) contiguous filters (each Discriminator.filter.weight is a view)
         self._last_labels = None
@@ -114,6 +119,7 @@ class Tracker(nn.Module):
         self._stack = None
         self._fbuf = None
         self._gn_table = None
+        self._blk_graph = None
         self._lut = torch.tensor([0] + list(sequence.obj_ids), dtype=torch.uint8, device=self.device)
         N = 0
         if speedrun:
@@ -308,9 +314,87 @@ class Tracker(nn.Module):
     def _track_block(self, images):
         """Tracks ``len(images)`` consecutive frames in one batched pass; returns the list of uint8 label maps."""
         nF = len(images)
+        if self.graph_blocks and nF == self.max_block and nF > 1 and self.disc_params["update_filters"] \
+                and not any(t.start_frame == self.current_frame for t in self.targets.values()):
+            out = self._track_block_graphed(images)
+            if out is not None:
+                return out
+        return self._track_block_eager(images)
+
+    def _track_block_graphed(self, images):
+        """Replay (or capture, the first time this sequence sees a full block) the CUDA graph of one full block."""
+        live = self._live()
+        nF, n = len(images), len(live)
+        d0 = live[0].discriminator
+        if d0.pw_params is None or d0.pw_params["method"] != "hinge":
+            return None
+        if any(t.discriminator.frame_num % t.discriminator.train_skipping != 0 for t in live):
+            return None                                    # not aligned to the update schedule: eager
+        key = (nF, tuple(t.object_id for t in live), tuple(images[0].shape[-2:]), d0.memory.samples.data_ptr(),
+               0 if self._fbuf is None else self._fbuf.data_ptr())
+        g = self._blk_graph
+        frames = [im if im.dim() == 3 else im[0] for im in images]
+        main = torch.cuda.current_stream()
+        if g is None or g["key"] != key:
+            self._blk_graph = None
+            static_in = torch.stack(frames)
+            # everything the eager path creates lazily and caches on the tracker is created BEFORE the capture, so no
+            # long-lived tensor comes out of the graph's private memory pool
+            dev = static_in.device
+            self._stacked_projection(live)
+            if getattr(self, "_fidx", None) is None or self._fidx[0] != (nF, n):
+                self._fidx = ((nF, n), torch.arange(n, dtype=torch.int32, device=dev).repeat(nF).contiguous())
+            if getattr(self, "_counts", None) is None or self._counts.numel() < n:
+                self._counts = torch.zeros(max(n, 8), dtype=torch.int32, device=dev)
+                self._gn_table = None
+            if getattr(self, "_counts_blk", None) is None or self._counts_blk.shape[0] < nF or self._counts_blk.shape[1] != n:
+                self._counts_blk = torch.zeros((self.max_block, n), dtype=torch.int32, device=dev)
+            self._ensure_gn_table(live, list(range(n)))
+            side = torch.cuda.Stream(device=dev)
+            graph = torch.cuda.CUDAGraph()
+            side.wait_stream(main)
+            frame_nums = [t.discriminator.frame_num for t in live]
+            try:
+                with torch.cuda.stream(side):
+                    graph.capture_begin(capture_error_mode="relaxed")
+                    try:
+                        self._track_block_eager([static_in[f] for f in range(nF)], stacked=static_in)
+                    finally:
+                        graph.capture_end()
+            except Exception as e:                                           # noqa: BLE001 - any capture problem -> eager
+                import warnings
+                warnings.warn("frtm_vos_b200: CUDA-graph capture of the track block failed (%s); running eagerly" % (e,))
+                self.graph_blocks = False
+                for t, fn in zip(live, frame_nums):
+                    t.discriminator.frame_num = fn
+                self._gn_table = None
+                return None
+            main.wait_stream(side)
+            # capture records, it does not execute: undo the host-side bookkeeping of the capture pass, then replay
+            for t, fn in zip(live, frame_nums):
+                t.discriminator.frame_num = fn
+            g = dict(key=key, graph=graph, static_in=static_in, labels=self._blk_labels_all, masks=self.current_masks,
+                     samples=[t.discriminator.current_sample for t in live], keep=(side,))
+            self._blk_graph = g
+        else:
+            torch.stack(frames, out=g["static_in"])
+        g["graph"].replay()
+        labels = g["labels"].clone()                      # the static buffers are overwritten by the next replay
+        for t, cs in zip(live, g["samples"]):
+            t.discriminator.frame_num += nF
+            t.discriminator.current_sample = cs
+        self.current_masks = g["masks"]
+        self._last_labels = labels[nF - 1]
+        return [labels[f] for f in range(nF)]
+
+    def _track_block_eager(self, images, stacked=None):
+        nF = len(images)
         im_size = images[0].shape[-2:]
-        batch = torch.stack([im if im.dim() == 3 else im[0] for im in images]) if nF > 1 else \
-            (images[0] if images[0].dim() == 4 else images[0].unsqueeze(0))
+        if stacked is not None:
+            batch = stacked
+        else:
+            batch = torch.stack([im if im.dim() == 3 else im[0] for im in images]) if nF > 1 else \
+                (images[0] if images[0].dim() == 4 else images[0].unsqueeze(0))
         feats, _, _ = self.feature_extractor.forward_split(batch)
         live = self._live()
         n = len(live)
@@ -361,6 +445,7 @@ class Tracker(nn.Module):
                 self._batched_gn_update(live, due)
             self.current_masks = masks_all[nF - 1]
             self._last_labels = labels_all[nF - 1]
+            self._blk_labels_all = labels_all
             return out_labels
         for f in range(nF):
             # merge (objects initialised on this frame take part with their start masks and suppress the others)
@@ -395,6 +480,19 @@ class Tracker(nn.Module):
         """One set of launches for the filter updates of all objects that are due on this frame (grid.y = object)."""
         import ctypes
         from .._lib import lib, ptr, stream
+        self._ensure_gn_table(live, due)
+        _, table, ws, nbytes = self._gn_table
+        d0 = live[due[0]].discriminator
+        cap, c, h, w = d0.memory.samples.shape
+        iters = [int(v) for v in d0.update_iters]
+        arr = (ctypes.c_int * len(iters))(*iters)
+        lib().gn_update_batched(ptr(table), len(due), 1, cap, c, h, w, arr, len(iters), float(d0.filter_reg[-1]),
+                                float(d0.precond[-1]), float(d0.direction_forget_factor), int(d0.min_px), ptr(ws), nbytes, stream())
+
+    def _ensure_gn_table(self, live, due):
+        """(Re)build the device pointer table and the workspace of the batched filter update when the object set changes."""
+        import ctypes
+        from .._lib import lib, ptr, stream
         key = tuple((live[k].object_id, live[k].discriminator.filter.weight.data_ptr()) for k in due)
         if getattr(self, "_gn_table", None) is None or self._gn_table[0] != key:
             rows = [[], [], [], [], [], [], [], []]
@@ -413,10 +511,3 @@ class Tracker(nn.Module):
             nbytes = len(due) * lib().gn_update_workspace(cap, c, h, w)
             ws = torch.empty(nbytes // 4, device=table.device, dtype=torch.float32)
             self._gn_table = (key, table, ws, nbytes)
-        _, table, ws, nbytes = self._gn_table
-        d0 = live[due[0]].discriminator
-        cap, c, h, w = d0.memory.samples.shape
-        iters = [int(v) for v in d0.update_iters]
-        arr = (ctypes.c_int * len(iters))(*iters)
-        lib().gn_update_batched(ptr(table), len(due), 1, cap, c, h, w, arr, len(iters), float(d0.filter_reg[-1]),
-                                float(d0.precond[-1]), float(d0.direction_forget_factor), int(d0.min_px), ptr(ws), nbytes, stream())
