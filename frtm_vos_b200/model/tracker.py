@@ -20,6 +20,8 @@ from __future__ import annotations
 from time import time
 
 import numpy as np
+import os
+
 import torch
 import torch.nn as nn
 
@@ -70,10 +72,12 @@ class Tracker(nn.Module):
         self.augment_workers = 4    # host threads preparing first-frame augmentations of several new objects at once
         self.block_batching = True  # run_sequence batches up to max_block frames between two filter updates
         self.max_block = 8
-        # Experimental, off by default: full blocks (max_block frames, no object starting inside) captured once per sequence
-        # as a CUDA graph and replayed (~170 launches and their Python cost per block -> one graph launch).  The capture
-        # still trips over a pageable host->device copy somewhere on the block path; falls back to eager on any error.
-        self.graph_blocks = False
+        # Experimental, off by default (FRTM_GRAPH_BLOCKS=1): full blocks (max_block frames, no object starting inside) are
+        # captured once per sequence as a CUDA graph and replayed.  Measured on B200: because every sequence re-creates its
+        # target-model buffers the graph has to be re-captured per sequence, and capture + instantiation of ~170 nodes
+        # costs more than the seven replays save (630 vs 750 frames/s on config 2).  It pays off only with the per-object
+        # buffers pooled across sequences; kept for that follow-up.
+        self.graph_blocks = os.environ.get("FRTM_GRAPH_BLOCKS", "0") == "1"
         self._blk_graph = None
         self._stack = None          # cached stacked projection of the live objects
         self._fbuf = None           # (maxN, c, 3, 3) contiguous filters (each Discriminator.filter.weight is a view)
@@ -342,6 +346,8 @@ class Tracker(nn.Module):
             # long-lived tensor comes out of the graph's private memory pool
             dev = static_in.device
             self._stacked_projection(live)
+            if getattr(self.refiner, "_packed", 0) is None:
+                self.refiner._pack()                      # host-side weight packing uploads pageable tensors
             if getattr(self, "_fidx", None) is None or self._fidx[0] != (nF, n):
                 self._fidx = ((nF, n), torch.arange(n, dtype=torch.int32, device=dev).repeat(nF).contiguous())
             if getattr(self, "_counts", None) is None or self._counts.numel() < n:
@@ -363,8 +369,11 @@ class Tracker(nn.Module):
                         graph.capture_end()
             except Exception as e:                                           # noqa: BLE001 - any capture problem -> eager
                 import warnings
+                if os.environ.get("FRTM_GRAPH_DEBUG"):
+                    import traceback
+                    traceback.print_exc()
                 warnings.warn("frtm_vos_b200: CUDA-graph capture of the track block failed (%s); running eagerly" % (e,))
-                self.graph_blocks = False
+                self.graph_blocks = os.environ.get("FRTM_GRAPH_BLOCKS", "0") == "1"
                 for t, fn in zip(live, frame_nums):
                     t.discriminator.frame_num = fn
                 self._gn_table = None

@@ -134,3 +134,40 @@ def test_cropped_telea_inpaint_is_identical_to_full_frame():
     edge = np.zeros(image.shape[:2], np.uint8); edge[:20, :30] = 1; edge[-5:, -40:] = 1
     assert np.array_equal(telea_inpaint_cropped(image, edge, 1), cv2.inpaint(image, edge, inpaintRadius=1, flags=cv2.INPAINT_TELEA))
     assert np.array_equal(telea_inpaint_cropped(image, np.zeros_like(edge), 1), image)
+
+
+def test_stem_weight_permutation_matches_patch_order():
+    """ops.stem_weight_as_1x1: k = ky*24 + c*8 + kx (kx = 7 and k >= 168 zero) — the order frtm_stem_patches_u8 writes."""
+    import torch
+    from frtm_vos_b200 import ops
+    w = torch.arange(2 * 3 * 7 * 7, dtype=torch.float32).reshape(2, 3, 7, 7)
+    p = ops.stem_weight_as_1x1(w)
+    assert p.shape == (2, 192, 1, 1)
+    for n, c, ky, kx in [(0, 0, 0, 0), (1, 2, 6, 6), (0, 1, 3, 5), (1, 0, 2, 0)]:
+        assert p[n, ky * 24 + c * 8 + kx, 0, 0] == w[n, c, ky, kx]
+    assert float(p[:, 168:].abs().sum()) == 0.0
+    assert float(p[:, 7:168:8].abs().sum()) == 0.0          # the padding element of every (ky, c) chunk
+    # a 1x1 conv over explicitly gathered patches equals the 7x7 / stride 2 / pad 3 conv
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 3, 12, 15, generator=g)
+    wt = torch.randn(4, 3, 7, 7, generator=g)
+    ref = torch.nn.functional.conv2d(x, wt, None, 2, 3)
+    xp = torch.nn.functional.pad(x, (3, 3, 3, 3))
+    Ho, Wo = ref.shape[-2:]
+    patches = torch.zeros(1, 192, Ho, Wo)
+    for ky in range(7):
+        for c in range(3):
+            for kx in range(7):
+                patches[0, ky * 24 + c * 8 + kx] = xp[0, c, ky:ky + 2 * Ho:2, kx:kx + 2 * Wo:2]
+    out = torch.nn.functional.conv2d(patches, ops.stem_weight_as_1x1(wt))
+    assert (out - ref).abs().max() < 1e-4
+
+
+def test_operator_image_size_formula():
+    """frtm_split_sample_bytes: even tile count of 64 pixels (hi + lo planes) plus 256-pixel stencil chunks."""
+    from frtm_vos_b200._lib import lib
+    L = lib()
+    for c, hw in [(96, 1620), (96, 3600), (64, 117), (96, 28), (112, 136)]:
+        ntiles = -(-hw // 128) * 2
+        nchunks = -(-hw // 256)
+        assert L.split_sample_bytes(c, hw) == ntiles * 2 * c * 64 * 2 + nchunks * 10 * 256 * 4
