@@ -349,6 +349,111 @@ __device__ __forceinline__ int softmax_argmax(const float *__restrict__ m, int N
   return arg;
 }
 
+// Register-resident variant for N <= NMAX objects: the same arithmetic in the same order as merge_masks_kernel below, but every
+// per-object value stays in registers between the passes (one global read of src, one global write of masks).
+template <int NMAX>
+__global__ void __launch_bounds__(256) merge_masks_reg_kernel(const float *__restrict__ src, unsigned long long logit_mask,
+                                                              const uint8_t *__restrict__ suppress, int N, int HW,
+                                                              const uint8_t *__restrict__ lut, int single,
+                                                              float *__restrict__ masks, uint8_t *__restrict__ labels,
+                                                              int *__restrict__ counts, int counts_stride) {
+  src += (int64_t)blockIdx.y * N * HW;
+  masks += (int64_t)blockIdx.y * (N + 1) * HW;
+  labels += (int64_t)blockIdx.y * HW;
+  counts += (int64_t)blockIdx.y * counts_stride;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const float lo = 1e-7f, hi = 1.f - 1e-7f;
+  float m[NMAX];
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n) m[n] = 0.f;
+  if (p < HW) {
+    float bg = INFINITY;
+    const float keep = suppress ? (float)(1 - (int)suppress[p]) : 1.f;
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n) {
+      if (n < N) {
+        float pr = src[(int64_t)n * HW + p];
+        if ((logit_mask >> n) & 1ull) pr = (1.f / (1.f + expf(-pr))) * keep;
+        pr = fminf(fmaxf(pr, lo), hi);
+        m[n] = pr;
+        bg = fminf(bg, 1.f - pr);
+      }
+    }
+    // first softmax / argmax (softmax_argmax on the register copy)
+    const float z0 = bg / (1.f - bg);
+    float mx = z0;
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n)
+      if (n < N) mx = fmaxf(mx, m[n] / (1.f - m[n]));
+    float den = expf(z0 - mx);
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n)
+      if (n < N) den += expf(m[n] / (1.f - m[n]) - mx);
+    float best = expf(z0 - mx) / den;
+    int arg = 0;
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n) {
+      if (n < N) {
+        const float sn = expf(m[n] / (1.f - m[n]) - mx) / den;
+        if (sn > best) { best = sn; arg = n + 1; }
+      }
+    }
+    masks[p] = (arg == 0) ? expf(z0 - mx) / den : 0.f;
+    float bg2 = INFINITY;
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n) {
+      if (n < N) {
+        const float c = m[n];
+        const float sn = (arg == n + 1) ? expf(c / (1.f - c) - mx) / den : 0.f;
+        m[n] = sn;
+        masks[(int64_t)(n + 1) * HW + p] = sn;
+        bg2 = fminf(bg2, 1.f - fminf(fmaxf(sn, lo), hi));
+      }
+    }
+    int lab;
+    if (single) {
+      lab = m[0] > 0.5f ? 1 : 0;
+    } else {
+      float mx2 = bg2 / (1.f - bg2);
+#pragma unroll
+      for (int n = 0; n < NMAX; ++n) {
+        if (n < N) {
+          const float c = fminf(fmaxf(m[n], lo), hi);
+          mx2 = fmaxf(mx2, c / (1.f - c));
+        }
+      }
+      float den2 = expf(bg2 / (1.f - bg2) - mx2);
+#pragma unroll
+      for (int n = 0; n < NMAX; ++n) {
+        if (n < N) {
+          const float c = fminf(fmaxf(m[n], lo), hi);
+          den2 += expf(c / (1.f - c) - mx2);
+        }
+      }
+      float best2 = expf(bg2 / (1.f - bg2) - mx2) / den2;
+      lab = 0;
+#pragma unroll
+      for (int n = 0; n < NMAX; ++n) {
+        if (n < N) {
+          const float c = fminf(fmaxf(m[n], lo), hi);
+          const float s2 = expf(c / (1.f - c) - mx2) / den2;
+          if (s2 > best2) { best2 = s2; lab = n + 1; }
+        }
+      }
+    }
+    labels[p] = lut[lab];
+  }
+  // per-object count of pixels > 0.5 (update gate), one atomic per warp per object (integer -> deterministic)
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n) {
+    if (n < N) {
+      const bool on = (p < HW) && m[n] > 0.5f;
+      const unsigned b = __ballot_sync(0xffffffffu, on);
+      if ((threadIdx.x & 31) == 0 && b) atomicAdd(&counts[n], __popc(b));
+    }
+  }
+}
+
 __global__ void merge_masks_kernel(const float *__restrict__ src, unsigned long long logit_mask,
                                    const uint8_t *__restrict__ suppress, int N, int HW, const uint8_t *__restrict__ lut,
                                    int single, float *__restrict__ masks, uint8_t *__restrict__ labels,
@@ -737,8 +842,12 @@ extern "C" int frtm_merge_masks(const float *src, uint64_t logit_mask, const uin
                                 const uint8_t *lut, int single_object, float *masks, uint8_t *labels, int *counts,
                                 void *stream) {
   FRTM_REQUIRE(src && lut && masks && labels && counts && N > 0 && N <= 64, "merge_masks: bad arguments");
-  merge_masks_kernel<<<cdiv(HW, 256), 256, 0, (cudaStream_t)stream>>>(src, (unsigned long long)logit_mask, suppress, N,
-                                                                      HW, lut, single_object, masks, labels, counts, 0);
+  if (N <= 8)
+    merge_masks_reg_kernel<8><<<cdiv(HW, 256), 256, 0, (cudaStream_t)stream>>>(src, (unsigned long long)logit_mask, suppress, N, HW,
+                                                                               lut, single_object, masks, labels, counts, 0);
+  else
+    merge_masks_kernel<<<cdiv(HW, 256), 256, 0, (cudaStream_t)stream>>>(src, (unsigned long long)logit_mask, suppress, N,
+                                                                        HW, lut, single_object, masks, labels, counts, 0);
   FRTM_CHECK_LAUNCH("merge_masks");
   return FRTM_OK;
 }
@@ -748,9 +857,14 @@ extern "C" int frtm_merge_masks_frames(const float *src, int F, uint64_t logit_m
                                        void *stream) {
   FRTM_REQUIRE(src && lut && masks && labels && counts && N > 0 && N <= 64 && F > 0 && F <= 65535 && counts_stride >= N,
                "merge_masks_frames: bad arguments");
-  merge_masks_kernel<<<dim3(cdiv(HW, 256), F), 256, 0, (cudaStream_t)stream>>>(src, (unsigned long long)logit_mask, nullptr, N, HW,
-                                                                               lut, single_object, masks, labels, counts,
-                                                                               counts_stride);
+  if (N <= 8)
+    merge_masks_reg_kernel<8><<<dim3(cdiv(HW, 256), F), 256, 0, (cudaStream_t)stream>>>(src, (unsigned long long)logit_mask, nullptr, N,
+                                                                                        HW, lut, single_object, masks, labels,
+                                                                                        counts, counts_stride);
+  else
+    merge_masks_kernel<<<dim3(cdiv(HW, 256), F), 256, 0, (cudaStream_t)stream>>>(src, (unsigned long long)logit_mask, nullptr, N, HW,
+                                                                                 lut, single_object, masks, labels, counts,
+                                                                                 counts_stride);
   FRTM_CHECK_LAUNCH("merge_masks_frames");
   return FRTM_OK;
 }

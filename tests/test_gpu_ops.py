@@ -224,6 +224,41 @@ def test_merge_golden(golden):
     assert (l1.cpu() != R.labels_from_masks(ref1.clone(), lut, True)[0]).float().mean() < 1e-4
 
 
+@pytest.mark.parametrize("N", [1, 2, 5, 8, 9, 12])
+def test_merge_object_counts(N):
+    """Both dispatch branches of frtm_merge_masks (register kernel N <= 8, general kernel above) and the all-frames entry
+    against the oracle restatement of tracker.py:208-221 / :143-150; ragged size (HW not a multiple of the block)."""
+    ops = _ops()
+    from oracle import frtm_ref as R
+    gen = torch.Generator().manual_seed(100 + N)
+    H, W, Fr = 37, 53, 3
+    lg = torch.randn(Fr, N, H, W, generator=gen) * 1.5
+    lg[:, :, :3] = 30.0                                     # saturated rows: every object at the clamp
+    lg[:, :, -3:] = -30.0
+    lut = torch.arange(0, 2 * (N + 1), 2, dtype=torch.uint8)
+    single = N == 1
+    counts = torch.full((Fr, N + 2), 7, dtype=torch.int32, device=DEV)
+    masks_f, labels_f = ops.merge_masks_frames(lg.to(DEV), (1 << N) - 1, lut.to(DEV), single, counts)
+    for f in range(Fr):
+        cm = torch.zeros(N + 1, H, W)
+        cm[1:] = torch.sigmoid(lg[f])
+        ref = R.merge_masks(cm)
+        ref_l = R.labels_from_masks(ref.clone(), lut, single)
+        ref_l = ref_l[0] if ref_l.dim() == 3 else ref_l
+        masks, labels, cnt = ops.merge_masks(lg[f].contiguous().to(DEV), (1 << N) - 1, None, lut.to(DEV), single)
+        # the two entry points run the same arithmetic
+        assert torch.equal(masks, masks_f[f]) and torch.equal(labels, labels_f[f])
+        assert torch.equal(cnt, counts[f, :N])
+        # away from saturation (p -> 1 makes p/(1-p) ill-conditioned, cf. test_gpu_model) the merged scores agree to rounding
+        cond = (cm[1:].max(0).values < 0.9)
+        assert ((masks.cpu() - ref).abs() * cond).max() < 2e-5
+        assert ((labels.cpu() != ref_l) & cond).float().mean() < 1e-3
+        # the count is the exact integer count of the masks the kernel wrote
+        assert cnt.cpu().tolist() == [int((masks[i + 1] > 0.5).sum()) for i in range(N)]
+        # invariants: one-hot support, labels consistent with the written masks
+        assert int(((masks > 0).sum(0) > 1).sum()) == 0
+
+
 def test_final_conv_commutes_with_upsampling():
     """conv3x3_to1_upsampled == conv3x3_to1(resize(pyrup(x))) (the reference order, seg_network.py:141-145)."""
     ops = _ops()
