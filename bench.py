@@ -29,6 +29,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+if int(os.environ.get("WORLD_SIZE", 1)) > 1:
+    # several ranks share the host: idle OpenMP workers of the few CPU-side torch ops must sleep, not spin
+    os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
+
 import torch  # noqa: E402
 
 CONFIGS = {
@@ -154,12 +158,20 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
     # host side per rank = OpenCV inpaint + kernel launches: do not oversubscribe the host cores with N ranks
-    torch.set_num_threads(max(1, (os.cpu_count() or 8) // max(world, 1)))
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 8)
+    torch.set_num_threads(max(1, cores // max(world, 1)))
     try:
         import cv2
-        cv2.setNumThreads(max(1, (os.cpu_count() or 8) // max(world, 1)))
+        cv2.setNumThreads(max(1, cores // max(world, 1)))
     except Exception:
         pass
+    from frtm_vos_b200.parallel import set_host_wait_policy
+    wait_policy = os.environ.get("FRTM_HOST_WAIT", "yield")
+    try:                                           # before torch creates the context: waiting host threads give their core away
+        set_host_wait_policy(local, wait_policy)
+    except (OSError, RuntimeError, KeyError) as e:
+        print("bench.py: host wait policy left at the CUDA default (%s)" % (e,), file=sys.stderr)
+        wait_policy = "default"
     torch.cuda.set_device(local)
     dev = "cuda:%d" % local
     dist = None
@@ -337,7 +349,8 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": cfg["name"], "sequences_per_gpu": 1, "objects": cfg["objects"], "frames": frames,
                    "init_iters": list(dp["init_iters"]), "update_iters": list(dp["update_iters"]), "memory_size": cfg["memory"],
-                   "l2": "256 MiB buffer written between steps", "parallelism": "sequence-sharded x%d, end-of-step all_gather of labels" % world},
+                   "l2": "256 MiB buffer written between steps", "parallelism": "sequence-sharded x%d, end-of-step all_gather of labels" % world,
+                   "host": "%d cores, wait policy %s" % (cores, wait_policy)},
         "e2e": {"value": e2e_v, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": k_e2e},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_conv": roofline_conv,
     }

@@ -36,3 +36,29 @@ def gather_label_maps(local: torch.Tensor, world_size: int, group=None) -> torch
     out = torch.empty((world_size * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, local, group=group)          # concatenated along dim 0 (accepted by gloo and NCCL)
     return out.view((world_size,) + tuple(local.shape))
+
+
+_WAIT_FLAGS = {"auto": 0, "spin": 1, "yield": 2, "block": 4}      # CU_CTX_SCHED_*
+
+
+def set_host_wait_policy(device_index: int, policy: str = "yield") -> int:
+    """How this process's host threads wait for GPU ``device_index`` (stream / event synchronisation).
+
+    The CUDA default spins.  With one process per GPU plus the augmentation workers, a host with fewer cores than
+    (ranks x threads) then spends its cores on waiting threads instead of on the ranks that still have kernels to
+    launch; ``"yield"`` gives the core away while waiting and costs nothing when cores are free.  Works before or after
+    the device's primary context exists (driver API, no torch involvement).  Returns the flags now in force."""
+    import ctypes
+    cu = ctypes.CDLL("libcuda.so.1")
+    dev, flags, active = ctypes.c_int(), ctypes.c_uint(), ctypes.c_int()
+
+    def chk(rc, what):
+        if rc != 0:
+            raise RuntimeError("frtm_vos_b200.parallel.set_host_wait_policy: %s failed (CUresult %d)" % (what, rc))
+    chk(cu.cuInit(0), "cuInit")
+    chk(cu.cuDeviceGet(ctypes.byref(dev), int(device_index)), "cuDeviceGet")
+    chk(cu.cuDevicePrimaryCtxGetState(dev, ctypes.byref(flags), ctypes.byref(active)), "cuDevicePrimaryCtxGetState")
+    want = (flags.value & ~0x7) | _WAIT_FLAGS[policy]
+    chk(cu.cuDevicePrimaryCtxSetFlags_v2(dev, ctypes.c_uint(want)), "cuDevicePrimaryCtxSetFlags")
+    chk(cu.cuDevicePrimaryCtxGetState(dev, ctypes.byref(flags), ctypes.byref(active)), "cuDevicePrimaryCtxGetState")
+    return int(flags.value)

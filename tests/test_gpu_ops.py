@@ -329,3 +329,16 @@ def test_stem_as_tensor_core_conv_over_patches(hw):
     out = ops.conv2d_tc(ops.stem_patches(img.to(DEV)), pc, relu=True)["y"]
     assert out.shape == (B, (hw[0] - 1) // 2 + 1, (hw[1] - 1) // 2 + 1, 64)
     assert (out.cpu().permute(0, 3, 1, 2) - ref).abs().max() < 1e-5 * max(1.0, ref.abs().max().item())
+
+
+def test_host_wait_policy_applies_to_live_context():
+    """parallel.set_host_wait_policy changes the primary context's scheduling flags in place (what bench.py relies on)."""
+    from frtm_vos_b200.parallel import set_host_wait_policy
+    torch.zeros(1, device=DEV)                      # context exists
+    try:
+        assert set_host_wait_policy(0, "yield") & 0x7 == 2
+        assert set_host_wait_policy(0, "spin") & 0x7 == 1
+    finally:
+        assert set_host_wait_policy(0, "auto") & 0x7 == 0
+    x = torch.arange(10, device=DEV).sum().item()   # synchronising call still works
+    assert x == 45

@@ -3,6 +3,7 @@
 import os
 import socket
 
+import pytest
 import torch
 import torch.multiprocessing as mp
 
@@ -46,3 +47,18 @@ def test_gather_label_maps_gloo_world2():
     res = sorted(q.get(timeout=120) for _ in range(2))
     [p.join(60) for p in procs]
     assert res == [(0, True), (1, True)]
+
+
+def test_host_wait_policy_rejects_unknown_and_fails_loudly_without_driver():
+    """set_host_wait_policy: unknown policy names are a KeyError before anything is touched; without a CUDA driver
+    (this container) it raises instead of silently doing nothing."""
+    import ctypes.util
+    from frtm_vos_b200.parallel import set_host_wait_policy, _WAIT_FLAGS
+    assert _WAIT_FLAGS == {"auto": 0, "spin": 1, "yield": 2, "block": 4}      # CU_CTX_SCHED_* values
+    import torch
+    if torch.cuda.is_available():
+        with pytest.raises(KeyError):
+            set_host_wait_policy(0, "sleepy")
+    else:
+        with pytest.raises((OSError, RuntimeError)):
+            set_host_wait_policy(0, "yield")
