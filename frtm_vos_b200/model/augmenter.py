@@ -95,8 +95,9 @@ def draw_specs(pool: dict, rng=np.random) -> List[dict]:
     return specs
 
 
-def spec_transform(spec: dict, bbox, im_size, limit_scale: bool = True) -> Tuple[np.ndarray, np.ndarray]:
-    """Affine 3x3 + blur kernel of one spec (augmenter.py:224-276)."""
+def spec_transform(spec: dict, bbox, im_size, limit_scale: bool = True, with_blur: bool = True) -> Tuple[np.ndarray, np.ndarray]:
+    """Affine 3x3 + blur kernel of one spec (augmenter.py:224-276).  ``with_blur=False`` skips building the kernel (mask warps
+    use the affine part only) and returns ``None`` for it."""
     cx, cy, bw, bh = bbox
     assert bw > 0 and bh > 0
     ih, iw = im_size
@@ -113,7 +114,9 @@ def spec_transform(spec: dict, bbox, im_size, limit_scale: bool = True) -> Tuple
     loc = spec["location"]
     T = _mat_translate(loc[0] * iw, loc[1] * ih) @ _mat_skew(*spec["skew"]) @ _mat_rotate(spec["rotation"] * d2r) @ \
         _mat_scale(mirror * s, s) @ _mat_translate(-cx, -cy)
-    if spec["blur_size"] > 0:
+    if not with_blur:
+        G = None
+    elif spec["blur_size"] > 0:
         G = directional_blur_kernel(spec["blur_size"], 0.1, _mat_rotate(spec["blur_angle"] * d2r)[:2, :2])
     else:
         G = np.array([[1.0]], dtype=np.float32)
@@ -140,18 +143,25 @@ def _blur_channels(img: torch.Tensor, kernel: np.ndarray) -> torch.Tensor:
     return F.conv2d(img.unsqueeze(1), k, padding=(fh // 2, fw // 2)).squeeze(1)
 
 
+def _hole_box(hole2d: np.ndarray, radius: int, margin: int, shape):
+    """Bounding box (y0, y1, x0, x1) of the nonzero pixels of ``hole2d`` grown by ``margin + 2*radius``, clipped; None if empty."""
+    ys = np.flatnonzero(hole2d.any(axis=1))
+    xs = np.flatnonzero(hole2d.any(axis=0))
+    if ys.size == 0:
+        return None
+    m = margin + 2 * radius
+    return (max(int(ys[0]) - m, 0), min(int(ys[-1]) + m + 1, shape[0]), max(int(xs[0]) - m, 0), min(int(xs[-1]) + m + 1, shape[1]))
+
+
 def telea_inpaint_cropped(image: np.ndarray, hole: np.ndarray, radius: int, margin: int = 16) -> np.ndarray:
     """``cv2.inpaint(image, hole, radius, INPAINT_TELEA)`` evaluated on the hole's bounding box grown by ``margin`` pixels and
     pasted back.  Telea's fast-marching fill only looks ``radius`` pixels beyond the hole, so the result is identical
     (tests/test_host.py) while the cost no longer scales with the frame."""
     hole2d = hole.reshape(hole.shape[0], hole.shape[1])
-    ys = np.flatnonzero(hole2d.any(axis=1))
-    xs = np.flatnonzero(hole2d.any(axis=0))
-    if ys.size == 0:
+    box = _hole_box(hole2d, radius, margin, image.shape[:2])
+    if box is None:
         return image.copy()
-    m = margin + 2 * radius
-    y0, y1 = max(int(ys[0]) - m, 0), min(int(ys[-1]) + m + 1, image.shape[0])
-    x0, x1 = max(int(xs[0]) - m, 0), min(int(xs[-1]) + m + 1, image.shape[1])
+    y0, y1, x0, x1 = box
     out = image.copy()
     out[y0:y1, x0:x1] = cv2.inpaint(np.ascontiguousarray(image[y0:y1, x0:x1]), np.ascontiguousarray(hole2d[y0:y1, x0:x1]),
                                     inpaintRadius=radius, flags=cv2.INPAINT_TELEA)
@@ -160,17 +170,27 @@ def telea_inpaint_cropped(image: np.ndarray, hole: np.ndarray, radius: int, marg
 
 def cut_and_inpaint(im: torch.Tensor, mask: torch.Tensor, d: int = 1, f: int = 1):
     """Object cut-out (RGBA, feathered alpha) + Telea-inpainted background (augmenter.py:297-340)."""
-    image = im.detach().cpu().numpy().transpose((1, 2, 0))
-    m = (mask.squeeze() > 0).byte().detach().cpu().numpy()[..., None]
     if d == 1 and f == 1:
         # The configuration the tracker uses (augmenter.py:497).  With 1x1 structuring elements and 1x1 box blurs,
         # erode/blur are identities: alpha = 255*m, and the "blur the inpainted border" blend x*r + (1-r)*x with
-        # r in {0,1} returns x exactly, so only the cut-out, the 2x2 dilation and the Telea inpaint remain.
-        cut = np.concatenate((m * image, m * 255), axis=-1)
-        outer = cv2.dilate(m, cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (2, 2)))
-        bg_np = telea_inpaint_cropped(np.ascontiguousarray(image), outer, 1)
-        return (torch.from_numpy(np.ascontiguousarray(cut.transpose((2, 0, 1)))),
-                torch.from_numpy(np.ascontiguousarray(bg_np.transpose((2, 0, 1)))))
+        # r in {0,1} returns x exactly, so only the cut-out, the 2x2 dilation and the Telea inpaint remain.  Everything
+        # stays planar (C,H,W); only the hole's bounding box is interleaved for cv2.inpaint and pasted back.
+        chw = im.detach().cpu().numpy()
+        m2 = (mask.squeeze() > 0).byte().detach().cpu().numpy()
+        cut = np.empty((4,) + m2.shape, dtype=np.uint8)
+        np.multiply(chw, m2[None], out=cut[:3])
+        np.multiply(m2, 255, out=cut[3])
+        outer = cv2.dilate(m2, cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (2, 2)))
+        bg = chw.copy()
+        box = _hole_box(outer, 1, 16, m2.shape)
+        if box is not None:
+            y0, y1, x0, x1 = box
+            patch = cv2.inpaint(np.ascontiguousarray(chw[:, y0:y1, x0:x1].transpose((1, 2, 0))),
+                                np.ascontiguousarray(outer[y0:y1, x0:x1]), inpaintRadius=1, flags=cv2.INPAINT_TELEA)
+            bg[:, y0:y1, x0:x1] = patch.transpose((2, 0, 1))
+        return torch.from_numpy(cut), torch.from_numpy(bg)
+    image = im.detach().cpu().numpy().transpose((1, 2, 0))
+    m = (mask.squeeze() > 0).byte().detach().cpu().numpy()[..., None]
     cut = m * image
     se = cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (f, f))
     alpha = cv2.blur(cv2.erode(m, se) * 255, (f, f))[..., None]
@@ -215,6 +235,17 @@ def target_locations(n: int, im_size, rng=np.random) -> List[Tuple[float, float]
     return pts[:n]
 
 
+_INPAINT_POOL = None
+
+
+def _inpaint_pool():
+    global _INPAINT_POOL
+    if _INPAINT_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _INPAINT_POOL = ThreadPoolExecutor(max_workers=4, thread_name_prefix="frtm-inpaint")
+    return _INPAINT_POOL
+
+
 class ImageAugmenter:
     """Drop-in for the reference class of the same name: ``augment_first_frame(im, mask)``."""
 
@@ -224,7 +255,7 @@ class ImageAugmenter:
         self.device_render = device_render     # CUDA inputs: render the selected views with libfrtm_b200 kernels
 
     def _warp_mask(self, mask, fg_spec, bbox, size):
-        T, _ = spec_transform(fg_spec, bbox, size)
+        T, _ = spec_transform(fg_spec, bbox, size, with_blur=False)
         return warp_affine_host(mask, np.array(T, dtype=np.float32), size, "nearest")
 
     def _render(self, bg, cut, fg_spec, bbox, bg_spec):
@@ -258,7 +289,7 @@ class ImageAugmenter:
         counts = torch.zeros(n, device=mask_d.device, dtype=torch.int32)
         src = mask_d.reshape(H, W).contiguous()
         for j, fs in enumerate(fg_specs):
-            T, _ = spec_transform(fs, bbox, size)
+            T, _ = spec_transform(fs, bbox, size, with_blur=False)
             M = (ctypes.c_double * 6)(*np.asarray(T, dtype=np.float32)[:2, :].astype(np.float64).ravel())
             L.warp_mask_nearest(ptr(src), H, W, ptr(out[j]), H, W, M, 1, counts[j:j + 1].data_ptr(), stream())
         return out, counts.tolist()
@@ -312,7 +343,13 @@ class ImageAugmenter:
         bbox = mask_center_bbox(lb_h)
         if tuple(bbox[-2:]) == (0, 0):
             raise ValueError("Augmentation failed: No object to augment.")
-        cut, bg = cut_and_inpaint(im_h, lb_h, d=1, f=1)
+        on_device = dev.type == "cuda" and self.device_render
+        if on_device:
+            # the Telea inpaint (5-20 ms of OpenCV, GIL released) draws no random numbers and is needed only by the
+            # rendering at the end: it runs beside the spec drawing / candidate mask warps below
+            pending = _inpaint_pool().submit(cut_and_inpaint, im_h, lb_h, 1, 1)
+        else:
+            cut, bg = cut_and_inpaint(im_h, lb_h, d=1, f=1)
 
         fg_pool = copy.deepcopy(dict(p["fg_aug_params"]))
         fg_pool["location"] = target_locations(p["num_aug"], size, rng)
@@ -323,7 +360,6 @@ class ImageAugmenter:
         # The reference renders all 19 candidate views of a round and keeps 4 of the valid ones.  Validity depends
         # only on the (cheap, nearest-neighbour) warped mask, so decide first and render only the survivors: same
         # random draws, same selected views, ~5x less host work.
-        on_device = dev.type == "cuda" and self.device_render
         cand, masks = [], []
         while len(cand) < want:
             fg_specs = draw_specs(fg_pool, rng)
@@ -345,9 +381,10 @@ class ImageAugmenter:
             order = order[:want]
             cand = [cand[i] for i in order]
             masks = [masks[i] for i in order]
-        if dev.type == "cuda" and self.device_render:
-            # rendering (bicubic warps, blur, alpha paste) on the GPU; inpainting, spec drawing and the nearest-neighbour
-            # mask warps above stay on the host like in the reference
+        if on_device:
+            # rendering (bicubic warps, blur, alpha paste) and the nearest-neighbour mask warps on the GPU; inpainting and
+            # spec drawing stay on the host like in the reference
+            cut, bg = pending.result()
             bg_d, cut_d = bg.to(dev), cut.to(dev)
             views = [self._render_device(bg_d, cut_d, fs, bbox, bs) for fs, bs in cand]
             return torch.stack([im] + views), torch.stack([lb.to(dev).reshape(1, *size)] + masks)
