@@ -171,3 +171,64 @@ def test_operator_image_size_formula():
         ntiles = -(-hw // 128) * 2
         nchunks = -(-hw // 256)
         assert L.split_sample_bytes(c, hw) == ntiles * 2 * c * 64 * 2 + nchunks * 10 * 256 * 4
+
+
+def test_block_scheduler_never_crosses_a_filter_update_or_an_object_start():
+    """Tracker._block_length (host logic): a block of frames goes through the network as one batch only if no live
+    object's filter changes inside it — the reference updates a filter when ``frame_num % train_skipping == 0`` after the
+    increment in ``apply`` (model/discriminator.py:201-227) — and no object starts inside it (model/tracker.py:165-191)."""
+    from types import SimpleNamespace as NS
+    from frtm_vos_b200.model.tracker import Tracker
+    rng = np.random.RandomState(3)
+    for trial in range(200):
+        skip = int(rng.choice([1, 3, 8, 16]))
+        max_block = int(rng.choice([1, 4, 8, 12]))
+        seq_len = int(rng.randint(2, 60))
+        starts = sorted(set([0] + [int(x) for x in rng.randint(0, seq_len, size=rng.randint(0, 3))]))
+        targets = {i + 1: NS(start_frame=s, discriminator=NS(frame_num=0, train_skipping=skip)) for i, s in enumerate(starts)}
+        trk = NS(block_batching=True, max_block=max_block, targets=targets)
+        trk._live_at = lambda f, trk=trk: Tracker._live_at(trk, f)
+        has_new = lambda j: j < seq_len and j in starts
+        first = 0
+        while first < seq_len:
+            if has_new(first):
+                n = 1                                                   # run_sequence processes start frames alone
+                assert Tracker._block_length(trk, first, seq_len, has_new) == 1
+            else:
+                n = Tracker._block_length(trk, first, seq_len, has_new)
+            assert 1 <= n <= max(max_block, 1) and first + n <= seq_len
+            live = [t for t in targets.values() if t.start_frame < first]
+            for k in range(n):
+                if k > 0:
+                    assert not has_new(first + k)                       # no object appears inside a block
+                for t in live:
+                    t.discriminator.frame_num += 1                      # Discriminator.apply
+                    if t.discriminator.frame_num % skip == 0:           # an update fires on this frame ...
+                        assert k == n - 1, (trial, first, k, n)         # ... so it must be the block's last frame
+            first += n
+    # batching switched off: always single frames
+    trk = NS(block_batching=False, max_block=8, targets={})
+    trk._live_at = lambda f: []
+    assert Tracker._block_length(trk, 3, 10, lambda j: False) == 1
+
+
+def test_planar_cut_and_inpaint_equals_the_interleaved_formula():
+    """cut_and_inpaint(d=1, f=1) works on planar (C,H,W) arrays and interleaves only the hole's box; it must equal the
+    reference's formula (model/augmenter.py:297-340 at d = f = 1) evaluated on the full interleaved frame."""
+    import cv2
+    from frtm_vos_b200 import synth
+    from frtm_vos_b200.model.augmenter import cut_and_inpaint
+    seq = synth.SyntheticSequence(num_objects=3, num_frames=1, size=GI.MID, seq_id=4)
+    im, lb, ids = seq[0]
+    masks = [(lb == o).byte() for o in ids] + [torch.zeros_like(lb), torch.ones_like(lb)]
+    edge = torch.zeros_like(lb); edge[..., :5, -7:] = 1           # object touching the frame corner
+    for mask in masks + [edge]:
+        image = im.numpy().transpose((1, 2, 0))
+        m = (mask.squeeze() > 0).byte().numpy()[..., None]
+        cut_ref = np.concatenate((m * image, m * 255), axis=-1).transpose((2, 0, 1))
+        outer = cv2.dilate(m, cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (2, 2)))
+        bg_ref = cv2.inpaint(np.ascontiguousarray(image), outer, inpaintRadius=1, flags=cv2.INPAINT_TELEA).transpose((2, 0, 1))
+        cut, bg = cut_and_inpaint(im, mask, 1, 1)
+        assert cut.dtype == torch.uint8 and bg.dtype == torch.uint8 and cut.is_contiguous() and bg.is_contiguous()
+        assert np.array_equal(cut.numpy(), cut_ref) and np.array_equal(bg.numpy(), bg_ref)
+    assert torch.equal(im, seq[0][0])                              # the input frame is not modified in place
