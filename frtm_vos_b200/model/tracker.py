@@ -99,12 +99,20 @@ class Tracker(nn.Module):
         fps_sum, fps_n = 0.0, 0
         print("Evaluating", dataset.name)
         restarted = False
-        for sequence in dataset:
+        n_seq = len(dataset)
+        for k in range(n_seq):
+            sequence = dataset[k]
             if restart is not None and not restarted:
                 if sequence.name != restart:
                     continue
                 restarted = True
             sequence.preload(self.device)
+            # I/O overlap (lib/datasets.py here): JPEG decode + H2D of the next sequence run behind this one's tracking.
+            # Sequences of the reference's own dataset classes have no preload_async and are simply preloaded in turn.
+            if k + 1 < n_seq:
+                nxt = dataset[k + 1]
+                if hasattr(nxt, "preload_async"):
+                    nxt.preload_async(self.device)
             self.clear()
             outputs, seq_fps = self.run_sequence(sequence, speedrun)
             if not np.isnan(seq_fps):
@@ -113,6 +121,8 @@ class Tracker(nn.Module):
             dst.mkdir(exist_ok=True)
             for lb, f in zip(outputs, sequence.frame_names):
                 imwrite_indexed(dst / (f + ".png"), lb)
+            if hasattr(sequence, "release"):
+                sequence.release()
         print("Average frame rate: %.2f fps" % (fps_sum / max(fps_n, 1)))
 
     def run_sequence(self, sequence, speedrun=False):

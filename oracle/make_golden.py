@@ -8,7 +8,8 @@ reference's own classes on the seeded inputs of ``tests/golden_inputs.py`` — a
 problem, two consecutive runs so the persistent CG state is exercised), ``init_step`` (RHS and one J^T J product
 of the joint project/filter problem at a fixed point), ``memory`` (sample-weight / replace-index trace),
 ``pixel_weights``, ``merge``, ``feedforward`` (backbone -> apply -> refinement logits at fixed (P, F)),
-``e2e`` (free-running label maps + target-model state of a short two-object sequence).
+``e2e`` (free-running label maps + target-model state of a short two-object sequence), ``eval`` (J / F measures,
+sequence statistics and report bar graphs of lib/davis.py / lib/utils.py on seeded label maps).
 """
 from __future__ import annotations
 
@@ -241,6 +242,24 @@ def gen_e2e(ref):
     print("e2e: %d frames, restatement bit-identical to the executed reference" % len(out_ref))
 
 
+def gen_eval(ref):
+    """J / F measures, sequence statistics and the bar graph of the executed reference (lib/davis.py, lib/utils.py:9-22) on the
+    seeded maps of ``golden_inputs.eval_mask_pairs`` — the pin for ``frtm_vos_b200/lib/davis.py`` where the reference is absent."""
+    pairs = GI.eval_mask_pairs()
+    with ref.numpy1_aliases():
+        J = np.array([float(ref.davis.davis_jaccard_measure(a.copy(), b.copy())) for a, b in pairs])
+        F = np.array([float(ref.davis.davis_f_measure(a.copy(), b.copy())) for a, b in pairs])
+        vecs = GI.eval_score_vectors()
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            stats = np.array([[float(ref.davis.mean(v)), float(ref.davis.recall(v)), float(ref.davis.decay(v)), float(ref.davis.std(v))]
+                              for v in vecs])
+        bars = np.array([ref.utils.text_bargraph(np.concatenate((v, [-0.1, 1.2]))) for v in vecs])
+    np.savez_compressed(os.path.join(OUT, "eval.npz"), J=J, F=F, stats=stats, bars=bars)
+    print("eval: %d mask pairs (J mean %.3f, F mean %.3f), %d score vectors" % (len(pairs), J.mean(), F.mean(), len(vecs)))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -252,7 +271,14 @@ def main():
     gen_feedforward(ref, "resnet18")
     gen_feedforward(ref, "resnet101")
     gen_e2e(ref)
+    gen_eval(ref)
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1:            # python -m oracle.make_golden eval  -> only the named fixtures
+        os.makedirs(OUT, exist_ok=True)
+        _ref = shims.load_reference()
+        for _name in sys.argv[1:]:
+            globals()["gen_" + _name](_ref)
+    else:
+        main()

@@ -7,7 +7,8 @@ against the executed reference.  The reference files are untouched; the shims be
 importable/runnable offline on torch 2.11 / numpy 2:
 
 1. ``easydict`` stand-in (attribute dict)                        — evaluate.py:4
-2. ``skimage.morphology`` stub                                   — lib/davis.py:5
+2. ``skimage.morphology`` stand-in (``disk`` restated, ``binary_dilation`` = scipy.ndimage's, which is what
+   scikit-image calls) and ``numpy1_aliases`` (``np.bool`` / ``np.int``) — lib/davis.py:5,63,160
 3. ``lib._npp`` stub (the NPP warp extension JIT-builds into ~/tmp on import and is only ever
    *called* for CUDA tensors)                                    — lib/image.py:6, lib/_npp/__init__.py
 4. torchvision ``resnetXX(pretrained=True)`` -> ``weights=None`` — model/feature_extractor.py:12-14
@@ -57,6 +58,38 @@ class _AttrDict(dict):
         return _AttrDict({k: copy.deepcopy(v, memo) for k, v in self.items()})
 
 
+def _disk(radius, dtype="uint8"):
+    """scikit-image's published ``morphology.disk``: all grid points within ``radius`` of the centre."""
+    import numpy as np
+    L = np.arange(-radius, radius + 1)
+    X, Y = np.meshgrid(L, L)
+    return np.array((X ** 2 + Y ** 2) <= radius ** 2, dtype=dtype)
+
+
+def _binary_dilation(image, footprint=None, out=None):
+    """scikit-image's ``morphology.binary_dilation`` is ``scipy.ndimage.binary_dilation`` with the footprint as structure."""
+    import scipy.ndimage as ndi
+    return ndi.binary_dilation(image, structure=footprint, output=out)
+
+
+class numpy1_aliases:
+    """``with numpy1_aliases():`` restores ``np.bool`` / ``np.int`` (removed in numpy 1.24) while reference code that
+    still uses them runs (lib/davis.py:63-64,160, lib/utils.py:16)."""
+
+    def __enter__(self):
+        import numpy as np
+        self._added = [n for n in ("bool", "int") if n not in np.__dict__]
+        for n in self._added:
+            setattr(np, n, {"bool": bool, "int": int}[n])
+        return self
+
+    def __exit__(self, *exc):
+        import numpy as np
+        for n in self._added:
+            delattr(np, n)
+        return False
+
+
 _loaded = None
 
 
@@ -79,7 +112,7 @@ def load_reference():
     except Exception:
         sk = types.ModuleType("skimage")
         mo = types.ModuleType("skimage.morphology")
-        mo.binary_dilation = mo.disk = None
+        mo.binary_dilation, mo.disk = _binary_dilation, _disk
         sk.morphology = mo
         sys.modules["skimage"], sys.modules["skimage.morphology"] = sk, mo
     if REFERENCE_ROOT not in sys.path:
@@ -114,7 +147,14 @@ def load_reference():
     import model.seg_network as seg_network
     import model.augmenter as augmenter
 
-    ns = types.SimpleNamespace(tracker=tracker, discriminator=discriminator, optimizer=optimizer, memory=memory,
+    import lib.datasets as datasets
+    import lib.davis as davis
+    import lib.evaluation as evaluation
+    import lib.utils as utils
+    import lib.image as image
+
+    ns = types.SimpleNamespace(datasets=datasets, davis=davis, evaluation=evaluation, utils=utils, image=image,
+                               numpy1_aliases=numpy1_aliases, tracker=tracker, discriminator=discriminator, optimizer=optimizer, memory=memory,
                                seg_network=seg_network, feature_extractor=fe, tensorlist=tl, augmenter=augmenter,
                                EasyDict=_AttrDict)
     _loaded = ns

@@ -94,3 +94,45 @@ def feedforward_case(arch="resnet18", size=MID, n_obj=2, seed=9):
 
 def strip_prefix(sd, prefix="refiner."):
     return OrderedDict(((k[len(prefix):] if k.startswith(prefix) else k), v) for k, v in sd.items())
+
+
+# ---- evaluation (SURVEY.md §8(f) row f3): seeded label maps for the J / F measures -------------------------------------------
+EVAL_SIZES = [(48, 64), (37, 53), (96, 128), (8, 8)]
+
+
+def eval_mask_pairs(seed=31):
+    """[(annotation, segmentation)] boolean maps: blobs and a shifted / eroded / noisy copy, plus the degenerate cases the
+    measures special-case (both empty, one empty, full frame, single pixel, touching the border)."""
+    import numpy as np
+    rng = np.random.RandomState(seed)
+    pairs = []
+    for (h, w) in EVAL_SIZES:
+        yy, xx = np.mgrid[:h, :w]
+        for _ in range(4):
+            cy, cx = rng.uniform(0.2, 0.8) * h, rng.uniform(0.2, 0.8) * w
+            ry, rx = rng.uniform(0.1, 0.35) * h, rng.uniform(0.1, 0.35) * w
+            gt = ((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 <= 1
+            dy, dx = rng.randint(-3, 4), rng.randint(-3, 4)
+            sg = np.roll(np.roll(gt, dy, 0), dx, 1) ^ (rng.uniform(size=(h, w)) > 0.97)
+            pairs.append((gt, sg))
+        z, o = np.zeros((h, w), bool), np.ones((h, w), bool)
+        one = z.copy(); one[h // 2, w // 2] = True
+        edge = z.copy(); edge[:3, :] = True; edge[:, -2:] = True
+        pairs += [(z, z), (z, pairs[-1][0]), (pairs[-1][0], z), (o, o), (o, one), (one, one), (edge, np.roll(edge, 1, 0))]
+    return pairs
+
+
+def eval_score_vectors(seed=32):
+    """Per-frame score vectors with NaNs (frames before the start / the last frame) for the sequence statistics."""
+    import numpy as np
+    rng = np.random.RandomState(seed)
+    out = []
+    for n in (4, 5, 9, 24, 70, 104):
+        v = rng.uniform(0, 1, size=n)
+        v[0] = np.nan
+        v[-1] = np.nan
+        if n > 8:
+            v[1:rng.randint(1, n // 2)] = np.nan
+        out.append(v)
+    out.append(np.array([np.nan, 0.2, 0.9, 1.0, 0.0, 0.51, 0.5, np.nan]))
+    return out
