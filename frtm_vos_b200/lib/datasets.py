@@ -161,114 +161,99 @@ class FileSequence(torch.utils.data.Dataset):
         return "%s: %s, %d frames" % (self.dset_name, self.name, len(self.images))
 
 
-def _missing_dataset(path):
-    # the reference prints and calls quit(1) (``:78-80``): same message, same exit status
-    print("Dataset directory '%s' not found." % path)
-    raise SystemExit(1)
+class _FileDataset:
+    """What DAVIS and YouTubeVOS share: a root that must exist (the reference prints and calls ``quit(1)`` otherwise,
+    ``:78-80`` — same message, same exit status), a sorted sequence list narrowed by ``sequences`` / ``restart``, a start
+    frame per object and sequence, and ``FileSequence`` objects created on access.  The most recent one is cached so that
+    the prefetch ``Tracker.run_dataset`` starts on sequence k+1 is found again when the loop gets there."""
 
+    merge_objects = False
 
-def _select(all_sequences: List[str], sequences, restart) -> List[str]:
-    out = list(all_sequences)
-    if sequences is not None:
-        assert set(sequences).issubset(out)
-        out = sorted(set(out).intersection(sequences))
-    if restart is not None:
-        assert restart in out
-        out = out[out.index(restart):]
-    return out
+    def __init__(self, path, name: str, year: str, all_annotations: bool):
+        self.dset_path = Path(path).expanduser().resolve()
+        if not self.dset_path.exists():
+            print("Dataset directory '%s' not found." % path)
+            raise SystemExit(1)
+        self.name, self.year, self.all_annotations = name, year, all_annotations
+        self._cache = (None, None)
 
-
-class _SequenceList:
-    """len / index / iteration shared by the two dataset classes; sequences are created on access and cached so that a
-    prefetch started by ``run_dataset`` is found again when the sequence is reached."""
+    def _narrow(self, sequences, restart):
+        if sequences is not None:
+            assert set(sequences).issubset(self.sequences)
+            self.sequences = sorted(set(self.sequences).intersection(sequences))
+        if restart is not None:
+            assert restart in self.sequences
+            self.sequences = self.sequences[self.sequences.index(restart):]
 
     def __len__(self):
         return len(self.sequences)
 
     def __iter__(self):
-        for i in range(len(self)):
-            yield self[i]
+        return (self[i] for i in range(len(self)))
 
-    def _cached(self, item, make):
-        cache = self.__dict__.setdefault("_seq_cache", {})
-        key = (self.sequences[item], self.all_annotations)
-        if key not in cache:
-            cache.clear()                        # keep at most the sequences of one pass alive
-            cache[key] = make()
-        return cache[key]
+    def __getitem__(self, item):
+        seq = self.sequences[item]                   # IndexError ends old-style iteration, as with the reference classes
+        key = (seq, self.all_annotations)
+        if self._cache[0] != key:
+            self._cache = (key, FileSequence(self.name, seq, self.jpeg_path / seq, self.anno_path / seq, self.start_frames[seq],
+                                             merge_objects=self.merge_objects, all_annotations=self.all_annotations))
+        return self._cache[1]
 
 
-class DAVISDataset(_SequenceList):
-    """DAVIS 2016 / 2017 at 480p (``lib/datasets.py:72-112``): every object starts on frame ``00000``; 2016 merges all
-    objects into one."""
+def _read_lines(path) -> List[str]:
+    with open(path) as f:
+        return [line.strip() for line in sorted(f.readlines())]
+
+
+class DAVISDataset(_FileDataset):
+    """DAVIS 2016 / 2017 at 480p (``lib/datasets.py:72-112``): ``ImageSets/<year>/<split>.txt`` lists the sequences, every
+    object starts on frame ``00000`` (its ids are read from that annotation), 2016 merges all objects into one."""
+
+    FIRST_FRAME = "00000"
 
     def __init__(self, path, year: str, split: str, restart: str = None, sequences=None, all_annotations=False):
-        self.dset_path = Path(path).expanduser().resolve()
-        if not self.dset_path.exists():
-            _missing_dataset(path)
+        super().__init__(path, "dv%s%s" % (year, split), year, all_annotations)
         self.jpeg_path = self.dset_path / "JPEGImages" / "480p"
         self.anno_path = self.dset_path / "Annotations" / "480p"
-        imset = self.dset_path / "ImageSets" / year / (split + ".txt")
-        with open(imset) as f:
-            self.sequences = [s.strip() for s in sorted(f.readlines())]
-        self.name = "dv%s%s" % (year, split)
-        self.year = year
-        self.all_annotations = all_annotations
-        self.sequences = _select(self.sequences, sequences, restart)
-        self.start_frames = dict()
-        first = "00000"
+        self.merge_objects = year == "2016"
+        self.sequences = _read_lines(self.dset_path / "ImageSets" / year / (split + ".txt"))
+        self._narrow(sequences, restart)
+        self.start_frames = {}
         for seq in self.sequences:
-            ids = np.unique(imread(self.anno_path / seq / (first + ".png")).numpy()).tolist()
-            self.start_frames[seq] = {int(i): first for i in sorted(ids) if i != 0}
-
-    def __getitem__(self, item):
-        seq = self.sequences[item]
-        return self._cached(item, lambda: FileSequence(self.name, seq, self.jpeg_path / seq, self.anno_path / seq,
-                                                       self.start_frames[seq], merge_objects=self.year == "2016",
-                                                       all_annotations=self.all_annotations))
+            ids = np.unique(imread(self.anno_path / seq / (self.FIRST_FRAME + ".png")).numpy())
+            self.start_frames[seq] = {int(i): self.FIRST_FRAME for i in ids if i != 0}
 
 
-class YouTubeVOSDataset(_SequenceList):
-    """YouTubeVOS 2018 (``lib/datasets.py:115-158``): objects start on the first frame listed for them in ``meta.json``.
+class YouTubeVOSDataset(_FileDataset):
+    """YouTubeVOS 2018 (``lib/datasets.py:115-158``): an object starts on the first frame ``meta.json`` lists for it.
 
-    The ``jjval`` / ``train`` splits read a sequence list (``ytvos_jjvalid.txt`` / ``ytvos_jjtrain.txt``) that ships
-    with the reference next to its ``lib/datasets.py``; pass its location as ``imset`` or place it next to this file."""
+    Splits: ``valid`` / ``test`` (sequences = annotation directories) and ``train`` / ``jjval`` (sequences from a list file:
+    ``ytvos_jjtrain.txt`` / ``ytvos_jjvalid.txt`` ship with the reference next to its ``lib/datasets.py`` — pass the location
+    as ``imset`` or place the file next to this module); the ``*_all_frames`` variants read the densely sampled JPEGs but
+    the same annotations and metadata."""
+
+    #           split  -> (annotation split, sequence list file or None)
+    _SPLITS = {"train": ("train", "ytvos_jjtrain.txt"), "jjval": ("train", "ytvos_jjvalid.txt"),
+               "valid": ("valid", None), "test": ("test", None)}
 
     def __init__(self, path, year: str, split: str, restart: str = None, sequences=None, all_annotations=False, imset=None):
-        self.dset_path = Path(path).expanduser().resolve()
-        if not self.dset_path.exists():
-            _missing_dataset(path)
-        self.name = "ytvos%s%s" % (year, split)
-        self.year = year
-        self.all_annotations = all_annotations
-        if split in ("train", "train_all_frames", "jjval", "jjval_all_frames"):
-            im_split = "train_all_frames" if split.endswith("_all_frames") else "train"
-            self.jpeg_path = self.dset_path / im_split / "JPEGImages"
-            self.anno_path = self.dset_path / "train" / "Annotations"
-            if imset is None:
-                imset = Path(__file__).parent / ("ytvos_jjvalid.txt" if split.startswith("jjval") else "ytvos_jjtrain.txt")
-            if not Path(imset).exists():
-                raise FileNotFoundError("YouTubeVOSDataset(split=%r): sequence list %s not found (pass imset=...)" % (split, imset))
-            with open(imset) as f:
-                self.sequences = [s.strip() for s in sorted(f.readlines())]
-            with open(self.dset_path / "train" / "meta.json") as f:
-                self.meta = json.load(f)["videos"]
-        elif split in ("test", "test_all_frames", "valid", "valid_all_frames"):
-            im_split = split
-            split = split[:-len("_all_frames")] if split.endswith("_all_frames") else split
-            self.jpeg_path = self.dset_path / im_split / "JPEGImages"
-            self.anno_path = self.dset_path / split / "Annotations"
-            self.sequences = [s.name for s in sorted(self.anno_path.glob("*")) if s.is_dir()]
-            with open(self.dset_path / split / "meta.json") as f:
-                self.meta = json.load(f)["videos"]
-        else:
+        super().__init__(path, "ytvos%s%s" % (year, split), year, all_annotations)
+        dense = split.endswith("_all_frames")
+        base = split[:-len("_all_frames")] if dense else split
+        if base not in self._SPLITS:
             raise ValueError("YouTubeVOSDataset: unknown split %r" % (split,))
-        self.sequences = _select(self.sequences, sequences, restart)
-        self.start_frames = dict()
-        for seq in self.sequences:
-            self.start_frames[seq] = {int(obj_id): v["frames"][0] for obj_id, v in self.meta[seq]["objects"].items()}
-
-    def __getitem__(self, item):
-        seq = self.sequences[item]
-        return self._cached(item, lambda: FileSequence(self.name, seq, self.jpeg_path / seq, self.anno_path / seq,
-                                                       self.start_frames[seq], all_annotations=self.all_annotations))
+        anno_split, list_file = self._SPLITS[base]
+        self.jpeg_path = self.dset_path / (anno_split + "_all_frames" if dense else anno_split) / "JPEGImages"
+        self.anno_path = self.dset_path / anno_split / "Annotations"
+        if list_file is not None:
+            imset = Path(imset) if imset is not None else Path(__file__).parent / list_file
+            if not imset.exists():
+                raise FileNotFoundError("YouTubeVOSDataset(split=%r): sequence list %s not found (pass imset=...)" % (split, imset))
+            self.sequences = _read_lines(imset)
+        else:
+            self.sequences = [d.name for d in sorted(self.anno_path.glob("*")) if d.is_dir()]
+        with open(self.dset_path / anno_split / "meta.json") as f:
+            self.meta = json.load(f)["videos"]
+        self._narrow(sequences, restart)
+        self.start_frames = {seq: {int(obj_id): info["frames"][0] for obj_id, info in self.meta[seq]["objects"].items()}
+                             for seq in self.sequences}

@@ -292,6 +292,9 @@ def test_evaluate_dataset_report_matches_reference(davis_tree, tmp_path, year, c
         assert capsys.readouterr().out == report                                     # the reference prints what it writes
         assert (out / ("evaluation-%s.txt" % measure)).read_text() == report        # line for line, digit for digit
         assert report.splitlines()[-1].startswith("%s: " % measure) and "recall" in report
+    # concurrent scoring: same report, same order
+    evaluate_dataset(mine, out, measure="F", workers=3)
+    assert capsys.readouterr().out == report == (out / "evaluation-F.txt").read_text()
     # per-object raw scores: NaN on the start frame and on the last frame, finite in between
     r = evaluate_dataset(mine, out, measure="J", to_file=False)[mine.sequences[0]]
     for scores in r["raw"].values():
