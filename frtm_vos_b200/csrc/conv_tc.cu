@@ -955,10 +955,6 @@ static int launch_tc1(const CUtensorMap &mh, const CUtensorMap &ml, const TcArgs
 
 using namespace frtm;
 
-static bool g_conv_slab_enabled = true;
-/* Tests / A-B measurements: route the 3x3, 64-input-channel convs through the general kernel (0) or the slab kernel (1). */
-extern "C" int frtm_conv_tc_slab_enable(int on) { g_conv_slab_enabled = on != 0; return FRTM_OK; }
-
 extern "C" int frtm_split_f16(const float *x, int64_t npix, int C, int ldx, void *hi, void *lo, int ldh, void *stream) {
   FRTM_REQUIRE(x && hi && lo && C % 4 == 0 && ldx % 4 == 0 && ldh % 8 == 0, "split_f16: bad arguments");
   const int64_t total = npix * (C / 4);
@@ -972,8 +968,10 @@ extern "C" int frtm_conv2d_tc(const void *x_hi, const void *x_lo, int B, int H, 
                               const void *res_hi, const void *res_lo, int ldrh, float *y, int ldy, int y_coff, float *y_nchw,
                               void *y_hi, void *y_lo, int ldyh, int yh_coff, int yh_cout, const float *tapw, float *y_tap,
                               const float *r1_score, const float *r1_w, const float *r1_bias, float *y_extra, int extra_ch,
-                              int Cout, int kh, int kw, int stride, int relu, void *stream) {
+                              int Cout, int kh, int kw, int stride, int relu, int kernel_select, void *stream) {
   FRTM_REQUIRE(x_hi && x_lo && wt && oscale && (y || y_nchw || y_hi || y_tap), "conv2d_tc: null pointer");
+  FRTM_REQUIRE(kernel_select == 0 || kernel_select == 1, "conv2d_tc: kernel_select must be 0 (automatic) or 1 (general tile kernel)");
+  const bool special = kernel_select == 0;
   FRTM_REQUIRE(!r1_score || r1_w, "conv2d_tc: the rank-1 score channel needs its weights");
   FRTM_REQUIRE(!y_extra || (extra_ch >= 0 && extra_ch < Cout), "conv2d_tc: extra_ch out of range");
   FRTM_REQUIRE(!y_tap || (tapw && Cout <= bn_tile && (reinterpret_cast<uintptr_t>(y_tap) & 15) == 0),
@@ -986,10 +984,10 @@ extern "C" int frtm_conv2d_tc(const void *x_hi, const void *x_lo, int B, int H, 
   FRTM_REQUIRE(!y_hi || (y_lo && ldyh % 2 == 0), "conv2d_tc: bad split output");
   // 3x3 / stride 1 / 64 input channels / one N tile of 32 or 64: the slab kernel with resident weights
   const bool slab3 = kh == 3 && stride == 1 && Cin == TC_BK && Cout <= bn_tile && (bn_tile == 64 || bn_tile == 32) &&
-                     !(y_tap && bn_tile != 32) && !(r1_score && bn_tile != 64) && g_conv_slab_enabled;
+                     !(y_tap && bn_tile != 32) && !(r1_score && bn_tile != 64) && special;
   // 1x1 / stride 1 / up to 256 input channels / one N tile of 32 or 64, plain epilogue: the persistent streaming kernel
   const bool stream1 = kh == 1 && stride == 1 && Cin <= 4 * TC_BK && Cout <= bn_tile && (bn_tile == 64 || bn_tile == 32) &&
-                       !y_tap && !r1_score && g_conv_slab_enabled;
+                       !y_tap && !r1_score && special;
   const int box_w = (slab3 || stream1) ? S3_TW : 0, box_h = slab3 ? S3_TH + 2 : (stream1 ? S3_TH : 0);
   CUtensorMap mh, ml;
   int rc = make_act_map(&mh, (const __half *)x_hi, B, H, W, Cin, ldx, stride, box_w, box_h);

@@ -54,15 +54,6 @@ __device__ __forceinline__ uint64_t umma_desc_ls(uint32_t saddr, uint32_t lbo_by
   return d;
 }
 
-// power of two that brings amax into [2^9, 2^10)
-__device__ __forceinline__ float pow2_scale(float amax) {
-  if (!(amax > 0.f) || !isfinite(amax)) return 1.f;
-  int e;
-  frexpf(amax, &e);
-  e = max(min(10 - e, 100), -100);
-  return ldexpf(1.f, e);
-}
-
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -83,11 +74,6 @@ __device__ __forceinline__ void drain_sync() { asm volatile("bar.sync 1, 128;" :
 #else
 #define GC_STAMP(role, k) do { } while (0)
 #endif
-
-struct GcParams {
-  int ntiles, nchunks, tile_bytes, slots;
-  int64_t image_bytes;
-};
 
 // the operator for the sample of this CTA (returns early, after zeroing its partial row, for inactive memory slots)
 __device__ __forceinline__ void gc_sample(const GaArgs &a, const GcParams &P) {
@@ -500,64 +486,9 @@ __device__ __forceinline__ void gc_sample(const GaArgs &a, const GcParams &P) {
   }
 }
 
-// The per-sample partials are reduced and the CG vector step is run by the operator kernel itself, so an operator
-// application is ONE launch instead of two: the CTA that retires last within a group of GC_RGROUP samples sums the
-// group's rows (fixed order), the one that completes the last group of an object sums the group rows (fixed order) and
-// advances the Polak-Ribiere recurrences.  Tickets are global atomics; every sum has a fixed order -> deterministic.
 __global__ void __launch_bounds__(GC_THREADS, 2) gn_apply_tc_kernel(const GaArgs a, const GcParams P, const GcFuse F) {
   gc_sample(a, P);
-  if (!F.enabled) return;
-  __shared__ float red[32];
-  __shared__ int s_last;
-  const int o = a.table ? blockIdx.y : 0;
-  const int n = a.c * 9;
-  const int ngrp = (a.cap + GC_RGROUP - 1) / GC_RGROUP;
-  const int grp = blockIdx.x / GC_RGROUP;
-  const int gsize = min(GC_RGROUP, a.cap - grp * GC_RGROUP);
-  int *cnt = F.counters + (int64_t)o * (1 + ngrp);
-  __threadfence();                                   // this CTA's partial row is visible before its ticket
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const int ticket = atomicAdd(cnt + 1 + grp, 1);
-    s_last = (ticket == gsize - 1) ? 1 : 0;
-    if (s_last) cnt[1 + grp] = 0;                    // every ticket of this group has been drawn: reset for the next launch
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  {   // group sum: rows grp*8 .. +gsize of this object's partials
-    const float *part = a.partial + ((int64_t)o * a.cap + (int64_t)grp * GC_RGROUP) * n;
-    float *dst = F.gsum + ((int64_t)o * ngrp + grp) * n;
-    for (int t = threadIdx.x; t < n; t += GC_THREADS) {
-      float v[GC_RGROUP];
-#pragma unroll
-      for (int u = 0; u < GC_RGROUP; ++u) v[u] = u < gsize ? __ldcg(part + (int64_t)u * n + t) : 0.f;
-      dst[t] = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
-    }
-  }
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const int ticket = atomicAdd(cnt, 1);
-    s_last = (ticket == ngrp - 1) ? 1 : 0;
-    if (s_last) cnt[0] = 0;
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  CgVec cg = F.cg;
-  const int *gate = F.gate;
-  if (a.table) {
-    float *cgst = reinterpret_cast<float *>(a.table[5 * a.n_obj + o]);
-    cg.f = reinterpret_cast<float *>(a.table[4 * a.n_obj + o]);
-    cg.p = cgst; cg.rprev = cgst + cg.n; cg.rho = cgst + 2 * cg.n; cg.hasp = cgst + 2 * cg.n + 1;
-    cg.r += (int64_t)o * 3 * cg.n; cg.x += (int64_t)o * 3 * cg.n; cg.q += (int64_t)o * 3 * cg.n;
-    gate = reinterpret_cast<const int *>(a.table[6 * a.n_obj + o]);
-  }
-  cg.partial = F.gsum + (int64_t)o * ngrp * n;       // the vector step sums the group rows
-  cg.cap = ngrp;
-  if (gate && gate[0] < F.min_px) return;
-  cg_vector_step_cta<GC_THREADS, 6>(cg, F.mode, red);
+  gc_fused_tail<GC_THREADS, 6>(a, F);
 }
 
 // n samples (c, hw) fp32 + their stencils -> operator images

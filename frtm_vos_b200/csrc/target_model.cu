@@ -1078,9 +1078,6 @@ extern "C" int frtm_memory_insert(const float *feat, int feat_elems, const float
 }
 
 // ---- filter-only GN/CG ------------------------------------------------------------------------------------------
-static float *g_gn_debug_dump = nullptr;   // tests only: device buffer receiving the score / v maps of CTA (0,0)
-extern "C" int frtm_gn_debug_dump(float *buf) { g_gn_debug_dump = buf; return FRTM_OK; }
-
 extern "C" int64_t frtm_gn_update_workspace(int cap, int c, int h, int w) {
   const int64_t n = (int64_t)c * 9, hw = (int64_t)h * w;
   // s[cap][hw] | v[cap][hw] | partial[cap][n] | r[n] | x[n] | q[n] | tickets[1 + ngroups] | group sums[ngroups][n]
@@ -1088,10 +1085,14 @@ extern "C" int64_t frtm_gn_update_workspace(int cap, int c, int h, int w) {
   return (2 * cap * hw + cap * n + 3 * n + 64 + (1 + ngrp) + 8 + ngrp * n) * (int64_t)sizeof(float);
 }
 
+extern "C" int64_t frtm_gn_operator_kind(int c, int h, int w) {
+  return gn_apply_mma_supported(c, h, w) ? 3 : (gn_apply_tc_supported(c, h, w) ? 2 : 1);
+}
+
 static int gn_update_impl(const float *samples, const __half *samples_split, const float *stencil, const float *uty,
                           const float *weights, const long long *table, bool table_has_split, int n_obj, int cap, int c, int h, int w, float *filt, float *cg_state,
                           const int *cg_iters, int n_gn, float reg, float precond, float forget, const int *gate_count,
-                          int min_px, float *workspace, int64_t workspace_bytes, cudaStream_t st) {
+                          int min_px, int operator_select, float *workspace, int64_t workspace_bytes, cudaStream_t st) {
   FRTM_REQUIRE(cg_iters && workspace && n_obj >= 1, "gn_update: null pointer");
   FRTM_REQUIRE(c * 9 <= 1024, "gn_update: filter too large for the single-block CG kernel (c*9 <= 1024)");
   FRTM_REQUIRE(workspace_bytes >= n_obj * frtm_gn_update_workspace(cap, c, h, w), "gn_update: workspace too small");
@@ -1113,9 +1114,17 @@ static int gn_update_impl(const float *samples, const __half *samples_split, con
   float *vecs = partial + (int64_t)n_obj * cap * n;
   GaArgs ga;
   ga.X = samples; ga.S = stencil; ga.T = uty; ga.sw = weights; ga.pvec = filt; ga.table = table; ga.partial = partial;
-  ga.XS = samples_split; ga.dbg = g_gn_debug_dump;
+  ga.XS = samples_split; ga.dbg = nullptr;
   // tensor-core operator kernel: needs the split tile image of the samples (written at insert time)
-  const bool use_tc = (table ? table_has_split : samples_split != nullptr) && gn_apply_tc_supported(c, h, w);
+  // Operator kernels over the operator images (written at insert time): the single-pass mma.sync kernel where the shape
+  // allows it, else the two-pass tcgen05 kernel, else CUDA cores.  operator_select forces one (tests, A-B measurements).
+  const bool have_image = table ? table_has_split : samples_split != nullptr;
+  FRTM_REQUIRE(operator_select >= 0 && operator_select <= 3, "gn_update: operator_select must be 0..3");
+  FRTM_REQUIRE(operator_select < 2 || have_image, "gn_update: the tensor-core operators need the operator images");
+  FRTM_REQUIRE(operator_select != 2 || gn_apply_tc_supported(c, h, w), "gn_update: shape not supported by the two-pass operator");
+  FRTM_REQUIRE(operator_select != 3 || gn_apply_mma_supported(c, h, w), "gn_update: shape not supported by the single-pass operator");
+  const bool use_mma = operator_select == 3 || (operator_select == 0 && have_image && gn_apply_mma_supported(c, h, w));
+  const bool use_tc = use_mma || operator_select == 2 || (operator_select == 0 && have_image && gn_apply_tc_supported(c, h, w));
   ga.n_obj = n_obj; ga.cap = cap; ga.c = c; ga.h = h; ga.w = w; ga.use_y = 1;
   CgVec cg;
   cg.f = filt; cg.p = cg_state; cg.rprev = cg_state ? cg_state + n : nullptr; cg.rho = cg_state ? cg_state + 2 * n : nullptr;
@@ -1159,7 +1168,7 @@ static int gn_update_impl(const float *samples, const __half *samples_split, con
   }
   auto launch_apply = [&]() -> int {
     if (use_tc) {
-      const int rc = gn_apply_tc_launch(ga, fuse, st);
+      const int rc = use_mma ? gn_apply_mma_launch(ga, fuse, st) : gn_apply_tc_launch(ga, fuse, st);
       if (rc == FRTM_OK) count_launch(-1);                  // counted again by FRTM_CHECK_LAUNCH at the call site
       return rc;
     }
@@ -1200,18 +1209,18 @@ static int gn_update_impl(const float *samples, const __half *samples_split, con
 extern "C" int frtm_gn_update(const float *samples, const void *samples_split, const float *stencil, const float *uty,
                               const float *weights, int cap, int c, int h, int w, float *filt, float *cg_state,
                               const int *cg_iters, int n_gn, float reg, float precond, float forget, const int *gate_count,
-                              int min_px, float *workspace, int64_t workspace_bytes, void *stream) {
+                              int min_px, int operator_select, float *workspace, int64_t workspace_bytes, void *stream) {
   FRTM_REQUIRE(samples && stencil && uty && weights && filt && cg_state, "gn_update: null pointer");
   return gn_update_impl(samples, (const __half *)samples_split, stencil, uty, weights, nullptr, false, 1, cap, c, h, w, filt, cg_state, cg_iters, n_gn, reg, precond,
-                        forget, gate_count, min_px, workspace, workspace_bytes, (cudaStream_t)stream);
+                        forget, gate_count, min_px, operator_select, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int frtm_gn_update_batched(const void *table, int n_obj, int has_split, int cap, int c, int h, int w,
                                       const int *cg_iters, int n_gn, float reg, float precond, float forget, int min_px,
-                                      float *workspace, int64_t workspace_bytes, void *stream) {
+                                      int operator_select, float *workspace, int64_t workspace_bytes, void *stream) {
   FRTM_REQUIRE(table && n_obj >= 1, "gn_update_batched: null table");
   return gn_update_impl(nullptr, nullptr, nullptr, nullptr, nullptr, reinterpret_cast<const long long *>(table), has_split != 0, n_obj, cap, c, h, w,
-                        nullptr, nullptr, cg_iters, n_gn, reg, precond, forget, nullptr, min_px, workspace, workspace_bytes,
+                        nullptr, nullptr, cg_iters, n_gn, reg, precond, forget, nullptr, min_px, operator_select, workspace, workspace_bytes,
                         (cudaStream_t)stream);
 }
 

@@ -35,11 +35,29 @@ __host__ __device__ inline int64_t gc_sample_items(int c, int hw) {
   return (int64_t)gc_ntiles(hw) * c * 8 + (int64_t)gc_nchunks(hw) * 10 * (GC_CHUNK_PX / 4);
 }
 
-// true if the tensor-core operator kernel supports this problem shape
+struct GcParams {
+  int ntiles, nchunks, tile_bytes, slots;
+  int64_t image_bytes;
+};
+
+// power of two that brings amax into [2^9, 2^10)
+__device__ __forceinline__ float pow2_scale(float amax) {
+  if (!(amax > 0.f) || !isfinite(amax)) return 1.f;
+  int e;
+  frexpf(amax, &e);
+  e = max(min(10 - e, 100), -100);
+  return ldexpf(1.f, e);
+}
+
+// Operator kernels over the operator images.  Both take one CTA per (memory slot, object), write the sample's gradient
+// partial and run the reduction + CG vector step in the tail of the launch (gc_fused_tail below):
+//   gn_apply_mma_*  single pass over the image (sliding window, warp-level mma.sync tiles) — the default
+//   gn_apply_tc_*   two passes (tcgen05 / TMEM, producer / issuer / drain roles) — kept for shapes the first does not take
 bool gn_apply_tc_supported(int c, int h, int w);
-// launches the tensor-core operator kernel over all (object, sample) pairs
+bool gn_apply_mma_supported(int c, int h, int w);
 struct GcFuse;
 int gn_apply_tc_launch(const GaArgs &a, const GcFuse &fuse, cudaStream_t st);
+int gn_apply_mma_launch(const GaArgs &a, const GcFuse &fuse, cudaStream_t st);
 
 // One work item of the image build.  Items [0, ntiles*c*8): 8 consecutive pixels of channel row r in tile j -> one
 // 16-byte chunk in each plane.  Remaining items: 4 consecutive pixels of one stencil / uty row of one chunk.
@@ -215,6 +233,67 @@ __device__ __forceinline__ void cg_vector_step_cta(const CgVec &s, int mode, flo
     *s.rho = rho_new;
     *s.hasp = 1.f;
   }
+}
+
+// The per-sample partials are reduced and the CG vector step is run by the operator kernel itself, so an operator
+// application is ONE launch instead of two: the CTA that retires last within a group of GC_RGROUP samples sums the
+// group's rows (fixed order), the one that completes the last group of an object sums the group rows (fixed order) and
+// advances the Polak-Ribiere recurrences.  Tickets are global atomics; every sum has a fixed order -> deterministic.
+// Called by every thread of every CTA of an operator launch after its partial row is written.
+template <int NT, int EPT>
+__device__ __forceinline__ void gc_fused_tail(const GaArgs &a, const GcFuse &F) {
+  if (!F.enabled) return;
+  __shared__ float red[32];
+  __shared__ int s_last;
+  const int o = a.table ? blockIdx.y : 0;
+  const int n = a.c * 9;
+  const int ngrp = (a.cap + GC_RGROUP - 1) / GC_RGROUP;
+  const int grp = blockIdx.x / GC_RGROUP;
+  const int gsize = min(GC_RGROUP, a.cap - grp * GC_RGROUP);
+  int *cnt = F.counters + (int64_t)o * (1 + ngrp);
+  __threadfence();                                   // this CTA's partial row is visible before its ticket
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int ticket = atomicAdd(cnt + 1 + grp, 1);
+    s_last = (ticket == gsize - 1) ? 1 : 0;
+    if (s_last) cnt[1 + grp] = 0;                    // every ticket of this group has been drawn: reset for the next launch
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  {   // group sum: rows grp*8 .. +gsize of this object's partials
+    const float *part = a.partial + ((int64_t)o * a.cap + (int64_t)grp * GC_RGROUP) * n;
+    float *dst = F.gsum + ((int64_t)o * ngrp + grp) * n;
+    for (int t = threadIdx.x; t < n; t += NT) {
+      float v[GC_RGROUP];
+#pragma unroll
+      for (int u = 0; u < GC_RGROUP; ++u) v[u] = u < gsize ? __ldcg(part + (int64_t)u * n + t) : 0.f;
+      dst[t] = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int ticket = atomicAdd(cnt, 1);
+    s_last = (ticket == ngrp - 1) ? 1 : 0;
+    if (s_last) cnt[0] = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  CgVec cg = F.cg;
+  const int *gate = F.gate;
+  if (a.table) {
+    float *cgst = reinterpret_cast<float *>(a.table[5 * a.n_obj + o]);
+    cg.f = reinterpret_cast<float *>(a.table[4 * a.n_obj + o]);
+    cg.p = cgst; cg.rprev = cgst + cg.n; cg.rho = cgst + 2 * cg.n; cg.hasp = cgst + 2 * cg.n + 1;
+    cg.r += (int64_t)o * 3 * cg.n; cg.x += (int64_t)o * 3 * cg.n; cg.q += (int64_t)o * 3 * cg.n;
+    gate = reinterpret_cast<const int *>(a.table[6 * a.n_obj + o]);
+  }
+  cg.partial = F.gsum + (int64_t)o * ngrp * n;       // the vector step sums the group rows
+  cg.cap = ngrp;
+  if (gate && gate[0] < F.min_px) return;
+  cg_vector_step_cta<NT, EPT>(cg, F.mode, red);
 }
 
 }  // namespace frtm

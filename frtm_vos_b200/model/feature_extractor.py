@@ -24,7 +24,8 @@ _ARCH = {"resnet18": ("basic", (2, 2, 2, 2), (64, 64, 128, 256, 512)),
 
 class FeatureMaps(dict):
     """``dict`` of NCHW feature maps (reference contract) + the working tensors the other kernels consume directly:
-    ``.split`` — fp16 hi/lo NHWC planes (operands of the tensor-core convs), ``.nhwc`` — fp32 NHWC where produced."""
+    ``.split`` — fp16 hi/lo NHWC planes (operands of the tensor-core convs), ``.nhwc`` — fp32 NHWC tensors of the layers a
+    caller of ``forward_split`` asked for through ``f32_layers`` (empty for ``__call__``)."""
 
     def __init__(self, nchw: Dict[str, torch.Tensor], nhwc: Dict[str, torch.Tensor], split=None):
         super().__init__(nchw)

@@ -76,6 +76,7 @@ class GaussNewtonCG:
         self.cg_state = torch.zeros(2 * n + 4, device=dev, dtype=torch.float32)
         self._n = n
         self._ws = None
+        self.operator_select = 0    # 0 = the library picks the operator kernel by shape (include/frtm_b200.h: frtm_gn_update)
 
     # -- persistent CG state, exposed like the reference's attributes ---------------------------------------------
     @property
@@ -136,5 +137,6 @@ class GaussNewtonCG:
             mem.refresh_split()
             L.gn_update(ptr(mem.samples), ptr(mem.split), ptr(mem.stencil), ptr(mem.uty), ptr(mem.weights), cap, c, h, w, ptr(self.x[0]),
                         ptr(self.cg_state), iters, len(num_cg_iter), pr.filter_regs[-1], pr.diag_M[-1],
-                        self.direction_forget_factor, ptr(gate_count), int(min_px), ptr(self._ws), nbytes, stream())
+                        self.direction_forget_factor, ptr(gate_count), int(min_px), int(self.operator_select), ptr(self._ws), nbytes,
+                        stream())
         return [], [], None

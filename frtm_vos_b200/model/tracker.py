@@ -43,7 +43,10 @@ class TargetObject:
             setattr(self, key, val)
 
     def initialize(self, ft, mask):
-        x_nhwc = ft.nhwc[self.disc_layer] if hasattr(ft, "nhwc") else None
+        # reference path (``model/tracker.py:30-31``): ``ft`` is the dict of NCHW maps; the fp32 NHWC working tensor is used
+        # when the extractor happened to produce it, else the NCHW map is converted by ``Discriminator.init``
+        nhwc = getattr(ft, "nhwc", None)
+        x_nhwc = nhwc.get(self.disc_layer) if isinstance(nhwc, dict) else None
         self.discriminator.init(ft[self.disc_layer] if x_nhwc is None else None, mask, x_nhwc=x_nhwc)
 
     def classify(self, ft):
@@ -414,9 +417,24 @@ class Tracker(nn.Module):
         else:
             batch = torch.stack([im if im.dim() == 3 else im[0] for im in images]) if nF > 1 else \
                 (images[0] if images[0].dim() == 4 else images[0].unsqueeze(0))
-        feats, _, _ = self.feature_extractor.forward_split(batch)
         live = self._live()
         n = len(live)
+        if n == 0:
+            # Nothing is being tracked yet (``track`` called on the frame the objects were initialised on, as the speedrun
+            # warm-up of ``run_sequence`` does, ``model/tracker.py:120-124``): the reference skips its per-object loops
+            # and only merges the start masks (``:208-221``).  The backbone pass feeds nothing, so it is skipped.
+            fresh = [t for t in self.targets.values() if t.start_frame == self.current_frame]
+            assert nF == 1, "a block without live objects is a single frame"
+            if not fresh:
+                self.current_masks = torch.zeros((1, *im_size), device=batch.device)
+                self._last_labels = torch.zeros(im_size, dtype=torch.uint8, device=batch.device)
+                return [self._last_labels]
+            src = torch.stack([t.start_mask.reshape(*im_size).float() for t in fresh])
+            masks, labels, _ = ops.merge_masks(src, 0, None, self._lut, len(self.object_ids) == 1)
+            self.current_masks = masks
+            self._last_labels = labels
+            return [labels]
+        feats, _, _ = self.feature_extractor.forward_split(batch)
         layer = live[0].disc_layer
         c = live[0].discriminator.filter.weight.shape[1]
         fmap = feats[layer]
@@ -506,7 +524,7 @@ class Tracker(nn.Module):
         iters = [int(v) for v in d0.update_iters]
         arr = (ctypes.c_int * len(iters))(*iters)
         lib().gn_update_batched(ptr(table), len(due), 1, cap, c, h, w, arr, len(iters), float(d0.filter_reg[-1]),
-                                float(d0.precond[-1]), float(d0.direction_forget_factor), int(d0.min_px), ptr(ws), nbytes, stream())
+                                float(d0.precond[-1]), float(d0.direction_forget_factor), int(d0.min_px), 0, ptr(ws), nbytes, stream())
 
     def _ensure_gn_table(self, live, due):
         """(Re)build the device pointer table and the workspace of the batched filter update when the object set changes."""

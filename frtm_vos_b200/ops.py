@@ -381,7 +381,7 @@ def split_f16(x: torch.Tensor, channels: Optional[int] = None, ld: Optional[int]
 
 def conv2d_tc(x: Split, pc: PackedConvTC, res=None, relu: bool = False, out_f32: bool = True, out_split: bool = False,
               nchw: bool = False, out: Optional[torch.Tensor] = None, coff: int = 0, split_ld: Optional[int] = None,
-              tapw: Optional[torch.Tensor] = None, r1=None, split_cout: int = 0, extra_ch: int = -1):
+              tapw: Optional[torch.Tensor] = None, r1=None, split_cout: int = 0, extra_ch: int = -1, kernel_select: int = 0):
     """Tensor-core conv.  Returns a dict with the requested outputs: 'y' (fp32 NHWC), 'split' (Split), 'nchw', and with
     ``tapw`` ((9, cout) weights of a following 3x3 -> 1 conv) 'tap': the (B,H,W,12) tap maps contracted in the epilogue."""
     B, Hi, Wi, ldx = x.hi.shape
@@ -414,7 +414,7 @@ def conv2d_tc(x: Split, pc: PackedConvTC, res=None, relu: bool = False, out_f32:
                     ptr(y), 0 if y is None else y.shape[3], coff, ptr(y_nchw),
                     None if sp is None else ptr(sp.hi), None if sp is None else ptr(sp.lo), 0 if sp is None else sp.hi.shape[3], 0,
                     int(split_cout), ptr(tapw), ptr(tap), ptr(r1_score), ptr(r1_w), ptr(r1_bias), ptr(extra), int(extra_ch),
-                    pc.cout, pc.k, pc.k, pc.stride, 1 if relu else 0, stream())
+                    pc.cout, pc.k, pc.k, pc.stride, 1 if relu else 0, int(kernel_select), stream())
     return dict(y=y, split=sp, nchw=y_nchw, tap=tap, extra=extra)
 
 

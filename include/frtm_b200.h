@@ -82,20 +82,20 @@ int frtm_conv2d_nhwc(const float *x, int B, int H, int W, int Cin, int ldx, cons
  *              r1_w [9][Cout] and bias r1_bias (TSE.transform on cat(h, score), seg_network.py:15,19-20; see frtm_rank1_finish)
  *   res / res_hi,res_lo   optional residual (fp32 NHWC or split planes) added before the ReLU
  * Same reference call sites as frtm_conv2d_nhwc; the products hi*hi + hi*lo + lo*hi (issued as A_hi x [B_hi | B_lo] and
- * A_lo x B_hi) keep the result within ~1e-6 relative of an fp32 convolution. */
+ * A_lo x B_hi) keep the result within ~1e-6 relative of an fp32 convolution.
+ *   kernel_select  0 = the library picks the kernel for the shape (slab kernel with resident weights for 3x3 / 64 input
+ *              channels, persistent streaming kernel for narrow 1x1, general tile kernel otherwise); 1 = general tile kernel
+ *              (A-B measurements and tests; a per-call argument, the library keeps no mode) */
 int frtm_conv2d_tc(const void *x_hi, const void *x_lo, int B, int H, int W, int Cin, int ldx, const void *wt,
                    const float *oscale, int bn_tile, const float *bias, const float *res, int ldr, const void *res_hi,
                    const void *res_lo, int ldrh, float *y, int ldy, int y_coff, float *y_nchw, void *y_hi, void *y_lo,
                    int ldyh, int yh_coff, int yh_cout, const float *tapw, float *y_tap, const float *r1_score,
                    const float *r1_w, const float *r1_bias, float *y_extra, int extra_ch, int Cout, int kh, int kw,
-                   int stride, int relu, void *stream);
+                   int stride, int relu, int kernel_select, void *stream);
 /* Device-side weight packer for 1x1 convs whose weights change at run time (project.weight, model/discriminator.py:81):
  * W (Cout,Cin) fp32 -> wt / oscale in the layout frtm_conv2d_tc expects (wt: cout_pad*Cin*2 halves, oscale: cout_pad). */
 int frtm_pack_tc_1x1(const float *W, int Cout, int Cin, int bn_tile, void *wt, float *oscale, void *stream);
 /* fp32 NHWC (npix, ldx)[0,C) -> fp16 planes hi, lo with hi + lo = 16 * x  (channel stride ldh, ldh % 8 == 0). */
-/* Tests / A-B measurements: route 3x3, stride-1, 64-input-channel convs through the slab kernel with resident weights
- * (1, default) or through the general kernel (0). */
-int frtm_conv_tc_slab_enable(int on);
 int frtm_split_f16(const float *x, int64_t npix, int C, int ldx, void *hi, void *lo, int ldh, void *stream);
 
 /* Completes a 3x3 conv over cat(64 channels, score) (TSE.transform, seg_network.py:15,19-20) after frtm_conv2d_tc has
@@ -224,9 +224,12 @@ int64_t frtm_split_sample_bytes(int c, int hw);
  * GaussNewtonCG.run on the update problem (optimizer.py:55-157, discriminator.py:38-64,221-227):
  *   residual  r = W (U (X * f) - y),  A p = X^T (U^T W^2 U) X p + reg^2 p,  b = -(X^T U^T W^2 (U X f - y) + reg^2 f)
  * samples (cap,c,h,w), stencil (cap,9,h,w), uty (cap,h,w), weights (cap) [inactive = 0];
- * samples_split (optional, NULL = absent): the operator images of the samples (frtm_split_samples); when given (and
- * c % 16 == 0, 48 <= c <= 128) the operator streams only the images and both contractions run on the tensor cores,
- * otherwise on CUDA cores;
+ * samples_split (optional, NULL = absent): the operator images of the samples (frtm_split_samples); when given the
+ * operator streams only the images and both contractions run on the tensor cores: in ONE pass over every image
+ * (sliding window, c == 96, 8 <= w <= 84 — gn_apply_mma.cu) or in two (tcgen05, c % 16 == 0, 48 <= c <= 128 —
+ * gn_apply_tc.cu); otherwise on CUDA cores.  operator_select: 0 = the library picks by shape, 1 = CUDA cores,
+ * 2 = two-pass tcgen05, 3 = single-pass (EINVAL if the shape is not supported) — a per-call argument for tests and
+ * A-B measurements, the library keeps no mode;
  * filt (c*9) updated in place;  cg_state = float[2*c*9 + 4]: p | r_prev | rho | has_p — persists across calls
  * (zero-initialised by the caller);  cg_iters_host[n_gn] CG iterations per GN iteration (host array);
  * the update is applied only if gate_count == NULL or gate_count[0] >= min_px (device-side predicate, replaces the
@@ -234,18 +237,18 @@ int64_t frtm_split_sample_bytes(int c, int hw);
 int frtm_gn_update(const float *samples, const void *samples_split, const float *stencil, const float *uty,
                    const float *weights, int cap, int c, int h, int w, float *filt, float *cg_state,
                    const int *cg_iters_host, int n_gn, float reg, float precond, float forget, const int *gate_count,
-                   int min_px, float *workspace, int64_t workspace_bytes, void *stream);
+                   int min_px, int operator_select, float *workspace, int64_t workspace_bytes, void *stream);
 int64_t frtm_gn_update_workspace(int cap, int c, int h, int w);
+/* Which operator kernel operator_select = 0 resolves to for this shape when the operator images are given:
+ * 3 = single-pass, 2 = two-pass tcgen05, 1 = CUDA cores. */
+int64_t frtm_gn_operator_kind(int c, int h, int w);
 /* The same update for n_obj objects in ONE set of launches (grid.y = object; the objects of a sequence update on the
  * same frames).  table: device int64[8][n_obj] of device pointers, rows = {samples, stencil, uty, weights, filt,
  * cg_state, gate_count (0 = ungated), samples_split (read only if has_split != 0)}; all objects share cap, c, h, w and
  * the schedule.  workspace >= n_obj times frtm_gn_update_workspace. */
 int frtm_gn_update_batched(const void *table, int n_obj, int has_split, int cap, int c, int h, int w,
                            const int *cg_iters_host, int n_gn, float reg, float precond, float forget, int min_px,
-                           float *workspace, int64_t workspace_bytes, void *stream);
-/* Tests only: when buf != NULL the right-hand-side launches of the tensor-core operator dump the padded score and v
- * maps of the first sample of the first object, 2*(h+2)*(w+2) floats, into buf. */
-int frtm_gn_debug_dump(float *buf);
+                           int operator_select, float *workspace, int64_t workspace_bytes, void *stream);
 
 /* Joint (project, filter) Gauss-Newton / CG of Discriminator.init (discriminator.py:154-175; optimizer.py:55-157):
  *   s = F * (P x),  J[dP,dF] = F * (dP x) + dF * (P x)  on the low-resolution grid, normal equations through the

@@ -176,13 +176,9 @@ def test_slab_kernel_matches_general_kernel(cout, hw, B):
     rs = _nhwc(res).to(DEV)
     out = {}
     for on in (1, 0):
-        lib().conv_tc_slab_enable(on)
-        try:
-            o = ops.conv2d_tc(xs, pc, res=rs, relu=True, out_split=True, nchw=(B <= 3))
-            torch.cuda.synchronize()
-        finally:
-            lib().conv_tc_slab_enable(1)
-        out[on] = o
+        # kernel_select is a per-call argument of frtm_conv2d_tc: 0 = library's choice (the specialised kernel), 1 = general
+        out[on] = ops.conv2d_tc(xs, pc, res=rs, relu=True, out_split=True, nchw=(B <= 3), kernel_select=1 - on)
+        torch.cuda.synchronize()
     if B <= 3:
         ref = F.relu(F.conv2d(x, w, b, 1, 1) + res)
         scale = max(1.0, ref.abs().max().item())
@@ -210,13 +206,9 @@ def test_streaming_1x1_kernel_matches_general_kernel(cin, cout, hw, B):
     rs = _nhwc(res).to(DEV)
     out = {}
     for on in (1, 0):
-        lib().conv_tc_slab_enable(on)
-        try:
-            o = ops.conv2d_tc(xs, pc, res=rs, relu=True, out_split=True, nchw=(B <= 3))
-            torch.cuda.synchronize()
-        finally:
-            lib().conv_tc_slab_enable(1)
-        out[on] = o
+        # kernel_select is a per-call argument of frtm_conv2d_tc: 0 = library's choice (the specialised kernel), 1 = general
+        out[on] = ops.conv2d_tc(xs, pc, res=rs, relu=True, out_split=True, nchw=(B <= 3), kernel_select=1 - on)
+        torch.cuda.synchronize()
     if B <= 3:
         ref = F.relu(F.conv2d(x, w, b) + res)
         scale = max(1.0, ref.abs().max().item())

@@ -1,0 +1,158 @@
+"""-m gpu: the sequence / dataset drivers on the device — ``run_sequence(speedrun=True)`` (the DAVIS-2016 path of
+``evaluate.py:157``), the reference-API target construction (``TargetObject.initialize``), ``track`` before any object is
+live, and row f2 of SURVEY.md §8: file-backed sequences whose JPEG decode + pinned-slab upload run behind the tracking
+of the previous sequence (``lib/datasets.py``, ``Tracker.run_dataset``)."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+from PIL import Image
+
+import golden_inputs as GI
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+SIZE = GI.MID
+
+
+def _tracker(n_frames=10, n_obj=2, seq_id=3):
+    from frtm_vos_b200 import synth
+    from test_gpu_model import _build
+    bb = synth.backbone_state_dict("resnet18", size=SIZE)
+    seg = synth.segnet_state_dict("resnet18")
+    trk, fe = _build("resnet18", bb, seg, GI.disc_params(256))
+    seq = synth.SyntheticSequence(num_objects=n_obj, num_frames=n_frames, size=SIZE, seq_id=seq_id)
+    return trk, fe, seq
+
+
+def test_speedrun_warmup_matches_plain_run():
+    """``speedrun=True`` initialises on frame 0, calls ``track`` while no object is live yet (the reference skips its
+    per-object loops there, ``model/tracker.py:120-124,193-227``), drops the targets and runs the sequence: same labels."""
+    trk, fe, seq = _tracker(n_frames=10, n_obj=1)          # DAVIS 2016: one object
+    torch.manual_seed(11)
+    plain, _ = trk.run_sequence(seq)
+    torch.manual_seed(11)
+    fast, fps = trk.run_sequence(seq, speedrun=True)
+    assert len(fast) == len(plain) == len(seq) and fps > 0
+    for a, b in zip(fast, plain):
+        assert torch.equal(a.cpu(), b.cpu())
+    trk2, _, seq2 = _tracker(n_frames=9, n_obj=2)
+    out, _ = trk2.run_sequence(seq2, speedrun=True)        # multi-object warm-up takes the merge of the start masks
+    assert len(out) == 9
+
+
+def test_track_with_only_fresh_targets_merges_start_masks():
+    from oracle import frtm_ref as R
+    trk, fe, seq = _tracker(n_frames=3, n_obj=2)
+    image, labels, ids = seq[0]
+    trk.object_ids = seq.obj_ids
+    trk.targets = dict()
+    trk.current_frame = 0
+    trk._lut = torch.tensor([0] + list(seq.obj_ids), dtype=torch.uint8, device=DEV)
+    trk.initialize(image.to(DEV), labels.to(DEV), ids)
+    masks = trk.track(image.to(DEV))
+    cm = torch.zeros(3, *SIZE)
+    for k, oid in enumerate(ids):
+        cm[k + 1] = (labels[0] == oid).float()
+    ref = R.merge_masks(cm)
+    assert torch.allclose(masks.cpu(), ref, atol=1e-6)
+    assert torch.equal(trk._last_labels.cpu(), labels[0])
+
+
+def test_target_object_initialize_reference_api():
+    """``TargetObject.initialize(ft, mask)`` with the dict the public ``ResnetFeatureExtractor.__call__`` returns."""
+    from frtm_vos_b200.model.tracker import TargetObject
+    trk, fe, seq = _tracker(n_frames=2, n_obj=1)
+    image, labels, ids = seq[0]
+    mask = (labels == 1).byte().to(DEV)
+    im5, m5 = trk.augment(image.to(DEV), mask)
+    ft = fe(im5.to(DEV), ["layer4"])
+    assert set(ft.keys()) == {"layer4"} and ft.nhwc == {}
+    torch.manual_seed(0)
+    t = TargetObject(obj_id=1, index=1, disc_params=trk.disc_params, start_frame=0, start_mask=mask)
+    t.initialize(ft, m5.to(DEV))
+    d = t.discriminator
+    assert d.memory.current_size == 5 and torch.isfinite(d.filter.weight).all()
+    s = d(ft["layer4"][:1])
+    up = torch.nn.functional.interpolate(s, SIZE, mode="bilinear", align_corners=False)[0, 0]
+    inter = ((up > 0.5) & (mask[0] > 0)).sum().item()
+    union = ((up > 0.5) | (mask[0] > 0)).sum().item()
+    assert inter / max(union, 1) > 0.6                       # the fitted target model segments its own first frame
+
+
+# ---- row f2: file-backed dataset on the device ---------------------------------------------------------------------------
+def _write_davis(root: Path, seqs):
+    from frtm_vos_b200.lib.image import imwrite_indexed
+    for name, seq in seqs.items():
+        jd, ad = root / "JPEGImages" / "480p" / name, root / "Annotations" / "480p" / name
+        jd.mkdir(parents=True); ad.mkdir(parents=True)
+        for t in range(len(seq)):
+            im, lb, ids = seq[t]
+            Image.fromarray(im.permute(1, 2, 0).numpy()).save(jd / ("%05d.jpg" % t), quality=95)
+            if t == 0:
+                imwrite_indexed(ad / "00000.png", lb[0])
+    (root / "ImageSets" / "2017").mkdir(parents=True)
+    (root / "ImageSets" / "2017" / "val.txt").write_text("\n".join(seqs) + "\n")
+
+
+class _Preloaded:
+    """Plain in-memory sequence over the same decoded frames (what the reference's synchronous preload produces)."""
+
+    def __init__(self, fs):
+        self.name, self.obj_ids, self.frame_names = fs.name, fs.obj_ids, fs.frame_names
+        self.items = [fs[i] for i in range(len(fs))]
+
+    def __len__(self):
+        return len(self.items)
+
+    def __getitem__(self, i):
+        im, lb, ids = self.items[i]
+        return im.to(DEV), (lb.to(DEV) if torch.is_tensor(lb) else lb), ids
+
+
+def test_run_dataset_async_preload_equals_preloaded_path(tmp_path):
+    from frtm_vos_b200 import synth
+    from frtm_vos_b200.lib import datasets as DS
+    from frtm_vos_b200.lib.image import imread
+    seqs = {"s%d" % k: synth.SyntheticSequence(num_objects=2, num_frames=9 + k, size=SIZE, seq_id=20 + k) for k in range(3)}
+    root = tmp_path / "DAVIS"
+    _write_davis(root, seqs)
+    ds = DS.DAVISDataset(root, "2017", "val")
+    assert len(ds) == 3
+    trk, fe, _ = _tracker(n_frames=2)
+    # reference path: frames decoded on the host and handed over as tensors, one sequence at a time
+    want = {}
+    for k in range(len(ds)):
+        plain = _Preloaded(DS.DAVISDataset(root, "2017", "val")[k])
+        torch.manual_seed(11)
+        out, _ = trk.run_sequence(plain)
+        want[plain.name] = torch.stack([o.reshape(SIZE).cpu() for o in out])
+    # driver path: threaded decode into a pinned slab, asynchronous H2D on a copy stream, next sequence prefetched
+    started = []
+    orig = DS.FileSequence.preload_async
+
+    def spy(self, device):
+        started.append((self.name, torch.device(device).type))
+        return orig(self, device)
+
+    DS.FileSequence.preload_async = spy
+    seeds = iter([11, 11, 11])
+    orig_run = trk.run_sequence
+
+    def seeded(sequence, speedrun=False):
+        torch.manual_seed(next(seeds))
+        assert sequence.preloaded_images is not None and all(t.is_cuda for t in sequence.preloaded_images)
+        return orig_run(sequence, speedrun)
+
+    trk.run_sequence = seeded
+    try:
+        trk.run_dataset(ds, tmp_path / "out")
+    finally:
+        DS.FileSequence.preload_async = orig
+    assert [n for n, _ in started].count("s1") >= 1 and all(t == "cuda" for _, t in started)
+    for name, ref in want.items():
+        files = sorted((tmp_path / "out" / name).glob("*.png"))
+        assert len(files) == ref.shape[0]
+        got = torch.stack([imread(f)[0] for f in files])
+        assert torch.equal(got, ref), name

@@ -30,24 +30,31 @@ def _build(arch, bb, seg, dp):
     return trk, fe
 
 
-@pytest.mark.parametrize("arch", ["resnet18", "resnet101"])
-def test_P1_feedforward_fixed_state(arch, golden):
+FULL = (480, 854)      # BASELINE.json configs 2-4
+
+
+@pytest.mark.parametrize("arch,size,n_obj", [("resnet18", GI.MID, 2), ("resnet101", GI.MID, 2),
+                                             ("resnet18", FULL, 3), ("resnet101", FULL, 5)])
+def test_P1_feedforward_fixed_state(arch, size, n_obj, golden):
+    """Feed-forward at fixed (P, F): the 128x224 cases also against the executed-reference fixture, the 480x854 cases at
+    the object counts of BASELINE configs 2 (rn18, 3 objects) and 3 (rn101, 5 objects) against the live oracle."""
     from oracle import frtm_ref as R
     from frtm_vos_b200 import ops
-    case = GI.feedforward_case(arch)
+    case = GI.feedforward_case(arch, size=size, n_obj=n_obj)
     C = case["PF"][0][0].shape[1]
     trk, fe = _build(arch, case["bb"], case["seg"], GI.disc_params(C))
     img = case["image"]
     feats = fe(img.to(DEV))
     ref = R.backbone_features(case["bb"], arch, img)
-    g = golden("feedforward_" + arch)
+    g = golden("feedforward_" + arch) if size == GI.MID else None
     for L in ("layer1", "layer2", "layer3", "layer4", "layer5"):
         d = (feats[L].cpu() - ref[L]).abs().max().item()
         assert d < 2e-4 * max(1.0, ref[L].abs().max().item()), (L, d)
         sp = feats.split[L]
         back = ((sp.hi.float() + sp.lo.float()) / ops.ACT_SCALE).permute(0, 3, 1, 2).cpu()
         assert (back - feats[L].cpu()).abs().max().item() < 1e-6 * max(1.0, ref[L].abs().max().item())
-    assert np.abs(feats["layer4"].cpu().numpy() - g["ft_layer4"]).max() < 2e-4 * max(1.0, np.abs(g["ft_layer4"]).max())
+    if g is not None:
+        assert np.abs(feats["layer4"].cpu().numpy() - g["ft_layer4"]).max() < 2e-4 * max(1.0, np.abs(g["ft_layer4"]).max())
     seg = GI.strip_prefix(case["seg"])
     logits_all = []
     for i, (P, Fw) in enumerate(case["PF"]):
@@ -59,13 +66,14 @@ def test_P1_feedforward_fixed_state(arch, golden):
         lg_ref = R.seg_forward(seg, s_ref, ref, img.shape[-2:])
         err = (lg.cpu() - lg_ref).abs().max().item()
         assert err < 1e-3, ("logits", i, err)                                   # north-star tolerance
-        assert np.abs(lg.cpu().numpy() - g["logits%d" % i]).max() < 1e-3        # vs the executed reference
+        if g is not None:
+            assert np.abs(lg.cpu().numpy() - g["logits%d" % i]).max() < 1e-3    # vs the executed reference
         logits_all.append((lg, lg_ref))
     # merged labels identical
-    lut = torch.tensor([0, 1, 2], dtype=torch.uint8)
+    lut = torch.arange(n_obj + 1, dtype=torch.uint8)
     src = torch.cat([l[0][0] for l in logits_all], 0)
-    masks, labels, _ = ops.merge_masks(src.contiguous(), 0b11, None, lut.to(DEV), False)
-    cm = torch.zeros(3, *img.shape[-2:])
+    masks, labels, _ = ops.merge_masks(src.contiguous(), (1 << n_obj) - 1, None, lut.to(DEV), False)
+    cm = torch.zeros(n_obj + 1, *img.shape[-2:])
     for i, l in enumerate(logits_all):
         cm[i + 1] = torch.sigmoid(l[1][0, 0])
     merged_ref = R.merge_masks(cm)
@@ -103,18 +111,19 @@ def _oracle_tracker(bb, seg, dp, hooks=None):
                         "cpu", hooks=hooks)
 
 
-def _e2e_setup(n_frames=18):
+def _e2e_setup(n_frames=18, size=GI.MID, n_obj=2):
     from frtm_vos_b200 import synth
-    size = GI.MID
     bb = synth.backbone_state_dict("resnet18", size=size)
     seg = synth.segnet_state_dict("resnet18")
     dp = GI.disc_params(256)
-    seq = synth.SyntheticSequence(num_objects=2, num_frames=n_frames, size=size, seq_id=3)
+    seq = synth.SyntheticSequence(num_objects=n_obj, num_frames=n_frames, size=size, seq_id=3)
     return bb, seg, dp, seq, size
 
 
-def test_P4_end_to_end_oracle_replay():
-    """Inject each object's post-init (P, F, memory, CG state) from the oracle, then run the sequence: logits within
+@pytest.mark.parametrize("size,n_obj", [(GI.MID, 2), (FULL, 3)])
+def test_P4_end_to_end_oracle_replay(size, n_obj):
+    """(128x224, 2 objects) and (480x854, 3 objects = BASELINE config 2's frame shape and object count), 18 frames.
+    Inject each object's post-init (P, F, memory, CG state) from the oracle, then run the sequence: logits within
     1e-3 and identical label maps on every frame, through two GN updates per object.
 
     The 5-iteration CG update amplifies fp32 rounding differences of its inputs: on this small problem the reference
@@ -123,7 +132,7 @@ def test_P4_end_to_end_oracle_replay():
     < 5e-3, the CUDA path lands at ~1e-4) and the oracle's filter is then re-injected, as SURVEY.md §4/P4 prescribes;
     the frame memory and CG state keep running free on the device."""
     from frtm_vos_b200 import ops
-    bb, seg, dp, seq, size = _e2e_setup()
+    bb, seg, dp, seq, size = _e2e_setup(size=size, n_obj=n_obj)
     dump = {"state": {}, "logits": {}}
 
     def after_init(oid, tm):
@@ -198,7 +207,7 @@ def test_P4_end_to_end_oracle_replay():
         e = (lg - lg_ref[0, 0]).abs().max().item()
         per_frame[frame] = max(per_frame.get(frame, 0.0), e)
         worst = max(worst, e)
-    assert len(f_err) == 4 and max(f_err.values()) < 5e-3, f_err
+    assert len(f_err) == 2 * n_obj and max(f_err.values()) < 5e-3, f_err
     assert worst < 1e-3, "logit err per frame: %s | filter rel err after updates: %s" % (
         " ".join("%d:%.1e" % kv for kv in sorted(per_frame.items())), f_err)
     # Label maps: identical, except that a pixel whose oracle decision flips under a +-1e-3 perturbation of the logits
@@ -213,15 +222,17 @@ def test_P4_end_to_end_oracle_replay():
         bad = a != b
         lg = torch.stack([dump["logits"][(i, oid)][0, 0] for oid in seq.obj_ids])
         explained = torch.zeros_like(bad)
-        for s0 in (-1e-3, 1e-3):
-            for s1 in (-1e-3, 1e-3):
-                cm = torch.zeros(3, *size)
-                cm[1:] = torch.sigmoid(lg + torch.tensor([s0, s1]).view(2, 1, 1))
-                alt = R.labels_from_masks(R.merge_masks(cm), lut, False)
-                explained |= (alt == a)
+        import itertools
+        for signs in itertools.product((-1e-3, 1e-3), repeat=n_obj):
+            cm = torch.zeros(n_obj + 1, *size)
+            cm[1:] = torch.sigmoid(lg + torch.tensor(signs).view(n_obj, 1, 1))
+            alt = R.labels_from_masks(R.merge_masks(cm), lut, False)
+            explained |= (alt == a)
         assert bool((explained | ~bad).all()), "labels differ on frame %d beyond logit-tolerance ties" % i
         ties += int(bad.sum())
-    assert ties <= 8, ties
+    # reported, not hidden: pixels whose label depends on the 1e-3 logit tolerance (of %d x %d x %d decided pixels)
+    print("P4 %s: worst logit err %.2e, tie pixels %d of %d" % (size, worst, ties, len(out) * size[0] * size[1]))
+    assert ties <= 8 * (size[0] * size[1]) // (GI.MID[0] * GI.MID[1]), ties
     for oid in seq.obj_ids:
         d, m = trk.targets[oid].discriminator, orc.targets[oid]["model"]
         assert torch.allclose(d.memory.weights.cpu(), m.memory.weights, atol=1e-6)
