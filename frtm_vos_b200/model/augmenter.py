@@ -363,7 +363,13 @@ class ImageAugmenter:
         cand, masks = [], []
         while len(cand) < want:
             fg_specs = draw_specs(fg_pool, rng)
-            bg_specs = draw_specs(bg_pool, rng) if bg_pool is not None else [None] * len(fg_specs)
+            if bg_pool is not None:
+                bg_specs = draw_specs(bg_pool, rng)
+            else:
+                # the reference pairs the foreground specs with ``[None] * (num_aug - 1)`` and ``zip`` stops there
+                # (augmenter.py:520-531): only the first num_aug - 1 candidates of a round are ever looked at
+                fg_specs = fg_specs[:want]
+                bg_specs = [None] * want
             if on_device:
                 warped, counts = self._warp_masks_device(lb.to(dev), fg_specs, bbox, size)
             for j, (fs, bs) in enumerate(zip(fg_specs, bg_specs)):

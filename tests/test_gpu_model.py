@@ -251,7 +251,10 @@ def test_P5_end_to_end_free_running():
     b = torch.stack([o.reshape(size) for o in out_ref])
     assert torch.equal(a[0], b[0])
     agree = (a == b).float().mean().item()
-    assert agree > 0.97, agree
+    # free-running: init is chaotic at ulp level, the reference agrees with itself (1 / 4 / 8 threads) on 99.992-99.998 % of
+    # the pixels of this sequence (profiles/r02_oracle_spread.md); SURVEY.md §4 asks >= 99.9 % of the CUDA path
+    print("P5 free-running label agreement with the oracle: %.6f (%d px differ)" % (agree, int((a != b).sum())))
+    assert agree > 0.999, agree
     assert trk.targets[1].discriminator.memory.current_size == orc.targets[1]["model"].memory.size
 
 
