@@ -15,7 +15,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "libfrtm_b200.so")
+LIB_PATH = os.environ.get("FRTM_B200_LIB") or os.path.join(_HERE, "libfrtm_b200.so")   # override: instrumented builds (make timing)
 HEADER_PATH = os.path.join(ROOT, "include", "frtm_b200.h")
 
 _CTYPES = {

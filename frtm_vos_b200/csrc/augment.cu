@@ -110,9 +110,58 @@ __global__ void warp_mask_cv_kernel(const uint8_t *__restrict__ src, int H, int 
   if ((threadIdx.x & 31) == 0 && b) atomicAdd(count, __popc(b));
 }
 
+// All candidate masks of an augmentation round in ONE launch: blockIdx.z selects the transform (inverse matrices as kernel
+// arguments, no upload), same arithmetic as warp_mask_cv_kernel.
+constexpr int WARP_BATCH = 32;
+struct WarpBatch {
+  double inv[WARP_BATCH][6];
+};
+__global__ void warp_mask_cv_batch_kernel(const uint8_t *__restrict__ src, int H, int W, uint8_t *__restrict__ dst, int Ho, int Wo,
+                                          const __grid_constant__ WarpBatch B, int count_value, int *__restrict__ counts) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, k = blockIdx.z;
+  const double i00 = B.inv[k][0], i01 = B.inv[k][1], i02 = B.inv[k][2], i10 = B.inv[k][3], i11 = B.inv[k][4], i12 = B.inv[k][5];
+  bool hit = false;
+  if (x < Wo) {
+    const int adx = __double2int_rn(i00 * x * 1024.0), ady = __double2int_rn(i10 * x * 1024.0);
+    const int X0 = __double2int_rn((i01 * y + i02) * 1024.0) + 512, Y0 = __double2int_rn((i11 * y + i12) * 1024.0) + 512;
+    const int sx = (X0 + adx) >> 10, sy = (Y0 + ady) >> 10;
+    uint8_t v = 0;
+    if (sx >= 0 && sx < W && sy >= 0 && sy < H) v = src[(int64_t)sy * W + sx];
+    dst[((int64_t)k * Ho + y) * Wo + x] = v;
+    hit = v == count_value;
+  }
+  const unsigned b = __ballot_sync(0xffffffffu, hit);
+  if ((threadIdx.x & 31) == 0 && b) atomicAdd(counts + k, __popc(b));
+}
+
 }  // namespace frtm
 
 using namespace frtm;
+
+// cv::warpAffine's own inversion of a 2x3 matrix (imgwarp.cpp), in double
+static void cv_invert_affine(const double *M_in, double *M) {
+  for (int i = 0; i < 6; ++i) M[i] = M_in[i];
+  double D = M[0] * M[4] - M[1] * M[3];
+  D = D != 0 ? 1. / D : 0;
+  const double A11 = M[4] * D, A22 = M[0] * D;
+  M[0] = A11; M[1] *= -D; M[3] *= -D; M[4] = A22;
+  const double b1 = -M[0] * M[2] - M[1] * M[5], b2 = -M[3] * M[2] - M[4] * M[5];
+  M[2] = b1; M[5] = b2;
+}
+
+extern "C" int frtm_warp_mask_nearest_batch(const uint8_t *src, int H, int W, uint8_t *dst, int Ho, int Wo, int n,
+                                            const double *M_host, int count_value, int *counts, void *stream) {
+  FRTM_REQUIRE(src && dst && M_host && counts && n >= 1 && Ho >= 1 && Ho <= 65535, "warp_mask_nearest_batch: bad arguments");
+  for (int k0 = 0; k0 < n; k0 += WARP_BATCH) {
+    const int nb = n - k0 < WARP_BATCH ? n - k0 : WARP_BATCH;
+    WarpBatch B;
+    for (int k = 0; k < WARP_BATCH; ++k) cv_invert_affine(M_host + 6 * (k0 + (k < nb ? k : 0)), B.inv[k]);
+    warp_mask_cv_batch_kernel<<<dim3(cdiv(Wo, 128), Ho, nb), 128, 0, (cudaStream_t)stream>>>(
+        src, H, W, dst + (int64_t)k0 * Ho * Wo, Ho, Wo, B, count_value, counts + k0);
+    FRTM_CHECK_LAUNCH("warp_mask_nearest_batch");
+  }
+  return FRTM_OK;
+}
 
 static bool invert_affine(const double *M, float *inv) {
   const double det = M[0] * M[4] - M[1] * M[3];

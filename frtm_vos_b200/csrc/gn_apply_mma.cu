@@ -58,6 +58,14 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_
   lo = *reinterpret_cast<const uint32_t *>(&l);
 }
 
+// Phase timeline (timing builds only, `make timing` -> libfrtm_b200_timing.so): thread 0 of CTA (0,0) accumulates the
+// clock64 time it spends in every phase of a sample and prints the totals.
+#ifdef GM_TIMING
+#define GM_T(k) do { if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) { const long long t__ = clock64(); tacc[k] += t__ - tlast; tlast = t__; } } while (0)
+#else
+#define GM_T(k) do { } while (0)
+#endif
+
 template <int C>
 __device__ __forceinline__ void gm_sample(const GaArgs &a, const GcParams &P) {
   constexpr int KS = C / 16;                          // channel k-steps of P1 = channel m-tiles of P3
@@ -160,6 +168,9 @@ __device__ __forceinline__ void gm_sample(const GaArgs &a, const GcParams &P) {
     gacc8[m][0] = 0.f; gacc8[m][1] = 0.f;
   }
 
+#ifdef GM_TIMING
+  long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
+#endif
   int s_hi = 0, v_hi = 0;
   for (int b = 0; b < nblocks + 2; ++b) {
     const int s_lo = s_hi, v_lo = v_hi;
@@ -177,7 +188,9 @@ __device__ __forceinline__ void gm_sample(const GaArgs &a, const GcParams &P) {
     // ---------------- P1(b) ----------------
     if (b < nblocks) {
       const int slot = b % GM_SLOTS;
+      GM_T(0);
       mbar_wait(bars + 8 * slot, (b / GM_SLOTS) & 1);
+      GM_T(1);
       const uint32_t t1 = ring + slot * blk_bytes + off1;
       float ys[4] = {0.f, 0.f, 0.f, 0.f}, y8[2] = {0.f, 0.f};
 #pragma unroll
@@ -211,7 +224,9 @@ __device__ __forceinline__ void gm_sample(const GaArgs &a, const GcParams &P) {
         ybuf[8 * GM_YSTRIDE + pr + 8] = y8[1] * yscale;
       }
     }
+    GM_T(2);
     __syncthreads();
+    GM_T(3);
 
     // ---------------- scores ----------------
     for (int q = s_lo + tid; q < s_hi; q += GM_THREADS) {
@@ -225,7 +240,9 @@ __device__ __forceinline__ void gm_sample(const GaArgs &a, const GcParams &P) {
       }
       sring[q & (GM_RING - 1)] = sum;
     }
+    GM_T(4);
     __syncthreads();
+    GM_T(5);
 
     // ---------------- residual ----------------
     for (int q = qv; q < v_hi; q += GM_BLK) {
@@ -246,7 +263,9 @@ __device__ __forceinline__ void gm_sample(const GaArgs &a, const GcParams &P) {
       if (use_y) av -= st[9];
       vring[q & (GM_RING - 1)] = av * wgt;
     }
+    GM_T(6);
     __syncthreads();
+    GM_T(7);
 
     // ---------------- P3(b - 2) ----------------
     if (b >= 2) {
@@ -307,7 +326,9 @@ __device__ __forceinline__ void gm_sample(const GaArgs &a, const GcParams &P) {
         gacc8[m][0] = fmaf((d4[0] + d4[1]) + (d5[0] + d5[1]), gscale, gacc8[m][0]);
         gacc8[m][1] = fmaf((d4[2] + d4[3]) + (d5[2] + d5[3]), gscale, gacc8[m][1]);
       }
+      GM_T(8);
       __syncthreads();                                 // every warp is done with block b - 2: its slot takes block b + 2
+      GM_T(9);
       if (tid == 0 && b + 2 < nblocks) {
         const int nb = b + 2;
         const uint32_t dst = ring + slot * blk_bytes;
@@ -319,6 +340,11 @@ __device__ __forceinline__ void gm_sample(const GaArgs &a, const GcParams &P) {
     }
   }
 
+#ifdef GM_TIMING
+  if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0)
+    printf("gm timeline (clocks, %d steps): stencil-issue %lld | wait-load %lld | P1 %lld | bar %lld | scores %lld | bar %lld | residual %lld | bar %lld "
+           "| P3 %lld | bar %lld\n", nblocks + 2, tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], tacc[5], tacc[6], tacc[7], tacc[8], tacc[9]);
+#endif
   // ---- the 8 warps' partial gradients, summed in a fixed order (the ring is idle: every block was consumed) ----
   float *gred = reinterpret_cast<float *>(gen);        // [GM_WARPS][n]
   {

@@ -236,6 +236,7 @@ def target_locations(n: int, im_size, rng=np.random) -> List[Tuple[float, float]
 
 
 _INPAINT_POOL = None
+_BLUR_CACHE = {}
 
 
 def _inpaint_pool():
@@ -288,10 +289,10 @@ class ImageAugmenter:
         out = torch.empty((n, 1, H, W), device=mask_d.device, dtype=torch.uint8)
         counts = torch.zeros(n, device=mask_d.device, dtype=torch.int32)
         src = mask_d.reshape(H, W).contiguous()
-        for j, fs in enumerate(fg_specs):
-            T, _ = spec_transform(fs, bbox, size, with_blur=False)
-            M = (ctypes.c_double * 6)(*np.asarray(T, dtype=np.float32)[:2, :].astype(np.float64).ravel())
-            L.warp_mask_nearest(ptr(src), H, W, ptr(out[j]), H, W, M, 1, counts[j:j + 1].data_ptr(), stream())
+        # one launch for the whole round: the n transforms travel as kernel arguments
+        Ms = np.stack([np.asarray(spec_transform(fs, bbox, size, with_blur=False)[0], dtype=np.float32)[:2, :] for fs in fg_specs])
+        M = (ctypes.c_double * (6 * n))(*Ms.astype(np.float64).ravel())
+        L.warp_mask_nearest_batch(ptr(src), H, W, ptr(out), H, W, n, M, 1, ptr(counts), stream())
         return out, counts.tolist()
 
     def _render_device(self, bg_d, cut_d, fg_spec, bbox, bg_spec):
@@ -313,7 +314,14 @@ class ImageAugmenter:
             G = np.asarray(G, dtype=np.float32)
             if G.shape == (1, 1):
                 return img
-            k = torch.from_numpy(np.ascontiguousarray(G)).to(dev)
+            # the blur kernels of a spec pool are few and recur for every object (the generators are reseeded per object,
+            # tracker.py:178-180): keep them on the device instead of a synchronous pageable upload per use
+            key = (str(dev), G.shape, G.tobytes())
+            k = _BLUR_CACHE.get(key)
+            if k is None:
+                if len(_BLUR_CACHE) > 256:
+                    _BLUR_CACHE.clear()
+                k = _BLUR_CACHE[key] = torch.from_numpy(np.ascontiguousarray(G)).to(dev)
             out = torch.empty_like(img)
             L.filter2d(ptr(img), img.shape[0], H, W, ptr(k), G.shape[0], G.shape[1], ptr(out), stream())
             return out

@@ -282,6 +282,11 @@ int frtm_warp_affine(const void *src, int src_is_u8, int C, int H, int W, float 
  * by the caller) — the visibility test of augmenter.py:453-471.  lib/image.py:53 with mode 'nearest'. */
 int frtm_warp_mask_nearest(const uint8_t *src, int H, int W, uint8_t *dst, int Ho, int Wo, const double *M_host,
                            int count_value, int *count, void *stream);
+/* The same warp for n transforms of ONE source mask in a single launch (all candidate masks of an augmentation round,
+ * model/augmenter.py:453-471,520-533): M_host holds n row-major 2x3 matrices, dst is (n,Ho,Wo), counts[n] (zeroed by the
+ * caller) receive the per-mask pixel counts.  The matrices travel as kernel arguments: no upload, no synchronisation. */
+int frtm_warp_mask_nearest_batch(const uint8_t *src, int H, int W, uint8_t *dst, int Ho, int Wo, int n, const double *M_host,
+                                 int count_value, int *counts, void *stream);
 /* Per-channel 2-D cross-correlation with zero padding kh/2, kw/2 (the directional blur, augmenter.py:342-350). */
 int frtm_filter2d(const float *src, int C, int H, int W, const float *kernel, int kh, int kw, float *dst, void *stream);
 /* out (3,H,W) uint8 = rgba[:3] * a + canvas * (1 - a), a = rgba[3] / 255, truncated (augmenter.py:391-394). */

@@ -87,6 +87,23 @@ def replay_on_device(trk, seq, dump, n_frames, device):
     return out, got_logits
 
 
+def tie_pixels(lg_ref, labels_got, labels_ref, lut, tol=1e-3):
+    """Pixels where ``labels_got != labels_ref``: (mismatching, explained) — explained = the oracle's own label becomes
+    ``labels_got`` when each object's reference logit map (n_obj,H,W) moves by +-tol (the stated logit tolerance)."""
+    import itertools
+    from oracle import frtm_ref as R
+    n_obj, size = lg_ref.shape[0], tuple(lg_ref.shape[-2:])
+    bad = labels_got != labels_ref
+    if not bool(bad.any()):
+        return 0, 0
+    explained = torch.zeros_like(bad)
+    for signs in itertools.product((-tol, tol), repeat=n_obj):
+        cm = torch.zeros(n_obj + 1, *size)
+        cm[1:] = torch.sigmoid(lg_ref + torch.tensor(signs).view(n_obj, 1, 1))
+        explained |= (R.labels_from_masks(R.merge_masks(cm), lut, n_obj == 1).reshape(size) == labels_got)
+    return int(bad.sum()), int((explained & bad).sum())
+
+
 def compare(seq, size, out, got_logits, out_ref, dump, n_frames):
     """-> dict(frames, objects, pixels, mismatching_px, tie_px, max_logit_err): label maps of the device path vs the
     oracle's on frames 1..n_frames-1; ``tie_px`` = mismatching pixels whose oracle label flips under a +-1e-3 change of

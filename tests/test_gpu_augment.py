@@ -70,3 +70,27 @@ def test_device_mask_warp_is_bit_identical_to_cv2():
                                     ptr(cnt), stream())
             assert torch.equal(out.cpu(), ref.reshape(480, 854)), spec
             assert int(cnt) == int((ref == 1).sum())
+
+
+def test_batched_mask_warp_equals_single_warps():
+    """frtm_warp_mask_nearest_batch (all candidate masks of a round in one launch) == n calls of frtm_warp_mask_nearest."""
+    import ctypes
+    from frtm_vos_b200._lib import lib, ptr, stream
+    L = lib()
+    g = torch.Generator().manual_seed(4)
+    H, W, n = 97, 131, 37                                  # more than one batch of 32
+    src = (torch.rand(H, W, generator=g) > 0.6).to(torch.uint8).to(DEV)
+    rng = np.random.RandomState(8)
+    Ms = []
+    for _ in range(n):
+        a, s = rng.uniform(-1, 1), rng.uniform(0.5, 1.6)
+        Ms.append([s * np.cos(a), -s * np.sin(a), rng.uniform(-20, 20), s * np.sin(a), s * np.cos(a), rng.uniform(-20, 20)])
+    Ms = np.asarray(Ms, dtype=np.float32).astype(np.float64)
+    out_b = torch.empty(n, H, W, dtype=torch.uint8, device=DEV)
+    cnt_b = torch.zeros(n, dtype=torch.int32, device=DEV)
+    L.warp_mask_nearest_batch(ptr(src), H, W, ptr(out_b), H, W, n, (ctypes.c_double * (6 * n))(*Ms.ravel()), 1, ptr(cnt_b), stream())
+    out_s = torch.empty_like(out_b)
+    cnt_s = torch.zeros_like(cnt_b)
+    for j in range(n):
+        L.warp_mask_nearest(ptr(src), H, W, ptr(out_s[j]), H, W, (ctypes.c_double * 6)(*Ms[j]), 1, cnt_s[j:j + 1].data_ptr(), stream())
+    assert torch.equal(out_b, out_s) and torch.equal(cnt_b, cnt_s) and int(cnt_b.sum()) > 0

@@ -78,7 +78,15 @@ def test_P1_feedforward_fixed_state(arch, size, n_obj, golden):
         cm[i + 1] = torch.sigmoid(l[1][0, 0])
     merged_ref = R.merge_masks(cm)
     labels_ref = R.labels_from_masks(merged_ref.clone(), lut, False)
-    assert torch.equal(labels.cpu(), labels_ref)                                 # bit-exact argmax label map
+    # argmax label map: identical, except where the oracle's own decision flips under the +-1e-3 logit tolerance (with
+    # random, unfitted (P, F) the objects overlap everywhere, so near-ties between saturated objects exist); every
+    # mismatch must be such a tie and they must be rare.  The small fixture cases are exactly identical.
+    import replay
+    bad, tie = replay.tie_pixels(torch.stack([l[1][0, 0] for l in logits_all]), labels.cpu(), labels_ref.reshape(labels.shape), lut)
+    print("P1 %s %s: %d mismatching label pixels (%d ties at +-1e-3) of %d" % (arch, tuple(size), bad, tie, labels.numel()))
+    assert bad == tie and bad <= 1e-5 * labels.numel(), (bad, tie)
+    if size == GI.MID:
+        assert bad == 0
     # merged scores are softmax(p/(1-p)): where two objects saturate (p -> 1) the value is ill-conditioned by
     # construction (z = p/(1-p) ~ 1e3 amplifies a 1e-4 logit difference to O(0.1)), so compare robustly
     dm = (masks.cpu() - merged_ref).abs()

@@ -106,7 +106,7 @@ def _operator_fp64(X, S, T, sw, p, use_y):
         v -= T.double()
     v = v * sw.double().view(-1, 1, 1)
     # gradient of sum(conv(X, p) * v) w.r.t. p
-    g = torch.nn.grad.conv2d_weight(Xd.reshape(1, cap * c, h, w), (cap, 1, 3, 3), v.view(1, cap, h, w), padding=1, groups=cap)
+    g = torch.nn.grad.conv2d_weight(Xd.reshape(1, cap * c, h, w), (cap, c, 3, 3), v.view(1, cap, h, w), padding=1, groups=cap)
     return g.view(cap, c, 3, 3).sum(0).reshape(-1)
 
 
