@@ -18,9 +18,14 @@
 //
 // Arithmetic: operands are split fp16 pairs (16 x = hi + lo in the image; p scaled per object, v per warp-step by a power
 // of two) and every product is hi*hi + hi*lo + lo*hi.  Taps 0-7 are one n-tile; tap 8 shares a second n-tile between its
-// hi and lo columns, so a product costs five m16n8k16 instructions.  mma.sync accumulates at most 2 k-steps x 3 products
-// before the result is folded into fp32 registers with ordinary adds; the 8 warps' partial gradients are summed in a fixed
-// order, the per-sample rows by the fused tail (target_model.cuh) — results are deterministic.
+// hi and lo columns, so a product costs five m16n8k16 instructions.  The warps are few (one CTA per SM, 8 warps), so the
+// instruction streams are written for instruction-level parallelism: all ldmatrix loads of a phase are issued first, the
+// products run as independent accumulator chains (P1: 5 chains over the 6 channel k-steps; P3: 12 chains, one per channel
+// m-tile and tap group, continued across up to 4 steps inside the tensor core before they are folded into fp32 sums), the
+// score / residual phases are branch-free.  The P3 operand is scaled by the running maximum of |v| of the sample (tracked
+// by the residual phase with one warp-reduce + shared atomicMax per warp), which changes rarely; the accumulators are
+// folded first when it does.  The 8 warps' partial gradients are summed in a fixed order, the per-sample rows by the fused
+// tail (target_model.cuh) — results are deterministic.
 #include "common.cuh"
 #include "target_model.cuh"
 #include "tc_ptx.cuh"
@@ -66,13 +71,22 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_
 #define GM_T(k) do { } while (0)
 #endif
 
+// power of two that brings a non-negative float (given by its bits) into [2^9, 2^10); 1 for 0 / inf / nan
+__device__ __forceinline__ float scale_from_bits(unsigned bits) {
+  const int e = (int)(bits >> 23);                    // biased exponent: value = 1.m x 2^(e-127)
+  if (bits == 0u || e == 0 || e >= 255) return 1.f;
+  const int se = min(max(127 + 9 - (e - 127), 27), 227);   // 2^(9 - (e-127)), clamped like pow2_scale
+  return __uint_as_float((unsigned)se << 23);
+}
+
 template <int C>
 __device__ __forceinline__ void gm_sample(const GaArgs &a, const GcParams &P) {
   constexpr int KS = C / 16;                          // channel k-steps of P1 = channel m-tiles of P3
+  constexpr int FOLD = 4;                             // P3 steps accumulated inside the tensor core between fp32 folds
   const int h = a.h, w = a.w, use_y = a.use_y;
   constexpr int n = C * 9;
   const int hw = h * w, lag = w + 1;
-  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, wp = uniform_warp_idx();
   const int nblocks = P.ntiles >> 1;
   const uint32_t tile_bytes = (uint32_t)P.tile_bytes, blk_bytes = 2u * tile_bytes;
   const int i = blockIdx.x;
@@ -102,7 +116,8 @@ __device__ __forceinline__ void gm_sample(const GaArgs &a, const GcParams &P) {
   float *ybuf = reinterpret_cast<float *>(gen + GM_SLOTS * blk_bytes);       // [9][GM_YSTRIDE]
   float *sring = ybuf + 9 * GM_YSTRIDE;
   float *vring = sring + GM_RING;
-  float *red = vring + GM_RING;                                               // 8 floats
+  float *red = vring + GM_RING;                                               // 8 floats: [0..7] warp maxima, then the running |v| max
+  unsigned *vmaxbits = reinterpret_cast<unsigned *>(red) + 7;
   const uint32_t bars = base + GM_SLOTS * blk_bytes + (9 * GM_YSTRIDE + 2 * GM_RING + 8) * 4;   // 8-byte aligned
 
   if (tid == 0) {
@@ -119,11 +134,15 @@ __device__ __forceinline__ void gm_sample(const GaArgs &a, const GcParams &P) {
   //      thread keeps its B fragments of all channel k-steps in registers ----
   float pscale;
   {
+    constexpr int PV = (n + GM_THREADS - 1) / GM_THREADS;
+    float pv[PV];
+#pragma unroll
+    for (int k = 0; k < PV; ++k) pv[k] = tid + k * GM_THREADS < n ? pvec[tid + k * GM_THREADS] : 0.f;   // all loads in flight
     float amax = 0.f;
-    for (int k = tid; k < n; k += GM_THREADS) {
-      const float v = pvec[k];
-      ybuf[k] = v;
-      amax = fmaxf(amax, fabsf(v));
+#pragma unroll
+    for (int k = 0; k < PV; ++k) {
+      if (tid + k * GM_THREADS < n) ybuf[tid + k * GM_THREADS] = pv[k];
+      amax = fmaxf(amax, fabsf(pv[k]));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
@@ -148,8 +167,11 @@ __device__ __forceinline__ void gm_sample(const GaArgs &a, const GcParams &P) {
     }
   }
   __syncthreads();                                     // p staging is read: the tap-map ring may be written
+  if (tid == 0) *vmaxbits = 0u;                        // (red[0..7] were consumed before the barrier)
   const float yscale = 1.f / (GC_ACT_SCALE * pscale);
 
+  // exact q / w for q < 65536 without an integer division
+  const unsigned magic = 0xFFFFFFFFu / (unsigned)w + 1u;
   // per-lane ldmatrix offsets inside an image tile (row r of an 8x8 matrix = lane & 7, matrix id = lane >> 3)
   const int lr = lane & 7, lid = lane >> 3;
   const int jj = wp >> 2;                              // image tile of the block this warp's 16 pixels live in
@@ -160,83 +182,123 @@ __device__ __forceinline__ void gm_sample(const GaArgs &a, const GcParams &P) {
   const uint32_t off3 = jj * tile_bytes + (uint32_t)((lid & 1) * 8 + lr) * 128u + (uint32_t)(((ch0 + (lid >> 1)) ^ lr) << 4);
   const uint32_t plane = (uint32_t)C * 128u;           // hi -> lo plane of a tile
 
-  float gacc[KS][4], gacc8[KS][2];
+  // P3 state: accumulators inside the tensor core (acc, at scale cur_scale), folded sums in fp32 (gsum)
+  float acc[KS][4], acc8[KS][4], gsum[KS][4], gsum8[KS][2];
 #pragma unroll
   for (int m = 0; m < KS; ++m) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) gacc[m][u] = 0.f;
-    gacc8[m][0] = 0.f; gacc8[m][1] = 0.f;
+    for (int u = 0; u < 4; ++u) { acc[m][u] = 0.f; acc8[m][u] = 0.f; gsum[m][u] = 0.f; }
+    gsum8[m][0] = 0.f; gsum8[m][1] = 0.f;
+  }
+  float cur_scale = 0.f;
+  int nacc = 0;
+  auto fold = [&]() {
+    const float gs = 1.f / (GC_ACT_SCALE * cur_scale);
+#pragma unroll
+    for (int m = 0; m < KS; ++m) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { gsum[m][u] = fmaf(acc[m][u], gs, gsum[m][u]); acc[m][u] = 0.f; }
+      gsum8[m][0] = fmaf(acc8[m][0] + acc8[m][1], gs, gsum8[m][0]);
+      gsum8[m][1] = fmaf(acc8[m][2] + acc8[m][3], gs, gsum8[m][1]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc8[m][u] = 0.f;
+    }
+    nacc = 0;
+  };
+  // tap of this lane's B column (taps 0-7) and the position of its first k pixel, advanced by one block per P3 step
+  const int tdy = g / 3 - 1, tdx = g % 3 - 1, toff = tdy * w + tdx;
+  const int step_y = (int)__umulhi((unsigned)GM_BLK, magic), step_x = GM_BLK - step_y * w;
+  int py, px;
+  {
+    const unsigned q0 = (unsigned)(wp * 16 + k0);
+    py = (int)__umulhi(q0, magic);
+    px = (int)q0 - py * w;
   }
 
 #ifdef GM_TIMING
   long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
 #endif
   int s_hi = 0, v_hi = 0;
+  float stn[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  {   // stencil rows of step 0's residual pixels
+    const int s_hi0 = 0 >= nblocks - 1 ? hw : GM_BLK - lag;
+    const int v_hi0 = 0 >= nblocks - 1 ? hw : max(s_hi0 - lag, 0);
+    const int q1 = tid >> 1;
+    if (q1 < v_hi0) {
+      const float *src = sten + (int64_t)(q1 >> 8) * (10 * GC_CHUNK_PX) + (q1 & (GC_CHUNK_PX - 1)) + (tid & 1) * 5 * GC_CHUNK_PX;
+#pragma unroll
+      for (int t = 0; t < 5; ++t) stn[t] = (t < 4 || !(tid & 1) || use_y) ? __ldg(src + t * GC_CHUNK_PX) : 0.f;
+    }
+  }
   for (int b = 0; b < nblocks + 2; ++b) {
     const int s_lo = s_hi, v_lo = v_hi;
     s_hi = b >= nblocks - 1 ? hw : GM_BLK * (b + 1) - lag;
     v_hi = b >= nblocks - 1 ? hw : max(s_hi - lag, 0);
-    // stencil rows of this step's residual pixels: issued now, consumed after P1 and the score gather
-    float st[10];
-    const int qv = v_lo + tid;
-    if (tid < GM_BLK && qv < v_hi) {
-      const float *src = sten + (int64_t)(qv >> 8) * (10 * GC_CHUNK_PX) + (qv & (GC_CHUNK_PX - 1));
+    // stencil rows of the NEXT step's residual pixels (two threads per pixel: taps 0-4 | taps 5-8 and t): the loads have a
+    // whole step to arrive from HBM; this step's rows were fetched during the previous one
+    float st[5];
 #pragma unroll
-      for (int t = 0; t < 10; ++t) st[t] = (t < 9 || use_y) ? __ldg(src + t * GC_CHUNK_PX) : 0.f;
+    for (int t = 0; t < 5; ++t) st[t] = stn[t];
+    {
+      const int b1 = b + 1;
+      const int s_hi1 = b1 >= nblocks - 1 ? hw : GM_BLK * (b1 + 1) - lag;
+      const int v_hi1 = b1 >= nblocks - 1 ? hw : max(s_hi1 - lag, 0);
+      const int q1 = v_hi + (tid >> 1);
+      if (b1 < nblocks + 2 && q1 < v_hi1) {
+        const float *src = sten + (int64_t)(q1 >> 8) * (10 * GC_CHUNK_PX) + (q1 & (GC_CHUNK_PX - 1)) + (tid & 1) * 5 * GC_CHUNK_PX;
+#pragma unroll
+        for (int t = 0; t < 5; ++t) stn[t] = (t < 4 || !(tid & 1) || use_y) ? __ldg(src + t * GC_CHUNK_PX) : 0.f;
+      }
     }
 
-    // ---------------- P1(b) ----------------
+    // ---------------- P1(b): five accumulator chains over the six channel k-steps ----------------
     if (b < nblocks) {
       const int slot = b % GM_SLOTS;
       GM_T(0);
       mbar_wait(bars + 8 * slot, (b / GM_SLOTS) & 1);
       GM_T(1);
       const uint32_t t1 = ring + slot * blk_bytes + off1;
-      float ys[4] = {0.f, 0.f, 0.f, 0.f}, y8[2] = {0.f, 0.f};
+      uint32_t ah[KS][4], al[KS][4];
 #pragma unroll
-      for (int kp = 0; kp < KS; kp += 2) {
-        float d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f}, d3[4] = {0.f, 0.f, 0.f, 0.f},
-              d4[4] = {0.f, 0.f, 0.f, 0.f}, d5[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int ks = 0; ks < KS; ++ks) {
+        ldsm_x4_t(t1 + ks * 2048, ah[ks]);
+        ldsm_x4_t(t1 + ks * 2048 + plane, al[ks]);
+      }
+      float d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f}, d3[4] = {0.f, 0.f, 0.f, 0.f},
+            d4[4] = {0.f, 0.f, 0.f, 0.f}, d5[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int ks = kp; ks < kp + 2 && ks < KS; ++ks) {
-          uint32_t ah[4], al[4];
-          ldsm_x4_t(t1 + ks * 2048, ah);
-          ldsm_x4_t(t1 + ks * 2048 + plane, al);
-          hmma(d1, ah, pbh[ks][0], pbh[ks][1]);
-          hmma(d2, ah, pbl[ks][0], pbl[ks][1]);
-          hmma(d3, al, pbh[ks][0], pbh[ks][1]);
-          hmma(d4, ah, pb8[ks][0], pb8[ks][1]);
-          hmma(d5, al, pb8[ks][0], pb8[ks][1]);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) ys[u] += (d1[u] + d2[u]) + d3[u];
-        y8[0] += (d4[0] + d4[1]) + (d5[0] + d5[1]);
-        y8[1] += (d4[2] + d4[3]) + (d5[2] + d5[3]);
+      for (int ks = 0; ks < KS; ++ks) {
+        hmma(d1, ah[ks], pbh[ks][0], pbh[ks][1]);
+        hmma(d4, ah[ks], pb8[ks][0], pb8[ks][1]);
+        hmma(d2, ah[ks], pbl[ks][0], pbl[ks][1]);
+        hmma(d3, al[ks], pbh[ks][0], pbh[ks][1]);
+        hmma(d5, al[ks], pb8[ks][0], pb8[ks][1]);
       }
       // D rows = pixels g, g + 8 of the m-tile; columns = taps k0, k0 + 1 (tap 8: column 0/1 sum, lanes with k0 == 0)
       const int pr = ((b * GM_BLK) & (GM_YPX - 1)) + wp * 16 + g;
-      ybuf[k0 * GM_YSTRIDE + pr] = ys[0] * yscale;
-      ybuf[(k0 + 1) * GM_YSTRIDE + pr] = ys[1] * yscale;
-      ybuf[k0 * GM_YSTRIDE + pr + 8] = ys[2] * yscale;
-      ybuf[(k0 + 1) * GM_YSTRIDE + pr + 8] = ys[3] * yscale;
+      ybuf[k0 * GM_YSTRIDE + pr] = ((d1[0] + d2[0]) + d3[0]) * yscale;
+      ybuf[(k0 + 1) * GM_YSTRIDE + pr] = ((d1[1] + d2[1]) + d3[1]) * yscale;
+      ybuf[k0 * GM_YSTRIDE + pr + 8] = ((d1[2] + d2[2]) + d3[2]) * yscale;
+      ybuf[(k0 + 1) * GM_YSTRIDE + pr + 8] = ((d1[3] + d2[3]) + d3[3]) * yscale;
       if (k0 == 0) {
-        ybuf[8 * GM_YSTRIDE + pr] = y8[0] * yscale;
-        ybuf[8 * GM_YSTRIDE + pr + 8] = y8[1] * yscale;
+        ybuf[8 * GM_YSTRIDE + pr] = ((d4[0] + d4[1]) + (d5[0] + d5[1])) * yscale;
+        ybuf[8 * GM_YSTRIDE + pr + 8] = ((d4[2] + d4[3]) + (d5[2] + d5[3])) * yscale;
       }
     }
     GM_T(2);
     __syncthreads();
     GM_T(3);
 
-    // ---------------- scores ----------------
+    // ---------------- scores (branch-free gather; every step's range fits one round of the CTA) ----------------
     for (int q = s_lo + tid; q < s_hi; q += GM_THREADS) {
-      const int y = q / w, x = q - y * w;
+      const int y = (int)__umulhi((unsigned)q, magic), x = q - y * w;
       float sum = 0.f;
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         const int dy = t / 3 - 1, dx = t % 3 - 1;
-        if ((unsigned)(y + dy) < (unsigned)h && (unsigned)(x + dx) < (unsigned)w)
-          sum += ybuf[t * GM_YSTRIDE + ((q + dy * w + dx) & (GM_YPX - 1))];
+        const bool ok = (unsigned)(y + dy) < (unsigned)h && (unsigned)(x + dx) < (unsigned)w;
+        const float yv = ybuf[t * GM_YSTRIDE + ((q + dy * w + dx) & (GM_YPX - 1))];
+        sum += ok ? yv : 0.f;
       }
       sring[q & (GM_RING - 1)] = sum;
     }
@@ -244,101 +306,122 @@ __device__ __forceinline__ void gm_sample(const GaArgs &a, const GcParams &P) {
     __syncthreads();
     GM_T(5);
 
-    // ---------------- residual ----------------
-    for (int q = qv; q < v_hi; q += GM_BLK) {
-      if (tid >= GM_BLK) break;
-      if (q != qv) {                                   // tail steps cover more than one round: load directly
-        const float *src = sten + (int64_t)(q >> 8) * (10 * GC_CHUNK_PX) + (q & (GC_CHUNK_PX - 1));
+    // ---------------- residual, and the running maximum of |v| (the scale of the P3 operand) ----------------
+    {
+      unsigned vb = 0u;
+      const int half = tid & 1;
+      for (int q0 = v_lo, round = 0; q0 < v_hi; q0 += GM_THREADS / 2, ++round) {     // CTA-uniform trip count
+        const int q = q0 + (tid >> 1);
+        const bool act = q < v_hi;
+        if (round && act) {                              // tail steps cover more than one round: load directly
+          const float *src = sten + (int64_t)(q >> 8) * (10 * GC_CHUNK_PX) + (q & (GC_CHUNK_PX - 1)) + half * 5 * GC_CHUNK_PX;
 #pragma unroll
-        for (int t = 0; t < 10; ++t) st[t] = (t < 9 || use_y) ? __ldg(src + t * GC_CHUNK_PX) : 0.f;
-      }
-      const int y = q / w, x = q - y * w;
-      float av = 0.f;
+          for (int t = 0; t < 5; ++t) st[t] = (t < 4 || !half || use_y) ? __ldg(src + t * GC_CHUNK_PX) : 0.f;
+        }
+        const int y = (int)__umulhi((unsigned)q, magic), x = q - y * w;
+        float av = 0.f;
 #pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const int dy = t / 3 - 1, dx = t % 3 - 1;
-        const bool ok = (unsigned)(y + dy) < (unsigned)h && (unsigned)(x + dx) < (unsigned)w;
-        av = fmaf(st[t], ok ? sring[(q + dy * w + dx) & (GM_RING - 1)] : 0.f, av);
+        for (int u = 0; u < 5; ++u) {
+          const int t = half * 5 + u;                    // taps 0-4 | 5-8 (u = 4 of the second half is the t row)
+          if (u < 4 || !half) {
+            const int dy = t / 3 - 1, dx = t % 3 - 1;
+            const bool ok = act && (unsigned)(y + dy) < (unsigned)h && (unsigned)(x + dx) < (unsigned)w;
+            const float sv = sring[(q + dy * w + dx) & (GM_RING - 1)];
+            av = fmaf(ok ? st[u] : 0.f, ok ? sv : 0.f, av);
+          }
+        }
+        if (half && use_y && act) av -= st[4];
+        av += __shfl_xor_sync(0xffffffffu, av, 1);       // the two halves of a pixel sit in neighbouring lanes
+        av *= wgt;
+        if (act) {
+          if (!half) vring[q & (GM_RING - 1)] = av;
+          vb = max(vb, __float_as_uint(fabsf(av)));
+        }
       }
-      if (use_y) av -= st[9];
-      vring[q & (GM_RING - 1)] = av * wgt;
+      vb = __reduce_max_sync(0xffffffffu, vb);
+      if (lane == 0 && vb) atomicMax(vmaxbits, vb);
     }
     GM_T(6);
     __syncthreads();
     GM_T(7);
 
-    // ---------------- P3(b - 2) ----------------
+    // ---------------- P3(b - 2): six independent accumulator chains (channel m-tiles) x 5 products ----------------
     if (b >= 2) {
       const int bb = b - 2;
       const int slot = bb % GM_SLOTS;
-      const int qb = bb * GM_BLK + wp * 16;
+      const uint32_t t3 = ring + slot * blk_bytes + off3;
+      uint32_t ah[KS][4], al[KS][4];
+#pragma unroll
+      for (int m = 0; m < KS; ++m) {                       // the A operand does not depend on v: issue its loads first
+        ldsm_x4(t3 + m * 2048, ah[m]);
+        ldsm_x4(t3 + m * 2048 + plane, al[m]);
+      }
+      // scale of the operand: the running max of |v| over everything computed so far (changes rarely; the tensor-core
+      // accumulators are folded into fp32 first when it does)
+      const float vscale = scale_from_bits(*vmaxbits);
+      if (vscale != cur_scale || nacc == FOLD) {
+        if (nacc) fold();
+        cur_scale = vscale;
+      }
       // B = shifted residual: B[k = pixel][n = tap] = v(y - dy, x - dx), zero outside the map
       float vv[4], v8[4];
       {
-        const int q0 = qb + k0;
-        int y = q0 / w, x = q0 - y * w;
-        const int dy = g / 3 - 1, dx = g % 3 - 1;       // tap g (0-7)
+        const int q0 = bb * GM_BLK + wp * 16 + k0;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          // k = k0, k0 + 1, k0 + 8, k0 + 9
-          const int q = q0 + (e & 1) + (e >> 1) * 8;
-          int yy = y, xx = x + (e & 1) + (e >> 1) * 8;
+        for (int e = 0; e < 4; ++e) {                      // k = k0, k0 + 1, k0 + 8, k0 + 9
+          const int dq = (e & 1) + (e >> 1) * 8;
+          const int q = q0 + dq;
+          int yy = py, xx = px + dq;
           if (xx >= w) { xx -= w; ++yy; }
           if (xx >= w) { xx -= w; ++yy; }
           const bool in = q < hw;
-          const bool ok = in && (unsigned)(yy - dy) < (unsigned)h && (unsigned)(xx - dx) < (unsigned)w;
-          vv[e] = ok ? vring[(q - dy * w - dx) & (GM_RING - 1)] : 0.f;
+          const bool ok = in && (unsigned)(yy - tdy) < (unsigned)h && (unsigned)(xx - tdx) < (unsigned)w;
           const bool ok8 = in && g < 2 && yy >= 1 && xx >= 1;                  // tap 8: dy = dx = +1
-          v8[e] = ok8 ? vring[(q - w - 1) & (GM_RING - 1)] : 0.f;
+          const float a0 = vring[(q - toff) & (GM_RING - 1)], a8 = vring[(q - w - 1) & (GM_RING - 1)];
+          vv[e] = ok ? a0 * vscale : 0.f;
+          v8[e] = ok8 ? a8 * vscale : 0.f;
         }
+        px += step_x; py += step_y;                        // next P3 step: one block further
+        if (px >= w) { px -= w; ++py; }
       }
-      float vmax = fmaxf(fmaxf(fabsf(vv[0]), fabsf(vv[1])), fmaxf(fabsf(vv[2]), fabsf(vv[3])));
-      vmax = fmaxf(vmax, fmaxf(fmaxf(fabsf(v8[0]), fabsf(v8[1])), fmaxf(fabsf(v8[2]), fabsf(v8[3]))));
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-      const float vscale = pow2_scale(vmax);
-      const float gscale = 1.f / (GC_ACT_SCALE * vscale);
       uint32_t bh[2], bl[2], b8[2];
-      split2(vv[0] * vscale, vv[1] * vscale, bh[0], bl[0]);
-      split2(vv[2] * vscale, vv[3] * vscale, bh[1], bl[1]);
+      split2(vv[0], vv[1], bh[0], bl[0]);
+      split2(vv[2], vv[3], bh[1], bl[1]);
       {
         uint32_t h0, l0, h1, l1;
-        split2(v8[0] * vscale, v8[1] * vscale, h0, l0);
-        split2(v8[2] * vscale, v8[3] * vscale, h1, l1);
+        split2(v8[0], v8[1], h0, l0);
+        split2(v8[2], v8[3], h1, l1);
         b8[0] = g == 0 ? h0 : (g == 1 ? l0 : 0u);
         b8[1] = g == 0 ? h1 : (g == 1 ? l1 : 0u);
       }
-      const uint32_t t3 = ring + slot * blk_bytes + off3;
 #pragma unroll
-      for (int m = 0; m < KS; ++m) {
-        uint32_t ah[4], al[4];
-        ldsm_x4(t3 + m * 2048, ah);
-        ldsm_x4(t3 + m * 2048 + plane, al);
-        float d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f}, d3[4] = {0.f, 0.f, 0.f, 0.f},
-              d4[4] = {0.f, 0.f, 0.f, 0.f}, d5[4] = {0.f, 0.f, 0.f, 0.f};
-        hmma(d1, ah, bh[0], bh[1]);
-        hmma(d2, ah, bl[0], bl[1]);
-        hmma(d3, al, bh[0], bh[1]);
-        hmma(d4, ah, b8[0], b8[1]);
-        hmma(d5, al, b8[0], b8[1]);
+      for (int m = 0; m < KS; ++m) hmma(acc[m], ah[m], bh[0], bh[1]);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) gacc[m][u] = fmaf((d1[u] + d2[u]) + d3[u], gscale, gacc[m][u]);
-        gacc8[m][0] = fmaf((d4[0] + d4[1]) + (d5[0] + d5[1]), gscale, gacc8[m][0]);
-        gacc8[m][1] = fmaf((d4[2] + d4[3]) + (d5[2] + d5[3]), gscale, gacc8[m][1]);
-      }
+      for (int m = 0; m < KS; ++m) hmma(acc8[m], ah[m], b8[0], b8[1]);
+#pragma unroll
+      for (int m = 0; m < KS; ++m) hmma(acc[m], ah[m], bl[0], bl[1]);
+#pragma unroll
+      for (int m = 0; m < KS; ++m) hmma(acc8[m], al[m], b8[0], b8[1]);
+#pragma unroll
+      for (int m = 0; m < KS; ++m) hmma(acc[m], al[m], bh[0], bh[1]);
+      ++nacc;
       GM_T(8);
       __syncthreads();                                 // every warp is done with block b - 2: its slot takes block b + 2
       GM_T(9);
-      if (tid == 0 && b + 2 < nblocks) {
+      if (wp == 0 && b + 2 < nblocks) {                // warp-uniform branch + elected lane: addresses stay in uniform registers
         const int nb = b + 2;
         const uint32_t dst = ring + slot * blk_bytes;
         const uint8_t *src = img + (int64_t)nb * blk_bytes;
-        mbar_expect_tx(bars + 8 * slot, blk_bytes);
-        bulk_load(dst, src, tile_bytes, bars + 8 * slot);
-        bulk_load(dst + tile_bytes, src + tile_bytes, tile_bytes, bars + 8 * slot);
+        if (elect_one()) {
+          mbar_expect_tx(bars + 8 * slot, blk_bytes);
+          bulk_load(dst, src, tile_bytes, bars + 8 * slot);
+          bulk_load(dst + tile_bytes, src + tile_bytes, tile_bytes, bars + 8 * slot);
+        }
+        __syncwarp();
       }
     }
   }
+  if (nacc) fold();
 
 #ifdef GM_TIMING
   if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0)
@@ -352,13 +435,13 @@ __device__ __forceinline__ void gm_sample(const GaArgs &a, const GcParams &P) {
 #pragma unroll
     for (int m = 0; m < KS; ++m) {
       const int ch = m * 16 + g;
-      mine[ch * 9 + k0] = gacc[m][0];
-      mine[ch * 9 + k0 + 1] = gacc[m][1];
-      mine[(ch + 8) * 9 + k0] = gacc[m][2];
-      mine[(ch + 8) * 9 + k0 + 1] = gacc[m][3];
+      mine[ch * 9 + k0] = gsum[m][0];
+      mine[ch * 9 + k0 + 1] = gsum[m][1];
+      mine[(ch + 8) * 9 + k0] = gsum[m][2];
+      mine[(ch + 8) * 9 + k0 + 1] = gsum[m][3];
       if (k0 == 0) {
-        mine[ch * 9 + 8] = gacc8[m][0];
-        mine[(ch + 8) * 9 + 8] = gacc8[m][1];
+        mine[ch * 9 + 8] = gsum8[m][0];
+        mine[(ch + 8) * 9 + 8] = gsum8[m][1];
       }
     }
   }
@@ -383,7 +466,7 @@ static size_t gm_smem(int c) {
 bool gn_apply_mma_supported(int c, int h, int w) {
   // the window lags are measured in rows of the map: three rows (+3) must fit in two 128-pixel blocks; the fragment
   // walk advances a pixel by up to 8 inside a row
-  return c == GM_MAXC && w >= 8 && 3 * (w + 1) <= 2 * GM_BLK && h >= 1 && gm_smem(c) <= 227 * 1024;
+  return c == GM_MAXC && w >= 8 && 3 * (w + 1) <= 2 * GM_BLK && h >= 1 && h * w < 65536 && gm_smem(c) <= 227 * 1024;
 }
 
 int gn_apply_mma_launch(const GaArgs &a, const GcFuse &fuse, cudaStream_t st) {

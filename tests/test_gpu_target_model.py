@@ -132,17 +132,18 @@ def _cg_fp64(X, S, T, sw, f0, n_cg, reg=1e-2, precond=1e-2):
     return (f + x).float()
 
 
-OPERATOR_SHAPES = [(16, 12, 96, 4, 7), (6, 5, 96, 30, 54), (4, 4, 64, 9, 13), (3, 3, 112, 17, 8), (5, 4, 96, 8, 14),
-                   (3, 3, 96, 45, 80), (4, 3, 96, 11, 84), (3, 2, 96, 2, 9)]
+# (cap, M, c, h, w, CG iterations): the last shape has 18 pixels for 864 unknowns — one iteration, or CG amplifies rounding
+OPERATOR_SHAPES = [(16, 12, 96, 4, 7, 5), (6, 5, 96, 30, 54, 5), (4, 4, 64, 9, 13, 5), (3, 3, 112, 17, 8, 5), (5, 4, 96, 8, 14, 5),
+                   (3, 3, 96, 45, 80, 5), (4, 3, 96, 11, 84, 5), (3, 2, 96, 2, 9, 1)]
 
 
-@pytest.mark.parametrize("cap,M,c,h,w", OPERATOR_SHAPES)
-def test_operator_kernels_match_fp64_and_each_other(cap, M, c, h, w):
+@pytest.mark.parametrize("cap,M,c,h,w,n_cg", OPERATOR_SHAPES)
+def test_operator_kernels_match_fp64_and_each_other(cap, M, c, h, w, n_cg):
     """Every operator kernel that takes the shape (single-pass mma.sync, two-pass tcgen05, CUDA cores; selected per call
-    through ``operator_select`` of the C ABI) against a float64 evaluation of the same RHS + 5 CG iterations."""
+    through ``operator_select`` of the C ABI) against a float64 evaluation of the same RHS + CG iterations."""
     from frtm_vos_b200._lib import lib, ptr, stream
     X, S, T, sw, f0 = _operator_problem(cap, M, c, h, w, seed=c + h)
-    ref = _cg_fp64(X, S, T, sw, f0, 5)
+    ref = _cg_fp64(X, S, T, sw, f0, n_cg)
     Xd, Sd, Td, swd = X.to(DEV), S.to(DEV), T.to(DEV), sw.to(DEV)
     L = lib()
     nb = L.split_sample_bytes(c, h * w)
@@ -151,7 +152,7 @@ def test_operator_kernels_match_fp64_and_each_other(cap, M, c, h, w):
     L.split_samples(ptr(Xd), ptr(Sd), ptr(Td), cap, c, h * w, ptr(XS), stream())
     nbytes = L.gn_update_workspace(cap, c, h, w)
     ws = torch.empty(nbytes // 4, device=DEV)
-    arr = (ctypes.c_int * 1)(5)
+    arr = (ctypes.c_int * 1)(n_cg)
     step = (ref - f0).abs().max().item()
     assert step > 1e-3                                         # the update did something
     scale = max(ref.abs().max().item(), 1.0)

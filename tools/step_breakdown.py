@@ -1,4 +1,5 @@
-"""Wall-clock breakdown of one 65-frame sequence (synchronising after each phase; profiling aid only)."""
+"""Wall-clock breakdown of one sequence of a BASELINE config (synchronising after each phase; profiling aid only):
+python tools/step_breakdown.py [2|3|5]"""
 import os, sys, time
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -6,9 +7,12 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.p
 from quick_run import build_tracker
 from frtm_vos_b200 import synth
 dev = "cuda:0"
-size = (480, 854)
-trk = build_tracker("resnet18", size, dev)
-seq = synth.SyntheticSequence(num_objects=3, num_frames=65, size=size, seq_id=1)
+sys.path.insert(0, ROOT)
+import bench as B
+cfg = B.CONFIGS[int(sys.argv[1]) if len(sys.argv) > 1 else 2]
+size = cfg["size"]
+trk = build_tracker(cfg["arch"], size, dev, fast=cfg["fast"], memory_size=cfg["memory"])
+seq = synth.SyntheticSequence(num_objects=cfg["objects"], num_frames=cfg["frames"], size=size, seq_id=1)
 seq.preload(dev)
 for _ in range(2):
     trk.run_sequence(seq)
@@ -23,6 +27,7 @@ def timed_block(imgs):
     acc["block"] += t2 - t0; acc["block_host"] += t1 - t0; acc["nblocks"] += 1; return r
 trk.initialize, trk._track_block = timed_init, timed_block
 t0 = time.time(); trk.run_sequence(seq); total = time.time() - t0
+print(cfg["name"])
 print("total %.1f ms | init %.1f ms (host part %.1f) | %d blocks %.1f ms (host part %.1f) | other %.1f ms" % (
     total * 1e3, acc["init"] * 1e3, acc["init_host"] * 1e3, acc["nblocks"], acc["block"] * 1e3, acc["block_host"] * 1e3,
     (total - acc["init"] - acc["block"]) * 1e3))
