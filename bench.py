@@ -340,12 +340,15 @@ def run_b200(cfg, steps, warmup, dev, rank, world, dist, with_clocks):
     rhs_bytes = M * 4 * (c * h * w + 10 * h * w)
     n_launch = n_cg + 1                       # the operator kernel's last CTA per object runs the CG vector step itself
     achieved = (rhs_bytes + n_cg * ap_bytes) / (ms_update * 1e-3) / 1e9
-    single = L.gn_operator_kind(c, h, w) == 3
+    kind = L.gn_operator_kind(c, h, w)
     roofline = dict(bound="hbm", achieved=achieved, peak=pk["hbm"], unit="GB/s", frac=achieved / pk["hbm"],
                     traffic=measured_traffic(cfg, M),
-                    kernel=("gn_apply_mma_kernel (single pass over the operator images: sliding window, mma.sync tiles, CG vector "
-                            "step fused into its tail)" if single else
-                            "gn_apply_tc_kernel (two-pass tcgen05 operator over the operator images, CG vector step fused)") +
+                    kernel={4: "gn_apply_cl_kernel (every sample held on chip by a thread-block cluster through its three phases: one "
+                               "HBM read per sample, mma.sync tiles, DSMEM halo exchange, persistent clusters, CG vector step fused)",
+                            3: "gn_apply_mma_kernel (single pass over the operator images: sliding window, mma.sync tiles, CG vector "
+                               "step fused into its tail)",
+                            2: "gn_apply_tc_kernel (two-pass tcgen05 operator over the operator images, CG vector step fused)",
+                            1: "gn_apply_kernel (CUDA cores)"}[int(kind)] +
                            " inside one batched filter update (RHS + %d x A.p, stencil form S; %d objects, M=%s active samples "
                            "of %d, sample = %dx%dx%d as split fp16 planes = fp32 bytes)" % (n_cg, len(live), Ms, cap, c, h, w),
                     ms=ms_update, launches=n_launch, algorithmic_bytes_per_launch=ap_bytes, peak_source=pk["src"],

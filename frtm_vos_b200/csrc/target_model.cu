@@ -1082,11 +1082,11 @@ extern "C" int64_t frtm_gn_update_workspace(int cap, int c, int h, int w) {
   const int64_t n = (int64_t)c * 9, hw = (int64_t)h * w;
   // s[cap][hw] | v[cap][hw] | partial[cap][n] | r[n] | x[n] | q[n] | tickets[1 + ngroups] | group sums[ngroups][n]
   const int64_t ngrp = (cap + GC_RGROUP - 1) / GC_RGROUP;
-  return (2 * cap * hw + cap * n + 3 * n + 64 + (1 + ngrp) + 8 + ngrp * n) * (int64_t)sizeof(float);
+  return (2 * cap * hw + cap * n + 3 * n + 64 + (1 + ngrp) + 8 + ngrp * n) * (int64_t)sizeof(float) + gn_apply_cl_workspace(1, cap, c);
 }
 
 extern "C" int64_t frtm_gn_operator_kind(int c, int h, int w) {
-  return gn_apply_mma_supported(c, h, w) ? 3 : (gn_apply_tc_supported(c, h, w) ? 2 : 1);
+  return gn_apply_cl_supported(c, h, w) ? 4 : gn_apply_mma_supported(c, h, w) ? 3 : (gn_apply_tc_supported(c, h, w) ? 2 : 1);
 }
 
 static int gn_update_impl(const float *samples, const __half *samples_split, const float *stencil, const float *uty,
@@ -1119,12 +1119,16 @@ static int gn_update_impl(const float *samples, const __half *samples_split, con
   // Operator kernels over the operator images (written at insert time): the single-pass mma.sync kernel where the shape
   // allows it, else the two-pass tcgen05 kernel, else CUDA cores.  operator_select forces one (tests, A-B measurements).
   const bool have_image = table ? table_has_split : samples_split != nullptr;
-  FRTM_REQUIRE(operator_select >= 0 && operator_select <= 3, "gn_update: operator_select must be 0..3");
+  FRTM_REQUIRE(operator_select >= 0 && operator_select <= 4, "gn_update: operator_select must be 0..4");
   FRTM_REQUIRE(operator_select < 2 || have_image, "gn_update: the tensor-core operators need the operator images");
   FRTM_REQUIRE(operator_select != 2 || gn_apply_tc_supported(c, h, w), "gn_update: shape not supported by the two-pass operator");
   FRTM_REQUIRE(operator_select != 3 || gn_apply_mma_supported(c, h, w), "gn_update: shape not supported by the single-pass operator");
-  const bool use_mma = operator_select == 3 || (operator_select == 0 && have_image && gn_apply_mma_supported(c, h, w));
-  const bool use_tc = use_mma || operator_select == 2 || (operator_select == 0 && have_image && gn_apply_tc_supported(c, h, w));
+  // the cluster operator gives every cluster a contiguous range of the active samples (at most 96 per launch and cluster)
+  const bool cl_ok = gn_apply_cl_supported(c, h, w) && (int64_t)n_obj * cap <= 16 * 96 && n_obj < 65536 && cap < 65536;
+  FRTM_REQUIRE(operator_select != 4 || cl_ok, "gn_update: shape not supported by the cluster operator");
+  const bool use_cl = operator_select == 4 || (operator_select == 0 && have_image && cl_ok);
+  const bool use_mma = !use_cl && (operator_select == 3 || (operator_select == 0 && have_image && gn_apply_mma_supported(c, h, w)));
+  const bool use_tc = use_cl || use_mma || operator_select == 2 || (operator_select == 0 && have_image && gn_apply_tc_supported(c, h, w));
   ga.n_obj = n_obj; ga.cap = cap; ga.c = c; ga.h = h; ga.w = w; ga.use_y = 1;
   CgVec cg;
   cg.f = filt; cg.p = cg_state; cg.rprev = cg_state ? cg_state + n : nullptr; cg.rho = cg_state ? cg_state + 2 * n : nullptr;
@@ -1166,9 +1170,15 @@ static int gn_update_impl(const float *samples, const __half *samples_split, con
       return FRTM_ELAUNCH;
     }
   }
+  // the cluster operator's own region sits behind the n_obj older layouts: rows per (object, cluster), tickets, work list
+  float *ws_cl = workspace + (n_obj * (frtm_gn_update_workspace(cap, c, h, w) - gn_apply_cl_workspace(1, cap, c))) / (int64_t)sizeof(float);
+  if (use_cl) {
+    if (int rc = gn_apply_cl_prepare(ga, ws_cl, st)) return rc;
+  }
   auto launch_apply = [&]() -> int {
     if (use_tc) {
-      const int rc = use_mma ? gn_apply_mma_launch(ga, fuse, st) : gn_apply_tc_launch(ga, fuse, st);
+      const int rc = use_cl ? gn_apply_cl_launch(ga, fuse, ws_cl, st)
+                            : use_mma ? gn_apply_mma_launch(ga, fuse, st) : gn_apply_tc_launch(ga, fuse, st);
       if (rc == FRTM_OK) count_launch(-1);                  // counted again by FRTM_CHECK_LAUNCH at the call site
       return rc;
     }

@@ -58,6 +58,12 @@ bool gn_apply_mma_supported(int c, int h, int w);
 struct GcFuse;
 int gn_apply_tc_launch(const GaArgs &a, const GcFuse &fuse, cudaStream_t st);
 int gn_apply_mma_launch(const GaArgs &a, const GcFuse &fuse, cudaStream_t st);
+// gn_apply_cl_*: one sample per thread-block cluster, resident on chip through its three phases (gn_apply_cl.cu); persistent
+// clusters over a work list built once per update (prepare), own workspace (rows per (object, cluster), tickets, the list)
+bool gn_apply_cl_supported(int c, int h, int w);
+int64_t gn_apply_cl_workspace(int n_obj, int cap, int c);
+int gn_apply_cl_prepare(const GaArgs &a, float *ws, cudaStream_t st);
+int gn_apply_cl_launch(const GaArgs &a, const GcFuse &fuse, float *ws, cudaStream_t st);
 
 // One work item of the image build.  Items [0, ntiles*c*8): 8 consecutive pixels of channel row r in tile j -> one
 // 16-byte chunk in each plane.  Remaining items: 4 consecutive pixels of one stencil / uty row of one chunk.

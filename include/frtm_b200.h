@@ -225,11 +225,12 @@ int64_t frtm_split_sample_bytes(int c, int hw);
  *   residual  r = W (U (X * f) - y),  A p = X^T (U^T W^2 U) X p + reg^2 p,  b = -(X^T U^T W^2 (U X f - y) + reg^2 f)
  * samples (cap,c,h,w), stencil (cap,9,h,w), uty (cap,h,w), weights (cap) [inactive = 0];
  * samples_split (optional, NULL = absent): the operator images of the samples (frtm_split_samples); when given the
- * operator streams only the images and both contractions run on the tensor cores: in ONE pass over every image
- * (sliding window, c == 96, 8 <= w <= 84 — gn_apply_mma.cu) or in two (tcgen05, c % 16 == 0, 48 <= c <= 128 —
- * gn_apply_tc.cu); otherwise on CUDA cores.  operator_select: 0 = the library picks by shape, 1 = CUDA cores,
- * 2 = two-pass tcgen05, 3 = single-pass (EINVAL if the shape is not supported) — a per-call argument for tests and
- * A-B measurements, the library keeps no mode;
+ * operator streams only the images and both contractions run on the tensor cores: in ONE pass with every sample held on
+ * chip by a thread-block cluster (c == 96, 8 <= w <= 95 — gn_apply_cl.cu) or streamed through a sliding window by one CTA
+ * (c == 96, 8 <= w <= 84 — gn_apply_mma.cu), or in two passes (tcgen05, c % 16 == 0, 48 <= c <= 128 — gn_apply_tc.cu);
+ * otherwise on CUDA cores.  operator_select: 0 = the library picks by shape, 1 = CUDA cores, 2 = two-pass tcgen05,
+ * 3 = single-pass sliding window, 4 = cluster (EINVAL if the shape is not supported) — a per-call argument for tests
+ * and A-B measurements, the library keeps no mode;
  * filt (c*9) updated in place;  cg_state = float[2*c*9 + 4]: p | r_prev | rho | has_p — persists across calls
  * (zero-initialised by the caller);  cg_iters_host[n_gn] CG iterations per GN iteration (host array);
  * the update is applied only if gate_count == NULL or gate_count[0] >= min_px (device-side predicate, replaces the
@@ -240,7 +241,7 @@ int frtm_gn_update(const float *samples, const void *samples_split, const float 
                    int min_px, int operator_select, float *workspace, int64_t workspace_bytes, void *stream);
 int64_t frtm_gn_update_workspace(int cap, int c, int h, int w);
 /* Which operator kernel operator_select = 0 resolves to for this shape when the operator images are given:
- * 3 = single-pass, 2 = two-pass tcgen05, 1 = CUDA cores. */
+ * 4 = cluster, 3 = single-pass sliding window, 2 = two-pass tcgen05, 1 = CUDA cores. */
 int64_t frtm_gn_operator_kind(int c, int h, int w);
 /* The same update for n_obj objects in ONE set of launches (grid.y = object; the objects of a sequence update on the
  * same frames).  table: device int64[8][n_obj] of device pointers, rows = {samples, stencil, uty, weights, filt,

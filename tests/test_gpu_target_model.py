@@ -139,8 +139,9 @@ OPERATOR_SHAPES = [(16, 12, 96, 4, 7, 5), (6, 5, 96, 30, 54, 5), (4, 4, 64, 9, 1
 
 @pytest.mark.parametrize("cap,M,c,h,w,n_cg", OPERATOR_SHAPES)
 def test_operator_kernels_match_fp64_and_each_other(cap, M, c, h, w, n_cg):
-    """Every operator kernel that takes the shape (single-pass mma.sync, two-pass tcgen05, CUDA cores; selected per call
-    through ``operator_select`` of the C ABI) against a float64 evaluation of the same RHS + CG iterations."""
+    """Every operator kernel that takes the shape (cluster-resident, single-pass sliding window, two-pass tcgen05, CUDA
+    cores; selected per call through ``operator_select`` of the C ABI) against a float64 evaluation of the same RHS + CG
+    iterations."""
     from frtm_vos_b200._lib import lib, ptr, stream
     X, S, T, sw, f0 = _operator_problem(cap, M, c, h, w, seed=c + h)
     ref = _cg_fp64(X, S, T, sw, f0, n_cg)
@@ -157,14 +158,14 @@ def test_operator_kernels_match_fp64_and_each_other(cap, M, c, h, w, n_cg):
     assert step > 1e-3                                         # the update did something
     scale = max(ref.abs().max().item(), 1.0)
     ran = []
-    for sel, name in ((3, "single-pass"), (2, "two-pass"), (1, "cuda-core"), (0, "auto")):
+    for sel, name in ((4, "cluster"), (3, "single-pass"), (2, "two-pass"), (1, "cuda-core"), (0, "auto")):
         filt = f0.clone().to(DEV)
         st = torch.zeros(2 * c * 9 + 4, device=DEV)
         try:
             L.gn_update(ptr(Xd), ptr(XS), ptr(Sd), ptr(Td), ptr(swd), cap, c, h, w, ptr(filt), ptr(st), arr, 1, 1e-2, 1e-2,
                         0.9 ** 750, None, 10, sel, ptr(ws), nbytes, stream())
         except RuntimeError as e:
-            assert "not supported" in str(e) and sel in (2, 3), (name, str(e))
+            assert "not supported" in str(e) and sel in (2, 3, 4), (name, str(e))
             continue
         torch.cuda.synchronize()
         ran.append(sel)
@@ -172,7 +173,8 @@ def test_operator_kernels_match_fp64_and_each_other(cap, M, c, h, w, n_cg):
         assert (filt.cpu() - ref).abs().max().item() < 1e-5 * scale, (name, (filt.cpu() - ref).abs().max().item())
     assert 1 in ran and 0 in ran
     if c == 96 and 8 <= w <= 84:
-        assert 3 in ran                                        # the production shapes run the single-pass kernel
+        assert 3 in ran and 4 in ran                           # the production shapes run the single-pass kernels
+    assert (4 in ran) == (L.gn_operator_kind(c, h, w) == 4)
 
 
 @pytest.mark.parametrize("cap,M,h,w,H,W,n_cg", [(80, 72, 30, 54, 480, 854, 10), (32, 32, 45, 80, 720, 1280, 10)])

@@ -2,8 +2,8 @@
 
     python tools/gn_operator_time.py [n_obj] [M] [cap] [h] [w] [n_cg] [kernels]
 
-defaults: 3 objects x 69 of 80 samples at 30x54, 5 CG iterations (the config-2 update), kernels = "3,2,1"
-(3 = single pass, 2 = two-pass tcgen05, 1 = CUDA cores).  Also checks the filters of the kernels against each other.
+defaults: 3 objects x 69 of 80 samples at 30x54, 5 CG iterations (the config-2 update), kernels = "4,3,2,1"
+(4 = cluster-resident, 3 = single-pass sliding window, 2 = two-pass tcgen05, 1 = CUDA cores).  Also checks the filters of the kernels against each other.
 Prints algorithmic GB/s (form S of SURVEY.md §8(d)) and the fraction of the measured HBM peak.
 """
 import ctypes, json, os, sys
@@ -14,7 +14,7 @@ from frtm_vos_b200._lib import lib, ptr, stream  # noqa: E402
 DEV = "cuda:0"
 arg = lambda k, d: type(d)(sys.argv[k]) if len(sys.argv) > k else d
 n_obj, M, cap, h, w, n_cg = arg(1, 3), arg(2, 69), arg(3, 80), arg(4, 30), arg(5, 54), arg(6, 5)
-kernels = [int(v) for v in arg(7, "3,2,1").split(",")]
+kernels = [int(v) for v in arg(7, "4,3,2,1").split(",")]
 c = 96
 peak = 6533.5
 pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -40,7 +40,7 @@ nbytes = n_obj * L.gn_update_workspace(cap, c, h, w)
 ws = torch.empty(nbytes // 4, device=DEV)
 arr = (ctypes.c_int * 1)(n_cg)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
-names = {1: "cuda-core", 2: "two-pass tcgen05", 3: "single-pass mma"}
+names = {1: "cuda-core", 2: "two-pass tcgen05", 3: "single-pass mma", 4: "cluster mma"}
 results = {}
 
 
