@@ -125,6 +125,10 @@ struct ClParams {
 
 __device__ __forceinline__ int cl_cluster_of(int u, int U, int NC) { return (int)(((long long)(u + 1) * NC - 1) / U); }
 
+__device__ __forceinline__ void ldsm_x2(uint32_t addr, uint32_t &r0, uint32_t &r1) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+
 __global__ void __launch_bounds__(CL_THREADS, 1) gn_apply_cl_kernel(const GaArgs a, const ClParams P, const GcFuse F) {
   constexpr int C = CL_C, KS = C / 16, n = C * 9;
   __shared__ int s_last;
@@ -137,6 +141,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gn_apply_cl_kernel(const GaArgs
   const int T0 = rank * P.ntiles / CS, T1 = (rank + 1) * P.ntiles / CS, ntl = T1 - T0;
   const int a0 = T0 * GC_TILE, own_px = max(min(T1 * GC_TILE, hw) - a0, 0);
   const int left_px = rank > 0 ? a0 - (rank - 1) * P.ntiles / CS * GC_TILE : 0;      // own pixels of the left neighbour
+  const int npx = GC_TILE * ntl;                                                      // pixels of the own tiles (incl. padding)
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -145,39 +150,68 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gn_apply_cl_kernel(const GaArgs
   const int EXT = 2 * CL_HALO + GC_TILE * P.nslot;                      // s / v arrays with halo
   const int YCAP = max(9 * YS, 5 * n);                                  // the tap-map area doubles as p / flush staging (5 n floats)
   const uint32_t ring = base;
-  float *ybuf = reinterpret_cast<float *>(gen + (size_t)P.nslot * tile_bytes);   // [9][YS]
+  // fixed block behind the ring (16-byte aligned): zero chunk | barriers | image pointers
+  uint8_t *fix = gen + (size_t)P.nslot * tile_bytes;
+  uint4 *zero16 = reinterpret_cast<uint4 *>(fix);                           // 16 zero bytes (ldmatrix rows of the unused taps)
+  const uint32_t bars = smem_u32(fix + 16);
+  const uint32_t bar_full = bars, bar_cons = bars + 8 * CL_MAXSLOT;
+  unsigned long long *item_img = reinterpret_cast<unsigned long long *>(fix + 16 + 16 * CL_MAXSLOT);   // [CL_MAXITEMS]
+  float *ybuf = reinterpret_cast<float *>(fix + 16 + 16 * CL_MAXSLOT + 8 * CL_MAXITEMS);   // [9][YS]; later the shifted-v operand
   float *sext = ybuf + YCAP;
   float *vext = sext + EXT;
   float *red = vext + EXT;                                                   // 8 floats
   unsigned *vmaxbits = reinterpret_cast<unsigned *>(red + 8);
   int *issued = reinterpret_cast<int *>(red + 10);                          // [CL_MAXSLOT]
-  uint32_t *my_items = reinterpret_cast<uint32_t *>(red + 10 + CL_MAXSLOT);  // [CL_MAXITEMS]
-  const uint32_t bars = (base + (uint32_t)(reinterpret_cast<uint8_t *>(my_items + CL_MAXITEMS) - gen) + 7u) & ~7u;
-  const uint32_t bar_full = bars, bar_cons = bars + 8 * CL_MAXSLOT;
+  float *item_wgt = red + 10 + CL_MAXSLOT;                                   // [CL_MAXITEMS] sample weights
+  int *item_obj = reinterpret_cast<int *>(item_wgt + CL_MAXITEMS);          // [CL_MAXITEMS]
+  uint16_t *maskv = reinterpret_cast<uint16_t *>(item_obj + CL_MAXITEMS);  // [64 * CL_MAXSLOT] tap validity of the own pixels
   const uint32_t ybuf_s = smem_u32(ybuf), sext_s = smem_u32(sext), vext_s = smem_u32(vext);
+  // shifted-v operand of P3 (aliases the tap maps, dead by then): fp16 [n][pixel] rows, pixels contiguous
+  const int VP = npx + 8;                                                // row pitch in halves (pitch bytes == 16 mod 128)
+  __half *vhi = reinterpret_cast<__half *>(ybuf), *vlo = vhi + 8 * VP, *v8h = vlo + 8 * VP, *v8l = v8h + VP;
 
-  // ---- the cluster's range of the work list ----
+  // ---- the cluster's range of the work list; everything an item needs from global memory is fetched up front ----
   // (fewer samples than clusters: the first U clusters take one each, so the clusters that hold rows of an object are
   //  always a contiguous interval; U == 0: no cluster has items and cl_cluster_of is never called)
   const int U = P.list.hdr[0];
   const int NC = min(P.nclusters, max(U, 1));
   const int u_lo = cid < NC ? (int)((long long)cid * U / NC) : 0, u_hi = cid < NC ? (int)((long long)(cid + 1) * U / NC) : 0;
   const int nitems = u_hi - u_lo;
-  for (int k = tid; k < nitems; k += CL_THREADS) my_items[k] = P.list.items[u_lo + k];
+  for (int k = tid; k < nitems; k += CL_THREADS) {
+    const uint32_t item = P.list.items[u_lo + k];
+    const int o = (int)(item >> 16), slot = (int)(item & 0xffffu);
+    const __half *xs = a.table ? reinterpret_cast<const __half *>(a.table[7 * a.n_obj + o]) : a.XS;
+    const float *swp = a.table ? reinterpret_cast<const float *>(a.table[3 * a.n_obj + o]) : a.sw;
+    item_obj[k] = o;
+    item_img[k] = (unsigned long long)(reinterpret_cast<const uint8_t *>(xs) + (int64_t)slot * P.image_bytes);
+    item_wgt[k] = swp[slot];
+  }
+  const unsigned magic = 0xFFFFFFFFu / (unsigned)w + 1u;   // exact q / w for q < 65536
+  for (int lp = tid; lp < GC_TILE * CL_MAXSLOT; lp += CL_THREADS) {
+    // bit t: pixel q + off(t) is inside the map (t = 3 (dy + 1) + dx + 1); bit 15: q itself is a pixel of the map
+    const int q = a0 + lp;
+    unsigned m = 0u;
+    if (lp < npx && q < hw) {
+      const int y = (int)__umulhi((unsigned)q, magic), x = q - y * w;
+      m = 0x8000u;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int dy = t / 3 - 1, dx = t % 3 - 1;
+        if ((unsigned)(y + dy) < (unsigned)h && (unsigned)(x + dx) < (unsigned)w) m |= 1u << t;
+      }
+    }
+    maskv[lp] = (uint16_t)m;
+  }
   if (tid == 0) {
     for (int s = 0; s < CL_MAXSLOT; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_cons + 8 * s, 4); issued[s] = 0; }
+    *zero16 = make_uint4(0u, 0u, 0u, 0u);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  auto image_of = [&](uint32_t item) -> const uint8_t * {
-    const int o = (int)(item >> 16), slot = (int)(item & 0xffffu);
-    const __half *xs = a.table ? reinterpret_cast<const __half *>(a.table[7 * a.n_obj + o]) : a.XS;
-    return reinterpret_cast<const uint8_t *>(xs) + (int64_t)slot * P.image_bytes;
-  };
   // first sample: all own tiles
   if (wp == 0 && nitems > 0) {
-    const uint8_t *img = image_of(my_items[0]) + (int64_t)T0 * tile_bytes;
+    const uint8_t *img = reinterpret_cast<const uint8_t *>(item_img[0]) + (int64_t)T0 * tile_bytes;
     if (elect_one()) {
       for (int j = 0; j < ntl; ++j) {
         mbar_expect_tx(bar_full + 8 * j, tile_bytes);
@@ -188,10 +222,8 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gn_apply_cl_kernel(const GaArgs
   }
   cluster_sync_all();                                  // every CTA of the cluster is resident before any DSMEM access
 
-  const unsigned magic = 0xFFFFFFFFu / (unsigned)w + 1u;   // exact q / w for q < 65536
   const int g = lane >> 2, k0 = (lane & 3) * 2;
   const int lr = lane & 7, lid = lane >> 3;
-  const int tdy = g / 3 - 1, tdx = g % 3 - 1, toff = tdy * w + tdx;
   const uint32_t plane = (uint32_t)C * 128u;
 
   float gsum[KS][4], gsum8[KS][2];
@@ -205,8 +237,6 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gn_apply_cl_kernel(const GaArgs
   float yscale = 0.f;
   int cur_obj = -1;
 
-  // Sum of the 8 warps, then of the CS CTAs (fixed orders); rank 0 writes the row of (object, this cluster) and draws the
-  // object's ticket; the cluster that draws the last one reduces the rows and runs the CG vector step.
   // the row of (object o, this cluster) is complete in global memory: draw the object's ticket; the last cluster sums the
   // rows (fixed order) and runs the CG vector step.  Rank 0 only; CTA-local synchronisation only.
   auto finish_object = [&](int o, int c_lo, int nrows, bool have_row) {
@@ -308,14 +338,11 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gn_apply_cl_kernel(const GaArgs
 #endif
   for (int it = 0; it < nitems; ++it) {
     CL_T(0);
-    const uint32_t item = my_items[it];
-    const int o = (int)(item >> 16), slot = (int)(item & 0xffffu);
+    const int o = item_obj[it];
     const uint32_t par = (uint32_t)it & 1u;
-    const float *swp = a.table ? reinterpret_cast<const float *>(a.table[3 * a.n_obj + o]) : a.sw;
-    const float wgt = swp[slot];
-    const uint8_t *img = image_of(item);
-    const float *sten = reinterpret_cast<const float *>(img + (int64_t)P.ntiles * tile_bytes);
-    const uint8_t *img_next = it + 1 < nitems ? image_of(my_items[it + 1]) + (int64_t)T0 * tile_bytes : nullptr;
+    const float wgt = item_wgt[it];
+    const float *sten = reinterpret_cast<const float *>(reinterpret_cast<const uint8_t *>(item_img[it]) + (int64_t)P.ntiles * tile_bytes);
+    const uint8_t *img_next = it + 1 < nitems ? reinterpret_cast<const uint8_t *>(item_img[it + 1]) + (int64_t)T0 * tile_bytes : nullptr;
 
     if (o != cur_obj) {
       // ---- new object: deliver the previous one, then p (scaled to [2^9, 2^10)) as B fragments in registers ----
@@ -390,36 +417,45 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gn_apply_cl_kernel(const GaArgs
       }
     }
     CL_T(2);
-    // stencil rows of the own pixels: issued now (the P1 registers are free), consumed two barriers later.
-    // Two threads per pixel (taps 0-4 | taps 5-8 and t), up to 4 rounds of 128 pixels.
-    constexpr int VR = (CL_MAXSLOT * GC_TILE) / (CL_THREADS / 2);
-    float st[VR][5];
-    const int half = tid & 1;
+    cluster_arrive();                                    // #1: this CTA's tap maps are written
+    // stencil rows of the own pixels, one thread per pixel (two rounds): issued behind the arrive — a release fence would
+    // wait for them — and consumed two barriers later
+    constexpr int VR = (CL_MAXSLOT * GC_TILE) / CL_THREADS;
+    float st[VR][10];
 #pragma unroll
     for (int r = 0; r < VR; ++r) {
-      const int lp = r * (CL_THREADS / 2) + (tid >> 1);
+      const int lp = r * CL_THREADS + tid;
       const int q = a0 + lp;
       if (lp < own_px) {
-        const float *src = sten + (int64_t)(q >> 8) * (10 * GC_CHUNK_PX) + (q & (GC_CHUNK_PX - 1)) + half * 5 * GC_CHUNK_PX;
+        const float *src = sten + (int64_t)(q >> 8) * (10 * GC_CHUNK_PX) + (q & (GC_CHUNK_PX - 1));
 #pragma unroll
-        for (int t = 0; t < 5; ++t) st[r][t] = (t < 4 || !half || use_y) ? __ldg(src + t * GC_CHUNK_PX) : 0.f;
+        for (int t = 0; t < 10; ++t) st[r][t] = (t < 9 || use_y) ? __ldg(src + t * GC_CHUNK_PX) : 0.f;
       }
     }
     CL_T(3);
-    cluster_sync_all();                                  // #1: every CTA's tap maps are written
+    cluster_wait();
     CL_T(4);
 
     // halo of the tap maps: the lag pixels before / after the own range live in the neighbours
+    // (thread = (pixel k of the halo, tap parity), no divisions; all remote loads of a thread are independent)
     {
-      const int nh = 9 * lag;
-      for (int e = tid; e < 2 * nh; e += CL_THREADS) {
-        const int side = e >= nh, r = side ? e - nh : e;
-        const int t = r / lag, k = r - t * lag;
-        if (!side) {
-          if (rank > 0)                                  // pixels a0 - lag + k of the left neighbour = its local left_px - lag + k
-            ybuf[t * YS + CL_HALO - lag + k] = dsmem_ld(dsmem_addr(ybuf_s + (uint32_t)(t * YS + CL_HALO + left_px - lag + k) * 4u, rank - 1));
-        } else if (rank + 1 < CS) {
-          ybuf[t * YS + CL_HALO + GC_TILE * ntl + k] = dsmem_ld(dsmem_addr(ybuf_s + (uint32_t)(t * YS + CL_HALO + k) * 4u, rank + 1));
+      const int k = tid & 127, t0 = tid >> 7;
+      if (k < lag) {
+        if (rank > 0) {
+          const uint32_t src = dsmem_addr(ybuf_s + (uint32_t)(CL_HALO + left_px - lag + k) * 4u, rank - 1);
+          float hv[5];
+#pragma unroll
+          for (int u = 0; u < 5; ++u) { const int t = t0 + 2 * u; hv[u] = t < 9 ? dsmem_ld(src + (uint32_t)(t * YS) * 4u) : 0.f; }
+#pragma unroll
+          for (int u = 0; u < 5; ++u) { const int t = t0 + 2 * u; if (t < 9) ybuf[t * YS + CL_HALO - lag + k] = hv[u]; }
+        }
+        if (rank + 1 < CS) {
+          const uint32_t src = dsmem_addr(ybuf_s + (uint32_t)(CL_HALO + k) * 4u, rank + 1);
+          float hv[5];
+#pragma unroll
+          for (int u = 0; u < 5; ++u) { const int t = t0 + 2 * u; hv[u] = t < 9 ? dsmem_ld(src + (uint32_t)(t * YS) * 4u) : 0.f; }
+#pragma unroll
+          for (int u = 0; u < 5; ++u) { const int t = t0 + 2 * u; if (t < 9) ybuf[t * YS + CL_HALO + npx + k] = hv[u]; }
         }
       }
     }
@@ -427,28 +463,24 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gn_apply_cl_kernel(const GaArgs
     CL_T(5);
     // ---------------- scores of the own pixels ----------------
     for (int lp = tid; lp < own_px; lp += CL_THREADS) {
-      const int q = a0 + lp;
-      const int y = (int)__umulhi((unsigned)q, magic), x = q - y * w;
+      const unsigned m = maskv[lp];
+      const float *yp = ybuf + CL_HALO + lp;
       float sum = 0.f;
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         const int dy = t / 3 - 1, dx = t % 3 - 1;
-        const bool ok = (unsigned)(y + dy) < (unsigned)h && (unsigned)(x + dx) < (unsigned)w;
-        const float yv = ybuf[t * YS + CL_HALO + lp + dy * w + dx];
-        sum += ok ? yv : 0.f;
+        const float yv = yp[t * YS + dy * w + dx];
+        sum += (m >> t) & 1u ? yv : 0.f;
       }
       sext[CL_HALO + lp] = sum;
     }
     CL_T(6);
     cluster_sync_all();                                  // #2
     CL_T(7);
-    for (int e = tid; e < 2 * lag; e += CL_THREADS) {
-      const int side = e >= lag, k = side ? e - lag : e;
-      if (!side) {
-        if (rank > 0) sext[CL_HALO - lag + k] = dsmem_ld(dsmem_addr(sext_s + (uint32_t)(CL_HALO + left_px - lag + k) * 4u, rank - 1));
-      } else if (rank + 1 < CS) {
-        sext[CL_HALO + GC_TILE * ntl + k] = dsmem_ld(dsmem_addr(sext_s + (uint32_t)(CL_HALO + k) * 4u, rank + 1));
-      }
+    if (tid < lag) {
+      if (rank > 0) sext[CL_HALO - lag + tid] = dsmem_ld(dsmem_addr(sext_s + (uint32_t)(CL_HALO + left_px - lag + tid) * 4u, rank - 1));
+    } else if (tid >= 128 && tid - 128 < lag) {
+      if (rank + 1 < CS) sext[CL_HALO + npx + tid - 128] = dsmem_ld(dsmem_addr(sext_s + (uint32_t)(CL_HALO + tid - 128) * 4u, rank + 1));
     }
     __syncthreads();
     CL_T(8);
@@ -457,26 +489,20 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gn_apply_cl_kernel(const GaArgs
       unsigned vb = 0u;
 #pragma unroll
       for (int r = 0; r < VR; ++r) {
-        const int lp = r * (CL_THREADS / 2) + (tid >> 1);
-        const bool act = lp < own_px;
-        const int q = a0 + lp;
-        const int y = (int)__umulhi((unsigned)q, magic), x = q - y * w;
-        float av = 0.f;
+        const int lp = r * CL_THREADS + tid;
+        if (lp < own_px) {
+          const unsigned m = maskv[lp];
+          const float *sp = sext + CL_HALO + lp;
+          float av = 0.f;
 #pragma unroll
-        for (int u = 0; u < 5; ++u) {
-          const int t = half * 5 + u;
-          if (u < 4 || !half) {
+          for (int t = 0; t < 9; ++t) {
             const int dy = t / 3 - 1, dx = t % 3 - 1;
-            const bool ok = act && (unsigned)(y + dy) < (unsigned)h && (unsigned)(x + dx) < (unsigned)w;
-            const float sv = sext[ok ? CL_HALO + lp + dy * w + dx : 0];
-            av = fmaf(ok ? st[r][u] : 0.f, ok ? sv : 0.f, av);
+            const float sv = sp[dy * w + dx];
+            av = fmaf(st[r][t], (m >> t) & 1u ? sv : 0.f, av);
           }
-        }
-        if (half && use_y && act) av -= st[r][4];
-        av += __shfl_xor_sync(0xffffffffu, av, 1);
-        av *= wgt;
-        if (act) {
-          if (!half) vext[CL_HALO + lp] = av;
+          if (use_y) av -= st[r][9];
+          av *= wgt;
+          vext[CL_HALO + lp] = av;
           vb = max(vb, __float_as_uint(fabsf(av)));
         }
       }
@@ -486,78 +512,78 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gn_apply_cl_kernel(const GaArgs
     CL_T(9);
     cluster_sync_all();                                  // #3
     CL_T(10);
-    for (int e = tid; e < 2 * lag; e += CL_THREADS) {
-      const int side = e >= lag, k = side ? e - lag : e;
+    {
       float hv = 0.f;
       bool got = false;
-      if (!side) {
-        if (rank > 0) { hv = dsmem_ld(dsmem_addr(vext_s + (uint32_t)(CL_HALO + left_px - lag + k) * 4u, rank - 1)); vext[CL_HALO - lag + k] = hv; got = true; }
-      } else if (rank + 1 < CS) {
-        hv = dsmem_ld(dsmem_addr(vext_s + (uint32_t)(CL_HALO + k) * 4u, rank + 1)); vext[CL_HALO + GC_TILE * ntl + k] = hv; got = true;
+      if (tid < lag) {
+        if (rank > 0) { hv = dsmem_ld(dsmem_addr(vext_s + (uint32_t)(CL_HALO + left_px - lag + tid) * 4u, rank - 1)); vext[CL_HALO - lag + tid] = hv; got = true; }
+      } else if (tid >= 128 && tid - 128 < lag) {
+        if (rank + 1 < CS) { hv = dsmem_ld(dsmem_addr(vext_s + (uint32_t)(CL_HALO + tid - 128) * 4u, rank + 1)); vext[CL_HALO + npx + tid - 128] = hv; got = true; }
       }
       if (got) atomicMax(vmaxbits, __float_as_uint(fabsf(hv)));      // the operand scale covers the halo values too
     }
     __syncthreads();
     CL_T(11);
 
+    // ---------------- the shifted-v operand of P3, built once for all warps: fp16 hi / lo rows [tap][pixel] ----------------
+    const float vscale = scale_from_bits(*vmaxbits);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      // B[k = pixel][n = tap t] = v(y - dy, x - dx) = v[q - off(t)], inside the map iff tap 8 - t of q is; two pixels per store
+      const int dy = t / 3 - 1, dx = t % 3 - 1;
+      for (int pr = tid; pr < (npx >> 1); pr += CL_THREADS) {
+        const int lp = pr * 2;
+        const unsigned m0 = maskv[lp], m1 = maskv[lp + 1];
+        const float *vp = vext + CL_HALO + lp - (dy * w + dx);
+        const float x0 = ((m0 >> (8 - t)) & 1u) ? vp[0] * vscale : 0.f, x1 = ((m1 >> (8 - t)) & 1u) ? vp[1] * vscale : 0.f;
+        uint32_t hh, ll;
+        split2(x0, x1, hh, ll);
+        if (t < 8) {
+          *reinterpret_cast<uint32_t *>(vhi + t * VP + lp) = hh;
+          *reinterpret_cast<uint32_t *>(vlo + t * VP + lp) = ll;
+        } else {
+          *reinterpret_cast<uint32_t *>(v8h + lp) = hh;
+          *reinterpret_cast<uint32_t *>(v8l + lp) = ll;
+        }
+      }
+    }
+    __syncthreads();
+
     // ---------------- P3: k-steps of 16 pixels, round-robin over the warps; consumed tiles are refilled ----------------
     {
-      const float vscale = scale_from_bits(*vmaxbits);
       float acc[KS][4], acc8[KS][4];
 #pragma unroll
       for (int m = 0; m < KS; ++m) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) { acc[m][u] = 0.f; acc8[m][u] = 0.f; }
       }
+      // ldmatrix row addresses of the B operand: x4 = (hi | k 0-7), (hi | k 8-15), (lo | k 0-7), (lo | k 8-15), row = tap
+      const uint32_t bsrc = smem_u32((lid < 2 ? vhi : vlo) + lr * VP) + (uint32_t)(lid & 1) * 16u;
+      // x2 for tap 8: row 0 = hi, row 1 = lo, rows 2-7 = zeros
+      const uint32_t b8src = lr == 0 ? smem_u32(v8h) + (uint32_t)(lid & 1) * 16u
+                           : lr == 1 ? smem_u32(v8l) + (uint32_t)(lid & 1) * 16u : smem_u32(zero16);
+      const uint32_t b8step = lr < 2 ? 32u : 0u;
       for (int ks = wp; ks < 4 * ntl; ks += CL_WARPS) {
         const int j = ks >> 2, ch0 = (ks & 3) * 2;
         const uint32_t t3 = ring + j * tile_bytes + (uint32_t)((lid & 1) * 8 + lr) * 128u + (uint32_t)(((ch0 + (lid >> 1)) ^ lr) << 4);
-        uint32_t ah[KS][4], al[KS][4];
+        uint32_t ah[KS][4], al[KS][4], bb[4], b8[2];
+        ldsm_x4(bsrc + (uint32_t)ks * 32u, bb);
+        ldsm_x2(b8src + (uint32_t)ks * b8step, b8[0], b8[1]);
 #pragma unroll
         for (int m = 0; m < KS; ++m) {
           ldsm_x4(t3 + m * 2048, ah[m]);
           ldsm_x4(t3 + m * 2048 + plane, al[m]);
         }
-        float vv[4], v8[4];
-        {
-          const int lp0 = ks * 16 + k0;
-          const int q0 = a0 + lp0;
-          const int py = (int)__umulhi((unsigned)q0, magic), px = q0 - py * w;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {                    // k = k0, k0 + 1, k0 + 8, k0 + 9
-            const int dq = (e & 1) + (e >> 1) * 8;
-            const int q = q0 + dq;
-            int yy = py, xx = px + dq;
-            if (xx >= w) { xx -= w; ++yy; }
-            if (xx >= w) { xx -= w; ++yy; }
-            const bool in = q < hw;
-            const bool ok = in && (unsigned)(yy - tdy) < (unsigned)h && (unsigned)(xx - tdx) < (unsigned)w;
-            const bool ok8 = in && g < 2 && yy >= 1 && xx >= 1;                  // tap 8: dy = dx = +1
-            const float b0 = vext[ok ? CL_HALO + lp0 + dq - toff : 0], b8v = vext[ok8 ? CL_HALO + lp0 + dq - w - 1 : 0];
-            vv[e] = ok ? b0 * vscale : 0.f;
-            v8[e] = ok8 ? b8v * vscale : 0.f;
-          }
-        }
-        uint32_t bh[2], bl[2], b8[2];
-        split2(vv[0], vv[1], bh[0], bl[0]);
-        split2(vv[2], vv[3], bh[1], bl[1]);
-        {
-          uint32_t h0, l0, h1, l1;
-          split2(v8[0], v8[1], h0, l0);
-          split2(v8[2], v8[3], h1, l1);
-          b8[0] = g == 0 ? h0 : (g == 1 ? l0 : 0u);
-          b8[1] = g == 0 ? h1 : (g == 1 ? l1 : 0u);
-        }
-#pragma unroll
-        for (int m = 0; m < KS; ++m) hmma(acc[m], ah[m], bh[0], bh[1]);
+        for (int m = 0; m < KS; ++m) hmma(acc[m], ah[m], bb[0], bb[1]);
 #pragma unroll
         for (int m = 0; m < KS; ++m) hmma(acc8[m], ah[m], b8[0], b8[1]);
 #pragma unroll
-        for (int m = 0; m < KS; ++m) hmma(acc[m], ah[m], bl[0], bl[1]);
+        for (int m = 0; m < KS; ++m) hmma(acc[m], ah[m], bb[2], bb[3]);
 #pragma unroll
         for (int m = 0; m < KS; ++m) hmma(acc8[m], al[m], b8[0], b8[1]);
 #pragma unroll
-        for (int m = 0; m < KS; ++m) hmma(acc[m], al[m], bh[0], bh[1]);
+        for (int m = 0; m < KS; ++m) hmma(acc[m], al[m], bb[0], bb[1]);
         // this warp is done with tile j (its ldmatrix loads have returned: the products above consumed them); the warp that
         // completes the tile's count refills the slot with the same tile of the cluster's next sample
         __syncwarp();
@@ -581,7 +607,8 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gn_apply_cl_kernel(const GaArgs
       }
     }
     CL_T(12);
-    // a tile whose last arrival did not see the completed phase (another warp's arrive raced its test) is refilled here
+    // a tile whose last arrival did not see the completed phase (another warp's arrive raced its test) is refilled here;
+    // the barrier also keeps the next sample's tap maps from overwriting the operand rows other warps still read
     __syncthreads();
     CL_T(13);
     if (wp == 0 && img_next != nullptr) {
@@ -602,7 +629,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gn_apply_cl_kernel(const GaArgs
 #ifdef GM_TIMING
   if (tid == 0 && cid == 0 && rank < 2)
     printf("cl timeline rank %d (clocks, %d items): top %lld | setup %lld | P1 %lld | sten-issue %lld | csync1 %lld | haloY %lld | scores %lld | "
-           "csync2 %lld | haloS %lld | resid %lld | csync3 %lld | haloV %lld | P3 %lld | bar %lld | tail %lld | flush %lld\n", rank, nitems,
+           "csync2 %lld | haloS %lld | resid %lld | csync3 %lld | haloV %lld | Vbuild+P3 %lld | bar %lld | tail %lld | flush %lld\n", rank, nitems,
            tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], tacc[5], tacc[6], tacc[7], tacc[8], tacc[9], tacc[10], tacc[11], tacc[12], tacc[13],
            tacc[14], tacc[15]);
 #endif
@@ -620,7 +647,9 @@ static int cl_cluster_size(int ntiles) {
 static size_t cl_smem(int c, int nslot) {
   const size_t ys = 2 * CL_HALO + GC_TILE * nslot + 4, ext = 2 * CL_HALO + GC_TILE * nslot;
   const size_t ycap = 9 * ys > (size_t)5 * c * 9 ? 9 * ys : (size_t)5 * c * 9;
-  return 1024 + (size_t)nslot * 2 * c * 128 + (ycap + 2 * ext + 10 + CL_MAXSLOT + CL_MAXITEMS) * 4 + 8 + 16 * CL_MAXSLOT;
+  // ring | zero chunk, barriers, image pointers | tap maps | s, v | red, vmax, issued | item weights, objects | masks
+  return 1024 + (size_t)nslot * 2 * c * 128 + 16 + 16 * CL_MAXSLOT + 8 * CL_MAXITEMS +
+         (ycap + 2 * ext + 10 + CL_MAXSLOT + 2 * CL_MAXITEMS) * 4 + 2 * GC_TILE * CL_MAXSLOT + 16;
 }
 
 bool gn_apply_cl_supported(int c, int h, int w) {
