@@ -67,6 +67,13 @@ __device__ __forceinline__ float dsmem_ld(uint32_t caddr) {
 __device__ __forceinline__ void dsmem_st(uint32_t caddr, float v) {
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(caddr), "f"(v) : "memory");
 }
+// asynchronous store into a peer CTA's shared memory that signals the peer's mbarrier (complete_tx) — no fences, no
+// cluster barrier: the halo exchange between neighbouring CTAs of a cluster is a push
+__device__ __forceinline__ void dsmem_push(uint32_t caddr, float v, uint32_t cbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(caddr), "r"(__float_as_uint(v)),
+               "r"(cbar)
+               : "memory");
+}
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
   uint32_t done;
   asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
@@ -154,9 +161,14 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gn_apply_cl_kernel(const GaArgs
   uint8_t *fix = gen + (size_t)P.nslot * tile_bytes;
   uint4 *zero16 = reinterpret_cast<uint4 *>(fix);                           // 16 zero bytes (ldmatrix rows of the unused taps)
   const uint32_t bars = smem_u32(fix + 16);
-  const uint32_t bar_full = bars, bar_cons = bars + 8 * CL_MAXSLOT;
-  unsigned long long *item_img = reinterpret_cast<unsigned long long *>(fix + 16 + 16 * CL_MAXSLOT);   // [CL_MAXITEMS]
-  float *ybuf = reinterpret_cast<float *>(fix + 16 + 16 * CL_MAXSLOT + 8 * CL_MAXITEMS);   // [9][YS]; later the shifted-v operand
+  const uint32_t bar_full = bars, bar_cons = bars + 8 * CL_MAXSLOT, bar_halo = bars + 16 * CL_MAXSLOT;   // + Y, s, v halo barriers
+  unsigned long long *item_img = reinterpret_cast<unsigned long long *>(fix + 16 + 16 * CL_MAXSLOT + 32);   // [CL_MAXITEMS]
+  // shifted-v operand of P3: fp16 [18 rows: taps 0-7 hi | taps 0-7 lo | tap 8 hi | tap 8 lo][VP] (also the p staging area)
+  const int VP = GC_TILE * ntl + 8;                                      // row pitch in halves (pitch bytes == 16 mod 128)
+  const int VCAP = max(18 * (GC_TILE * P.nslot + 8) * 2, n * 4);        // bytes
+  __half *vhi = reinterpret_cast<__half *>(fix + 16 + 16 * CL_MAXSLOT + 32 + 8 * CL_MAXITEMS);
+  __half *vlo = vhi + 8 * VP, *v8h = vlo + 8 * VP, *v8l = v8h + VP;
+  float *ybuf = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(vhi) + VCAP);   // [9][YS] tap maps
   float *sext = ybuf + YCAP;
   float *vext = sext + EXT;
   float *red = vext + EXT;                                                   // 8 floats
@@ -166,9 +178,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gn_apply_cl_kernel(const GaArgs
   int *item_obj = reinterpret_cast<int *>(item_wgt + CL_MAXITEMS);          // [CL_MAXITEMS]
   uint16_t *maskv = reinterpret_cast<uint16_t *>(item_obj + CL_MAXITEMS);  // [64 * CL_MAXSLOT] tap validity of the own pixels
   const uint32_t ybuf_s = smem_u32(ybuf), sext_s = smem_u32(sext), vext_s = smem_u32(vext);
-  // shifted-v operand of P3 (aliases the tap maps, dead by then): fp16 [n][pixel] rows, pixels contiguous
-  const int VP = npx + 8;                                                // row pitch in halves (pitch bytes == 16 mod 128)
-  __half *vhi = reinterpret_cast<__half *>(ybuf), *vlo = vhi + 8 * VP, *v8h = vlo + 8 * VP, *v8l = v8h + VP;
+  const int nnb = (rank > 0 ? 1 : 0) + (rank + 1 < CS ? 1 : 0);         // neighbours that push halos into this CTA
 
   // ---- the cluster's range of the work list; everything an item needs from global memory is fetched up front ----
   // (fewer samples than clusters: the first U clusters take one each, so the clusters that hold rows of an object are
@@ -204,6 +214,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gn_apply_cl_kernel(const GaArgs
   }
   if (tid == 0) {
     for (int s = 0; s < CL_MAXSLOT; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_cons + 8 * s, 4); issued[s] = 0; }
+    for (int s = 0; s < 3; ++s) mbar_init(bar_halo + 8 * s, 1);
     *zero16 = make_uint4(0u, 0u, 0u, 0u);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -319,9 +330,14 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gn_apply_cl_kernel(const GaArgs
         __syncthreads();
       }
     }
+    if (rank == 0) {
+      float *row = P.rows + ((int64_t)o * P.rowcap + cid) * n;
+      for (int k = tid; k < n; k += CL_THREADS) row[k] = outv[k];
+    }
+    // the staging area is the tap-map area, whose halo columns the neighbours push into as soon as they run the next
+    // sample's P1: nobody proceeds before rank 0 has read its staging rows
+    cluster_sync_all();
     if (rank != 0) return;
-    float *row = P.rows + ((int64_t)o * P.rowcap + cid) * n;
-    for (int k = tid; k < n; k += CL_THREADS) row[k] = outv[k];
     const int f0 = P.list.hdr[1 + o], f1 = P.list.hdr[2 + o];
     const int c_lo = cl_cluster_of(f0, U, NC), c_hi = cl_cluster_of(f1 - 1, U, NC);
     finish_object(o, c_lo, c_hi - c_lo + 1, true);
@@ -354,7 +370,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gn_apply_cl_kernel(const GaArgs
 #pragma unroll
       for (int k = 0; k < PV; ++k) pv[k] = tid + k * CL_THREADS < n ? pvec[tid + k * CL_THREADS] : 0.f;
       float amax = 0.f;
-      float *pst = ybuf;                                 // staging in the tap-map area (free between samples)
+      float *pst = reinterpret_cast<float *>(vhi);       // staging in the operand area (free between samples)
 #pragma unroll
       for (int k = 0; k < PV; ++k) {
         if (tid + k * CL_THREADS < n) pst[tid + k * CL_THREADS] = pv[k];
@@ -380,7 +396,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gn_apply_cl_kernel(const GaArgs
           pb8[ks][u] = g == 0 ? h8 : (g == 1 ? l8 : 0u);
         }
       }
-      __syncthreads();                                   // staging consumed before the tap maps are written again
+      __syncthreads();                                   // staging consumed before the operand rows are written again
     }
     if (tid == 0) *vmaxbits = 0u;
     CL_T(1);
@@ -417,9 +433,26 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gn_apply_cl_kernel(const GaArgs
       }
     }
     CL_T(2);
-    cluster_arrive();                                    // #1: this CTA's tap maps are written
-    // stencil rows of the own pixels, one thread per pixel (two rounds): issued behind the arrive — a release fence would
-    // wait for them — and consumed two barriers later
+    __syncthreads();                                     // this CTA's tap maps are written
+    // halo exchange #1: push the first / last lag pixels of the own tap maps into the neighbours' halo columns
+    // (thread = (pixel k of the halo, tap parity); asynchronous stores that complete on the receiver's barrier)
+    if (nnb) {
+      if (tid == 0) mbar_expect_tx(bar_halo, (uint32_t)(nnb * 9 * lag * 4));
+      const int k = tid & 127, t0 = tid >> 7;
+      if (k < lag) {
+        if (rank > 0) {
+          const uint32_t dst = dsmem_addr(ybuf_s + (uint32_t)(CL_HALO + left_px + k) * 4u, rank - 1), bar = dsmem_addr(bar_halo, rank - 1);
+#pragma unroll
+          for (int u = 0; u < 5; ++u) { const int t = t0 + 2 * u; if (t < 9) dsmem_push(dst + (uint32_t)(t * YS) * 4u, ybuf[t * YS + CL_HALO + k], bar); }
+        }
+        if (rank + 1 < CS) {
+          const uint32_t dst = dsmem_addr(ybuf_s + (uint32_t)(CL_HALO - lag + k) * 4u, rank + 1), bar = dsmem_addr(bar_halo, rank + 1);
+#pragma unroll
+          for (int u = 0; u < 5; ++u) { const int t = t0 + 2 * u; if (t < 9) dsmem_push(dst + (uint32_t)(t * YS) * 4u, ybuf[t * YS + CL_HALO + npx - lag + k], bar); }
+        }
+      }
+    }
+    // stencil rows of the own pixels, one thread per pixel (two rounds): issued now, consumed after the score phase
     constexpr int VR = (CL_MAXSLOT * GC_TILE) / CL_THREADS;
     float st[VR][10];
 #pragma unroll
@@ -433,32 +466,8 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gn_apply_cl_kernel(const GaArgs
       }
     }
     CL_T(3);
-    cluster_wait();
+    if (nnb) mbar_wait(bar_halo, par);                   // the neighbours' tap values have landed in the halo columns
     CL_T(4);
-
-    // halo of the tap maps: the lag pixels before / after the own range live in the neighbours
-    // (thread = (pixel k of the halo, tap parity), no divisions; all remote loads of a thread are independent)
-    {
-      const int k = tid & 127, t0 = tid >> 7;
-      if (k < lag) {
-        if (rank > 0) {
-          const uint32_t src = dsmem_addr(ybuf_s + (uint32_t)(CL_HALO + left_px - lag + k) * 4u, rank - 1);
-          float hv[5];
-#pragma unroll
-          for (int u = 0; u < 5; ++u) { const int t = t0 + 2 * u; hv[u] = t < 9 ? dsmem_ld(src + (uint32_t)(t * YS) * 4u) : 0.f; }
-#pragma unroll
-          for (int u = 0; u < 5; ++u) { const int t = t0 + 2 * u; if (t < 9) ybuf[t * YS + CL_HALO - lag + k] = hv[u]; }
-        }
-        if (rank + 1 < CS) {
-          const uint32_t src = dsmem_addr(ybuf_s + (uint32_t)(CL_HALO + k) * 4u, rank + 1);
-          float hv[5];
-#pragma unroll
-          for (int u = 0; u < 5; ++u) { const int t = t0 + 2 * u; hv[u] = t < 9 ? dsmem_ld(src + (uint32_t)(t * YS) * 4u) : 0.f; }
-#pragma unroll
-          for (int u = 0; u < 5; ++u) { const int t = t0 + 2 * u; if (t < 9) ybuf[t * YS + CL_HALO + npx + k] = hv[u]; }
-        }
-      }
-    }
     __syncthreads();
     CL_T(5);
     // ---------------- scores of the own pixels ----------------
@@ -475,14 +484,17 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gn_apply_cl_kernel(const GaArgs
       sext[CL_HALO + lp] = sum;
     }
     CL_T(6);
-    cluster_sync_all();                                  // #2
-    CL_T(7);
-    if (tid < lag) {
-      if (rank > 0) sext[CL_HALO - lag + tid] = dsmem_ld(dsmem_addr(sext_s + (uint32_t)(CL_HALO + left_px - lag + tid) * 4u, rank - 1));
-    } else if (tid >= 128 && tid - 128 < lag) {
-      if (rank + 1 < CS) sext[CL_HALO + npx + tid - 128] = dsmem_ld(dsmem_addr(sext_s + (uint32_t)(CL_HALO + tid - 128) * 4u, rank + 1));
-    }
     __syncthreads();
+    CL_T(7);
+    if (nnb) {                                           // halo exchange #2: scores
+      if (tid == 0) mbar_expect_tx(bar_halo + 8, (uint32_t)(nnb * lag * 4));
+      if (tid < lag) {
+        if (rank > 0) dsmem_push(dsmem_addr(sext_s + (uint32_t)(CL_HALO + left_px + tid) * 4u, rank - 1), sext[CL_HALO + tid], dsmem_addr(bar_halo + 8, rank - 1));
+      } else if (tid >= 128 && tid - 128 < lag) {
+        if (rank + 1 < CS) dsmem_push(dsmem_addr(sext_s + (uint32_t)(CL_HALO - lag + tid - 128) * 4u, rank + 1), sext[CL_HALO + npx - lag + tid - 128], dsmem_addr(bar_halo + 8, rank + 1));
+      }
+      mbar_wait(bar_halo + 8, par);
+    }
     CL_T(8);
     // ---------------- residual of the own pixels, maximum of |v| ----------------
     {
@@ -510,17 +522,22 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gn_apply_cl_kernel(const GaArgs
       if (lane == 0 && vb) atomicMax(vmaxbits, vb);
     }
     CL_T(9);
-    cluster_sync_all();                                  // #3
+    __syncthreads();
     CL_T(10);
-    {
-      float hv = 0.f;
-      bool got = false;
+    if (nnb) {                                           // halo exchange #3: residual
+      if (tid == 0) mbar_expect_tx(bar_halo + 16, (uint32_t)(nnb * lag * 4));
       if (tid < lag) {
-        if (rank > 0) { hv = dsmem_ld(dsmem_addr(vext_s + (uint32_t)(CL_HALO + left_px - lag + tid) * 4u, rank - 1)); vext[CL_HALO - lag + tid] = hv; got = true; }
+        if (rank > 0) dsmem_push(dsmem_addr(vext_s + (uint32_t)(CL_HALO + left_px + tid) * 4u, rank - 1), vext[CL_HALO + tid], dsmem_addr(bar_halo + 16, rank - 1));
       } else if (tid >= 128 && tid - 128 < lag) {
-        if (rank + 1 < CS) { hv = dsmem_ld(dsmem_addr(vext_s + (uint32_t)(CL_HALO + tid - 128) * 4u, rank + 1)); vext[CL_HALO + npx + tid - 128] = hv; got = true; }
+        if (rank + 1 < CS) dsmem_push(dsmem_addr(vext_s + (uint32_t)(CL_HALO - lag + tid - 128) * 4u, rank + 1), vext[CL_HALO + npx - lag + tid - 128], dsmem_addr(bar_halo + 16, rank + 1));
       }
-      if (got) atomicMax(vmaxbits, __float_as_uint(fabsf(hv)));      // the operand scale covers the halo values too
+      mbar_wait(bar_halo + 16, par);
+      // the operand scale covers the halo values too
+      float hv = 0.f;
+      if (tid < lag) { if (rank > 0) hv = vext[CL_HALO - lag + tid]; }
+      else if (tid >= 128 && tid - 128 < lag) { if (rank + 1 < CS) hv = vext[CL_HALO + npx + tid - 128]; }
+      const unsigned hb = __reduce_max_sync(0xffffffffu, __float_as_uint(fabsf(hv)));
+      if (lane == 0 && hb) atomicMax(vmaxbits, hb);
     }
     __syncthreads();
     CL_T(11);
@@ -637,29 +654,30 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gn_apply_cl_kernel(const GaArgs
 }
 
 // -------------------------------------------------------------------------------------------------------------------
-static int cl_cluster_size(int ntiles) {
-  for (int cs = 1; cs <= 8; cs *= 2) {
-    const int per = (ntiles + cs - 1) / cs;
-    if (per <= CL_MAXSLOT && (cs == 1 || ntiles / cs >= 3)) return cs;
-  }
-  return 0;
-}
 static size_t cl_smem(int c, int nslot) {
   const size_t ys = 2 * CL_HALO + GC_TILE * nslot + 4, ext = 2 * CL_HALO + GC_TILE * nslot;
   const size_t ycap = 9 * ys > (size_t)5 * c * 9 ? 9 * ys : (size_t)5 * c * 9;
-  // ring | zero chunk, barriers, image pointers | tap maps | s, v | red, vmax, issued | item weights, objects | masks
-  return 1024 + (size_t)nslot * 2 * c * 128 + 16 + 16 * CL_MAXSLOT + 8 * CL_MAXITEMS +
+  const size_t vcap = (size_t)18 * (GC_TILE * nslot + 8) * 2 > (size_t)c * 9 * 4 ? (size_t)18 * (GC_TILE * nslot + 8) * 2 : (size_t)c * 9 * 4;
+  // ring | zero chunk, barriers, image pointers | P3 operand | tap maps | s, v | red, vmax, issued | item weights, objects | masks
+  return 1024 + (size_t)nslot * 2 * c * 128 + 16 + 16 * CL_MAXSLOT + 32 + 8 * CL_MAXITEMS + vcap +
          (ycap + 2 * ext + 10 + CL_MAXSLOT + 2 * CL_MAXITEMS) * 4 + 2 * GC_TILE * CL_MAXSLOT + 16;
+}
+// smallest cluster whose CTAs can hold their share of a sample (<= 8 tiles, shared memory) and whose ranges cover the
+// neighbours' halos; 16 is the hardware maximum (non-portable size, opted into at launch)
+static int cl_cluster_size(int c, int ntiles, int w) {
+  for (int cs = 1; cs <= 16; cs *= 2) {
+    const int per = (ntiles + cs - 1) / cs;
+    if (per > CL_MAXSLOT || cl_smem(c, per) > 227 * 1024) continue;
+    if (cs > 1 && ((ntiles / cs) < 1 || (ntiles / cs) * GC_TILE < w + 1)) continue;
+    return cs;
+  }
+  return 0;
 }
 
 bool gn_apply_cl_supported(int c, int h, int w) {
   const int hw = h * w, ntiles = gc_ntiles(hw);
-  const int cs = cl_cluster_size(ntiles);
-  if (c != CL_C || w < 8 || w + 1 > CL_HALO || hw >= 65536 || cs == 0) return false;
-  const int nslot = (ntiles + cs - 1) / cs;
-  // a CTA's range must cover its neighbours' halos
-  if (cs > 1 && (ntiles / cs) * GC_TILE < w + 1) return false;
-  return cl_smem(c, nslot) <= 227 * 1024;
+  if (c != CL_C || w < 8 || w + 1 > CL_HALO || hw >= 65536) return false;
+  return cl_cluster_size(c, ntiles, w) != 0;
 }
 
 int64_t gn_apply_cl_workspace(int n_obj, int cap, int c) {
@@ -675,7 +693,7 @@ struct ClPlan {
 static int cl_plan(const GaArgs &a, float *ws, ClPlan &plan) {
   const int hw = a.h * a.w, n = a.c * 9;
   ClParams &P = plan.P;
-  P.ntiles = gc_ntiles(hw); P.tile_bytes = 2 * a.c * 128; P.cs = cl_cluster_size(P.ntiles);
+  P.ntiles = gc_ntiles(hw); P.tile_bytes = 2 * a.c * 128; P.cs = cl_cluster_size(a.c, P.ntiles, a.w);
   P.nslot = (P.ntiles + P.cs - 1) / P.cs; P.image_bytes = gc_sample_bytes(a.c, hw); P.rowcap = 160;
   plan.smem = cl_smem(a.c, P.nslot);
   P.rows = ws;
@@ -683,10 +701,11 @@ static int cl_plan(const GaArgs &a, float *ws, ClPlan &plan) {
   P.list.hdr = P.tickets + a.n_obj;
   P.list.items = reinterpret_cast<uint32_t *>(P.list.hdr + 2 + a.n_obj);
   // persistent clusters: as many as the device can hold at once for this cluster size / shared-memory footprint
-  static int cached_nc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  static size_t cached_smem[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  static int cached_nc[17] = {0};
+  static size_t cached_smem[17] = {0};
   if (cached_nc[P.cs] == 0 || cached_smem[P.cs] != plan.smem) {
     cudaError_t e = cudaFuncSetAttribute(gn_apply_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+    if (e == cudaSuccess && P.cs > 8) e = cudaFuncSetAttribute(gn_apply_cl_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) { set_error("gn_apply_cl: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return FRTM_ELAUNCH; }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(P.cs * 64); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = plan.smem;

@@ -190,36 +190,17 @@ __device__ __forceinline__ void gm_sample(const GaArgs &a, const GcParams &P) {
   long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
 #endif
   int s_hi = 0, v_hi = 0;
-  float stn[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-  {   // stencil rows of step 0's residual pixels
-    const int s_hi0 = 0 >= nblocks - 1 ? hw : GM_BLK - lag;
-    const int v_hi0 = 0 >= nblocks - 1 ? hw : max(s_hi0 - lag, 0);
-    const int q1 = tid >> 1;
-    if (q1 < v_hi0) {
-      const float *src = sten + (int64_t)(q1 >> 8) * (10 * GC_CHUNK_PX) + (q1 & (GC_CHUNK_PX - 1)) + (tid & 1) * 5 * GC_CHUNK_PX;
-#pragma unroll
-      for (int t = 0; t < 5; ++t) stn[t] = (t < 4 || !(tid & 1) || use_y) ? __ldg(src + t * GC_CHUNK_PX) : 0.f;
-    }
-  }
   for (int b = 0; b < nblocks + 2; ++b) {
     const int s_lo = s_hi, v_lo = v_hi;
     s_hi = b >= nblocks - 1 ? hw : GM_BLK * (b + 1) - lag;
     v_hi = b >= nblocks - 1 ? hw : max(s_hi - lag, 0);
-    // stencil rows of the NEXT step's residual pixels (two threads per pixel: taps 0-4 | taps 5-8 and t): the loads have a
-    // whole step to arrive from HBM; this step's rows were fetched during the previous one
-    float st[5];
+    // stencil rows of this step's residual pixels: issued now, consumed after P1 and the score gather
+    float st[10];
+    const int qv = v_lo + tid;
+    if (qv < v_hi) {
+      const float *src = sten + (int64_t)(qv >> 8) * (10 * GC_CHUNK_PX) + (qv & (GC_CHUNK_PX - 1));
 #pragma unroll
-    for (int t = 0; t < 5; ++t) st[t] = stn[t];
-    {
-      const int b1 = b + 1;
-      const int s_hi1 = b1 >= nblocks - 1 ? hw : GM_BLK * (b1 + 1) - lag;
-      const int v_hi1 = b1 >= nblocks - 1 ? hw : max(s_hi1 - lag, 0);
-      const int q1 = v_hi + (tid >> 1);
-      if (b1 < nblocks + 2 && q1 < v_hi1) {
-        const float *src = sten + (int64_t)(q1 >> 8) * (10 * GC_CHUNK_PX) + (q1 & (GC_CHUNK_PX - 1)) + (tid & 1) * 5 * GC_CHUNK_PX;
-#pragma unroll
-        for (int t = 0; t < 5; ++t) stn[t] = (t < 4 || !(tid & 1) || use_y) ? __ldg(src + t * GC_CHUNK_PX) : 0.f;
-      }
+      for (int t = 0; t < 10; ++t) st[t] = (t < 9 || use_y) ? __ldg(src + t * GC_CHUNK_PX) : 0.f;
     }
 
     // ---------------- P1(b): five accumulator chains over the six channel k-steps ----------------
@@ -280,32 +261,26 @@ __device__ __forceinline__ void gm_sample(const GaArgs &a, const GcParams &P) {
     // ---------------- residual, and the running maximum of |v| (the scale of the P3 operand) ----------------
     {
       unsigned vb = 0u;
-      const int half = tid & 1;
-      for (int q0 = v_lo, round = 0; q0 < v_hi; q0 += GM_THREADS / 2, ++round) {     // CTA-uniform trip count
-        const int q = q0 + (tid >> 1);
-        const bool act = q < v_hi;
-        if (round && act) {                              // tail steps cover more than one round: load directly
-          const float *src = sten + (int64_t)(q >> 8) * (10 * GC_CHUNK_PX) + (q & (GC_CHUNK_PX - 1)) + half * 5 * GC_CHUNK_PX;
+      for (int q0 = v_lo, round = 0; q0 < v_hi; q0 += GM_THREADS, ++round) {      // CTA-uniform trip count
+        const int q = q0 + tid;
+        if (q < v_hi) {
+          if (round) {                                   // tail steps cover more than one round: load directly
+            const float *src = sten + (int64_t)(q >> 8) * (10 * GC_CHUNK_PX) + (q & (GC_CHUNK_PX - 1));
 #pragma unroll
-          for (int t = 0; t < 5; ++t) st[t] = (t < 4 || !half || use_y) ? __ldg(src + t * GC_CHUNK_PX) : 0.f;
-        }
-        const int y = (int)__umulhi((unsigned)q, magic), x = q - y * w;
-        float av = 0.f;
-#pragma unroll
-        for (int u = 0; u < 5; ++u) {
-          const int t = half * 5 + u;                    // taps 0-4 | 5-8 (u = 4 of the second half is the t row)
-          if (u < 4 || !half) {
-            const int dy = t / 3 - 1, dx = t % 3 - 1;
-            const bool ok = act && (unsigned)(y + dy) < (unsigned)h && (unsigned)(x + dx) < (unsigned)w;
-            const float sv = sring[(q + dy * w + dx) & (GM_RING - 1)];
-            av = fmaf(ok ? st[u] : 0.f, ok ? sv : 0.f, av);
+            for (int t = 0; t < 10; ++t) st[t] = (t < 9 || use_y) ? __ldg(src + t * GC_CHUNK_PX) : 0.f;
           }
-        }
-        if (half && use_y && act) av -= st[4];
-        av += __shfl_xor_sync(0xffffffffu, av, 1);       // the two halves of a pixel sit in neighbouring lanes
-        av *= wgt;
-        if (act) {
-          if (!half) vring[q & (GM_RING - 1)] = av;
+          const int y = (int)__umulhi((unsigned)q, magic), x = q - y * w;
+          float av = 0.f;
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            const int dy = t / 3 - 1, dx = t % 3 - 1;
+            const bool ok = (unsigned)(y + dy) < (unsigned)h && (unsigned)(x + dx) < (unsigned)w;
+            const float sv = sring[(q + dy * w + dx) & (GM_RING - 1)];
+            av = fmaf(st[t], ok ? sv : 0.f, av);
+          }
+          if (use_y) av -= st[9];
+          av *= wgt;
+          vring[q & (GM_RING - 1)] = av;
           vb = max(vb, __float_as_uint(fabsf(av)));
         }
       }

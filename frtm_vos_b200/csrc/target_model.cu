@@ -1086,7 +1086,7 @@ extern "C" int64_t frtm_gn_update_workspace(int cap, int c, int h, int w) {
 }
 
 extern "C" int64_t frtm_gn_operator_kind(int c, int h, int w) {
-  return gn_apply_cl_supported(c, h, w) ? 4 : gn_apply_mma_supported(c, h, w) ? 3 : (gn_apply_tc_supported(c, h, w) ? 2 : 1);
+  return gn_apply_mma_supported(c, h, w) ? 3 : (gn_apply_tc_supported(c, h, w) ? 2 : 1);
 }
 
 static int gn_update_impl(const float *samples, const __half *samples_split, const float *stencil, const float *uty,
@@ -1126,7 +1126,9 @@ static int gn_update_impl(const float *samples, const __half *samples_split, con
   // the cluster operator gives every cluster a contiguous range of the active samples (at most 96 per launch and cluster)
   const bool cl_ok = gn_apply_cl_supported(c, h, w) && (int64_t)n_obj * cap <= 16 * 96 && n_obj < 65536 && cap < 65536;
   FRTM_REQUIRE(operator_select != 4 || cl_ok, "gn_update: shape not supported by the cluster operator");
-  const bool use_cl = operator_select == 4 || (operator_select == 0 && have_image && cl_ok);
+  // (measured on B200, profiles/r02_gn_operator.md: the sliding-window kernel is the fastest of the three on the BASELINE
+  //  shapes, so it is what 0 resolves to; the cluster kernel runs only when asked for)
+  const bool use_cl = operator_select == 4;
   const bool use_mma = !use_cl && (operator_select == 3 || (operator_select == 0 && have_image && gn_apply_mma_supported(c, h, w)));
   const bool use_tc = use_cl || use_mma || operator_select == 2 || (operator_select == 0 && have_image && gn_apply_tc_supported(c, h, w));
   ga.n_obj = n_obj; ga.cap = cap; ga.c = c; ga.h = h; ga.w = w; ga.use_y = 1;

@@ -241,7 +241,7 @@ int frtm_gn_update(const float *samples, const void *samples_split, const float 
                    int min_px, int operator_select, float *workspace, int64_t workspace_bytes, void *stream);
 int64_t frtm_gn_update_workspace(int cap, int c, int h, int w);
 /* Which operator kernel operator_select = 0 resolves to for this shape when the operator images are given:
- * 4 = cluster, 3 = single-pass sliding window, 2 = two-pass tcgen05, 1 = CUDA cores. */
+ * 3 = single-pass sliding window, 2 = two-pass tcgen05, 1 = CUDA cores (the cluster kernel, 4, runs only when asked for). */
 int64_t frtm_gn_operator_kind(int c, int h, int w);
 /* The same update for n_obj objects in ONE set of launches (grid.y = object; the objects of a sequence update on the
  * same frames).  table: device int64[8][n_obj] of device pointers, rows = {samples, stencil, uty, weights, filt,

@@ -174,7 +174,7 @@ def test_operator_kernels_match_fp64_and_each_other(cap, M, c, h, w, n_cg):
     assert 1 in ran and 0 in ran
     if c == 96 and 8 <= w <= 84:
         assert 3 in ran and 4 in ran                           # the production shapes run the single-pass kernels
-    assert (4 in ran) == (L.gn_operator_kind(c, h, w) == 4)
+    assert L.gn_operator_kind(c, h, w) == (3 if 3 in ran else 2 if 2 in ran else 1)
 
 
 @pytest.mark.parametrize("cap,M,h,w,H,W,n_cg", [(80, 72, 30, 54, 480, 854, 10), (32, 32, 45, 80, 720, 1280, 10)])
