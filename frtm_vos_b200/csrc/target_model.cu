@@ -120,26 +120,6 @@ __global__ void reduce_rows_kernel(const float *__restrict__ partial, int rows, 
   out[i] = s;
 }
 
-// gx[n][pix][ch] = sum_tap f[ch][tap] v[n][pix - tap]      (adjoint of the correlation w.r.t. its input), NHWC out
-__global__ void corr3x3_grad_input_kernel(const float *__restrict__ v, const float *__restrict__ filt, int c, int h, int w,
-                                          float *__restrict__ out) {
-  extern __shared__ float fs[];
-  for (int i = threadIdx.x; i < c * 9; i += blockDim.x) fs[i] = filt[i];
-  __syncthreads();
-  const int n = blockIdx.y, hw = h * w;
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)hw * c) return;
-  const int ch = (int)(idx % c), pix = (int)(idx / c);
-  const int py = pix / w, px = pix - py * w;
-  const float *vn = v + (int64_t)n * hw;
-  float acc = 0.f;
-#pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    const int yy = py - (t / 3 - 1), xx = px - (t % 3 - 1);
-    if (yy >= 0 && yy < h && xx >= 0 && xx < w) acc = fmaf(fs[ch * 9 + t], vn[yy * w + xx], acc);
-  }
-  out[((int64_t)n * hw + pix) * c + ch] = acc;
-}
 
 // ---------------------------------------------------------------- fused J^T S J apply ----------------------------
 // One CTA per memory sample computes that sample's contribution to  g = X^T [ sw (S (X * p) - use_y t) ]  in a single
@@ -918,6 +898,20 @@ __global__ void transpose_pad_kernel(const float *src, int rows, int cols, float
   const int r = (int)(i / cols), c = (int)(i % cols);
   dst[(int64_t)c * ld + r] = src[i];
 }
+// dst[c][r] = src[r][c]   (rows x cols -> cols x rows), 32 x 32 tiles through shared memory
+__global__ void transpose_tiled_kernel(const float *__restrict__ src, int rows, int cols, float *__restrict__ dst) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (r < rows && c < cols) ? src[(int64_t)r * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) dst[(int64_t)c * rows + r] = tile[threadIdx.x][j];
+  }
+}
 __global__ void untranspose_kernel(const float *src, int rows, int cols, int ld, float *dst) {  // dst[r][c] = src[c][r]
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)rows * cols) return;
@@ -925,83 +919,6 @@ __global__ void untranspose_kernel(const float *src, int rows, int cols, int ld,
   dst[i] = src[(int64_t)c * ld + r];
 }
 
-// ---------------------------------------------------------------- TN GEMM (J^T over pixels) ----------------------
-// out[m][n] = sum_k A[k][m] B[k][n],  A: K x M (lda), B: K x N (ldb); split-K partials [split][M][N].
-constexpr int TM_ = 64, TN_ = 96, TK_ = 32, KSPLIT = 256;
-__global__ void __launch_bounds__(256) gemm_tn_kernel(const float *__restrict__ A, int lda, const float *__restrict__ Bm,
-                                                      int ldb, int K, int M, int N, float *__restrict__ part) {
-  __shared__ __align__(16) float As[TK_][TM_];
-  __shared__ __align__(16) float Bs[TK_][TN_];
-  const int t = threadIdx.x;
-  const int m0 = blockIdx.x * TM_, split = blockIdx.y;
-  const int k0 = split * KSPLIT, k1 = min(k0 + KSPLIT, K);
-  const int tx = t & 15, ty = t >> 4;  // thread tile: 4 (m) x 6 (n)
-  const bool vecA = (lda % 4 == 0) && (m0 + TM_ <= M) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
-  const bool vecB = (ldb % 4 == 0) && (N == TN_) && ((reinterpret_cast<uintptr_t>(Bm) & 15) == 0);
-  float acc[4][6];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 6; ++j) acc[i][j] = 0.f;
-  for (int kb = k0; kb < k1; kb += TK_) {
-    // A tile: 32 rows x 16 float4, B tile: 32 rows x 24 float4
-    for (int i = t; i < TK_ * (TM_ / 4); i += 256) {
-      const int kk = i / (TM_ / 4), m4 = (i % (TM_ / 4)) * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (kb + kk < k1) {
-        const float *src = A + (int64_t)(kb + kk) * lda + m0 + m4;
-        if (vecA) v = *reinterpret_cast<const float4 *>(src);
-        else {
-          if (m0 + m4 + 0 < M) v.x = src[0];
-          if (m0 + m4 + 1 < M) v.y = src[1];
-          if (m0 + m4 + 2 < M) v.z = src[2];
-          if (m0 + m4 + 3 < M) v.w = src[3];
-        }
-      }
-      *reinterpret_cast<float4 *>(&As[kk][m4]) = v;
-    }
-    for (int i = t; i < TK_ * (TN_ / 4); i += 256) {
-      const int kk = i / (TN_ / 4), n4 = (i % (TN_ / 4)) * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (kb + kk < k1) {
-        const float *src = Bm + (int64_t)(kb + kk) * ldb + n4;
-        if (vecB) v = *reinterpret_cast<const float4 *>(src);
-        else {
-          if (n4 + 0 < N) v.x = src[0];
-          if (n4 + 1 < N) v.y = src[1];
-          if (n4 + 2 < N) v.z = src[2];
-          if (n4 + 3 < N) v.w = src[3];
-        }
-      }
-      *reinterpret_cast<float4 *>(&Bs[kk][n4]) = v;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < TK_; ++kk) {
-      const float4 a4 = *reinterpret_cast<const float4 *>(&As[kk][ty * 4]);
-      const float2 b0 = *reinterpret_cast<const float2 *>(&Bs[kk][tx * 6]);
-      const float2 b1 = *reinterpret_cast<const float2 *>(&Bs[kk][tx * 6 + 2]);
-      const float2 b2 = *reinterpret_cast<const float2 *>(&Bs[kk][tx * 6 + 4]);
-      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
-      const float b[6] = {b0.x, b0.y, b1.x, b1.y, b2.x, b2.y};
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 6; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
-    if (m >= M) continue;
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      const int n = tx * 6 + j;
-      if (n < N) part[((int64_t)split * M + m) * N + n] = acc[i][j];
-    }
-  }
-}
 
 }  // namespace frtm
 
@@ -1236,20 +1153,150 @@ extern "C" int frtm_gn_update_batched(const void *table, int n_obj, int has_spli
                         (cudaStream_t)stream);
 }
 
+// ---- rank-9 form of the joint problem's operator ---------------------------------------------------------------
+// The target model's output is ONE channel, so the two products of J and J^T with the projection matrix collapse:
+//   F * (dP x)            = conv3x3(x; G),  G[ch][tap] = sum_c F[c][tap] dP[c][ch]          (C x 9 instead of c x C)
+//   J_P^T v = x^T (V F^T) = (x^T V) F^T,    H[ch][tap] = sum_p x[p][ch] v[p - tap]           (C x 9), gP[c][ch] = sum_tap F[c][tap] H[ch][tap]
+// i.e. 2 x 9 FMAs per element of x instead of 2 x 96: the two dense (c x C x pixels) contractions per operator application
+// (the reference's conv / conv-backward of the 1x1 projection, model/discriminator.py:168-175) become two streaming passes
+// over x.  Mathematically identical, the summation order differs.
+constexpr int JG_LD = 12;                  // G / tap-map rows padded to 12 floats (three 16-byte loads)
+
+// G[ch][t] = sum_c Pt[ch][c] F[c][t]
+__global__ void __launch_bounds__(256) joint_G_kernel(const float *__restrict__ Pt, const float *__restrict__ F, int C, int c,
+                                                      float *__restrict__ G) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * JG_LD) return;
+  const int ch = i / JG_LD, t = i - ch * JG_LD;
+  float acc = 0.f;
+  if (t < 9)
+    for (int cc = 0; cc < c; ++cc) acc = fmaf(Pt[(int64_t)ch * c + cc], F[cc * 9 + t], acc);
+  G[i] = acc;
+}
+
+// Y[p][t] = sum_ch xT[ch][p] G[ch][t]     xT: (C, NP) channel-major copy of x; block = 32 pixels x 8 channel slices
+__global__ void __launch_bounds__(256) joint_tapmaps_kernel(const float *__restrict__ xT, const float *__restrict__ G, int C, int NP,
+                                                            float *__restrict__ Y) {
+  __shared__ float red[8][9][33];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int p = blockIdx.x * 32 + lane;
+  float acc[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+  const int c0 = (int)((int64_t)C * wp / 8), c1 = (int)((int64_t)C * (wp + 1) / 8);
+  if (p < NP) {
+    for (int ch = c0; ch < c1; ++ch) {
+      const float xv = xT[(int64_t)ch * NP + p];
+      const float4 g0 = __ldg(reinterpret_cast<const float4 *>(G + (int64_t)ch * JG_LD));
+      const float4 g1 = __ldg(reinterpret_cast<const float4 *>(G + (int64_t)ch * JG_LD + 4));
+      const float g8 = __ldg(G + (int64_t)ch * JG_LD + 8);
+      acc[0] = fmaf(xv, g0.x, acc[0]); acc[1] = fmaf(xv, g0.y, acc[1]); acc[2] = fmaf(xv, g0.z, acc[2]);
+      acc[3] = fmaf(xv, g0.w, acc[3]); acc[4] = fmaf(xv, g1.x, acc[4]); acc[5] = fmaf(xv, g1.y, acc[5]);
+      acc[6] = fmaf(xv, g1.z, acc[6]); acc[7] = fmaf(xv, g1.w, acc[7]); acc[8] = fmaf(xv, g8, acc[8]);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 9; ++t) red[wp][t][lane] = acc[t];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 9 * 32; i += 256) {
+    const int t = i >> 5, l = i & 31;
+    const float sum = ((red[0][t][l] + red[1][t][l]) + (red[2][t][l] + red[3][t][l])) +
+                      ((red[4][t][l] + red[5][t][l]) + (red[6][t][l] + red[7][t][l]));
+    if (blockIdx.x * 32 + l < NP) Y[(int64_t)(blockIdx.x * 32 + l) * JG_LD + t] = sum;
+  }
+}
+
+// s[n][pix] = sum_t Y[n*hw + pix + off(t)][t]   (zero outside the map)
+__global__ void __launch_bounds__(256) joint_gather_scores_kernel(const float *__restrict__ Y, int h, int w, float *__restrict__ s) {
+  const int n = blockIdx.y, hw = h * w;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= hw) return;
+  const int py = pix / w, px = pix - py * w;
+  float acc = 0.f;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int yy = py + t / 3 - 1, xx = px + t % 3 - 1;
+    if (yy >= 0 && yy < h && xx >= 0 && xx < w) acc += Y[((int64_t)n * hw + yy * w + xx) * JG_LD + t];
+  }
+  s[(int64_t)n * hw + pix] = acc;
+}
+
+// Hp[split][ch][t] = sum_{p in split} x[p][ch] v[p - off(t)]    x NHWC (NP, C); thread = channel; split = JH_PIX pixels of a sample
+constexpr int JH_PIX = 128;
+__global__ void __launch_bounds__(256) joint_gradx_kernel(const float *__restrict__ x, const float *__restrict__ v, int C, int h, int w,
+                                                          int splits_per_sample, float *__restrict__ Hp) {
+  __shared__ __align__(16) float Vs[JH_PIX][JG_LD];
+  const int hw = h * w;
+  const int n = blockIdx.y / splits_per_sample, sp = blockIdx.y - n * splits_per_sample;
+  const int p0 = sp * JH_PIX, np = min(JH_PIX, hw - p0);
+  for (int i = threadIdx.x; i < JH_PIX * JG_LD; i += 256) {
+    const int lp = i / JG_LD, t = i - lp * JG_LD;
+    float val = 0.f;
+    if (lp < np && t < 9) {
+      const int pix = p0 + lp, py = pix / w, px = pix - py * w;
+      const int yy = py - (t / 3 - 1), xx = px - (t % 3 - 1);
+      if (yy >= 0 && yy < h && xx >= 0 && xx < w) val = v[(int64_t)n * hw + yy * w + xx];
+    }
+    Vs[lp][t] = val;
+  }
+  __syncthreads();
+  const int ch = blockIdx.x * 256 + threadIdx.x;
+  if (ch >= C) return;
+  float acc[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+  const float *xp = x + ((int64_t)n * hw + p0) * C + ch;
+  for (int lp = 0; lp < np; ++lp) {
+    const float xv = xp[(int64_t)lp * C];
+    const float4 a = *reinterpret_cast<const float4 *>(&Vs[lp][0]), b = *reinterpret_cast<const float4 *>(&Vs[lp][4]);
+    const float v8 = Vs[lp][8];
+    acc[0] = fmaf(xv, a.x, acc[0]); acc[1] = fmaf(xv, a.y, acc[1]); acc[2] = fmaf(xv, a.z, acc[2]);
+    acc[3] = fmaf(xv, a.w, acc[3]); acc[4] = fmaf(xv, b.x, acc[4]); acc[5] = fmaf(xv, b.y, acc[5]);
+    acc[6] = fmaf(xv, b.z, acc[6]); acc[7] = fmaf(xv, b.w, acc[7]); acc[8] = fmaf(xv, v8, acc[8]);
+  }
+  float *dst = Hp + ((int64_t)blockIdx.y * C + ch) * 9;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) dst[t] = acc[t];
+}
+
+// gP[ch][cc] = sum_t F[cc][t] H[ch][t],  H = sum_split Hp (fixed order); block = 8 channels
+__global__ void __launch_bounds__(256) joint_gP_kernel(const float *__restrict__ Hp, int nsplit, const float *__restrict__ F, int C, int c,
+                                                       float *__restrict__ gP) {
+  __shared__ float Hs[8][9];
+  const int ch0 = blockIdx.x * 8;
+  if (threadIdx.x < 72) {
+    const int lc = threadIdx.x / 9, t = threadIdx.x - lc * 9;
+    float acc = 0.f;
+    if (ch0 + lc < C)
+      for (int sidx = 0; sidx < nsplit; ++sidx) acc += Hp[((int64_t)sidx * C + ch0 + lc) * 9 + t];
+    Hs[lc][t] = acc;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 8 * c; i += 256) {
+    const int lc = i / c, cc = i - lc * c;
+    if (ch0 + lc >= C) continue;
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc = fmaf(F[cc * 9 + t], Hs[lc][t], acc);
+    gP[(int64_t)(ch0 + lc) * c + cc] = acc;
+  }
+}
+
 // ---- joint (project, filter) GN/CG of Discriminator.init --------------------------------------------------------
 namespace {
 struct InitWs {
   // sizes
-  int K, C, c, h, w, hw, nP, nF, splits;
+  int K, C, c, h, w, hw, nP, nF, sps, nsplit;
   // buffers (all float)
-  float *Pt, *cx, *a, *s, *v, *ga, *gpart, *fpart, *rP, *rF, *rpP, *rpF, *pP, *pF, *qP, *qF, *xP, *xF, *scal, *dpart;
+  float *Pt, *cx, *xT, *G, *Y, *s, *v, *Hp, *fpart, *rP, *rF, *rpP, *rpF, *pP, *pF, *qP, *qF, *xP, *xF, *scal, *dpart;
   int64_t total;
   InitWs(int K_, int C_, int c_, int h_, int w_, float *base) : K(K_), C(C_), c(c_), h(h_), w(w_) {
-    hw = h * w; nP = C * c; nF = c * 9; splits = cdiv((int64_t)K * hw, KSPLIT);
+    hw = h * w; nP = C * c; nF = c * 9; sps = cdiv(hw, JH_PIX); nsplit = K * sps;
     int64_t o = 0;
     auto take = [&](int64_t n) { float *p = base ? base + o : nullptr; o += (n + 3) / 4 * 4; return p; };
-    Pt = take(nP); cx = take((int64_t)K * c * hw); a = take((int64_t)K * c * hw); s = take((int64_t)K * hw);
-    v = take((int64_t)K * hw); ga = take((int64_t)K * hw * c); gpart = take((int64_t)splits * nP); fpart = take((int64_t)K * nF);
+    Pt = take(nP); cx = take((int64_t)K * c * hw); xT = take((int64_t)K * hw * C); G = take((int64_t)C * JG_LD);
+    Y = take((int64_t)K * hw * JG_LD); s = take((int64_t)K * hw); v = take((int64_t)K * hw);
+    Hp = take((int64_t)nsplit * C * 9); fpart = take((int64_t)K * nF);
     rP = take(nP); rF = take(nF); rpP = take(nP); rpF = take(nF); pP = take(nP); pF = take(nF); qP = take(nP); qF = take(nF);
     xP = take(nP); xF = take(nF); scal = take(16); dpart = take(2 * VB);
     total = o;
@@ -1260,15 +1307,17 @@ struct InitWs {
 int joint_products(const InitWs &W, const float *x, const float *stencil, const float *uty, const float *sw, const float *F,
                    const float *dP, const float *dF, float *gP, float *gF, cudaStream_t st) {
   const size_t fsm = (size_t)W.nF * sizeof(float), csm = fsm + 512 * sizeof(float);
+  const int NP = W.K * W.hw;
   dim3 gpix(cdiv(W.hw, 128), W.K), gpix256(cdiv(W.hw, 256), W.K), ggrad(cdiv(W.c, 8), W.K);
-  int rc;
   if (dP == nullptr) {  // RHS: s = F * (P x)
     corr3x3_kernel<<<gpix, 512, csm, st>>>(W.cx, F, nullptr, W.c, W.h, W.w, W.s, 0, nullptr);
     FRTM_CHECK_LAUNCH("gn_init/score");
-  } else {              // J d: s = F * (dP x) + dF * (P x)
-    rc = frtm_conv2d_nhwc(x, W.K, W.h, W.w, W.C, W.C, dP, nullptr, nullptr, 0, nullptr, 0, 0, W.a, W.c, 1, 1, 1, 0, 0, st);
-    if (rc) return rc;
-    corr3x3_kernel<<<gpix, 512, csm, st>>>(W.a, F, nullptr, W.c, W.h, W.w, W.s, 0, nullptr);
+  } else {              // J d: s = F * (dP x) + dF * (P x), the first term as conv3x3(x; G(dP, F))
+    joint_G_kernel<<<cdiv((int64_t)W.C * JG_LD, 256), 256, 0, st>>>(dP, F, W.C, W.c, W.G);
+    FRTM_CHECK_LAUNCH("gn_init/G");
+    joint_tapmaps_kernel<<<cdiv(NP, 32), 256, 0, st>>>(W.xT, W.G, W.C, NP, W.Y);
+    FRTM_CHECK_LAUNCH("gn_init/tapmaps");
+    joint_gather_scores_kernel<<<gpix256, 256, 0, st>>>(W.Y, W.h, W.w, W.s);
     FRTM_CHECK_LAUNCH("gn_init/score(dP)");
     corr3x3_kernel<<<gpix, 512, csm, st>>>(W.cx, dF, nullptr, W.c, W.h, W.w, W.s, 1, nullptr);
     FRTM_CHECK_LAUNCH("gn_init/score(dF)");
@@ -1279,12 +1328,11 @@ int joint_products(const InitWs &W, const float *x, const float *stencil, const 
   FRTM_CHECK_LAUNCH("gn_init/gradF");
   reduce_rows_kernel<<<cdiv(W.nF, 256), 256, 0, st>>>(W.fpart, W.K, W.nF, gF);
   FRTM_CHECK_LAUNCH("gn_init/gradF.reduce");
-  corr3x3_grad_input_kernel<<<dim3(cdiv((int64_t)W.hw * W.c, 256), W.K), 256, fsm, st>>>(W.v, F, W.c, W.h, W.w, W.ga);
-  FRTM_CHECK_LAUNCH("gn_init/gradIn");
-  gemm_tn_kernel<<<dim3(cdiv(W.C, TM_), W.splits), 256, 0, st>>>(x, W.C, W.ga, W.c, W.K * W.hw, W.C, W.c, W.gpart);
-  FRTM_CHECK_LAUNCH("gn_init/gemm_tn");
-  reduce_rows_kernel<<<cdiv(W.nP, 256), 256, 0, st>>>(W.gpart, W.splits, W.nP, gP);
-  FRTM_CHECK_LAUNCH("gn_init/gemm_tn.reduce");
+  // J_P^T v = (x^T V) F^T
+  joint_gradx_kernel<<<dim3(cdiv(W.C, 256), W.nsplit), 256, 0, st>>>(x, W.v, W.C, W.h, W.w, W.sps, W.Hp);
+  FRTM_CHECK_LAUNCH("gn_init/gradx");
+  joint_gP_kernel<<<cdiv(W.C, 8), 256, 0, st>>>(W.Hp, W.nsplit, F, W.C, W.c, gP);
+  FRTM_CHECK_LAUNCH("gn_init/gradP");
   return FRTM_OK;
 }
 }  // namespace
@@ -1300,7 +1348,7 @@ static int gn_init_impl(const float *x, const float *stencil, const float *uty, 
                         float forget, float *ws, int64_t ws_bytes, cudaStream_t st, const float *dP, const float *dF,
                         float *out_bP, float *out_bF, float *out_AP, float *out_AF) {
   FRTM_REQUIRE(x && stencil && uty && sw && P && F && ws, "gn_init: null pointer");
-  FRTM_REQUIRE(C % 4 == 0 && c % 4 == 0 && c <= TN_ && c * 9 <= 1024, "gn_init: unsupported channel counts C=%d c=%d", C, c);
+  FRTM_REQUIRE(C % 4 == 0 && c % 4 == 0 && c <= 128 && c * 9 <= 1024, "gn_init: unsupported channel counts C=%d c=%d", C, c);
   FRTM_REQUIRE(ws_bytes >= frtm_gn_init_workspace(K, C, c, h, w), "gn_init: workspace too small");
   FRTM_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "gn_init: workspace must be 16-byte aligned");
   InitWs W(K, C, c, h, w, ws);
@@ -1309,6 +1357,11 @@ static int gn_init_impl(const float *x, const float *stencil, const float *uty, 
   auto blocks = [](int64_t n) { return cdiv(n, 256); };
   transpose_pad_kernel<<<blocks(nP), 256, 0, st>>>(P, c, C, W.Pt, c);   // Pt[C][c]
   FRTM_CHECK_LAUNCH("gn_init/transpose");
+  {   // channel-major copy of the features for the tap-map pass (x itself is pixel-major), once per call
+    const int NP = K * h * w;
+    transpose_tiled_kernel<<<dim3(cdiv(C, 32), cdiv(NP, 32)), dim3(32, 8), 0, st>>>(x, NP, C, W.xT);
+    FRTM_CHECK_LAUNCH("gn_init/xT");
+  }
   cudaMemsetAsync(W.scal, 0, 16 * sizeof(float), st);
   const bool probe = dP != nullptr;
   int scal_cur = 0;
