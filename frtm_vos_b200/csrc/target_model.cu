@@ -1440,10 +1440,30 @@ struct InitKey {
   std::vector<long long> v;
   bool operator<(const InitKey &o) const { return v < o.v; }
 };
-struct InitGraph { int calls = 0; int kernels = 1; cudaGraphExec_t exec = nullptr; };
+struct InitGraph { int calls = 0; int kernels = 1; cudaGraphExec_t exec = nullptr; long long stamp = 0; };
 std::map<InitKey, InitGraph> g_init_graphs;
 std::mutex g_init_mutex;
+long long g_init_clock = 0;
+constexpr size_t INIT_GRAPH_CAP = 16;      // signatures kept (one per staged buffer set / stream); least recently used goes first
+// key.v[6] is the workspace pointer of the signature
+void drop_init_graphs_locked(const void *workspace) {
+  for (auto it = g_init_graphs.begin(); it != g_init_graphs.end();) {
+    if (workspace == nullptr || it->first.v[6] == (long long)reinterpret_cast<uintptr_t>(workspace)) {
+      if (it->second.exec) cudaGraphExecDestroy(it->second.exec);
+      it = g_init_graphs.erase(it);
+    } else ++it;
+  }
+}
 }  // namespace
+
+// Forget the captured optimisation graphs that use `workspace` (NULL: all of them).  The caller owns the staged buffers a
+// graph was captured over; it calls this before freeing them (frtm_vos_b200.model.optimizer drops a staging set when its
+// small LRU overflows and when the tracker is cleared), so no graph outlives its memory.
+extern "C" int frtm_gn_init_release(const void *workspace) {
+  std::lock_guard<std::mutex> lock(g_init_mutex);
+  drop_init_graphs_locked(workspace);
+  return FRTM_OK;
+}
 
 extern "C" int frtm_gn_init(const float *x_nhwc, const float *stencil, const float *uty, const float *sw, int K, int C, int c,
                             int h, int w, float *P, float *F, const int *cg_iters, int n_gn, float regP, float regF,
@@ -1463,7 +1483,15 @@ extern "C" int frtm_gn_init(const float *x_nhwc, const float *stencil, const flo
   for (int i = 0; i < n_gn; ++i) key.v.push_back(cg_iters[i]);
   for (float f : {regP, regF, precondP, precondF, forget}) { long long b = 0; memcpy(&b, &f, sizeof(float)); key.v.push_back(b); }
   std::lock_guard<std::mutex> lock(g_init_mutex);
+  if (g_init_graphs.size() >= INIT_GRAPH_CAP && g_init_graphs.find(key) == g_init_graphs.end()) {
+    auto oldest = g_init_graphs.begin();
+    for (auto it = g_init_graphs.begin(); it != g_init_graphs.end(); ++it)
+      if (it->second.stamp < oldest->second.stamp) oldest = it;
+    if (oldest->second.exec) cudaGraphExecDestroy(oldest->second.exec);
+    g_init_graphs.erase(oldest);
+  }
   InitGraph &g = g_init_graphs[key];
+  g.stamp = ++g_init_clock;
   g.calls += 1;
   if (g.calls < 2 || g.calls < 0) return eager();
   // The legacy default stream cannot be captured: fork to an internal stream (event in / event out) for graph work.

@@ -13,6 +13,7 @@ autograd fallback, which this package does not ship by design.
 """
 from __future__ import annotations
 
+import collections
 import ctypes
 
 import torch
@@ -21,19 +22,39 @@ from ..lib.tensorlist import TensorList
 from .._lib import lib, ptr, stream
 
 
-_INIT_STAGE = {}
+# Staging buffers of the joint (project, filter) optimisation, one set per (shape, device, stream): the library replays the
+# whole schedule as a CUDA graph when it sees the same buffers again.  A small LRU: datasets with mixed resolutions
+# (YouTubeVOS) would otherwise pin one set (tens of MB) per resolution for the life of the process; an evicted set's graphs
+# are released in the library before its memory is.  ``release_init_stages()`` (``Tracker.clear``) drops everything.
+_INIT_STAGE = collections.OrderedDict()
+_INIT_STAGE_CAP = 6
+
+
+def _drop_stage(st):
+    lib().gn_init_release(ptr(st["ws"]))
+
+
+def release_init_stages():
+    while _INIT_STAGE:
+        _, st = _INIT_STAGE.popitem(last=False)
+        _drop_stage(st)
 
 
 def _init_stage(K, C, c, h, w, device):
     key = (K, C, c, h, w, str(device), torch.cuda.current_stream().cuda_stream)
     st = _INIT_STAGE.get(key)
     if st is None:
+        while len(_INIT_STAGE) >= _INIT_STAGE_CAP:
+            _, old = _INIT_STAGE.popitem(last=False)
+            _drop_stage(old)
         nbytes = lib().gn_init_workspace(K, C, c, h, w)
         f = dict(device=device, dtype=torch.float32)
         st = dict(x=torch.empty((K, h, w, C), **f), stencil=torch.empty((K, 9, h, w), **f), uty=torch.empty((K, h, w), **f),
                   sw=torch.empty(K, **f), P=torch.empty((c, C), **f), F=torch.empty(c * 9, **f),
                   ws=torch.empty(nbytes // 4, **f), nbytes=nbytes)
         _INIT_STAGE[key] = st
+    else:
+        _INIT_STAGE.move_to_end(key)
     return st
 
 

@@ -72,7 +72,10 @@ class Tracker(nn.Module):
         self.num_objects = 0
         self.targets = dict()
         self.object_ids = []
-        self.augment_workers = 4    # host threads preparing first-frame augmentations of several new objects at once
+        # host threads preparing the first-frame augmentations of several new objects at once: the OpenCV inpaint (7 ms,
+        # GIL released) dominates a job, so one thread per object up to the process's thread budget (bench.py caps
+        # torch's thread count at cores / ranks)
+        self.augment_workers = max(4, min(12, torch.get_num_threads()))
         self.block_batching = True  # run_sequence batches up to max_block frames between two filter updates
         self.max_block = 8
         # Experimental, off by default (FRTM_GRAPH_BLOCKS=1): full blocks (max_block frames, no object starting inside) are
@@ -92,6 +95,18 @@ class Tracker(nn.Module):
         self.current_masks = None
         self.num_objects = 0
         self._stack = None
+        torch.cuda.empty_cache()
+
+    def release_buffers(self):
+        """Drop everything cached across sequences: the staging sets of the joint optimisation with their captured CUDA
+        graphs (``model/optimizer.py`` keeps a small LRU of them, one per feature resolution and stream) and the
+        per-sequence tables.  Not needed between sequences; for long-lived processes that switch models or resolutions."""
+        from .optimizer import release_init_stages
+        self.targets = dict()
+        self._fbuf = None
+        self._gn_table = None
+        self._blk_graph = None
+        release_init_stages()
         torch.cuda.empty_cache()
 
     # ------------------------------------------------------------------------------------------------------------

@@ -259,6 +259,10 @@ int frtm_gn_init(const float *x_nhwc, const float *stencil, const float *uty, co
                  int w, float *P, float *F, const int *cg_iters_host, int n_gn, float regP, float regF, float precondP,
                  float precondF, float forget, float *workspace, int64_t workspace_bytes, void *stream);
 int64_t frtm_gn_init_workspace(int K, int C, int c, int h, int w);
+/* frtm_gn_init replays its fixed launch schedule as a CUDA graph when it is called again with the same buffers.  The
+ * library keeps at most 16 such graphs (least recently used first out); a caller that frees the buffers of a signature
+ * calls this with that signature's workspace pointer first (NULL forgets every graph). */
+int frtm_gn_init_release(const void *workspace);
 /* Teacher-forced probe of the joint problem at (P,F): out_b = -(J^T r0 + reg^2 theta), out_A = J^T J d + reg^2 d. */
 int frtm_gn_init_probe(const float *x_nhwc, const float *stencil, const float *uty, const float *sw, int K, int C, int c,
                        int h, int w, float *P, float *F, const float *dP, const float *dF, float regP, float regF,
