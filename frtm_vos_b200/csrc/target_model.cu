@@ -758,7 +758,8 @@ __global__ void __launch_bounds__(1024) cg_vector_kernel(CgVec s, int mode, cons
   }
   float r = 0.f, p = 0.f, rp = 0.f;
   float rho = *s.rho;
-  const bool hasp = *s.hasp != 0.f;
+  // direction_forget_factor == 0: the CG state is reset at the start of every run (optimizer.py:93-103)
+  const bool hasp = *s.hasp != 0.f && !(mode == 0 && s.forget == 0.f);
   if (mode == 0) {
     if (act) {
       r = -(g + s.reg2 * s.f[t]);
@@ -1013,7 +1014,7 @@ static int gn_update_impl(const float *samples, const __half *samples_split, con
   FRTM_REQUIRE(cg_iters && workspace && n_obj >= 1, "gn_update: null pointer");
   FRTM_REQUIRE(c * 9 <= 1024, "gn_update: filter too large for the single-block CG kernel (c*9 <= 1024)");
   FRTM_REQUIRE(workspace_bytes >= n_obj * frtm_gn_update_workspace(cap, c, h, w), "gn_update: workspace too small");
-  FRTM_REQUIRE(forget > 0.f, "gn_update: direction_forget_factor must be > 0 (0 = reset is not used on this path)");
+  FRTM_REQUIRE(forget >= 0.f, "gn_update: direction_forget_factor must be >= 0 (0 resets the CG state at every run, optimizer.py:102-103)");
   const int n = c * 9, hw = h * w;
   FRTM_REQUIRE(c % 4 == 0, "gn_update: needs c %% 4 == 0 (got %d)", c);
   const bool fast = (w % 2 == 0);
@@ -1185,6 +1186,7 @@ __global__ void __launch_bounds__(256) joint_tapmaps_kernel(const float *__restr
   for (int t = 0; t < 9; ++t) acc[t] = 0.f;
   const int c0 = (int)((int64_t)C * wp / 8), c1 = (int)((int64_t)C * (wp + 1) / 8);
   if (p < NP) {
+#pragma unroll 8                                   // eight independent 128-byte loads in flight per warp
     for (int ch = c0; ch < c1; ++ch) {
       const float xv = xT[(int64_t)ch * NP + p];
       const float4 g0 = __ldg(reinterpret_cast<const float4 *>(G + (int64_t)ch * JG_LD));
@@ -1246,6 +1248,7 @@ __global__ void __launch_bounds__(256) joint_gradx_kernel(const float *__restric
 #pragma unroll
   for (int t = 0; t < 9; ++t) acc[t] = 0.f;
   const float *xp = x + ((int64_t)n * hw + p0) * C + ch;
+#pragma unroll 8
   for (int lp = 0; lp < np; ++lp) {
     const float xv = xp[(int64_t)lp * C];
     const float4 a = *reinterpret_cast<const float4 *>(&Vs[lp][0]), b = *reinterpret_cast<const float4 *>(&Vs[lp][4]);
@@ -1396,12 +1399,13 @@ static int gn_init_impl(const float *x, const float *stencil, const float *uty, 
     cudaMemsetAsync(W.xP, 0, nP * sizeof(float), st);
     cudaMemsetAsync(W.xF, 0, nF * sizeof(float), st);
     const int iters = cg_iters[gi];
+    if (forget == 0.f) cudaMemsetAsync(W.scal, 0, 16 * sizeof(float), st);   // factor 0: the CG state is reset at every run (optimizer.py:102-103)
     for (int it = 0; it < iters; ++it) {
       float *sin = W.scal + 4 * scal_cur, *sout = W.scal + 4 * (scal_cur ^ 1);
       joint_dots_rz_kernel<<<VB, 256, 0, st>>>(W.rP, W.rpP, nP, 1.f / mP, W.rF, W.rpF, nF, 1.f / mF, W.dpart);
       FRTM_CHECK_LAUNCH("gn_init/dots_rz");
       joint_direction_kernel<<<VB, 256, 0, st>>>(W.pP, W.rP, nP, 1.f / mP, W.pF, W.rF, nF, 1.f / mF, W.dpart, sin, sout,
-                                                 it == 0 ? forget : 1.f);
+                                                 it == 0 && forget > 0.f ? forget : 1.f);
       FRTM_CHECK_LAUNCH("gn_init/direction");
       scal_cur ^= 1;
       rc = joint_products(W, x, stencil, uty, sw, F, W.pP, W.pF, W.qP, W.qF, st);

@@ -168,7 +168,8 @@ __device__ __forceinline__ void cg_vector_step_cta(const CgVec &s, int mode, flo
       g[e] = ((g8[e][0] + g8[e][1]) + (g8[e][2] + g8[e][3])) + ((g8[e][4] + g8[e][5]) + (g8[e][6] + g8[e][7]));
   }
   float rho = *s.rho;
-  const bool hasp = *s.hasp != 0.f;
+  // direction_forget_factor == 0: the CG state is reset at the start of every run (optimizer.py:93-103)
+  const bool hasp = *s.hasp != 0.f && !(mode == 0 && s.forget == 0.f);
   if (mode == 0) {
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {

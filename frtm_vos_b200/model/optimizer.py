@@ -85,8 +85,8 @@ class GaussNewtonCG:
         if fletcher_reeves or not standard_alpha or step_alpha != 1.0 or cg_eps != 0.0:
             raise NotImplementedError("only the configuration FRTM uses is implemented: Polak-Ribiere, standard_alpha, "
                                       "step_alpha=1, cg_eps=0 (model/discriminator.py:172,192)")
-        if not direction_forget_factor > 0:
-            raise NotImplementedError("direction_forget_factor must be > 0")
+        if direction_forget_factor < 0:
+            raise ValueError("direction_forget_factor must be >= 0 (0 = reset the CG state at every run)")
         self.problem = problem
         self.x = variable
         self.direction_forget_factor = float(direction_forget_factor)
