@@ -84,44 +84,6 @@ __device__ __forceinline__ void mbar_arrive_cta(uint32_t bar) {
   asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-// Work list of an update, built once (the sample weights do not change between its operator applications):
-//   hdr[0] = U (active samples of all objects), hdr[1 + o] = first item of object o (hdr[1 + n_obj] = U),
-//   items[u] = (object << 16) | slot, object-major, slots ascending.
-struct ClList {
-  int *hdr;
-  uint32_t *items;
-};
-
-__global__ void __launch_bounds__(256) gn_build_items_kernel(const float *sw_single, const long long *table, int n_obj, int cap,
-                                                             ClList L) {
-  __shared__ int wsum[8];
-  __shared__ int base_s;
-  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
-  if (tid == 0) base_s = 0;
-  __syncthreads();
-  const int total = n_obj * cap;
-  for (int e0 = 0; e0 < total; e0 += 256) {
-    const int e = e0 + tid;
-    const int o = e < total ? e / cap : 0, slot = e < total ? e - o * cap : 0;
-    const float *sw = table ? reinterpret_cast<const float *>(table[3 * n_obj + o]) : sw_single;
-    const bool act = e < total && sw[slot] != 0.f;
-    const unsigned m = __ballot_sync(0xffffffffu, act);
-    const int before = __popc(m & ((1u << lane) - 1u));
-    if (lane == 0) wsum[wp] = __popc(m);
-    __syncthreads();
-    int woff = 0, tot = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { if (k < wp) woff += wsum[k]; tot += wsum[k]; }
-    const int idx = base_s + woff + before;
-    if (act) L.items[idx] = ((uint32_t)o << 16) | (uint32_t)slot;
-    if (e < total && slot == 0) L.hdr[1 + o] = idx;
-    __syncthreads();
-    if (tid == 0) base_s += tot;
-    __syncthreads();
-  }
-  if (tid == 0) { L.hdr[0] = base_s; L.hdr[1 + n_obj] = base_s; }
-}
-
 struct ClParams {
   int ntiles, tile_bytes, cs, nslot, nclusters, rowcap;
   int64_t image_bytes;
@@ -680,26 +642,19 @@ bool gn_apply_cl_supported(int c, int h, int w) {
   return cl_cluster_size(c, ntiles, w) != 0;
 }
 
-int64_t gn_apply_cl_workspace(int n_obj, int cap, int c) {
-  // rows [n_obj][160][n] | tickets [n_obj] | list header [2 + n_obj] | items [n_obj * cap]      (floats / ints, 4 bytes each)
-  return ((int64_t)n_obj * 160 * c * 9 + n_obj + (2 + n_obj) + (int64_t)n_obj * cap + 16) * 4;
-}
-
 struct ClPlan {
   ClParams P;
   size_t smem;
 };
 
-static int cl_plan(const GaArgs &a, float *ws, ClPlan &plan) {
+static int cl_plan(const GaArgs &a, const GnListWs &ws, ClPlan &plan) {
   const int hw = a.h * a.w, n = a.c * 9;
   ClParams &P = plan.P;
   P.ntiles = gc_ntiles(hw); P.tile_bytes = 2 * a.c * 128; P.cs = cl_cluster_size(a.c, P.ntiles, a.w);
   P.nslot = (P.ntiles + P.cs - 1) / P.cs; P.image_bytes = gc_sample_bytes(a.c, hw); P.rowcap = 160;
   plan.smem = cl_smem(a.c, P.nslot);
-  P.rows = ws;
-  P.tickets = reinterpret_cast<int *>(ws + (int64_t)a.n_obj * 160 * n);
-  P.list.hdr = P.tickets + a.n_obj;
-  P.list.items = reinterpret_cast<uint32_t *>(P.list.hdr + 2 + a.n_obj);
+  P.rows = ws.rows; P.tickets = ws.tickets; P.list = ws.list;
+  (void)n;
   // persistent clusters: as many as the device can hold at once for this cluster size / shared-memory footprint
   static int cached_nc[17] = {0};
   static size_t cached_smem[17] = {0};
@@ -727,17 +682,7 @@ static int cl_plan(const GaArgs &a, float *ws, ClPlan &plan) {
   return FRTM_OK;
 }
 
-// once per update, before its first operator application: the work list and zeroed tickets
-int gn_apply_cl_prepare(const GaArgs &a, float *ws, cudaStream_t st) {
-  ClPlan plan;
-  if (int rc = cl_plan(a, ws, plan)) return rc;
-  if (cudaMemsetAsync(plan.P.tickets, 0, sizeof(int) * a.n_obj, st) != cudaSuccess) { set_error("gn_apply_cl: memset failed"); return FRTM_ELAUNCH; }
-  gn_build_items_kernel<<<1, 256, 0, st>>>(a.sw, a.table, a.n_obj, a.cap, plan.P.list);
-  FRTM_CHECK_LAUNCH("gn_build_items");
-  return FRTM_OK;
-}
-
-int gn_apply_cl_launch(const GaArgs &a, const GcFuse &fuse, float *ws, cudaStream_t st) {
+int gn_apply_cl_launch(const GaArgs &a, const GcFuse &fuse, const GnListWs &ws, cudaStream_t st) {
   ClPlan plan;
   if (int rc = cl_plan(a, ws, plan)) return rc;
   FRTM_REQUIRE(((int64_t)a.n_obj * a.cap + plan.P.nclusters - 1) / plan.P.nclusters + 1 <= CL_MAXITEMS,

@@ -45,13 +45,15 @@ constexpr int GM_MAXC = 96;
 // Phase timeline (timing builds only, `make timing` -> libfrtm_b200_timing.so): thread 0 of CTA (0,0) accumulates the
 // clock64 time it spends in every phase of a sample and prints the totals.
 #ifdef GM_TIMING
-#define GM_T(k) do { if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) { const long long t__ = clock64(); tacc[k] += t__ - tlast; tlast = t__; } } while (0)
+#define GM_T(k) do { if (tid == 0 && blockIdx.x == 0) { const long long t__ = clock64(); tacc[k] += t__ - tlast; tlast = t__; } } while (0)
 #else
 #define GM_T(k) do { } while (0)
 #endif
 
+// One unit of work: P3 blocks [pb0, pb1) of memory slot `i` of object `o` (a whole sample: [0, nblocks)); P1 runs two blocks
+// further on either side (the window's lag).  The unit's gradient goes to `part` (n floats).
 template <int C>
-__device__ __forceinline__ void gm_sample(const GaArgs &a, const GcParams &P) {
+__device__ __forceinline__ void gm_sample(const GaArgs &a, const GcParams &P, int o, int i, int pb0, int pb1, float *part) {
   constexpr int KS = C / 16;                          // channel k-steps of P1 = channel m-tiles of P3
   constexpr int FOLD = 4;                             // P3 steps accumulated inside the tensor core between fp32 folds
   const int h = a.h, w = a.w, use_y = a.use_y;
@@ -59,24 +61,17 @@ __device__ __forceinline__ void gm_sample(const GaArgs &a, const GcParams &P) {
   const int hw = h * w, lag = w + 1;
   const int tid = threadIdx.x, lane = tid & 31, wp = uniform_warp_idx();
   const int nblocks = P.ntiles >> 1;
+  const int fb = max(pb0 - 2, 0), lb = min(pb1 + 2, nblocks);          // P1 blocks [fb, lb)
   const uint32_t tile_bytes = (uint32_t)P.tile_bytes, blk_bytes = 2u * tile_bytes;
-  const int i = blockIdx.x;
   const float *sw = a.sw, *pvec = a.pvec;
   const __half *xs = a.XS;
-  float *part = a.partial + (int64_t)i * n;
   if (a.table) {
-    const int o = blockIdx.y;
     sw = reinterpret_cast<const float *>(a.table[3 * a.n_obj + o]);
     // RHS pass linearises at the filter itself, CG passes apply the operator to the direction p (= cg_state[0:n])
     pvec = reinterpret_cast<const float *>(a.table[(use_y ? 4 : 5) * a.n_obj + o]);
     xs = reinterpret_cast<const __half *>(a.table[7 * a.n_obj + o]);
-    part += (int64_t)o * a.cap * n;
   }
   const float wgt = sw[i];
-  if (wgt == 0.f) {
-    for (int k = tid; k < n; k += GM_THREADS) part[k] = 0.f;
-    return;
-  }
   const uint8_t *img = reinterpret_cast<const uint8_t *>(xs) + (int64_t)i * P.image_bytes;
   const float *sten = reinterpret_cast<const float *>(img + (int64_t)P.ntiles * tile_bytes);
 
@@ -94,10 +89,10 @@ __device__ __forceinline__ void gm_sample(const GaArgs &a, const GcParams &P) {
   if (tid == 0) {
     for (int s = 0; s < GM_SLOTS; ++s) mbar_init(bars + 8 * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    for (int b = 0; b < GM_SLOTS && b < nblocks; ++b) {
+    for (int b = 0; b < GM_SLOTS && fb + b < lb; ++b) {
       mbar_expect_tx(bars + 8 * b, blk_bytes);
-      bulk_load(ring + b * blk_bytes, img + (int64_t)b * blk_bytes, tile_bytes, bars + 8 * b);
-      bulk_load(ring + b * blk_bytes + tile_bytes, img + (int64_t)b * blk_bytes + tile_bytes, tile_bytes, bars + 8 * b);
+      bulk_load(ring + b * blk_bytes, img + (int64_t)(fb + b) * blk_bytes, tile_bytes, bars + 8 * b);
+      bulk_load(ring + b * blk_bytes + tile_bytes, img + (int64_t)(fb + b) * blk_bytes + tile_bytes, tile_bytes, bars + 8 * b);
     }
   }
 
@@ -181,7 +176,7 @@ __device__ __forceinline__ void gm_sample(const GaArgs &a, const GcParams &P) {
   const int step_y = (int)__umulhi((unsigned)GM_BLK, magic), step_x = GM_BLK - step_y * w;
   int py, px;
   {
-    const unsigned q0 = (unsigned)(wp * 16 + k0);
+    const unsigned q0 = (unsigned)(pb0 * GM_BLK + wp * 16 + k0);
     py = (int)__umulhi(q0, magic);
     px = (int)q0 - py * w;
   }
@@ -189,11 +184,13 @@ __device__ __forceinline__ void gm_sample(const GaArgs &a, const GcParams &P) {
 #ifdef GM_TIMING
   long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
 #endif
-  int s_hi = 0, v_hi = 0;
-  for (int b = 0; b < nblocks + 2; ++b) {
+  // scores are needed two rows beyond the unit's P3 pixels, residuals one row beyond
+  const int s_end = min(GM_BLK * pb1 + 2 * lag, hw), v_end = min(GM_BLK * pb1 + lag, hw);
+  int s_hi = max(GM_BLK * pb0 - 2 * lag, 0), v_hi = max(GM_BLK * pb0 - lag, 0);
+  for (int b = fb; b < lb + 2; ++b) {
     const int s_lo = s_hi, v_lo = v_hi;
-    s_hi = b >= nblocks - 1 ? hw : GM_BLK * (b + 1) - lag;
-    v_hi = b >= nblocks - 1 ? hw : max(s_hi - lag, 0);
+    s_hi = b >= lb - 1 ? s_end : min(s_end, max(GM_BLK * (b + 1) - lag, s_lo));
+    v_hi = b >= lb - 1 ? v_end : min(v_end, max(s_hi - lag, v_lo));
     // stencil rows of this step's residual pixels: issued now, consumed after P1 and the score gather
     float st[10];
     const int qv = v_lo + tid;
@@ -204,10 +201,10 @@ __device__ __forceinline__ void gm_sample(const GaArgs &a, const GcParams &P) {
     }
 
     // ---------------- P1(b): five accumulator chains over the six channel k-steps ----------------
-    if (b < nblocks) {
-      const int slot = b % GM_SLOTS;
+    if (b < lb) {
+      const int slot = (b - fb) % GM_SLOTS;
       GM_T(0);
-      mbar_wait(bars + 8 * slot, (b / GM_SLOTS) & 1);
+      mbar_wait(bars + 8 * slot, ((b - fb) / GM_SLOTS) & 1);
       GM_T(1);
       const uint32_t t1 = ring + slot * blk_bytes + off1;
       uint32_t ah[KS][4], al[KS][4];
@@ -292,9 +289,10 @@ __device__ __forceinline__ void gm_sample(const GaArgs &a, const GcParams &P) {
     GM_T(7);
 
     // ---------------- P3(b - 2): six independent accumulator chains (channel m-tiles) x 5 products ----------------
-    if (b >= 2) {
+    if (b - 2 >= fb) {                                   // block b - 2 leaves the window (P3 on it if it belongs to the unit)
       const int bb = b - 2;
-      const int slot = bb % GM_SLOTS;
+      const int slot = (bb - fb) % GM_SLOTS;
+      if (bb >= pb0 && bb < pb1) {
       const uint32_t t3 = ring + slot * blk_bytes + off3;
       uint32_t ah[KS][4], al[KS][4];
 #pragma unroll
@@ -351,10 +349,11 @@ __device__ __forceinline__ void gm_sample(const GaArgs &a, const GcParams &P) {
 #pragma unroll
       for (int m = 0; m < KS; ++m) hmma(acc[m], al[m], bh[0], bh[1]);
       ++nacc;
+      }
       GM_T(8);
       __syncthreads();                                 // every warp is done with block b - 2: its slot takes block b + 2
       GM_T(9);
-      if (wp == 0 && b + 2 < nblocks) {                // warp-uniform branch + elected lane: addresses stay in uniform registers
+      if (wp == 0 && b + 2 < lb) {                     // warp-uniform branch + elected lane: addresses stay in uniform registers
         const int nb = b + 2;
         const uint32_t dst = ring + slot * blk_bytes;
         const uint8_t *src = img + (int64_t)nb * blk_bytes;
@@ -370,7 +369,7 @@ __device__ __forceinline__ void gm_sample(const GaArgs &a, const GcParams &P) {
   if (nacc) fold();
 
 #ifdef GM_TIMING
-  if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0)
+  if (tid == 0 && blockIdx.x == 0)
     printf("gm timeline (clocks, %d steps): stencil-issue %lld | wait-load %lld | P1 %lld | bar %lld | scores %lld | bar %lld | residual %lld | bar %lld "
            "| P3 %lld | bar %lld\n", nblocks + 2, tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], tacc[5], tacc[6], tacc[7], tacc[8], tacc[9]);
 #endif
@@ -400,9 +399,86 @@ __device__ __forceinline__ void gm_sample(const GaArgs &a, const GcParams &P) {
   }
 }
 
-__global__ void __launch_bounds__(GM_THREADS, 1) gn_apply_mma_kernel(const GaArgs a, const GcParams P, const GcFuse F) {
-  gm_sample<GM_MAXC>(a, P);
-  gc_fused_tail<GM_THREADS, 4>(a, F);
+// Units of a launch.  The U active samples of the work list run as whole samples, one CTA each (one CTA per SM, CTAs are
+// dispatched in index order), except the R = U mod nsm samples of the last, partial wave: those are cut into k = min(4,
+// nsm / R) parts each (P3 block ranges; the parts recompute two blocks of P1 on either side), so the last wave fills the
+// machine with units a k-th as long instead of leaving nsm - R SMs idle for a whole sample time.
+struct GmUnits {
+  GnListWs ws;
+  int nsm;
+};
+__device__ __forceinline__ int gm_unit_of_item(int t, int n_whole, int k) { return t < n_whole ? t : n_whole + (t - n_whole) * k; }
+
+__global__ void __launch_bounds__(GM_THREADS, 1) gn_apply_mma_kernel(const GaArgs a, const GcParams P, const GcFuse F, const GmUnits Q) {
+  constexpr int n = GM_MAXC * 9;
+  __shared__ float red[32];
+  __shared__ int s_last;
+  const int nblocks = P.ntiles >> 1;
+  const int U = Q.ws.list.hdr[0];
+  const int R = U % Q.nsm;
+  int k = R ? min(4, Q.nsm / R) : 1;
+  k = max(1, min(k, nblocks / 2));                   // a part is at least two blocks
+  const int n_whole = k > 1 ? U - R : U;
+  const int units = n_whole + (U - n_whole) * k;
+  const int b = blockIdx.x;
+  if (b >= units) return;
+  const int item_idx = b < n_whole ? b : n_whole + (b - n_whole) / k;
+  const int part_idx = b < n_whole ? 0 : (b - n_whole) % k, parts = b < n_whole ? 1 : k;
+  const uint32_t item = Q.ws.list.items[item_idx];
+  const int o = (int)(item >> 16), slot = (int)(item & 0xffffu);
+  float *row = Q.ws.rows + (int64_t)b * n;
+  gm_sample<GM_MAXC>(a, P, o, slot, part_idx * nblocks / parts, (part_idx + 1) * nblocks / parts, row);
+  if (!F.enabled) return;
+
+  // ---- reduction + CG vector step in the tail of the launch (as gc_fused_tail, over the object's unit rows) ----
+  const int r0 = gm_unit_of_item(Q.ws.list.hdr[1 + o], n_whole, k), r1 = gm_unit_of_item(Q.ws.list.hdr[2 + o], n_whole, k);
+  const int n_o = r1 - r0, ngrp = (n_o + GC_RGROUP - 1) / GC_RGROUP;
+  const int grp = (b - r0) / GC_RGROUP, gsize = min(GC_RGROUP, n_o - grp * GC_RGROUP);
+  int *cnt = Q.ws.counters + (int64_t)o * (1 + Q.ws.ngrp_max);
+  float *gs = Q.ws.gsum + (int64_t)o * Q.ws.ngrp_max * n;
+  __threadfence();                                   // this unit's row is visible before its ticket
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int ticket = atomicAdd(cnt + 1 + grp, 1);
+    s_last = (ticket == gsize - 1) ? 1 : 0;
+    if (s_last) cnt[1 + grp] = 0;                    // every ticket of this group has been drawn: reset for the next launch
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  {
+    const float *part = Q.ws.rows + ((int64_t)r0 + (int64_t)grp * GC_RGROUP) * n;
+    float *dst = gs + (int64_t)grp * n;
+    for (int t = threadIdx.x; t < n; t += GM_THREADS) {
+      float v[GC_RGROUP];
+#pragma unroll
+      for (int u = 0; u < GC_RGROUP; ++u) v[u] = u < gsize ? __ldcg(part + (int64_t)u * n + t) : 0.f;
+      dst[t] = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int ticket = atomicAdd(cnt, 1);
+    s_last = (ticket == ngrp - 1) ? 1 : 0;
+    if (s_last) cnt[0] = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  CgVec cg = F.cg;
+  const int *gate = F.gate;
+  if (a.table) {
+    float *cgst = reinterpret_cast<float *>(a.table[5 * a.n_obj + o]);
+    cg.f = reinterpret_cast<float *>(a.table[4 * a.n_obj + o]);
+    cg.p = cgst; cg.rprev = cgst + cg.n; cg.rho = cgst + 2 * cg.n; cg.hasp = cgst + 2 * cg.n + 1;
+    cg.r += (int64_t)o * 3 * cg.n; cg.x += (int64_t)o * 3 * cg.n; cg.q += (int64_t)o * 3 * cg.n;
+    gate = reinterpret_cast<const int *>(a.table[6 * a.n_obj + o]);
+  }
+  cg.partial = gs;                                   // the vector step sums the group rows
+  cg.cap = ngrp;
+  if (gate && gate[0] < F.min_px) return;
+  cg_vector_step_cta<GM_THREADS, 4>(cg, F.mode, red);
 }
 
 static size_t gm_smem(int c) {
@@ -415,20 +491,25 @@ bool gn_apply_mma_supported(int c, int h, int w) {
   return c == GM_MAXC && w >= 8 && 3 * (w + 1) <= 2 * GM_BLK && h >= 1 && h * w < 65536 && gm_smem(c) <= 227 * 1024;
 }
 
-int gn_apply_mma_launch(const GaArgs &a, const GcFuse &fuse, cudaStream_t st) {
+int gn_apply_mma_launch(const GaArgs &a, const GcFuse &fuse, const GnListWs &ws, cudaStream_t st) {
   GcParams P;
   const int hw = a.h * a.w;
   P.ntiles = gc_ntiles(hw); P.nchunks = gc_nchunks(hw); P.tile_bytes = 2 * a.c * 128; P.slots = GM_SLOTS;
   P.image_bytes = gc_sample_bytes(a.c, hw);
   const size_t smem = gm_smem(a.c);
-  static bool configured = false;
-  if (!configured) {
+  static int nsm = 0;
+  if (nsm == 0) {
     cudaError_t e = cudaFuncSetAttribute(gn_apply_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("gn_apply_mma: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return FRTM_ELAUNCH; }
-    configured = true;
+    int dev = 0, v = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    nsm = v < 160 ? v : 160;                           // the unit rows are sized for up to 160 extra part units
   }
-  const dim3 grid(a.cap, a.table ? a.n_obj : 1);
-  gn_apply_mma_kernel<<<grid, GM_THREADS, smem, st>>>(a, P, fuse);
+  GmUnits Q;
+  Q.ws = ws; Q.nsm = nsm;
+  // at most (n_obj * cap) whole samples + nsm part units; CTAs beyond the launch's unit count exit at once
+  gn_apply_mma_kernel<<<a.n_obj * a.cap + nsm, GM_THREADS, smem, st>>>(a, P, fuse, Q);
   FRTM_CHECK_LAUNCH("gn_apply_mma");
   return FRTM_OK;
 }

@@ -996,11 +996,70 @@ extern "C" int frtm_memory_insert(const float *feat, int feat_elems, const float
 }
 
 // ---- filter-only GN/CG ------------------------------------------------------------------------------------------
+namespace frtm {
+// ---- work list + workspace of the list-driven operator kernels -------------------------------------------------------
+__global__ void __launch_bounds__(256) gn_build_items_kernel(const float *sw_single, const long long *table, int n_obj, int cap,
+                                                             ClList L) {
+  __shared__ int wsum[8];
+  __shared__ int base_s;
+  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+  if (tid == 0) base_s = 0;
+  __syncthreads();
+  const int total = n_obj * cap;
+  for (int e0 = 0; e0 < total; e0 += 256) {
+    const int e = e0 + tid;
+    const int o = e < total ? e / cap : 0, slot = e < total ? e - o * cap : 0;
+    const float *sw = table ? reinterpret_cast<const float *>(table[3 * n_obj + o]) : sw_single;
+    const bool act = e < total && sw[slot] != 0.f;
+    const unsigned m = __ballot_sync(0xffffffffu, act);
+    const int before = __popc(m & ((1u << lane) - 1u));
+    if (lane == 0) wsum[wp] = __popc(m);
+    __syncthreads();
+    int woff = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { if (k < wp) woff += wsum[k]; tot += wsum[k]; }
+    const int idx = base_s + woff + before;
+    if (act) L.items[idx] = ((uint32_t)o << 16) | (uint32_t)slot;
+    if (e < total && slot == 0) L.hdr[1 + o] = idx;
+    __syncthreads();
+    if (tid == 0) base_s += tot;
+    __syncthreads();
+  }
+  if (tid == 0) { L.hdr[0] = base_s; L.hdr[1 + n_obj] = base_s; }
+}
+
+
+int gn_items_build(const GaArgs &a, ClList list, cudaStream_t st) {
+  gn_build_items_kernel<<<1, 256, 0, st>>>(a.sw, a.table, a.n_obj, a.cap, list);
+  FRTM_CHECK_LAUNCH("gn_build_items");
+  return FRTM_OK;
+}
+static int64_t gn_list_ngrp(int cap) { return (cap + 160 + GC_RGROUP - 1) / GC_RGROUP; }
+int64_t gn_list_workspace_bytes(int n_obj, int cap, int c) {
+  const int64_t n = (int64_t)c * 9, ngrp = gn_list_ngrp(cap);
+  // rows [n_obj*cap + 160*n_obj][n] | gsum [n_obj][ngrp][n] | counters [n_obj][1 + ngrp] | tickets [n_obj] | hdr [2 + n_obj] | items
+  return (((int64_t)n_obj * (cap + 160)) * n + n_obj * ngrp * n + n_obj * (1 + ngrp) + n_obj + (2 + n_obj) + (int64_t)n_obj * cap + 16) * 4;
+}
+GnListWs gn_list_workspace(float *base, int n_obj, int cap, int c) {
+  const int64_t n = (int64_t)c * 9, ngrp = gn_list_ngrp(cap);
+  GnListWs w;
+  w.rows = base;
+  w.gsum = base + ((int64_t)n_obj * (cap + 160)) * n;
+  w.counters = reinterpret_cast<int *>(w.gsum + n_obj * ngrp * n);
+  w.tickets = w.counters + n_obj * (1 + ngrp);
+  w.list.hdr = w.tickets + n_obj;
+  w.list.items = reinterpret_cast<uint32_t *>(w.list.hdr + 2 + n_obj);
+  w.ngrp_max = (int)ngrp;
+  return w;
+}
+
+}  // namespace frtm
+
 extern "C" int64_t frtm_gn_update_workspace(int cap, int c, int h, int w) {
   const int64_t n = (int64_t)c * 9, hw = (int64_t)h * w;
   // s[cap][hw] | v[cap][hw] | partial[cap][n] | r[n] | x[n] | q[n] | tickets[1 + ngroups] | group sums[ngroups][n]
   const int64_t ngrp = (cap + GC_RGROUP - 1) / GC_RGROUP;
-  return (2 * cap * hw + cap * n + 3 * n + 64 + (1 + ngrp) + 8 + ngrp * n) * (int64_t)sizeof(float) + gn_apply_cl_workspace(1, cap, c);
+  return (2 * cap * hw + cap * n + 3 * n + 64 + (1 + ngrp) + 8 + ngrp * n) * (int64_t)sizeof(float) + gn_list_workspace_bytes(1, cap, c);
 }
 
 extern "C" int64_t frtm_gn_operator_kind(int c, int h, int w) {
@@ -1090,15 +1149,21 @@ static int gn_update_impl(const float *samples, const __half *samples_split, con
       return FRTM_ELAUNCH;
     }
   }
-  // the cluster operator's own region sits behind the n_obj older layouts: rows per (object, cluster), tickets, work list
-  float *ws_cl = workspace + (n_obj * (frtm_gn_update_workspace(cap, c, h, w) - gn_apply_cl_workspace(1, cap, c))) / (int64_t)sizeof(float);
-  if (use_cl) {
-    if (int rc = gn_apply_cl_prepare(ga, ws_cl, st)) return rc;
+  // the list-driven operators' region sits behind the n_obj older layouts: rows per unit / (object, cluster), group sums,
+  // tickets, the work list of this update (built once: the sample weights do not change between operator applications)
+  float *ws_list = workspace + (n_obj * (frtm_gn_update_workspace(cap, c, h, w) - gn_list_workspace_bytes(1, cap, c))) / (int64_t)sizeof(float);
+  const GnListWs lws = gn_list_workspace(ws_list, n_obj, cap, c);
+  if (use_cl || use_mma) {
+    if (cudaMemsetAsync(lws.counters, 0, sizeof(int) * ((int64_t)n_obj * (2 + lws.ngrp_max)), st) != cudaSuccess) {
+      set_error("gn_update: cudaMemsetAsync failed");
+      return FRTM_ELAUNCH;
+    }
+    if (int rc = gn_items_build(ga, lws.list, st)) return rc;
   }
   auto launch_apply = [&]() -> int {
     if (use_tc) {
-      const int rc = use_cl ? gn_apply_cl_launch(ga, fuse, ws_cl, st)
-                            : use_mma ? gn_apply_mma_launch(ga, fuse, st) : gn_apply_tc_launch(ga, fuse, st);
+      const int rc = use_cl ? gn_apply_cl_launch(ga, fuse, lws, st)
+                            : use_mma ? gn_apply_mma_launch(ga, fuse, lws, st) : gn_apply_tc_launch(ga, fuse, st);
       if (rc == FRTM_OK) count_launch(-1);                  // counted again by FRTM_CHECK_LAUNCH at the call site
       return rc;
     }

@@ -57,13 +57,32 @@ bool gn_apply_tc_supported(int c, int h, int w);
 bool gn_apply_mma_supported(int c, int h, int w);
 struct GcFuse;
 int gn_apply_tc_launch(const GaArgs &a, const GcFuse &fuse, cudaStream_t st);
-int gn_apply_mma_launch(const GaArgs &a, const GcFuse &fuse, cudaStream_t st);
+// Work list of an update, built once per update by gn_items_build (the sample weights do not change between its operator
+// applications): hdr[0] = U (active samples of all objects), hdr[1 + o] = first item of object o (hdr[1 + n_obj] = U),
+// items[u] = (object << 16) | slot, object-major, slots ascending.
+struct ClList {
+  int *hdr;
+  uint32_t *items;
+};
+int gn_items_build(const GaArgs &a, ClList list, cudaStream_t st);
+
+// Workspace of the list-driven operator kernels (floats): see gn_list_workspace() in target_model.cu.
+struct GnListWs {
+  ClList list;
+  float *rows;        // sliding-window kernel: one row per unit [n_obj*cap + 160][n]; cluster kernel: [n_obj][160][n]
+  float *gsum;        // [n_obj][ngrp_max][n] group sums (sliding-window kernel)
+  int *counters;      // [n_obj][1 + ngrp_max] tickets, zero between launches
+  int *tickets;       // [n_obj] (cluster kernel)
+  int ngrp_max;
+};
+int64_t gn_list_workspace_bytes(int n_obj, int cap, int c);
+GnListWs gn_list_workspace(float *base, int n_obj, int cap, int c);
+
 // gn_apply_cl_*: one sample per thread-block cluster, resident on chip through its three phases (gn_apply_cl.cu); persistent
 // clusters over a work list built once per update (prepare), own workspace (rows per (object, cluster), tickets, the list)
 bool gn_apply_cl_supported(int c, int h, int w);
-int64_t gn_apply_cl_workspace(int n_obj, int cap, int c);
-int gn_apply_cl_prepare(const GaArgs &a, float *ws, cudaStream_t st);
-int gn_apply_cl_launch(const GaArgs &a, const GcFuse &fuse, float *ws, cudaStream_t st);
+int gn_apply_cl_launch(const GaArgs &a, const GcFuse &fuse, const GnListWs &ws, cudaStream_t st);
+int gn_apply_mma_launch(const GaArgs &a, const GcFuse &fuse, const GnListWs &ws, cudaStream_t st);
 
 // One work item of the image build.  Items [0, ntiles*c*8): 8 consecutive pixels of channel row r in tile j -> one
 // 16-byte chunk in each plane.  Remaining items: 4 consecutive pixels of one stencil / uty row of one chunk.
