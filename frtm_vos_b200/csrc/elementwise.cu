@@ -703,6 +703,102 @@ static bool upsample_tapsum_fits(int h, int w, int H, int W) {
   const int nuy = (int)((FT_TY + 2) * sy) + 3, nux = (int)((FT_TX + 2) * sx) + 3;
   return nuy <= FT_UY && nux <= FT_UX && nuy / 2 + 5 <= FT_NTY && nux / 2 + 5 <= FT_NTX;
 }
+
+// Bicubic resize (ATen upsample_bicubic2d, align_corners=False, A = -0.75): source = scale (dst + 0.5) - 0.5 WITHOUT the
+// clamp at 0 the bilinear mode has, 4 x 4 taps at floor(source) - 1 .. + 2 with indices clamped to the image.
+__device__ __forceinline__ void cubic_coeffs(float t, float (&w)[4]) {
+  const float A = -0.75f;
+  const float x0 = t + 1.f, x3 = 2.f - t, u = 1.f - t;
+  w[0] = ((A * x0 - 5.f * A) * x0 + 8.f * A) * x0 - 4.f * A;
+  w[1] = ((A + 2.f) * t - (A + 3.f)) * t * t + 1.f;
+  w[2] = ((A + 2.f) * u - (A + 3.f)) * u * u + 1.f;
+  w[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
+}
+__global__ void __launch_bounds__(256) resize_bicubic_kernel(const float *__restrict__ x, int B, int H, int W, int C, int ldx,
+                                                             float *__restrict__ y, int Ho, int Wo, int ldy, float sh, float sw) {
+  const int C4 = C >> 2;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)B * Ho * Wo * C4) return;
+  const int c4 = (int)(idx % C4);
+  int64_t r = idx / C4;
+  const int ox = (int)(r % Wo); r /= Wo;
+  const int oy = (int)(r % Ho);
+  const int b = (int)(r / Ho);
+  const float fy = sh * ((float)oy + 0.5f) - 0.5f, fx = sw * ((float)ox + 0.5f) - 0.5f;
+  const float fy0 = floorf(fy), fx0 = floorf(fx);
+  float wy[4], wx[4];
+  cubic_coeffs(fy - fy0, wy);
+  cubic_coeffs(fx - fx0, wx);
+  const int iy = (int)fy0, ix = (int)fx0;
+  const float *xb = x + (int64_t)b * H * W * ldx + c4 * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int yy = min(max(iy - 1 + j, 0), H - 1);
+    float4 row = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int xx = min(max(ix - 1 + i, 0), W - 1);
+      const float4 v = *reinterpret_cast<const float4 *>(xb + ((int64_t)yy * W + xx) * ldx);
+      row.x = fmaf(wx[i], v.x, row.x); row.y = fmaf(wx[i], v.y, row.y); row.z = fmaf(wx[i], v.z, row.z); row.w = fmaf(wx[i], v.w, row.w);
+    }
+    acc.x = fmaf(wy[j], row.x, acc.x); acc.y = fmaf(wy[j], row.y, acc.y); acc.z = fmaf(wy[j], row.z, acc.z); acc.w = fmaf(wy[j], row.w, acc.w);
+  }
+  *reinterpret_cast<float4 *>(y + (((int64_t)b * Ho + oy) * Wo + ox) * ldy + c4 * 4) = acc;
+}
+
+
+// labels[p] = lut[ argmax softmax( p / (1 - p) ) ] over {background = min_i (1 - p_i), p_1 .. p_N} after the clamp to
+// [1e-7, 1 - 1e-7] — the single-stage label rule of model/tracker.py:143-150 and ytvos_validation/tracker.py:53-62,106-107
+// applied to RAW object probabilities (first maximum wins, as torch.argmax)
+__global__ void __launch_bounds__(256) labels_from_probs_kernel(const float *__restrict__ src, int N, int HW, const uint8_t *__restrict__ lut,
+                                                                uint8_t *__restrict__ labels) {
+  src += (int64_t)blockIdx.y * N * HW;
+  labels += (int64_t)blockIdx.y * HW;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  const float lo = 1e-7f, hi = 1.f - 1e-7f;
+  float bg = INFINITY;
+  for (int n = 0; n < N; ++n) bg = fminf(bg, 1.f - fminf(fmaxf(src[(int64_t)n * HW + p], lo), hi));
+  const float z0 = bg / (1.f - bg);
+  float mx = z0;
+  for (int n = 0; n < N; ++n) {
+    const float c = fminf(fmaxf(src[(int64_t)n * HW + p], lo), hi);
+    mx = fmaxf(mx, c / (1.f - c));
+  }
+  float den = expf(z0 - mx);
+  for (int n = 0; n < N; ++n) {
+    const float c = fminf(fmaxf(src[(int64_t)n * HW + p], lo), hi);
+    den += expf(c / (1.f - c) - mx);
+  }
+  float best = expf(z0 - mx) / den;
+  int lab = 0;
+  for (int n = 0; n < N; ++n) {
+    const float c = fminf(fmaxf(src[(int64_t)n * HW + p], lo), hi);
+    const float sv = expf(c / (1.f - c) - mx) / den;
+    if (sv > best) { best = sv; lab = n + 1; }
+  }
+  labels[p] = lut[lab];
+}
+
+
+// out[i] = x[i] > thr ? 1 : 0   (binary training labels of the "thresh" update method, ytvos_validation/discriminator.py:364-367)
+__global__ void __launch_bounds__(256) threshold_kernel(const float *__restrict__ x, int64_t n, float thr, float *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = x[i] > thr ? 1.f : 0.f;
+}
+
+
+// out[n][p] = sigmoid(logit[n][p]) * (1 - suppress[p])   (per-object probabilities before the merge,
+// ytvos_validation/tracker.py:133-139,176-178)
+__global__ void __launch_bounds__(256) sigmoid_suppress_kernel(const float *__restrict__ logits, const uint8_t *__restrict__ suppress,
+                                                               int N, int HW, float *__restrict__ out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  const float keep = suppress ? (float)(1 - (int)suppress[p]) : 1.f;
+  for (int n = 0; n < N; ++n) out[(int64_t)n * HW + p] = (1.f / (1.f + expf(-logits[(int64_t)n * HW + p]))) * keep;
+}
+
 }  // namespace frtm
 
 using namespace frtm;
@@ -764,6 +860,16 @@ extern "C" int frtm_resize_bilinear_nhwc(const float *x, int B, int H, int W, in
     resize_bilinear_kernel<1><<<cdiv(total, 256), 256, 0, st>>>(x, B, H, W, C, ldx, y, Ho, Wo, ldy, y_coff, accumulate, sh, sw);
   }
   FRTM_CHECK_LAUNCH("resize_bilinear");
+  return FRTM_OK;
+}
+
+extern "C" int frtm_resize_bicubic_nhwc(const float *x, int B, int H, int W, int C, int ldx, float *y, int Ho, int Wo, int ldy,
+                                        void *stream) {
+  FRTM_REQUIRE(x && y && B > 0 && C > 0 && C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "resize_bicubic: C, ldx, ldy must be multiples of 4");
+  const int64_t total = (int64_t)B * Ho * Wo * (C / 4);
+  resize_bicubic_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, C, ldx, y, Ho, Wo, ldy, (float)H / (float)Ho,
+                                                                            (float)W / (float)Wo);
+  FRTM_CHECK_LAUNCH("resize_bicubic");
   return FRTM_OK;
 }
 
@@ -849,6 +955,28 @@ extern "C" int frtm_merge_masks(const float *src, uint64_t logit_mask, const uin
     merge_masks_kernel<<<cdiv(HW, 256), 256, 0, (cudaStream_t)stream>>>(src, (unsigned long long)logit_mask, suppress, N,
                                                                         HW, lut, single_object, masks, labels, counts, 0);
   FRTM_CHECK_LAUNCH("merge_masks");
+  return FRTM_OK;
+}
+
+extern "C" int frtm_sigmoid_suppress(const float *logits, const uint8_t *suppress, int N, int HW, float *out, void *stream) {
+  FRTM_REQUIRE(logits && out && N > 0 && HW > 0, "sigmoid_suppress: bad arguments");
+  sigmoid_suppress_kernel<<<cdiv(HW, 256), 256, 0, (cudaStream_t)stream>>>(logits, suppress, N, HW, out);
+  FRTM_CHECK_LAUNCH("sigmoid_suppress");
+  return FRTM_OK;
+}
+
+extern "C" int frtm_threshold_f32(const float *x, int64_t n, float thr, float *out, void *stream) {
+  FRTM_REQUIRE(x && out && n >= 0, "threshold_f32: bad arguments");
+  if (n == 0) return FRTM_OK;
+  threshold_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, thr, out);
+  FRTM_CHECK_LAUNCH("threshold_f32");
+  return FRTM_OK;
+}
+
+extern "C" int frtm_labels_from_probs(const float *src, int F, int N, int HW, const uint8_t *lut, uint8_t *labels, void *stream) {
+  FRTM_REQUIRE(src && lut && labels && F > 0 && N > 0 && HW > 0, "labels_from_probs: bad arguments");
+  labels_from_probs_kernel<<<dim3(cdiv(HW, 256), F), 256, 0, (cudaStream_t)stream>>>(src, N, HW, lut, labels);
+  FRTM_CHECK_LAUNCH("labels_from_probs");
   return FRTM_OK;
 }
 

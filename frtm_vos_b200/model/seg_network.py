@@ -74,10 +74,25 @@ class BackwardCompatibleUpsampler(_Params):
         self.conv2 = _conv(in_channels // 2, 1, 3)
 
 
+class Upsampler(_Params):
+    """The all-frames YouTubeVOS variant's upsampler (``ytvos_validation/seg_network.py:62-74``): true bicubic x2 -> conv1 +
+    ReLU -> true bicubic to the image size -> conv2.  Same parameter names as the back-compat module."""
+
+    def __init__(self, in_channels=64):
+        super().__init__()
+        self.conv1 = _conv(in_channels, in_channels // 2, 3)
+        self.conv2 = _conv(in_channels // 2, 1, 3)
+
+
 class SegNetwork(nn.Module):
 
-    def __init__(self, in_channels=1, out_channels=32, ft_channels=None, use_bn=False):
+    def __init__(self, in_channels=1, out_channels=32, ft_channels=None, use_bn=False, upsampler="backcompat"):
+        """``upsampler``: "backcompat" = ``BackwardCompatibleUpsampler`` (``model/seg_network.py:129-146``, the released
+        checkpoints); "bicubic" = ``Upsampler`` of ``ytvos_validation/seg_network.py:62-74``."""
         super().__init__()
+        if upsampler not in ("backcompat", "bicubic"):
+            raise ValueError("upsampler must be 'backcompat' or 'bicubic'")
+        self.upsampler = upsampler
         assert ft_channels is not None
         if in_channels != 1:
             raise ValueError("the fused TSE kernels expect a single score channel (in_channels=1)")
@@ -90,7 +105,7 @@ class SegNetwork(nn.Module):
             self.RRB1[L] = RRB(out_channels, use_bn=use_bn)
             self.CAB[L] = CAB(out_channels, i == 0)   # reference: L == 'layer5', i.e. the first (deepest) level
             self.RRB2[L] = RRB(out_channels, use_bn=use_bn)
-        self.project = BackwardCompatibleUpsampler(out_channels)
+        self.project = BackwardCompatibleUpsampler(out_channels) if upsampler == "backcompat" else Upsampler(out_channels)
         self._packed = None
         self._bufs: Dict[tuple, torch.Tensor] = {}
 
@@ -199,6 +214,13 @@ class SegNetwork(nn.Module):
         # conv2 is linear and so is the bicubic/bilinear chain in front of it: the 32 channels are contracted to the 9 tap
         # maps of conv2 at 240x428 in conv1's epilogue (the 32-channel tensor is never written); one kernel then does
         # bicubic x2 -> bilinear -> sum of the 9 shifted maps.  The x2 in front of conv1 writes conv1's input planes directly.
+        if self.upsampler == "bicubic":
+            # ytvos_validation Upsampler: the same contraction of conv2 before the (linear) second resize, with true bicubic
+            # interpolation (A = -0.75, align_corners=False) in both places
+            h, w = x.shape[1:3]
+            u = ops.split_f16(ops.resize_bicubic(x, (2 * h, 2 * w)))
+            t12 = ops.conv2d_tc(u, P["up1"], relu=True, out_f32=False, tapw=P["up2_w"])["tap"]
+            return ops.shift_sum9(ops.resize_bicubic(t12, image_size[-2:]), P["up2_b"])
         u = ops.pyrup_bicubic(x, split=True)
         t12 = ops.conv2d_tc(u, P["up1"], relu=True, out_f32=False, tapw=P["up2_w"])["tap"]
         return ops.upsample_tapsum(t12, P["up2_b"], image_size[-2:])

@@ -108,6 +108,16 @@ def resize_bilinear(x: torch.Tensor, size, channels: Optional[int] = None, out: 
     return y
 
 
+def resize_bicubic(x: torch.Tensor, size, channels: Optional[int] = None) -> torch.Tensor:
+    """F.interpolate(mode='bicubic', align_corners=False) of an NHWC tensor (C % 4 == 0)."""
+    B, H, W, ldx = x.shape
+    C = channels or ldx
+    Ho, Wo = int(size[0]), int(size[1])
+    y = torch.empty((B, Ho, Wo, C), device=x.device, dtype=torch.float32)
+    lib().resize_bicubic_nhwc(ptr(x), B, H, W, C, ldx, ptr(y), Ho, Wo, C, stream())
+    return y
+
+
 def stem_weight_as_1x1(weight: torch.Tensor) -> torch.Tensor:
     """conv1.weight (64,3,7,7) -> (64,192,1,1) in the k order of ``stem_patches``: k = ky*24 + c*8 + kx."""
     cout = weight.shape[0]
@@ -223,6 +233,30 @@ def merge_masks_frames(src: torch.Tensor, logit_mask: int, lut: torch.Tensor, si
     return masks, labels
 
 
+def sigmoid_suppress(logits: torch.Tensor, suppress: Optional[torch.Tensor]) -> torch.Tensor:
+    """logits (N,H,W), suppress (H,W) uint8 or None -> sigmoid(logits) * (1 - suppress)."""
+    N, H, W = logits.shape
+    out = torch.empty_like(logits)
+    lib().sigmoid_suppress(ptr(logits.contiguous()), ptr(suppress), N, H * W, ptr(out), stream())
+    return out
+
+
+def threshold(x: torch.Tensor, thr: float = 0.5) -> torch.Tensor:
+    """(x > thr) as float32, same shape."""
+    x = x.contiguous()
+    out = torch.empty_like(x, dtype=torch.float32)
+    lib().threshold_f32(ptr(x), x.numel(), float(thr), ptr(out), stream())
+    return out
+
+
+def labels_from_probs(probs: torch.Tensor, lut: torch.Tensor) -> torch.Tensor:
+    """probs (F,N,H,W) raw object probabilities -> labels (F,H,W) uint8 (single-stage softmax/argmax rule)."""
+    F, N, H, W = probs.shape
+    labels = torch.empty((F, H, W), device=probs.device, dtype=torch.uint8)
+    lib().labels_from_probs(ptr(probs.contiguous()), F, N, H * W, ptr(lut), ptr(labels), stream())
+    return labels
+
+
 def corr3x3(x: torch.Tensor, filt: torch.Tensor, index: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x (NB,c,h,w) NCHW, filt (NF,c,3,3) -> (NB,h,w); sample n uses filter index[n] (default 0)."""
     NB, c, h, w = x.shape
@@ -253,6 +287,14 @@ def upsample_tapsum(t12: torch.Tensor, bias, image_size) -> torch.Tensor:
     else:
         u = resize_bilinear(pyrup_bicubic(t12), (H, W))
         lib().shift_sum9(ptr(u), B, H, W, ptr(bias), ptr(out), stream())
+    return out
+
+
+def shift_sum9(t12: torch.Tensor, bias) -> torch.Tensor:
+    """Full-resolution tap maps (B,H,W,12) -> sum of the 9 tap-shifted maps (zero padding) + bias -> (B,H,W)."""
+    B, H, W, _ = t12.shape
+    out = torch.empty((B, H, W), device=t12.device, dtype=torch.float32)
+    lib().shift_sum9(ptr(t12), B, H, W, ptr(bias), ptr(out), stream())
     return out
 
 

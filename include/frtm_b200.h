@@ -117,6 +117,10 @@ int frtm_maxpool3x3s2_nhwc(const float *x, int B, int H, int W, int C, float *y,
  * channel stride ldy.  If accumulate != 0 the result is added to y.  (lib/utils.py:33-35, seg_network.py:39,144) */
 int frtm_resize_bilinear_nhwc(const float *x, int B, int H, int W, int C, int ldx, float *y, int Ho, int Wo, int ldy,
                               int y_coff, int accumulate, void *stream);
+/* Bicubic resize (ATen upsample_bicubic2d semantics: align_corners=False, A = -0.75, clamped 4 x 4 taps) of an
+ * NHWC tensor, C % 4 == 0.  The `Upsampler` of the YouTubeVOS all-frames variant (ytvos_validation/seg_network.py:62-74). */
+int frtm_resize_bicubic_nhwc(const float *x, int B, int H, int W, int C, int ldx, float *y, int Ho, int Wo, int ldy,
+                             void *stream);
 
 /* Fixed x2 bicubic pyramid upsample (replicate pad 2, 4 depthwise 4x4 phases, crop 1) NHWC (B,H,W,C)->(B,2H,2W,C)
  * (model/seg_network.py:75-126). */
@@ -178,6 +182,16 @@ int frtm_merge_masks(const float *src, uint64_t logit_mask, const uint8_t *suppr
  * a block). */
 int frtm_merge_masks_frames(const float *src, int F, uint64_t logit_mask, int N, int HW, const uint8_t *lut, int single_object,
                             float *masks, uint8_t *labels, int *counts, int counts_stride, void *stream);
+/* Label maps from RAW object probabilities src (F,N,HW), one stage: clamp to [1e-7, 1 - 1e-7], background = min_i (1 - p_i),
+ * softmax(p / (1 - p)), first maximum -> lut (model/tracker.py:143-150; ytvos_validation/tracker.py:53-62,106-107, where the
+ * rule runs once over all frames of a sequence after the ground truth has been re-inserted). */
+int frtm_labels_from_probs(const float *src, int F, int N, int HW, const uint8_t *lut, uint8_t *labels, void *stream);
+/* out[i] = x[i] > thr ? 1 : 0 — the binary training labels of the "thresh" update method of the all-frames variant
+ * (ytvos_validation/discriminator.py:364-367). */
+int frtm_threshold_f32(const float *x, int64_t n, float thr, float *out, void *stream);
+/* out (N,HW) = sigmoid(logits) * (1 - suppress): the per-object probabilities the all-frames variant returns per frame, with
+ * the pixels of objects that start on this frame suppressed (ytvos_validation/tracker.py:133-139,176-178). */
+int frtm_sigmoid_suppress(const float *logits, const uint8_t *suppress, int N, int HW, float *out, void *stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Target model: correlation, memory, GN/CG  (model/discriminator.py, model/memory.py, model/optimizer.py)

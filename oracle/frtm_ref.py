@@ -147,7 +147,7 @@ def _rrb(sd, key, x, use_bn):
 
 def seg_forward(sd: Dict[str, Tensor], scores: Tensor, features: Dict[str, Tensor], image_size,
                 layers: Sequence[str] = ("layer5", "layer4", "layer3", "layer2"), use_bn: bool = True,
-                taps: Optional[dict] = None) -> Tensor:
+                taps: Optional[dict] = None, upsampler: str = "backcompat") -> Tensor:
     """scores (B,1,h,w) + feature maps -> logits (B,1,H,W) (model/seg_network.py:176-189).
 
     ``sd`` keys are un-prefixed (``TSE.layer4.reduce.0.weight`` …).
@@ -172,11 +172,21 @@ def seg_forward(sd: Dict[str, Tensor], scores: Tensor, features: Dict[str, Tenso
         x = _rrb(sd, "RRB2.%s" % L, h, use_bn)
         if taps is not None:
             taps[L] = x
+    if upsampler == "bicubic":
+        return upsampler_bicubic(sd, x, image_size)
     # BackwardCompatibleUpsampler (:129-146)
     x = pyr_up_bicubic(x)
     x = F.relu(_conv(sd, "project.conv1", x, 3))
     x = pyr_up_bicubic(x)
     x = F.interpolate(x, tuple(int(v) for v in image_size[-2:]), mode="bilinear", align_corners=False)
+    return _conv(sd, "project.conv2", x, 3)
+
+
+def upsampler_bicubic(sd: Dict[str, Tensor], x: Tensor, image_size) -> Tensor:
+    """``Upsampler`` of the all-frames YouTubeVOS variant (ytvos_validation/seg_network.py:62-74)."""
+    x = F.interpolate(x, (2 * x.shape[-2], 2 * x.shape[-1]), mode="bicubic", align_corners=False)
+    x = F.relu(_conv(sd, "project.conv1", x, 3))
+    x = F.interpolate(x, tuple(int(v) for v in image_size[-2:]), mode="bicubic", align_corners=False)
     return _conv(sd, "project.conv2", x, 3)
 
 
@@ -412,14 +422,15 @@ class TargetModelRef:
         self.current_sample = cft
         return F.conv2d(cft, self.F, None, 1, 1)
 
-    def update(self, train_y: Tensor) -> bool:
-        """discriminator.py:208-227; returns True when a GN update ran."""
+    def update(self, train_y: Tensor, method: str = "soft") -> bool:
+        """discriminator.py:208-227; returns True when a GN update ran.  ``method='thresh'``: the all-frames variant stores
+        the binarised mask as the training label (ytvos_validation/discriminator.py:364-367)."""
         if self.current_sample is None:
             return False
         if (train_y > 0.5).sum() < 10:
             return False
         ys = (train_y > 0.5).float()
-        self.memory.insert(self.current_sample, train_y, pixel_weights(ys, self.tf))
+        self.memory.insert(self.current_sample, ys if method == "thresh" else train_y, pixel_weights(ys, self.tf))
         if self.frame_num % self.train_skipping != 0:
             return False
         self.optimizer.run(self.update_iters)
@@ -547,3 +558,82 @@ class TrackerRef:
             torch.cuda.synchronize()
         dt = time() - t0
         return outputs, len(sequence) / dt
+
+
+# --------------------------------------------------------------------------------------
+# f4 — the all-frames YouTubeVOS variant of the driver (ytvos_validation/tracker.py:53-207)
+# --------------------------------------------------------------------------------------
+def merge_segmentations(fg: Tensor) -> Tensor:
+    """ytvos_validation/tracker.py:53-62 — fg (N, ...) object probabilities -> softmax over {background, objects}."""
+    fg = torch.clamp(fg, 1e-7, 1 - 1e-7)
+    bg = torch.min((1 - fg), dim=0, keepdim=True)[0]
+    p = torch.cat((bg, fg), dim=0)
+    return F.softmax(p / (1 - p), dim=0)
+
+
+class YtvosTrackerRef(TrackerRef):
+    """Every object initialised up front from its own first frame, raw probabilities per frame, ground truth re-inserted,
+    ONE merge over all frames (``:82-207``); bicubic ``Upsampler``; ``update_method='thresh'``."""
+
+    def __init__(self, *a, update_method: str = "thresh", **k):
+        super().__init__(*a, **k)
+        self.update_method = update_method
+
+    def _track_frame(self, image: Tensor, index: Dict[int, int], n_obj: int) -> Tensor:
+        im_size = image.shape[-2:]
+        out = torch.zeros((n_obj, *im_size), device=self.device)
+        live = [t for t in self.targets.values() if t["start_frame"] < self.current_frame]
+        if not live:
+            return out
+        feats = self._features(image)
+        ys = {}
+        for t in live:
+            with torch.no_grad():
+                s = t["model"].apply(feats[self.layer])
+                logits = seg_forward(self.seg, s, feats, im_size, self.seg_layers, self.use_bn, upsampler="bicubic")
+            if "logits" in self.hooks:
+                self.hooks["logits"](self.current_frame, t["id"], s, logits)
+            ys[t["id"]] = torch.sigmoid(logits)[0, 0]
+        if self.current_frame > 0:                               # update (:133-161)
+            upd = torch.zeros((n_obj, *im_size), device=self.device)
+            for t1 in live:
+                for t2 in self.targets.values():
+                    if t1["id"] != t2["id"] and t2["start_frame"] == self.current_frame:
+                        ys[t1["id"]] = ys[t1["id"]] * (1 - t2["start_mask"].reshape(*im_size)).float()
+                upd[index[t1["id"]]] = ys[t1["id"]]
+            segs = merge_segmentations(upd)
+            inds = segs.argmax(dim=0)
+            for i in range(n_obj):
+                m = inds == (i + 1)
+                upd[i] = torch.where(m, segs[i + 1], torch.zeros_like(segs[i + 1]))
+            for t in live:
+                t["model"].update(upd[index[t["id"]]].unsqueeze(0).unsqueeze(0), method=self.update_method)
+        for t in live:
+            out[index[t["id"]]] = ys[t["id"]]
+        return out
+
+    def run_sequence(self, sequence):
+        from time import time
+        ids = list(sequence.obj_ids)
+        items = [sequence[i] for i in range(len(sequence))]
+        first = {}
+        for i, (im, lb, new) in enumerate(items):
+            for oid in new:
+                first[oid] = i
+        self.targets = OrderedDict()
+        t0 = time()
+        for f0 in sorted(set(first.values())):
+            self.current_frame = f0
+            self.initialize(items[f0][0].to(self.device), items[f0][1].to(self.device), [o for o in ids if first[o] == f0])
+        index = {o: k for k, o in enumerate(ids)}
+        outs = []
+        for i in range(len(items)):
+            self.current_frame = i
+            outs.append(self._track_frame(items[i][0].to(self.device), index, len(ids)))
+        out = torch.stack(outs)                                   # (T, N, H, W)
+        for o in ids:
+            out[first[o], index[o]] = (items[first[o]][1].to(self.device)[0] == o).float()
+        segs = merge_segmentations(out.permute(1, 0, 2, 3))
+        lut = torch.tensor([0] + ids, dtype=torch.uint8, device=self.device)
+        labels = lut[segs.argmax(dim=0)]                          # (T, H, W)
+        return [labels[i].unsqueeze(0) for i in range(len(items))], len(items) / (time() - t0)

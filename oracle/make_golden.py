@@ -260,6 +260,42 @@ def gen_eval(ref):
     print("eval: %d mask pairs (J mean %.3f, F mean %.3f), %d score vectors" % (len(pairs), J.mean(), F.mean(), len(vecs)))
 
 
+def gen_ytvos(ref):
+    """Pieces of the all-frames YouTubeVOS variant (ytvos_validation/): the bicubic ``Upsampler``, ``merge_segmentations``
+    and the hinge weights / binary labels of the 'thresh' update method, executed from the reference's own modules."""
+    import importlib
+    sn = importlib.import_module("ytvos_validation.seg_network")
+    tr = importlib.import_module("ytvos_validation.tracker")
+    dc = importlib.import_module("ytvos_validation.discriminator")
+    case = GI.ytvos_case()
+    up = sn.Upsampler(64)
+    up.load_state_dict({k[len("project."):]: v for k, v in case["up"].items()})
+    with torch.no_grad():
+        logits = up(case["x"], case["image_size"])
+    mine = R.upsampler_bicubic(case["up"], case["x"], case["image_size"])
+    assert torch.equal(logits, mine), "Upsampler restatement differs from the reference"
+    segs, ids = tr.Tracker.merge_segmentations(case["probs"], [3, 5, 9])
+    mine = R.merge_segmentations(case["probs"])
+    assert torch.equal(segs, mine) and ids.tolist() == [0, 3, 5, 9]
+    labels = ids[segs.argmax(dim=0)]
+    # 'thresh' update: binary labels + per-frame hinge weights (discriminator.py:159-215,364-367)
+    E = ref.EasyDict
+    params = E(layer="layer4", cdims=96, kernel_size=[3], filter_reg=[1e-4, 1e-2], precon=[1e-4, 1e-2], n_channels=[1],
+               with_bias=False, init_iters=[5], update_iters=[5],
+               pixel_weighting=dict(method="hinge", tf=0.1, distractor_mult=1.0, per_frame=True, update_method="thresh",
+                                    max_fg_weight=100))
+    d = dc.Discriminator(params)
+    pw, yb = d.get_online_weights(case["soft"])
+    mine_y = (case["soft"] > 0.5).float()
+    assert torch.equal(yb, mine_y)
+    mine_pw = R.pixel_weights(mine_y, 0.1)
+    assert torch.equal(pw, mine_pw), "thresh-mode hinge weights differ from the restatement"
+    np.savez_compressed(os.path.join(OUT, "ytvos.npz"), logits=_np(logits), segs=_np(segs), labels=_np(labels).astype(np.uint8),
+                        pw=_np(pw), yb=_np(yb))
+    print("ytvos: Upsampler %s, merge_segmentations %s, thresh weights %s — restatement bit-identical"
+          % (tuple(logits.shape), tuple(segs.shape), tuple(pw.shape)))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -272,6 +308,7 @@ def main():
     gen_feedforward(ref, "resnet101")
     gen_e2e(ref)
     gen_eval(ref)
+    gen_ytvos(ref)
 
 
 if __name__ == "__main__":

@@ -92,6 +92,24 @@ def feedforward_case(arch="resnet18", size=MID, n_obj=2, seed=9):
     return dict(image=seq[2][0], bb=bb, seg=seg, PF=PF, arch=arch)
 
 
+def ytvos_case(seed=41):
+    """Seeded inputs of the all-frames variant's own pieces: an ``Upsampler`` state + input, object
+    probabilities for ``merge_segmentations``, a soft mask for the 'thresh' update labels / hinge weights."""
+    g = torch.Generator().manual_seed(seed)
+    up = OrderedDict()
+    up["project.conv1.weight"] = torch.randn(32, 64, 3, 3, generator=g) / 24.0
+    up["project.conv1.bias"] = torch.randn(32, generator=g) * 0.1
+    up["project.conv2.weight"] = torch.randn(1, 32, 3, 3, generator=g) / 17.0
+    up["project.conv2.bias"] = torch.randn(1, generator=g) * 0.1
+    x = torch.randn(2, 64, 9, 13, generator=g)
+    probs = torch.rand(3, 4, 20, 30, generator=g)               # (objects, frames, H, W)
+    probs[1, 2] = 0.0
+    probs[:, 3, :5] = 1.0
+    soft = blob_masks(3, (48, 64), g, soft=True)
+    soft[2] = soft[2] * 0.01                                     # fewer than 10 pixels above 0.5
+    return dict(up=up, x=x, image_size=(70, 101), probs=probs, soft=soft)
+
+
 def strip_prefix(sd, prefix="refiner."):
     return OrderedDict(((k[len(prefix):] if k.startswith(prefix) else k), v) for k, v in sd.items())
 

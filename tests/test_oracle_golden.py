@@ -108,3 +108,20 @@ def test_e2e_labels(golden):
     agree = (lab == g["labels"]).mean()
     assert np.array_equal(lab[0], g["labels"][0])
     assert agree > 0.98, agree    # bit-identical in the build container; chaotic init elsewhere (finding 8)
+
+
+def test_ytvos_variant_pieces_match_reference_fixture(golden):
+    """Row f4: the all-frames variant's own pieces (bicubic Upsampler, merge_segmentations + labels, 'thresh' update labels
+    and hinge weights) of the restatement against the fixture produced by executing ytvos_validation/*.py."""
+    from oracle import frtm_ref as R
+    g = golden("ytvos")
+    case = GI.ytvos_case()
+    logits = R.upsampler_bicubic(case["up"], case["x"], case["image_size"])
+    assert np.abs(logits.numpy() - g["logits"]).max() < 1e-5
+    segs = R.merge_segmentations(case["probs"])
+    assert np.abs(segs.numpy() - g["segs"]).max() < 1e-6
+    lut = torch.tensor([0, 3, 5, 9], dtype=torch.uint8)
+    assert np.array_equal(lut[segs.argmax(dim=0)].numpy(), g["labels"])
+    yb = (case["soft"] > 0.5).float()
+    assert np.array_equal(yb.numpy(), g["yb"])
+    assert np.abs(R.pixel_weights(yb, 0.1).numpy() - g["pw"]).max() < 1e-6
