@@ -18,6 +18,8 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 extern "C" const char *frtm_last_error(void) { return frtm::g_err; }
 extern "C" int frtm_version(void) { return 100; }
 extern "C" int64_t frtm_launch_count(void) { return frtm::g_launches.load(std::memory_order_relaxed); }
+/* A caller that replays launches of this library through a CUDA graph it captured itself reports the kernels of a replay. */
+extern "C" int64_t frtm_count_launches(int64_t n) { frtm::count_launch((int)n); return frtm::g_launches.load(std::memory_order_relaxed); }
 
 // Small host->device constant uploads WITHOUT a memcpy (a pageable cudaMemcpy would synchronise the caller with all
 // work queued on the stream): the values travel as kernel arguments.
@@ -38,6 +40,21 @@ extern "C" int frtm_fill_small(float *fdst, const float *fvals_host, int nf, int
   for (int k = 0; k < 16; ++k) { v.f[k] = k < nf ? fvals_host[k] : 0.f; v.i[k] = k < ni ? ivals_host[k] : 0; }
   frtm::fill_values_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(fdst, nf, idst, ni, v);
   FRTM_CHECK_LAUNCH("fill_small");
+  return FRTM_OK;
+}
+
+namespace frtm {
+__global__ void fill_u8_kernel(uint8_t *dst, int n, const Vals16 v) {
+  if ((int)threadIdx.x < n) dst[threadIdx.x] = (uint8_t)v.i[threadIdx.x];
+}
+}  // namespace frtm
+
+extern "C" int frtm_fill_u8(uint8_t *dst, const int *vals_host, int n, void *stream) {
+  FRTM_REQUIRE(dst && vals_host && n >= 0 && n <= 16, "fill_u8: at most 16 values");
+  frtm::Vals16 v;
+  for (int k = 0; k < 16; ++k) { v.f[k] = 0.f; v.i[k] = k < n ? vals_host[k] : 0; }
+  frtm::fill_u8_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(dst, n, v);
+  FRTM_CHECK_LAUNCH("fill_u8");
   return FRTM_OK;
 }
 

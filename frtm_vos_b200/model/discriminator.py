@@ -121,13 +121,25 @@ class Discriminator(nn.Module):
 
         # re-project with the learned matrix, fill the memory, warm up the filter-only optimiser
         cx = self._project_nchw(x_nhwc)
-        memory = Memory(self.memory_size, cx.shape[-3:], yf.shape[-3:], x_nhwc.device, self.learning_rate)
+        # ``buffer_pool`` (set by the tracker): the frame memory and the CG state of this object slot are reused across
+        # sequences — same addresses, so a captured track-block graph stays valid — instead of being reallocated
+        pool = getattr(self, "buffer_pool", None)
+        memory = pool.get("memory") if pool is not None else None
+        if memory is not None and memory.matches(self.memory_size, cx.shape[-3:], yf.shape[-3:], x_nhwc.device):
+            memory.reset()
+        else:
+            memory = Memory(self.memory_size, cx.shape[-3:], yf.shape[-3:], x_nhwc.device, self.learning_rate)
+            if pool is not None:
+                pool["memory"] = memory
         memory.initialize(cx, yf, pw, stencil, uty)
         problem = DiscriminatorLoss(x=memory.samples, y=memory.labels, filter_regs=self.filter_reg[1:],
                                     precond=self.precond[1:], sample_weights=memory.weights, net=self.filter,
                                     pixel_weighting=memory.pixel_weights, memory=memory)
         optimizer = GaussNewtonCG(problem, TensorList([self.filter.weight]), fletcher_reeves=False, standard_alpha=True,
-                                  direction_forget_factor=self.direction_forget_factor)
+                                  direction_forget_factor=self.direction_forget_factor,
+                                  cg_state=pool.get("cg_state") if pool is not None else None)
+        if pool is not None:
+            pool["cg_state"] = optimizer.cg_state
         optimizer.run(self.update_iters)
         self.memory = memory
         self.update_optimizer = optimizer

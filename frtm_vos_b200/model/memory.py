@@ -37,6 +37,16 @@ class Memory:
         self.device = device
         self.learning_rates = learning_rates
 
+    def reset(self):
+        """Empty the memory in place (buffers and their addresses are kept): all sample weights zero, fresh policy state.
+        Slots with weight 0 are skipped by every kernel, so their stale contents need not be cleared."""
+        self.weights.zero_()
+        ops.fill_small(idst=self.state, ivals=(0, -1, -1, 0))
+
+    def matches(self, capacity, feature_size, labels_size, device):
+        return (self._capacity == capacity and tuple(self.samples.shape[1:]) == tuple(feature_size)
+                and tuple(self.labels.shape[1:]) == tuple(labels_size) and self.samples.device == torch.device(device))
+
     @property
     def capacity(self):
         return self._capacity

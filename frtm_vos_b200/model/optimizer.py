@@ -77,7 +77,7 @@ class MinimizationProblem:
 class GaussNewtonCG:
 
     def __init__(self, problem, variable: TensorList, cg_eps=0.0, fletcher_reeves=True, standard_alpha=True,
-                 direction_forget_factor=0, step_alpha=1.0):
+                 direction_forget_factor=0, step_alpha=1.0, cg_state=None):
         from .discriminator import DiscriminatorLoss
         if not isinstance(problem, DiscriminatorLoss):
             raise NotImplementedError("GaussNewtonCG runs DiscriminatorLoss problems in closed form on the GPU; generic "
@@ -94,7 +94,10 @@ class GaussNewtonCG:
         n = variable[-1].numel()
         dev = variable[-1].device
         # p | r_prev | rho | has_p | pad | pad   (filter-only problem; persists across run() calls)
-        self.cg_state = torch.zeros(2 * n + 4, device=dev, dtype=torch.float32)
+        if cg_state is not None and cg_state.numel() == 2 * n + 4 and cg_state.device == dev:
+            self.cg_state = cg_state.zero_()             # pooled buffer (stable address), fresh state
+        else:
+            self.cg_state = torch.zeros(2 * n + 4, device=dev, dtype=torch.float32)
         self._n = n
         self._ws = None
         self.operator_select = 0    # 0 = the library picks the operator kernel by shape (include/frtm_b200.h: frtm_gn_update)

@@ -78,16 +78,27 @@ class Tracker(nn.Module):
         self.augment_workers = max(4, min(12, torch.get_num_threads()))
         self.block_batching = True  # run_sequence batches up to max_block frames between two filter updates
         self.max_block = 8
-        # Experimental, off by default (FRTM_GRAPH_BLOCKS=1): full blocks (max_block frames, no object starting inside) are
-        # captured once per sequence as a CUDA graph and replayed.  Measured on B200: because every sequence re-creates its
-        # target-model buffers the graph has to be re-captured per sequence, and capture + instantiation of ~170 nodes
-        # costs more than the seven replays save (630 vs 750 frames/s on config 2).  It pays off only with the per-object
-        # buffers pooled across sequences; kept for that follow-up.
-        self.graph_blocks = os.environ.get("FRTM_GRAPH_BLOCKS", "0") == "1"
+        # Full blocks (max_block frames, no object starting inside, aligned to the update schedule) are captured ONCE as a
+        # CUDA graph and replayed: ~170 launches become one.  The per-slot target-model buffers are pooled across sequences
+        # (see _obj_pool below), so the capture made on the first sequence serves every later sequence with the same number
+        # of objects and frame size — re-capturing per sequence, as round 1 did, cost more than its seven replays saved.
+        # Measured on B200 (profiles/r02_graph_blocks.md): +1.9 % frames/s on config 2, +2.8 % on config 3 at one GPU (the
+        # block is GPU-bound there); the point is the host: 20 ms of launch work per sequence disappear, which is what
+        # multi-rank runs on shared cores were short of.  FRTM_GRAPH_BLOCKS=0 turns it off; code that instruments the
+        # per-kernel path (the oracle-replay harness) sets ``graph_blocks = False`` on its tracker.
+        self.graph_blocks = os.environ.get("FRTM_GRAPH_BLOCKS", "1") == "1"
         self._blk_graph = None
         self._stack = None          # cached stacked projection of the live objects
+        self._stack_buf = None      # its packed buffers, rewritten in place (stable addresses across sequences)
         self._fbuf = None           # (maxN, c, 3, 3) contiguous filters (each Discriminator.filter.weight is a view)
         self._last_labels = None
+        # Per object slot (1, 2, ...): the frame memory and CG state of the target model in that slot, reused by every
+        # sequence (``Discriminator.buffer_pool``).  With the filter buffer, the packed projection, the GN pointer table and
+        # the label LUT kept in place as well, every device address a track block touches is the same from one sequence to
+        # the next, so ONE captured CUDA graph of a full block serves all sequences with the same number of objects.
+        self._obj_pool = {}
+        self._lut_buf = None
+        self.graph_captures = 0     # how many times a block graph was captured (tests / diagnostics)
 
     def clear(self):
         self.first_frames = []
@@ -106,6 +117,9 @@ class Tracker(nn.Module):
         self._fbuf = None
         self._gn_table = None
         self._blk_graph = None
+        self._stack = self._stack_buf = None
+        self._gn_table_buf = None
+        self._obj_pool = {}
         release_init_stages()
         torch.cuda.empty_cache()
 
@@ -149,10 +163,11 @@ class Tracker(nn.Module):
         self.current_frame = 0
         self.targets = dict()
         self._stack = None
-        self._fbuf = None
-        self._gn_table = None
-        self._blk_graph = None
-        self._lut = torch.tensor([0] + list(sequence.obj_ids), dtype=torch.uint8, device=self.device)
+        lut = [0] + list(sequence.obj_ids)
+        if self._lut_buf is None or self._lut_buf.numel() < len(lut):
+            self._lut_buf = torch.zeros(max(len(lut), 16), dtype=torch.uint8, device=self.device)
+        ops.fill_u8(self._lut_buf, lut)                 # in place: the LUT's address is part of a captured block graph
+        self._lut = self._lut_buf[:len(lut)]
         N = 0
         if speedrun:
             image, labels, obj_ids = sequence[0]
@@ -163,7 +178,6 @@ class Tracker(nn.Module):
             torch.cuda.synchronize()
             self.targets = dict()
             self._stack = None
-            self._fbuf = None
 
         outputs = []
         single = len(sequence.obj_ids) == 1
@@ -253,6 +267,7 @@ class Tracker(nn.Module):
                 # weights then waits for that stream only
                 target = TargetObject(obj_id=obj_id, index=len(self.targets) + 1, disc_params=self.disc_params,
                                       start_frame=self.current_frame, start_mask=mask)
+            target.discriminator.buffer_pool = self._obj_pool.setdefault(target.index, {})
             self.targets[obj_id] = target
             targets.append(target)
             torch.random.manual_seed(0)
@@ -315,7 +330,8 @@ class Tracker(nn.Module):
         key = tuple(t.object_id for t in live)
         if self._stack is None or self._stack[0] != key:
             W = torch.cat([t.discriminator.project.weight.detach() for t in live], dim=0)   # (N*c, C, 1, 1)
-            self._stack = (key, ops.pack_conv_tc_1x1_device(W))
+            self._stack_buf = ops.pack_conv_tc_1x1_device(W, out=self._stack_buf)
+            self._stack = (key, self._stack_buf)
         return self._stack[1]
 
     def track(self, image):
@@ -362,32 +378,42 @@ class Tracker(nn.Module):
             return None
         if any(t.discriminator.frame_num % t.discriminator.train_skipping != 0 for t in live):
             return None                                    # not aligned to the update schedule: eager
-        key = (nF, tuple(t.object_id for t in live), tuple(images[0].shape[-2:]), d0.memory.samples.data_ptr(),
-               0 if self._fbuf is None else self._fbuf.data_ptr())
+        # everything the eager path creates lazily and caches on the tracker exists BEFORE the key is taken / the capture
+        # starts, so no long-lived tensor comes out of the graph's private memory pool
+        dev = images[0].device
+        if getattr(self.refiner, "_packed", 0) is None:
+            self.refiner._pack()                          # host-side weight packing uploads pageable tensors
+        if getattr(self, "_fidx", None) is None or self._fidx[0] != (nF, n):
+            self._fidx = ((nF, n), torch.arange(n, dtype=torch.int32, device=dev).repeat(nF).contiguous())
+        if getattr(self, "_counts", None) is None or self._counts.numel() < n:
+            self._counts = torch.zeros(max(n, 8), dtype=torch.int32, device=dev)
+            self._gn_table = None
+        if getattr(self, "_counts_blk", None) is None or self._counts_blk.shape[0] < nF or self._counts_blk.shape[1] != n:
+            self._counts_blk = torch.zeros((self.max_block, n), dtype=torch.int32, device=dev)
+        self._ensure_gn_table(live, list(range(n)))
+        pc = self._stacked_projection(live)
+        # every device address the block's launches carry: the graph is replayed only while all of them are unchanged
+        addr = []
+        for t in live:
+            d, m = t.discriminator, t.discriminator.memory
+            addr += [t.index, m.samples.data_ptr(), m.labels.data_ptr(), m.pixel_weights.data_ptr(), m.weights.data_ptr(),
+                     m.stencil.data_ptr(), m.uty.data_ptr(), m.split.data_ptr(), m.state.data_ptr(),
+                     d.update_optimizer.cg_state.data_ptr(), d.filter.weight.data_ptr()]
+        key = (nF, n, tuple(images[0].shape[-2:]), tuple(addr), self._fbuf.data_ptr(), pc.wt.data_ptr(), pc.oscale.data_ptr(),
+               self._lut.data_ptr(), len(self.object_ids) == 1, tuple(int(v) for v in d0.update_iters), self._counts.data_ptr(),
+               self._counts_blk.data_ptr(), self._fidx[1].data_ptr(), self._gn_table[1].data_ptr(), self._gn_table[2].data_ptr())
         g = self._blk_graph
         frames = [im if im.dim() == 3 else im[0] for im in images]
         main = torch.cuda.current_stream()
         if g is None or g["key"] != key:
             self._blk_graph = None
             static_in = torch.stack(frames)
-            # everything the eager path creates lazily and caches on the tracker is created BEFORE the capture, so no
-            # long-lived tensor comes out of the graph's private memory pool
-            dev = static_in.device
-            self._stacked_projection(live)
-            if getattr(self.refiner, "_packed", 0) is None:
-                self.refiner._pack()                      # host-side weight packing uploads pageable tensors
-            if getattr(self, "_fidx", None) is None or self._fidx[0] != (nF, n):
-                self._fidx = ((nF, n), torch.arange(n, dtype=torch.int32, device=dev).repeat(nF).contiguous())
-            if getattr(self, "_counts", None) is None or self._counts.numel() < n:
-                self._counts = torch.zeros(max(n, 8), dtype=torch.int32, device=dev)
-                self._gn_table = None
-            if getattr(self, "_counts_blk", None) is None or self._counts_blk.shape[0] < nF or self._counts_blk.shape[1] != n:
-                self._counts_blk = torch.zeros((self.max_block, n), dtype=torch.int32, device=dev)
-            self._ensure_gn_table(live, list(range(n)))
             side = torch.cuda.Stream(device=dev)
             graph = torch.cuda.CUDAGraph()
             side.wait_stream(main)
             frame_nums = [t.discriminator.frame_num for t in live]
+            from .._lib import lib
+            launches0 = lib().launch_count()
             try:
                 with torch.cuda.stream(side):
                     graph.capture_begin(capture_error_mode="relaxed")
@@ -401,7 +427,7 @@ class Tracker(nn.Module):
                     import traceback
                     traceback.print_exc()
                 warnings.warn("frtm_vos_b200: CUDA-graph capture of the track block failed (%s); running eagerly" % (e,))
-                self.graph_blocks = os.environ.get("FRTM_GRAPH_BLOCKS", "0") == "1"
+                self.graph_blocks = False                  # do not try again on this tracker
                 for t, fn in zip(live, frame_nums):
                     t.discriminator.frame_num = fn
                 self._gn_table = None
@@ -411,11 +437,15 @@ class Tracker(nn.Module):
             for t, fn in zip(live, frame_nums):
                 t.discriminator.frame_num = fn
             g = dict(key=key, graph=graph, static_in=static_in, labels=self._blk_labels_all, masks=self.current_masks,
-                     samples=[t.discriminator.current_sample for t in live], keep=(side,))
+                     samples=[t.discriminator.current_sample for t in live], keep=(side,),
+                     kernels=int(lib().launch_count() - launches0))
             self._blk_graph = g
+            self.graph_captures += 1
         else:
             torch.stack(frames, out=g["static_in"])
         g["graph"].replay()
+        from .._lib import lib
+        lib().count_launches(g["kernels"])                # a replay runs the captured kernels without passing the counters
         labels = g["labels"].clone()                      # the static buffers are overwritten by the next replay
         for t, cs in zip(live, g["samples"]):
             t.discriminator.frame_num += nF
@@ -545,7 +575,8 @@ class Tracker(nn.Module):
         """(Re)build the device pointer table and the workspace of the batched filter update when the object set changes."""
         import ctypes
         from .._lib import lib, ptr, stream
-        key = tuple((live[k].object_id, live[k].discriminator.filter.weight.data_ptr()) for k in due)
+        key = tuple((live[k].object_id, live[k].discriminator.filter.weight.data_ptr(), live[k].discriminator.memory.samples.data_ptr(),
+                     live[k].discriminator.update_optimizer.cg_state.data_ptr()) for k in due) + (self._counts.data_ptr(),)
         if getattr(self, "_gn_table", None) is None or self._gn_table[0] != key:
             rows = [[], [], [], [], [], [], [], []]
             for k in due:
@@ -556,10 +587,17 @@ class Tracker(nn.Module):
                 rows[6].append(self._counts.data_ptr() + 4 * k)
                 rows[7].append(m.split.data_ptr())
             flat = [v for r in rows for v in r]
-            table = torch.empty((8, len(due)), dtype=torch.int64, device=self._counts.device)
-            lib().fill_i64(ptr(table), (ctypes.c_int64 * len(flat))(*flat), len(flat), stream())   # no synchronising H2D
+            # the table and the workspace keep their addresses when the object count is unchanged (they are part of a
+            # captured block graph); only the contents are rewritten
+            old = getattr(self, "_gn_table_buf", None)
             d0 = live[due[0]].discriminator
             cap, c, h, w = d0.memory.samples.shape
             nbytes = len(due) * lib().gn_update_workspace(cap, c, h, w)
-            ws = torch.empty(nbytes // 4, device=table.device, dtype=torch.float32)
+            if old is not None and old[0].shape == (8, len(due)) and old[2] >= nbytes and old[0].device == self._counts.device:
+                table, ws = old[0], old[1]
+            else:
+                table = torch.empty((8, len(due)), dtype=torch.int64, device=self._counts.device)
+                ws = torch.empty(nbytes // 4, device=table.device, dtype=torch.float32)
+                self._gn_table_buf = (table, ws, nbytes)
+            lib().fill_i64(ptr(table), (ctypes.c_int64 * len(flat))(*flat), len(flat), stream())   # no synchronising H2D
             self._gn_table = (key, table, ws, nbytes)

@@ -505,16 +505,30 @@ def conv65(h: Split, score: torch.Tensor, pc: PackedConv65, n_obj: int = 1, relu
     return y, sp, extra
 
 
-def pack_conv_tc_1x1_device(weight: torch.Tensor, bn_tile: Optional[int] = None) -> PackedConvTC:
-    """(Cout,Cin[,1,1]) fp32 ON THE DEVICE -> PackedConvTC without a host round trip (no synchronisation)."""
+def pack_conv_tc_1x1_device(weight: torch.Tensor, bn_tile: Optional[int] = None, out: Optional[PackedConvTC] = None) -> PackedConvTC:
+    """(Cout,Cin[,1,1]) fp32 ON THE DEVICE -> PackedConvTC without a host round trip (no synchronisation).  ``out``: a
+    previous result of the same shape whose buffers are rewritten in place (stable addresses for captured graphs)."""
     w = weight.detach().reshape(weight.shape[0], -1).contiguous()
     cout, cin = w.shape
     tile = bn_tile or _pick_bn(cout)
     cout_p = (cout + tile - 1) // tile * tile
+    if out is not None and out.cin == cin and out.cout == cout and out.bn == tile and out.wt.device == w.device:
+        lib().pack_tc_1x1(ptr(w), cout, cin, tile, ptr(out.wt), ptr(out.oscale), stream())
+        return out
     wt = torch.empty(cout_p * cin * 2, device=w.device, dtype=torch.float16)
     osc = torch.empty(cout_p, device=w.device, dtype=torch.float32)
     lib().pack_tc_1x1(ptr(w), cout, cin, tile, ptr(wt), ptr(osc), stream())
     return PackedConvTC(wt, osc, None, cin, cout, 1, tile, 1)
+
+
+def fill_u8(dst: torch.Tensor, vals):
+    """Write up to 16 host bytes into a uint8 device tensor asynchronously (values travel as kernel arguments)."""
+    import ctypes
+    assert dst.dtype == torch.uint8 and dst.numel() >= len(vals)
+    for o in range(0, max(len(vals), 1), 16):
+        chunk = [int(v) for v in vals[o:o + 16]]
+        arr = (ctypes.c_int * max(len(chunk), 1))(*chunk)
+        lib().fill_u8(dst.data_ptr() + o, arr, len(chunk), stream())
 
 
 def fill_small(fdst: Optional[torch.Tensor] = None, fvals=(), idst: Optional[torch.Tensor] = None, ivals=()):

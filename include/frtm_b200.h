@@ -38,11 +38,16 @@ const char *frtm_last_error(void);
 int frtm_version(void);
 /* Number of kernels this library has launched in this process (bench.py "gpu_launches"). */
 int64_t frtm_launch_count(void);
+/* Adds n to the launch counter: for callers that replay captured launches of this library as a CUDA graph (a replay runs
+ * the kernels without passing through the entry points that count them).  Returns the new count. */
+int64_t frtm_count_launches(int64_t n);
 
 /* Upload up to 16 floats and 16 ints from HOST arrays to device memory as kernel arguments (no memcpy, hence no
  * synchronisation with work already queued on the stream).  Used for memory.weights / memory state initialisation
  * (model/memory.py:38-46). */
 int frtm_fill_small(float *fdst, const float *fvals_host, int nf, int *idst, const int *ivals_host, int ni, void *stream);
+/* The same for up to 16 bytes (the label look-up table of a sequence, kept at a stable address). */
+int frtm_fill_u8(uint8_t *dst, const int *vals_host, int n, void *stream);
 /* Same for n 64-bit integers (device pointer tables of the batched GN update). */
 int frtm_fill_i64(void *dst, const int64_t *vals_host, int n, void *stream);
 

@@ -79,11 +79,13 @@ def replay_on_device(trk, seq, dump, n_frames, device):
 
     trk.refiner.forward_nhwc = spy
     trk.initialize = init_and_inject
+    graph_blocks, trk.graph_blocks = trk.graph_blocks, False      # the spy needs the per-kernel path, not a graph replay
     try:
         out, _ = trk.run_sequence(Head(seq, n_frames))
     finally:
         trk.refiner.forward_nhwc = orig_fwd
         trk.initialize = orig_init
+        trk.graph_blocks = graph_blocks
     return out, got_logits
 
 

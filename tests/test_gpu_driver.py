@@ -160,3 +160,28 @@ def test_run_dataset_async_preload_equals_preloaded_path(tmp_path):
         assert len(files) == ref.shape[0]
         got = torch.stack([imread(f)[0] for f in files])
         assert torch.equal(got, ref), name
+
+
+def test_block_graph_is_captured_once_and_matches_eager():
+    """``graph_blocks``: full 8-frame blocks are replayed as one CUDA graph.  With the per-slot target-model buffers pooled
+    across sequences the graph captured on the first sequence serves the following ones (same object count): identical
+    labels, filters and memory weights to the eager path, one capture for three sequences."""
+    from frtm_vos_b200 import synth
+    trk_e, _, _ = _tracker()
+    trk_e.graph_blocks = False
+    trk_g, _, _ = _tracker()
+    trk_g.graph_blocks = True
+    seqs = [synth.SyntheticSequence(num_objects=2, num_frames=25, size=SIZE, seq_id=30 + k) for k in range(3)]
+    for seq in seqs:
+        torch.manual_seed(11)
+        a, _ = trk_e.run_sequence(seq)
+        torch.manual_seed(11)
+        b, _ = trk_g.run_sequence(seq)
+        for x, y in zip(a, b):
+            assert torch.equal(x.cpu(), y.cpu()), seq.name
+        for o in seq.obj_ids:
+            de, dg = trk_e.targets[o].discriminator, trk_g.targets[o].discriminator
+            assert torch.equal(de.filter.weight.cpu(), dg.filter.weight.cpu())
+            assert torch.equal(de.memory.weights.cpu(), dg.memory.weights.cpu())
+    assert trk_g.graph_captures == 1, trk_g.graph_captures
+    assert trk_e.graph_captures == 0

@@ -162,6 +162,7 @@ def test_P4_end_to_end_oracle_replay(size, n_obj):
     out_ref, _ = orc.run_sequence(seq)
 
     trk, fe = _build("resnet18", bb, seg, dp)
+    trk.graph_blocks = False                               # the spies below need the per-kernel path
     got_logits = {}
     orig_fwd = trk.refiner.forward_nhwc
 
