@@ -386,6 +386,349 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
 }
 
 // ----------------------------------------------------------------------------------------------------------------
+// CTA-pair kernel for the wide convolutions (Cout a multiple of 128: the bottleneck stages of ResNet-101 and the deep
+// stages of ResNet-18 — 1x1 and 3x3, stride 1 and 2).  The general kernel above moves 48 KB from L2 per 128x64x64
+// product and is bound by the L2 -> shared-memory path (~42 B/clk/SM) at a quarter of the tensor rate.  Here two CTAs of
+// a cluster (the two SMs of a TPC) run ONE tcgen05.mma.cta_group::2 product of M = 256 pixels x N = 2*HALF output
+// channels: each CTA stages its own 128-pixel A tile and HALF of the weight rows, so a k-block costs a CTA 32 + HALF/4 KB
+// for 128 x 2*HALF x 64 MACs — a third (HALF = 128) or half (HALF = 64) of the general kernel's traffic per MAC — and
+// every product runs at the full N >= 128 issue rate.  The three split products hi*hi + hi*lo + lo*hi go into the same
+// accumulator; accumulation is two-level as above (TC_FOLD k-blocks per TMEM slot, eight epilogue warps fold the slots into
+// fp32 registers: warp = (lane quarter, column half)).  Protocol: both producers load into their own shared memory and
+// count the bytes on the LEADER's full barrier; the leader's MMA warp issues for the pair and its commits arrive on the
+// empty / accumulator-full barriers of both CTAs (multicast); the epilogue warps of both CTAs arrive on the leader's
+// accumulator-drained barrier.
+// Weights: the N tile 64 packing of TcArgs::wt, read through a 2-D tensor map (rows of 128 B, pre-swizzled image).
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int P2_THREADS = 64 + 8 * 32;
+#ifndef P2_FOLD_N
+#define P2_FOLD_N 1
+#endif
+// k-blocks per TMEM slot between register folds.  The three split products share one accumulator here (12 truncating
+// accumulations per k-block against 8 at the main magnitude in the packed scheme of the general kernel), so the pair
+// kernel folds every k-block: 12 per fold instead of 16.
+constexpr int P2_FOLD = P2_FOLD_N;
+
+// Epilogue of a 128-pixel x BN-channel tile staged through shared memory (the pipeline stages are free once the last
+// accumulator slot has been committed): the TMEM-row-per-thread layout of the accumulators would make every global access a
+// 32 x 16-byte scatter and needs a fully unrolled store routine (tens of KB of code, instruction-cache bound); through the
+// tile a small rolled loop reads / writes 8 consecutive channels per thread, i.e. whole 128-byte lines per quarter warp.
+// `tile` = [128][BN + 4] fp32 holding acc * oscale + bias; called by the 256 epilogue threads (te = 0..255) after a barrier.
+template <int BN>
+__device__ __forceinline__ void pair_epilogue_store(const TcArgs &a, float *tile, int te, int b, int y0, int x0, int n0) {
+  constexpr int LDT = BN + 4, G = BN / 8, ITERS = 128 * G / 256, U = 4;
+  static_assert(ITERS % U == 0, "pair_epilogue_store: iteration count");
+  const bool vec_f32 = (a.ldy % 4 == 0) && (a.y_coff % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 15) == 0);
+  const bool vec_res = (a.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.res) & 15) == 0);
+  const bool vec_h = (a.ldyh % 8 == 0) && (a.yh_coff % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.y_hi) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(a.y_lo) & 15) == 0);
+  const bool vec_rh = (a.ldrh % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.res_hi) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(a.res_lo) & 15) == 0);
+  const bool post = a.res || a.res_hi || a.relu;
+  // U iterations at a time with all their residual loads issued first: one load round trip per thread and iteration would
+  // leave the loop latency-bound (8 KB in flight per SM)
+#pragma unroll 1
+  for (int it = 0; it < ITERS; it += U) {
+    int64_t pix[U];
+    int pp[U], cc[U];
+    bool ok[U];
+    uint4 rh4[U], rl4[U];
+    float4 rf[U][2];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int idx = te + (it + u) * 256;
+      pp[u] = idx / G;
+      cc[u] = (idx - pp[u] * G) * 8;
+      const int py = y0 + pp[u] / TC_TW, px = x0 + pp[u] % TC_TW;
+      ok[u] = py < a.Ho && px < a.Wo;
+      pix[u] = ((int64_t)b * a.Ho + py) * a.Wo + px;
+      rh4[u] = make_uint4(0u, 0u, 0u, 0u); rl4[u] = rh4[u];
+      rf[u][0] = make_float4(0.f, 0.f, 0.f, 0.f); rf[u][1] = rf[u][0];
+      if (ok[u] && a.res_hi) {
+        const __half *rh = a.res_hi + pix[u] * a.ldrh + n0 + cc[u], *rl = a.res_lo + pix[u] * a.ldrh + n0 + cc[u];
+        if (vec_rh) {
+          rh4[u] = *reinterpret_cast<const uint4 *>(rh);
+          rl4[u] = *reinterpret_cast<const uint4 *>(rl);
+        } else {
+          __half *hh = reinterpret_cast<__half *>(&rh4[u]), *ll = reinterpret_cast<__half *>(&rl4[u]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { hh[j] = rh[j]; ll[j] = rl[j]; }
+        }
+      }
+      if (ok[u] && a.res) {
+        const float *r = a.res + pix[u] * a.ldr + n0 + cc[u];
+        if (vec_res) {
+          rf[u][0] = *reinterpret_cast<const float4 *>(r);
+          rf[u][1] = *reinterpret_cast<const float4 *>(r + 4);
+        } else {
+          float *f = reinterpret_cast<float *>(&rf[u][0]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = r[j];
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!ok[u]) continue;
+      const int c = cc[u];
+      float *tp = tile + pp[u] * LDT + c;
+      float v[8];
+      *reinterpret_cast<float4 *>(v) = *reinterpret_cast<const float4 *>(tp);
+      *reinterpret_cast<float4 *>(v + 4) = *reinterpret_cast<const float4 *>(tp + 4);
+      {
+        const float *f = reinterpret_cast<const float *>(&rf[u][0]);
+        const __half2 *h2 = reinterpret_cast<const __half2 *>(&rh4[u]), *l2 = reinterpret_cast<const __half2 *>(&rl4[u]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 fh = __half22float2(h2[k]), fl = __half22float2(l2[k]);
+          v[2 * k] += f[2 * k] + (fh.x + fl.x) * (1.f / TC_ACT_SCALE);
+          v[2 * k + 1] += f[2 * k + 1] + (fh.y + fl.y) * (1.f / TC_ACT_SCALE);
+        }
+      }
+      if (a.relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      if (a.y) {
+        float *dst = a.y + pix[u] * a.ldy + a.y_coff + n0 + c;
+        if (vec_f32) {
+          *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4 *>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = v[j];
+        }
+      }
+      if (a.y_hi && n0 + c < a.yh_cout) {
+        __half *dh = a.y_hi + pix[u] * a.ldyh + a.yh_coff + n0 + c, *dl = a.y_lo + pix[u] * a.ldyh + a.yh_coff + n0 + c;
+        __align__(16) __half hh[8];
+        __align__(16) __half ll[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float sc = v[j] * TC_ACT_SCALE;
+          hh[j] = __float2half_rn(sc);
+          ll[j] = __float2half_rn(sc - __half2float(hh[j]));
+        }
+        if (n0 + c + 8 <= a.yh_cout && vec_h) {
+          *reinterpret_cast<uint4 *>(dh) = *reinterpret_cast<const uint4 *>(hh);
+          *reinterpret_cast<uint4 *>(dl) = *reinterpret_cast<const uint4 *>(ll);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (n0 + c + j < a.yh_cout) { dh[j] = hh[j]; dl[j] = ll[j]; }
+        }
+      }
+      if (a.y_nchw && post) {               // the NCHW pass below reads the finished values
+        *reinterpret_cast<float4 *>(tp) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4 *>(tp + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      }
+    }
+  }
+  if (a.y_nchw) {                           // exported feature map: lanes along the 16 contiguous pixels of a tile row
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const int64_t hw = (int64_t)a.Ho * a.Wo;
+#pragma unroll 1
+    for (int idx = te; idx < 128 * BN; idx += 256) {
+      const int p = idx & 127, c = idx >> 7;
+      const int py = y0 + p / TC_TW, px = x0 + p % TC_TW;
+      if (py < a.Ho && px < a.Wo) a.y_nchw[((int64_t)b * a.Cout + n0 + c) * hw + (int64_t)py * a.Wo + px] = tile[p * LDT + c];
+    }
+  }
+}
+
+template <int HALF>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P2_THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+                const __grid_constant__ CUtensorMap tm_w, const TcArgs a) {
+  constexpr int BN = 2 * HALF;                       // output channels of the pair's tile
+  constexpr int B_PLANE = HALF * 128;                // one weight plane (hi or lo) of this CTA's rows
+  constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_PLANE;
+  constexpr int STAGES = HALF == 128 ? 3 : 4;
+  constexpr int SLOT = BN;
+  constexpr int COLS = tmem_cols(2 * SLOT);
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar_full = base + STAGES * STAGE_BYTES;       // leader's are the ones in use
+  const uint32_t bar_empty = bar_full + 8 * STAGES;
+  const uint32_t bar_accf = bar_empty + 8 * STAGES;            // 2 x 8 B: accumulator slot full (both CTAs)
+  const uint32_t bar_acce = bar_accf + 16;                     // 2 x 8 B: slot drained by the 16 epilogue warps of the pair (leader's)
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gen + STAGES * STAGE_BYTES + 16 * STAGES + 32);
+  float *s_osc = reinterpret_cast<float *>(gen + STAGES * STAGE_BYTES + 16 * STAGES + 48);   // [2 halves][osc HALF | bias HALF]
+
+#ifdef TC2_TIMING
+  __shared__ long long tc2_stamps[10][8];
+  const long long t_start = clock64();
+#define TC2_STAMP(i) do { if (lane == 0) tc2_stamps[warp][i] = clock64() - t_start; } while (0)
+#else
+#define TC2_STAMP(i) do {} while (0)
+#endif
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  const uint32_t rank = pair_ctarank();
+  const int tiles_per_img = a.tiles_x * a.tiles_y;
+  const int tile = blockIdx.x;                       // the pair owns tiles 2p, 2p+1; the last one may be past the end
+  const int b = tile / tiles_per_img;
+  const int tr = tile - b * tiles_per_img;
+  const int y0 = (tr / a.tiles_x) * TC_TH, x0 = (tr % a.tiles_x) * TC_TW;
+  const int ntile = blockIdx.y;
+  const int ntaps = a.kh * a.kw;
+  const int nkb = ntaps * a.kchunks;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_hi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_lo)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_w)) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int j = 0; j < 2; ++j) {
+      mbar_init(bar_accf + 8 * j, 1);
+      mbar_init(bar_acce + 8 * j, 16);     // one arrive per epilogue warp of either CTA
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  pair_sync_all();                          // barriers of both CTAs initialised, TMEM of both allocated
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  TC2_STAMP(0);
+
+  if (warp == 0) {
+    // ---- producer (both CTAs): own A tile (hi, lo) + this CTA's HALF weight rows (hi, lo), bytes counted by the leader ----
+    const uint32_t lead_full = mapa_shared(bar_full, 0);
+    const int sub0 = (ntile * BN + (int)rank * HALF) / 64;       // first 64-row weight tile of this CTA
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      mbar_wait(bar_empty + 8 * s, ph ^ 1);
+      const int tap = kb / a.kchunks, kc = kb - tap * a.kchunks;
+      const int ky = tap / a.kw, kx = tap - ky * a.kw;
+      const uint32_t sa = base + s * STAGE_BYTES;
+      if (elect_one()) {
+        if (rank == 0) mbar_expect_tx(bar_full + 8 * s, 2 * STAGE_BYTES);
+        const uint32_t fb = lead_full + 8 * s;
+        tma2_load_4d(sa, &tm_hi, kc * TC_BK, x0 * a.stride + kx - a.pad, y0 * a.stride + ky - a.pad, b, fb);
+        tma2_load_4d(sa + TC_A_BYTES, &tm_lo, kc * TC_BK, x0 * a.stride + kx - a.pad, y0 * a.stride + ky - a.pad, b, fb);
+#pragma unroll
+        for (int j = 0; j < HALF / 64; ++j) {
+          const int row = ((sub0 + j) * nkb + kb) * 128;          // [hi 64 rows | lo 64 rows] of weight tile sub0 + j
+          tma2_load_2d(sa + 2 * TC_A_BYTES + j * 8192, &tm_w, 0, row, fb);
+          tma2_load_2d(sa + 2 * TC_A_BYTES + B_PLANE + j * 8192, &tm_w, 0, row + 64, fb);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      // ---- MMA issuer (leader): per k-step  D += A_hi x B_hi,  D += A_hi x B_lo,  D += A_lo x B_hi  over the pair ----
+      constexpr uint32_t idesc = umma_idesc(256, BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(bar_full + 8 * s, ph);
+        tc_fence_after();
+        if (kb == 0) TC2_STAMP(1);
+        const int grp = kb / P2_FOLD, first = (kb % P2_FOLD) == 0;
+        const uint32_t slot = grp & 1;
+        if (first) {                        // both CTAs' epilogues must have drained this slot (two groups ago)
+          mbar_wait(bar_acce + 8 * slot, ((grp >> 1) & 1) ^ 1);
+          tc_fence_after();
+        }
+        const uint32_t tacc = tmem_base + slot * SLOT;
+        const uint32_t sa = base + s * STAGE_BYTES;
+        const uint64_t a_hi = umma_desc(sa), a_lo = umma_desc(sa + TC_A_BYTES);
+        const uint64_t b_hi = umma_desc(sa + 2 * TC_A_BYTES), b_lo = umma_desc(sa + 2 * TC_A_BYTES + B_PLANE);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+            umma2_f16(tacc, a_hi + adv, b_hi + adv, idesc, (first && k == 0) ? 0u : 1u);
+            umma2_f16(tacc, a_hi + adv, b_lo + adv, idesc, 1u);
+            umma2_f16(tacc, a_lo + adv, b_hi + adv, idesc, 1u);
+          }
+          umma2_commit(bar_empty + 8 * s);
+          if ((kb % P2_FOLD) == P2_FOLD - 1 || kb == nkb - 1) umma2_commit(bar_accf + 8 * slot);
+        }
+        __syncwarp();
+      }
+      TC2_STAMP(2);
+    }
+  } else {
+    // ---- epilogue (both CTAs): warp = (TMEM lane quarter q, column half h); a thread owns HALF channels of one pixel ----
+    const int q = warp & 3, h = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const int n0 = ntile * BN;
+    for (int i = threadIdx.x - 64; i < BN; i += P2_THREADS - 64) {
+      const int hh = i / HALF, ii = i - hh * HALF;
+      s_osc[hh * 2 * HALF + ii] = a.oscale[n0 + i];
+      s_osc[hh * 2 * HALF + HALF + ii] = (a.bias != nullptr && n0 + i < a.Cout) ? a.bias[n0 + i] : 0.f;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const uint32_t lead_acce = mapa_shared(bar_acce, 0);
+    float acc[HALF];
+#pragma unroll
+    for (int j = 0; j < HALF; ++j) acc[j] = 0.f;
+    const int ngrp = (nkb + P2_FOLD - 1) / P2_FOLD;
+#pragma unroll 1
+    for (int grp = 0; grp < ngrp; ++grp) {
+      const uint32_t slot = grp & 1;
+      mbar_wait(bar_accf + 8 * slot, (grp >> 1) & 1);
+      tc_fence_after();
+      const uint32_t col0 = tmem_base + ((uint32_t)(q * 32) << 16) + slot * SLOT + (uint32_t)(h * HALF);
+#pragma unroll
+      for (int c0 = 0; c0 < HALF; c0 += 32) {
+        float t[32];
+        tmem_ld32(col0 + c0, t);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[c0 + j] += t[j];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive_local(bar_acce + 8 * slot);
+        else mbar_arrive_cluster(lead_acce + 8 * slot);
+      }
+    }
+    TC2_STAMP(3);
+    // every MMA of the pair has completed: the pipeline stages are free and become the staging tile [128][BN + 4] fp32
+    float *tile = reinterpret_cast<float *>(gen);
+    {
+      const float *so = s_osc + h * 2 * HALF, *sb = so + HALF;
+      float *trow = tile + row * (BN + 4) + h * HALF;
+#pragma unroll
+      for (int c0 = 0; c0 < HALF; c0 += 4)
+        *reinterpret_cast<float4 *>(trow + c0) =
+            make_float4(fmaf(acc[c0], so[c0], sb[c0]), fmaf(acc[c0 + 1], so[c0 + 1], sb[c0 + 1]),
+                        fmaf(acc[c0 + 2], so[c0 + 2], sb[c0 + 2]), fmaf(acc[c0 + 3], so[c0 + 3], sb[c0 + 3]));
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    TC2_STAMP(4);
+    if (b < a.B) pair_epilogue_store<BN>(a, tile, (int)threadIdx.x - 64, b, y0, x0, n0);
+    TC2_STAMP(5);
+  }
+  tc_fence_before();
+  TC2_STAMP(6);
+  pair_sync_all();                          // no CTA of the pair leaves while the other may still signal it or use its TMEM
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(COLS) : "memory");
+  }
+#ifdef TC2_TIMING
+  __syncthreads();
+  if (threadIdx.x == 0 && blockIdx.y == 0 && (blockIdx.x < 2 || blockIdx.x == gridDim.x - 2))
+    printf("tc2 cta %d: setup %lld | mma: first_full %lld issued %lld | epi w2: folds %lld staged %lld stored %lld | w9: folds %lld staged %lld stored %lld | final %lld end %lld\n",
+           blockIdx.x, tc2_stamps[0][0], tc2_stamps[1][1], tc2_stamps[1][2], tc2_stamps[2][3], tc2_stamps[2][4], tc2_stamps[2][5],
+           tc2_stamps[9][3], tc2_stamps[9][4], tc2_stamps[9][5], tc2_stamps[2][6], clock64() - t_start);
+#endif
+}
+
+// ----------------------------------------------------------------------------------------------------------------
 // 3x3 stride-1 convolution with 64 input channels — the shape of every 3x3 conv of the refinement network and of the
 // first backbone stage, i.e. most of the conv time at 480p.  The general kernel above is bound by L2 -> shared-memory
 // operand traffic (every CTA re-fetches each tap's shifted A tile and all the weights: 48 KB per 128x64x64 product,
@@ -897,6 +1240,39 @@ static int make_act_map(CUtensorMap *tm, const __half *ptr, int B, int H, int W,
   return FRTM_OK;
 }
 
+// the pre-swizzled weight image as rows of 128 B; a box is one plane (hi or lo) of one 64-row weight tile of one k-block
+static int make_weight_map(CUtensorMap *tm, const __half *wt, int64_t rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("conv_tc: cuTensorMapEncodeTiled entry point not available"); return FRTM_ELAUNCH; }
+  cuuint64_t dims[2] = {64, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {128};
+  cuuint32_t box[2] = {64, 64};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half *>(wt), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled (weights) failed (%d)", (int)r); return FRTM_ELAUNCH; }
+  return FRTM_OK;
+}
+
+template <int HALF>
+static int launch_tc2(const CUtensorMap &mh, const CUtensorMap &ml, const CUtensorMap &mw, const TcArgs &a, cudaStream_t st) {
+  constexpr int stages = HALF == 128 ? 3 : 4;
+  constexpr int smem = stages * (2 * TC_A_BYTES + 2 * HALF * 128) + 16 * stages + 48 + 16 * HALF + 1024;
+  static_assert(smem <= 227 * 1024, "conv_tc2: shared memory budget");
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { set_error("conv_tc2: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return FRTM_ELAUNCH; }
+    configured = true;
+  }
+  const int ntiles = a.B * a.tiles_x * a.tiles_y;
+  dim3 grid((unsigned)(2 * cdiv(ntiles, 2)), (unsigned)(a.Cout / (2 * HALF)));
+  conv_tc2_kernel<HALF><<<grid, P2_THREADS, smem, st>>>(mh, ml, mw, a);
+  FRTM_CHECK_LAUNCH("conv_tc2");
+  return FRTM_OK;
+}
+
 template <int BN, int STAGES, bool R1, bool TAP>
 static int launch_tc(const CUtensorMap &mh, const CUtensorMap &ml, const TcArgs &a, dim3 grid, cudaStream_t st) {
   constexpr int smem = STAGES * (2 * TC_A_BYTES + 2 * BN * 128) + 16 * STAGES + 48 + 84 * BN + 1024;
@@ -970,7 +1346,8 @@ extern "C" int frtm_conv2d_tc(const void *x_hi, const void *x_lo, int B, int H, 
                               const float *r1_score, const float *r1_w, const float *r1_bias, float *y_extra, int extra_ch,
                               int Cout, int kh, int kw, int stride, int relu, int kernel_select, void *stream) {
   FRTM_REQUIRE(x_hi && x_lo && wt && oscale && (y || y_nchw || y_hi || y_tap), "conv2d_tc: null pointer");
-  FRTM_REQUIRE(kernel_select == 0 || kernel_select == 1, "conv2d_tc: kernel_select must be 0 (automatic) or 1 (general tile kernel)");
+  FRTM_REQUIRE(kernel_select >= 0 && kernel_select <= 3,
+               "conv2d_tc: kernel_select must be 0 (automatic), 1 (general tile kernel), 2 or 3 (CTA-pair kernel, N = 128 / 256)");
   const bool special = kernel_select == 0;
   FRTM_REQUIRE(!r1_score || r1_w, "conv2d_tc: the rank-1 score channel needs its weights");
   FRTM_REQUIRE(!y_extra || (extra_ch >= 0 && extra_ch < Cout), "conv2d_tc: extra_ch out of range");
@@ -1009,6 +1386,28 @@ extern "C" int frtm_conv2d_tc(const void *x_hi, const void *x_lo, int B, int H, 
   cudaStream_t st = (cudaStream_t)stream;
   const bool r1 = r1_score != nullptr, tap = y_tap != nullptr;
   FRTM_REQUIRE(!(r1 && tap), "conv2d_tc: rank-1 input and tap-map output cannot be combined");
+  // wide convs (Cout a multiple of 128, weights in the N tile 64 packing, plain epilogue): the CTA-pair kernel.  Pair tile
+  // N = 256 when that still gives every SM a CTA, else N = 128 (twice the CTAs at 1.5x the L2 traffic per MAC).
+  const bool pair_ok = bn_tile == 64 && Cout % 128 == 0 && !r1 && !tap;
+  FRTM_REQUIRE(kernel_select < 2 || (pair_ok && (kernel_select == 2 || Cout % 256 == 0)),
+               "conv2d_tc: the CTA-pair kernel needs the N tile 64 packing, Cout %% 128 == 0 (N = 256: %% 256) and a plain epilogue");
+  if (kernel_select >= 2 || (special && pair_ok)) {
+    bool wide = kernel_select == 3;
+    if (kernel_select == 0 && Cout % 256 == 0) {
+      static int num_sms = 0;
+      if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+      }
+      const int ctas256 = 2 * cdiv((int64_t)B * a.tiles_x * a.tiles_y, 2) * (Cout / 256);
+      wide = 10 * ctas256 >= 7 * num_sms;
+    }
+    CUtensorMap mw;
+    rc = make_weight_map(&mw, (const __half *)wt, (int64_t)(Cout / 64) * a.kh * a.kw * a.kchunks * 128);
+    if (rc) return rc;
+    return wide ? launch_tc2<128>(mh, ml, mw, a, st) : launch_tc2<64>(mh, ml, mw, a, st);
+  }
   if (stream1) {
     a.tiles_x = cdiv(a.Wo, S3_TW); a.tiles_y = cdiv(a.Ho, S3_TH);
     return bn_tile == 64 ? launch_tc1<64>(mh, ml, a, st) : launch_tc1<32>(mh, ml, a, st);

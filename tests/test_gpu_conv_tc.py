@@ -234,3 +234,42 @@ def test_conv2d_tc_wide_tile_128():
         assert pc.bn == tile
         o = ops.conv2d_tc(xs, pc, relu=True)
         assert (_nchw(o["y"].cpu()) - ref).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,hw,B", [
+    (128, 128, 3, 1, (15, 27), 1),      # pair N = 128 only, 2 tiles = one pair
+    (256, 256, 3, 1, (30, 54), 1),      # rn101 stage-3 3x3 (one frame)
+    (256, 256, 3, 1, (30, 54), 8),      # ... at the block batch: 128 tiles, N = 256 chosen automatically
+    (1024, 256, 1, 1, (30, 54), 8),     # rn101 stage-3 reduce
+    (256, 1024, 1, 1, (30, 54), 8),     # rn101 stage-3 expand (residual + ReLU epilogue)
+    (512, 1024, 1, 2, (60, 107), 2),    # stage-3 downsample, stride 2
+    (256, 256, 3, 2, (60, 107), 3),     # stride-2 3x3, odd tile count (last pair half empty)
+    (512, 512, 3, 1, (15, 27), 8),      # rn18 layer4 / rn101 stage 4
+    (128, 512, 1, 1, (60, 107), 1),     # stage-2 expand
+])
+def test_pair_kernel_matches_fp32_and_general_kernel(cin, cout, k, stride, hw, B):
+    """conv_tc2_kernel (tcgen05.mma.cta_group::2 over a CTA pair, M = 256 x N = 128 / 256) at the ResNet-101 / ResNet-18
+    production shapes: against torch fp32 on the CPU and against the general tile kernel, for both pair tile widths."""
+    from frtm_vos_b200 import ops
+    g = torch.Generator().manual_seed(cin + 3 * cout + k + stride)
+    x = torch.randn(B, cin, *hw, generator=g)
+    w = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    b = torch.randn(cout, generator=g)
+    ref = F.conv2d(x, w, b, stride, k // 2)
+    res = torch.randn(ref.shape, generator=g)
+    ref = F.relu(ref + res)
+    scale = max(1.0, ref.abs().max().item())
+    xs = ops.split_f16(_nhwc(x).to(DEV))
+    pc = ops.pack_conv_tc(w, b, device=DEV, stride=stride)
+    assert pc.bn == 64
+    rs = ops.split_f16(_nhwc(res).to(DEV))
+    gen = ops.conv2d_tc(xs, pc, res=rs, relu=True, out_split=True, kernel_select=1)
+    sels = [0, 2] + ([3] if cout % 256 == 0 else [])
+    for sel in sels:
+        o = ops.conv2d_tc(xs, pc, res=rs, relu=True, out_split=True, nchw=True, kernel_select=sel)
+        torch.cuda.synchronize()
+        assert (_nchw(o["y"].cpu()) - ref).abs().max().item() < 1e-5 * scale, sel
+        assert (o["nchw"].cpu() - ref).abs().max().item() < 1e-5 * scale, sel
+        assert (o["y"] - gen["y"]).abs().max().item() < 4e-6 * scale, sel
+        d = (o["split"].hi.float() + o["split"].lo.float()) - (gen["split"].hi.float() + gen["split"].lo.float())
+        assert d.abs().max().item() / 16.0 < 4e-6 * scale, sel
