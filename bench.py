@@ -256,9 +256,12 @@ def run_b200(cfg, steps, warmup, dev, rank, world, dist, with_clocks):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def step(seqs, read_back=False):
+        # the rank's sequences run back to back as in Tracker.run_dataset: while one is tracked, the host half of the next
+        # one's first-frame initialisation (augmentation) is prepared in worker threads; the sequence after the last one
+        # of a step is the first one of the next step (FRTM_PREFETCH_INIT=0 turns the overlap off)
         maps = []
-        for s in seqs:
-            outs, _ = trk.run_sequence(s)
+        for k, s in enumerate(seqs):
+            outs, _ = trk.run_sequence(s, next_sequence=seqs[(k + 1) % len(seqs)])
             maps.append(torch.stack([o.reshape(H, W) for o in outs]))
         labels = torch.stack(maps)                                 # (S,T,H,W) uint8
         if world > 1:
@@ -303,10 +306,24 @@ def run_b200(cfg, steps, warmup, dev, rank, world, dist, with_clocks):
     e3.record()
     sync()
     ms_e2e = e2.elapsed_time(e3)
-    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    # the same device-resident steps with the cross-sequence overlap of the initialisation turned off
+    trk.prefetch_next = False
+    trk._prefetched.clear()
+    step(mine)
+    sync()
+    e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e4.record()
+    for _ in range(k_e2e):
+        step(mine)
+        flush.zero_()
+    e5.record()
+    sync()
+    ms_np = e4.elapsed_time(e5)
+    trk.prefetch_next = os.environ.get("FRTM_PREFETCH_INIT", "1") == "1"
+    t = torch.tensor([ms, ms_e2e, ms_np], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = t.tolist()
+    ms, ms_e2e, ms_np = t.tolist()
 
     # ---- roofline of the GN/CG operator on this rank's real frame memories (all objects, one batched update) -------
     pk = peaks()
@@ -385,7 +402,13 @@ def run_b200(cfg, steps, warmup, dev, rank, world, dist, with_clocks):
     return dict(value=steps * total_frames / (ms * 1e-3), ms_per_step=ms / steps, scaling=scaling,
                 e2e={"value": k_e2e * total_frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                      "d2h_bytes_per_step": d2h, "steps": k_e2e},
-                gpu_launches=int(launches), clocks=clocks, roofline=roofline, roofline_conv=roofline_conv, dp=dp, trk=trk)
+                gpu_launches=int(launches), clocks=clocks, roofline=roofline, roofline_conv=roofline_conv, dp=dp, trk=trk,
+                pipeline={"what": "sequences run back to back (Tracker.run_dataset semantics): the host half of the next "
+                                  "sequence's first-frame initialisation (OpenCV cut-out / inpaint, candidate masks) is prepared "
+                                  "in worker threads behind the current sequence's tracking; every step does one such "
+                                  "preparation and consumes one",
+                          "without_overlap": {"value": k_e2e * total_frames / (ms_np * 1e-3), "unit": "frames/s",
+                                              "ms_per_step": ms_np / k_e2e, "steps": k_e2e}})
 
 
 def measured_traffic(cfg, M):
@@ -493,7 +516,7 @@ def main():
         "metric": METRIC, "value": r["value"], "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": r["scaling"], "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": config, "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "clocks": r["clocks"],
-        "roofline": r["roofline"], "roofline_conv": r["roofline_conv"], "cpu_baseline": None,
+        "roofline": r["roofline"], "roofline_conv": r["roofline_conv"], "pipeline": r["pipeline"], "cpu_baseline": None,
         "host": "%d cores, wait policy %s" % (cores, wait_policy),
     }
     del r
@@ -523,7 +546,7 @@ def main():
                 others[CONFIGS[k]["name"]] = {
                     "value": o["value"], "unit": "frames/s", "ms_per_step": o["ms_per_step"], "steps": 3, "warmup": 3,
                     "e2e": o["e2e"], "gpu_launches": o["gpu_launches"], "clocks": o["clocks"], "roofline": o["roofline"],
-                    "roofline_conv": o["roofline_conv"],
+                    "roofline_conv": o["roofline_conv"], "pipeline": o["pipeline"],
                     "config": workload_config(CONFIGS[k], o["dp"], 1, cores, wait_policy)}
                 del o
             except Exception as e:                                        # noqa: BLE001

@@ -98,6 +98,11 @@ class Tracker(nn.Module):
         # the next, so ONE captured CUDA graph of a full block serves all sequences with the same number of objects.
         self._obj_pool = {}
         self._lut_buf = None
+        # First-frame augmentations of the NEXT sequence prepared behind the current one's tracking (``prefetch_init``):
+        # {(id(sequence), frame): record}.  Half of an initialisation is host work (OpenCV inpaint of the cut-out object)
+        # that depends on the first frame and its ground truth only — both known before the sequence starts.
+        self._prefetched = {}
+        self.prefetch_next = os.environ.get("FRTM_PREFETCH_INIT", "1") == "1"
         self.graph_captures = 0     # how many times a block graph was captured (tests / diagnostics)
 
     def clear(self):
@@ -146,7 +151,7 @@ class Tracker(nn.Module):
                 if hasattr(nxt, "preload_async"):
                     nxt.preload_async(self.device)
             self.clear()
-            outputs, seq_fps = self.run_sequence(sequence, speedrun)
+            outputs, seq_fps = self.run_sequence(sequence, speedrun, next_sequence=dataset[k + 1] if k + 1 < n_seq else None)
             if not np.isnan(seq_fps):
                 fps_sum, fps_n = fps_sum + seq_fps, fps_n + 1
             dst = out_path / sequence.name
@@ -157,7 +162,10 @@ class Tracker(nn.Module):
                 sequence.release()
         print("Average frame rate: %.2f fps" % (fps_sum / max(fps_n, 1)))
 
-    def run_sequence(self, sequence, speedrun=False):
+    def run_sequence(self, sequence, speedrun=False, next_sequence=None):
+        """``next_sequence`` (optional, not in the reference signature): the sequence that will be run after this one; the
+        host part of its first-frame initialisation (augmentation) is prepared in worker threads while this sequence is
+        tracked.  Results are identical with and without it."""
         self.eval()
         self.object_ids = sequence.obj_ids
         self.current_frame = 0
@@ -198,7 +206,11 @@ class Tracker(nn.Module):
                 image = image.to(self.device)
                 if len(new_objects) > 0:
                     labels = labels.to(self.device)
-                    self.initialize(image, labels, new_objects)
+                    pf = self._prefetched.pop((id(sequence), i), None)
+                    if pf is None:
+                        self.initialize(image, labels, new_objects)        # the reference's call
+                    else:
+                        self.initialize(image, labels, new_objects, prefetched=pf)
                 if had_targets:
                     self.track(image)
                     labels = self._last_labels.unsqueeze(0) if single else self._last_labels
@@ -212,6 +224,9 @@ class Tracker(nn.Module):
                 continue
             nb = self._block_length(i, n_frames, lambda j: j < n_frames and len(item(j)[2]) > 0)
             images = [item(j)[0].to(self.device, non_blocking=True) for j in range(i, i + nb)]
+            if next_sequence is not None and self.prefetch_next:
+                self.prefetch_init(next_sequence)         # once: behind the first track block of this sequence
+                next_sequence = None
             for lab in self._track_block(images):
                 outputs.append(lab.unsqueeze(0) if single else lab)
             for j in range(i, i + nb):
@@ -243,7 +258,77 @@ class Tracker(nn.Module):
         if d.update_optimizer is not None:
             d.update_optimizer.x[0] = d.filter.weight
 
-    def initialize(self, image, labels, new_objects):
+    def _augment_uses_rng(self):
+        if getattr(self, "_augment_takes_rng", None) is None:
+            import inspect
+            try:
+                self._augment_takes_rng = "rng" in inspect.signature(self.augment).parameters
+            except (TypeError, ValueError):
+                self._augment_takes_rng = False
+        return self._augment_takes_rng
+
+    def _aug_pool(self):
+        if getattr(self, "_pool", None) is None:
+            from concurrent.futures import ThreadPoolExecutor
+            self._pool = ThreadPoolExecutor(max_workers=self.augment_workers, thread_name_prefix="frtm-aug")
+        return self._pool
+
+    def prefetch_init(self, sequence, frame=0):
+        """Start the first-frame augmentations of ``sequence`` (every object that starts in ``frame``) in the worker threads,
+        on side streams of their own; ``run_sequence(sequence)`` picks the views up in ``initialize``.  The views depend on
+        the frame, its ground truth and a per-object ``RandomState(0)`` only (``model/tracker.py:178-183``), so they are
+        the ones ``initialize`` would compute itself."""
+        key = (id(sequence), frame)
+        if key in self._prefetched or not self._augment_uses_rng():
+            return
+        image, labels, new_objects = sequence[frame]
+        if len(new_objects) == 0:
+            return
+        n_new = len(new_objects)
+        main = torch.cuda.current_stream()
+        if getattr(self, "_pf_streams", None) is None or len(self._pf_streams) < n_new:
+            self._pf_streams = [torch.cuda.Stream(device=self.device) for _ in range(n_new)]
+        up = self._pf_streams[0]
+        up.wait_stream(main)
+        with torch.cuda.stream(up):                   # the first frame may still be on the host (pinned): upload it here
+            image_d = image.to(self.device, non_blocking=True)
+            labels_d = labels.to(self.device, non_blocking=True)
+            uploaded = up.record_event()
+
+        def job(k):
+            side = self._pf_streams[k]
+            with torch.cuda.stream(side):
+                side.wait_event(uploaded)
+                image_d.record_stream(side); labels_d.record_stream(side)
+                mask = (labels_d == new_objects[k]).byte()
+                im, msk = self.augment(image_d, mask, rng=np.random.RandomState(0))
+                im, msk = im.to(self.device), msk.to(self.device)
+                return im, msk, side.record_event()
+
+        pool = self._aug_pool()
+        futures = [pool.submit(job, k) for k in range(n_new)]
+        layer = self.disc_params["layer"]
+
+        def features():
+            # the views of all objects through the backbone as ONE batch (the pass does not depend on the target models,
+            # which ``initialize`` draws and fits at the reference's place in the random stream)
+            res = [f.result() for f in futures]
+            side = self._pf_streams[0]
+            with torch.cuda.stream(side):
+                for im, msk, ev in res:
+                    side.wait_event(ev)
+                    im.record_stream(side)
+                _, f32, _ = self.feature_extractor.forward_split(torch.cat([r[0] for r in res]), (), (layer,), upto=layer)
+                x, done = f32[layer], side.record_event()
+            nv = res[0][0].shape[0]
+            return [(res[k][0], res[k][1], done, x[k * nv:(k + 1) * nv]) for k in range(n_new)]
+
+        self._prefetched[key] = dict(sequence=sequence, objects=tuple(new_objects), keep=(image_d, labels_d), futures=futures,
+                                     features=pool.submit(features))
+        while len(self._prefetched) > 2:              # an entry whose sequence never ran
+            self._prefetched.pop(next(iter(self._prefetched)))
+
+    def initialize(self, image, labels, new_objects, prefetched=None):
         """Create and fit a target model per new object (``:165-191``).
 
         Augmentation is host work (OpenCV inpaint, spec drawing) plus a few device kernels and one small device->host read
@@ -283,18 +368,12 @@ class Tracker(nn.Module):
                 im, msk = im.to(self.device), msk.to(self.device)
                 return im, msk, side.record_event()
 
-        if getattr(self, "_augment_takes_rng", None) is None:
-            import inspect
-            try:
-                self._augment_takes_rng = "rng" in inspect.signature(self.augment).parameters
-            except (TypeError, ValueError):
-                self._augment_takes_rng = False
-        workers = min(n_new, self.augment_workers) if self._augment_takes_rng else 1
-        if workers > 1:
-            if getattr(self, "_pool", None) is None:
-                from concurrent.futures import ThreadPoolExecutor
-                self._pool = ThreadPoolExecutor(max_workers=self.augment_workers, thread_name_prefix="frtm-aug")
-            futures = [self._pool.submit(augment_job, k) for k in range(n_new)]
+        workers = min(n_new, self.augment_workers) if self._augment_uses_rng() else 1
+        if prefetched is not None and prefetched["objects"] == tuple(new_objects):
+            results = iter(prefetched["features"].result())                # prepared behind the previous sequence
+        elif workers > 1:
+            pool = self._aug_pool()
+            futures = [pool.submit(augment_job, k) for k in range(n_new)]
             results = (f.result() for f in futures)
         else:
             def sequential():
@@ -305,11 +384,18 @@ class Tracker(nn.Module):
         # Object k is fitted on its own stream k (the one its augmentation ran on): the fits are chains of small kernels
         # (~650 per object, replayed as one CUDA graph each) that leave most of the GPU idle, so the objects of a frame
         # overlap on the device instead of queueing behind each other.
-        for k, (target, (im, msk, ready)) in enumerate(zip(targets, results)):
+        for k, (target, (im, msk, ready, *feat)) in enumerate(zip(targets, results)):
             side = self._aug_streams[k]
             with torch.cuda.stream(side):
-                _, f32, _ = self.feature_extractor.forward_split(im, (), (target.disc_layer,), upto=target.disc_layer)
-                target.discriminator.init(None, msk, x_nhwc=f32[target.disc_layer])
+                side.wait_event(ready)               # a no-op unless the views come from prefetch_init's streams
+                im.record_stream(side); msk.record_stream(side)
+                if feat:                             # prefetched: the backbone pass is done as well
+                    x = feat[0]
+                    x.record_stream(side)
+                else:
+                    _, f32, _ = self.feature_extractor.forward_split(im, (), (target.disc_layer,), upto=target.disc_layer)
+                    x = f32[target.disc_layer]
+                target.discriminator.init(None, msk, x_nhwc=x)
         for k, target in enumerate(targets):
             main.wait_stream(self._aug_streams[k])
             d = target.discriminator
@@ -356,13 +442,23 @@ class Tracker(nn.Module):
                 break
         return max(n, 1)
 
+    def _frame_index(self, nF, n, dev):
+        """Object index of every (frame, object) row of a block, one cached tensor per block shape (its address is part of
+        the captured graph of that block length)."""
+        if getattr(self, "_fidx", None) is None:
+            self._fidx = {}
+        t = self._fidx.get((nF, n))
+        if t is None or t.device != torch.device(dev):
+            t = self._fidx[(nF, n)] = torch.arange(n, dtype=torch.int32, device=dev).repeat(nF).contiguous()
+        return t
+
     def _live_at(self, frame):
         return [t for t in self.targets.values() if t.start_frame < frame]
 
     def _track_block(self, images):
         """Tracks ``len(images)`` consecutive frames in one batched pass; returns the list of uint8 label maps."""
         nF = len(images)
-        if self.graph_blocks and nF == self.max_block and nF > 1 and self.disc_params["update_filters"] \
+        if self.graph_blocks and 1 < nF <= self.max_block and self.disc_params["update_filters"] \
                 and not any(t.start_frame == self.current_frame for t in self.targets.values()):
             out = self._track_block_graphed(images)
             if out is not None:
@@ -383,8 +479,7 @@ class Tracker(nn.Module):
         dev = images[0].device
         if getattr(self.refiner, "_packed", 0) is None:
             self.refiner._pack()                          # host-side weight packing uploads pageable tensors
-        if getattr(self, "_fidx", None) is None or self._fidx[0] != (nF, n):
-            self._fidx = ((nF, n), torch.arange(n, dtype=torch.int32, device=dev).repeat(nF).contiguous())
+        fidx = self._frame_index(nF, n, dev)
         if getattr(self, "_counts", None) is None or self._counts.numel() < n:
             self._counts = torch.zeros(max(n, 8), dtype=torch.int32, device=dev)
             self._gn_table = None
@@ -401,12 +496,14 @@ class Tracker(nn.Module):
                      d.update_optimizer.cg_state.data_ptr(), d.filter.weight.data_ptr()]
         key = (nF, n, tuple(images[0].shape[-2:]), tuple(addr), self._fbuf.data_ptr(), pc.wt.data_ptr(), pc.oscale.data_ptr(),
                self._lut.data_ptr(), len(self.object_ids) == 1, tuple(int(v) for v in d0.update_iters), self._counts.data_ptr(),
-               self._counts_blk.data_ptr(), self._fidx[1].data_ptr(), self._gn_table[1].data_ptr(), self._gn_table[2].data_ptr())
-        g = self._blk_graph
+               self._counts_blk.data_ptr(), fidx.data_ptr(), self._gn_table[1].data_ptr(), self._gn_table[2].data_ptr())
+        if not isinstance(self._blk_graph, dict):
+            self._blk_graph = {}                           # one graph per block length (full blocks and the aligned tail)
+        g = self._blk_graph.get(nF)
         frames = [im if im.dim() == 3 else im[0] for im in images]
         main = torch.cuda.current_stream()
         if g is None or g["key"] != key:
-            self._blk_graph = None
+            self._blk_graph.pop(nF, None)
             static_in = torch.stack(frames)
             side = torch.cuda.Stream(device=dev)
             graph = torch.cuda.CUDAGraph()
@@ -439,7 +536,7 @@ class Tracker(nn.Module):
             g = dict(key=key, graph=graph, static_in=static_in, labels=self._blk_labels_all, masks=self.current_masks,
                      samples=[t.discriminator.current_sample for t in live], keep=(side,),
                      kernels=int(lib().launch_count() - launches0))
-            self._blk_graph = g
+            self._blk_graph[nF] = g
             self.graph_captures += 1
         else:
             torch.stack(frames, out=g["static_in"])
@@ -488,9 +585,7 @@ class Tracker(nn.Module):
 
         # classify: one conv for all projections of all frames, one correlation for all filters
         samples = ops.conv2d_tc(fmap, self._stacked_projection(live), out_f32=False, nchw=True)["nchw"].view(nF * n, c, h, w)
-        if getattr(self, "_fidx", None) is None or self._fidx[0] != (nF, n):
-            self._fidx = ((nF, n), torch.arange(n, dtype=torch.int32, device=dev).repeat(nF).contiguous())
-        scores = ops.corr3x3(samples, self._fbuf, self._fidx[1])
+        scores = ops.corr3x3(samples, self._fbuf, self._frame_index(nF, n, dev))
         logits = self.refiner.forward_nhwc(scores, feats, im_size).view(nF, n, *im_size)
 
         fresh = [t for t in self.targets.values() if t.start_frame == self.current_frame]

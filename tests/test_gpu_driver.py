@@ -144,10 +144,10 @@ def test_run_dataset_async_preload_equals_preloaded_path(tmp_path):
     seeds = iter([11, 11, 11])
     orig_run = trk.run_sequence
 
-    def seeded(sequence, speedrun=False):
+    def seeded(sequence, speedrun=False, **kw):
         torch.manual_seed(next(seeds))
         assert sequence.preloaded_images is not None and all(t.is_cuda for t in sequence.preloaded_images)
-        return orig_run(sequence, speedrun)
+        return orig_run(sequence, speedrun, **kw)
 
     trk.run_sequence = seeded
     try:
@@ -163,16 +163,17 @@ def test_run_dataset_async_preload_equals_preloaded_path(tmp_path):
 
 
 def test_block_graph_is_captured_once_and_matches_eager():
-    """``graph_blocks``: full 8-frame blocks are replayed as one CUDA graph.  With the per-slot target-model buffers pooled
-    across sequences the graph captured on the first sequence serves the following ones (same object count): identical
-    labels, filters and memory weights to the eager path, one capture for three sequences."""
+    """``graph_blocks``: blocks aligned to the update schedule are replayed as one CUDA graph per block length (full 8-frame
+    blocks and the shorter tail of a sequence).  With the per-slot target-model buffers pooled across sequences the graphs
+    captured on the first sequence serve the following ones (same object count): identical labels, filters and memory
+    weights to the eager path, one capture per block length for three sequences."""
     from frtm_vos_b200 import synth
     trk_e, _, _ = _tracker()
     trk_e.graph_blocks = False
     trk_g, _, _ = _tracker()
     trk_g.graph_blocks = True
-    seqs = [synth.SyntheticSequence(num_objects=2, num_frames=25, size=SIZE, seq_id=30 + k) for k in range(3)]
-    for seq in seqs:
+    seqs = [synth.SyntheticSequence(num_objects=2, num_frames=29, size=SIZE, seq_id=30 + k) for k in range(3)]
+    for seq in seqs:                                     # 28 tracked frames: three full blocks + a 4-frame tail
         torch.manual_seed(11)
         a, _ = trk_e.run_sequence(seq)
         torch.manual_seed(11)
@@ -183,5 +184,53 @@ def test_block_graph_is_captured_once_and_matches_eager():
             de, dg = trk_e.targets[o].discriminator, trk_g.targets[o].discriminator
             assert torch.equal(de.filter.weight.cpu(), dg.filter.weight.cpu())
             assert torch.equal(de.memory.weights.cpu(), dg.memory.weights.cpu())
-    assert trk_g.graph_captures == 1, trk_g.graph_captures
+    assert trk_g.graph_captures == 2, trk_g.graph_captures
     assert trk_e.graph_captures == 0
+
+
+def test_prefetched_initialisation_gives_identical_sequences():
+    """``run_sequence(seq, next_sequence=nxt)`` prepares the first-frame augmentations of ``nxt`` in worker threads behind
+    the tracking of ``seq`` (``Tracker.prefetch_init``); ``nxt`` must then run exactly as without the overlap: same views,
+    hence bit-identical labels, filters and memory weights.  Device-resident and host (pinned) sequences."""
+    from frtm_vos_b200 import synth
+    trk, fe, seq_a = _tracker(n_frames=18, n_obj=2, seq_id=3)
+    seq_b = synth.SyntheticSequence(num_objects=3, num_frames=18, size=SIZE, seq_id=5)
+
+    def run(seq, nxt):
+        torch.manual_seed(5)
+        outs, _ = trk.run_sequence(seq, next_sequence=nxt)
+        filt = [trk.targets[o].discriminator.filter.weight.detach().clone() for o in seq.obj_ids]
+        wts = [trk.targets[o].discriminator.memory.weights.clone() for o in seq.obj_ids]
+        return [o.cpu() for o in outs], filt, wts
+
+    trk.prefetch_next = False
+    ref_b = run(seq_b, None)
+    trk.prefetch_next = True
+    run(seq_a, seq_b)                                     # prepares seq_b's three objects
+    assert (id(seq_b), 0) in trk._prefetched and len(trk._prefetched[(id(seq_b), 0)]["futures"]) == 3
+    got_b = run(seq_b, seq_a)                             # consumes them (and prepares seq_a's)
+    assert (id(seq_b), 0) not in trk._prefetched
+    for a, b in zip(ref_b[0], got_b[0]):
+        assert torch.equal(a, b)
+    for a, b in zip(ref_b[1] + ref_b[2], got_b[1] + got_b[2]):
+        assert torch.equal(a, b)
+
+    class Host:                                           # frames in pinned host memory: the prefetch uploads frame 0 itself
+        def __init__(self, seq):
+            self.name, self.obj_ids, self.frame_names = seq.name, seq.obj_ids, seq.frame_names
+            self.items = [(im.pin_memory(), (lb.pin_memory() if torch.is_tensor(lb) else lb), ids)
+                          for im, lb, ids in (seq[t] for t in range(len(seq)))]
+
+        def __len__(self):
+            return len(self.items)
+
+        def __getitem__(self, i):
+            return self.items[i]
+
+    hb = Host(seq_b)
+    run(seq_a, hb)
+    got_h = run(hb, None)
+    for a, b in zip(ref_b[0], got_h[0]):
+        assert torch.equal(a, b)
+    for a, b in zip(ref_b[1] + ref_b[2], got_h[1] + got_h[2]):
+        assert torch.equal(a, b)

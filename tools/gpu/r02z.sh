@@ -1,0 +1,9 @@
+#!/bin/bash
+O=gpurun_out/r02z; mkdir -p $O
+timeout 900 python -m pytest tests/test_gpu_driver.py -x -q -m gpu > $O/pytest_driver.log 2>&1; tail -15 $O/pytest_driver.log
+timeout 900 python bench.py --steps 8 --warmup 3 --no-cpu-baseline > $O/bench2.json 2> $O/bench2.err
+python tools/bench_brief.py $O/bench2.json 2>&1 | head -3; python -c "
+import json;d=json.loads(open('$O/bench2.json').read().strip().splitlines()[-1]);print(d['pipeline']['without_overlap'])"; tail -3 $O/bench2.err
+timeout 900 python bench.py --config 3 --steps 4 --warmup 3 --no-cpu-baseline > $O/bench3.json 2> $O/bench3.err
+python tools/bench_brief.py $O/bench3.json 2>&1 | head -3; python -c "
+import json;d=json.loads(open('$O/bench3.json').read().strip().splitlines()[-1]);print(d['pipeline']['without_overlap'])"; tail -3 $O/bench3.err
