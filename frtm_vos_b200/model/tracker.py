@@ -151,7 +151,10 @@ class Tracker(nn.Module):
                 if hasattr(nxt, "preload_async"):
                     nxt.preload_async(self.device)
             self.clear()
-            outputs, seq_fps = self.run_sequence(sequence, speedrun, next_sequence=dataset[k + 1] if k + 1 < n_seq else None)
+            if k + 1 < n_seq and getattr(self, "prefetch_next", False):
+                outputs, seq_fps = self.run_sequence(sequence, speedrun, next_sequence=dataset[k + 1])
+            else:
+                outputs, seq_fps = self.run_sequence(sequence, speedrun)
             if not np.isnan(seq_fps):
                 fps_sum, fps_n = fps_sum + seq_fps, fps_n + 1
             dst = out_path / sequence.name

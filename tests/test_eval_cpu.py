@@ -178,7 +178,7 @@ def test_run_dataset_prefetches_the_next_sequence_and_writes_indexed_pngs(davis_
             events.append(("prefetch", self.name))
         return orig(self, device)
 
-    def run_sequence(sequence, speedrun=False):
+    def run_sequence(sequence, speedrun=False, **kw):
         events.append(("run", sequence.name))
         assert sequence.preloaded_images is not None
         outs = []
