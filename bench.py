@@ -255,6 +255,8 @@ def run_b200(cfg, steps, warmup, dev, rank, world, dist, with_clocks):
         s.preload(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
+    pinned_out = [None]
+
     def step(seqs, read_back=False):
         # the rank's sequences run back to back as in Tracker.run_dataset: while one is tracked, the host half of the next
         # one's first-frame initialisation (augmentation) is prepared in worker threads; the sequence after the last one
@@ -266,7 +268,13 @@ def run_b200(cfg, steps, warmup, dev, rank, world, dist, with_clocks):
         labels = torch.stack(maps)                                 # (S,T,H,W) uint8
         if world > 1:
             gather_label_maps(labels, world)                       # end-of-batch gather of the label maps (NCCL/NVLink)
-        return labels.cpu() if read_back else labels
+        if not read_back:
+            return labels
+        if pinned_out[0] is None or pinned_out[0].shape != labels.shape:
+            pinned_out[0] = torch.empty(labels.shape, dtype=labels.dtype).pin_memory()
+        pinned_out[0].copy_(labels, non_blocking=True)             # device -> pinned host; the step's sync() completes it
+        torch.cuda.current_stream().synchronize()
+        return pinned_out[0]
 
     def sync():
         torch.cuda.synchronize()

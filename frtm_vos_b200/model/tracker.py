@@ -199,6 +199,30 @@ class Tracker(nn.Module):
                 new_cache[i] = sequence[i]
             return new_cache[i]
 
+        # Frames that live on the host are uploaded one block AHEAD on a copy stream: the H2D of block b+1 runs behind the
+        # kernels of block b (and the first block's behind the initialisation) instead of in front of its own block.
+        ahead = {}
+        main = torch.cuda.current_stream()
+
+        def upload_ahead(j0, j1):
+            for j in range(j0, min(j1, n_frames)):
+                im = item(j)[0]
+                if j in ahead or not torch.is_tensor(im) or im.is_cuda:
+                    continue
+                if getattr(self, "_h2d_stream", None) is None:
+                    self._h2d_stream = torch.cuda.Stream(device=self.device)
+                with torch.cuda.stream(self._h2d_stream):
+                    d = im.to(self.device, non_blocking=True)
+                    ahead[j] = (d, self._h2d_stream.record_event())
+
+        def frame(j):
+            if j in ahead:
+                d, ev = ahead.pop(j)
+                main.wait_event(ev)
+                d.record_stream(main)
+                return d
+            return item(j)[0].to(self.device, non_blocking=True)
+
         t0 = time()
         i = 0
         n_frames = len(sequence)
@@ -206,7 +230,8 @@ class Tracker(nn.Module):
             image, labels, new_objects = item(i)
             had_targets = len(self.targets) > 0
             if len(new_objects) > 0 or not had_targets:
-                image = image.to(self.device)
+                upload_ahead(i + 1, i + 1 + self.max_block)
+                image = frame(i)
                 if len(new_objects) > 0:
                     labels = labels.to(self.device)
                     pf = self._prefetched.pop((id(sequence), i), None)
@@ -226,12 +251,13 @@ class Tracker(nn.Module):
                 N += 1
                 continue
             nb = self._block_length(i, n_frames, lambda j: j < n_frames and len(item(j)[2]) > 0)
-            images = [item(j)[0].to(self.device, non_blocking=True) for j in range(i, i + nb)]
+            images = [frame(j) for j in range(i, i + nb)]
             if next_sequence is not None and self.prefetch_next:
                 self.prefetch_init(next_sequence)         # once: behind the first track block of this sequence
                 next_sequence = None
             for lab in self._track_block(images):
                 outputs.append(lab.unsqueeze(0) if single else lab)
+            upload_ahead(i + nb, i + nb + self.max_block)
             for j in range(i, i + nb):
                 new_cache.pop(j, None)
             self.current_frame += nb
