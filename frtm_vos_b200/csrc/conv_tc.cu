@@ -594,6 +594,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
+  __syncthreads();                          // (the cluster barrier below implies it; racecheck only knows this one)
   pair_sync_all();                          // barriers of both CTAs initialised, TMEM of both allocated
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
