@@ -440,7 +440,7 @@ __device__ __forceinline__ void pair_epilogue_store(const TcArgs &a, float *tile
       pp[u] = idx / G;
       cc[u] = (idx - pp[u] * G) * 8;
       const int py = y0 + pp[u] / TC_TW, px = x0 + pp[u] % TC_TW;
-      ok[u] = py < a.Ho && px < a.Wo;
+      ok[u] = py < a.Ho && px < a.Wo && b < a.B;
       pix[u] = ((int64_t)b * a.Ho + py) * a.Wo + px;
       rh4[u] = make_uint4(0u, 0u, 0u, 0u); rl4[u] = rh4[u];
       rf[u][0] = make_float4(0.f, 0.f, 0.f, 0.f); rf[u][1] = rf[u][0];
@@ -531,7 +531,7 @@ __device__ __forceinline__ void pair_epilogue_store(const TcArgs &a, float *tile
     for (int idx = te; idx < 128 * BN; idx += 256) {
       const int p = idx & 127, c = idx >> 7;
       const int py = y0 + p / TC_TW, px = x0 + p % TC_TW;
-      if (py < a.Ho && px < a.Wo) a.y_nchw[((int64_t)b * a.Cout + n0 + c) * hw + (int64_t)py * a.Wo + px] = tile[p * LDT + c];
+      if (py < a.Ho && px < a.Wo && b < a.B) a.y_nchw[((int64_t)b * a.Cout + n0 + c) * hw + (int64_t)py * a.Wo + px] = tile[p * LDT + c];
     }
   }
 }
@@ -710,7 +710,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
     TC2_STAMP(4);
-    if (b < a.B) pair_epilogue_store<BN>(a, tile, (int)threadIdx.x - 64, b, y0, x0, n0);
+    pair_epilogue_store<BN>(a, tile, (int)threadIdx.x - 64, b, y0, x0, n0);
     TC2_STAMP(5);
   }
   tc_fence_before();
@@ -727,6 +727,191 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
            blockIdx.x, tc2_stamps[0][0], tc2_stamps[1][1], tc2_stamps[1][2], tc2_stamps[2][3], tc2_stamps[2][4], tc2_stamps[2][5],
            tc2_stamps[9][3], tc2_stamps[9][4], tc2_stamps[9][5], tc2_stamps[2][6], clock64() - t_start);
 #endif
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Persistent form of the CTA-pair kernel for the shapes with several tiles per SM (the K = 64..256 expand convs of the
+// bottleneck stages, the stage-2 convs): there the launch is its epilogue — a 128 x 256 tile means 128 KB of residual reads
+// and 128 KB of split-plane writes per CTA, DRAM-bound when every CTA of a wave stores at the same time while the tensor pipe
+// idles, followed by the next wave's cold prologue.  Here one pair per TPC walks the (pixel-pair, N tile) items; pair tile
+// N = 128 (HALF = 64) so that three 48 KB stages leave room for a DEDICATED [128][132] fp32 staging tile, and the 512 TMEM
+// columns are four accumulator slots (one k-block each): while the eight epilogue warps stage and store item i, the
+// producer and the MMA warp run up to four k-blocks — whole items at K <= 256 — ahead.
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int P2P_STAGES = 3, P2P_SLOTS = 4;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P2_THREADS, 1)
+conv_tc2p_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+                 const __grid_constant__ CUtensorMap tm_w, const TcArgs a, const int n_items, const int ntiles_n) {
+  constexpr int HALF = 64, BN = 128;
+  constexpr int B_PLANE = HALF * 128;
+  constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_PLANE;            // 48 KB
+  constexpr int TILE_BYTES = 128 * (BN + 4) * 4;                       // staging tile
+  constexpr int SLOT = BN;
+  constexpr int COLS = 512;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
+  float *tile = reinterpret_cast<float *>(gen + P2P_STAGES * STAGE_BYTES);
+  constexpr int TAIL = P2P_STAGES * STAGE_BYTES + TILE_BYTES;
+  const uint32_t bar_full = base + TAIL;
+  const uint32_t bar_empty = bar_full + 8 * P2P_STAGES;
+  const uint32_t bar_accf = bar_empty + 8 * P2P_STAGES;               // P2P_SLOTS x 8 B
+  const uint32_t bar_acce = bar_accf + 8 * P2P_SLOTS;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gen + TAIL + 16 * P2P_STAGES + 16 * P2P_SLOTS);
+  float *s_osc = reinterpret_cast<float *>(gen + TAIL + 16 * P2P_STAGES + 16 * P2P_SLOTS + 16);   // [2 halves][osc 64 | bias 64]
+
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  const uint32_t rank = pair_ctarank();
+  const int tiles_per_img = a.tiles_x * a.tiles_y;
+  const int nkb = a.kh * a.kw * a.kchunks;
+  const int cluster = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_hi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_lo)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_w)) : "memory");
+    for (int s = 0; s < P2P_STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int j = 0; j < P2P_SLOTS; ++j) {
+      mbar_init(bar_accf + 8 * j, 1);
+      mbar_init(bar_acce + 8 * j, 16);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  pair_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---- producer (both CTAs) ----
+    const uint32_t lead_full = mapa_shared(bar_full, 0);
+    uint32_t it = 0;
+    for (int item = cluster; item < n_items; item += n_clusters) {
+      const int pairi = item / ntiles_n, ntile = item - pairi * ntiles_n;
+      const int tl = 2 * pairi + (int)rank;
+      const int b = tl / tiles_per_img, tr = tl - b * tiles_per_img;
+      const int y0 = (tr / a.tiles_x) * TC_TH, x0 = (tr % a.tiles_x) * TC_TW;
+      const int sub0 = (ntile * BN + (int)rank * HALF) / 64;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % P2P_STAGES;
+        mbar_wait(bar_empty + 8 * s, ((it / P2P_STAGES) & 1) ^ 1);
+        const int tap = kb / a.kchunks, kc = kb - tap * a.kchunks;
+        const int ky = tap / a.kw, kx = tap - ky * a.kw;
+        const uint32_t sa = base + s * STAGE_BYTES;
+        if (elect_one()) {
+          if (rank == 0) mbar_expect_tx(bar_full + 8 * s, 2 * STAGE_BYTES);
+          const uint32_t fb = lead_full + 8 * s;
+          tma2_load_4d(sa, &tm_hi, kc * TC_BK, x0 * a.stride + kx - a.pad, y0 * a.stride + ky - a.pad, b, fb);
+          tma2_load_4d(sa + TC_A_BYTES, &tm_lo, kc * TC_BK, x0 * a.stride + kx - a.pad, y0 * a.stride + ky - a.pad, b, fb);
+          const int row = (sub0 * nkb + kb) * 128;
+          tma2_load_2d(sa + 2 * TC_A_BYTES, &tm_w, 0, row, fb);
+          tma2_load_2d(sa + 2 * TC_A_BYTES + B_PLANE, &tm_w, 0, row + 64, fb);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      // ---- MMA issuer (leader): one k-block per accumulator slot ----
+      constexpr uint32_t idesc = umma_idesc(256, BN);
+      uint32_t it = 0;
+      for (int item = cluster; item < n_items; item += n_clusters) {
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % P2P_STAGES;
+          const uint32_t slot = it % P2P_SLOTS;
+          mbar_wait(bar_acce + 8 * slot, ((it / P2P_SLOTS) & 1) ^ 1);      // drained by both CTAs' epilogues
+          mbar_wait(bar_full + 8 * s, (it / P2P_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t tacc = tmem_base + slot * SLOT;
+          const uint32_t sa = base + s * STAGE_BYTES;
+          const uint64_t a_hi = umma_desc(sa), a_lo = umma_desc(sa + TC_A_BYTES);
+          const uint64_t b_hi = umma_desc(sa + 2 * TC_A_BYTES), b_lo = umma_desc(sa + 2 * TC_A_BYTES + B_PLANE);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k) {
+              const uint64_t adv = (uint64_t)(k * 32 >> 4);
+              umma2_f16(tacc, a_hi + adv, b_hi + adv, idesc, k == 0 ? 0u : 1u);
+              umma2_f16(tacc, a_hi + adv, b_lo + adv, idesc, 1u);
+              umma2_f16(tacc, a_lo + adv, b_hi + adv, idesc, 1u);
+            }
+            umma2_commit(bar_empty + 8 * s);
+            umma2_commit(bar_accf + 8 * slot);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ---- epilogue (both CTAs): warp = (TMEM lane quarter q, column half h) ----
+    const int q = warp & 3, h = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const int te = (int)threadIdx.x - 64;
+    const uint32_t lead_acce = mapa_shared(bar_acce, 0);
+    uint32_t it = 0;
+    for (int item = cluster; item < n_items; item += n_clusters) {
+      const int pairi = item / ntiles_n, ntile = item - pairi * ntiles_n;
+      const int tl = 2 * pairi + (int)rank;
+      const int b = tl / tiles_per_img, tr = tl - b * tiles_per_img;
+      const int y0 = (tr / a.tiles_x) * TC_TH, x0 = (tr % a.tiles_x) * TC_TW;
+      const int n0 = ntile * BN;
+      if (te < BN) {                          // this item's scales / biases (read by the tile write below, after barrier A)
+        const int hh = te / HALF, ii = te - hh * HALF;
+        s_osc[hh * 2 * HALF + ii] = a.oscale[n0 + te];
+        s_osc[hh * 2 * HALF + HALF + ii] = (a.bias != nullptr && n0 + te < a.Cout) ? a.bias[n0 + te] : 0.f;
+      }
+      float acc[HALF];
+#pragma unroll
+      for (int j = 0; j < HALF; ++j) acc[j] = 0.f;
+#pragma unroll 1
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const uint32_t slot = it % P2P_SLOTS;
+        mbar_wait(bar_accf + 8 * slot, (it / P2P_SLOTS) & 1);
+        tc_fence_after();
+        const uint32_t col0 = tmem_base + ((uint32_t)(q * 32) << 16) + slot * SLOT + (uint32_t)(h * HALF);
+#pragma unroll
+        for (int c0 = 0; c0 < HALF; c0 += 32) {
+          float t[32];
+          tmem_ld32(col0 + c0, t);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[c0 + j] += t[j];
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (rank == 0) mbar_arrive_local(bar_acce + 8 * slot);
+          else mbar_arrive_cluster(lead_acce + 8 * slot);
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");      // A: scales staged, the previous item's store loop is over
+      {
+        const float *so = s_osc + h * 2 * HALF, *sb = so + HALF;
+        float *trow = tile + row * (BN + 4) + h * HALF;
+#pragma unroll
+        for (int c0 = 0; c0 < HALF; c0 += 4)
+          *reinterpret_cast<float4 *>(trow + c0) =
+              make_float4(fmaf(acc[c0], so[c0], sb[c0]), fmaf(acc[c0 + 1], so[c0 + 1], sb[c0 + 1]),
+                          fmaf(acc[c0 + 2], so[c0 + 2], sb[c0 + 2]), fmaf(acc[c0 + 3], so[c0 + 3], sb[c0 + 3]));
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");      // B: tile complete
+      pair_epilogue_store<BN>(a, tile, te, b, y0, x0, n0);
+    }
+  }
+  tc_fence_before();
+  pair_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(COLS) : "memory");
+  }
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -1274,6 +1459,23 @@ static int launch_tc2(const CUtensorMap &mh, const CUtensorMap &ml, const CUtens
   return FRTM_OK;
 }
 
+static int launch_tc2p(const CUtensorMap &mh, const CUtensorMap &ml, const CUtensorMap &mw, const TcArgs &a, int num_sms, cudaStream_t st) {
+  constexpr int smem = P2P_STAGES * (2 * TC_A_BYTES + 2 * 64 * 128) + 128 * 132 * 4 + 16 * P2P_STAGES + 16 * P2P_SLOTS + 16 + 1024 + 1024;
+  static_assert(smem <= 227 * 1024, "conv_tc2p: shared memory budget");
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { set_error("conv_tc2p: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return FRTM_ELAUNCH; }
+    configured = true;
+  }
+  const int ntiles = a.B * a.tiles_x * a.tiles_y, ntiles_n = a.Cout / 128;
+  const int n_items = cdiv(ntiles, 2) * ntiles_n;
+  const int clusters = n_items < num_sms / 2 ? n_items : num_sms / 2;
+  conv_tc2p_kernel<<<2 * clusters, P2_THREADS, smem, st>>>(mh, ml, mw, a, n_items, ntiles_n);
+  FRTM_CHECK_LAUNCH("conv_tc2p");
+  return FRTM_OK;
+}
+
 template <int BN, int STAGES, bool R1, bool TAP>
 static int launch_tc(const CUtensorMap &mh, const CUtensorMap &ml, const TcArgs &a, dim3 grid, cudaStream_t st) {
   constexpr int smem = STAGES * (2 * TC_A_BYTES + 2 * BN * 128) + 16 * STAGES + 48 + 84 * BN + 1024;
@@ -1347,8 +1549,9 @@ extern "C" int frtm_conv2d_tc(const void *x_hi, const void *x_lo, int B, int H, 
                               const float *r1_score, const float *r1_w, const float *r1_bias, float *y_extra, int extra_ch,
                               int Cout, int kh, int kw, int stride, int relu, int kernel_select, void *stream) {
   FRTM_REQUIRE(x_hi && x_lo && wt && oscale && (y || y_nchw || y_hi || y_tap), "conv2d_tc: null pointer");
-  FRTM_REQUIRE(kernel_select >= 0 && kernel_select <= 3,
-               "conv2d_tc: kernel_select must be 0 (automatic), 1 (general tile kernel), 2 or 3 (CTA-pair kernel, N = 128 / 256)");
+  FRTM_REQUIRE(kernel_select >= 0 && kernel_select <= 4,
+               "conv2d_tc: kernel_select must be 0 (automatic), 1 (general tile kernel), 2 / 3 (CTA-pair kernel, N = 128 / 256) or 4 "
+               "(persistent CTA-pair kernel)");
   const bool special = kernel_select == 0;
   FRTM_REQUIRE(!r1_score || r1_w, "conv2d_tc: the rank-1 score channel needs its weights");
   FRTM_REQUIRE(!y_extra || (extra_ch >= 0 && extra_ch < Cout), "conv2d_tc: extra_ch out of range");
@@ -1390,23 +1593,27 @@ extern "C" int frtm_conv2d_tc(const void *x_hi, const void *x_lo, int B, int H, 
   // wide convs (Cout a multiple of 128, weights in the N tile 64 packing, plain epilogue): the CTA-pair kernel.  Pair tile
   // N = 256 when that still gives every SM a CTA, else N = 128 (twice the CTAs at 1.5x the L2 traffic per MAC).
   const bool pair_ok = bn_tile == 64 && Cout % 128 == 0 && !r1 && !tap;
-  FRTM_REQUIRE(kernel_select < 2 || (pair_ok && (kernel_select == 2 || Cout % 256 == 0)),
-               "conv2d_tc: the CTA-pair kernel needs the N tile 64 packing, Cout %% 128 == 0 (N = 256: %% 256) and a plain epilogue");
+  FRTM_REQUIRE(kernel_select < 2 || (pair_ok && (kernel_select != 3 || Cout % 256 == 0)),
+               "conv2d_tc: the CTA-pair kernels need the N tile 64 packing, Cout %% 128 == 0 (N = 256: %% 256) and a plain epilogue");
   if (kernel_select >= 2 || (special && pair_ok)) {
-    bool wide = kernel_select == 3;
-    if (kernel_select == 0 && Cout % 256 == 0) {
-      static int num_sms = 0;
-      if (num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
-      }
-      const int ctas256 = 2 * cdiv((int64_t)B * a.tiles_x * a.tiles_y, 2) * (Cout / 256);
-      wide = 10 * ctas256 >= 7 * num_sms;
+    static int num_sms = 0;
+    if (num_sms == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+    }
+    const int pairs = cdiv((int64_t)B * a.tiles_x * a.tiles_y, 2);
+    // several N = 128 items per TPC: the persistent kernel (store of item i behind the products of item i+1); else one
+    // tile per CTA, N = 256 when that still gives 0.7 CTAs per SM
+    bool persistent = kernel_select == 4, wide = kernel_select == 3;
+    if (kernel_select == 0) {
+      persistent = 2 * pairs * (Cout / 128) >= 5 * (num_sms / 2);
+      wide = !persistent && Cout % 256 == 0 && 10 * (2 * pairs * (Cout / 256)) >= 7 * num_sms;
     }
     CUtensorMap mw;
     rc = make_weight_map(&mw, (const __half *)wt, (int64_t)(Cout / 64) * a.kh * a.kw * a.kchunks * 128);
     if (rc) return rc;
+    if (persistent) return launch_tc2p(mh, ml, mw, a, num_sms, st);
     return wide ? launch_tc2<128>(mh, ml, mw, a, st) : launch_tc2<64>(mh, ml, mw, a, st);
   }
   if (stream1) {

@@ -89,7 +89,9 @@ int frtm_conv2d_nhwc(const float *x, int B, int H, int W, int Cin, int ldx, cons
  * Same reference call sites as frtm_conv2d_nhwc; the products hi*hi + hi*lo + lo*hi (issued as A_hi x [B_hi | B_lo] and
  * A_lo x B_hi) keep the result within ~1e-6 relative of an fp32 convolution.
  *   kernel_select  0 = the library picks the kernel for the shape (slab kernel with resident weights for 3x3 / 64 input
- *              channels, persistent streaming kernel for narrow 1x1, general tile kernel otherwise); 1 = general tile kernel
+ *              channels, persistent streaming kernel for narrow 1x1, CTA-pair kernels (tcgen05.mma.cta_group::2) for Cout a
+ *              multiple of 128 — persistent when there are several tiles per SM —, general tile kernel otherwise);
+ *              1 = general tile kernel, 2 / 3 = CTA-pair kernel with pair tile N = 128 / 256, 4 = persistent CTA-pair kernel
  *              (A-B measurements and tests; a per-call argument, the library keeps no mode) */
 int frtm_conv2d_tc(const void *x_hi, const void *x_lo, int B, int H, int W, int Cin, int ldx, const void *wt,
                    const float *oscale, int bn_tile, const float *bias, const float *res, int ldr, const void *res_hi,

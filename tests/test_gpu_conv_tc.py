@@ -264,7 +264,7 @@ def test_pair_kernel_matches_fp32_and_general_kernel(cin, cout, k, stride, hw, B
     assert pc.bn == 64
     rs = ops.split_f16(_nhwc(res).to(DEV))
     gen = ops.conv2d_tc(xs, pc, res=rs, relu=True, out_split=True, kernel_select=1)
-    sels = [0, 2] + ([3] if cout % 256 == 0 else [])
+    sels = [0, 2, 4] + ([3] if cout % 256 == 0 else [])
     for sel in sels:
         o = ops.conv2d_tc(xs, pc, res=rs, relu=True, out_split=True, nchw=True, kernel_select=sel)
         torch.cuda.synchronize()

@@ -34,13 +34,13 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--no-flush", action="store_true", help="leave L2 warm between launches (the state inside a block)")
     ap.add_argument("--only", default="", help="substring of the shape names to run")
-    ap.add_argument("--sels", default="1,2,3,0", help="kernel_select values to time")
+    ap.add_argument("--sels", default="1,2,3,4,0", help="kernel_select values to time")
     args = ap.parse_args()
     dev = "cuda:0"
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     g = torch.Generator().manual_seed(0)
-    print("| conv | GFLOP (alg.) | general us | pair N=128 us | pair N=256 us | auto us | auto alg. TFLOP/s |")
-    print("|---|---:|---:|---:|---:|---:|---:|")
+    print("| conv | GFLOP (alg.) | general us | pair N=128 us | pair N=256 us | persistent pair us | auto us | auto alg. TFLOP/s |")
+    print("|---|---:|---:|---:|---:|---:|---:|---:|")
     sels = [int(v) for v in args.sels.split(",")]
     for name, cin, cout, k, stride, hw, with_res in SHAPES:
         if args.only not in name:
@@ -54,7 +54,7 @@ def main():
         rs = ops.split_f16(torch.randn(B, Ho, Wo, cout, generator=g).to(dev)) if with_res else None
         gflop = 2.0 * B * Ho * Wo * cin * cout * k * k / 1e9
         row = []
-        for sel in (1, 2, 3, 0):
+        for sel in (1, 2, 3, 4, 0):
             if (sel == 3 and cout % 256) or sel not in sels:
                 row.append(float("nan"))
                 continue
@@ -71,8 +71,8 @@ def main():
                     ts.append(e0.elapsed_time(e1) * 1e3)
             ts.sort()
             row.append(ts[len(ts) // 2])
-        print("| %s %d->%d k%d s%d %dx%d | %.1f | %.1f | %.1f | %.1f | %.1f | %.0f |" % (
-            name, cin, cout, k, stride, hw[0], hw[1], gflop, row[0], row[1], row[2], row[3], gflop / row[3] * 1e3))
+        print("| %s %d->%d k%d s%d %dx%d | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %.0f |" % (
+            name, cin, cout, k, stride, hw[0], hw[1], gflop, row[0], row[1], row[2], row[3], row[4], gflop / row[4] * 1e3))
 
 
 if __name__ == "__main__":
