@@ -766,6 +766,16 @@ conv_tc2p_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   const int tiles_per_img = a.tiles_x * a.tiles_y;
   const int nkb = a.kh * a.kw * a.kchunks;
   const int cluster = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  // phase totals of the first pair (timing builds only: `make tc2timing`, FRTM_B200_LIB=.../libfrtm_b200_timing.so)
+#ifdef TC2_TIMING
+  __shared__ long long p2p_t[10][8];
+  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long t_begin = clock64();
+  long long tlast = t_begin;
+#define P2P_T(k) do { const long long t__ = clock64(); tacc[k] += t__ - tlast; tlast = t__; } while (0)
+#else
+#define P2P_T(k) do {} while (0)
+#endif
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_hi)) : "memory");
@@ -829,8 +839,11 @@ conv_tc2p_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % P2P_STAGES;
           const uint32_t slot = it % P2P_SLOTS;
+          P2P_T(0);
           mbar_wait(bar_acce + 8 * slot, ((it / P2P_SLOTS) & 1) ^ 1);      // drained by both CTAs' epilogues
+          P2P_T(1);
           mbar_wait(bar_full + 8 * s, (it / P2P_STAGES) & 1);
+          P2P_T(2);
           tc_fence_after();
           const uint32_t tacc = tmem_base + slot * SLOT;
           const uint32_t sa = base + s * STAGE_BYTES;
@@ -872,6 +885,7 @@ conv_tc2p_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       float acc[HALF];
 #pragma unroll
       for (int j = 0; j < HALF; ++j) acc[j] = 0.f;
+      P2P_T(0);
 #pragma unroll 1
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const uint32_t slot = it % P2P_SLOTS;
@@ -892,7 +906,9 @@ conv_tc2p_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
           else mbar_arrive_cluster(lead_acce + 8 * slot);
         }
       }
+      P2P_T(2);
       asm volatile("bar.sync 1, 256;" ::: "memory");      // A: scales staged, the previous item's store loop is over
+      P2P_T(3);
       {
         const float *so = s_osc + h * 2 * HALF, *sb = so + HALF;
         float *trow = tile + row * (BN + 4) + h * HALF;
@@ -902,16 +918,30 @@ conv_tc2p_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
               make_float4(fmaf(acc[c0], so[c0], sb[c0]), fmaf(acc[c0 + 1], so[c0 + 1], sb[c0 + 1]),
                           fmaf(acc[c0 + 2], so[c0 + 2], sb[c0 + 2]), fmaf(acc[c0 + 3], so[c0 + 3], sb[c0 + 3]));
       }
+      P2P_T(4);
       asm volatile("bar.sync 1, 256;" ::: "memory");      // B: tile complete
+      P2P_T(5);
       pair_epilogue_store<BN>(a, tile, te, b, y0, x0, n0);
+      P2P_T(6);
     }
   }
+#ifdef TC2_TIMING
+  if (lane == 0) for (int i = 0; i < 8; ++i) p2p_t[warp][i] = tacc[i];
+#endif
   tc_fence_before();
   pair_sync_all();
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(COLS) : "memory");
   }
+#ifdef TC2_TIMING
+  __syncthreads();
+  if (threadIdx.x == 0 && blockIdx.x < 2)
+    printf("tc2p cta %d total %lld | mma: other %lld wait_drained %lld wait_full %lld | epi w2: other %lld folds+waits %lld barA %lld "
+           "tile %lld barB %lld store %lld | epi w9: folds+waits %lld barA %lld tile %lld barB %lld store %lld\n",
+           blockIdx.x, clock64() - t_begin, p2p_t[1][0], p2p_t[1][1], p2p_t[1][2], p2p_t[2][0], p2p_t[2][2], p2p_t[2][3],
+           p2p_t[2][4], p2p_t[2][5], p2p_t[2][6], p2p_t[9][2], p2p_t[9][3], p2p_t[9][4], p2p_t[9][5], p2p_t[9][6]);
+#endif
 }
 
 // ----------------------------------------------------------------------------------------------------------------
