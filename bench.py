@@ -316,6 +316,7 @@ def run_b200(cfg, steps, warmup, dev, rank, world, dist, with_clocks):
     ms_e2e = e2.elapsed_time(e3)
     # the same device-resident steps with the cross-sequence overlap of the initialisation turned off
     trk.prefetch_next = False
+    trk._drain_prefetch()
     trk._prefetched.clear()
     step(mine)
     sync()
@@ -404,6 +405,8 @@ def run_b200(cfg, steps, warmup, dev, rank, world, dist, with_clocks):
                                 "FLOPs = 3x)" % cfg["objects"],
                          ms_per_frame=ms_track, algorithmic_gflop_per_frame=gb + cfg["objects"] * go, peak_source=pk["src"])
 
+    trk._drain_prefetch()                     # the preparation started by the last step is never consumed: let it finish
+    torch.cuda.synchronize()
     n_seq = len(mine)
     h2d = n_seq * (cfg["frames"] * 3 * H * W + H * W)
     d2h = n_seq * cfg["frames"] * H * W

@@ -27,7 +27,7 @@ from .._lib import lib, ptr, stream
 # (YouTubeVOS) would otherwise pin one set (tens of MB) per resolution for the life of the process; an evicted set's graphs
 # are released in the library before its memory is.  ``release_init_stages()`` (``Tracker.clear``) drops everything.
 _INIT_STAGE = collections.OrderedDict()
-_INIT_STAGE_CAP = 6
+_INIT_STAGE_CAP = 16          # = the library's graph cache; one set per object stream (10 objects in BASELINE config 5)
 
 
 def _drop_stage(st):

@@ -105,12 +105,22 @@ class Tracker(nn.Module):
         self.prefetch_next = os.environ.get("FRTM_PREFETCH_INIT", "1") == "1"
         self.graph_captures = 0     # how many times a block graph was captured (tests / diagnostics)
 
+    def _drain_prefetch(self):
+        """Wait until the worker threads have issued everything they prepare for coming sequences (host side only)."""
+        for rec in list(self._prefetched.values()):
+            for f in [rec["features"]]:
+                try:
+                    f.result()
+                except Exception:                          # noqa: BLE001 - surfaces in initialize, where it is consumed
+                    pass
+
     def clear(self):
         self.first_frames = []
         self.current_frame = 0
         self.current_masks = None
         self.num_objects = 0
         self._stack = None
+        self._drain_prefetch()      # no cudaFree under the worker threads' launches
         torch.cuda.empty_cache()
 
     def release_buffers(self):
@@ -118,6 +128,8 @@ class Tracker(nn.Module):
         graphs (``model/optimizer.py`` keeps a small LRU of them, one per feature resolution and stream) and the
         per-sequence tables.  Not needed between sequences; for long-lived processes that switch models or resolutions."""
         from .optimizer import release_init_stages
+        self._drain_prefetch()
+        self._prefetched = {}
         self.targets = dict()
         self._fbuf = None
         self._gn_table = None
@@ -352,10 +364,18 @@ class Tracker(nn.Module):
             nv = res[0][0].shape[0]
             return [(res[k][0], res[k][1], done, x[k * nv:(k + 1) * nv]) for k in range(n_new)]
 
-        self._prefetched[key] = dict(sequence=sequence, objects=tuple(new_objects), keep=(image_d, labels_d), futures=futures,
-                                     features=pool.submit(features))
+        rec = dict(sequence=sequence, objects=tuple(new_objects), keep=(image_d, labels_d), futures=futures,
+                   features=pool.submit(features))
+        self._prefetched[key] = rec
         while len(self._prefetched) > 2:              # an entry whose sequence never ran
             self._prefetched.pop(next(iter(self._prefetched)))
+
+    def _reseed0(self):
+        # torch.random.manual_seed(0) of the reference (``:178``), without its detour through the lazy-init queues of back
+        # ends that are not in use (each queued call formats a stack trace: 0.3 ms per object)
+        torch.default_generator.manual_seed(0)
+        if torch.cuda.is_initialized():
+            torch.cuda.manual_seed_all(0)
 
     def initialize(self, image, labels, new_objects, prefetched=None):
         """Create and fit a target model per new object (``:165-191``).
@@ -373,6 +393,7 @@ class Tracker(nn.Module):
             st.wait_stream(main)                     # image / labels uploads are visible to the side streams
         # targets are constructed in order on the main thread: each constructor draws its initial weights from the global
         # torch generator exactly where the reference does (before the reseed of that object)
+        matches = prefetched is not None and prefetched["objects"] == tuple(new_objects)
         targets = []
         for k, obj_id in enumerate(new_objects):
             with torch.cuda.stream(self._aug_streams[k]):
@@ -384,7 +405,7 @@ class Tracker(nn.Module):
             target.discriminator.buffer_pool = self._obj_pool.setdefault(target.index, {})
             self.targets[obj_id] = target
             targets.append(target)
-            torch.random.manual_seed(0)
+            self._reseed0()
             np.random.seed(0)
 
         def augment_job(k):
@@ -398,7 +419,7 @@ class Tracker(nn.Module):
                 return im, msk, side.record_event()
 
         workers = min(n_new, self.augment_workers) if self._augment_uses_rng() else 1
-        if prefetched is not None and prefetched["objects"] == tuple(new_objects):
+        if matches:
             results = iter(prefetched["features"].result())                # prepared behind the previous sequence
         elif workers > 1:
             pool = self._aug_pool()
