@@ -645,11 +645,9 @@ __global__ void __launch_bounds__(256) build_stencil_kernel(const float *__restr
 
 // ---------------------------------------------------------------- memory -----------------------------------------
 // state: {current_size, prev_replace_ind (-1 none), slot chosen now (-1 = skipped), inserts so far}
-__global__ void __launch_bounds__(32) memory_next_slot_kernel(float *__restrict__ sw, int cap, float lr, int *__restrict__ state,
-                                                              const int *__restrict__ gate_count, int min_px) {
-  // one warp; lanes stride over the capacity, reductions by shuffle (first-minimum tie break = lowest index)
-  const int lane = threadIdx.x;
-  if (gate_count && gate_count[0] < min_px) { if (lane == 0) state[2] = -1; return; }
+// one step of the replace-minimum policy with its sample-weight update (memory.py:65-92); one warp
+__device__ __forceinline__ void memory_policy_step(float *__restrict__ sw, int cap, float lr, int *__restrict__ state, int lane) {
+  // lanes stride over the capacity, reductions by shuffle (first-minimum tie break = lowest index)
   const int size = state[0], prev = state[1];
   __syncwarp();
   int r = 0;
@@ -684,11 +682,41 @@ __global__ void __launch_bounds__(32) memory_next_slot_kernel(float *__restrict_
   for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
   const float ft = (float)tot;
   for (int i = lane; i < cap; i += 32) sw[i] = sw[i] / ft;
+  __syncwarp();
   if (lane == 0) {
     state[1] = r;
     state[2] = r;
     state[0] = min(size + 1, cap);
     state[3] += 1;
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(32) memory_next_slot_kernel(float *__restrict__ sw, int cap, float lr, int *__restrict__ state,
+                                                              const int *__restrict__ gate_count, int min_px) {
+  const int lane = threadIdx.x;
+  if (gate_count && gate_count[0] < min_px) { if (lane == 0) state[2] = -1; return; }
+  memory_policy_step(sw, cap, lr, state, lane);
+}
+
+// The policy steps of all frames of a track block, one warp per object: the frames of an object are sequential (every
+// insert changes the weights the next choice looks at), the objects are independent.  slots[f * n_obj + o] = slot of
+// frame f (-1 = gated out).  table rows: 6 = sample weights, 7 = policy state (see MemBlockArgs).
+__global__ void __launch_bounds__(32) memory_slots_block_kernel(const long long *__restrict__ table, int n_obj, int nF, int cap,
+                                                                float lr, const int *__restrict__ gate_counts, int min_px,
+                                                                int *__restrict__ slots) {
+  const int o = blockIdx.x, lane = threadIdx.x;
+  float *sw = reinterpret_cast<float *>(table[6 * n_obj + o]);
+  int *state = reinterpret_cast<int *>(table[7 * n_obj + o]);
+  for (int f = 0; f < nF; ++f) {
+    if (gate_counts[f * n_obj + o] < min_px) {
+      if (lane == 0) { state[2] = -1; slots[f * n_obj + o] = -1; }
+      __syncwarp();
+      continue;
+    }
+    memory_policy_step(sw, cap, lr, state, lane);
+    if (lane == 0) slots[f * n_obj + o] = state[2];
+    __syncwarp();
   }
 }
 
@@ -717,6 +745,55 @@ __global__ void memory_insert_kernel(const InsertArgs a, const int *__restrict__
   for (int k = 0; k < 5; ++k) {
     if (i < a.n[k]) {
       a.dst[k][(int64_t)slot * a.n[k] + i] = a.src[k][i];
+      return;
+    }
+    i -= a.n[k];
+  }
+}
+
+// All inserts of a track block in one launch: blockIdx.y = f * n_obj + o copies sample (f, o) into the slot the policy
+// kernel chose for it.  table rows (each n_obj pointers): samples, labels, pixel weights, stencil, uty, operator images.
+// A slot chosen twice inside the block keeps the LAST frame's sample, as the sequential inserts would leave it.
+struct MemBlockArgs {
+  const long long *table;
+  const int *slots;
+  const float *src[5];      // features, labels, pixel weights, stencil, uty of all (frame, object) rows, row-major
+  int64_t n[5];
+  int64_t total, split_items;
+  int n_obj, nF, c, hw;
+};
+template <int V>   // elements per thread of the copy part: 4 (every piece a multiple of 4 floats, 16-byte aligned) or 1
+__global__ void __launch_bounds__(256) memory_insert_block_kernel(const MemBlockArgs a, int copy_blocks) {
+  const int row = blockIdx.y, f = row / a.n_obj, o = row - f * a.n_obj;
+  __shared__ int s_slot;
+  if (threadIdx.x == 0) {
+    int slot = a.slots[row];
+    for (int g = f + 1; g < a.nF && slot >= 0; ++g)
+      if (a.slots[g * a.n_obj + o] == slot) slot = -1;
+    s_slot = slot;
+  }
+  __syncthreads();
+  const int slot = s_slot;
+  if (slot < 0) return;
+  if ((int)blockIdx.x >= copy_blocks) {            // operator image of the sample
+    const int64_t i = (int64_t)(blockIdx.x - copy_blocks) * blockDim.x + threadIdx.x;
+    uint8_t *split = reinterpret_cast<uint8_t *>(a.table[5 * a.n_obj + o]);
+    if (i < a.split_items && split)
+      gc_image_item(a.src[0] + (int64_t)row * a.n[0], a.src[3] + (int64_t)row * a.n[3], a.src[4] + (int64_t)row * a.n[4],
+                    split + (int64_t)slot * gc_sample_bytes(a.c, a.hw), a.c, a.hw, i);
+    return;
+  }
+  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
+  if (i >= a.total) return;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    if (i < a.n[k]) {
+      float *dst = reinterpret_cast<float *>(a.table[k * a.n_obj + o]);
+      if (!dst) return;
+      const float *src = a.src[k] + (int64_t)row * a.n[k] + i;
+      dst += (int64_t)slot * a.n[k] + i;
+      if (V == 4) *reinterpret_cast<float4 *>(dst) = *reinterpret_cast<const float4 *>(src);
+      else *dst = *src;
       return;
     }
     i -= a.n[k];
@@ -992,6 +1069,37 @@ extern "C" int frtm_memory_insert(const float *feat, int feat_elems, const float
   }
   memory_insert_kernel<<<cdiv(a.total + a.split_items, 256), 256, 0, (cudaStream_t)stream>>>(a, state);
   FRTM_CHECK_LAUNCH("memory_insert");
+  return FRTM_OK;
+}
+
+extern "C" int frtm_memory_insert_block(const void *table, int n_obj, int n_frames, int capacity, float lr, const int *gate_counts,
+                                        int min_px, const float *feat, int feat_elems, const float *labels, const float *pw,
+                                        int HW, const float *stencil, const float *uty, int hw, int with_split, int *slots,
+                                        void *stream) {
+  FRTM_REQUIRE(table && gate_counts && feat && labels && pw && stencil && uty && slots, "memory_insert_block: null pointer");
+  FRTM_REQUIRE(n_obj >= 1 && n_frames >= 1 && n_obj * n_frames <= 65535 && capacity >= 1, "memory_insert_block: bad sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  memory_slots_block_kernel<<<n_obj, 32, 0, st>>>((const long long *)table, n_obj, n_frames, capacity, lr, gate_counts, min_px, slots);
+  FRTM_CHECK_LAUNCH("memory_slots_block");
+  MemBlockArgs a;
+  a.table = (const long long *)table; a.slots = slots;
+  const float *src[5] = {feat, labels, pw, stencil, uty};
+  const int64_t n[5] = {feat_elems, HW, HW, 9 * (int64_t)hw, hw};
+  a.total = 0;
+  for (int k = 0; k < 5; ++k) { a.src[k] = src[k]; a.n[k] = n[k]; a.total += n[k]; }
+  a.n_obj = n_obj; a.nF = n_frames; a.hw = hw; a.c = 0; a.split_items = 0;
+  if (with_split) {
+    FRTM_REQUIRE(hw > 0 && feat_elems % hw == 0 && (feat_elems / hw) % 8 == 0, "memory_insert_block: operator image needs c %% 8 == 0");
+    a.c = feat_elems / hw;
+    a.split_items = gc_sample_items(a.c, hw);
+  }
+  bool vec = true;
+  for (int k = 0; k < 5; ++k) vec = vec && n[k] % 4 == 0 && (reinterpret_cast<uintptr_t>(src[k]) & 15) == 0;
+  const int copy_blocks = cdiv(vec ? a.total / 4 : a.total, 256);
+  dim3 grid((unsigned)(copy_blocks + cdiv(a.split_items, 256)), (unsigned)(n_obj * n_frames));
+  if (vec) memory_insert_block_kernel<4><<<grid, 256, 0, st>>>(a, copy_blocks);   // (the memory's own arrays come from the
+  else memory_insert_block_kernel<1><<<grid, 256, 0, st>>>(a, copy_blocks);      // allocator: 256-byte aligned)
+  FRTM_CHECK_LAUNCH("memory_insert_block");
   return FRTM_OK;
 }
 

@@ -232,6 +232,16 @@ int frtm_memory_insert(const float *feat, int feat_elems, const float *label, co
                        float *mem_pw, float *mem_stencil, float *mem_uty, void *mem_split, const int *state,
                        void *stream);
 
+/* All memory inserts of a track block (n_frames consecutive frames x n_obj objects) in two launches: the policy steps of
+ * every object (sequential over its frames, frtm_memory_next_slot's arithmetic, gated per (frame, object) on
+ * gate_counts[f * n_obj + o] >= min_px) and ONE copy launch for all samples (frtm_memory_insert's).  Row (f, o) of feat
+ * (feat_elems floats), labels / pw (HW), stencil (9 hw), uty (hw) is row f * n_obj + o.  table = device int64[8][n_obj]:
+ * per object the addresses of samples, labels, pixel_weights, stencil, uty, operator images (0 = none), sample weights,
+ * policy state (model/memory.py:59-92 applied n_frames times).  slots = int[n_frames * n_obj] workspace (out: the slots). */
+int frtm_memory_insert_block(const void *table, int n_obj, int n_frames, int capacity, float lr, const int *gate_counts,
+                             int min_px, const float *feat, int feat_elems, const float *labels, const float *pw, int HW,
+                             const float *stencil, const float *uty, int hw, int with_split, int *slots, void *stream);
+
 /* Operator images of n memory samples for the tensor-core GN/CG operator kernel.  Per sample:
  *   [ntiles][hi|lo][c][64 pixels] fp16 with 16*x = hi + lo, rows in the 128-byte swizzled shared-memory layout, pixels
  *   beyond hw zero, ntiles = hw/64 rounded up to an even count;  then  [ceil(hw/256)][10][256] fp32: the 9 stencil taps
