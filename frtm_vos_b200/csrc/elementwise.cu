@@ -195,9 +195,11 @@ __global__ void __launch_bounds__(256) pyrup_bicubic_kernel(const float *__restr
 }
 
 // ---------------------------------------------------------------- global average pool ---------------------------
-constexpr int GAP_CHUNK = 256;  // pixels per stage-1 block
+constexpr int GAP_CHUNK = 64;   // pixels per stage-1 block
 
-// stage 1: block = 4 pixel groups x 64 channel lanes; each group strides over the chunk's pixels, then a smem reduce
+// stage 1: block = 4 pixel groups x 64 channel lanes; a thread sums the 16 pixels of its group with ALL loads in flight
+// (a strided loop with 4 loads in flight per thread made the launch a chain of 16 memory round trips: 17 us even for a
+// 15 x 27 map), then a smem reduce.  Fixed order -> deterministic.
 __global__ void __launch_bounds__(256) gap_stage1_kernel(const float *__restrict__ x, int HW, int C, int ldx, int nchunks,
                                                          float *__restrict__ part) {
   __shared__ float red[4][64];
@@ -206,55 +208,94 @@ __global__ void __launch_bounds__(256) gap_stage1_kernel(const float *__restrict
   const int lane = threadIdx.x & 63, grp = threadIdx.x >> 6;
   for (int c0 = 0; c0 < C; c0 += 64) {
     const int c = c0 + lane;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    if (c < C) {
-      const float *base = x + (int64_t)b * HW * ldx + c;
-      int p = p0 + grp;
-      for (; p + 12 < p1; p += 16) {   // 4 independent loads in flight per thread
-        s0 += base[(int64_t)p * ldx];
-        s1 += base[(int64_t)(p + 4) * ldx];
-        s2 += base[(int64_t)(p + 8) * ldx];
-        s3 += base[(int64_t)(p + 12) * ldx];
-      }
-      for (; p < p1; p += 4) s0 += base[(int64_t)p * ldx];
+    float v[GAP_CHUNK / 4];
+    const float *base = x + (int64_t)b * HW * ldx + c;
+#pragma unroll
+    for (int k = 0; k < GAP_CHUNK / 4; ++k) {
+      const int p = p0 + grp + 4 * k;
+      v[k] = (c < C && p < p1) ? base[(int64_t)p * ldx] : 0.f;
     }
-    red[grp][lane] = (s0 + s1) + (s2 + s3);
+#pragma unroll
+    for (int w = GAP_CHUNK / 8; w > 0; w >>= 1)
+#pragma unroll
+      for (int k = 0; k < w; ++k) v[k] += v[k + w];
+    red[grp][lane] = v[0];
     __syncthreads();
     if (grp == 0 && c < C) part[((int64_t)b * nchunks + ch) * C + c] = (red[0][lane] + red[1][lane]) + (red[2][lane] + red[3][lane]);
     __syncthreads();
   }
 }
-__global__ void gap_stage2_kernel(const float *__restrict__ part, int HW, int C, int nchunks, float *__restrict__ out) {
+// stage 2: block = one image; 4 chunk groups x 64 channel lanes, 4 partial sums in flight per thread, smem reduce
+__global__ void __launch_bounds__(256) gap_stage2_kernel(const float *__restrict__ part, int HW, int C, int nchunks,
+                                                         float *__restrict__ out) {
+  __shared__ float red[4][64];
   const int b = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = 0.f;
-    for (int k = 0; k < nchunks; ++k) s += part[((int64_t)b * nchunks + k) * C + c];
-    out[(int64_t)b * C + c] = s / (float)HW;
+  const int lane = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  for (int c0 = 0; c0 < C; c0 += 64) {
+    const int c = c0 + lane;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (c < C) {
+      const float *base = part + (int64_t)b * nchunks * C + c;
+      int k = grp;
+      for (; k + 12 < nchunks; k += 16) {
+        s0 += base[(int64_t)k * C];
+        s1 += base[(int64_t)(k + 4) * C];
+        s2 += base[(int64_t)(k + 8) * C];
+        s3 += base[(int64_t)(k + 12) * C];
+      }
+      for (; k < nchunks; k += 4) s0 += base[(int64_t)k * C];
+    }
+    red[grp][lane] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (grp == 0 && c < C) out[(int64_t)b * C + c] = ((red[0][lane] + red[1][lane]) + (red[2][lane] + red[3][lane])) / (float)HW;
+    __syncthreads();
   }
 }
 
 // ---------------------------------------------------------------- CAB -------------------------------------------
+// gate = sigmoid(W2 relu(W1 [sp | dp] + b1) + b2) per image (seg_network.py:34-37).  One block per image, blockDim = 4 * C:
+// four threads share an output row (a quarter of the dot product each, float4 loads, two accumulators), then a shared
+// memory reduce — the single 128-long FMA chain per thread it replaces took 14 us per launch.
 __global__ void cab_gate_kernel(const float *__restrict__ sp, const float *__restrict__ dp, const float *__restrict__ w1,
                                 const float *__restrict__ b1, const float *__restrict__ w2, const float *__restrict__ b2,
                                 int C, float *__restrict__ gate) {
-  extern __shared__ float sm[];  // pooled[2C] + hidden[C]
-  float *pooled = sm, *hid = sm + 2 * C;
+  extern __shared__ float sm[];  // pooled[2C] + hidden[C] + partial[4C]
+  float *pooled = sm, *hid = sm + 2 * C, *part = sm + 3 * C;
   const int b = blockIdx.x;
   for (int i = threadIdx.x; i < C; i += blockDim.x) {
     pooled[i] = sp[(int64_t)b * C + i];
     pooled[C + i] = dp[(int64_t)b * C + i];
   }
   __syncthreads();
-  for (int o = threadIdx.x; o < C; o += blockDim.x) {
-    float s = 0.f;
-    for (int k = 0; k < 2 * C; ++k) s = fmaf(w1[(int64_t)o * 2 * C + k], pooled[k], s);
-    hid[o] = fmaxf(s + b1[o], 0.f);
+  const int o = threadIdx.x >> 2, q = threadIdx.x & 3;
+  {
+    const int K = 2 * C, kq = K / 4;
+    const float *wr = w1 + (int64_t)o * K + q * kq, *pv = pooled + q * kq;
+    float s0 = 0.f, s1 = 0.f;
+    for (int k = 0; k < kq; k += 8) {
+      const float4 a0 = *reinterpret_cast<const float4 *>(wr + k), a1 = *reinterpret_cast<const float4 *>(wr + k + 4);
+      s0 = fmaf(a0.x, pv[k], s0); s0 = fmaf(a0.y, pv[k + 1], s0); s0 = fmaf(a0.z, pv[k + 2], s0); s0 = fmaf(a0.w, pv[k + 3], s0);
+      s1 = fmaf(a1.x, pv[k + 4], s1); s1 = fmaf(a1.y, pv[k + 5], s1); s1 = fmaf(a1.z, pv[k + 6], s1); s1 = fmaf(a1.w, pv[k + 7], s1);
+    }
+    part[threadIdx.x] = s0 + s1;
   }
   __syncthreads();
-  for (int o = threadIdx.x; o < C; o += blockDim.x) {
-    float s = 0.f;
-    for (int k = 0; k < C; ++k) s = fmaf(w2[(int64_t)o * C + k], hid[k], s);
-    s += b2[o];
+  if (q == 0) hid[o] = fmaxf(((part[4 * o] + part[4 * o + 1]) + (part[4 * o + 2] + part[4 * o + 3])) + b1[o], 0.f);
+  __syncthreads();
+  {
+    const int kq = C / 4;
+    const float *wr = w2 + (int64_t)o * C + q * kq, *hv = hid + q * kq;
+    float s0 = 0.f, s1 = 0.f;
+    for (int k = 0; k < kq; k += 8) {
+      const float4 a0 = *reinterpret_cast<const float4 *>(wr + k), a1 = *reinterpret_cast<const float4 *>(wr + k + 4);
+      s0 = fmaf(a0.x, hv[k], s0); s0 = fmaf(a0.y, hv[k + 1], s0); s0 = fmaf(a0.z, hv[k + 2], s0); s0 = fmaf(a0.w, hv[k + 3], s0);
+      s1 = fmaf(a1.x, hv[k + 4], s1); s1 = fmaf(a1.y, hv[k + 5], s1); s1 = fmaf(a1.z, hv[k + 6], s1); s1 = fmaf(a1.w, hv[k + 7], s1);
+    }
+    part[threadIdx.x] = s0 + s1;
+  }
+  __syncthreads();
+  if (q == 0) {
+    const float s = ((part[4 * o] + part[4 * o + 1]) + (part[4 * o + 2] + part[4 * o + 3])) + b2[o];
     gate[(int64_t)b * C + o] = 1.f / (1.f + expf(-s));
   }
 }
@@ -894,7 +935,7 @@ extern "C" int frtm_global_avgpool_nhwc(const float *x, int B, int HW, int C, in
   cudaStream_t st = (cudaStream_t)stream;
   gap_stage1_kernel<<<dim3(nchunks, B), 256, 0, st>>>(x, HW, C, ldx, nchunks, workspace);
   FRTM_CHECK_LAUNCH("gap_stage1");
-  gap_stage2_kernel<<<B, 64, 0, st>>>(workspace, HW, C, nchunks, out);
+  gap_stage2_kernel<<<B, 256, 0, st>>>(workspace, HW, C, nchunks, out);
   FRTM_CHECK_LAUNCH("gap_stage2");
   return FRTM_OK;
 }
@@ -902,7 +943,9 @@ extern "C" int frtm_global_avgpool_nhwc(const float *x, int B, int HW, int C, in
 extern "C" int frtm_cab_gate(const float *sp, const float *dp, const float *w1, const float *b1, const float *w2,
                              const float *b2, int B, int C, float *gate, void *stream) {
   FRTM_REQUIRE(sp && dp && w1 && b1 && w2 && b2 && gate, "cab_gate: null pointer");
-  cab_gate_kernel<<<B, 64, 3 * C * sizeof(float), (cudaStream_t)stream>>>(sp, dp, w1, b1, w2, b2, C, gate);
+  FRTM_REQUIRE(C % 32 == 0 && C <= 256 && (reinterpret_cast<uintptr_t>(w1) & 15) == 0 && (reinterpret_cast<uintptr_t>(w2) & 15) == 0,
+               "cab_gate: C must be a multiple of 32 (<= 256) and the weights 16-byte aligned");
+  cab_gate_kernel<<<B, 4 * C, 7 * C * sizeof(float), (cudaStream_t)stream>>>(sp, dp, w1, b1, w2, b2, C, gate);
   FRTM_CHECK_LAUNCH("cab_gate");
   return FRTM_OK;
 }
