@@ -420,32 +420,38 @@ __global__ void __launch_bounds__(256) merge_masks_reg_kernel(const float *__res
         bg = fminf(bg, 1.f - pr);
       }
     }
-    // first softmax / argmax (softmax_argmax on the register copy)
+    // first softmax / argmax (softmax_argmax on the register copy).  Every odds ratio z = m / (1 - m) and every
+    // exponential exp(z - max) is evaluated ONCE and kept in registers (the same expressions on the same inputs as the
+    // three separate passes of merge_masks_kernel, hence the same bits; a third of the divisions and exponentials)
     const float z0 = bg / (1.f - bg);
     float mx = z0;
+    float z[NMAX], e[NMAX];
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n) {
+      z[n] = 0.f; e[n] = 0.f;
+      if (n < N) { z[n] = m[n] / (1.f - m[n]); mx = fmaxf(mx, z[n]); }
+    }
+    const float e0 = expf(z0 - mx);
+    float den = e0;
 #pragma unroll
     for (int n = 0; n < NMAX; ++n)
-      if (n < N) mx = fmaxf(mx, m[n] / (1.f - m[n]));
-    float den = expf(z0 - mx);
-#pragma unroll
-    for (int n = 0; n < NMAX; ++n)
-      if (n < N) den += expf(m[n] / (1.f - m[n]) - mx);
-    float best = expf(z0 - mx) / den;
+      if (n < N) { e[n] = expf(z[n] - mx); den += e[n]; }
+    float best = e0 / den;
     int arg = 0;
 #pragma unroll
     for (int n = 0; n < NMAX; ++n) {
       if (n < N) {
-        const float sn = expf(m[n] / (1.f - m[n]) - mx) / den;
+        const float sn = e[n] / den;
+        e[n] = sn;                                   // the softmax value itself from here on
         if (sn > best) { best = sn; arg = n + 1; }
       }
     }
-    masks[p] = (arg == 0) ? expf(z0 - mx) / den : 0.f;
+    masks[p] = (arg == 0) ? e0 / den : 0.f;
     float bg2 = INFINITY;
 #pragma unroll
     for (int n = 0; n < NMAX; ++n) {
       if (n < N) {
-        const float c = m[n];
-        const float sn = (arg == n + 1) ? expf(c / (1.f - c) - mx) / den : 0.f;
+        const float sn = (arg == n + 1) ? e[n] : 0.f;
         m[n] = sn;
         masks[(int64_t)(n + 1) * HW + p] = sn;
         bg2 = fminf(bg2, 1.f - fminf(fmaxf(sn, lo), hi));
@@ -455,29 +461,27 @@ __global__ void __launch_bounds__(256) merge_masks_reg_kernel(const float *__res
     if (single) {
       lab = m[0] > 0.5f ? 1 : 0;
     } else {
-      float mx2 = bg2 / (1.f - bg2);
+      const float zb = bg2 / (1.f - bg2);
+      float mx2 = zb;
 #pragma unroll
       for (int n = 0; n < NMAX; ++n) {
         if (n < N) {
           const float c = fminf(fmaxf(m[n], lo), hi);
-          mx2 = fmaxf(mx2, c / (1.f - c));
+          z[n] = c / (1.f - c);
+          mx2 = fmaxf(mx2, z[n]);
         }
       }
-      float den2 = expf(bg2 / (1.f - bg2) - mx2);
+      const float eb = expf(zb - mx2);
+      float den2 = eb;
 #pragma unroll
-      for (int n = 0; n < NMAX; ++n) {
-        if (n < N) {
-          const float c = fminf(fmaxf(m[n], lo), hi);
-          den2 += expf(c / (1.f - c) - mx2);
-        }
-      }
-      float best2 = expf(bg2 / (1.f - bg2) - mx2) / den2;
+      for (int n = 0; n < NMAX; ++n)
+        if (n < N) { e[n] = expf(z[n] - mx2); den2 += e[n]; }
+      float best2 = eb / den2;
       lab = 0;
 #pragma unroll
       for (int n = 0; n < NMAX; ++n) {
         if (n < N) {
-          const float c = fminf(fmaxf(m[n], lo), hi);
-          const float s2 = expf(c / (1.f - c) - mx2) / den2;
+          const float s2 = e[n] / den2;
           if (s2 > best2) { best2 = s2; lab = n + 1; }
         }
       }
