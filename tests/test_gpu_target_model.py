@@ -330,3 +330,60 @@ def test_memory_trace_golden(golden):
     before = m.weights.clone()
     m.update(z[0], z[0], z[0], gate_count=torch.tensor([3], dtype=torch.int32, device=DEV))
     assert torch.equal(before, m.weights) and int(m.state[2]) == -1
+
+
+def test_memory_insert_block_equals_sequential_inserts():
+    """frtm_memory_insert_block (all inserts of a track block in two launches) against the same inserts applied frame by
+    frame with Memory.update (model/memory.py:59-92): two objects whose memories fill up and start replacing inside the
+    block, some (frame, object) pairs gated out — every buffer, the sample weights, the policy state and the operator
+    images bit-identical; the slots reported by the block call are the replace indices of the sequential run."""
+    import ctypes
+    from frtm_vos_b200.model.memory import Memory
+    from frtm_vos_b200._lib import lib, ptr, stream
+    from frtm_vos_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    c, h, w, H, W, cap, n, nF = 96, 4, 7, 64, 112, 8, 2, 8
+
+    def fresh():
+        mems = []
+        gi = torch.Generator().manual_seed(9)
+        for o in range(n):
+            m = Memory(cap, (c, h, w), (1, H, W), DEV, 0.1)
+            K = 5
+            m.initialize(torch.randn(K, c, h, w, generator=gi).to(DEV), (torch.rand(K, 1, H, W, generator=gi) > 0.5).to(DEV),
+                         (0.5 + torch.rand(K, 1, H, W, generator=gi)).to(DEV))
+            mems.append(m)
+        return mems
+
+    feats = torch.randn(nF * n, c, h, w, generator=g).to(DEV)
+    ys = torch.rand(nF * n, 1, H, W, generator=g).to(DEV)
+    pw = (0.5 + torch.rand(nF * n, 1, H, W, generator=g)).to(DEV)
+    st, uty = ops.build_stencil(pw, ys, (h, w))
+    counts = torch.full((nF, n), 100, dtype=torch.int32)
+    counts[2, 0] = 3
+    counts[5, 1] = 0                                        # below min_px = 10: skipped on the device
+    counts = counts.to(DEV)
+
+    seq = fresh()
+    slots_seq = []
+    for f in range(nF):
+        for o in range(n):
+            j = f * n + o
+            seq[o].update(feats[j:j + 1], ys[j:j + 1], pw[j:j + 1], st[j:j + 1], uty[j:j + 1], gate_count=counts[f, o:o + 1], min_px=10)
+            slots_seq.append(int(seq[o].state[2]))
+
+    blk = fresh()
+    rows = [[m.samples.data_ptr() for m in blk], [m.labels.data_ptr() for m in blk], [m.pixel_weights.data_ptr() for m in blk],
+            [m.stencil.data_ptr() for m in blk], [m.uty.data_ptr() for m in blk], [m.split.data_ptr() for m in blk],
+            [m.weights.data_ptr() for m in blk], [m.state.data_ptr() for m in blk]]
+    table = torch.tensor([v for r in rows for v in r], dtype=torch.int64).to(DEV)
+    slots = torch.empty(nF * n, dtype=torch.int32, device=DEV)
+    lib().memory_insert_block(ptr(table), n, nF, cap, 0.1, ptr(counts), 10, ptr(feats), feats[0].numel(), ptr(ys), ptr(pw), H * W,
+                              ptr(st), ptr(uty), h * w, 1, ptr(slots), stream())
+    assert slots.cpu().tolist() == slots_seq
+    used = [s for s in slots_seq[0::n] if s >= 0]
+    assert slots_seq[2 * n + 0] == -1 and slots_seq[5 * n + 1] == -1
+    assert len(set(used)) >= 3 and len(used) > len(set(used))       # the full memory replaces a slot twice inside the block
+    for a, b in zip(seq, blk):
+        for name in ("samples", "labels", "pixel_weights", "stencil", "uty", "weights", "state", "split"):
+            assert torch.equal(getattr(a, name), getattr(b, name)), name
