@@ -255,26 +255,21 @@ def run_b200(cfg, steps, warmup, dev, rank, world, dist, with_clocks):
         s.preload(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    pinned_out = [None]
+    host_out = [torch.empty((cfg["frames"], H, W), dtype=torch.uint8).pin_memory() for _ in mine]
 
     def step(seqs, read_back=False):
         # the rank's sequences run back to back as in Tracker.run_dataset: while one is tracked, the host half of the next
         # one's first-frame initialisation (augmentation) is prepared in worker threads; the sequence after the last one
-        # of a step is the first one of the next step (FRTM_PREFETCH_INIT=0 turns the overlap off)
+        # of a step is the first one of the next step (FRTM_PREFETCH_INIT=0 turns the overlap off).  With read_back the
+        # label maps of every block go to pinned host memory on a copy stream while the next block is tracked.
         maps = []
         for k, s in enumerate(seqs):
-            outs, _ = trk.run_sequence(s, next_sequence=seqs[(k + 1) % len(seqs)])
+            outs, _ = trk.run_sequence(s, next_sequence=seqs[(k + 1) % len(seqs)], host_labels=host_out[k] if read_back else None)
             maps.append(torch.stack([o.reshape(H, W) for o in outs]))
         labels = torch.stack(maps)                                 # (S,T,H,W) uint8
         if world > 1:
             gather_label_maps(labels, world)                       # end-of-batch gather of the label maps (NCCL/NVLink)
-        if not read_back:
-            return labels
-        if pinned_out[0] is None or pinned_out[0].shape != labels.shape:
-            pinned_out[0] = torch.empty(labels.shape, dtype=labels.dtype).pin_memory()
-        pinned_out[0].copy_(labels, non_blocking=True)             # device -> pinned host; the step's sync() completes it
-        torch.cuda.current_stream().synchronize()
-        return pinned_out[0]
+        return host_out if read_back else labels
 
     def sync():
         torch.cuda.synchronize()
@@ -305,7 +300,8 @@ def run_b200(cfg, steps, warmup, dev, rank, world, dist, with_clocks):
     # e2e: pinned host frames in, label maps out, through the public run_sequence API
     step(hseqs, True)
     sync()
-    k_e2e = max(1, min(steps, 3))
+    k_e2e = max(1, min(steps, 8))
+    k_np = max(1, min(steps, 3))
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     for _ in range(k_e2e):
@@ -322,7 +318,7 @@ def run_b200(cfg, steps, warmup, dev, rank, world, dist, with_clocks):
     sync()
     e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e4.record()
-    for _ in range(k_e2e):
+    for _ in range(k_np):
         step(mine)
         flush.zero_()
     e5.record()
@@ -418,8 +414,8 @@ def run_b200(cfg, steps, warmup, dev, rank, world, dist, with_clocks):
                                   "sequence's first-frame initialisation (OpenCV cut-out / inpaint, candidate masks) is prepared "
                                   "in worker threads behind the current sequence's tracking; every step does one such "
                                   "preparation and consumes one",
-                          "without_overlap": {"value": k_e2e * total_frames / (ms_np * 1e-3), "unit": "frames/s",
-                                              "ms_per_step": ms_np / k_e2e, "steps": k_e2e}})
+                          "without_overlap": {"value": k_np * total_frames / (ms_np * 1e-3), "unit": "frames/s",
+                                              "ms_per_step": ms_np / k_np, "steps": k_np}})
 
 
 def measured_traffic(cfg, M):

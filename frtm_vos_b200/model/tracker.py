@@ -177,10 +177,12 @@ class Tracker(nn.Module):
                 sequence.release()
         print("Average frame rate: %.2f fps" % (fps_sum / max(fps_n, 1)))
 
-    def run_sequence(self, sequence, speedrun=False, next_sequence=None):
+    def run_sequence(self, sequence, speedrun=False, next_sequence=None, host_labels=None):
         """``next_sequence`` (optional, not in the reference signature): the sequence that will be run after this one; the
         host part of its first-frame initialisation (augmentation) is prepared in worker threads while this sequence is
-        tracked.  Results are identical with and without it."""
+        tracked.  Results are identical with and without it.  ``host_labels`` (optional): a pinned uint8 tensor
+        (frames, H, W); every frame's label map is also copied into it on a copy stream as soon as its block is done, so the
+        device->host transfer of the results runs behind the tracking instead of after it (complete on return)."""
         self.eval()
         self.object_ids = sequence.obj_ids
         self.current_frame = 0
@@ -227,6 +229,16 @@ class Tracker(nn.Module):
                     d = im.to(self.device, non_blocking=True)
                     ahead[j] = (d, self._h2d_stream.record_event())
 
+        def to_host(j, lab):
+            if host_labels is None:
+                return
+            if getattr(self, "_d2h_stream", None) is None:
+                self._d2h_stream = torch.cuda.Stream(device=self.device)
+            self._d2h_stream.wait_stream(main)
+            with torch.cuda.stream(self._d2h_stream):
+                host_labels[j].copy_(lab.reshape(host_labels.shape[-2:]), non_blocking=True)
+            lab.record_stream(self._d2h_stream)
+
         def frame(j):
             if j in ahead:
                 d, ev = ahead.pop(j)
@@ -257,6 +269,7 @@ class Tracker(nn.Module):
                 if isinstance(labels, list) and len(labels) == 0:
                     labels = image.new_zeros(1, *image.shape[-2:])
                 outputs.append(labels)
+                to_host(i, labels)
                 self.current_frame += 1
                 new_cache.pop(i, None)
                 i += 1
@@ -267,8 +280,9 @@ class Tracker(nn.Module):
             if next_sequence is not None and self.prefetch_next:
                 self.prefetch_init(next_sequence)         # once: behind the first track block of this sequence
                 next_sequence = None
-            for lab in self._track_block(images):
+            for f, lab in enumerate(self._track_block(images)):
                 outputs.append(lab.unsqueeze(0) if single else lab)
+                to_host(i + f, lab)
             upload_ahead(i + nb, i + nb + self.max_block)
             for j in range(i, i + nb):
                 new_cache.pop(j, None)

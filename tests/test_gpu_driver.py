@@ -234,3 +234,10 @@ def test_prefetched_initialisation_gives_identical_sequences():
         assert torch.equal(a, b)
     for a, b in zip(ref_b[1] + ref_b[2], got_h[1] + got_h[2]):
         assert torch.equal(a, b)
+    # label maps streamed to pinned host memory block by block
+    pinned = torch.zeros((len(seq_b), *SIZE), dtype=torch.uint8).pin_memory()
+    torch.manual_seed(5)
+    outs, _ = trk.run_sequence(seq_b, host_labels=pinned)
+    assert torch.equal(torch.stack([o.reshape(SIZE).cpu() for o in outs]), pinned)
+    assert torch.equal(pinned, torch.stack([o.reshape(SIZE) for o in ref_b[0]]))
+
