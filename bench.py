@@ -257,6 +257,11 @@ def run_b200(cfg, steps, warmup, dev, rank, world, dist, with_clocks):
 
     host_out = [torch.empty((cfg["frames"], H, W), dtype=torch.uint8).pin_memory() for _ in mine]
 
+    # [sync] flag of run_sequence.  FRTM_BENCH_CHAIN=1 chains the sequences without a device synchronisation between them
+    # (the next initialisation overlaps the last block): +1-2 % on B200, but one e2e run in four showed a 100-200 ms stall,
+    # so the default keeps the reference's per-sequence synchronisation
+    chain = [os.environ.get("FRTM_BENCH_CHAIN", "0") != "1"]
+
     def step(seqs, read_back=False):
         # the rank's sequences run back to back as in Tracker.run_dataset: while one is tracked, the host half of the next
         # one's first-frame initialisation (augmentation) is prepared in worker threads; the sequence after the last one
@@ -264,7 +269,8 @@ def run_b200(cfg, steps, warmup, dev, rank, world, dist, with_clocks):
         # label maps of every block go to pinned host memory on a copy stream while the next block is tracked.
         maps = []
         for k, s in enumerate(seqs):
-            outs, _ = trk.run_sequence(s, next_sequence=seqs[(k + 1) % len(seqs)], host_labels=host_out[k] if read_back else None)
+            outs, _ = trk.run_sequence(s, next_sequence=seqs[(k + 1) % len(seqs)], host_labels=host_out[k] if read_back else None,
+                                       sync=chain[0])
             maps.append(torch.stack([o.reshape(H, W) for o in outs]))
         labels = torch.stack(maps)                                 # (S,T,H,W) uint8
         if world > 1:

@@ -98,6 +98,13 @@ class Discriminator(nn.Module):
 
     def init(self, x, y, x_nhwc=None):
         """x (K,C,h,w) first-frame augmented features, y (K,1,H,W) masks (``:154-199``)."""
+        self.init_joint(x, y, x_nhwc)
+        self.init_memory()
+
+    def init_joint(self, x, y, x_nhwc=None):
+        """First half of ``init`` (``:154-175``): the joint Gauss-Newton fit of projection and filter on the raw features.
+        It touches nothing but this object's own ``project`` / ``filter`` weights, so the tracker runs it while the previous
+        sequence's last block is still executing; ``init_memory`` (pooled per-slot buffers) completes the initialisation."""
         if x_nhwc is None:
             x_nhwc = ops.nchw_to_nhwc(x)
         x_nhwc = x_nhwc.contiguous()
@@ -118,8 +125,13 @@ class Discriminator(nn.Module):
         optimizer = GaussNewtonCG(problem, TensorList([self.project.weight, self.filter.weight]), fletcher_reeves=False,
                                   standard_alpha=True, direction_forget_factor=self.direction_forget_factor)
         optimizer.run(self.init_iters)
+        self._init_ctx = (x_nhwc, yf, pw, stencil, uty)
 
-        # re-project with the learned matrix, fill the memory, warm up the filter-only optimiser
+    def init_memory(self):
+        """Second half of ``init`` (``:177-199``): re-project with the learned matrix, fill the memory, warm up the
+        filter-only optimiser.  Uses the pooled per-slot buffers, so it runs once the slot's previous owner is done."""
+        x_nhwc, yf, pw, stencil, uty = self._init_ctx
+        self._init_ctx = None
         cx = self._project_nchw(x_nhwc)
         # ``buffer_pool`` (set by the tracker): the frame memory and the CG state of this object slot are reused across
         # sequences — same addresses, so a captured track-block graph stays valid — instead of being reallocated

@@ -177,12 +177,15 @@ class Tracker(nn.Module):
                 sequence.release()
         print("Average frame rate: %.2f fps" % (fps_sum / max(fps_n, 1)))
 
-    def run_sequence(self, sequence, speedrun=False, next_sequence=None, host_labels=None):
+    def run_sequence(self, sequence, speedrun=False, next_sequence=None, host_labels=None, sync=True):
         """``next_sequence`` (optional, not in the reference signature): the sequence that will be run after this one; the
         host part of its first-frame initialisation (augmentation) is prepared in worker threads while this sequence is
         tracked.  Results are identical with and without it.  ``host_labels`` (optional): a pinned uint8 tensor
         (frames, H, W); every frame's label map is also copied into it on a copy stream as soon as its block is done, so the
-        device->host transfer of the results runs behind the tracking instead of after it (complete on return)."""
+        device->host transfer of the results runs behind the tracking instead of after it (complete on return).
+        ``sync=False``: do not wait for the device at the end — the returned label maps (and ``host_labels``) are complete once
+        ``self.sequence_done`` (a CUDA event) has been reached, the frame rate is not measured (nan) — so that a driver can
+        issue the next sequence at once: its initialisation then overlaps this sequence's last block."""
         self.eval()
         self.object_ids = sequence.obj_ids
         self.current_frame = 0
@@ -289,6 +292,11 @@ class Tracker(nn.Module):
             self.current_frame += nb
             i += nb
             N += nb
+        if getattr(self, "_d2h_stream", None) is not None and host_labels is not None:
+            main.wait_stream(self._d2h_stream)
+        self.sequence_done = main.record_event()
+        if not sync:
+            return outputs, float("nan")
         torch.cuda.synchronize()
         T = time() - t0
         return outputs, N / T
@@ -378,7 +386,7 @@ class Tracker(nn.Module):
             nv = res[0][0].shape[0]
             return [(res[k][0], res[k][1], done, x[k * nv:(k + 1) * nv]) for k in range(n_new)]
 
-        rec = dict(sequence=sequence, objects=tuple(new_objects), keep=(image_d, labels_d), futures=futures,
+        rec = dict(sequence=sequence, objects=tuple(new_objects), keep=(image_d, labels_d), uploaded=uploaded, futures=futures,
                    features=pool.submit(features))
         self._prefetched[key] = rec
         while len(self._prefetched) > 2:              # an entry whose sequence never ran
@@ -403,11 +411,20 @@ class Tracker(nn.Module):
         n_new = len(new_objects)
         if getattr(self, "_aug_streams", None) is None or len(self._aug_streams) < n_new:
             self._aug_streams = [torch.cuda.Stream(device=image.device) for _ in range(max(n_new, 1))]
-        for st in self._aug_streams[:n_new]:
-            st.wait_stream(main)                     # image / labels uploads are visible to the side streams
+        matches = prefetched is not None and prefetched["objects"] == tuple(new_objects)
+        if matches:
+            # Views and features were prepared on streams of their own: the joint fits below depend on nothing the main
+            # stream still has queued, so they start at once — while the PREVIOUS sequence's last block is still running
+            # when the caller chains sequences with ``run_sequence(..., sync=False)`` — and only the second half of an
+            # initialisation (the pooled frame memory of the object slot) waits for the main stream.
+            labels = prefetched["keep"][1]           # the same ground truth, uploaded by prefetch_init on its own stream
+            for st in self._aug_streams[:n_new]:
+                st.wait_event(prefetched["uploaded"])
+        else:
+            for st in self._aug_streams[:n_new]:
+                st.wait_stream(main)                 # image / labels uploads are visible to the side streams
         # targets are constructed in order on the main thread: each constructor draws its initial weights from the global
         # torch generator exactly where the reference does (before the reseed of that object)
-        matches = prefetched is not None and prefetched["objects"] == tuple(new_objects)
         targets = []
         for k, obj_id in enumerate(new_objects):
             with torch.cuda.stream(self._aug_streams[k]):
@@ -456,10 +473,13 @@ class Tracker(nn.Module):
                 if feat:                             # prefetched: the backbone pass is done as well
                     x = feat[0]
                     x.record_stream(side)
+                    target.discriminator.init_joint(None, msk, x_nhwc=x)
+                    side.wait_stream(main)           # the slot's pooled memory may still serve the previous sequence
+                    target.discriminator.init_memory()
                 else:
                     _, f32, _ = self.feature_extractor.forward_split(im, (), (target.disc_layer,), upto=target.disc_layer)
                     x = f32[target.disc_layer]
-                target.discriminator.init(None, msk, x_nhwc=x)
+                    target.discriminator.init(None, msk, x_nhwc=x)
         for k, target in enumerate(targets):
             main.wait_stream(self._aug_streams[k])
             d = target.discriminator

@@ -240,4 +240,18 @@ def test_prefetched_initialisation_gives_identical_sequences():
     outs, _ = trk.run_sequence(seq_b, host_labels=pinned)
     assert torch.equal(torch.stack([o.reshape(SIZE).cpu() for o in outs]), pinned)
     assert torch.equal(pinned, torch.stack([o.reshape(SIZE) for o in ref_b[0]]))
+    # chained sequences: no device synchronisation between them, the joint fits of seq_b's objects start while seq_a's
+    # last block is still running; complete once ``sequence_done`` has been reached
+    pinned.zero_()
+    torch.manual_seed(5)
+    trk.run_sequence(seq_a, next_sequence=seq_b, sync=False)
+    torch.manual_seed(5)
+    outs, fps = trk.run_sequence(seq_b, host_labels=pinned, sync=False)
+    assert fps != fps                                      # nan: not measured
+    trk.sequence_done.synchronize()
+    assert torch.equal(pinned, torch.stack([o.reshape(SIZE) for o in ref_b[0]]))
+    got = [trk.targets[o].discriminator.filter.weight.detach().clone() for o in seq_b.obj_ids] + \
+          [trk.targets[o].discriminator.memory.weights.clone() for o in seq_b.obj_ids]
+    for a, b in zip(ref_b[1] + ref_b[2], got):
+        assert torch.equal(a, b)
 
