@@ -1,6 +1,6 @@
 #!/bin/bash
 O=gpurun_out/r04a; mkdir -p $O
-for v in 1 1 1 1 0 0 1 1; do
+for v in 0 0 0 0 1 1 1 1; do
 FRTM_BENCH_CHAIN=$v timeout 900 python bench.py --steps 8 --warmup 3 --no-cpu-baseline > $O/b.json 2> $O/b.err
 python - <<PY
 import json
