@@ -1286,6 +1286,239 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_tc1_kernel(const __grid_co
   }
 }
 
+// ----------------------------------------------------------------------------------------------------------------
+// The 7x7 / stride-2 stem (torchvision resnet.py conv1 + bn1 + relu, model/feature_extractor.py:42-46) straight from the
+// uint8 image.  The stem is a 1x1 tensor-core conv over im2col patches (K = ky*24 + c*8 + kx = 192, frtm_stem_patches_u8);
+// materialising the patches costs 570 MB of writes and the same again of reads per 8 frames of 480x854 for a 3 MB input.
+// Here eight builder warps write the patches of a 16x8-pixel tile directly into the shared-memory image the MMA reads:
+// one thread = one 16-byte chunk (the 7 kx taps of one (pixel, ky, c) + a zero) of the hi and of the lo plane, placed at
+// its 128-byte-swizzled position (row = pixel, chunk j of k-block kc at j ^ (pixel % 8)); a fence.proxy.async publishes
+// the generic-proxy writes to the tensor core.  Everything else is the streaming 1x1 kernel: weights resident, a 4-stage
+// ring of k-blocks, one TMEM slot per tile, fp32 fold + bias (folded BatchNorm) + ReLU in the epilogue.  The patch values
+// are computed exactly as stem_patches_kernel computes them, so the result is bit-identical to the two-kernel path.
+// warp 0: weights; warp 1: MMA; warps 2-5: epilogue; warps 6-13: builders.
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int ST_THREADS = 448, ST_BUILD0 = 192, ST_NBUILD = 256;
+constexpr int ST_KC = 3;                                         // k-blocks of 64: K = 192
+constexpr int ST_RROWS = 2 * S3_TH + 5, ST_RCOLS = 24;           // image region behind a tile: 37 rows x (2*8+5 = 21 -> 24) columns
+
+__global__ void __launch_bounds__(ST_THREADS, 1) conv_stem_kernel(const uint8_t *__restrict__ img, const TcArgs a, float s0, float s1,
+                                                                  float s2, float b0, float b1, float b2) {
+  constexpr int BN = 64;
+  constexpr int B_BYTES = BN * 128;
+  constexpr int STAGE_BYTES = 2 * S1_TILE_BYTES;
+  constexpr int SLOT = 2 * BN;
+  constexpr int COLS = tmem_cols(2 * SLOT);
+  constexpr int W_BYTES = ST_KC * 2 * B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t ring = base;
+  const uint32_t wsm = base + S1_STAGES * STAGE_BYTES;
+  constexpr int TAIL = S1_STAGES * STAGE_BYTES + W_BYTES;
+  const uint32_t bar_full = base + TAIL;                         // S1_STAGES x 8 B: one arrive per builder warp
+  const uint32_t bar_empty = bar_full + 8 * S1_STAGES;
+  const uint32_t bar_accf = bar_empty + 8 * S1_STAGES;           // 2 x 8 B
+  const uint32_t bar_acce = bar_accf + 16;
+  const uint32_t bar_w = bar_acce + 16;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gen + TAIL + 16 * S1_STAGES + 40);
+  float *s_osc = reinterpret_cast<float *>(gen + TAIL + 16 * S1_STAGES + 64);          // osc[64] | bias[64] (+ unused tap / r1 areas)
+  uint8_t *region = gen + TAIL + 16 * S1_STAGES + 64 + 84 * BN;                          // 2 x [hi|lo][3][ST_RROWS][ST_RCOLS] halves
+
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  const int tiles_per_img = a.tiles_x * a.tiles_y;
+  const int ntiles = a.B * tiles_per_img;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < S1_STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, ST_NBUILD / 32);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int j = 0; j < 2; ++j) {
+      mbar_init(bar_accf + 8 * j, 1);
+      mbar_init(bar_acce + 8 * j, 4);
+    }
+    mbar_init(bar_w, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(bar_w, W_BYTES);
+      for (int kc = 0; kc < ST_KC; ++kc)
+        bulk_load(wsm + kc * 2 * B_BYTES, reinterpret_cast<const uint8_t *>(a.wt) + (size_t)kc * 2 * B_BYTES, 2 * B_BYTES, bar_w);
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = umma_idesc(128, BN), idesc2 = umma_idesc(128, 2 * BN);
+    mbar_wait(bar_w, 0);
+    uint32_t it = 0, nt = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++nt) {
+      const uint32_t slot = nt & 1;
+      mbar_wait(bar_acce + 8 * slot, ((nt >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + slot * SLOT;
+      for (int kc = 0; kc < ST_KC; ++kc, ++it) {
+        const int s = it % S1_STAGES;
+        mbar_wait(bar_full + 8 * s, (it / S1_STAGES) & 1);
+        tc_fence_after();
+        const uint64_t a_hi = umma_desc(ring + s * STAGE_BYTES), a_lo = a_hi + (uint64_t)(S1_TILE_BYTES >> 4);
+        const uint64_t b_hl = umma_desc(wsm + kc * 2 * B_BYTES);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+            umma_f16(tacc, a_hi + adv, b_hl + adv, idesc2, (kc == 0 && k == 0) ? 0u : 1u);
+            umma_f16(tacc, a_lo + adv, b_hl + adv, idesc, 1u);
+          }
+          umma_commit(bar_empty + 8 * s);
+          if (kc == ST_KC - 1) umma_commit(bar_accf + 8 * slot);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 6) {
+    // ---- epilogue: tiles alternate between the two TMEM slots ----
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    tc_epilogue_stage<BN, false, false>(a, 0, s_osc);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    uint32_t nt = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++nt) {
+      const uint32_t slot = nt & 1;
+      const int b = tile / tiles_per_img, tr = tile - b * tiles_per_img;
+      const int y0 = (tr / a.tiles_x) * S3_TH, x0 = (tr % a.tiles_x) * S3_TW;
+      float acc[BN];
+      mbar_wait(bar_accf + 8 * slot, (nt >> 1) & 1);
+      tc_fence_after();
+      const uint32_t col0 = tmem_base + ((uint32_t)(q * 32) << 16) + slot * SLOT;
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float t[32], t2[32];
+        tmem_ld32(col0 + c0, t);
+        tmem_ld32(col0 + BN + c0, t2);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[c0 + j] = t[j] + t2[j];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_acce + 8 * slot) : "memory");
+      tc_epilogue_store<BN, false, false>(a, acc, b, y0 + row / S3_TW, x0 + row % S3_TW, 0, s_osc);
+    }
+  } else {
+    // ---- builders: the tile's image region -> shared memory, then its patches k-block by k-block into the ring.  The
+    //      region of the NEXT tile is fetched into registers (all loads in flight) before the current tile's patches are
+    //      built and stored to the other region buffer afterwards, so its global-memory latency hides behind the build ----
+    const int tb = (int)threadIdx.x - ST_BUILD0;
+    constexpr int RBYTES = 3 * ST_RROWS * ST_RCOLS, RPT = (RBYTES + ST_NBUILD - 1) / ST_NBUILD;
+    uint32_t nxt[RPT];      // one register per byte (a packed uint8_t array would make every load wait for its byte insert); 256 = outside
+    auto fetch = [&](int tile) {
+      const int b = tile / tiles_per_img, tr = tile - b * tiles_per_img;
+      const int ry0 = 2 * (tr / a.tiles_x) * S3_TH - 3, rx0 = 2 * (tr % a.tiles_x) * S3_TW - 3;
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) {
+        const int i = tb + k * ST_NBUILD;
+        const int c = i / (ST_RROWS * ST_RCOLS), rr = (i / ST_RCOLS) % ST_RROWS, cc = i % ST_RCOLS;
+        const int iy = ry0 + rr, ix = rx0 + cc;
+        nxt[k] = 256u;
+        if (i < RBYTES && tile < ntiles && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W)
+          nxt[k] = img[(((int64_t)b * 3 + c) * a.H + iy) * (int64_t)a.W + ix];
+      }
+    };
+    // the region as split fp16 planes of 16 * normalised value (exactly stem_patches_kernel's arithmetic: mul then add,
+    // separately rounded), zero outside the image: every input pixel is converted once per tile instead of once per
+    // patch it appears in (~12 x), and a patch chunk becomes a plain 14-byte gather per plane
+    auto stash = [&](__half *dst) {
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) {
+        const int i = tb + k * ST_NBUILD;
+        if (i < RBYTES) {
+          const int c = i / (ST_RROWS * ST_RCOLS);
+          const float sc = c == 0 ? s0 : (c == 1 ? s1 : s2), bc = c == 0 ? b0 : (c == 1 ? b1 : b2);
+          const float v = nxt[k] < 256u ? __fadd_rn(__fmul_rn(sc, (float)nxt[k]), bc) * 16.f : 0.f;
+          const __half h = __float2half_rn(v);
+          dst[i] = h;
+          dst[RBYTES + i] = __float2half_rn(v - __half2float(h));
+        }
+      }
+    };
+    __half *region0 = reinterpret_cast<__half *>(region);        // two buffers of [hi | lo][3][rows][cols] halves, tiles alternate
+    fetch(blockIdx.x);
+    stash(region0);
+    asm volatile("bar.sync 2, 256;" ::: "memory");
+#ifdef TC2_TIMING
+    long long tacc[6] = {0, 0, 0, 0, 0, 0}, tlast = clock64();
+#define ST_T(k) do { const long long t__ = clock64(); tacc[k] += t__ - tlast; tlast = t__; } while (0)
+#else
+#define ST_T(k) do {} while (0)
+#endif
+    uint32_t it = 0, nt = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++nt) {
+      const int b = tile / tiles_per_img, tr = tile - b * tiles_per_img;
+      const int y0 = (tr / a.tiles_x) * S3_TH, x0 = (tr % a.tiles_x) * S3_TW;
+      (void)b;
+      const __half *reg_h = region0 + (nt & 1) * 2 * RBYTES, *reg_l = reg_h + RBYTES;
+      ST_T(0);
+      fetch(tile + (int)gridDim.x);
+      ST_T(1);
+      for (int kc = 0; kc < ST_KC; ++kc, ++it) {
+        const int s = it % S1_STAGES;
+        mbar_wait(bar_empty + 8 * s, ((it / S1_STAGES) & 1) ^ 1);
+        ST_T(2);
+        uint8_t *st_hi = gen + s * STAGE_BYTES, *st_lo = st_hi + S1_TILE_BYTES;
+#pragma unroll 2
+        for (int i = tb; i < 128 * 8; i += ST_NBUILD) {
+          const int r = i >> 3, jc = i & 7, j = kc * 8 + jc;
+          const int ty = r >> 3, tx = r & 7;
+          const int ky = min(j / 3, 6), c = j - (j / 3) * 3;
+          // seven consecutive halves of a region row (even start: 4-byte aligned), the eighth is the zero pad
+          const int ro = (c * ST_RROWS + 2 * ty + ky) * ST_RCOLS + 2 * tx;
+          const uint32_t *gh = reinterpret_cast<const uint32_t *>(reg_h + ro), *gl = reinterpret_cast<const uint32_t *>(reg_l + ro);
+          uint32_t ph[4], pl[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { ph[e] = gh[e]; pl[e] = gl[e]; }
+          ph[3] &= 0xffffu; pl[3] &= 0xffffu;
+          if (j >= 21) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { ph[e] = 0u; pl[e] = 0u; }
+          }
+          const int off = r * 128 + ((jc ^ (r & 7)) << 4);
+          *reinterpret_cast<uint4 *>(st_hi + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+          *reinterpret_cast<uint4 *>(st_lo + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+        }
+        ST_T(3);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_full + 8 * s) : "memory");
+        ST_T(4);
+      }
+      stash(region0 + ((nt & 1) ^ 1) * 2 * RBYTES);
+      asm volatile("bar.sync 2, 256;" ::: "memory");              // next region complete, this one no longer read
+      ST_T(5);
+    }
+#ifdef TC2_TIMING
+    if (tb == 0 && blockIdx.x == 0)
+      printf("stem cta 0 builder: tiles %u | other %lld fetch-issue %lld wait-empty %lld build %lld fence+arrive %lld stash+bar %lld\n", nt,
+             tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], tacc[5]);
+#endif
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(COLS) : "memory");
+  }
+}
+
 // fp32 NHWC (ldx) -> two fp16 planes hi/lo of x * 2^4 (channel stride ldh)
 __global__ void split_kernel(const float *__restrict__ x, int64_t npix, int C, int ldx, __half *__restrict__ hi,
                              __half *__restrict__ lo, int ldh) {
@@ -1563,6 +1796,45 @@ static int launch_tc1(const CUtensorMap &mh, const CUtensorMap &ml, const TcArgs
 }  // namespace frtm
 
 using namespace frtm;
+
+extern "C" int frtm_stem_conv_u8(const uint8_t *img, int B, int H, int W, const void *wt, const float *oscale, const float *bias,
+                                 float *y, int ldy, int relu, void *stream) {
+  FRTM_REQUIRE(img && wt && oscale && y && B > 0 && H > 0 && W > 0, "stem_conv: bad arguments");
+  FRTM_REQUIRE(ldy >= 64 && (reinterpret_cast<uintptr_t>(wt) & 15) == 0, "stem_conv: 64 output channels, 16-byte aligned weights");
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+  float s[3], b[3];
+  for (int i = 0; i < 3; ++i) {        // same constants, rounded the same way, as frtm_normalize_u8 / frtm_stem_patches_u8
+    volatile float rcp = 1.0f / stdv[i];
+    s[i] = rcp * (float)(1.0 / 255.0);
+    b[i] = -mean[i] / stdv[i];
+  }
+  TcArgs a;
+  a.wt = (const __half *)wt; a.oscale = oscale; a.bias = bias; a.res = nullptr; a.res_hi = nullptr; a.res_lo = nullptr;
+  a.y = y; a.y_nchw = nullptr; a.y_hi = nullptr; a.y_lo = nullptr; a.tapw = nullptr; a.y_tap = nullptr;
+  a.r1_score = nullptr; a.r1_w = nullptr; a.r1_bias = nullptr; a.y_extra = nullptr; a.extra_ch = -1; a.yh_cout = 64;
+  a.ldr = 0; a.ldrh = 0; a.ldy = ldy; a.y_coff = 0; a.ldyh = 0; a.yh_coff = 0;
+  a.B = B; a.H = H; a.W = W; a.Cout = 64; a.kh = 1; a.kw = 1; a.pad = 0; a.relu = relu; a.stride = 1;
+  a.Ho = (H + 6 - 7) / 2 + 1; a.Wo = (W + 6 - 7) / 2 + 1;
+  a.tiles_x = cdiv(a.Wo, S3_TW); a.tiles_y = cdiv(a.Ho, S3_TH); a.kchunks = ST_KC;
+  constexpr int smem = S1_STAGES * 2 * S1_TILE_BYTES + ST_KC * 2 * 64 * 128 + 16 * S1_STAGES + 64 + 84 * 64 +
+                       2 * 2 * 3 * ST_RROWS * ST_RCOLS * 2 + 64 + 1024;
+  static_assert(smem <= 227 * 1024, "conv_stem: shared memory budget");
+  static bool configured = false;
+  static int num_sms = 0;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { set_error("stem_conv: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return FRTM_ELAUNCH; }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+    configured = true;
+  }
+  const int ntiles = a.B * a.tiles_x * a.tiles_y;
+  conv_stem_kernel<<<ntiles < num_sms ? ntiles : num_sms, ST_THREADS, smem, (cudaStream_t)stream>>>(img, a, s[0], s[1], s[2], b[0],
+                                                                                                    b[1], b[2]);
+  FRTM_CHECK_LAUNCH("stem_conv");
+  return FRTM_OK;
+}
 
 extern "C" int frtm_split_f16(const float *x, int64_t npix, int C, int ldx, void *hi, void *lo, int ldh, void *stream) {
   FRTM_REQUIRE(x && hi && lo && C % 4 == 0 && ldx % 4 == 0 && ldh % 8 == 0, "split_f16: bad arguments");

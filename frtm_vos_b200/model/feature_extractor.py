@@ -96,7 +96,7 @@ class ResnetFeatureExtractor:
         require_cuda(images, "image")
         w = self._w
         split, f32, nchw = {}, {}, {}
-        x = ops.conv2d_tc(ops.stem_patches(images), w["stem"], relu=True)["y"]
+        x = ops.stem_conv(images, w["stem"])            # 7x7/s2 stem + bn1 + relu: patches built in shared memory
         if "layer1" in nchw_layers:
             x, nchw["layer1"] = ops.maxpool3x3s2(x, nchw=True)
         else:

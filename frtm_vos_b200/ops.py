@@ -139,6 +139,19 @@ def stem_patches(images: torch.Tensor) -> "Split":
     return sp
 
 
+def stem_conv(images: torch.Tensor, pc: "PackedConvTC", relu: bool = True) -> torch.Tensor:
+    """uint8 (B,3,H,W) -> fp32 NHWC (B,Ho,Wo,64): the 7x7/s2/p3 stem (+ folded BatchNorm + ReLU) in one kernel; the im2col
+    patches are built in shared memory.  ``pc`` = ``pack_conv_tc(stem_weight_as_1x1(conv1.weight), bn=...)``.  Bit-identical
+    to ``conv2d_tc(stem_patches(images), pc, relu=relu)``."""
+    B, C, H, W = images.shape
+    assert C == 3 and images.dtype == torch.uint8 and pc.cout == 64 and pc.cin == 192 and pc.bn == 64 and pc.k == 1
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    y = torch.empty((B, Ho, Wo, 64), device=images.device, dtype=torch.float32)
+    lib().stem_conv_u8(ptr(images.contiguous()), B, H, W, ptr(pc.wt), ptr(pc.oscale), ptr(pc.bias), ptr(y), 64, 1 if relu else 0,
+                       stream())
+    return y
+
+
 def pyrup_bicubic(x: torch.Tensor, split: bool = False):
     """x2 bicubic pyramid upsample; ``split=True`` returns the result as ``Split`` planes (the next conv's input format)
     without ever writing the fp32 tensor."""

@@ -118,6 +118,12 @@ int frtm_rank1_finish(const float *y_in, int ldin, int n_obj, float *y_out, int 
  * (B,Ho,Wo,192) of 16*x: k = ky*24 + c*8 + kx (kx = 7 and k >= 168 are zero); Ho = (H-1)/2+1.  The stem is then a 1x1
  * frtm_conv2d_tc with Cin = 192 and conv1.weight permuted the same way (frtm_vos_b200.ops.stem_weight_as_1x1). */
 int frtm_stem_patches_u8(const uint8_t *img, int B, int H, int W, void *hi, void *lo, void *stream);
+/* The stem in ONE kernel: the patches above are built tile by tile in shared memory (never written to HBM) and consumed by
+ * the tensor core; y (B,Ho,Wo,ldy)[0,64) = relu?(conv7x7/s2(normalise(img)) * folded BatchNorm), fp32 NHWC.  wt / oscale / bias:
+ * conv1.weight as frtm_vos_b200.ops.stem_weight_as_1x1 packs it for frtm_conv2d_tc with the N tile 64.  Bit-identical to
+ * frtm_stem_patches_u8 + frtm_conv2d_tc. */
+int frtm_stem_conv_u8(const uint8_t *img, int B, int H, int W, const void *wt, const float *oscale, const float *bias, float *y,
+                      int ldy, int relu, void *stream);
 int frtm_maxpool3x3s2_nhwc(const float *x, int B, int H, int W, int C, float *y, float *y_nchw, void *stream);
 
 /* Bilinear resize (align_corners=False) of an NHWC tensor; writes C channels at offset y_coff of a tensor with

@@ -273,3 +273,29 @@ def test_pair_kernel_matches_fp32_and_general_kernel(cin, cout, k, stride, hw, B
         assert (o["y"] - gen["y"]).abs().max().item() < 4e-6 * scale, sel
         d = (o["split"].hi.float() + o["split"].lo.float()) - (gen["split"].hi.float() + gen["split"].lo.float())
         assert d.abs().max().item() / 16.0 < 4e-6 * scale, sel
+
+
+@pytest.mark.parametrize("hw,B", [((480, 854), 2), ((128, 224), 3), ((61, 75), 1), ((720, 1280), 1)])
+def test_fused_stem_is_bit_identical_to_patches_plus_conv(hw, B):
+    """frtm_stem_conv_u8 (im2col patches of the 7x7/s2 stem built in shared memory) against frtm_stem_patches_u8 +
+    frtm_conv2d_tc bit for bit, and against F.conv2d on the normalised image (torchvision resnet.py conv1 + bn1 + relu)."""
+    from frtm_vos_b200 import ops
+    g = torch.Generator().manual_seed(hw[0] + B)
+    img = torch.randint(0, 256, (B, 3, *hw), dtype=torch.uint8, generator=g)
+    w = torch.randn(64, 3, 7, 7, generator=g) / 12
+    bn = dict(weight=torch.rand(64, generator=g) + 0.5, bias=torch.randn(64, generator=g) * 0.1,
+              running_mean=torch.randn(64, generator=g) * 0.1, running_var=torch.rand(64, generator=g) + 0.5)
+    pc = ops.pack_conv_tc(ops.stem_weight_as_1x1(w), bn=bn, device=DEV)
+    d = img.to(DEV)
+    old = ops.conv2d_tc(ops.stem_patches(d), pc, relu=True)["y"]
+    new = ops.stem_conv(d, pc)
+    torch.cuda.synchronize()
+    assert torch.equal(old, new)
+    mean, std = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1), torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    x = (img.float() / 255 - mean) / std
+    ref = F.conv2d(x, w, None, 2, 3)
+    ref = (ref - bn["running_mean"].view(1, -1, 1, 1)) / torch.sqrt(bn["running_var"].view(1, -1, 1, 1) + 1e-5) * \
+        bn["weight"].view(1, -1, 1, 1) + bn["bias"].view(1, -1, 1, 1)
+    ref = F.relu(ref)
+    assert (_nchw(new.cpu()) - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
+
