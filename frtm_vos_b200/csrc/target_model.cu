@@ -595,12 +595,22 @@ __global__ void __launch_bounds__(256) build_stencil_kernel(const float *__restr
   int Y0 = (int)floorf(((float)i - 1.f + 0.5f) / sh - 0.5f) - 1, Y1 = (int)ceilf(((float)i + 1.f + 0.5f) / sh - 0.5f) + 1;
   int X0 = (int)floorf(((float)j - 1.f + 0.5f) / sw - 0.5f) - 1, X1 = (int)ceilf(((float)j + 1.f + 0.5f) / sw - 0.5f) + 1;
   Y0 = max(Y0, 0); X0 = max(X0, 0); Y1 = min(Y1, H - 1); X1 = min(X1, W - 1);
-  const int nx = X1 - X0 + 1;
   float acc[9], accy = 0.f;
 #pragma unroll
   for (int t = 0; t < 9; ++t) acc[t] = 0.f;
   const float *pwk = pw + (int64_t)k * H * W, *yk = y + (int64_t)k * H * W;
-  for (int xb = 0; xb < nx; xb += 32) {                    // (one or two passes: the window is ~2W/w + 4 columns wide)
+  // The columns that really touch j (source x in (j-1, j+1)) are one interval of at most 2W/w <= 32 columns inside the
+  // conservative window (~2W/w + 4): start the pass at the first of them, and the second pass — four live lanes repeating
+  // all the row work — is needed only when the interval is wider than a warp.
+  {
+    const int X = X0 + lane;
+    int x0, x1;
+    float lx;
+    bilinear_src(min(X, X1), sw, w, x0, x1, lx);
+    const unsigned live = __ballot_sync(0xffffffffu, X <= X1 && tent(j, x0, x1, lx) != 0.f);
+    if (live != 0u) X0 += __ffs(live) - 1;
+  }
+  for (int xb = 0; xb < X1 - X0 + 1; xb += 32) {
     const int X = X0 + xb + lane;
     float cx[3] = {0.f, 0.f, 0.f}, cxc = 0.f;
     if (X <= X1) {
