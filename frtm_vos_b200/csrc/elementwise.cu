@@ -965,6 +965,59 @@ extern "C" int frtm_cab_apply_nhwc(const float *shallow, const float *gate, cons
   return FRTM_OK;
 }
 
+// CAB with the deeper level resized on the fly (seg_network.py:38-39: shallower * gate + F.interpolate(deeper, bilinear)):
+// the (B,Hd,Wd,C) map is 4x smaller than the resized one and stays in L2, so the resize kernel's write of the full-size
+// map and this kernel's read of it disappear.  Same bilinear arithmetic as resize_bilinear_kernel.
+namespace frtm {
+__global__ void __launch_bounds__(256) cab_apply_resized_kernel(const float4 *__restrict__ sh, const float *__restrict__ gate,
+                                                                const float *__restrict__ deeper, int H, int W, int C, int Hd,
+                                                                int Wd, float shy, float shx, int64_t total4,
+                                                                float4 *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int C4 = C / 4;
+  const int c = (int)(i % C4) * 4;
+  int64_t r = i / C4;
+  const int ox = (int)(r % W);
+  r /= W;
+  const int oy = (int)(r % H);
+  const int64_t b = r / H;
+  int y0, y1, x0, x1;
+  float ly, lx;
+  bilinear_src(oy, shy, Hd, y0, y1, ly);
+  bilinear_src(ox, shx, Wd, x0, x1, lx);
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  const float4 p00 = *reinterpret_cast<const float4 *>(deeper + ((b * Hd + y0) * Wd + x0) * C + c);
+  const float4 p01 = *reinterpret_cast<const float4 *>(deeper + ((b * Hd + y0) * Wd + x1) * C + c);
+  const float4 p10 = *reinterpret_cast<const float4 *>(deeper + ((b * Hd + y1) * Wd + x0) * C + c);
+  const float4 p11 = *reinterpret_cast<const float4 *>(deeper + ((b * Hd + y1) * Wd + x1) * C + c);
+  float4 d;
+  d.x = hy * (hx * p00.x + lx * p01.x) + ly * (hx * p10.x + lx * p11.x);
+  d.y = hy * (hx * p00.y + lx * p01.y) + ly * (hx * p10.y + lx * p11.y);
+  d.z = hy * (hx * p00.z + lx * p01.z) + ly * (hx * p10.z + lx * p11.z);
+  d.w = hy * (hx * p00.w + lx * p01.w) + ly * (hx * p10.w + lx * p11.w);
+  const float4 g = *reinterpret_cast<const float4 *>(gate + b * C + c);
+  const float4 s = sh[i];
+  float4 o;
+  o.x = __fadd_rn(__fmul_rn(s.x, g.x), d.x);
+  o.y = __fadd_rn(__fmul_rn(s.y, g.y), d.y);
+  o.z = __fadd_rn(__fmul_rn(s.z, g.z), d.z);
+  o.w = __fadd_rn(__fmul_rn(s.w, g.w), d.w);
+  out[i] = o;
+}
+}  // namespace frtm
+
+extern "C" int frtm_cab_apply_resized_nhwc(const float *shallow, const float *gate, const float *deeper, int B, int H, int W, int C,
+                                           int Hd, int Wd, float *out, void *stream) {
+  FRTM_REQUIRE(shallow && gate && deeper && out && C % 4 == 0 && Hd > 0 && Wd > 0, "cab_apply_resized: bad arguments");
+  const int64_t total4 = (int64_t)B * H * W * (C / 4);
+  frtm::cab_apply_resized_kernel<<<cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4 *>(shallow), gate, deeper, H, W, C, Hd, Wd, (float)Hd / (float)H, (float)Wd / (float)W, total4,
+      reinterpret_cast<float4 *>(out));
+  FRTM_CHECK_LAUNCH("cab_apply_resized");
+  return FRTM_OK;
+}
+
 extern "C" int frtm_scatter_channel_nhwc(const float *src, int B, int HW, float *dst, int ld, int coff, int nzero,
                                          void *stream) {
   FRTM_REQUIRE(src && dst && coff + nzero < ld, "scatter_channel: bad arguments");

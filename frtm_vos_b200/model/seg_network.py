@@ -208,8 +208,8 @@ class SegNetwork(nn.Module):
                 t = ops.cab(t, sp, hpool, hpool, W["cab_w1"], W["cab_b1"], W["cab_w2"], W["cab_b2"])
             else:
                 dp = ops.global_avgpool(x)
-                deeper = ops.resize_bilinear(x, (h, w))
-                t = ops.cab(t, sp, dp, deeper, W["cab_w1"], W["cab_b1"], W["cab_w2"], W["cab_b2"])
+                # F.interpolate(deeper, (h, w)) of seg_network.py:39 happens inside the CAB kernel
+                t = ops.cab(t, sp, dp, x, W["cab_w1"], W["cab_b1"], W["cab_w2"], W["cab_b2"])
             x = self._rrb(ops.split_f16(t), W, "rrb2")
         # conv2 is linear and so is the bicubic/bilinear chain in front of it: the 32 channels are contracted to the 9 tap
         # maps of conv2 at 240x428 in conv1's epilogue (the 32-channel tensor is never written); one kernel then does

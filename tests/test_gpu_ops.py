@@ -127,6 +127,13 @@ def test_gap_and_cab():
     ref = x * gate[:, :, None, None] + deeper
     out = ops.cab(_nhwc(x).to(DEV), pooled, dp.to(DEV), _nhwc(deeper).to(DEV), w1.to(DEV), b1.to(DEV), w2.to(DEV), b2.to(DEV))
     assert (_nchw(out.cpu()) - ref).abs().max() < 1e-5
+    low = torch.randn(3, 64, 15, 27, generator=g)                       # deeper level at its own resolution: resized in the kernel
+    out_r = ops.cab(_nhwc(x).to(DEV), pooled, dp.to(DEV), _nhwc(low).to(DEV), w1.to(DEV), b1.to(DEV), w2.to(DEV), b2.to(DEV))
+    ref_r = x * gate[:, :, None, None] + F.interpolate(low, (30, 54), mode="bilinear", align_corners=False)
+    assert (_nchw(out_r.cpu()) - ref_r).abs().max() < 1e-5
+    two = ops.cab(_nhwc(x).to(DEV), pooled, dp.to(DEV), ops.resize_bilinear(_nhwc(low).to(DEV), (30, 54)), w1.to(DEV), b1.to(DEV),
+                  w2.to(DEV), b2.to(DEV))
+    assert (two - out_r).abs().max().item() < 2e-6                      # resize + CAB as two kernels (fma contraction may differ)
     ref_v = x * gate[:, :, None, None] + dp[:, :, None, None]
     out_v = ops.cab(_nhwc(x).to(DEV), pooled, dp.to(DEV), dp.to(DEV), w1.to(DEV), b1.to(DEV), w2.to(DEV), b2.to(DEV))
     assert (_nchw(out_v.cpu()) - ref_v).abs().max() < 1e-5
