@@ -972,7 +972,8 @@ namespace frtm {
 __global__ void __launch_bounds__(256) cab_apply_resized_kernel(const float4 *__restrict__ sh, const float *__restrict__ gate,
                                                                 const float *__restrict__ deeper, int H, int W, int C, int Hd,
                                                                 int Wd, float shy, float shx, int64_t total4,
-                                                                float4 *__restrict__ out) {
+                                                                float4 *__restrict__ out, __half *__restrict__ y_hi,
+                                                                __half *__restrict__ y_lo) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total4) return;
   const int C4 = C / 4;
@@ -1003,17 +1004,29 @@ __global__ void __launch_bounds__(256) cab_apply_resized_kernel(const float4 *__
   o.y = __fadd_rn(__fmul_rn(s.y, g.y), d.y);
   o.z = __fadd_rn(__fmul_rn(s.z, g.z), d.z);
   o.w = __fadd_rn(__fmul_rn(s.w, g.w), d.w);
-  out[i] = o;
+  if (out) out[i] = o;
+  if (y_hi) {   // split planes of 16*x for the tensor-core conv that follows (the same conversion as split_kernel)
+    const float v[4] = {o.x * 16.f, o.y * 16.f, o.z * 16.f, o.w * 16.f};
+    __half h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      h[k] = __float2half_rn(v[k]);
+      l[k] = __float2half_rn(v[k] - __half2float(h[k]));
+    }
+    *reinterpret_cast<uint2 *>(y_hi + i * 4) = *reinterpret_cast<const uint2 *>(h);
+    *reinterpret_cast<uint2 *>(y_lo + i * 4) = *reinterpret_cast<const uint2 *>(l);
+  }
 }
 }  // namespace frtm
 
 extern "C" int frtm_cab_apply_resized_nhwc(const float *shallow, const float *gate, const float *deeper, int B, int H, int W, int C,
-                                           int Hd, int Wd, float *out, void *stream) {
-  FRTM_REQUIRE(shallow && gate && deeper && out && C % 4 == 0 && Hd > 0 && Wd > 0, "cab_apply_resized: bad arguments");
+                                           int Hd, int Wd, float *out, void *y_hi, void *y_lo, void *stream) {
+  FRTM_REQUIRE(shallow && gate && deeper && (out || y_hi) && (!y_hi || y_lo) && C % 4 == 0 && Hd > 0 && Wd > 0,
+               "cab_apply_resized: bad arguments");
   const int64_t total4 = (int64_t)B * H * W * (C / 4);
   frtm::cab_apply_resized_kernel<<<cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const float4 *>(shallow), gate, deeper, H, W, C, Hd, Wd, (float)Hd / (float)H, (float)Wd / (float)W, total4,
-      reinterpret_cast<float4 *>(out));
+      reinterpret_cast<float4 *>(out), (__half *)y_hi, (__half *)y_lo);
   FRTM_CHECK_LAUNCH("cab_apply_resized");
   return FRTM_OK;
 }

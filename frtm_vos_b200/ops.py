@@ -177,21 +177,30 @@ def global_avgpool(x: torch.Tensor, channels: Optional[int] = None) -> torch.Ten
     return out
 
 
-def cab(shallow: torch.Tensor, shallow_pool: torch.Tensor, deep_pool: torch.Tensor, deeper: torch.Tensor, w1, b1, w2, b2):
+def cab(shallow: torch.Tensor, shallow_pool: torch.Tensor, deep_pool: torch.Tensor, deeper: torch.Tensor, w1, b1, w2, b2,
+        out_split: bool = False):
     """gate from pooled vectors, then shallow*gate + deeper (a map of the same shape, a lower-resolution map that is resized
     bilinearly on the fly, or a (B,C) vector)."""
     B, H, W, C = shallow.shape
     gate = torch.empty((B, C), device=shallow.device, dtype=torch.float32)
     lib().cab_gate(ptr(shallow_pool), ptr(deep_pool), ptr(w1), ptr(b1), ptr(w2), ptr(b2), B, C, ptr(gate), stream())
-    out = torch.empty_like(shallow)
     if deeper.dim() == 4 and tuple(deeper.shape[1:3]) != (H, W):
-        # deeper level at its own resolution: resized bilinearly inside the kernel (no full-size intermediate)
+        # deeper level at its own resolution: resized bilinearly inside the kernel (no full-size intermediate); with
+        # ``out_split`` the result leaves as the split planes the next tensor-core conv reads (no fp32 round trip)
         assert deeper.shape[0] == B and deeper.shape[3] == C and deeper.is_contiguous()
+        if out_split:
+            sp = Split(torch.empty((B, H, W, C), device=shallow.device, dtype=torch.float16),
+                       torch.empty((B, H, W, C), device=shallow.device, dtype=torch.float16), C)
+            lib().cab_apply_resized_nhwc(ptr(shallow), ptr(gate), ptr(deeper), B, H, W, C, deeper.shape[1], deeper.shape[2], None,
+                                         ptr(sp.hi), ptr(sp.lo), stream())
+            return sp
+        out = torch.empty_like(shallow)
         lib().cab_apply_resized_nhwc(ptr(shallow), ptr(gate), ptr(deeper), B, H, W, C, deeper.shape[1], deeper.shape[2], ptr(out),
-                                     stream())
+                                     None, None, stream())
         return out
+    out = torch.empty_like(shallow)
     lib().cab_apply_nhwc(ptr(shallow), ptr(gate), ptr(deeper), 1 if deeper.dim() == 2 else 0, B, H * W, C, ptr(out), stream())
-    return out
+    return split_f16(out) if out_split else out
 
 
 def scatter_channel(src: torch.Tensor, dst: torch.Tensor, coff: int, nzero: int):

@@ -153,9 +153,10 @@ int frtm_cab_gate(const float *shallow_pool, const float *deep_pool, const float
 int frtm_cab_apply_nhwc(const float *shallow, const float *gate, const float *deeper, int deeper_is_vector, int B,
                         int HW, int C, float *out, void *stream);
 /* The same with the deeper level still at its own resolution (B,Hd,Wd,C): the bilinear resize (align_corners=False) to
- * (H,W) is evaluated inside the kernel, with frtm_resize_bilinear_nhwc's arithmetic. */
+ * (H,W) is evaluated inside the kernel, with frtm_resize_bilinear_nhwc's arithmetic.  out (fp32 NHWC) and / or the split
+ * planes y_hi, y_lo (B,H,W,C halves, frtm_split_f16's conversion) for the tensor-core conv that follows. */
 int frtm_cab_apply_resized_nhwc(const float *shallow, const float *gate, const float *deeper, int B, int H, int W, int C, int Hd,
-                                int Wd, float *out, void *stream);
+                                int Wd, float *out, void *y_hi, void *y_lo, void *stream);
 
 /* Copy a 1-channel map (B,H,W) into channel `coff` of an NHWC tensor with channel stride ld and zero channels
  * (coff, coff+nzero] (builds cat(h, score), lib/utils.py:38-41 / seg_network.py:19). */
