@@ -103,6 +103,12 @@ class Tracker(nn.Module):
         # that depends on the first frame and its ground truth only — both known before the sequence starts.
         self._prefetched = {}
         self.prefetch_next = os.environ.get("FRTM_PREFETCH_INIT", "1") == "1"
+        # ``Memory.labels`` / ``Memory.pixel_weights`` (cap,1,H,W) mirror the reference's buffers (model/memory.py:20-21),
+        # but nothing on this path reads them after the insert: the optimiser works on the stencil / U^T w^2 y built from
+        # them at insert time.  The block inserts therefore skip the two full-resolution copies (84 % of an insert's bytes)
+        # unless somebody wants the mirrors kept up to date: ``store_fullres_memory = True`` (or
+        # FRTM_STORE_FULLRES_MEMORY=1).  The first-frame samples and the frame-by-frame path always store them.
+        self.store_fullres_memory = os.environ.get("FRTM_STORE_FULLRES_MEMORY", "0") == "1"
         self.graph_captures = 0     # how many times a block graph was captured (tests / diagnostics)
 
     def _drain_prefetch(self):
@@ -746,11 +752,12 @@ class Tracker(nn.Module):
         n = len(live)
         mems = [t.discriminator.memory for t in live]
         m0, d0 = mems[0], live[0].discriminator
-        key = tuple((m.samples.data_ptr(), m.labels.data_ptr(), m.pixel_weights.data_ptr(), m.state.data_ptr()) for m in mems)
+        full = bool(self.store_fullres_memory)
+        key = (full,) + tuple((m.samples.data_ptr(), m.labels.data_ptr(), m.pixel_weights.data_ptr(), m.state.data_ptr()) for m in mems)
         tab = getattr(self, "_ins_table", None)
         if tab is None or tab[0] != key:
-            rows = [[m.samples.data_ptr() for m in mems], [m.labels.data_ptr() for m in mems],
-                    [m.pixel_weights.data_ptr() for m in mems], [m.stencil.data_ptr() for m in mems],
+            rows = [[m.samples.data_ptr() for m in mems], [m.labels.data_ptr() if full else 0 for m in mems],
+                    [m.pixel_weights.data_ptr() if full else 0 for m in mems], [m.stencil.data_ptr() for m in mems],
                     [m.uty.data_ptr() for m in mems], [m.split.data_ptr() if m._split_ok else 0 for m in mems],
                     [m.weights.data_ptr() for m in mems], [m.state.data_ptr() for m in mems]]
             flat = [v for r in rows for v in r]

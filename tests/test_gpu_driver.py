@@ -255,3 +255,34 @@ def test_prefetched_initialisation_gives_identical_sequences():
     for a, b in zip(ref_b[1] + ref_b[2], got):
         assert torch.equal(a, b)
 
+
+def test_block_inserts_may_skip_the_fullres_mirrors():
+    """``Tracker.store_fullres_memory``: with it the block inserts keep ``Memory.labels`` / ``Memory.pixel_weights`` up to date
+    (reference buffers, model/memory.py:20-21); without it (default) those two copies are skipped.  Nothing on the path reads
+    them, so labels, filters, samples, stencils and sample weights are identical either way."""
+    from frtm_vos_b200 import synth
+    seq = synth.SyntheticSequence(num_objects=2, num_frames=18, size=SIZE, seq_id=51)
+    res = {}
+    for full in (False, True):
+        trk, _, _ = _tracker(n_frames=2)
+        trk.store_fullres_memory = full
+        torch.manual_seed(13)
+        outs, _ = trk.run_sequence(seq)
+        mems = [trk.targets[o].discriminator.memory for o in seq.obj_ids]
+        res[full] = ([o.cpu() for o in outs], [trk.targets[o].discriminator.filter.weight.detach().clone() for o in seq.obj_ids],
+                     [(m.samples.clone(), m.stencil.clone(), m.uty.clone(), m.weights.clone(), m.split.clone()) for m in mems],
+                     [(m.labels.clone(), m.pixel_weights.clone(), int(m.state[0])) for m in mems])
+    for a, b in zip(res[False][0], res[True][0]):
+        assert torch.equal(a, b)
+    for a, b in zip(res[False][1], res[True][1]):
+        assert torch.equal(a, b)
+    for ma, mb in zip(res[False][2], res[True][2]):
+        for a, b in zip(ma, mb):
+            assert torch.equal(a, b)
+    for (la, pa, na), (lb, pb, nb) in zip(res[False][3], res[True][3]):
+        assert na == nb and na > 5                                  # the block inserts happened
+        assert torch.equal(la[:5], lb[:5]) and torch.equal(pa[:5], pb[:5])      # first-frame samples: always stored
+        filled = lambda x: int((x[5:na].flatten(1).abs().sum(1) > 0).sum())
+        assert filled(lb) == na - 5 and filled(pb) == na - 5        # every inserted sample mirrored
+        assert filled(la) <= 1 and filled(pa) <= 1                  # block inserts skipped (the 17th frame runs frame by frame)
+
