@@ -63,7 +63,8 @@ __global__ void __launch_bounds__(256) stem_patches_kernel(const uint8_t *__rest
 
 // ---------------------------------------------------------------- max pool -------------------------------------
 __global__ void maxpool_kernel(const float *__restrict__ x, int B, int H, int W, int C, int Ho, int Wo,
-                               float *__restrict__ y, float *__restrict__ y_nchw) {
+                               float *__restrict__ y, float *__restrict__ y_nchw, __half *__restrict__ y_hi = nullptr,
+                               __half *__restrict__ y_lo = nullptr) {
   const int C4 = C / 4;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t total = (int64_t)B * Ho * Wo * C4;
@@ -85,7 +86,18 @@ __global__ void maxpool_kernel(const float *__restrict__ x, int B, int H, int W,
       m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
     }
   }
-  *reinterpret_cast<float4 *>(y + (((int64_t)b * Ho + oy) * Wo + ox) * C + c4 * 4) = m;
+  if (y) *reinterpret_cast<float4 *>(y + (((int64_t)b * Ho + oy) * Wo + ox) * C + c4 * 4) = m;
+  if (y_hi) {   // split planes of 16*x for the tensor-core conv that follows (split_kernel's conversion)
+    const float v[4] = {m.x * 16.f, m.y * 16.f, m.z * 16.f, m.w * 16.f};
+    __half h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      h[k] = __float2half_rn(v[k]);
+      l[k] = __float2half_rn(v[k] - __half2float(h[k]));
+    }
+    *reinterpret_cast<uint2 *>(y_hi + i * 4) = *reinterpret_cast<const uint2 *>(h);
+    *reinterpret_cast<uint2 *>(y_lo + i * 4) = *reinterpret_cast<const uint2 *>(l);
+  }
   if (y_nchw) {
     const int64_t hw = (int64_t)Ho * Wo, pix = (int64_t)oy * Wo + ox;
     float *d = y_nchw + ((int64_t)b * C + c4 * 4) * hw + pix;
@@ -889,6 +901,16 @@ extern "C" int frtm_maxpool3x3s2_nhwc(const float *x, int B, int H, int W, int C
   const int64_t total = (int64_t)B * Ho * Wo * (C / 4);
   maxpool_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, C, Ho, Wo, y, y_nchw);
   FRTM_CHECK_LAUNCH("maxpool3x3s2");
+  return FRTM_OK;
+}
+
+extern "C" int frtm_maxpool3x3s2_split_nhwc(const float *x, int B, int H, int W, int C, float *y, void *y_hi, void *y_lo,
+                                            void *stream) {
+  FRTM_REQUIRE(x && y_hi && y_lo && C % 4 == 0, "maxpool_split: bad arguments");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const int64_t total = (int64_t)B * Ho * Wo * (C / 4);
+  maxpool_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, C, Ho, Wo, y, nullptr, (__half *)y_hi, (__half *)y_lo);
+  FRTM_CHECK_LAUNCH("maxpool3x3s2_split");
   return FRTM_OK;
 }
 

@@ -99,11 +99,11 @@ class ResnetFeatureExtractor:
         x = ops.stem_conv(images, w["stem"])            # 7x7/s2 stem + bn1 + relu: patches built in shared memory
         if "layer1" in nchw_layers:
             x, nchw["layer1"] = ops.maxpool3x3s2(x, nchw=True)
-        else:
-            x = ops.maxpool3x3s2(x)
+            xs = ops.split_f16(x)
+        else:                                           # the pooling writes the split planes the first block reads
+            xs, x = ops.maxpool3x3s2_split(x, want_f32="layer1" in f32_layers)
         if "layer1" in f32_layers:
             f32["layer1"] = x
-        xs = ops.split_f16(x)
         split["layer1"] = xs
         last = int(upto[-1])
         for si, nblk in enumerate(self.depth):

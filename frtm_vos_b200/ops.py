@@ -98,6 +98,17 @@ def maxpool3x3s2(x: torch.Tensor, nchw: bool = False):
     return (y, y_nchw) if nchw else y
 
 
+def maxpool3x3s2_split(x: torch.Tensor, want_f32: bool = False):
+    """3x3/s2/p1 max pooling straight into split planes; returns (Split, fp32 y or None)."""
+    B, H, W, C = x.shape
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    y = torch.empty((B, Ho, Wo, C), device=x.device, dtype=torch.float32) if want_f32 else None
+    sp = Split(torch.empty((B, Ho, Wo, C), device=x.device, dtype=torch.float16),
+               torch.empty((B, Ho, Wo, C), device=x.device, dtype=torch.float16), C)
+    lib().maxpool3x3s2_split_nhwc(ptr(x), B, H, W, C, ptr(y), ptr(sp.hi), ptr(sp.lo), stream())
+    return sp, y
+
+
 def resize_bilinear(x: torch.Tensor, size, channels: Optional[int] = None, out: Optional[torch.Tensor] = None,
                     coff: int = 0, accumulate: bool = False) -> torch.Tensor:
     B, H, W, ldx = x.shape

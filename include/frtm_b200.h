@@ -125,6 +125,9 @@ int frtm_stem_patches_u8(const uint8_t *img, int B, int H, int W, void *hi, void
 int frtm_stem_conv_u8(const uint8_t *img, int B, int H, int W, const void *wt, const float *oscale, const float *bias, float *y,
                       int ldy, int relu, void *stream);
 int frtm_maxpool3x3s2_nhwc(const float *x, int B, int H, int W, int C, float *y, float *y_nchw, void *stream);
+/* The same pooling writing the split fp16 planes (B,Ho,Wo,C) of 16*y that the next tensor-core conv reads (frtm_split_f16's
+ * conversion); y (fp32) optional. */
+int frtm_maxpool3x3s2_split_nhwc(const float *x, int B, int H, int W, int C, float *y, void *y_hi, void *y_lo, void *stream);
 
 /* Bilinear resize (align_corners=False) of an NHWC tensor; writes C channels at offset y_coff of a tensor with
  * channel stride ldy.  If accumulate != 0 the result is added to y.  (lib/utils.py:33-35, seg_network.py:39,144) */
