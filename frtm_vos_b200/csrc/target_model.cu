@@ -1084,8 +1084,8 @@ extern "C" int frtm_memory_insert(const float *feat, int feat_elems, const float
 
 extern "C" int frtm_memory_insert_block(const void *table, int n_obj, int n_frames, int capacity, float lr, const int *gate_counts,
                                         int min_px, const float *feat, int feat_elems, const float *labels, const float *pw,
-                                        int HW, const float *stencil, const float *uty, int hw, int with_split, int *slots,
-                                        void *stream) {
+                                        int HW, const float *stencil, const float *uty, int hw, int with_split, int with_fullres,
+                                        int *slots, void *stream) {
   FRTM_REQUIRE(table && gate_counts && feat && labels && pw && stencil && uty && slots, "memory_insert_block: null pointer");
   FRTM_REQUIRE(n_obj >= 1 && n_frames >= 1 && n_obj * n_frames <= 65535 && capacity >= 1, "memory_insert_block: bad sizes");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1094,7 +1094,8 @@ extern "C" int frtm_memory_insert_block(const void *table, int n_obj, int n_fram
   MemBlockArgs a;
   a.table = (const long long *)table; a.slots = slots;
   const float *src[5] = {feat, labels, pw, stencil, uty};
-  const int64_t n[5] = {feat_elems, HW, HW, 9 * (int64_t)hw, hw};
+  // without the full-resolution mirrors (labels, pixel weights) the copy grid covers a sixth of the elements
+  const int64_t n[5] = {feat_elems, with_fullres ? HW : 0, with_fullres ? HW : 0, 9 * (int64_t)hw, hw};
   a.total = 0;
   for (int k = 0; k < 5; ++k) { a.src[k] = src[k]; a.n[k] = n[k]; a.total += n[k]; }
   a.n_obj = n_obj; a.nF = n_frames; a.hw = hw; a.c = 0; a.split_items = 0;

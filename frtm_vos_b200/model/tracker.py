@@ -775,7 +775,7 @@ class Tracker(nn.Module):
         HW = m0.labels.shape[-1] * m0.labels.shape[-2]
         lib().memory_insert_block(ptr(table), n, nF, m0.capacity, float(m0.learning_rates), ptr(cblk), int(d0.min_px),
                                   ptr(samples), samples[0].numel(), ptr(ys_all), ptr(pw_all), HW, ptr(st_all), ptr(uty_all), hw,
-                                  1 if m0._split_ok else 0, ptr(slots), stream())
+                                  1 if m0._split_ok else 0, 1 if self.store_fullres_memory else 0, ptr(slots), stream())
 
     def _batched_gn_update(self, live, due):
         """One set of launches for the filter updates of all objects that are due on this frame (grid.y = object)."""

@@ -251,10 +251,12 @@ int frtm_memory_insert(const float *feat, int feat_elems, const float *label, co
  * gate_counts[f * n_obj + o] >= min_px) and ONE copy launch for all samples (frtm_memory_insert's).  Row (f, o) of feat
  * (feat_elems floats), labels / pw (HW), stencil (9 hw), uty (hw) is row f * n_obj + o.  table = device int64[8][n_obj]:
  * per object the addresses of samples, labels, pixel_weights, stencil, uty, operator images (0 = none), sample weights,
- * policy state (model/memory.py:59-92 applied n_frames times).  slots = int[n_frames * n_obj] workspace (out: the slots). */
+ * policy state (model/memory.py:59-92 applied n_frames times).  with_fullres = 0: the labels / pixel_weights mirrors are
+ * not written.  slots = int[n_frames * n_obj] workspace (out: the slots). */
 int frtm_memory_insert_block(const void *table, int n_obj, int n_frames, int capacity, float lr, const int *gate_counts,
                              int min_px, const float *feat, int feat_elems, const float *labels, const float *pw, int HW,
-                             const float *stencil, const float *uty, int hw, int with_split, int *slots, void *stream);
+                             const float *stencil, const float *uty, int hw, int with_split, int with_fullres, int *slots,
+                             void *stream);
 
 /* Operator images of n memory samples for the tensor-core GN/CG operator kernel.  Per sample:
  *   [ntiles][hi|lo][c][64 pixels] fp16 with 16*x = hi + lo, rows in the 128-byte swizzled shared-memory layout, pixels

@@ -379,7 +379,7 @@ def test_memory_insert_block_equals_sequential_inserts():
     table = torch.tensor([v for r in rows for v in r], dtype=torch.int64).to(DEV)
     slots = torch.empty(nF * n, dtype=torch.int32, device=DEV)
     lib().memory_insert_block(ptr(table), n, nF, cap, 0.1, ptr(counts), 10, ptr(feats), feats[0].numel(), ptr(ys), ptr(pw), H * W,
-                              ptr(st), ptr(uty), h * w, 1, ptr(slots), stream())
+                              ptr(st), ptr(uty), h * w, 1, 1, ptr(slots), stream())
     assert slots.cpu().tolist() == slots_seq
     used = [s for s in slots_seq[0::n] if s >= 0]
     assert slots_seq[2 * n + 0] == -1 and slots_seq[5 * n + 1] == -1
