@@ -60,6 +60,9 @@ __device__ __forceinline__ void gm_sample(const GaArgs &a, const GcParams &P, in
   constexpr int n = C * 9;
   const int hw = h * w, lag = w + 1;
   const int tid = threadIdx.x, lane = tid & 31, wp = uniform_warp_idx();
+#ifdef GM_TIMING
+  const long long t_entry = clock64();
+#endif
   const int nblocks = P.ntiles >> 1;
   const int fb = max(pb0 - 2, 0), lb = min(pb1 + 2, nblocks);          // P1 blocks [fb, lb)
   const uint32_t tile_bytes = (uint32_t)P.tile_bytes, blk_bytes = 2u * tile_bytes;
@@ -183,6 +186,7 @@ __device__ __forceinline__ void gm_sample(const GaArgs &a, const GcParams &P, in
 
 #ifdef GM_TIMING
   long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
+  const long long t_loop = tlast;
 #endif
   // scores are needed two rows beyond the unit's P3 pixels, residuals one row beyond
   const int s_end = min(GM_BLK * pb1 + 2 * lag, hw), v_end = min(GM_BLK * pb1 + lag, hw);
@@ -369,6 +373,9 @@ __device__ __forceinline__ void gm_sample(const GaArgs &a, const GcParams &P, in
   if (nacc) fold();
 
 #ifdef GM_TIMING
+  const long long t_end = clock64();
+  if (tid == 0 && blockIdx.x == 0)
+    printf("gm prologue %lld | loop %lld clocks\n", t_loop - t_entry, t_end - t_loop);
   if (tid == 0 && blockIdx.x == 0)
     printf("gm timeline (clocks, %d steps): stencil-issue %lld | wait-load %lld | P1 %lld | bar %lld | scores %lld | bar %lld | residual %lld | bar %lld "
            "| P3 %lld | bar %lld\n", nblocks + 2, tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], tacc[5], tacc[6], tacc[7], tacc[8], tacc[9]);
@@ -421,6 +428,10 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gn_apply_mma_kernel(const GaArg
   const int n_whole = k > 1 ? U - R : U;
   const int units = n_whole + (U - n_whole) * k;
   const int b = blockIdx.x;
+#ifdef GM_TIMING
+  unsigned long long g0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
+#endif
   if (b >= units) return;
   const int item_idx = b < n_whole ? b : n_whole + (b - n_whole) / k;
   const int part_idx = b < n_whole ? 0 : (b - n_whole) % k, parts = b < n_whole ? 1 : k;
@@ -428,6 +439,13 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gn_apply_mma_kernel(const GaArg
   const int o = (int)(item >> 16), slot = (int)(item & 0xffffu);
   float *row = Q.ws.rows + (int64_t)b * n;
   gm_sample<GM_MAXC>(a, P, o, slot, part_idx * nblocks / parts, (part_idx + 1) * nblocks / parts, row);
+#ifdef GM_TIMING
+  if (threadIdx.x == 0 && (b == 0 || b == 100 || b == 147 || b == 148 || b == 200 || b == units - 1)) {
+    unsigned long long g1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+    printf("gm cta %d of %d units: start %llu end %llu (ns mod 1e6) = %llu ns\n", b, units, g0 % 1000000ull, g1 % 1000000ull, g1 - g0);
+  }
+#endif
   if (!F.enabled) return;
 
   // ---- reduction + CG vector step in the tail of the launch (as gc_fused_tail, over the object's unit rows) ----
