@@ -626,17 +626,47 @@ __global__ void __launch_bounds__(256) shift_sum9_kernel(const float *__restrict
 // ---------------------------------------------------------------- fused tail of the upsampler --------------------
 // out[b][Y][X] = bias + sum_tap R_tap[Y+dy][X+dx]  (zero outside the image = the final conv's zero padding), where
 // R_tap = bilinear_(H,W)( pyrup_bicubic( t_tap ) ) and t (B,h,w,12) are the 9 tap maps of the final 3x3 conv contracted at
-// low resolution (seg_network.py:139-145 by linearity).  One block = a 16x64 output tile: the tap maps of the tile
-// (with halo) are staged once, then per tap the bicubic x2 runs separably in shared memory (rows, then columns) and the
-// bilinear + shifted sum accumulate in registers — nothing but t is read and nothing but the logits are written.
+// low resolution (seg_network.py:139-145 by linearity).  Along each axis bilinear o bicubic-x2 is ONE 5-tap window on the
+// low-resolution samples (the two upsampled neighbours of a bilinear source position share or straddle one 4-tap bicubic
+// window), with weights that depend on the destination index and the tap shift only.  One block = a 16x64 output tile:
+// the tap maps of the tile (with halo) are staged once, a row pass applies the x windows of the three column shifts
+// (every thread keeps the windows of its own column in registers), a column pass the y windows of the three row shifts
+// (from a small table) — three block barriers per tile, nothing but t is read and nothing but the logits are written.
 constexpr int FT_TY = 16, FT_TX = 64, FT_UY = 24, FT_UX = 76, FT_NTY = 16, FT_NTX = 42;
+constexpr int FT_SMEM = (9 * FT_NTY * (FT_NTX + 1) + 9 * FT_NTY * FT_TX + 3 * FT_TY * 8) * 4;
+
+// 5-tap window of bilinear(pyrup_bicubic(.)) at destination index d (already clamped to the image; ok = false -> zero
+// weights): samples lo + base .. lo + base + 4 of the low-resolution axis.
+__device__ __forceinline__ void fused_axis_window(int d, bool ok, float scale, int up_size, int lo, int &base, float (&a)[5]) {
+  int u0, u1;
+  float lam;
+  bilinear_src(d, scale, up_size, u0, u1, lam);
+  // upsampled (cropped) index u = pre-crop u + 1 = 2n (+1): window n-2 .. n+1, even -> kCubicE, odd -> reversed
+  const int n0 = (u0 + 1) >> 1, n1 = (u1 + 1) >> 1;
+  const bool odd0 = (u0 + 1) & 1, odd1 = (u1 + 1) & 1;
+  const float w0 = ok ? 1.f - lam : 0.f, w1 = ok ? lam : 0.f;
+  float c0[4], c1[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    c0[k] = w0 * (odd0 ? kCubicE[3 - k] : kCubicE[k]);
+    c1[k] = w1 * (odd1 ? kCubicE[3 - k] : kCubicE[k]);
+  }
+  const bool same = n1 == n0;                               // else n1 = n0 + 1
+  a[0] = c0[0] + (same ? c1[0] : 0.f);
+  a[1] = c0[1] + (same ? c1[1] : c1[0]);
+  a[2] = c0[2] + (same ? c1[2] : c1[1]);
+  a[3] = c0[3] + (same ? c1[3] : c1[2]);
+  a[4] = same ? 0.f : c1[3];
+  base = n0 - 2 - lo;
+}
 
 __global__ void __launch_bounds__(256) upsample_tapsum_kernel(const float *__restrict__ t12, int B, int h, int w, int H,
                                                               int W, const float *__restrict__ bias,
                                                               float *__restrict__ out) {
-  __shared__ float T[9][FT_NTY][FT_NTX + 1];
-  __shared__ float H1[FT_NTY][FT_UX + 1];
-  __shared__ float U[FT_UY][FT_UX + 1];
+  extern __shared__ __align__(16) float ft_smem[];
+  float (*T)[FT_NTY][FT_NTX + 1] = reinterpret_cast<float (*)[FT_NTY][FT_NTX + 1]>(ft_smem);                 // [9]
+  float (*R)[FT_NTY][FT_TX] = reinterpret_cast<float (*)[FT_NTY][FT_TX]>(ft_smem + 9 * FT_NTY * (FT_NTX + 1));   // [9]
+  float *WY = ft_smem + 9 * FT_NTY * (FT_NTX + 1) + 9 * FT_NTY * FT_TX;   // [3][FT_TY][8]: a[0..4], base (int bits)
   const int Hu = 2 * h, Wu = 2 * w;
   const float sy = (float)Hu / (float)H, sx = (float)Wu / (float)W;
   const int b = blockIdx.z, Y0 = blockIdx.y * FT_TY, X0 = blockIdx.x * FT_TX;
@@ -654,7 +684,7 @@ __global__ void __launch_bounds__(256) upsample_tapsum_kernel(const float *__res
   const int nux = i1 - ux_lo + 1;
   const int ty_lo = ((uy_lo + 1) >> 1) - 2, nty = ((uy_lo + nuy) >> 1) + 1 - ty_lo + 1;
   const int tx_lo = ((ux_lo + 1) >> 1) - 2, ntx = ((ux_lo + nux) >> 1) + 1 - tx_lo + 1;
-  // (the host checks nuy <= FT_UY, nux <= FT_UX, nty <= FT_NTY, ntx <= FT_NTX for the given sizes)
+  // (the host checks nty <= FT_NTY, ntx <= FT_NTX for the given sizes)
   for (int i = tid; i < nty * ntx; i += 256) {
     const int ry = i / ntx, rx = i - ry * ntx;
     const int sy_ = min(max(ty_lo + ry, 0), h - 1), sx_ = min(max(tx_lo + rx, 0), w - 1);   // replicate padding
@@ -664,91 +694,58 @@ __global__ void __launch_bounds__(256) upsample_tapsum_kernel(const float *__res
     T[4][ry][rx] = a1.x; T[5][ry][rx] = a1.y; T[6][ry][rx] = a1.z; T[7][ry][rx] = a1.w;
     T[8][ry][rx] = a2.x;
   }
-  // own output pixels: rows tid/64 + 4k, column tid%64.  The bilinear source indices / weights of the three horizontal
-  // and twelve vertical tap-shifted positions do not depend on the tap map: computed once, relative to the U window.
+  // own output pixels: rows tid/64 + 4k, column tid%64
   const int lx = tid & 63, ly = tid >> 6;
-  int bx0[3], bx1[3];
-  float blx[3];
-  bool okx[3];
+  if (tid < 3 * FT_TY) {                                    // y windows of the tile's rows under the three row shifts
+    const int d = tid / FT_TY, r = tid - d * FT_TY;
+    const int Ys = Y0 + r + d - 1;
+    int base;
+    float a[5];
+    fused_axis_window(min(max(Ys, 0), H - 1), Ys >= 0 && Ys < H && Y0 + r < H, sy, Hu, ty_lo, base, a);
+    float *dst = WY + tid * 8;
+    dst[0] = a[0]; dst[1] = a[1]; dst[2] = a[2]; dst[3] = a[3]; dst[4] = a[4];
+    dst[5] = __int_as_float(base);
+  }
+  int bx[3], bx4[3];
+  float ax[3][5];
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     const int Xs = X0 + lx + d - 1;
-    okx[d] = Xs >= 0 && Xs < W && X0 + lx < W;
-    bilinear_src(min(max(Xs, 0), W - 1), sx, Wu, bx0[d], bx1[d], blx[d]);
-    bx0[d] -= ux_lo; bx1[d] -= ux_lo;
+    fused_axis_window(min(max(Xs, 0), W - 1), Xs >= 0 && Xs < W && X0 + lx < W, sx, Wu, tx_lo, bx[d], ax[d]);
+    bx4[d] = min(bx[d] + 4, ntx - 1);                        // (its weight is zero whenever the clamp acts)
   }
-  int by0[3][4], by1[3][4];
-  float bly[3][4];
-  bool oky[3][4];
-#pragma unroll
-  for (int d = 0; d < 3; ++d)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int Ys = Y0 + ly + 4 * k + d - 1;
-      oky[d][k] = Ys >= 0 && Ys < H;
-      bilinear_src(min(max(Ys, 0), H - 1), sy, Hu, by0[d][k], by1[d][k], bly[d][k]);
-      by0[d][k] -= uy_lo; by1[d][k] -= uy_lo;
-    }
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  // window geometry of the two bicubic passes: one item = one low-resolution sample position and the even / odd pair of
-  // upsampled positions (pre-crop indices 2n, 2n+1) that share its 4-tap window
-  const int n_lo = (ux_lo + 1) >> 1, n_cnt = ((ux_lo + nux) >> 1) - n_lo + 1;
-  const int m_lo = (uy_lo + 1) >> 1, m_cnt = ((uy_lo + nuy) >> 1) - m_lo + 1;
   __syncthreads();
+  // row pass: R[tap][ry][X] = x window of the tap's column shift applied to the tap map's row ry
+  for (int ry = ly; ry < nty; ry += 4) {
 #pragma unroll
-  for (int tap = 0; tap < 9; ++tap) {
-    // bicubic x2 along x: H1[ry][ux] = sum_kx wx[kx] T[ry][n - 2 + kx],  upsampled column (cropped index) = 2n + rx - 1
-    for (int i = tid; i < nty * FT_NTX; i += 256) {
-      const int ry = i / FT_NTX, nn = i - ry * FT_NTX;
-      if (nn < n_cnt) {
-        const int n = n_lo + nn;
-        const float *row = &T[tap][ry][n - 2 - tx_lo];
-        const float r0 = row[0], r1 = row[1], r2 = row[2], r3 = row[3];
-        const int ue = 2 * n - 1 - ux_lo;                    // even pre-crop index 2n -> cropped 2n - 1
-        if (ue >= 0 && ue < nux) H1[ry][ue] = (kCubicE[0] * r0 + kCubicE[1] * r1) + (kCubicE[2] * r2 + kCubicE[3] * r3);
-        if (ue + 1 >= 0 && ue + 1 < nux) H1[ry][ue + 1] = (kCubicE[3] * r0 + kCubicE[2] * r1) + (kCubicE[1] * r2 + kCubicE[0] * r3);
-      }
+    for (int tap = 0; tap < 9; ++tap) {
+      const int dx = tap % 3;
+      const float *row = &T[tap][ry][0];
+      const float *r0 = row + bx[dx];
+      R[tap][ry][lx] = ((ax[dx][0] * r0[0] + ax[dx][1] * r0[1]) + (ax[dx][2] * r0[2] + ax[dx][3] * r0[3])) + ax[dx][4] * row[bx4[dx]];
     }
-    __syncthreads();
-    // ... and along y
-    for (int i = tid; i < m_cnt * FT_UX; i += 256) {
-      const int mm = i / FT_UX, ux = i - mm * FT_UX;
-      if (ux < nux) {
-        const int m = m_lo + mm;
-        const int r0 = m - 2 - ty_lo;
-        const float v0 = H1[r0][ux], v1 = H1[r0 + 1][ux], v2 = H1[r0 + 2][ux], v3 = H1[r0 + 3][ux];
-        const int ue = 2 * m - 1 - uy_lo;
-        if (ue >= 0 && ue < nuy) U[ue][ux] = (kCubicE[0] * v0 + kCubicE[1] * v1) + (kCubicE[2] * v2 + kCubicE[3] * v3);
-        if (ue + 1 >= 0 && ue + 1 < nuy) U[ue + 1][ux] = (kCubicE[3] * v0 + kCubicE[2] * v1) + (kCubicE[1] * v2 + kCubicE[0] * v3);
-      }
-    }
-    __syncthreads();
-    // bilinear to (H, W) at the tap-shifted position, accumulated per output pixel
-    const int dy = tap / 3, dx = tap - dy * 3;
-    if (okx[dx]) {
-      const int x0 = bx0[dx], x1 = bx1[dx];
-      const float lx_ = blx[dx];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (oky[dy][k]) {
-          const int y0 = by0[dy][k], y1 = by1[dy][k];
-          const float ly_ = bly[dy][k];
-          // ATen's order: (1-ly) * ((1-lx) a + lx b) + ly * ((1-lx) c + lx d)
-          const float top = (1.f - lx_) * U[y0][x0] + lx_ * U[y0][x1];
-          const float bot = (1.f - lx_) * U[y1][x0] + lx_ * U[y1][x1];
-          acc[k] += (1.f - ly_) * top + ly_ * bot;
-        }
-      }
-    }
-    __syncthreads();
   }
+  __syncthreads();
+  // column pass: the y window of the tap's row shift over R, summed over the taps
   const float bv = bias ? bias[0] : 0.f;
-  if (X0 + lx < W) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int Y = Y0 + ly + 4 * k;
-      if (Y < H) out[((int64_t)b * H + Y) * W + X0 + lx] = acc[k] + bv;
+  for (int k = 0; k < 4; ++k) {
+    const int Yl = ly + 4 * k;
+    float acc = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const float4 a03 = *reinterpret_cast<const float4 *>(WY + (dy * FT_TY + Yl) * 8);
+      const float2 a4b = *reinterpret_cast<const float2 *>(WY + (dy * FT_TY + Yl) * 8 + 4);
+      const int base = __float_as_int(a4b.y), r4 = min(base + 4, nty - 1);
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const float *col = &R[dy * 3 + dx][0][lx];
+        acc += ((a03.x * col[base * FT_TX] + a03.y * col[(base + 1) * FT_TX]) +
+                (a03.z * col[(base + 2) * FT_TX] + a03.w * col[(base + 3) * FT_TX])) + a4b.x * col[r4 * FT_TX];
+      }
     }
+    const int Y = Y0 + Yl;
+    if (X0 + lx < W && Y < H) out[((int64_t)b * H + Y) * W + X0 + lx] = acc + bv;
   }
 }
 
@@ -1153,7 +1150,13 @@ extern "C" int frtm_upsample_tapsum(const float *t12, int B, int h, int w, int H
                w, H, W);
   FRTM_REQUIRE(B <= 65535, "upsample_tapsum: batch too large");
   const dim3 grid(cdiv(W, FT_TX), cdiv(H, FT_TY), B);
-  upsample_tapsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(t12, B, h, w, H, W, bias, out);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(upsample_tapsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM);
+    if (e != cudaSuccess) { set_error("upsample_tapsum: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return FRTM_ELAUNCH; }
+    attr_set = true;
+  }
+  upsample_tapsum_kernel<<<grid, 256, FT_SMEM, (cudaStream_t)stream>>>(t12, B, h, w, H, W, bias, out);
   FRTM_CHECK_LAUNCH("upsample_tapsum");
   return FRTM_OK;
 }
