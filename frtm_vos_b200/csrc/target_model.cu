@@ -622,24 +622,39 @@ __global__ void __launch_bounds__(256) build_stencil_kernel(const float *__restr
       for (int d = 0; d < 3; ++d) cx[d] = cxc * tent(j + d - 1, x0, x1, lx);
     }
     if (__ballot_sync(0xffffffffu, cxc != 0.f) == 0u) continue;
-    for (int Y = Y0; Y <= Y1; ++Y) {
-      int y0, y1;
-      float ly;
-      bilinear_src(Y, sh, h, y0, y1, ly);
-      const float cyc = tent(i, y0, y1, ly);
-      if (cyc == 0.f) continue;                            // warp-uniform
-      float cy[3];
+    // rows in batches of BS_ROWS with all their loads in flight (one load pair per row and trip made the warp a chain of
+    // ~40 memory round trips); the accumulation order over Y is unchanged
+    constexpr int BS_ROWS = 8;
+    for (int Yb = Y0; Yb <= Y1; Yb += BS_ROWS) {
+      float pv[BS_ROWS], yv[BS_ROWS];
 #pragma unroll
-      for (int d = 0; d < 3; ++d) cy[d] = cyc * tent(i + d - 1, y0, y1, ly);
-      if (cxc != 0.f) {
-        const float p = pwk[(int64_t)Y * W + X];
-        const float p2 = p * p;
-        accy = fmaf(p2 * (cyc * cxc), yk[(int64_t)Y * W + X], accy);
+      for (int u = 0; u < BS_ROWS; ++u) {
+        const bool in = Yb + u <= Y1 && cxc != 0.f;
+        pv[u] = in ? __ldg(pwk + (int64_t)(Yb + u) * W + X) : 0.f;
+        yv[u] = in ? __ldg(yk + (int64_t)(Yb + u) * W + X) : 0.f;
+      }
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {
-          const float r = p2 * cy[dy];
+      for (int u = 0; u < BS_ROWS; ++u) {
+        const int Y = Yb + u;
+        if (Y > Y1) break;                                   // warp-uniform
+        int y0, y1;
+        float ly;
+        bilinear_src(Y, sh, h, y0, y1, ly);
+        const float cyc = tent(i, y0, y1, ly);
+        if (cyc == 0.f) continue;                            // warp-uniform
+        float cy[3];
 #pragma unroll
-          for (int dx = 0; dx < 3; ++dx) acc[dy * 3 + dx] = fmaf(r, cx[dx], acc[dy * 3 + dx]);
+        for (int d = 0; d < 3; ++d) cy[d] = cyc * tent(i + d - 1, y0, y1, ly);
+        if (cxc != 0.f) {
+          const float p = pv[u];
+          const float p2 = p * p;
+          accy = fmaf(p2 * (cyc * cxc), yv[u], accy);
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+            const float r = p2 * cy[dy];
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) acc[dy * 3 + dx] = fmaf(r, cx[dx], acc[dy * 3 + dx]);
+          }
         }
       }
     }
