@@ -87,22 +87,78 @@ def workload_config(cfg, dp, world, cores, wait_policy):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region: NVML polled every 20 ms from a thread (the counters
+    nvidia-smi prints), or — when pynvml cannot open the device — an `nvidia-smi -lms` child process."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.nvml, self.samples, self.max_mhz = None, [], None
+        self._halt = threading.Event()
+
+    def _start_nvml(self):
+        import pynvml as N
+        N.nvmlInit()
+        h = None
+        try:                                               # CUDA_VISIBLE_DEVICES may renumber: look the device up by UUID
+            uuid = "GPU-" + str(torch.cuda.get_device_properties(self.index).uuid)
+            for u in (uuid, uuid.encode()):
+                try:
+                    h = N.nvmlDeviceGetHandleByUUID(u)
+                    break
+                except Exception:
+                    h = None
+        except Exception:
+            h = None
+        if h is None:
+            h = N.nvmlDeviceGetHandleByIndex(self.index)
+
+        def reasons():
+            try:
+                return int(N.nvmlDeviceGetCurrentClocksEventReasons(h))
+            except Exception:
+                return int(N.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+
+        self.max_mhz = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+        N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)       # probes: fail here, not in the thread
+        reasons()
+
+        def loop():
+            while not self._halt.is_set():
+                try:
+                    self.samples.append((float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)), reasons()))
+                except Exception:
+                    pass
+                self._halt.wait(0.02)
+
+        self.nvml = threading.Thread(target=loop, daemon=True)
+        self.nvml.start()
 
     def start(self):
         try:
+            self._start_nvml()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
         except Exception:
             self.proc = None
 
     def stop(self):
+        if self.nvml is not None:
+            self._halt.set()
+            self.nvml.join(timeout=1.0)
+            sm = sorted(v for v, _ in self.samples)
+            bits = 0
+            for _, r in self.samples:
+                bits |= r
+            return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=self.max_mhz,
+                        reasons=[n for b, n in self.BITS if bits & b], samples=len(sm), source="nvml")
         if self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
         self.proc.terminate()
@@ -120,7 +176,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         sm.sort()
-        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm),
+                    source="nvidia-smi")
 
 
 # ------------------------------------------------------------------------------------------------------------------

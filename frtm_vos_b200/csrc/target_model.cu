@@ -633,18 +633,25 @@ __global__ void __launch_bounds__(256) build_stencil_kernel(const float *__restr
         pv[u] = in ? __ldg(pwk + (int64_t)(Yb + u) * W + X) : 0.f;
         yv[u] = in ? __ldg(yk + (int64_t)(Yb + u) * W + X) : 0.f;
       }
+      // the row factors are the same in every lane: lane u computes those of row Yb + u once, the loop broadcasts them
+      float f_cyc, f_cy[3];
+      {
+        int y0, y1;
+        float ly;
+        bilinear_src(min(Yb + (lane & (BS_ROWS - 1)), Y1), sh, h, y0, y1, ly);
+        f_cyc = tent(i, y0, y1, ly);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) f_cy[d] = f_cyc * tent(i + d - 1, y0, y1, ly);
+      }
 #pragma unroll
       for (int u = 0; u < BS_ROWS; ++u) {
         const int Y = Yb + u;
         if (Y > Y1) break;                                   // warp-uniform
-        int y0, y1;
-        float ly;
-        bilinear_src(Y, sh, h, y0, y1, ly);
-        const float cyc = tent(i, y0, y1, ly);
+        const float cyc = __shfl_sync(0xffffffffu, f_cyc, u);
         if (cyc == 0.f) continue;                            // warp-uniform
         float cy[3];
 #pragma unroll
-        for (int d = 0; d < 3; ++d) cy[d] = cyc * tent(i + d - 1, y0, y1, ly);
+        for (int d = 0; d < 3; ++d) cy[d] = __shfl_sync(0xffffffffu, f_cy[d], u);
         if (cxc != 0.f) {
           const float p = pv[u];
           const float p2 = p * p;
