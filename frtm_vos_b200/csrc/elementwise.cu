@@ -312,6 +312,111 @@ __global__ void cab_gate_kernel(const float *__restrict__ sp, const float *__res
   }
 }
 
+// CAB gate straight from the two maps (C = 64): stage 1 of both global average pools in ONE launch, then one block per
+// image that finishes both pools (the arithmetic of gap_stage2_kernel, term for term) and runs the gate on them — two
+// launches instead of five small, latency-bound ones per refinement level.  Bit-identical to the separate kernels.
+__global__ void __launch_bounds__(256) gap_stage1_pair_kernel(const float *__restrict__ xa, int HWa, int lda, int nca,
+                                                              float *__restrict__ parta, const float *__restrict__ xb, int HWb,
+                                                              int ldb, int ncb, float *__restrict__ partb, int C) {
+  __shared__ float red[4][64];
+  const bool second = (int)blockIdx.x >= nca;
+  const float *x = second ? xb : xa;
+  const int HW = second ? HWb : HWa, ldx = second ? ldb : lda, nchunks = second ? ncb : nca;
+  float *part = second ? partb : parta;
+  const int b = blockIdx.y, ch = second ? blockIdx.x - nca : blockIdx.x;
+  const int p0 = ch * GAP_CHUNK, p1 = min(p0 + GAP_CHUNK, HW);
+  const int lane = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  for (int c0 = 0; c0 < C; c0 += 64) {
+    const int c = c0 + lane;
+    float v[GAP_CHUNK / 4];
+    const float *base = x + (int64_t)b * HW * ldx + c;
+#pragma unroll
+    for (int k = 0; k < GAP_CHUNK / 4; ++k) {
+      const int p = p0 + grp + 4 * k;
+      v[k] = (c < C && p < p1) ? base[(int64_t)p * ldx] : 0.f;
+    }
+#pragma unroll
+    for (int w = GAP_CHUNK / 8; w > 0; w >>= 1)
+#pragma unroll
+      for (int k = 0; k < w; ++k) v[k] += v[k + w];
+    red[grp][lane] = v[0];
+    __syncthreads();
+    if (grp == 0 && c < C) part[((int64_t)b * nchunks + ch) * C + c] = (red[0][lane] + red[1][lane]) + (red[2][lane] + red[3][lane]);
+    __syncthreads();
+  }
+}
+
+// pooled[c] of image b from the stage-1 partial sums: gap_stage2_kernel for C = 64 (lane = channel, 4 chunk groups)
+__device__ __forceinline__ void gap_finish64(const float *__restrict__ part, int b, int HW, int nchunks, float (*red)[64],
+                                             float *__restrict__ pooled) {
+  const int lane = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  const float *base = part + (int64_t)b * nchunks * 64 + lane;
+  int k = grp;
+  for (; k + 12 < nchunks; k += 16) {
+    s0 += base[(int64_t)k * 64];
+    s1 += base[(int64_t)(k + 4) * 64];
+    s2 += base[(int64_t)(k + 8) * 64];
+    s3 += base[(int64_t)(k + 12) * 64];
+  }
+  for (; k < nchunks; k += 4) s0 += base[(int64_t)k * 64];
+  red[grp][lane] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (grp == 0) pooled[lane] = ((red[0][lane] + red[1][lane]) + (red[2][lane] + red[3][lane])) / (float)HW;
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) cab_pool_gate64_kernel(const float *__restrict__ parta, int HWa, int nca,
+                                                              const float *__restrict__ partb, int HWb, int ncb,
+                                                              const float *__restrict__ deep_pool, const float *__restrict__ w1,
+                                                              const float *__restrict__ b1, const float *__restrict__ w2,
+                                                              const float *__restrict__ b2, float *__restrict__ gate,
+                                                              float *__restrict__ pool_out) {
+  constexpr int C = 64;
+  __shared__ float red[4][64];
+  __shared__ __align__(16) float pooled[2 * C];
+  __shared__ __align__(16) float hid[C];
+  __shared__ float part[4 * C];
+  const int b = blockIdx.x;
+  gap_finish64(parta, b, HWa, nca, red, pooled);
+  if (partb) gap_finish64(partb, b, HWb, ncb, red, pooled + C);
+  else if (threadIdx.x < C) pooled[C + threadIdx.x] = deep_pool[(int64_t)b * C + threadIdx.x];
+  __syncthreads();
+  if (pool_out && threadIdx.x < 2 * C) pool_out[(int64_t)b * 2 * C + threadIdx.x] = pooled[threadIdx.x];
+  // the gate: cab_gate_kernel at C = 64 (blockDim = 4 C)
+  const int o = threadIdx.x >> 2, q = threadIdx.x & 3;
+  {
+    const int K = 2 * C, kq = K / 4;
+    const float *wr = w1 + (int64_t)o * K + q * kq, *pv = pooled + q * kq;
+    float s0 = 0.f, s1 = 0.f;
+    for (int k = 0; k < kq; k += 8) {
+      const float4 a0 = *reinterpret_cast<const float4 *>(wr + k), a1 = *reinterpret_cast<const float4 *>(wr + k + 4);
+      s0 = fmaf(a0.x, pv[k], s0); s0 = fmaf(a0.y, pv[k + 1], s0); s0 = fmaf(a0.z, pv[k + 2], s0); s0 = fmaf(a0.w, pv[k + 3], s0);
+      s1 = fmaf(a1.x, pv[k + 4], s1); s1 = fmaf(a1.y, pv[k + 5], s1); s1 = fmaf(a1.z, pv[k + 6], s1); s1 = fmaf(a1.w, pv[k + 7], s1);
+    }
+    part[threadIdx.x] = s0 + s1;
+  }
+  __syncthreads();
+  if (q == 0) hid[o] = fmaxf(((part[4 * o] + part[4 * o + 1]) + (part[4 * o + 2] + part[4 * o + 3])) + b1[o], 0.f);
+  __syncthreads();
+  {
+    const int kq = C / 4;
+    const float *wr = w2 + (int64_t)o * C + q * kq, *hv = hid + q * kq;
+    float s0 = 0.f, s1 = 0.f;
+    for (int k = 0; k < kq; k += 8) {
+      const float4 a0 = *reinterpret_cast<const float4 *>(wr + k), a1 = *reinterpret_cast<const float4 *>(wr + k + 4);
+      s0 = fmaf(a0.x, hv[k], s0); s0 = fmaf(a0.y, hv[k + 1], s0); s0 = fmaf(a0.z, hv[k + 2], s0); s0 = fmaf(a0.w, hv[k + 3], s0);
+      s1 = fmaf(a1.x, hv[k + 4], s1); s1 = fmaf(a1.y, hv[k + 5], s1); s1 = fmaf(a1.z, hv[k + 6], s1); s1 = fmaf(a1.w, hv[k + 7], s1);
+    }
+    part[threadIdx.x] = s0 + s1;
+  }
+  __syncthreads();
+  if (q == 0) {
+    const float s = ((part[4 * o] + part[4 * o + 1]) + (part[4 * o + 2] + part[4 * o + 3])) + b2[o];
+    gate[(int64_t)b * C + o] = 1.f / (1.f + expf(-s));
+  }
+}
+
 __global__ void cab_apply_kernel(const float4 *__restrict__ sh, const float *__restrict__ gate,
                                  const float *__restrict__ deeper, int vec, int HW, int C, int64_t total4,
                                  float4 *__restrict__ out) {
@@ -970,6 +1075,30 @@ extern "C" int frtm_cab_gate(const float *sp, const float *dp, const float *w1, 
                "cab_gate: C must be a multiple of 32 (<= 256) and the weights 16-byte aligned");
   cab_gate_kernel<<<B, 4 * C, 7 * C * sizeof(float), (cudaStream_t)stream>>>(sp, dp, w1, b1, w2, b2, C, gate);
   FRTM_CHECK_LAUNCH("cab_gate");
+  return FRTM_OK;
+}
+
+extern "C" int64_t frtm_cab_gate_from_maps_workspace(int B, int HWs, int HWd, int C) {
+  return (int64_t)B * (cdiv(HWs, GAP_CHUNK) + cdiv(HWd > 0 ? HWd : 0, GAP_CHUNK)) * C * sizeof(float);
+}
+
+extern "C" int frtm_cab_gate_from_maps(const float *shallow, int HWs, int lds, const float *deeper, int HWd, int ldd,
+                                       const float *deep_pool, int B, int C, const float *w1, const float *b1, const float *w2,
+                                       const float *b2, float *gate, float *pool_out, float *workspace, int64_t workspace_bytes,
+                                       void *stream) {
+  FRTM_REQUIRE(shallow && (deeper || deep_pool) && w1 && b1 && w2 && b2 && gate && workspace, "cab_gate_from_maps: null pointer");
+  FRTM_REQUIRE(C == 64 && (reinterpret_cast<uintptr_t>(w1) & 15) == 0 && (reinterpret_cast<uintptr_t>(w2) & 15) == 0,
+               "cab_gate_from_maps: C must be 64 and the weights 16-byte aligned (else: global_avgpool + cab_gate)");
+  FRTM_REQUIRE(B > 0 && B <= 65535 && HWs > 0 && (!deeper || HWd > 0), "cab_gate_from_maps: bad sizes");
+  FRTM_REQUIRE(workspace_bytes >= frtm_cab_gate_from_maps_workspace(B, HWs, deeper ? HWd : 0, C),
+               "cab_gate_from_maps: workspace too small");
+  const int nca = cdiv(HWs, GAP_CHUNK), ncb = deeper ? cdiv(HWd, GAP_CHUNK) : 0;
+  float *parta = workspace, *partb = deeper ? workspace + (int64_t)B * nca * C : nullptr;
+  cudaStream_t st = (cudaStream_t)stream;
+  gap_stage1_pair_kernel<<<dim3(nca + ncb, B), 256, 0, st>>>(shallow, HWs, lds, nca, parta, deeper, HWd, ldd, ncb, partb, C);
+  FRTM_CHECK_LAUNCH("gap_stage1_pair");
+  cab_pool_gate64_kernel<<<B, 256, 0, st>>>(parta, HWs, nca, partb, HWd, ncb, deep_pool, w1, b1, w2, b2, gate, pool_out);
+  FRTM_CHECK_LAUNCH("cab_pool_gate64");
   return FRTM_OK;
 }
 

@@ -203,14 +203,13 @@ class SegNetwork(nn.Module):
             _, t, e = ops.conv65(t, e, W["tr2"])
             _, t, _ = ops.conv65(t, e, W["tr4"])
             t = self._rrb(t, W, "rrb1")
-            sp = ops.global_avgpool(t)
+            # the two global average pools and the gate: two launches (ops.cab with the pools left to it)
             if li == 0:
-                t = ops.cab(t, sp, hpool, hpool, W["cab_w1"], W["cab_b1"], W["cab_w2"], W["cab_b2"], out_split=True)
+                t = ops.cab(t, None, hpool, hpool, W["cab_w1"], W["cab_b1"], W["cab_w2"], W["cab_b2"], out_split=True)
             else:
-                dp = ops.global_avgpool(x)
                 # F.interpolate(deeper, (h, w)) of seg_network.py:39 happens inside the CAB kernel, which writes the split
                 # planes RRB2's first conv reads
-                t = ops.cab(t, sp, dp, x, W["cab_w1"], W["cab_b1"], W["cab_w2"], W["cab_b2"], out_split=True)
+                t = ops.cab(t, None, None, x, W["cab_w1"], W["cab_b1"], W["cab_w2"], W["cab_b2"], out_split=True)
             x = self._rrb(t, W, "rrb2")
         # conv2 is linear and so is the bicubic/bilinear chain in front of it: the 32 channels are contracted to the 9 tap
         # maps of conv2 at 240x428 in conv1's epilogue (the 32-channel tensor is never written); one kernel then does

@@ -188,13 +188,27 @@ def global_avgpool(x: torch.Tensor, channels: Optional[int] = None) -> torch.Ten
     return out
 
 
-def cab(shallow: torch.Tensor, shallow_pool: torch.Tensor, deep_pool: torch.Tensor, deeper: torch.Tensor, w1, b1, w2, b2,
-        out_split: bool = False):
+def cab(shallow: torch.Tensor, shallow_pool: Optional[torch.Tensor], deep_pool: Optional[torch.Tensor], deeper: torch.Tensor,
+        w1, b1, w2, b2, out_split: bool = False):
     """gate from pooled vectors, then shallow*gate + deeper (a map of the same shape, a lower-resolution map that is resized
-    bilinearly on the fly, or a (B,C) vector)."""
+    bilinearly on the fly, or a (B,C) vector).  ``shallow_pool`` / ``deep_pool`` = None: the pools are taken from the maps
+    themselves (``deeper`` must be a map when ``deep_pool`` is None) — at C = 64 in two launches together with the gate."""
     B, H, W, C = shallow.shape
     gate = torch.empty((B, C), device=shallow.device, dtype=torch.float32)
-    lib().cab_gate(ptr(shallow_pool), ptr(deep_pool), ptr(w1), ptr(b1), ptr(w2), ptr(b2), B, C, ptr(gate), stream())
+    if shallow_pool is None and C == 64 and shallow.is_contiguous() and (deep_pool is not None or (deeper.dim() == 4 and deeper.is_contiguous())):
+        from_map = deep_pool is None
+        HWd = deeper.shape[1] * deeper.shape[2] if from_map else 0
+        nbytes = lib().cab_gate_from_maps_workspace(B, H * W, HWd, C)
+        ws = torch.empty(nbytes // 4, device=shallow.device, dtype=torch.float32)
+        lib().cab_gate_from_maps(ptr(shallow), H * W, C, ptr(deeper) if from_map else None, HWd, C,
+                                 None if from_map else ptr(deep_pool), B, C, ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(gate), None,
+                                 ptr(ws), nbytes, stream())
+    else:
+        if shallow_pool is None:
+            shallow_pool = global_avgpool(shallow)
+        if deep_pool is None:
+            deep_pool = global_avgpool(deeper)
+        lib().cab_gate(ptr(shallow_pool), ptr(deep_pool), ptr(w1), ptr(b1), ptr(w2), ptr(b2), B, C, ptr(gate), stream())
     if deeper.dim() == 4 and tuple(deeper.shape[1:3]) != (H, W):
         # deeper level at its own resolution: resized bilinearly inside the kernel (no full-size intermediate); with
         # ``out_split`` the result leaves as the split planes the next tensor-core conv reads (no fp32 round trip)

@@ -155,6 +155,15 @@ int frtm_cab_gate(const float *shallow_pool, const float *deep_pool, const float
                   const float *b2, int B, int C, float *gate, void *stream);
 int frtm_cab_apply_nhwc(const float *shallow, const float *gate, const float *deeper, int deeper_is_vector, int B,
                         int HW, int C, float *out, void *stream);
+/* The gate straight from the maps (C = 64): both global average pools — of shallow (B,HWs,lds)[0,C) and of deeper
+ * (B,HWd,ldd)[0,C), or with deeper == NULL the pooled vector deep_pool (B,C) in its place — and the gate in two launches
+ * (stage 1 of both pools; one block per image that finishes them and runs the two small matrix products) instead of the
+ * five of frtm_global_avgpool_nhwc x2 + frtm_cab_gate, bit-identical to them.  pool_out (B,2C) = [sp | dp] or NULL. */
+int frtm_cab_gate_from_maps(const float *shallow, int HWs, int lds, const float *deeper, int HWd, int ldd,
+                            const float *deep_pool, int B, int C, const float *w1, const float *b1, const float *w2,
+                            const float *b2, float *gate, float *pool_out, float *workspace, int64_t workspace_bytes,
+                            void *stream);
+int64_t frtm_cab_gate_from_maps_workspace(int B, int HWs, int HWd, int C);
 /* The same with the deeper level still at its own resolution (B,Hd,Wd,C): the bilinear resize (align_corners=False) to
  * (H,W) is evaluated inside the kernel, with frtm_resize_bilinear_nhwc's arithmetic.  out (fp32 NHWC) and / or the split
  * planes y_hi, y_lo (B,H,W,C halves, frtm_split_f16's conversion) for the tensor-core conv that follows. */

@@ -139,6 +139,40 @@ def test_gap_and_cab():
     assert (_nchw(out_v.cpu()) - ref_v).abs().max() < 1e-5
 
 
+@pytest.mark.parametrize("hw,hwd", [((30, 54), (15, 27)), ((120, 214), (60, 107)), ((15, 27), None), ((7, 9), (4, 5))])
+def test_cab_gate_from_maps_is_bit_identical_to_the_separate_kernels(hw, hwd):
+    """frtm_cab_gate_from_maps (both pools + the gate in two launches) == global_avgpool x2 + cab_gate, bit for bit; with
+    ``hwd`` None the deeper pool is a given vector (the coarsest level of the refinement network)."""
+    ops = _ops()
+    from frtm_vos_b200._lib import lib, ptr, stream
+    g = torch.Generator().manual_seed(61)
+    B, C = 5, 64
+    x = torch.randn(B, hw[0], hw[1], C, generator=g).to(DEV)
+    w1, b1 = (torch.randn(64, 128, generator=g) / 11).to(DEV), torch.randn(64, generator=g).to(DEV)
+    w2, b2 = (torch.randn(64, 64, generator=g) / 8).to(DEV), torch.randn(64, generator=g).to(DEV)
+    sp = ops.global_avgpool(x)
+    if hwd is None:
+        deeper = torch.randn(B, C, generator=g).to(DEV)
+        dp = deeper
+    else:
+        deeper = torch.randn(B, hwd[0], hwd[1], C, generator=g).to(DEV)
+        dp = ops.global_avgpool(deeper)
+    gate_ref = torch.empty((B, C), device=DEV)
+    lib().cab_gate(ptr(sp), ptr(dp), ptr(w1), ptr(b1), ptr(w2), ptr(b2), B, C, ptr(gate_ref), stream())
+    HWd = 0 if hwd is None else hwd[0] * hwd[1]
+    nbytes = lib().cab_gate_from_maps_workspace(B, hw[0] * hw[1], HWd, C)
+    ws = torch.empty(nbytes // 4, device=DEV)
+    gate, pools = torch.empty((B, C), device=DEV), torch.empty((B, 2 * C), device=DEV)
+    lib().cab_gate_from_maps(ptr(x), hw[0] * hw[1], C, None if hwd is None else ptr(deeper), HWd, C, ptr(dp) if hwd is None else None,
+                             B, C, ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(gate), ptr(pools), ptr(ws), nbytes, stream())
+    assert torch.equal(pools[:, :C], sp) and torch.equal(pools[:, C:], dp)
+    assert torch.equal(gate, gate_ref)
+    # and through ops.cab with the pools left to it
+    a = ops.cab(x, None, None if hwd is not None else dp, deeper, w1, b1, w2, b2)
+    b = ops.cab(x, sp, dp, deeper, w1, b1, w2, b2)
+    assert torch.equal(a, b)
+
+
 def test_concat_helpers_and_layout():
     ops = _ops()
     g = torch.Generator().manual_seed(8)
