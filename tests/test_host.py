@@ -232,3 +232,21 @@ def test_planar_cut_and_inpaint_equals_the_interleaved_formula():
         assert cut.dtype == torch.uint8 and bg.dtype == torch.uint8 and cut.is_contiguous() and bg.is_contiguous()
         assert np.array_equal(cut.numpy(), cut_ref) and np.array_equal(bg.numpy(), bg_ref)
     assert torch.equal(im, seq[0][0])                              # the input frame is not modified in place
+
+
+def test_bench_clock_sampler_degrades_without_a_gpu():
+    """bench.ClockSampler (NVML poll thread, nvidia-smi child as the second choice) must not raise where neither can open a
+    device — the reference arm and the CPU checks run it on boxes without one — and says so in ``reasons``."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    s = bench.ClockSampler(0)
+    s.start()
+    out = s.stop()
+    assert set(out) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    if not torch.cuda.is_available():
+        assert out["sm_mhz"] is None
+    # the throttle-reason bits are NVML's (nvml.h: nvmlClocksThrottleReason*)
+    assert dict((n, b) for b, n in bench.ClockSampler.BITS) == dict(
+        hw_slowdown=0x8, hw_thermal_slowdown=0x40, sw_thermal_slowdown=0x20, sw_power_cap=0x4)
